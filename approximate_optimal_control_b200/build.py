@@ -1,0 +1,80 @@
+"""Builds libb200pmp.so (hand-written sm_100a CUDA + the C ABI of include/b200pmp.h) in-tree.
+
+    python -m approximate_optimal_control_b200.build [--force]
+
+nvcc cross-compiles without a GPU; the resulting .so sits next to this file so that it travels
+with the repo snapshot to the GPU box (it is git-ignored, not gpurun-ignored).
+"""
+from __future__ import annotations
+
+import concurrent.futures as cf
+import os
+import shutil
+import subprocess
+import sys
+
+_PKG = os.path.dirname(os.path.abspath(__file__))
+_CSRC = os.path.join(_PKG, "csrc")
+_ROOT = os.path.dirname(_PKG)
+LIB_PATH = os.path.join(_PKG, "libb200pmp.so")
+_OBJ_DIR = os.path.join(_PKG, "build")
+
+SOURCES = ["pmp_capi.cu", "pmp_eval.cu", "pmp_sys_flatquad.cu", "pmp_sys_orbits.cu", "pmp_sys_lqr.cu"]
+HEADERS = ["pmp_common.cuh", "pmp_systems.cuh", "pmp_tableau.cuh", "pmp_solve.cuh"]
+
+NVCC_FLAGS = [
+    "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
+    "--expt-relaxed-constexpr", "-Xcompiler", "-fPIC",
+    # IEEE division / sqrt, no flush-to-zero, FMA contraction on (the default): the state path
+    # must not silently lose precision; approximate ops are requested explicitly where wanted.
+    "--prec-div=true", "--prec-sqrt=true", "--ftz=false",
+]
+
+
+def _nvcc() -> str:
+    exe = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
+    if not os.path.exists(exe):
+        raise RuntimeError("nvcc not found: libb200pmp.so cannot be built")
+    return exe
+
+
+def _stale() -> bool:
+    if not os.path.exists(LIB_PATH):
+        return True
+    deps = [os.path.join(_CSRC, f) for f in SOURCES + HEADERS]
+    deps += [os.path.join(_ROOT, "include", "b200pmp.h"), os.path.abspath(__file__)]
+    return os.path.getmtime(LIB_PATH) < max(os.path.getmtime(d) for d in deps)
+
+
+def build(force: bool = False, verbose: bool = False) -> str:
+    if not force and not _stale():
+        return LIB_PATH
+    os.makedirs(_OBJ_DIR, exist_ok=True)
+    nvcc = _nvcc()
+    env = dict(os.environ)
+    # the image exports CC/CXX pointing at a gcc wrapper without its spec files; use the system one
+    host = "/usr/bin/g++" if os.path.exists("/usr/bin/g++") else "g++"
+
+    def compile_one(src):
+        obj = os.path.join(_OBJ_DIR, src.replace(".cu", ".o"))
+        cmd = [nvcc, *NVCC_FLAGS, "-ccbin", host, "-c", os.path.join(_CSRC, src), "-o", obj]
+        if verbose:
+            cmd.insert(1, "-Xptxas=-v")
+        r = subprocess.run(cmd, capture_output=True, text=True, env=env)
+        if r.returncode != 0:
+            raise RuntimeError(f"nvcc failed for {src}:\n{r.stdout}\n{r.stderr}")
+        if verbose:
+            sys.stderr.write(r.stderr)
+        return obj
+
+    with cf.ThreadPoolExecutor(max_workers=len(SOURCES)) as ex:
+        objs = list(ex.map(compile_one, SOURCES))
+    link = [nvcc, "-shared", "-ccbin", host, "-gencode", "arch=compute_100a,code=sm_100a", "-o", LIB_PATH, *objs]
+    r = subprocess.run(link, capture_output=True, text=True, env=env)
+    if r.returncode != 0:
+        raise RuntimeError(f"link failed:\n{r.stdout}\n{r.stderr}")
+    return LIB_PATH
+
+
+if __name__ == "__main__":
+    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))

@@ -1,0 +1,158 @@
+// pmp_capi.cu -- extern "C" surface of libb200pmp.so (declared in include/b200pmp.h).
+#include <cuda_runtime.h>
+
+#include <cstdio>
+#include <string>
+
+#include "../../include/b200pmp.h"
+
+namespace pmp {
+int solve_flatquad(const pmp_problem_t&, const pmp_opts_t&, long long, const void*, void*, const pmp_dense_t*,
+                   int32_t*, int32_t*, int32_t*, void*, cudaStream_t);
+int solve_orbits(const pmp_problem_t&, const pmp_opts_t&, long long, const void*, void*, const pmp_dense_t*,
+                 int32_t*, int32_t*, int32_t*, void*, cudaStream_t);
+int solve_lqr(const pmp_problem_t&, const pmp_opts_t&, long long, const void*, void*, const pmp_dense_t*,
+              int32_t*, int32_t*, int32_t*, void*, cudaStream_t);
+int eval_batch(int what, const pmp_problem_t& p, int dtype, long long n, const void* a, const void* b, void* out,
+               cudaStream_t st);
+int fma_peak(int dtype, int variant, int iters, void* scratch, double* flops_out, cudaStream_t st);
+}  // namespace pmp
+
+namespace {
+thread_local std::string g_err = "";
+
+int fail(int code, const std::string& msg) {
+    g_err = msg;
+    return code;
+}
+int cuda_fail(int e) {
+    return fail(PMP_ERR_CUDA, std::string("CUDA error: ") + cudaGetErrorString((cudaError_t)e));
+}
+
+int expected_nx(int sys) { return sys == PMP_SYS_FLATQUAD ? 6 : 2; }
+int expected_nu(int sys) { return sys == PMP_SYS_FLATQUAD ? 2 : 1; }
+
+int check_problem(const pmp_problem_t* p) {
+    if (!p) return fail(PMP_ERR_BAD_ARG, "problem is NULL");
+    if (p->system_id < 0 || p->system_id > PMP_SYS_LQR_STATEPENALTY)
+        return fail(PMP_ERR_UNSUPPORTED, "unknown system_id " + std::to_string(p->system_id) +
+                                             " (compiled systems: 0 flatquad, 1 orbits, 2 lqr_statepenalty)");
+    if (p->nx != expected_nx(p->system_id) || p->nu != expected_nu(p->system_id))
+        return fail(PMP_ERR_BAD_ARG, "nx/nu do not match system_id");
+    for (int i = 0; i < p->nu; i++)
+        if (!(p->u_lo[i] < p->u_hi[i])) return fail(PMP_ERR_BAD_ARG, "U_interval: need u_lo < u_hi");
+    return 0;
+}
+
+int check_opts(const pmp_opts_t* o) {
+    if (!o) return fail(PMP_ERR_BAD_ARG, "opts is NULL");
+    if (o->method < PMP_METHOD_RK4 || o->method > PMP_METHOD_DOPRI5) return fail(PMP_ERR_UNSUPPORTED, "unknown method");
+    if (o->dtype != PMP_F32 && o->dtype != PMP_F64) return fail(PMP_ERR_BAD_ARG, "dtype must be 0 (f32) or 1 (f64)");
+    if (o->indep != PMP_INDEP_TIME && o->indep != PMP_INDEP_VALUE) return fail(PMP_ERR_BAD_ARG, "bad indep");
+    if (o->max_steps < 1) return fail(PMP_ERR_BAD_ARG, "max_steps must be >= 1");
+    if (o->event != PMP_EVENT_NONE && o->event != PMP_EVENT_VALUE_GE) return fail(PMP_ERR_UNSUPPORTED, "unknown event");
+    if (o->adaptive && o->method == PMP_METHOD_RK4)
+        return fail(PMP_ERR_UNSUPPORTED, "RK4 has no embedded error estimate: adaptive must be 0");
+    if (!(o->dt0 != 0.0) || o->dt0 != o->dt0) return fail(PMP_ERR_BAD_ARG, "dt0 must be non-zero");
+    if (o->indep == PMP_INDEP_TIME) {
+        if (!(o->t0 != o->t1)) return fail(PMP_ERR_BAD_ARG, "t0 == t1");
+        if ((o->t1 - o->t0) * o->dt0 < 0) return fail(PMP_ERR_BAD_ARG, "dt0 must point from t0 to t1");
+    } else if (!(o->dt0 > 0)) {
+        return fail(PMP_ERR_BAD_ARG, "value-parameterised solve needs dt0 > 0");
+    }
+    if (o->adaptive) {
+        if (!(o->rtol >= 0) || !(o->atol >= 0) || !(o->rtol + o->atol > 0)) return fail(PMP_ERR_BAD_ARG, "bad rtol/atol");
+        if (!(o->safety > 0) || !(o->factormin > 0) || !(o->factormax >= 1)) return fail(PMP_ERR_BAD_ARG, "bad controller factors");
+    }
+    return 0;
+}
+}  // namespace
+
+extern "C" {
+
+int pmp_abi_version(void) { return PMP_ABI_VERSION; }
+const char* pmp_last_error(void) { return g_err.c_str(); }
+
+int pmp_state_rows(const pmp_problem_t* p) {
+    if (int e = check_problem(p)) return e;
+    return 2 * p->nx + 2;
+}
+
+int pmp_device_count(void) {
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e == cudaErrorNoDevice || e == cudaErrorInsufficientDriver) { cudaGetLastError(); return 0; }
+    if (e != cudaSuccess) return cuda_fail((int)e);
+    return n;
+}
+
+int64_t pmp_solve_workspace_bytes(const pmp_problem_t* p, const pmp_opts_t* o, int64_t n) {
+    if (int e = check_problem(p)) return e;
+    if (int e = check_opts(o)) return e;
+    if (n < 0) return fail(PMP_ERR_BAD_ARG, "n < 0");
+    const int64_t nd = 2 * p->nx + 1;
+    return 256 + nd * n * (o->dtype == PMP_F32 ? 4 : 8);
+}
+
+int pmp_solve_launch_count(const pmp_problem_t* p, const pmp_opts_t* o, int64_t n) {
+    if (int e = check_problem(p)) return e;
+    if (int e = check_opts(o)) return e;
+    return n > 0 ? 2 : 0;  // prep (k1 / counter reset) + integrator
+}
+
+int pmp_solve_batch_cuda(const pmp_problem_t* p, const pmp_opts_t* o, int64_t n, const void* y_f, void* y_end,
+                         const pmp_dense_t* dense, int32_t* n_accepted, int32_t* n_steps, int32_t* result,
+                         void* workspace, int64_t workspace_bytes, void* cuda_stream) {
+    if (int e = check_problem(p)) return e;
+    if (int e = check_opts(o)) return e;
+    if (n < 0) return fail(PMP_ERR_BAD_ARG, "n < 0");
+    if (n == 0) return PMP_OK;
+    if (!y_f || !y_end) return fail(PMP_ERR_BAD_ARG, "y_f / y_end is NULL");
+    if (o->save_dense && !dense) return fail(PMP_ERR_BAD_ARG, "save_dense set but dense is NULL");
+    if (!workspace || workspace_bytes < pmp_solve_workspace_bytes(p, o, n))
+        return fail(PMP_ERR_BAD_ARG, "workspace is NULL or smaller than pmp_solve_workspace_bytes()");
+    if (((uintptr_t)workspace & 255u) != 0) return fail(PMP_ERR_BAD_ARG, "workspace must be 256-byte aligned");
+    int ndev = pmp_device_count();
+    if (ndev <= 0) return fail(PMP_ERR_NO_DEVICE, "no CUDA device: libb200pmp has no CPU fallback");
+    cudaStream_t st = (cudaStream_t)cuda_stream;
+    int rc = -1000;
+    switch (p->system_id) {
+        case PMP_SYS_FLATQUAD: rc = pmp::solve_flatquad(*p, *o, n, y_f, y_end, dense, n_accepted, n_steps, result, workspace, st); break;
+        case PMP_SYS_ORBITS: rc = pmp::solve_orbits(*p, *o, n, y_f, y_end, dense, n_accepted, n_steps, result, workspace, st); break;
+        case PMP_SYS_LQR_STATEPENALTY: rc = pmp::solve_lqr(*p, *o, n, y_f, y_end, dense, n_accepted, n_steps, result, workspace, st); break;
+    }
+    if (rc == -1000) return fail(PMP_ERR_UNSUPPORTED, "no kernel for this (system, dtype, method) combination");
+    if (rc != 0) return cuda_fail(rc);
+    return PMP_OK;
+}
+
+int pmp_rhs_batch_cuda(const pmp_problem_t* p, int32_t dtype, int64_t n, const void* y, void* dy, void* cuda_stream) {
+    if (int e = check_problem(p)) return e;
+    if (dtype != PMP_F32 && dtype != PMP_F64) return fail(PMP_ERR_BAD_ARG, "dtype must be 0 (f32) or 1 (f64)");
+    if (n < 0 || (n > 0 && (!y || !dy))) return fail(PMP_ERR_BAD_ARG, "bad n or NULL buffers");
+    if (n == 0) return PMP_OK;
+    if (pmp_device_count() <= 0) return fail(PMP_ERR_NO_DEVICE, "no CUDA device: libb200pmp has no CPU fallback");
+    int rc = pmp::eval_batch(0, *p, dtype, n, y, nullptr, dy, (cudaStream_t)cuda_stream);
+    return rc ? cuda_fail(rc) : PMP_OK;
+}
+
+int pmp_ustar_batch_cuda(const pmp_problem_t* p, int32_t dtype, int64_t n, const void* x, const void* lam, void* u,
+                         void* cuda_stream) {
+    if (int e = check_problem(p)) return e;
+    if (dtype != PMP_F32 && dtype != PMP_F64) return fail(PMP_ERR_BAD_ARG, "dtype must be 0 (f32) or 1 (f64)");
+    if (n < 0 || (n > 0 && (!x || !lam || !u))) return fail(PMP_ERR_BAD_ARG, "bad n or NULL buffers");
+    if (n == 0) return PMP_OK;
+    if (pmp_device_count() <= 0) return fail(PMP_ERR_NO_DEVICE, "no CUDA device: libb200pmp has no CPU fallback");
+    int rc = pmp::eval_batch(1, *p, dtype, n, x, lam, u, (cudaStream_t)cuda_stream);
+    return rc ? cuda_fail(rc) : PMP_OK;
+}
+
+int pmp_fma_peak_cuda(int32_t dtype, int32_t variant, int32_t iters, void* scratch, double* flops_out, void* cuda_stream) {
+    if (dtype != PMP_F32 && dtype != PMP_F64) return fail(PMP_ERR_BAD_ARG, "dtype must be 0 (f32) or 1 (f64)");
+    if (variant < 0 || variant > 1 || iters < 1 || !scratch) return fail(PMP_ERR_BAD_ARG, "bad variant / iters / scratch");
+    if (pmp_device_count() <= 0) return fail(PMP_ERR_NO_DEVICE, "no CUDA device");
+    int rc = pmp::fma_peak(dtype, variant, iters, scratch, flops_out, (cudaStream_t)cuda_stream);
+    return rc ? cuda_fail(rc) : PMP_OK;
+}
+
+}  // extern "C"

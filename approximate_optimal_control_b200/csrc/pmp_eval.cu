@@ -1,0 +1,108 @@
+// pmp_eval.cu -- batched pointwise evaluations of the plug-in dynamics and the FMA-peak probe.
+//   rhs_batch   <- jax.vmap(f_extended)             pontryagin_utils.py:418-482
+//   ustar_batch <- jax.vmap(u_star_2d / u_star_new) pontryagin_utils.py:11-216, :532-562
+//                  (batched over all saved nodes at levelsets.py:604-628)
+#include "pmp_common.cuh"
+#include "pmp_systems.cuh"
+
+namespace pmp {
+
+template <class Sys, class R>
+__global__ void __launch_bounds__(256) rhs_kernel(const typename Sys::Consts sc, const R* __restrict__ y,
+                                                  R* __restrict__ dy, long long n) {
+    constexpr int NX = Sys::NX;
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    R x[NX], lam[NX], xd[NX], ld[NX], vd;
+#pragma unroll
+    for (int q = 0; q < NX; q++) { x[q] = y[q * n + i]; lam[q] = y[(NX + 2 + q) * n + i]; }
+    Sys::template rhs<false>(sc, x, lam, xd, vd, ld);
+#pragma unroll
+    for (int q = 0; q < NX; q++) { dy[q * n + i] = xd[q]; dy[(NX + 2 + q) * n + i] = ld[q]; }
+    dy[NX * n + i] = R(1);  // state_dot['t'] = 1.   (pontryagin_utils.py:456)
+    dy[(NX + 1) * n + i] = vd;
+}
+
+template <class Sys, class R>
+__global__ void __launch_bounds__(256) ustar_kernel(const typename Sys::Consts sc, const R* __restrict__ x_,
+                                                    const R* __restrict__ lam_, R* __restrict__ u_, long long n) {
+    constexpr int NX = Sys::NX, NU = Sys::NU;
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    R x[NX], lam[NX], u[NU];
+#pragma unroll
+    for (int q = 0; q < NX; q++) { x[q] = x_[q * n + i]; lam[q] = lam_[q * n + i]; }
+    Sys::ustar(sc, x, lam, u);
+#pragma unroll
+    for (int q = 0; q < NU; q++) u_[q * n + i] = u[q];
+}
+
+template <template <class> class SysT>
+int eval_dispatch(int what, const pmp_problem_t& p, int dtype, long long n, const void* a, const void* b, void* out,
+                  cudaStream_t st) {
+    if (n == 0) return 0;
+    const unsigned grid = (unsigned)((n + 255) / 256);
+    if (dtype == PMP_F32) {
+        using S = SysT<float>;
+        if (what == 0) rhs_kernel<S, float><<<grid, 256, 0, st>>>(S::make(p), (const float*)a, (float*)out, n);
+        else ustar_kernel<S, float><<<grid, 256, 0, st>>>(S::make(p), (const float*)a, (const float*)b, (float*)out, n);
+    } else {
+        using S = SysT<double>;
+        if (what == 0) rhs_kernel<S, double><<<grid, 256, 0, st>>>(S::make(p), (const double*)a, (double*)out, n);
+        else ustar_kernel<S, double><<<grid, 256, 0, st>>>(S::make(p), (const double*)a, (const double*)b, (double*)out, n);
+    }
+    return (int)cudaGetLastError();
+}
+
+int eval_batch(int what, const pmp_problem_t& p, int dtype, long long n, const void* a, const void* b, void* out,
+               cudaStream_t st) {
+    switch (p.system_id) {
+        case PMP_SYS_FLATQUAD: return eval_dispatch<Flatquad>(what, p, dtype, n, a, b, out, st);
+        case PMP_SYS_ORBITS: return eval_dispatch<Orbits>(what, p, dtype, n, a, b, out, st);
+        case PMP_SYS_LQR_STATEPENALTY: return eval_dispatch<LqrStatePenalty>(what, p, dtype, n, a, b, out, st);
+    }
+    return -1000;
+}
+
+// ---- FMA peak probe: 16 independent dependent-FMA chains per thread, all in registers ------------
+constexpr int kPeakChains = 16, kPeakBlock = 256, kPeakBlocksPerSM = 4;
+
+template <class R, int VARIANT>
+__global__ void __launch_bounds__(kPeakBlock) fma_peak_kernel(int iters, R b, R c, R* sink) {
+    R a[kPeakChains];
+#pragma unroll
+    for (int j = 0; j < kPeakChains; j++) a[j] = R(threadIdx.x + j) * R(1e-3);
+    for (int it = 0; it < iters; it++) {
+#pragma unroll
+        for (int rep = 0; rep < 8; rep++) {
+#pragma unroll
+            for (int j = 0; j < kPeakChains; j++) {
+                if (VARIANT == 0) a[j] = Math<R>::fma(a[j], b, c);
+                else a[j] = Math<R>::fma(a[j], R(0.999999), R(1e-7));
+            }
+        }
+    }
+    R s = R(0);
+#pragma unroll
+    for (int j = 0; j < kPeakChains; j++) s += a[j];
+    if (s == R(-12345.678)) *sink = s;  // never true; keeps the chains alive
+}
+
+int fma_peak(int dtype, int variant, int iters, void* scratch, double* flops_out, cudaStream_t st) {
+    int dev = 0, sms = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) return (int)e;
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    const int grid = sms * kPeakBlocksPerSM;
+    if (flops_out) *flops_out = 2.0 * kPeakChains * 8.0 * (double)iters * (double)grid * kPeakBlock;
+    if (dtype == PMP_F32) {
+        if (variant == 0) fma_peak_kernel<float, 0><<<grid, kPeakBlock, 0, st>>>(iters, 0.999999f, 1e-7f, (float*)scratch);
+        else fma_peak_kernel<float, 1><<<grid, kPeakBlock, 0, st>>>(iters, 0.f, 0.f, (float*)scratch);
+    } else {
+        if (variant == 0) fma_peak_kernel<double, 0><<<grid, kPeakBlock, 0, st>>>(iters, 0.999999, 1e-7, (double*)scratch);
+        else fma_peak_kernel<double, 1><<<grid, kPeakBlock, 0, st>>>(iters, 0., 0., (double*)scratch);
+    }
+    return (int)cudaGetLastError();
+}
+
+}  // namespace pmp

@@ -1,0 +1,419 @@
+// pmp_solve.cuh -- the batched PMP backward-shooting integrator (sm_100a).
+//
+// Replaces jax.vmap(solve_backward) (pontryagin_utils.py:488-527 as called at levelsets.py:601,1254):
+// diffrax.diffeqsolve(ODETerm(f_extended), Tsit5(), t0=0, t1=-T, dt0=-0.1, y0, PIDController(rtol,
+// atol, dtmin, dtmax), SaveAt(steps=True, t0=True), max_steps, throw=False), one solve per
+// trajectory, with the diffrax 0.4.1 step-control semantics restated in DESIGN.md.
+//
+// Design (one thread per trajectory, everything in registers):
+//   * y (2nx+1 dynamic scalars), the stage derivatives k1..kS and the stage state live in registers;
+//     tableau coefficients are compile-time immediates (pmp_tableau.cuh), system constants sit in
+//     the kernel parameter bank.  No shared memory, no local memory for the fp32 flatquad kernel.
+//   * Adaptive step control is per lane: every lane of a warp executes one step ATTEMPT per loop
+//     iteration (accept/reject are selects, not branches), so the only divergence is trajectories
+//     finishing at different attempt counts.
+//   * Lane refill: a persistent grid pulls trajectory indices from a global counter in warp-sized
+//     chunks.  After every attempt the warp ballots the lanes whose trajectory finished (reached
+//     t1, event, max_steps, NaN), retires them (endpoint + stats written) and hands each a new
+//     trajectory, so all 32 lanes stay busy until the queue is empty.  The first-stage derivative
+//     k1 = F(y_f) of a fresh trajectory (FSAL) is NOT computed in the divergent refill branch: a
+//     coalesced prep kernel evaluates it for the whole batch up front (1 RHS per trajectory,
+//     ~0.7 % of the work) and the refill just loads it.
+//   * Time reversal as in diffrax: integrate tau = dir*t from T0 to T1 with positive steps; k holds
+//     the forward-time field and the signed step h = dir*dt multiplies it.
+//   * The reference's 't' leaf (dt/dt = 1) is not integrated numerically: t = t_f + dir*(tau - T0).
+//     It still counts as one leaf of the RMS error norm (its own error is ~1e-9 of the tolerance).
+#pragma once
+#include "pmp_common.cuh"
+#include "pmp_systems.cuh"
+#include "pmp_tableau.cuh"
+
+namespace pmp {
+
+constexpr int kBlock = 128;  // threads per CTA
+constexpr int kChunk = 64;   // trajectory indices claimed per atomicAdd
+
+// ---- forward-time field on the integrator's vector layout y = (x[NX], lam[NX], aux) -------------
+// time mode : aux = v,  k = (f, -dH/dx, -l)
+// value mode: aux = t,  k = (f, -dH/dx, 1) / (dv/dt)      (experiment_orbits.py:109-111)
+template <class Sys, class R, bool VALUE, bool WARP_VOTE>
+__device__ __forceinline__ void field(const typename Sys::Consts& sc, const R* y, R* k) {
+    constexpr int NX = Sys::NX;
+    R vd;
+    Sys::template rhs<WARP_VOTE>(sc, y, y + NX, k, vd, k + NX);
+    if (VALUE) {
+        const R iv = Math<R>::div(R(1), vd);
+#pragma unroll
+        for (int q = 0; q < 2 * NX; q++) k[q] *= iv;
+        k[2 * NX] = iv;
+    } else {
+        k[2 * NX] = vd;
+    }
+}
+
+// rows of the public [NS][n] layout: x -> 0.., t -> NX, v -> NX+1, vx -> NX+2..
+template <class R, int NX, bool VALUE>
+__device__ __forceinline__ void load_state(const R* __restrict__ y_f, long long n, long long i, R* y, R& clock0,
+                                           R& aux_fixed) {
+#pragma unroll
+    for (int q = 0; q < NX; q++) y[q] = __ldg(y_f + q * n + i);
+#pragma unroll
+    for (int q = 0; q < NX; q++) y[NX + q] = __ldg(y_f + (NX + 2 + q) * n + i);
+    const R t = __ldg(y_f + NX * n + i), v = __ldg(y_f + (NX + 1) * n + i);
+    if (VALUE) { y[2 * NX] = t; clock0 = v; aux_fixed = R(0); }
+    else { y[2 * NX] = v; clock0 = R(0); aux_fixed = t; }
+}
+
+// ---- prep kernel: k1 = field(y_f) for every trajectory (coalesced), and reset of the work counter
+template <class Sys, class R, bool VALUE>
+__global__ void __launch_bounds__(kBlock) prep_kernel(const typename Sys::Consts sc, const R* __restrict__ y_f,
+                                                      R* __restrict__ k1, long long n,
+                                                      unsigned long long* counter) {
+    constexpr int NX = Sys::NX, ND = 2 * NX + 1;
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i == 0) *counter = 0ull;
+    if (i >= n) return;
+    R y[ND], k[ND], c0, af;
+    load_state<R, NX, VALUE>(y_f, n, i, y, c0, af);
+    field<Sys, R, VALUE, false>(sc, y, k);
+#pragma unroll
+    for (int q = 0; q < ND; q++) k1[q * n + i] = k[q];
+}
+
+static __global__ void reset_counter_kernel(unsigned long long* counter) { *counter = 0ull; }
+
+// ---- the integrator -----------------------------------------------------------------------------
+template <class Sys, class R, int METHOD, bool DENSE, bool VALUE, int MINB>
+__global__ void __launch_bounds__(kBlock, MINB)
+solve_kernel(const typename Sys::Consts sc, const SolveOpts<R> o, const SolveIO<R> io) {
+    using M = Math<R>;
+    using TB = Tab<METHOD>;
+    constexpr int NX = Sys::NX, ND = 2 * NX + 1, NS = 2 * NX + 2, S = TB::S;
+    constexpr int AUX = 2 * NX;
+    constexpr unsigned FULL = 0xffffffffu;
+    const int lane = threadIdx.x & 31;
+    const long long n = io.n;
+    const int S1 = o.max_steps + 1;
+    // leaves of the RMS norm: x, t, v, vx in time mode (NS); x, lambda, t in value mode (NS-1)
+    const R inv_nleaf = VALUE ? R(1.0 / (NS - 1)) : R(1.0 / NS);
+
+    // per-lane trajectory state
+    R y[ND], k[S][ND];
+    R tprev = R(0), tnext = R(0), clock0 = R(0), aux_fixed = R(0);
+    long long idx = -1;
+    int nsteps = 0, nacc = 0, result = 0;
+    bool at_dtmin = false, has_work = false, finished = false;
+#pragma unroll
+    for (int q = 0; q < ND; q++) {
+        y[q] = R(0);
+#pragma unroll
+        for (int j = 0; j < S; j++) k[j][q] = R(0);
+    }
+    // warp-local slice of the work queue (uniform across the warp)
+    long long w_next = 0, w_end = 0;
+    bool exhausted = false;
+
+    while (true) {
+        // =============================== retire + refill =========================================
+        const bool fin = has_work && finished;
+        unsigned want = __ballot_sync(FULL, fin || !has_work);
+        if (want) {
+            if (fin) {
+                // endpoint = last accepted state (== ys[num_accepted_steps], levelsets.py:1215)
+                const R clock = tprev * o.dir;  // t (time mode) or v (value mode)
+                R* ye = io.y_end;
+#pragma unroll
+                for (int q = 0; q < NX; q++) ye[q * n + idx] = y[q];
+#pragma unroll
+                for (int q = 0; q < NX; q++) ye[(NX + 2 + q) * n + idx] = y[NX + q];
+                if (VALUE) { ye[NX * n + idx] = y[AUX]; ye[(NX + 1) * n + idx] = clock; }
+                else { ye[NX * n + idx] = aux_fixed + (clock - clock0); ye[(NX + 1) * n + idx] = y[AUX]; }
+                if (io.n_accepted) io.n_accepted[idx] = nacc;
+                if (io.n_steps) io.n_steps[idx] = nsteps;
+                if (io.result) io.result[idx] = result;
+                has_work = false;
+            }
+            if (DENSE) {
+                // pad the unused slots of every retiring trajectory with +inf (ts: dir*inf), the warp
+                // writing each tail cooperatively so that the stores coalesce.
+                unsigned rm = __ballot_sync(FULL, fin);
+                while (rm) {
+                    const int src = __ffs(rm) - 1;
+                    rm &= rm - 1;
+                    const long long ti = __shfl_sync(FULL, idx, src);
+                    const int first = __shfl_sync(FULL, nacc, src) + 1;
+                    const R inf = M::inf();
+                    const int tail = S1 - first;
+                    if (io.dense.ts) { R* p = io.dense.ts + ti * S1 + first; for (int e = lane; e < tail; e += 32) p[e] = inf * o.dir; }
+                    if (io.dense.t) { R* p = io.dense.t + ti * S1 + first; for (int e = lane; e < tail; e += 32) p[e] = inf; }
+                    if (io.dense.v) { R* p = io.dense.v + ti * S1 + first; for (int e = lane; e < tail; e += 32) p[e] = inf; }
+                    if (io.dense.x) { R* p = io.dense.x + (ti * S1 + first) * NX; for (int e = lane; e < tail * NX; e += 32) p[e] = inf; }
+                    if (io.dense.vx) { R* p = io.dense.vx + (ti * S1 + first) * NX; for (int e = lane; e < tail * NX; e += 32) p[e] = inf; }
+                }
+            }
+            // hand out new trajectories to the lanes in `want`, in rank order
+            while (want && !exhausted) {
+                if (w_next >= w_end) {
+                    unsigned long long base = 0;
+                    if (lane == 0) base = atomicAdd(io.counter, (unsigned long long)kChunk);
+                    base = __shfl_sync(FULL, base, 0);
+                    w_next = (long long)base;
+                    w_end = w_next + kChunk < n ? w_next + kChunk : n;
+                    if (w_next >= n) { exhausted = true; break; }
+                }
+                const int avail = (int)(w_end - w_next);
+                const bool mine = (want >> lane) & 1u;
+                const int rank = __popc(want & ((1u << lane) - 1u));
+                const bool take = mine && rank < avail;
+                if (take) {
+                    idx = w_next + rank;
+                    load_state<R, NX, VALUE>(io.y_f, n, idx, y, clock0, aux_fixed);
+                    if (TB::FSAL) {
+#pragma unroll
+                        for (int q = 0; q < ND; q++) k[0][q] = __ldg(io.k1 + q * n + idx);
+                    }
+                    // diffrax: t0, t1, dt0 are multiplied by the direction; tnext = min(t0+dt0, t1)
+                    const R T0 = VALUE ? clock0 * o.dir : o.T0;
+                    clock0 = T0 * o.dir;  // keep the un-normalised start for the t output
+                    tprev = T0;
+                    tnext = M::min(T0 + o.dt0, o.T1);
+                    nsteps = 0; nacc = 0; result = 0; at_dtmin = false;
+                    has_work = true;
+                    bool bad = false;
+#pragma unroll
+                    for (int q = 0; q < ND; q++) bad = bad || (y[q] != y[q]);
+                    // NaN terminal state (levelsets.py:1233): retire at once with result 4
+                    finished = bad || !(tprev < o.T1);
+                    if (bad) result = PMP_RESULT_NAN;
+                    if (DENSE) {  // slot 0 = the terminal state (SaveAt(t0=True))
+                        const long long s0 = idx * S1;
+                        if (io.dense.ts) io.dense.ts[s0] = tprev * o.dir;
+                        if (io.dense.t) io.dense.t[s0] = VALUE ? y[AUX] : aux_fixed;
+                        if (io.dense.v) io.dense.v[s0] = VALUE ? tprev * o.dir : y[AUX];
+#pragma unroll
+                        for (int q = 0; q < NX; q++) {
+                            if (io.dense.x) io.dense.x[s0 * NX + q] = y[q];
+                            if (io.dense.vx) io.dense.vx[s0 * NX + q] = y[NX + q];
+                        }
+                    }
+                }
+                const unsigned took = __ballot_sync(FULL, take);
+                want &= ~took;
+                w_next += __popc(took);
+            }
+        }
+        if (!__any_sync(FULL, has_work)) break;
+        const bool live = has_work && !finished;
+
+        // =============================== one step attempt ========================================
+        const R dt = tnext - tprev;
+        const R h = dt * o.dir;
+        if (!TB::FSAL) field<Sys, R, VALUE, true>(sc, y, k[0]);
+        R y1[ND];
+#pragma unroll
+        for (int i = 1; i < S; i++) {
+            R ys[ND];
+            const bool last_fsal = TB::FSAL && i == S - 1;
+#pragma unroll
+            for (int q = 0; q < ND; q++) {
+                // the field does not depend on the aux scalar: skip it for intermediate stages
+                if (q == AUX && !last_fsal) { ys[q] = y[q]; continue; }
+                R acc = R(TB::a(i, 0)) * k[0][q];
+#pragma unroll
+                for (int j = 1; j < i; j++)
+                    if (TB::a(i, j) != 0.0) acc = M::fma(R(TB::a(i, j)), k[j][q], acc);
+                ys[q] = M::fma(h, acc, y[q]);
+            }
+            field<Sys, R, VALUE, true>(sc, ys, k[i]);
+            if (last_fsal) {
+#pragma unroll
+                for (int q = 0; q < ND; q++) y1[q] = ys[q];
+            }
+        }
+        if (!TB::FSAL) {
+#pragma unroll
+            for (int q = 0; q < ND; q++) {
+                R acc = R(TB::b(0)) * k[0][q];
+#pragma unroll
+                for (int j = 1; j < S; j++)
+                    if (TB::b(j) != 0.0) acc = M::fma(R(TB::b(j)), k[j][q], acc);
+                y1[q] = M::fma(h, acc, y[q]);
+            }
+        }
+
+        // ---- error estimate + I-controller (diffrax PIDController, pcoeff=dcoeff=0) --------------
+        bool keep = true;
+        R next_t0, next_t1;
+        if (TB::EMBEDDED && o.adaptive) {
+            R sumsq = R(0);
+#pragma unroll
+            for (int q = 0; q < ND; q++) {
+                R acc = R(TB::berr(0)) * k[0][q];
+#pragma unroll
+                for (int j = 1; j < S; j++)
+                    if (TB::berr(j) != 0.0) acc = M::fma(R(TB::berr(j)), k[j][q], acc);
+                R e = h * acc;
+                e = (e != e) ? M::inf() : e;  // integrate.py: NaN error -> inf (=> reject, shrink)
+                // scale = atol + rtol*max(|y0|,|y1|); fmax drops a NaN y1 (diffrax substitutes y0)
+                const R scale = M::fma(o.rtol, M::max(M::abs(y[q]), M::abs(y1[q])), o.atol);
+                const R ratio = M::div(e, scale);
+                sumsq = M::fma(ratio, ratio, sumsq);
+            }
+            const R msq = sumsq * inv_nleaf;  // scaled_error^2 (rms_norm over all leaves)
+            keep = (msq < R(1)) || at_dtmin;
+            // factor = clip(safety * scaled_error^(-1/order), keep ? 1 : factormin, factormax)
+            R factor = o.safety * M::pow_neg_inv(msq, R(0.5) * o.inv_order);
+            factor = M::min(M::max(factor, keep ? R(1) : o.factormin), o.factormax);
+            R dtn = dt * factor;
+            if (o.use_dtmax) dtn = M::min(dtn, o.dtmax);
+            bool dt_min_hit = false;
+            if (o.use_dtmin) {
+                dt_min_hit = dtn < o.dtmin;
+                at_dtmin = dtn <= o.dtmin;
+                dtn = M::max(dtn, o.dtmin);
+            } else {
+                at_dtmin = false;
+            }
+            if (live && !o.force_dtmin && dt_min_hit) result = PMP_RESULT_DT_MIN;
+            next_t0 = keep ? tnext : tprev;
+            next_t1 = next_t0 + dtn;
+        } else {  // diffrax ConstantStepSize: next interval as long as the last one
+            next_t0 = tnext;
+            next_t1 = tnext + dt;
+        }
+        if (live) {
+            // integrate.py: tprev = min(tprev, t1); tnext = _clip_to_end(tprev, tnext, t1, keep)
+            tprev = M::min(next_t0, o.T1);
+            if (next_t1 > o.T1 - M::clip_tol()) next_t1 = keep ? o.T1 : M::fma(R(0.5), o.T1 - tprev, tprev);
+            tnext = next_t1;
+            nsteps += 1;
+            bool nan_state = false;
+            if (keep) {
+                nacc += 1;
+                bool bad = false;
+#pragma unroll
+                for (int q = 0; q < ND; q++) {
+                    y[q] = y1[q];
+                    bad = bad || (y1[q] != y1[q]);
+                    if (TB::FSAL) k[0][q] = k[S - 1][q];
+                }
+                if (DENSE && nacc < S1) {
+                    const long long s = idx * S1 + nacc;
+                    const R clock = tprev * o.dir;
+                    if (io.dense.ts) io.dense.ts[s] = clock;
+                    if (io.dense.t) io.dense.t[s] = VALUE ? y[AUX] : aux_fixed + (clock - clock0);
+                    if (io.dense.v) io.dense.v[s] = VALUE ? clock : y[AUX];
+#pragma unroll
+                    for (int q = 0; q < NX; q++) {
+                        if (io.dense.x) io.dense.x[s * NX + q] = y[q];
+                        if (io.dense.vx) io.dense.vx[s * NX + q] = y[NX + q];
+                    }
+                }
+                nan_state = bad;
+            }
+            // DiscreteTerminatingEvent, evaluated on the post-step state after every attempt
+            if (!VALUE && result == 0 && o.event == PMP_EVENT_VALUE_GE && y[AUX] >= o.event_level)
+                result = PMP_RESULT_EVENT;
+            if (result == 0 && nan_state) result = PMP_RESULT_NAN;  // diffrax would idle to max_steps
+            const bool more = tprev < o.T1;
+            if (result == 0 && more && nsteps >= o.max_steps) result = PMP_RESULT_MAX_STEPS;
+            finished = !more || result != 0;
+        }
+    }
+}
+
+// ---- host-side launcher for one system ----------------------------------------------------------
+template <class R> inline SolveOpts<R> make_solve_opts(const pmp_opts_t& o, int order) {
+    SolveOpts<R> s;
+    const double dir = (o.indep == PMP_INDEP_VALUE) ? 1.0 : ((o.t0 < o.t1) ? 1.0 : -1.0);
+    s.dir = R(dir);
+    s.T0 = R(o.t0 * dir);
+    s.T1 = R(o.t1 * dir);
+    s.dt0 = R(o.dt0 * dir);
+    s.rtol = R(o.rtol); s.atol = R(o.atol);
+    s.dtmin = R(o.dtmin); s.dtmax = R(o.dtmax);
+    s.use_dtmin = o.dtmin > 0; s.use_dtmax = o.dtmax > 0;
+    s.safety = R(o.safety); s.factormin = R(o.factormin); s.factormax = R(o.factormax);
+    s.inv_order = R(1.0 / order);
+    s.event_level = R(o.event_level);
+    s.max_steps = o.max_steps; s.adaptive = o.adaptive; s.force_dtmin = o.force_dtmin; s.event = o.event;
+    return s;
+}
+
+struct LaunchPlan {
+    int grid_solve, grid_prep, sm_count, blocks_per_sm;
+};
+
+// workspace layout: [counter: 256 B][k1: ND*n reals]
+inline size_t workspace_bytes_for(int nd, long long n, size_t real_size) {
+    return 256 + (size_t)nd * (size_t)n * real_size;
+}
+
+template <class Sys, class R, int METHOD, bool DENSE, bool VALUE, int MINB>
+int launch_one(const pmp_problem_t& p, const pmp_opts_t& o, long long n, const void* y_f, void* y_end,
+               const pmp_dense_t* dense, int32_t* n_acc, int32_t* n_steps, int32_t* result,
+               void* workspace, cudaStream_t st) {
+    using TB = Tab<METHOD>;
+    constexpr int ND = 2 * Sys::NX + 1;
+    auto kern = solve_kernel<Sys, R, METHOD, DENSE, VALUE, MINB>;
+    int dev = 0, sms = 0, occ = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) return (int)e;
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, kBlock, 0);
+    if (e != cudaSuccess) return (int)e;
+    if (occ < 1) occ = 1;
+    long long need = (n + kBlock - 1) / kBlock;
+    long long cap = (long long)sms * occ;
+    const int grid = (int)(need < cap ? need : cap);
+
+    const typename Sys::Consts sc = Sys::make(p);
+    SolveIO<R> io;
+    io.y_f = (const R*)y_f;
+    io.counter = (unsigned long long*)workspace;
+    io.k1 = (const R*)((char*)workspace + 256);
+    io.y_end = (R*)y_end;
+    io.n_accepted = n_acc; io.n_steps = n_steps; io.result = result;
+    io.n = n;
+    io.dense = DensePtrs<R>{nullptr, nullptr, nullptr, nullptr, nullptr};
+    if (DENSE && dense)
+        io.dense = DensePtrs<R>{(R*)dense->ts, (R*)dense->x, (R*)dense->t, (R*)dense->v, (R*)dense->vx};
+    if (TB::FSAL) {
+        prep_kernel<Sys, R, VALUE><<<(unsigned)need, kBlock, 0, st>>>(sc, (const R*)y_f, (R*)((char*)workspace + 256), n,
+                                                                    io.counter);
+    } else {
+        reset_counter_kernel<<<1, 1, 0, st>>>(io.counter);
+    }
+    const SolveOpts<R> so = make_solve_opts<R>(o, TB::ORDER);
+    kern<<<grid, kBlock, 0, st>>>(sc, so, io);
+    return (int)cudaGetLastError();
+}
+
+template <template <class> class SysT, int MINB32, int MINB64>
+int launch_solve(const pmp_problem_t& p, const pmp_opts_t& o, long long n, const void* y_f, void* y_end,
+                 const pmp_dense_t* dense, int32_t* a, int32_t* s, int32_t* r, void* ws, cudaStream_t st) {
+    const bool dn = o.save_dense != 0, val = o.indep == PMP_INDEP_VALUE;
+#define PMP_GO(R, METHOD, DENSE, VALUE, MINB) \
+    return launch_one<SysT<R>, R, METHOD, DENSE, VALUE, MINB>(p, o, n, y_f, y_end, dense, a, s, r, ws, st)
+#define PMP_BY_FLAGS(R, METHOD, MINB)                           \
+    do {                                                        \
+        if (dn && val) PMP_GO(R, METHOD, true, true, MINB);     \
+        if (dn && !val) PMP_GO(R, METHOD, true, false, MINB);   \
+        if (!dn && val) PMP_GO(R, METHOD, false, true, MINB);   \
+        PMP_GO(R, METHOD, false, false, MINB);                  \
+    } while (0)
+#define PMP_BY_METHOD(R, MINB)                                                   \
+    do {                                                                         \
+        if (o.method == PMP_METHOD_RK4) PMP_BY_FLAGS(R, PMP_METHOD_RK4, MINB);   \
+        if (o.method == PMP_METHOD_TSIT5) PMP_BY_FLAGS(R, PMP_METHOD_TSIT5, MINB); \
+        if (o.method == PMP_METHOD_DOPRI5) PMP_BY_FLAGS(R, PMP_METHOD_DOPRI5, MINB); \
+    } while (0)
+    if (o.dtype == PMP_F32) PMP_BY_METHOD(float, MINB32);
+    if (o.dtype == PMP_F64) PMP_BY_METHOD(double, MINB64);
+#undef PMP_BY_METHOD
+#undef PMP_BY_FLAGS
+#undef PMP_GO
+    return -1000;
+}
+
+}  // namespace pmp

@@ -1,0 +1,330 @@
+"""Host-side mirror of the reference's `pontryagin_utils` module for the PMP backward-shooting path.
+
+Same names, argument meaning and error behaviour as /root/reference/pontryagin_utils.py:
+
+    define_backward_solver(problem_params, algo_params) -> (solve_backward, f_extended)   :414-529
+    u_star_2d(x, costate, problem_params, smooth=False, debug_oups=False)                 :11-254
+    u_star_new(x, costate, problem_params)                                                :532-562
+    lqr(A, B, Q, R) -> (K, X, eigVals)                                                    :569-599
+    get_terminal_lqr(problem_params) -> (K_lqr, P_lqr)                                    :603-628
+    make_pontryagin_solver_reparam(problem_params, algo_params) -> solver(y0, v0, v1)
+        (absent from the snapshot; contract from experiment_orbits.py:117,181-184,
+         experiment_lqr_statepenalty.py:119,147, rrt_sampler.py:62-77)
+
+Differences, all forced by the move from "jax closure traced on CPU" to "compiled CUDA kernel":
+  * the arithmetic runs in libb200pmp.so (hand-written sm_100a CUDA) through ctypes; arrays are
+    torch CUDA tensors (numpy / CPU tensors are accepted and copied to the current CUDA device);
+  * `jax.vmap(solve_backward)` is replaced by passing a leading batch axis: every function accepts
+    either one state (the reference's shapes) or a batch;
+  * dynamics are selected by problem_params['system_name'] (compiled functors), not by tracing f, l;
+  * there is no CPU fallback: without the library or a CUDA device the calls raise.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Dict, Tuple
+
+import numpy as np
+import scipy.linalg
+import torch
+
+from . import _capi, systems
+from .solution import Solution
+
+__all__ = ["define_backward_solver", "u_star_2d", "u_star_new", "lqr", "get_terminal_lqr",
+           "make_pontryagin_solver_reparam", "solve_batch_soa", "pack_state", "unpack_state"]
+
+# solver constants hard-coded in the reference (pontryagin_utils.py:500-501,515); overridable through
+# optional algo_params keys of the same name prefixed with 'pontryagin_solver_'
+_DEFAULTS = dict(dtmin=0.0005, dtmax=0.5, dt0=0.1, safety=0.9, factormin=0.2, factormax=10.0,
+                 force_dtmin=1, method="tsit5")
+
+
+# ---- tensor plumbing --------------------------------------------------------------------------------
+def _device(*xs) -> torch.device:
+    for x in xs:
+        if isinstance(x, torch.Tensor) and x.is_cuda:
+            return x.device
+    if not torch.cuda.is_available():
+        raise _capi.PmpError("no CUDA device visible: the PMP path has no CPU fallback")
+    return torch.device("cuda", torch.cuda.current_device())
+
+
+def _as_tensor(x, dtype, device) -> torch.Tensor:
+    if isinstance(x, torch.Tensor):
+        return x.to(device=device, dtype=dtype)
+    return torch.as_tensor(np.asarray(x), dtype=dtype, device=device)
+
+
+def _infer_dtype(algo_params, *xs) -> torch.dtype:
+    """algo_params['dtype'] ('float32'/'float64') wins; else float64 inputs select fp64 (the
+    reference's jax_enable_x64, experiment_orbits.py:18-19), anything else fp32 (jax default)."""
+    d = (algo_params or {}).get("dtype")
+    if d is not None:
+        return {"float32": torch.float32, "float64": torch.float64, torch.float32: torch.float32,
+                torch.float64: torch.float64, np.float32: torch.float32, np.float64: torch.float64}[d]
+    for x in xs:
+        if isinstance(x, torch.Tensor) and x.dtype == torch.float64:
+            return torch.float64
+        if isinstance(x, np.ndarray) and x.dtype == np.float64:
+            return torch.float64
+    return torch.float32
+
+
+def _code(dtype: torch.dtype) -> int:
+    return _capi.F64 if dtype == torch.float64 else _capi.F32
+
+
+def _stream_ptr(device) -> C.c_void_p:
+    return C.c_void_p(torch.cuda.current_stream(device).cuda_stream)
+
+
+_workspaces: Dict[Tuple[int, int], torch.Tensor] = {}
+
+
+def _workspace(device: torch.device, nbytes: int) -> torch.Tensor:
+    """Per-(device, stream) scratch, grown geometrically and reused across calls."""
+    key = (device.index or 0, torch.cuda.current_stream(device).cuda_stream)
+    ws = _workspaces.get(key)
+    if ws is None or ws.numel() < nbytes:
+        ws = torch.empty(max(nbytes, 1 << 20), dtype=torch.uint8, device=device)
+        _workspaces[key] = ws
+    return ws
+
+
+def pack_state(state: dict, nx: int, dtype: torch.dtype, device) -> Tuple[torch.Tensor, bool]:
+    """The reference's state dict {'x','t','v','vx'} (pontryagin_utils.py:421-423, levelsets.py:588-593)
+    -> struct-of-arrays [NS, n].  Returns (y, batched)."""
+    if "vxx" in state:
+        raise NotImplementedError("the vxx (Hessian) branch of f_extended is not on the accelerated path")
+    x = _as_tensor(state["x"], dtype, device)
+    batched = x.dim() == 2
+    x = x.reshape(-1, nx)
+    n = x.shape[0]
+    y = torch.empty((2 * nx + 2, n), dtype=dtype, device=device)
+    y[:nx] = x.t()
+    y[nx] = _as_tensor(state.get("t", 0.0), dtype, device).reshape(-1).expand(n)
+    y[nx + 1] = _as_tensor(state["v"], dtype, device).reshape(-1).expand(n)
+    y[nx + 2:] = _as_tensor(state["vx"], dtype, device).reshape(-1, nx).t()
+    return y, batched
+
+
+def unpack_state(y: torch.Tensor, nx: int, batched: bool = True) -> dict:
+    """[NS, n] -> {'x': (n,nx), 't': (n,), 'v': (n,), 'vx': (n,nx)} (leading axis dropped if single)."""
+    d = {"x": y[:nx].t(), "t": y[nx], "v": y[nx + 1], "vx": y[nx + 2:].t()}
+    if not batched:
+        d = {k: v[0] for k, v in d.items()}
+    return d
+
+
+# ---- the batched solve on the C ABI -----------------------------------------------------------------
+def solve_batch_soa(problem: _capi.Problem, opts: _capi.Opts, y_f: torch.Tensor, out=None):
+    """Thin wrapper of pmp_solve_batch_cuda on struct-of-arrays CUDA tensors.  Asynchronous on the
+    current stream.  `out` may carry preallocated outputs (keys y_end, n_accepted, n_steps, result,
+    and ts, x, t, v, vx when opts.save_dense)."""
+    L = _capi.lib()
+    assert y_f.is_cuda and y_f.is_contiguous()
+    ns, n = y_f.shape
+    nx = problem.nx
+    dev = y_f.device
+    out = {} if out is None else out
+    if "y_end" not in out:
+        out["y_end"] = torch.empty_like(y_f)
+    for k in ("n_accepted", "n_steps", "result"):
+        if k not in out:
+            out[k] = torch.empty(n, dtype=torch.int32, device=dev)
+    dense = None
+    if opts.save_dense:
+        s1 = opts.max_steps + 1
+        shapes = {"ts": (n, s1), "x": (n, s1, nx), "t": (n, s1), "v": (n, s1), "vx": (n, s1, nx)}
+        for k, shp in shapes.items():
+            if k not in out:
+                out[k] = torch.empty(shp, dtype=y_f.dtype, device=dev)
+        dense = _capi.Dense(*(out[k].data_ptr() for k in ("ts", "x", "t", "v", "vx")))
+    nbytes = _capi.check(L.pmp_solve_workspace_bytes(C.byref(problem), C.byref(opts), n))
+    ws = _workspace(dev, nbytes)
+    with torch.cuda.device(dev):
+        _capi.check(L.pmp_solve_batch_cuda(
+            C.byref(problem), C.byref(opts), n, y_f.data_ptr(), out["y_end"].data_ptr(),
+            C.byref(dense) if dense is not None else None, out["n_accepted"].data_ptr(),
+            out["n_steps"].data_ptr(), out["result"].data_ptr(), ws.data_ptr(), ws.numel(),
+            _stream_ptr(dev)))
+    return out
+
+
+def _wrap_solution(out, nx, batched, t0, t1, opts) -> Solution:
+    ys = None
+    ts = None
+    if opts.save_dense:
+        ts = out["ts"]
+        ys = {"x": out["x"], "t": out["t"], "v": out["v"], "vx": out["vx"]}
+    stats = {"num_steps": out["n_steps"], "num_accepted_steps": out["n_accepted"],
+             "num_rejected_steps": out["n_steps"] - out["n_accepted"]}
+    sol = Solution(t0=t0, t1=t1, ts=ts, ys=ys, y_end=unpack_state(out["y_end"], nx), stats=stats,
+                   result=out["result"], batched=True)
+    return sol if batched else sol[0]
+
+
+def _solver_opts(algo_params: dict, dtype: torch.dtype, **over) -> _capi.Opts:
+    g = lambda k: algo_params.get("pontryagin_solver_" + k, _DEFAULTS[k])
+    kw = dict(method=g("method"), dtype=_code(dtype), dtmin=g("dtmin"), dtmax=g("dtmax"),
+              safety=g("safety"), factormin=g("factormin"), factormax=g("factormax"),
+              force_dtmin=g("force_dtmin"),
+              rtol=algo_params.get("pontryagin_solver_rtol", 1e-5),
+              atol=algo_params.get("pontryagin_solver_atol", 1e-5),
+              max_steps=int(algo_params["pontryagin_solver_maxsteps"]))
+    kw.update(over)
+    return _capi.make_opts(**kw)
+
+
+def define_backward_solver(problem_params: dict, algo_params: dict):
+    """pontryagin_utils.py:414-529.  Returns (solve_backward, f_extended).
+
+    solve_backward(y_f): y_f = {'x','t','v','vx'} with the reference's shapes, or with a leading
+    batch axis N on every leaf (replaces jax.vmap, levelsets.py:601,1254).  Integrates the extended
+    characteristic system from t0=0 to t1=-T with Tsit5 + PIDController(rtol, atol, dtmin=5e-4,
+    dtmax=.5), dt0=-0.1, at most `pontryagin_solver_maxsteps` step attempts, throw=False semantics
+    (per-trajectory `result` codes, inf padding).  Optional algo_params keys:
+    'pontryagin_solver_method' ('tsit5' | 'dopri5' | 'rk4'), 'pontryagin_solver_adaptive' (default
+    True; RK4 is fixed-step), 'pontryagin_solver_dt0', '..._dtmin', '..._dtmax',
+    'pontryagin_solver_save_steps' (default True = SaveAt(steps=True)), 'dtype'.
+    """
+    if algo_params.get("pontryagin_solver_vxx", False):
+        raise NotImplementedError("pontryagin_solver_vxx=True (Hessian propagation, pontryagin_utils.py:"
+                                  "460-467) is not on the accelerated path")
+    problem = systems.to_c_problem(problem_params)
+    nx = problem.nx
+
+    def f_extended(t, state, args=None):
+        """RHS of the extended system in forward time (pontryagin_utils.py:418-482)."""
+        dev = _device(state["x"])
+        dtype = _infer_dtype(algo_params, state["x"])
+        y, batched = pack_state(state, nx, dtype, dev)
+        dy = torch.empty_like(y)
+        with torch.cuda.device(dev):
+            _capi.check(_capi.lib().pmp_rhs_batch_cuda(C.byref(problem), _code(dtype), y.shape[1],
+                                                       y.data_ptr(), dy.data_ptr(), _stream_ptr(dev)))
+        return unpack_state(dy, nx, batched)
+
+    def solve_backward(y_f, save_steps=None):
+        dev = _device(y_f["x"])
+        dtype = _infer_dtype(algo_params, y_f["x"])
+        y, batched = pack_state(y_f, nx, dtype, dev)
+        T = float(algo_params["pontryagin_solver_T"])
+        method = algo_params.get("pontryagin_solver_method", _DEFAULTS["method"])
+        adaptive = bool(algo_params.get("pontryagin_solver_adaptive", True)) and str(method).lower() != "rk4"
+        if save_steps is None:
+            save_steps = bool(algo_params.get("pontryagin_solver_save_steps", True))
+        dt0 = float(algo_params.get("pontryagin_solver_dt0", _DEFAULTS["dt0"]))
+        opts = _solver_opts(algo_params, dtype, t0=0.0, t1=-T, dt0=-abs(dt0), adaptive=int(adaptive),
+                            save_dense=int(save_steps))
+        out = solve_batch_soa(problem, opts, y)
+        return _wrap_solution(out, nx, batched, 0.0, -T, opts)
+
+    return solve_backward, f_extended
+
+
+def _ustar(x, costate, problem_params):
+    problem = systems.to_c_problem(problem_params)
+    nx, nu = problem.nx, problem.nu
+    dev = _device(x, costate)
+    dtype = _infer_dtype(problem_params, x, costate)
+    xt = _as_tensor(x, dtype, dev)
+    batched = xt.dim() == 2
+    xs = xt.reshape(-1, nx).t().contiguous()
+    ls = _as_tensor(costate, dtype, dev).reshape(-1, nx).t().contiguous()
+    u = torch.empty((nu, xs.shape[1]), dtype=dtype, device=dev)
+    with torch.cuda.device(dev):
+        _capi.check(_capi.lib().pmp_ustar_batch_cuda(C.byref(problem), _code(dtype), xs.shape[1],
+                                                     xs.data_ptr(), ls.data_ptr(), u.data_ptr(),
+                                                     _stream_ptr(dev)))
+    u = u.t()
+    return u if batched else u[0]
+
+
+def u_star_2d(x, costate, problem_params, smooth=False, debug_oups=False):
+    """pontryagin_utils.py:11-254: u* = argmin_u l(x,u) + costate.f(x,u) over the 2-D input box.
+    x, costate: (nx,) or (N, nx).  smooth=True (logsumexp blend, :217-254) is a debugging aid of
+    the reference and is not implemented."""
+    if not problem_params["nu"] == 2:
+        raise NotImplementedError("this ustar function is for 2d only!")
+    if smooth:
+        raise NotImplementedError("smooth=True variant of u_star_2d is not on the accelerated path")
+    return _ustar(x, costate, problem_params)
+
+
+def u_star_new(x, costate, problem_params):
+    """pontryagin_utils.py:532-562: clip(solve(R+R', -costate' df/du), U) for nu == 1."""
+    assert problem_params["nu"] == 1
+    return _ustar(x, costate, problem_params)
+
+
+def lqr(A, B, Q, R):
+    """pontryagin_utils.py:569-599: continuous-time LQR; X such that the LQR value is 0.5 x'Xx."""
+    A, B, Q, R = (np.asarray(M, dtype=float) for M in (A, B, Q, R))
+    X = scipy.linalg.solve_continuous_are(A, B, Q, R)
+    K = np.linalg.inv(R) @ (B.T @ X)
+    eigVals = np.linalg.eigvals(A - B @ K)
+    if not (eigVals.real < 0).all():
+        raise ValueError("LQR closed loop not stable...")
+    return K, X, eigVals
+
+
+def get_terminal_lqr(problem_params):
+    """pontryagin_utils.py:603-628: linearise at (x_eq, u_eq), check equilibrium and
+    controllability, solve the CARE.  Host-side setup (scipy), not part of the GPU path."""
+    x_eq = np.asarray(problem_params["x_eq"], dtype=float)
+    u_eq = np.asarray(problem_params["u_eq"], dtype=float)
+    f0 = np.asarray(systems._call_f(problem_params["f"], x_eq, u_eq), dtype=float)
+    assert np.allclose(f0, 0), "(x_eq, u_eq) does not seem to be an equilibrium"
+    A, B, Q, R = systems.linearise(problem_params)
+    nx = problem_params["nx"]
+    ctrb = np.hstack([np.linalg.matrix_power(A, j) @ B for j in range(nx)])
+    if np.linalg.matrix_rank(ctrb) < nx:
+        raise ValueError("linearisation not controllable aaaaah what did you do idiot")
+    K_lqr, P_lqr, _ = lqr(A, B, Q, R)
+    return K_lqr, P_lqr
+
+
+def make_pontryagin_solver_reparam(problem_params: dict, algo_params: dict):
+    """The value-reparameterised characteristic solver the stale experiments call
+    (experiment_orbits.py:117, experiment_lqr_statepenalty.py:119, rrt_sampler.py:64-70) and the
+    snapshot no longer defines.  Contract rebuilt from the call sites:
+
+        solver(y0, v0, v1) -> Solution
+          y0 = [x (nx), lambda (nx), t (1)] flat, or (N, 2nx+1)       rrt_sampler.py:62
+          v0 = value at y0 (scalar or (N,)), v1 = V_max               experiment_orbits.py:128-129
+          integrates dy/dv = (f, -H_x, 1) / (dv/dt), dv/dt = -l(x,u*) experiment_orbits.py:109-111
+          sol.ts = value levels, sol.ys = (S+1, 2nx+1) [batched: (N, S+1, 2nx+1)]  rrt_sampler.py:76-82
+    algo_params: pontryagin_solver_{dt, adaptive, rtol, atol, maxsteps} (experiment_orbits.py:97-104).
+    No reference output exists for this function: parity is pinned only against the oracle.
+    """
+    problem = systems.to_c_problem(problem_params)
+    nx = problem.nx
+
+    def solver(y0, v0, v1, save_steps=True):
+        dev = _device(y0)
+        dtype = _infer_dtype(algo_params, y0)
+        y0t = _as_tensor(y0, dtype, dev)
+        batched = y0t.dim() == 2
+        y0t = y0t.reshape(-1, 2 * nx + 1)
+        n = y0t.shape[0]
+        y = torch.empty((2 * nx + 2, n), dtype=dtype, device=dev)
+        y[:nx] = y0t[:, :nx].t()
+        y[nx] = y0t[:, 2 * nx]
+        y[nx + 1] = _as_tensor(v0, dtype, dev).reshape(-1).expand(n)
+        y[nx + 2:] = y0t[:, nx:2 * nx].t()
+        adaptive = bool(algo_params.get("pontryagin_solver_adaptive", True))
+        opts = _solver_opts(algo_params, dtype, indep=_capi.INDEP_VALUE, t0=0.0, t1=float(v1),
+                            dt0=float(algo_params.get("pontryagin_solver_dt", 1 / 16)),
+                            adaptive=int(adaptive), save_dense=int(save_steps),
+                            dtmin=float(algo_params.get("pontryagin_solver_dtmin", 0.0)),
+                            dtmax=float(algo_params.get("pontryagin_solver_dtmax", 0.0)))
+        out = solve_batch_soa(problem, opts, y)
+        sol = _wrap_solution(out, nx, True, None, float(v1), opts)
+        if sol.ys is not None:  # flat (.., 2nx+1) layout of the missing solver
+            sol.extra["ys_dict"] = sol.ys
+            sol.ys = torch.cat([sol.ys["x"], sol.ys["vx"], sol.ys["t"][..., None]], dim=-1)
+        return sol if batched else sol[0]
+
+    return solver

@@ -1,0 +1,50 @@
+"""`Solution`: the subset of diffrax.Solution that the reference's callers touch, backed by torch
+CUDA tensors.
+
+Attributes used by the reference (file:line in /root/reference):
+  .ts      (N, S+1)            saved times, padded -inf/+inf      visualiser.py:97-99
+  .ys      {'x','t','v','vx'}  (N, S+1[, nx]), padded +inf        levelsets.py:679-693, visualiser.py:76-77
+  .stats   {'num_steps','num_accepted_steps','num_rejected_steps'} levelsets.py:1215, rrt_sampler.py:497
+  .result  (N,) int32, 1 == terminating event                     levelsets.py:1218
+  .t0 .t1
+Extension: .y_end = {'x','t','v','vx'} the last accepted state, i.e. ys[..][num_accepted_steps]
+(levelsets.py:1215) without materialising the dense buffers.
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass, field
+from typing import Dict, Optional
+
+import torch
+
+
+@dataclass
+class Solution:
+    t0: float
+    t1: float
+    ts: Optional[torch.Tensor]
+    ys: Optional[Dict[str, torch.Tensor]]
+    y_end: Dict[str, torch.Tensor]
+    stats: Dict[str, torch.Tensor]
+    result: torch.Tensor
+    batched: bool = True
+    extra: dict = field(default_factory=dict)
+
+    def evaluate(self, t):
+        raise NotImplementedError(
+            "dense interpolation (diffrax Solution.evaluate) is not part of the accelerated path yet; "
+            "use .ts/.ys (every accepted step) or .y_end")
+
+    def numpy(self) -> "Solution":
+        """Copy every tensor to host numpy arrays (same structure)."""
+        cv = lambda t: None if t is None else t.detach().cpu().numpy()
+        cd = lambda d: ({k: cv(v) for k, v in d.items()} if isinstance(d, dict) else cv(d))
+        return Solution(self.t0, self.t1, cv(self.ts), cd(self.ys), cd(self.y_end), cd(self.stats),
+                        cv(self.result), self.batched, dict(self.extra))
+
+    def __getitem__(self, i) -> "Solution":
+        """Select trajectories (the reference does jax.tree_util.tree_map(itemgetter(i), sols))."""
+        sel = lambda t: None if t is None else t[i]
+        sd = lambda d: ({k: v[i] for k, v in d.items()} if isinstance(d, dict) else sel(d))
+        return Solution(self.t0, self.t1, sel(self.ts), sd(self.ys), sd(self.y_end), sd(self.stats),
+                        sel(self.result), not isinstance(i, int), dict(self.extra))

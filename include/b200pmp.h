@@ -1,0 +1,178 @@
+/*
+ * b200pmp.h -- C ABI of libb200pmp.so: batched Pontryagin (PMP) backward-shooting rollouts on B200.
+ *
+ * This is the drop-in boundary for ONE hot path of mbjd/approximate_optimal_control.  The reference
+ * has no FFI (it is a Python closure API over JAX pytrees); every entry point below names the
+ * reference interface it replaces.  All citations are relative to the reference checkout.
+ *
+ *   pmp_solve_batch_cuda   <- jax.vmap(solve_backward)            pontryagin_utils.py:488-527 as
+ *                             vmapped at levelsets.py:601,1254; and the missing value-reparameterised
+ *                             solver called at experiment_orbits.py:117,182, rrt_sampler.py:64-70
+ *   pmp_rhs_batch_cuda     <- jax.vmap(f_extended)                pontryagin_utils.py:418-482
+ *   pmp_ustar_batch_cuda   <- jax.vmap(u_star_2d) / u_star_new    pontryagin_utils.py:11-216, :532-562
+ *                             (batched at levelsets.py:604-628 find_min_l)
+ *   pmp_fma_peak_cuda      <- (no reference counterpart) register-resident FMA chain used as the
+ *                             roofline denominator of bench.py
+ *
+ * Conventions
+ *   - plain pointers and sizes; no torch / CUDA types in signatures (cuda_stream is a cudaStream_t
+ *     passed as void*; NULL = the legacy default stream).
+ *   - every *_cuda pointer argument is a DEVICE pointer owned by the caller; nothing is allocated,
+ *     nothing is freed, no hidden host<->device copy, no synchronisation: the call enqueues work on
+ *     `cuda_stream` and returns.
+ *   - return value 0 = ok, <0 = error (PMP_ERR_*); pmp_last_error() gives a thread-local message.
+ *     Functions never throw and never abort.
+ *   - real arrays are float (dtype 0) or double (dtype 1), chosen by pmp_opts_t.dtype.
+ *
+ * ODE state of one trajectory ("extended state"), NS = 2*nx + 2 scalars, in the order of the
+ * reference's state dict {'x','t','v','vx'} (pontryagin_utils.py:454-458):
+ *       row 0 .. nx-1        x        state
+ *       row nx               t        time (integrated as a state with dt/dt = 1)
+ *       row nx+1             v        value / cost-to-go
+ *       row nx+2 .. 2nx+1    vx       costate  lambda = V_x
+ * Batches are struct-of-arrays: y[row * n + i] is component `row` of trajectory i, so that a warp
+ * reading 32 consecutive trajectories issues one coalesced 128-byte load per row.
+ */
+#ifndef B200PMP_H
+#define B200PMP_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PMP_ABI_VERSION 1
+
+/* systems (dynamics are compile-time functors; problem_params['system_name'] selects one) */
+enum {
+    PMP_SYS_FLATQUAD = 0,         /* flatquad_landing_experiment.py:269-365   nx=6 nu=2 */
+    PMP_SYS_ORBITS = 1,           /* experiment_orbits.py:24-40,83-104        nx=2 nu=1 */
+    PMP_SYS_LQR_STATEPENALTY = 2  /* experiment_lqr_statepenalty.py:23-38     nx=2 nu=1 */
+};
+
+/* integrators */
+enum {
+    PMP_METHOD_RK4 = 0,   /* classic fixed-step RK4 (BASELINE.json config 0) */
+    PMP_METHOD_TSIT5 = 1, /* diffrax.Tsit5, the only solver the reference uses (pontryagin_utils.py:515,522) */
+    PMP_METHOD_DOPRI5 = 2 /* Dormand-Prince 5(4) (BASELINE.json config 1) */
+};
+
+enum { PMP_F32 = 0, PMP_F64 = 1 };
+
+/* independent variable */
+enum {
+    PMP_INDEP_TIME = 0, /* solve_backward, pontryagin_utils.py:488-527 */
+    PMP_INDEP_VALUE = 1 /* value-reparameterised solver (experiment_orbits.py:109-117) */
+};
+
+/* terminating events (diffrax.DiscreteTerminatingEvent, evaluated after every step attempt) */
+enum {
+    PMP_EVENT_NONE = 0,
+    PMP_EVENT_VALUE_GE = 1 /* stop once v >= event_level (value level set, problem_params['V_max']) */
+};
+
+/* per-trajectory result codes, diffrax-compatible (levelsets.py:1218 tests result == 1) */
+enum {
+    PMP_RESULT_OK = 0,
+    PMP_RESULT_EVENT = 1,
+    PMP_RESULT_MAX_STEPS = 2,
+    PMP_RESULT_DT_MIN = 3,
+    PMP_RESULT_NAN = 4
+};
+
+/* error codes */
+enum {
+    PMP_OK = 0,
+    PMP_ERR_BAD_ARG = -1,
+    PMP_ERR_UNSUPPORTED = -2,
+    PMP_ERR_CUDA = -3,
+    PMP_ERR_NO_DEVICE = -4
+};
+
+typedef struct {
+    int32_t system_id;
+    int32_t nx, nu;
+    double u_lo[2], u_hi[2]; /* problem_params['U_interval'] */
+    /* flatquad:  m, g, r, I, q_pos, q_ang, q_vel, q_omega   (q = 1/length_scale^2)
+     * orbits:    w_dist (0.1), w_u (10)
+     * lqr:       a (state-penalty steepness 0.01), r_u (1) */
+    double params[16];
+} pmp_problem_t;
+
+typedef struct {
+    int32_t method;      /* PMP_METHOD_*                                                  */
+    int32_t dtype;       /* PMP_F32 / PMP_F64                                             */
+    int32_t indep;       /* PMP_INDEP_*                                                   */
+    int32_t adaptive;    /* 1: PIDController (I-controller) step control; 0: constant dt0 */
+    int32_t max_steps;   /* step ATTEMPTS (accepted + rejected), diffrax max_steps        */
+    int32_t force_dtmin; /* diffrax PIDController.force_dtmin (default 1)                 */
+    int32_t event;       /* PMP_EVENT_*                                                   */
+    int32_t save_dense;  /* 1: every accepted step is written to pmp_dense_t              */
+    double t0, t1, dt0;  /* t1 < t0 integrates backward (pontryagin_utils.py:515: 0 -> -T, dt0=-0.1);
+                            PMP_INDEP_VALUE: t0 is ignored (each trajectory starts at its own v),
+                            t1 = V_max, dt0 > 0 in value units                             */
+    double rtol, atol;   /* algo_params['pontryagin_solver_rtol'|'_atol']                  */
+    double dtmin, dtmax; /* 0.0005, 0.5 hard-coded at pontryagin_utils.py:500-501; <=0 disables */
+    double safety, factormin, factormax; /* diffrax defaults .9, .2, 10                   */
+    double event_level;
+} pmp_opts_t;
+
+/* Dense ("SaveAt(steps=True, t0=True)") output, the reference's Solution layout: slot 0 is the
+ * terminal state, one slot per ACCEPTED step, unused slots are +inf (ts: -inf when integrating
+ * backward, cf. visualiser.py:76-99).  S1 = max_steps + 1 slots per trajectory.  Any pointer may
+ * be NULL to skip that leaf. */
+typedef struct {
+    void *ts; /* [n][S1]     */
+    void *x;  /* [n][S1][nx] */
+    void *t;  /* [n][S1]     */
+    void *v;  /* [n][S1]     */
+    void *vx; /* [n][S1][nx] */
+} pmp_dense_t;
+
+int pmp_abi_version(void);
+const char *pmp_last_error(void);
+int pmp_state_rows(const pmp_problem_t *problem); /* NS = 2*nx+2 */
+
+/* number of CUDA devices visible to this process (<0: error, 0: none) */
+int pmp_device_count(void);
+
+/* Scratch the solve needs for n trajectories (work-queue counter + the first-stage derivative
+ * k1 = F(y_f) of every trajectory, [2nx+1][n] reals).  The caller allocates it on the device. */
+int64_t pmp_solve_workspace_bytes(const pmp_problem_t *problem, const pmp_opts_t *opts, int64_t n);
+
+/* Integrate n trajectories from their terminal states y_f [NS][n].
+ *   y_end      [NS][n]  last accepted state (== ys[num_accepted_steps], levelsets.py:1215)
+ *   dense      may be NULL unless opts->save_dense
+ *   n_accepted,n_steps,result  [n] int32 (any may be NULL)
+ *   workspace  device scratch of >= pmp_solve_workspace_bytes() bytes, 256-byte aligned; its
+ *              content is undefined afterwards; must not be shared by concurrent calls
+ * Work is enqueued on cuda_stream of the CURRENT device; returns immediately. */
+int pmp_solve_batch_cuda(const pmp_problem_t *problem, const pmp_opts_t *opts, int64_t n,
+                         const void *y_f, void *y_end, const pmp_dense_t *dense,
+                         int32_t *n_accepted, int32_t *n_steps, int32_t *result,
+                         void *workspace, int64_t workspace_bytes, void *cuda_stream);
+
+/* number of kernels one pmp_solve_batch_cuda call launches with these options (bench bookkeeping) */
+int pmp_solve_launch_count(const pmp_problem_t *problem, const pmp_opts_t *opts, int64_t n);
+
+/* forward-time extended RHS f_extended(t, state) for n states: y [NS][n] -> dy [NS][n] */
+int pmp_rhs_batch_cuda(const pmp_problem_t *problem, int32_t dtype, int64_t n, const void *y,
+                       void *dy, void *cuda_stream);
+
+/* u* = argmin_u H(x,u,lambda) over the input box: x [nx][n], lam [nx][n] -> u [nu][n] */
+int pmp_ustar_batch_cuda(const pmp_problem_t *problem, int32_t dtype, int64_t n, const void *x,
+                         const void *lam, void *u, void *cuda_stream);
+
+/* Register-resident dependent-FMA chains on every SM (roofline denominator of bench.py): enqueues
+ * one kernel that executes *flops_out floating point operations (written on the host, may be
+ * NULL); the caller times it with events on cuda_stream.  dtype selects FFMA / DFMA.
+ * variant 0: a = fma(a, b, c) with register operands; variant 1: multiplier/addend as
+ * compile-time immediates (the form the integrator's tableau FMAs take). */
+int pmp_fma_peak_cuda(int32_t dtype, int32_t variant, int32_t iters, void *scratch /* >= 8 B device */,
+                      double *flops_out, void *cuda_stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* B200PMP_H */

@@ -1,0 +1,185 @@
+"""ctypes front end of the CPU ORACLE (oracle/libpmp_oracle.so).
+
+TEST INFRASTRUCTURE, NOT PRODUCT CODE.  Only tests/, __graft_entry__.smoke() and bench.py's
+cpu_baseline / --impl reference legs import this module; nothing under
+approximate_optimal_control_b200/ does.  The structs mirror include/b200pmp.h so that the oracle and
+the CUDA library are driven with byte-identical problem / option records.
+
+Batches are numpy arrays in the product's struct-of-arrays layout: y[row, i] with
+rows = (x[0..nx), t, v, vx[0..nx)) -- the reference's state dict order
+(/root/reference pontryagin_utils.py:454-458).
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB_PATH = os.path.join(_HERE, "libpmp_oracle.so")
+
+SYS_FLATQUAD, SYS_ORBITS, SYS_LQR = 0, 1, 2
+RK4, TSIT5, DOPRI5 = 0, 1, 2
+F32, F64 = 0, 1
+INDEP_TIME, INDEP_VALUE = 0, 1
+EVENT_NONE, EVENT_VALUE_GE = 0, 1
+
+
+class Problem(C.Structure):
+    _fields_ = [("system_id", C.c_int32), ("nx", C.c_int32), ("nu", C.c_int32),
+                ("u_lo", C.c_double * 2), ("u_hi", C.c_double * 2), ("params", C.c_double * 16)]
+
+
+class Opts(C.Structure):
+    _fields_ = [("method", C.c_int32), ("dtype", C.c_int32), ("indep", C.c_int32),
+                ("adaptive", C.c_int32), ("max_steps", C.c_int32), ("force_dtmin", C.c_int32),
+                ("event", C.c_int32), ("save_dense", C.c_int32),
+                ("t0", C.c_double), ("t1", C.c_double), ("dt0", C.c_double),
+                ("rtol", C.c_double), ("atol", C.c_double), ("dtmin", C.c_double),
+                ("dtmax", C.c_double), ("safety", C.c_double), ("factormin", C.c_double),
+                ("factormax", C.c_double), ("event_level", C.c_double)]
+
+
+class Dense(C.Structure):
+    _fields_ = [("ts", C.c_void_p), ("x", C.c_void_p), ("t", C.c_void_p), ("v", C.c_void_p),
+                ("vx", C.c_void_p)]
+
+
+def build(force: bool = False) -> str:
+    """Compile oracle/libpmp_oracle.so with the committed Makefile (g++, OpenMP)."""
+    src_m = max(os.path.getmtime(os.path.join(_HERE, f))
+                for f in ("pmp_oracle.cpp", "pmp_oracle.hpp", "opcount.hpp", "Makefile"))
+    if force or not os.path.exists(_LIB_PATH) or os.path.getmtime(_LIB_PATH) < src_m:
+        subprocess.run(["make", "-C", _HERE, "-B", "libpmp_oracle.so"], check=True,
+                       stdout=subprocess.DEVNULL)
+    return _LIB_PATH
+
+
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        build()
+        L = C.CDLL(_LIB_PATH)
+        L.pmp_oracle_last_error.restype = C.c_char_p
+        L.pmp_oracle_solve_batch.argtypes = [C.POINTER(Problem), C.POINTER(Opts), C.c_int64,
+                                             C.c_void_p, C.c_void_p, C.POINTER(Dense), C.c_void_p,
+                                             C.c_void_p, C.c_void_p, C.c_int, C.c_int]
+        L.pmp_oracle_rhs_batch.argtypes = [C.POINTER(Problem), C.c_int32, C.c_int64, C.c_void_p,
+                                           C.c_void_p, C.c_int]
+        L.pmp_oracle_ustar_batch.argtypes = [C.POINTER(Problem), C.c_int32, C.c_int64, C.c_void_p,
+                                             C.c_void_p, C.c_void_p, C.c_int]
+        L.pmp_oracle_opcount.argtypes = [C.POINTER(Problem), C.POINTER(Opts), C.c_void_p, C.c_void_p]
+        _lib = L
+    return _lib
+
+
+def num_threads() -> int:
+    return int(lib().pmp_oracle_num_threads())
+
+
+# ---- the three systems with the reference's constants ---------------------------------------------
+def flatquad_problem() -> Problem:
+    """flatquad_landing_experiment.py:269-273, :313-315, :355-358."""
+    m, g, r = 20.0, 9.81, 0.5
+    I = m * (r / 2) ** 2
+    umax = m * g * 1.2 / 2
+    p = Problem(system_id=SYS_FLATQUAD, nx=6, nu=2)
+    p.u_lo[:] = [0.0, 0.0]
+    p.u_hi[:] = [umax, umax]
+    scales = [0.3, np.deg2rad(30.0), 0.5, np.deg2rad(120.0)]
+    vals = [m, g, r, I] + [1.0 / s ** 2 for s in scales]
+    for i, v in enumerate(vals):
+        p.params[i] = v
+    return p
+
+
+def orbits_problem() -> Problem:
+    """experiment_orbits.py:24-40, :83-94."""
+    p = Problem(system_id=SYS_ORBITS, nx=2, nu=1)
+    p.u_lo[0], p.u_hi[0] = -0.2, 0.2
+    p.params[0], p.params[1] = 0.1, 10.0
+    return p
+
+
+def lqr_problem(u_lo=-1.0, u_hi=1.0, a=0.01) -> Problem:
+    """experiment_lqr_statepenalty.py:23-38, :89."""
+    p = Problem(system_id=SYS_LQR, nx=2, nu=1)
+    p.u_lo[0], p.u_hi[0] = u_lo, u_hi
+    p.params[0], p.params[1] = a, 1.0
+    return p
+
+
+def make_opts(method=TSIT5, dtype=F32, indep=INDEP_TIME, adaptive=1, max_steps=128, force_dtmin=1,
+              event=EVENT_NONE, save_dense=0, t0=0.0, t1=-3.0, dt0=-0.1, rtol=1e-5, atol=1e-5,
+              dtmin=0.0005, dtmax=0.5, safety=0.9, factormin=0.2, factormax=10.0,
+              event_level=0.0) -> Opts:
+    """Defaults = the flatquad solve (pontryagin_utils.py:496-525, flatquad_landing_experiment.py:368-382)."""
+    return Opts(method, dtype, indep, adaptive, max_steps, force_dtmin, event, save_dense, t0, t1,
+                dt0, rtol, atol, dtmin, dtmax, safety, factormin, factormax, event_level)
+
+
+def _np_dtype(dtype):
+    return np.float32 if dtype == F32 else np.float64
+
+
+def _check(rc):
+    if rc != 0:
+        raise RuntimeError(f"oracle error {rc}: {lib().pmp_oracle_last_error().decode()}")
+
+
+def solve_batch(problem: Problem, opts: Opts, y_f: np.ndarray, n_threads: int = 0,
+                model_pass1: bool = False):
+    """y_f [NS, n] -> dict(y_end [NS,n], n_accepted, n_steps, result [, ts, x, t, v, vx])."""
+    dt = _np_dtype(opts.dtype)
+    y_f = np.ascontiguousarray(y_f, dtype=dt)
+    ns, n = y_f.shape
+    nx = problem.nx
+    assert ns == 2 * nx + 2
+    out = {"y_end": np.empty((ns, n), dt), "n_accepted": np.empty(n, np.int32),
+           "n_steps": np.empty(n, np.int32), "result": np.empty(n, np.int32)}
+    dense = None
+    if opts.save_dense:
+        s1 = opts.max_steps + 1
+        out.update(ts=np.empty((n, s1), dt), x=np.empty((n, s1, nx), dt), t=np.empty((n, s1), dt),
+                   v=np.empty((n, s1), dt), vx=np.empty((n, s1, nx), dt))
+        dense = Dense(*(out[k].ctypes.data for k in ("ts", "x", "t", "v", "vx")))
+    _check(lib().pmp_oracle_solve_batch(C.byref(problem), C.byref(opts), n, y_f.ctypes.data,
+                                        out["y_end"].ctypes.data,
+                                        C.byref(dense) if dense is not None else None,
+                                        out["n_accepted"].ctypes.data, out["n_steps"].ctypes.data,
+                                        out["result"].ctypes.data, int(n_threads), int(model_pass1)))
+    return out
+
+
+def rhs_batch(problem: Problem, dtype: int, y: np.ndarray, model_pass1: bool = False) -> np.ndarray:
+    dt = _np_dtype(dtype)
+    y = np.ascontiguousarray(y, dtype=dt)
+    dy = np.empty_like(y)
+    _check(lib().pmp_oracle_rhs_batch(C.byref(problem), dtype, y.shape[1], y.ctypes.data,
+                                      dy.ctypes.data, int(model_pass1)))
+    return dy
+
+
+def ustar_batch(problem: Problem, dtype: int, x: np.ndarray, lam: np.ndarray,
+                model_pass1: bool = False) -> np.ndarray:
+    dt = _np_dtype(dtype)
+    x = np.ascontiguousarray(x, dtype=dt)
+    lam = np.ascontiguousarray(lam, dtype=dt)
+    u = np.empty((problem.nu, x.shape[1]), dt)
+    _check(lib().pmp_oracle_ustar_batch(C.byref(problem), dtype, x.shape[1], x.ctypes.data,
+                                        lam.ctypes.data, u.ctypes.data, int(model_pass1)))
+    return u
+
+
+def opcount(problem: Problem, opts: Opts, y0: np.ndarray) -> dict:
+    """Algorithmic flops / specials per RHS and per step attempt."""
+    y0 = np.ascontiguousarray(y0, dtype=np.float64)
+    out = np.zeros(4, np.int64)
+    _check(lib().pmp_oracle_opcount(C.byref(problem), C.byref(opts), y0.ctypes.data, out.ctypes.data))
+    return {"rhs_flops": int(out[0]), "rhs_special": int(out[1]), "attempt_flops": int(out[2]),
+            "attempt_special": int(out[3])}

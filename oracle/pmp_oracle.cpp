@@ -1,0 +1,199 @@
+// pmp_oracle.cpp -- C entry points of the CPU ORACLE (test infrastructure, NOT product code).
+// See pmp_oracle.hpp for what is restated and the parity status.  Host pointers everywhere; the
+// batch layout is the product's (include/b200pmp.h): struct-of-arrays y[row*n + i].
+#include "pmp_oracle.hpp"
+
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "opcount.hpp"
+#ifdef _OPENMP
+#include <omp.h>
+#endif
+
+using namespace pmpo;
+
+namespace {
+thread_local std::string g_err;
+int fail(int code, const char* msg) {
+    g_err = msg;
+    return code;
+}
+
+template <class R, class Sys>
+int solve_batch_t(const pmp_problem_t& p, const pmp_opts_t& o, int64_t n, const R* y_f, R* y_end,
+                  const pmp_dense_t* dense, int32_t* n_acc, int32_t* n_steps, int32_t* result,
+                  int n_threads, int model_pass1) {
+    constexpr int NX = Sys::NX, NS = 2 * NX + 2;
+    Sys sys(p);
+    if constexpr (Sys::NU == 2) sys.model_pass1 = model_pass1 != 0;
+    const int64_t S1 = o.max_steps + 1;
+    (void)n_threads;
+#ifdef _OPENMP
+    if (n_threads < 1) n_threads = omp_get_max_threads();
+#pragma omp parallel for schedule(dynamic, 256) num_threads(n_threads)
+#endif
+    for (int64_t i = 0; i < n; i++) {
+        R y0[NS], y1[NS];
+        for (int q = 0; q < NS; q++) y0[q] = y_f[q * n + i];
+        DenseSink<R> sink;
+        if (dense && o.save_dense) {
+            if (dense->ts) sink.ts = (R*)dense->ts + i * S1;
+            if (dense->x) sink.x = (R*)dense->x + i * S1 * NX;
+            if (dense->t) sink.t = (R*)dense->t + i * S1;
+            if (dense->v) sink.v = (R*)dense->v + i * S1;
+            if (dense->vx) sink.vx = (R*)dense->vx + i * S1 * NX;
+        }
+        TrajStats st = solve_one<R, Sys>(sys, o, y0, y1, sink);
+        for (int q = 0; q < NS; q++) y_end[q * n + i] = y1[q];
+        if (n_acc) n_acc[i] = st.n_accepted;
+        if (n_steps) n_steps[i] = st.n_steps;
+        if (result) result[i] = st.result;
+    }
+    return 0;
+}
+
+template <class Sys32, class Sys64>
+int solve_dispatch(const pmp_problem_t& p, const pmp_opts_t& o, int64_t n, const void* y_f,
+                   void* y_end, const pmp_dense_t* dense, int32_t* a, int32_t* s, int32_t* r,
+                   int nt, int mp1) {
+    if (o.dtype == PMP_F32)
+        return solve_batch_t<float, Sys32>(p, o, n, (const float*)y_f, (float*)y_end, dense, a, s, r, nt, mp1);
+    return solve_batch_t<double, Sys64>(p, o, n, (const double*)y_f, (double*)y_end, dense, a, s, r, nt, mp1);
+}
+
+int check(const pmp_problem_t* p, const pmp_opts_t* o) {
+    if (!p) return fail(PMP_ERR_BAD_ARG, "problem is NULL");
+    if (p->system_id < 0 || p->system_id > 2) return fail(PMP_ERR_UNSUPPORTED, "unknown system_id");
+    if (o) {
+        if (!tableau_for(o->method)) return fail(PMP_ERR_UNSUPPORTED, "unknown method");
+        if (o->dtype != PMP_F32 && o->dtype != PMP_F64) return fail(PMP_ERR_BAD_ARG, "bad dtype");
+        if (o->max_steps < 1) return fail(PMP_ERR_BAD_ARG, "max_steps < 1");
+    }
+    return 0;
+}
+
+template <class R, class Sys> void rhs_batch_t(const pmp_problem_t& p, int64_t n, const R* y, R* dy, int mp1) {
+    constexpr int NS = 2 * Sys::NX + 2;
+    Sys sys(p);
+    if constexpr (Sys::NU == 2) sys.model_pass1 = mp1 != 0;
+    for (int64_t i = 0; i < n; i++) {
+        R a[NS], b[NS];
+        for (int q = 0; q < NS; q++) a[q] = y[q * n + i];
+        sys.rhs(a, b);
+        for (int q = 0; q < NS; q++) dy[q * n + i] = b[q];
+    }
+}
+template <class R, class Sys>
+void ustar_batch_t(const pmp_problem_t& p, int64_t n, const R* x, const R* lam, R* u, int mp1) {
+    constexpr int NX = Sys::NX, NU = Sys::NU;
+    Sys sys(p);
+    if constexpr (Sys::NU == 2) sys.model_pass1 = mp1 != 0;
+    for (int64_t i = 0; i < n; i++) {
+        R xx[NX], ll[NX], uu[NU];
+        for (int q = 0; q < NX; q++) { xx[q] = x[q * n + i]; ll[q] = lam[q * n + i]; }
+        sys.ustar(xx, ll, uu);
+        for (int q = 0; q < NU; q++) u[q * n + i] = uu[q];
+    }
+}
+}  // namespace
+
+extern "C" {
+
+const char* pmp_oracle_last_error(void) { return g_err.c_str(); }
+
+int pmp_oracle_num_threads(void) {
+#ifdef _OPENMP
+    return omp_get_max_threads();
+#else
+    return 1;
+#endif
+}
+
+// same contract as pmp_solve_batch_cuda (include/b200pmp.h) with host pointers.
+// n_threads: OpenMP threads (<1 = all).  model_pass1: score u* pass 1 with the quadratic model.
+int pmp_oracle_solve_batch(const pmp_problem_t* p, const pmp_opts_t* o, int64_t n, const void* y_f,
+                           void* y_end, const pmp_dense_t* dense, int32_t* n_accepted,
+                           int32_t* n_steps, int32_t* result, int n_threads, int model_pass1) {
+    if (int e = check(p, o)) return e;
+    if (!o) return fail(PMP_ERR_BAD_ARG, "opts is NULL");
+    if (n < 0 || (n > 0 && (!y_f || !y_end))) return fail(PMP_ERR_BAD_ARG, "bad n / NULL buffers");
+    switch (p->system_id) {
+        case PMP_SYS_FLATQUAD:
+            return solve_dispatch<Flatquad<float>, Flatquad<double>>(*p, *o, n, y_f, y_end, dense, n_accepted, n_steps, result, n_threads, model_pass1);
+        case PMP_SYS_ORBITS:
+            return solve_dispatch<Orbits<float>, Orbits<double>>(*p, *o, n, y_f, y_end, dense, n_accepted, n_steps, result, n_threads, model_pass1);
+        case PMP_SYS_LQR_STATEPENALTY:
+            return solve_dispatch<LqrStatePenalty<float>, LqrStatePenalty<double>>(*p, *o, n, y_f, y_end, dense, n_accepted, n_steps, result, n_threads, model_pass1);
+    }
+    return fail(PMP_ERR_UNSUPPORTED, "unknown system_id");
+}
+
+int pmp_oracle_rhs_batch(const pmp_problem_t* p, int32_t dtype, int64_t n, const void* y, void* dy,
+                         int model_pass1) {
+    if (int e = check(p, nullptr)) return e;
+#define RHS_CASE(SYS)                                                                         \
+    if (dtype == PMP_F32) rhs_batch_t<float, SYS<float>>(*p, n, (const float*)y, (float*)dy, model_pass1); \
+    else rhs_batch_t<double, SYS<double>>(*p, n, (const double*)y, (double*)dy, model_pass1);  \
+    return 0;
+    switch (p->system_id) {
+        case PMP_SYS_FLATQUAD: RHS_CASE(Flatquad)
+        case PMP_SYS_ORBITS: RHS_CASE(Orbits)
+        case PMP_SYS_LQR_STATEPENALTY: RHS_CASE(LqrStatePenalty)
+    }
+#undef RHS_CASE
+    return fail(PMP_ERR_UNSUPPORTED, "unknown system_id");
+}
+
+int pmp_oracle_ustar_batch(const pmp_problem_t* p, int32_t dtype, int64_t n, const void* x,
+                           const void* lam, void* u, int model_pass1) {
+    if (int e = check(p, nullptr)) return e;
+#define US_CASE(SYS)                                                                                  \
+    if (dtype == PMP_F32) ustar_batch_t<float, SYS<float>>(*p, n, (const float*)x, (const float*)lam, (float*)u, model_pass1); \
+    else ustar_batch_t<double, SYS<double>>(*p, n, (const double*)x, (const double*)lam, (double*)u, model_pass1); \
+    return 0;
+    switch (p->system_id) {
+        case PMP_SYS_FLATQUAD: US_CASE(Flatquad)
+        case PMP_SYS_ORBITS: US_CASE(Orbits)
+        case PMP_SYS_LQR_STATEPENALTY: US_CASE(LqrStatePenalty)
+    }
+#undef US_CASE
+    return fail(PMP_ERR_UNSUPPORTED, "unknown system_id");
+}
+
+// Algorithmic work.  out[0..1] = flops, specials of ONE f_extended evaluation
+// (u* scored with the quadratic model, i.e. the cheaper reading of the reference's algorithm);
+// out[2..3] = flops, specials of ONE step attempt of opts->method excluding nothing (stages, RHS
+// evaluations, error estimate, norm, controller); measured by running one attempt on the counting
+// scalar from the state y0 [NS] (doubles).
+int pmp_oracle_opcount(const pmp_problem_t* p, const pmp_opts_t* o, const double* y0, int64_t* out) {
+    if (int e = check(p, o)) return e;
+    auto run = [&](auto sys) {
+        using Sys = decltype(sys);
+        constexpr int NS = 2 * Sys::NX + 2;
+        if constexpr (Sys::NU == 2) sys.model_pass1 = true;
+        Counted y[NS], dy[NS], ye[NS];
+        for (int q = 0; q < NS; q++) y[q] = Counted(y0[q]);
+        op_counts() = OpCounts{};
+        sys.rhs(y, dy);
+        out[0] = op_counts().flops;
+        out[1] = op_counts().special;
+        pmp_opts_t one = *o;
+        one.max_steps = 1;
+        one.save_dense = 0;
+        op_counts() = OpCounts{};
+        solve_one<Counted, Sys>(sys, one, y, ye, DenseSink<Counted>{});
+        // solve_one evaluates the FSAL stage once up front: that RHS is per trajectory, not per attempt
+        out[2] = op_counts().flops - out[0];
+        out[3] = op_counts().special - out[1];
+    };
+    switch (p->system_id) {
+        case PMP_SYS_FLATQUAD: run(Flatquad<Counted>(*p)); return 0;
+        case PMP_SYS_ORBITS: run(Orbits<Counted>(*p)); return 0;
+        case PMP_SYS_LQR_STATEPENALTY: run(LqrStatePenalty<Counted>(*p)); return 0;
+    }
+    return fail(PMP_ERR_UNSUPPORTED, "unknown system_id");
+}
+
+}  // extern "C"

@@ -1,0 +1,614 @@
+// pmp_oracle.hpp -- CPU ORACLE (test infrastructure, NOT product code).
+//
+// A plain, scalar, readable restatement of the reference's PMP backward-shooting path.  Only
+// tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs may use it;
+// nothing under approximate_optimal_control_b200/ includes, links or calls this directory.
+//
+// PARITY STATUS (see DESIGN.md "Oracle"):
+//   * RHS maths (u_star_2d, u_star_new, f_extended): PINNED against the reference's own Python code
+//     executed in the build container through a torch-backed stand-in for jax
+//     (tests/golden/make_golden.py -> tests/golden/rhs_*.npz).
+//   * Converged trajectories: PINNED against scipy.integrate.solve_ivp(DOP853, rtol=1e-12) driven by
+//     the reference's own f_extended (tests/golden/traj_*.npz) and against the analytic LQR
+//     expm known answer.
+//   * Adaptive step control (accept/reject sequence): diffrax 0.4.1 is an un-vendored dependency
+//     (requirements.txt:10) that cannot be installed offline and the reference holds no golden
+//     vectors for it => the control-flow restatement below is PARITY UNPINNED.
+//
+// Everything is templated on the scalar type R so that the same code runs in float, double and on
+// the op-counting scalar of opcount.hpp (the algorithmic-flop contract of SURVEY.md section 8(d)).
+#pragma once
+#include <cmath>
+#include <cstdint>
+#include <limits>
+#include <type_traits>
+
+#include "../include/b200pmp.h"
+
+namespace pmpo {
+
+// ---- scalar helpers (overloaded for the counting scalar in opcount.hpp) -------------------------
+inline float r_sin(float x) { return std::sin(x); }
+inline double r_sin(double x) { return std::sin(x); }
+inline float r_cos(float x) { return std::cos(x); }
+inline double r_cos(double x) { return std::cos(x); }
+inline float r_sqrt(float x) { return std::sqrt(x); }
+inline double r_sqrt(double x) { return std::sqrt(x); }
+inline float r_pow(float x, float y) { return std::pow(x, y); }
+inline double r_pow(double x, double y) { return std::pow(x, y); }
+inline float r_abs(float x) { return std::fabs(x); }
+inline double r_abs(double x) { return std::fabs(x); }
+inline bool r_isnan(float x) { return std::isnan(x); }
+inline bool r_isnan(double x) { return std::isnan(x); }
+inline double r_val(float x) { return x; }
+inline double r_val(double x) { return x; }
+// NaN-propagating max/min like jnp.maximum / jnp.minimum
+template <class R> inline R r_max(R a, R b) {
+    if (r_isnan(a)) return a;
+    if (r_isnan(b)) return b;
+    return r_val(a) > r_val(b) ? a : b;
+}
+template <class R> inline R r_min(R a, R b) {
+    if (r_isnan(a)) return a;
+    if (r_isnan(b)) return b;
+    return r_val(a) < r_val(b) ? a : b;
+}
+template <class R> inline R r_clip(R x, R lo, R hi) { return r_min(r_max(x, lo), hi); }
+template <class R> inline R r_inf() { return R(std::numeric_limits<double>::infinity()); }
+template <class R> inline R r_nan() { return R(std::numeric_limits<double>::quiet_NaN()); }
+
+// =================================================================================================
+// Systems.  Each supplies f, l, dH/dx (u held fixed), and u* = argmin_u H.
+// =================================================================================================
+
+// ---- flat (planar) quadrotor: flatquad_landing_experiment.py:269-329 ----------------------------
+// Quantities that do not depend on (x, lambda) -- 1/m, r/I, the constant Hessian H_uu, its inverse,
+// the box vertices and per-edge constants -- are folded in the constructor, as a compiler would do
+// for the reference's jitted code, so that the op-counting instantiation reports the per-call work
+// only ("H_uu and vertex constants folded").
+template <class R> struct Flatquad {
+    static constexpr int NX = 6, NU = 2;
+    R m, g, r, I, q_pos, q_ang, q_vel, q_om;
+    R ulo[2], uhi[2];
+    bool model_pass1 = false;  // score pass 1 with the quadratic model instead of the true H
+    // folded constants
+    R inv_m, r_I, two_g_m, two_g, two_qpos, two_qang, two_qvel, two_qom;
+    R Huu[2][2], Hinv[2][2], half_h00, half_h11;
+    R hull[4][2];
+    int edge_axis[4];   // the coordinate that moves along edge k (a-b has one non-zero entry)
+    R edge_g[4];        // (b' H_uu)[axis]
+    R edge_d[4];        // (a-b)[axis]
+    R edge_inv_den[4];  // 1 / ((a-b)' H_uu (a-b))
+
+    explicit Flatquad(const pmp_problem_t& p) {
+        m = R(p.params[0]); g = R(p.params[1]); r = R(p.params[2]); I = R(p.params[3]);
+        q_pos = R(p.params[4]); q_ang = R(p.params[5]); q_vel = R(p.params[6]); q_om = R(p.params[7]);
+        for (int i = 0; i < 2; i++) { ulo[i] = R(p.u_lo[i]); uhi[i] = R(p.u_hi[i]); }
+        inv_m = R(1) / m; r_I = r / I; two_g = R(2) * g; two_g_m = two_g / m;
+        two_qpos = R(2) * q_pos; two_qang = R(2) * q_ang; two_qvel = R(2) * q_vel; two_qom = R(2) * q_om;
+        // H_uu = d^2/du^2 (ax^2+ay^2+aw^2) = 2 [[1/m^2+r^2/I^2, 1/m^2-r^2/I^2],[.,.]]  (constant)
+        R d = R(2) * (inv_m * inv_m + r_I * r_I), o = R(2) * (inv_m * inv_m - r_I * r_I);
+        Huu[0][0] = d; Huu[0][1] = o; Huu[1][0] = o; Huu[1][1] = d;
+        R det = d * d - o * o;
+        Hinv[0][0] = d / det; Hinv[0][1] = -o / det; Hinv[1][0] = -o / det; Hinv[1][1] = d / det;
+        half_h00 = R(0.5) * d; half_h11 = R(0.5) * d;
+        // pontryagin_utils.py:78-86 box vertices; edge k = (a = vertex k, b = vertex k-1)
+        R h[4][2] = {{ulo[0], ulo[1]}, {ulo[0], uhi[1]}, {uhi[0], uhi[1]}, {uhi[0], ulo[1]}};
+        for (int k = 0; k < 4; k++) { hull[k][0] = h[k][0]; hull[k][1] = h[k][1]; }
+        for (int k = 0; k < 4; k++) {
+            const R* a = hull[k];
+            const R* b = hull[(k + 3) % 4];
+            int ax = (r_val(a[0]) != r_val(b[0])) ? 0 : 1;
+            edge_axis[k] = ax;
+            edge_d[k] = a[ax] - b[ax];
+            edge_g[k] = b[0] * Huu[0][ax] + b[1] * Huu[1][ax];
+            edge_inv_den[k] = R(1) / (edge_d[k] * Huu[ax][ax] * edge_d[k]);
+        }
+    }
+
+    // xdot = f(x,u)                                  flatquad_landing_experiment.py:277-292
+    void f(const R* x, const R* u, R* xd) const {
+        R s = r_sin(x[2]), c = r_cos(x[2]);
+        f_sc(x, u, s, c, xd);
+    }
+    void f_sc(const R* x, const R* u, R s, R c, R* xd) const {
+        R Sm = (u[0] + u[1]) * inv_m;
+        xd[0] = x[3];
+        xd[1] = x[4];
+        xd[2] = x[5];
+        xd[3] = -(s * Sm);
+        xd[4] = c * Sm - g;
+        xd[5] = (u[1] - u[0]) * r_I;
+    }
+    // running cost l(x,u)                            flatquad_landing_experiment.py:294-329
+    // state cost on (px,py,cos,sin,vx,vy,omega) minus its value at 0, diagonal Q = 1/scale^2;
+    // input cost = |accelerations|^2.
+    R l(const R* x, const R* u) const {
+        R s = r_sin(x[2]), c = r_cos(x[2]);
+        R xd[6];
+        f_sc(x, u, s, c, xd);
+        return l_acc(x, s, c, xd[3], xd[4], xd[5]);
+    }
+    R l_acc(const R* x, R s, R c, R ax, R ay, R aw) const {
+        R cm1 = c - R(1);
+        R state_cost = q_pos * (x[0] * x[0] + x[1] * x[1]) + q_ang * (cm1 * cm1 + s * s) +
+                       q_vel * (x[3] * x[3] + x[4] * x[4]) + q_om * (x[5] * x[5]);
+        return state_cost + (ax * ax + ay * ay + aw * aw);
+    }
+    // dH/dx at fixed u, H = l + lam.f                pontryagin_utils.py:430,439 (hand-derived;
+    // checked against the reference's autodiff by tests/golden/rhs_flatquad_*.npz)
+    void dHdx_sm(const R* x, const R* lam, R s, R c, R Sm, R* hx) const {
+        hx[0] = two_qpos * x[0];
+        hx[1] = two_qpos * x[1];
+        hx[2] = s * (two_qang + two_g * Sm) - Sm * (lam[3] * c + lam[4] * s);
+        hx[3] = two_qvel * x[3] + lam[0];
+        hx[4] = two_qvel * x[4] + lam[1];
+        hx[5] = two_qom * x[5] + lam[2];
+    }
+    // gradient of H in u at u=0                      pontryagin_utils.py:37
+    void hu0(const R* lam, R s, R c, R* Hu) const {
+        R base = (lam[4] * c - lam[3] * s) * inv_m - two_g_m * c;
+        R rot = lam[5] * r_I;
+        Hu[0] = base - rot;
+        Hu[1] = base + rot;
+    }
+    // 1/2 w'H_uu w + gvec'w in 9 flops
+    R quad(R w0, R w1, R g0, R g1) const {
+        return w0 * (half_h00 * w0 + Huu[0][1] * w1 + g0) + w1 * (half_h11 * w1 + g1);
+    }
+
+    // u_star_2d(x, costate, problem_params, smooth=False)     pontryagin_utils.py:11-216
+    void ustar(const R* x, const R* lam, R* u) const {
+        R s = r_sin(x[2]), c = r_cos(x[2]);
+        ustar_sc(x, lam, s, c, u);
+    }
+    void ustar_sc(const R* x, const R* lam, R s, R c, R* u) const {
+        R Hu[2];
+        hu0(lam, s, c, Hu);
+        R cand[5][2];
+        // :41  unconstrained minimiser solve(H_uu, -H_u)
+        cand[0][0] = -(Hinv[0][0] * Hu[0] + Hinv[0][1] * Hu[1]);
+        cand[0][1] = -(Hinv[1][0] * Hu[0] + Hinv[1][1] * Hu[1]);
+        // :53-75,86  minimiser along each box edge {s a + (1-s) b}:
+        //   s = -(H_u + b'H_uu)(a-b) / ((a-b)'H_uu(a-b)), clipped to [0,1]
+        for (int k = 0; k < 4; k++) {
+            const R* a = hull[k];
+            const R* b = hull[(k + 3) % 4];
+            const int ax = edge_axis[k];
+            R sc = r_clip(-((Hu[ax] + edge_g[k]) * edge_d[k]) * edge_inv_den[k], R(0), R(1));
+            cand[k + 1][ax] = sc * a[ax] + (R(1) - sc) * b[ax];
+            cand[k + 1][1 - ax] = a[1 - ax];
+        }
+        // :129  is the unconstrained candidate outside the box?  (NaN compares false => "inside")
+        R viol = r_max(r_max(ulo[0] - cand[0][0], ulo[1] - cand[0][1]),
+                       r_max(cand[0][0] - uhi[0], cand[0][1] - uhi[1]));
+        bool outside = r_val(viol) > 0;
+        // :88-90  score ALL five candidates (the reference vmaps H over them, no branching)
+        R Hs[5];
+        for (int k = 0; k < 5; k++) {
+            if (model_pass1) {  // quadratic model, constant term dropped (equal by assumption, :34)
+                Hs[k] = quad(cand[k][0], cand[k][1], Hu[0], Hu[1]);
+            } else {  // :35,90 the true H(u) = l(x,u) + lam.f(x,u)
+                R xd[6];
+                f_sc(x, cand[k], s, c, xd);
+                R h = l_acc(x, s, c, xd[3], xd[4], xd[5]);
+                for (int i = 0; i < 6; i++) h = h + lam[i] * xd[i];
+                Hs[k] = h;
+            }
+        }
+        // :131-135  penalty = outside*inf is +inf when outside and NaN (False*inf) when inside;
+        // argmin returns the NaN slot => inside: candidate 0 wins unconditionally; outside: best edge
+        const R penalty = outside ? r_inf<R>() : r_nan<R>();
+        Hs[0] = Hs[0] + penalty;
+        int best = argmin5(Hs);
+        // :151-158 second pass: re-expand about the winner, compare suboptimalities
+        R us0 = cand[best][0], us1 = cand[best][1];
+        R hn0 = Huu[0][0] * us0 + Huu[0][1] * us1 + Hu[0];
+        R hn1 = Huu[1][0] * us0 + Huu[1][1] * us1 + Hu[1];
+        for (int k = 0; k < 5; k++) Hs[k] = quad(cand[k][0] - us0, cand[k][1] - us1, hn0, hn1);
+        Hs[0] = Hs[0] + penalty;
+        best = argmin5(Hs);
+        u[0] = cand[best][0];
+        u[1] = cand[best][1];
+    }
+    // numpy/jax argmin: the first NaN wins, else the first minimum
+    static int argmin5(const R* Hs) {
+        for (int k = 0; k < 5; k++)
+            if (r_isnan(Hs[k])) return k;
+        int best = 0;
+        for (int k = 1; k < 5; k++)
+            if (r_val(Hs[k]) < r_val(Hs[best])) best = k;
+        return best;
+    }
+
+    // f_extended, forward time                       pontryagin_utils.py:418-458
+    // (u* is computed once; the reference traces it twice, :435 and :446, with identical inputs)
+    void rhs(const R* y, R* dy) const {
+        const R* x = y;
+        const R* lam = y + NX + 2;
+        R s = r_sin(x[2]), c = r_cos(x[2]);
+        R u[2];
+        ustar_sc(x, lam, s, c, u);
+        R Sm = (u[0] + u[1]) * inv_m;
+        R ax = -(s * Sm), ay = c * Sm - g, aw = (u[1] - u[0]) * r_I;
+        dy[0] = x[3]; dy[1] = x[4]; dy[2] = x[5]; dy[3] = ax; dy[4] = ay; dy[5] = aw;
+        dy[NX] = R(1);
+        dy[NX + 1] = -l_acc(x, s, c, ax, ay, aw);
+        R hx[6];
+        dHdx_sm(x, lam, s, c, Sm, hx);
+        for (int i = 0; i < NX; i++) dy[NX + 2 + i] = -hx[i];
+    }
+    R running_cost(const R* y) const {
+        const R* x = y;
+        const R* lam = y + NX + 2;
+        R u[2];
+        ustar(x, lam, u);
+        return l(x, u);
+    }
+};
+
+// ---- "orbits" toy system: experiment_orbits.py:24-40 --------------------------------------------
+template <class R> struct Orbits {
+    static constexpr int NX = 2, NU = 1;
+    R w_dist, w_u, ulo, uhi;
+    explicit Orbits(const pmp_problem_t& p) {
+        w_dist = R(p.params[0]); w_u = R(p.params[1]);
+        ulo = R(p.u_lo[0]); uhi = R(p.u_hi[0]);
+    }
+    // f = [[u,-rho],[rho,u]] x, rho = |x|^2-1       experiment_orbits.py:24-30
+    void f(const R* x, const R* u, R* xd) const {
+        R rho = x[0] * x[0] + x[1] * x[1] - R(1);
+        xd[0] = u[0] * x[0] - rho * x[1];
+        xd[1] = rho * x[0] + u[0] * x[1];
+    }
+    // l = rho^2 + 0.1 |x-(0,1)|^2 + 10 u^2          experiment_orbits.py:33-40
+    R l(const R* x, const R* u) const {
+        R rho = x[0] * x[0] + x[1] * x[1] - R(1);
+        R e1 = x[1] - R(1);
+        return rho * rho + w_dist * (x[0] * x[0] + e1 * e1) + w_u * (u[0] * u[0]);
+    }
+    void dHdx(const R* x, const R* u, const R* lam, R* hx) const {
+        R rho = x[0] * x[0] + x[1] * x[1] - R(1);
+        R e1 = x[1] - R(1);
+        // d rho / dx = 2x
+        hx[0] = R(4) * rho * x[0] + R(2) * w_dist * x[0] + lam[0] * (u[0] - R(2) * x[0] * x[1]) +
+                lam[1] * (rho + R(2) * x[0] * x[0]);
+        hx[1] = R(4) * rho * x[1] + R(2) * w_dist * e1 + lam[0] * (-rho - R(2) * x[1] * x[1]) +
+                lam[1] * (R(2) * x[0] * x[1] + u[0]);
+    }
+    // u_star_new: clip(solve(R+R', -lam' df/du), U)  pontryagin_utils.py:532-562, df/du = x
+    void ustar(const R* x, const R* lam, R* u) const {
+        R un = -(lam[0] * x[0] + lam[1] * x[1]) / (R(2) * w_u);
+        u[0] = r_clip(un, ulo, uhi);
+    }
+    void rhs(const R* y, R* dy) const {
+        const R* x = y;
+        const R* lam = y + NX + 2;
+        R u[1];
+        ustar(x, lam, u);
+        f(x, u, dy);
+        dy[NX] = R(1);
+        dy[NX + 1] = -l(x, u);
+        R hx[2];
+        dHdx(x, u, lam, hx);
+        for (int i = 0; i < NX; i++) dy[NX + 2 + i] = -hx[i];
+    }
+    R running_cost(const R* y) const {
+        R u[1];
+        ustar(y, y + NX + 2, u);
+        return l(y, u);
+    }
+};
+
+// ---- double integrator with soft state constraints: experiment_lqr_statepenalty.py:23-38 --------
+template <class R> struct LqrStatePenalty {
+    static constexpr int NX = 2, NU = 1;
+    R a, r_u, ulo, uhi;
+    explicit LqrStatePenalty(const pmp_problem_t& p) {
+        a = R(p.params[0]); r_u = R(p.params[1]);
+        ulo = R(p.u_lo[0]); uhi = R(p.u_hi[0]);
+    }
+    void f(const R* x, const R* u, R* xd) const {  // :23-28
+        xd[0] = x[1];
+        xd[1] = u[0];
+    }
+    R l(const R* x, const R* u) const {  // :30-38
+        R z1 = r_max(R(0), x[1] - R(1));
+        R z0 = r_max(R(0), x[0] - R(1));
+        return (x[0] * x[0] + x[1] * x[1]) + r_u * (u[0] * u[0]) + (z1 * z1 / a + z0 * z0 / a);
+    }
+    void dHdx(const R* x, const R* u, const R* lam, R* hx) const {
+        (void)u;
+        R z1 = r_max(R(0), x[1] - R(1));
+        R z0 = r_max(R(0), x[0] - R(1));
+        hx[0] = R(2) * x[0] + R(2) * z0 / a;
+        hx[1] = R(2) * x[1] + R(2) * z1 / a + lam[0];
+    }
+    void ustar(const R* x, const R* lam, R* u) const {  // df/du = (0,1)
+        (void)x;
+        u[0] = r_clip(-lam[1] / (R(2) * r_u), ulo, uhi);
+    }
+    void rhs(const R* y, R* dy) const {
+        const R* x = y;
+        const R* lam = y + NX + 2;
+        R u[1];
+        ustar(x, lam, u);
+        f(x, u, dy);
+        dy[NX] = R(1);
+        dy[NX + 1] = -l(x, u);
+        R hx[2];
+        dHdx(x, u, lam, hx);
+        for (int i = 0; i < NX; i++) dy[NX + 2 + i] = -hx[i];
+    }
+    R running_cost(const R* y) const {
+        R u[1];
+        ustar(y, y + NX + 2, u);
+        return l(y, u);
+    }
+};
+
+// =================================================================================================
+// Butcher tableaus (explicit RK, optional embedded error estimate, optional FSAL)
+// =================================================================================================
+struct Tableau {
+    int stages;
+    int order;
+    bool fsal;      // last stage is evaluated at y1 and reused as the first stage of the next step
+    bool embedded;  // has an error estimate
+    double c[7];
+    double a[7][7];
+    double b[7];
+    double berr[7];  // b - bhat
+};
+
+// diffrax.Tsit5 (Tsitouras 2011); constants as listed in SURVEY.md section 8(c)
+inline const Tableau& tsit5() {
+    static const Tableau t = [] {
+        Tableau q{};
+        q.stages = 7; q.order = 5; q.fsal = true; q.embedded = true;
+        const double c[7] = {0, 0.161, 0.327, 0.9, 0.9800255409045097, 1, 1};
+        const double b[7] = {0.09646076681806523, 0.01, 0.4798896504144996, 1.379008574103742,
+                             -3.290069515436081, 2.324710524099774, 0.0};
+        const double bh[7] = {0.09468075576583945, 0.009183565540343254, 0.4877705284247616,
+                              1.234297566930479, -2.707712349983526, 1.866628418170587, 1.0 / 66.0};
+        const double a[7][7] = {
+            {0},
+            {0.161},
+            {-0.008480655492356992, 0.3354806554923570},
+            {2.897153057105494, -6.359448489975075, 4.362295432869581},
+            {5.325864828439259, -11.74888356406283, 7.495539342889836, -0.09249506636175525},
+            {5.861455442946420, -12.92096931784711, 8.159367898576159, -0.07158497328140100,
+             -0.02826905039406838},
+            {0.09646076681806523, 0.01, 0.4798896504144996, 1.379008574103742, -3.290069515436081,
+             2.324710524099774}};
+        for (int i = 0; i < 7; i++) {
+            q.c[i] = c[i]; q.b[i] = b[i]; q.berr[i] = b[i] - bh[i];
+            for (int j = 0; j < 7; j++) q.a[i][j] = a[i][j];
+        }
+        return q;
+    }();
+    return t;
+}
+
+// Dormand-Prince 5(4)
+inline const Tableau& dopri5() {
+    static const Tableau t = [] {
+        Tableau q{};
+        q.stages = 7; q.order = 5; q.fsal = true; q.embedded = true;
+        const double c[7] = {0, 1.0 / 5, 3.0 / 10, 4.0 / 5, 8.0 / 9, 1, 1};
+        const double b[7] = {35.0 / 384, 0, 500.0 / 1113, 125.0 / 192, -2187.0 / 6784, 11.0 / 84, 0};
+        const double bh[7] = {5179.0 / 57600, 0, 7571.0 / 16695, 393.0 / 640, -92097.0 / 339200,
+                              187.0 / 2100, 1.0 / 40};
+        const double a[7][7] = {
+            {0},
+            {1.0 / 5},
+            {3.0 / 40, 9.0 / 40},
+            {44.0 / 45, -56.0 / 15, 32.0 / 9},
+            {19372.0 / 6561, -25360.0 / 2187, 64448.0 / 6561, -212.0 / 729},
+            {9017.0 / 3168, -355.0 / 33, 46732.0 / 5247, 49.0 / 176, -5103.0 / 18656},
+            {35.0 / 384, 0, 500.0 / 1113, 125.0 / 192, -2187.0 / 6784, 11.0 / 84}};
+        for (int i = 0; i < 7; i++) {
+            q.c[i] = c[i]; q.b[i] = b[i]; q.berr[i] = b[i] - bh[i];
+            for (int j = 0; j < 7; j++) q.a[i][j] = a[i][j];
+        }
+        return q;
+    }();
+    return t;
+}
+
+// classic RK4
+inline const Tableau& rk4() {
+    static const Tableau t = [] {
+        Tableau q{};
+        q.stages = 4; q.order = 4; q.fsal = false; q.embedded = false;
+        q.c[1] = 0.5; q.c[2] = 0.5; q.c[3] = 1.0;
+        q.a[1][0] = 0.5; q.a[2][1] = 0.5; q.a[3][2] = 1.0;
+        q.b[0] = 1.0 / 6; q.b[1] = 1.0 / 3; q.b[2] = 1.0 / 3; q.b[3] = 1.0 / 6;
+        return q;
+    }();
+    return t;
+}
+
+inline const Tableau* tableau_for(int method) {
+    switch (method) {
+        case PMP_METHOD_RK4: return &rk4();
+        case PMP_METHOD_TSIT5: return &tsit5();
+        case PMP_METHOD_DOPRI5: return &dopri5();
+    }
+    return nullptr;
+}
+
+// =================================================================================================
+// One trajectory.  Restates diffrax.diffeqsolve(ODETerm(f_extended), Tsit5(), t0, t1, dt0, y0,
+// PIDController(rtol, atol, dtmin, dtmax), SaveAt(steps=True, t0=True), max_steps, throw=False)
+// as called at pontryagin_utils.py:492-525, with diffrax 0.4.1 semantics.
+// =================================================================================================
+template <class R> struct DenseSink {  // one trajectory's rows of the dense buffers (may be null)
+    R* ts = nullptr; R* x = nullptr; R* t = nullptr; R* v = nullptr; R* vx = nullptr;
+};
+
+struct TrajStats {
+    int32_t n_accepted = 0, n_steps = 0, result = 0;
+};
+
+template <class R, class Sys>
+TrajStats solve_one(const Sys& sys, const pmp_opts_t& o, const R* y_f, R* y_end, DenseSink<R> sink) {
+    constexpr int NX = Sys::NX, NS = 2 * NX + 2, IT = NX, IV = NX + 1;
+    const Tableau& tb = *tableau_for(o.method);
+    const bool value_mode = o.indep == PMP_INDEP_VALUE;
+    const int S1 = o.max_steps + 1;
+    const R inf = r_inf<R>();
+    TrajStats st;
+
+    R y[NS];
+    for (int i = 0; i < NS; i++) y[i] = y_f[i];
+
+    // time reversal: integrate tau = dir*t forward, vector field multiplied by dir
+    const double t_start = value_mode ? double(r_val(y[IV])) : o.t0;
+    const R dir = (t_start < o.t1) ? R(1) : R(-1);
+    const R T0 = R(t_start) * dir, T1 = R(o.t1) * dir;
+    R tprev = T0;
+    R tnext = r_min(T0 + R(o.dt0) * dir, T1);
+    const R clip_tol = std::is_same<R, float>::value ? R(1e-6) : R(1e-10);  // integrate.py _clip_to_end
+
+    auto save = [&](int slot, R tnow) {
+        if (slot >= S1) return;
+        if (sink.ts) sink.ts[slot] = tnow * dir;
+        if (sink.x) for (int i = 0; i < NX; i++) sink.x[slot * NX + i] = y[i];
+        if (sink.t) sink.t[slot] = y[IT];
+        if (sink.v) sink.v[slot] = y[IV];
+        if (sink.vx) for (int i = 0; i < NX; i++) sink.vx[slot * NX + i] = y[NX + 2 + i];
+    };
+    auto pad = [&](int from) {
+        for (int slot = from; slot < S1; slot++) {
+            if (sink.ts) sink.ts[slot] = inf * dir;
+            if (sink.x) for (int i = 0; i < NX; i++) sink.x[slot * NX + i] = inf;
+            if (sink.t) sink.t[slot] = inf;
+            if (sink.v) sink.v[slot] = inf;
+            if (sink.vx) for (int i = 0; i < NX; i++) sink.vx[slot * NX + i] = inf;
+        }
+    };
+    // internal-time vector field.  time mode: dir * f_extended.  value mode: the same field divided
+    // by dv/dtau so that v advances at unit rate (experiment_orbits.py:109-111).
+    auto field = [&](const R* yy, R* k) {
+        sys.rhs(yy, k);
+        if (value_mode) {
+            R vdot = k[IV];  // dv/dt = -l: dy/dv = (dy/dt) / (dv/dt)
+            for (int i = 0; i < NS; i++) k[i] = dir * (k[i] / vdot);
+            k[IV] = dir;
+        } else {
+            for (int i = 0; i < NS; i++) k[i] = dir * k[i];
+        }
+    };
+
+    save(0, tprev);
+    bool bad0 = false;
+    for (int i = 0; i < NS; i++) bad0 = bad0 || r_isnan(y[i]);
+    if (bad0) {  // NaN terminal state (levelsets.py:1233): retire at once (DESIGN.md "NaN lanes")
+        st.result = PMP_RESULT_NAN;
+        for (int i = 0; i < NS; i++) y_end[i] = y[i];
+        pad(1);
+        return st;
+    }
+
+    R k[7][NS];
+    field(y, k[0]);
+    bool at_dtmin = false;
+
+    while (r_val(tprev) < r_val(T1) && st.result == 0 && st.n_steps < o.max_steps) {
+        const R dt = tnext - tprev;
+        R ys[NS], y1[NS], yerr[NS];
+        const int last = tb.stages - 1;
+        for (int i = 1; i < tb.stages; i++) {
+            for (int q = 0; q < NS; q++) {
+                R acc = R(tb.a[i][0]) * k[0][q];
+                for (int j = 1; j < i; j++) acc = acc + R(tb.a[i][j]) * k[j][q];
+                ys[q] = y[q] + dt * acc;
+            }
+            field(ys, k[i]);
+            if (tb.fsal && i == last)
+                for (int q = 0; q < NS; q++) y1[q] = ys[q];
+        }
+        if (!tb.fsal) {
+            for (int q = 0; q < NS; q++) {
+                R acc = R(tb.b[0]) * k[0][q];
+                for (int j = 1; j < tb.stages; j++) acc = acc + R(tb.b[j]) * k[j][q];
+                y1[q] = y[q] + dt * acc;
+            }
+        }
+        bool keep = true;
+        R next_t0, next_t1;
+        if (o.adaptive && tb.embedded) {
+            for (int q = 0; q < NS; q++) {
+                R acc = R(tb.berr[0]) * k[0][q];
+                for (int j = 1; j < tb.stages; j++) acc = acc + R(tb.berr[j]) * k[j][q];
+                yerr[q] = dt * acc;
+                if (r_isnan(yerr[q])) yerr[q] = inf;  // integrate.py: nan error -> inf
+            }
+            // per-leaf NaN guard of the scale (leaves: x, t, v, vx)
+            auto leaf_of = [&](int q) { return q < NX ? 0 : (q == IT ? 1 : (q == IV ? 2 : 3)); };
+            bool leaf_nan[4] = {false, false, false, false};
+            for (int q = 0; q < NS; q++) leaf_nan[leaf_of(q)] = leaf_nan[leaf_of(q)] || r_isnan(y1[q]);
+            R sumsq = R(0);
+            // value mode: the missing solver's state was y=[x, lambda, t] (rrt_sampler.py:62), v is
+            // the independent variable and not a leaf of the error norm
+            const int n_norm = value_mode ? NS - 1 : NS;
+            for (int q = 0; q < NS; q++) {
+                if (value_mode && q == IV) continue;
+                R y1c = leaf_nan[leaf_of(q)] ? y[q] : y1[q];
+                R sc = R(o.atol) + r_max(r_abs(y[q]), r_abs(y1c)) * R(o.rtol);
+                R e = yerr[q] / sc;
+                sumsq = sumsq + e * e;
+            }
+            R scaled = r_sqrt(sumsq / R(n_norm));  // rms_norm over the whole pytree (incl. the t leaf)
+            keep = (r_val(scaled) < 1.0) || at_dtmin;
+            R inv = R(1) / scaled;
+            R factor = R(o.safety) * r_pow(inv, R(1.0 / tb.order));
+            R fmin = keep ? R(1) : R(o.factormin);
+            factor = r_clip(factor, fmin, R(o.factormax));
+            R dtn = (tnext - tprev) * factor;
+            if (o.dtmax > 0) dtn = r_min(dtn, R(o.dtmax));
+            if (o.dtmin > 0) {
+                if (!o.force_dtmin && r_val(dtn) < o.dtmin) st.result = PMP_RESULT_DT_MIN;
+                at_dtmin = r_val(dtn) <= o.dtmin;
+                dtn = r_max(dtn, R(o.dtmin));
+            } else {
+                at_dtmin = false;
+            }
+            next_t0 = keep ? tnext : tprev;
+            next_t1 = next_t0 + dtn;
+        } else {  // ConstantStepSize: next interval has the same length as the last one
+            next_t0 = tnext;
+            next_t1 = tnext + (tnext - tprev);
+        }
+        // integrate.py: tprev = min(tprev, t1); tnext = _clip_to_end(tprev, tnext, t1, keep_step)
+        tprev = r_min(next_t0, T1);
+        if (r_val(next_t1) > r_val(T1 - clip_tol))
+            next_t1 = keep ? T1 : tprev + R(0.5) * (T1 - tprev);
+        tnext = next_t1;
+
+        if (keep) {
+            for (int q = 0; q < NS; q++) y[q] = y1[q];
+            if (tb.fsal) for (int q = 0; q < NS; q++) k[0][q] = k[last][q];
+            else field(y, k[0]);
+        }
+        st.n_steps += 1;
+        if (keep) {
+            st.n_accepted += 1;
+            save(st.n_accepted, tprev);
+        }
+        if (st.result == 0 && o.event == PMP_EVENT_VALUE_GE && r_val(y[IV]) >= o.event_level)
+            st.result = PMP_RESULT_EVENT;
+        if (keep && st.result == 0) {
+            bool bad = r_isnan(tnext);
+            for (int q = 0; q < NS; q++) bad = bad || r_isnan(y[q]);
+            if (bad) st.result = PMP_RESULT_NAN;  // diffrax would idle to max_steps; we retire
+        }
+    }
+    if (st.result == 0 && r_val(tprev) < r_val(T1)) st.result = PMP_RESULT_MAX_STEPS;
+    for (int i = 0; i < NS; i++) y_end[i] = y[i];
+    pad(st.n_accepted + 1);
+    return st;
+}
+
+}  // namespace pmpo
