@@ -215,14 +215,19 @@ solve_kernel(const typename Sys::Consts sc, const SolveOpts<R> o, const SolveIO<
             R ys[ND];
             const bool last_fsal = TB::FSAL && i == S - 1;
 #pragma unroll
+            // ys = y + sum_j (h a_ij) k_j : i scalar products, then i FMAs per component
+            R ha[S];
+#pragma unroll
+            for (int j = 0; j < i; j++) ha[j] = h * R(TB::a(i, j));
+#pragma unroll
             for (int q = 0; q < ND; q++) {
                 // the field does not depend on the aux scalar: skip it for intermediate stages
                 if (q == AUX && !last_fsal) { ys[q] = y[q]; continue; }
-                R acc = R(TB::a(i, 0)) * k[0][q];
+                R acc = y[q];
 #pragma unroll
-                for (int j = 1; j < i; j++)
-                    if (TB::a(i, j) != 0.0) acc = M::fma(R(TB::a(i, j)), k[j][q], acc);
-                ys[q] = M::fma(h, acc, y[q]);
+                for (int j = 0; j < i; j++)
+                    if (TB::a(i, j) != 0.0) acc = M::fma(ha[j], k[j][q], acc);
+                ys[q] = acc;
             }
             field<Sys, R, VALUE, true>(sc, ys, k[i]);
             if (last_fsal) {
@@ -231,35 +236,46 @@ solve_kernel(const typename Sys::Consts sc, const SolveOpts<R> o, const SolveIO<
             }
         }
         if (!TB::FSAL) {
+            R hb[S];
+#pragma unroll
+            for (int j = 0; j < S; j++) hb[j] = h * R(TB::b(j));
 #pragma unroll
             for (int q = 0; q < ND; q++) {
-                R acc = R(TB::b(0)) * k[0][q];
+                R acc = y[q];
 #pragma unroll
-                for (int j = 1; j < S; j++)
-                    if (TB::b(j) != 0.0) acc = M::fma(R(TB::b(j)), k[j][q], acc);
-                y1[q] = M::fma(h, acc, y[q]);
+                for (int j = 0; j < S; j++)
+                    if (TB::b(j) != 0.0) acc = M::fma(hb[j], k[j][q], acc);
+                y1[q] = acc;
             }
         }
 
         // ---- error estimate + I-controller (diffrax PIDController, pcoeff=dcoeff=0) --------------
         bool keep = true;
+        // an ACCEPTED step (force-accept at dtmin) whose scaled error is not finite means the state
+        // has left the representable range / turned NaN: the trajectory retires with result 4
+        bool step_nonfinite = false;
         R next_t0, next_t1;
         if (TB::EMBEDDED && o.adaptive) {
             R sumsq = R(0);
+            R he[S];
+#pragma unroll
+            for (int j = 0; j < S; j++) he[j] = h * R(TB::berr(j));
 #pragma unroll
             for (int q = 0; q < ND; q++) {
-                R acc = R(TB::berr(0)) * k[0][q];
+                R e = he[0] * k[0][q];
 #pragma unroll
                 for (int j = 1; j < S; j++)
-                    if (TB::berr(j) != 0.0) acc = M::fma(R(TB::berr(j)), k[j][q], acc);
-                R e = h * acc;
-                e = (e != e) ? M::inf() : e;  // integrate.py: NaN error -> inf (=> reject, shrink)
+                    if (TB::berr(j) != 0.0) e = M::fma(he[j], k[j][q], e);
                 // scale = atol + rtol*max(|y0|,|y1|); fmax drops a NaN y1 (diffrax substitutes y0)
                 const R scale = M::fma(o.rtol, M::max(M::abs(y[q]), M::abs(y1[q])), o.atol);
-                const R ratio = M::div(e, scale);
+                const R ratio = M::ctl_div(e, scale);
                 sumsq = M::fma(ratio, ratio, sumsq);
             }
+            // integrate.py maps a NaN error estimate to +inf (=> reject, shrink by factormin); a NaN
+            // in any component makes the whole sum NaN, so one test on the sum is equivalent
+            sumsq = (sumsq != sumsq) ? M::inf() : sumsq;
             const R msq = sumsq * inv_nleaf;  // scaled_error^2 (rms_norm over all leaves)
+            step_nonfinite = !(msq < M::inf());
             keep = (msq < R(1)) || at_dtmin;
             // factor = clip(safety * scaled_error^(-1/order), keep ? 1 : factormin, factormax)
             R factor = o.safety * M::pow_neg_inv(msq, R(0.5) * o.inv_order);
@@ -290,11 +306,11 @@ solve_kernel(const typename Sys::Consts sc, const SolveOpts<R> o, const SolveIO<
             bool nan_state = false;
             if (keep) {
                 nacc += 1;
-                bool bad = false;
+                bool bad = step_nonfinite;
 #pragma unroll
                 for (int q = 0; q < ND; q++) {
                     y[q] = y1[q];
-                    bad = bad || (y1[q] != y1[q]);
+                    if (!(TB::EMBEDDED)) bad = bad || (y1[q] != y1[q]);
                     if (TB::FSAL) k[0][q] = k[S - 1][q];
                 }
                 if (DENSE && nacc < S1) {

@@ -46,8 +46,9 @@ def allgather_endpoints(local: torch.Tensor, n: int, interleaved: bool = False, 
     world = dist.get_world_size(group)
     rows, m = local.shape
     assert m == shard_size(n, world), "local shard has the wrong size"
-    gathered = torch.empty((world, rows, m), dtype=local.dtype, device=local.device)
-    dist.all_gather_into_tensor(gathered, local.contiguous(), group=group)
+    flat = torch.empty((world * rows, m), dtype=local.dtype, device=local.device)  # rank-major concat
+    dist.all_gather_into_tensor(flat, local.contiguous(), group=group)
+    gathered = flat.view(world, rows, m)
     if interleaved:
         full = gathered.permute(1, 2, 0).reshape(rows, m * world)  # column j*W + r
     else:

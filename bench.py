@@ -1,0 +1,379 @@
+#!/usr/bin/env python
+"""bench.py -- PMP backward-shooting rollouts: trajectories/s on N B200s, fraction of the FP32 FMA peak.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload endpoints|dense]
+                    [--dtype f32|f64] [--method tsit5|dopri5|rk4] [--log2n 20] [--impl reference]
+
+A "step" is ONE pass of the hot path over one batch of synthetic terminal samples: per GPU,
+2^20 flat-quadrotor trajectories (flatquad_landing_experiment.py:340-437 constants, terminal states
+on the LQR level set V_f = 1e-3 as in levelsets.py:551-599), Tsit5 + I-controller at
+rtol = atol = 1e-5, T = 3, <= 128 step attempts, fp32 -- BASELINE.json's headline configuration
+("2^20 flat-quadrotor PMP rollouts", config C4).  With N > 1 every rank solves its own 2^20 shard
+(weak scaling, no collective during the solve) and the step ends with the ONE all-gather of the
+endpoint records (x, lambda, v, t) the north star names.
+
+JSON keys beyond the base contract:
+  roofline      bound "fp32_fma" (the path is not a dense contraction and, endpoints-only, moves
+                ~170 B per trajectory): achieved = ALGORITHMIC flops (approximate_optimal_control_b200/
+                flops.py, counted on the oracle's op-counting scalar) / CUDA-event time of the solve;
+                peak = a register-resident FFMA chain measured in this same process
+                (MEASURED_PEAKS.json holds only HBM and bf16 numbers).  --workload dense reports the
+                HBM write roofline instead (peak = MEASURED_PEAKS.json hbm_gbs).
+  cpu_baseline  the CPU oracle (kind "port": a C++ restatement of the reference; jax/diffrax cannot
+                be installed here) on all host threads, on a bounded sample of the same workload.
+  e2e           the same metric through the public API (define_backward_solver -> solve_backward)
+                from pinned HOST buffers, host->device and device->host copies inside the timed region.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+
+
+# --------------------------------------------------------------------------------------------------
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default="endpoints", choices=["endpoints", "dense"])
+    ap.add_argument("--dtype", default="f32", choices=["f32", "f64"])
+    ap.add_argument("--method", default="tsit5", choices=["tsit5", "dopri5", "rk4"])
+    ap.add_argument("--log2n", type=int, default=20, help="log2 of trajectories per GPU")
+    ap.add_argument("--cpu-log2n", type=int, default=19, help="log2 of the cpu_baseline sample")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    return ap.parse_args()
+
+
+def terminal_batch(n: int, seed: int, dtype):
+    """Synthetic terminal samples, [14, n] struct-of-arrays (x, t, v, vx)."""
+    from approximate_optimal_control_b200 import pontryagin_utils as pu, systems, terminal
+    pp = systems.flatquad_problem_params()
+    _, P = pu.get_terminal_lqr(pp)
+    st = terminal.sample_terminal_states(P, pp["V_f"], n, seed=seed, dtype=np.float64)
+    y = np.concatenate([st["x"].T, st["t"][None], st["v"][None], st["vx"].T], 0)
+    return np.ascontiguousarray(y, dtype=dtype), {k: v.astype(dtype) for k, v in st.items()}
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled during the timed region (B200_PROFILING.md)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.rows = []
+        self.proc = None
+        self.gpu = gpu_index
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "100", "-i", str(gpu_index)], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append((time.time(), line.strip()))
+
+    def stop(self, t_begin, t_end):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, smax, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        rows = [r for (t, r) in self.rows if t_begin - 0.3 <= t <= t_end + 0.15] or [r for (_, r) in self.rows]
+        for r in rows:
+            f = [x.strip() for x in r.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1])); smax.append(float(f[2]))
+            except ValueError:
+                continue
+            for nm, val in zip(names, f[5:9]):
+                if val.lower().startswith("active"):
+                    reasons.add(nm)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(smax) if smax else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# --------------------------------------------------------------------------------------------------
+def run_reference(args):
+    """--impl reference: the reference's algorithm on the host cores.  The reference itself (jax 0.4.23 +
+    diffrax 0.4.1) is not installable offline, so this is the CPU oracle ("port"), all host threads,
+    each step a bounded sample (2^17 trajectories) of the same workload."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from oracle import oracle as O
+    n = 1 << 17
+    odt = O.F32 if args.dtype == "f32" else O.F64
+    y, _ = terminal_batch(n, 1, np.float32 if args.dtype == "f32" else np.float64)
+    method = {"tsit5": O.TSIT5, "dopri5": O.DOPRI5, "rk4": O.RK4}[args.method]
+    opts = O.make_opts(method=method, dtype=odt, adaptive=int(args.method != "rk4"),
+                       dt0=-0.1 if args.method != "rk4" else -1 / 32, save_dense=int(args.workload == "dense"))
+    prob = O.flatquad_problem()
+    cores = O.num_threads()
+    for _ in range(args.warmup):
+        O.solve_batch(prob, opts, y)
+    t0 = time.perf_counter()
+    attempts = 0
+    for _ in range(args.steps):
+        out = O.solve_batch(prob, opts, y)
+        attempts += int(out["n_steps"].sum())
+    dt = time.perf_counter() - t0
+    value = n * args.steps / dt
+    line = {
+        "impl": "reference", "metric": "PMP trajectories/sec", "value": value, "unit": "trajectories/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": args.dtype, "data": "synthetic",
+        "rk_step_attempts_per_s": attempts / dt,
+        "config": workload_config(args, n),
+        "cpu_baseline": {"value": value, "unit": "trajectories/s", "cores": cores, "kind": "port",
+                         "sample": f"{args.steps} x 2^17 flatquad terminal samples, same solver settings "
+                                   "(CPU restatement of the reference; jax/diffrax unavailable offline)"},
+        "e2e": {"value": value, "unit": "trajectories/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line), flush=True)
+
+
+def workload_config(args, n_per_gpu):
+    return {
+        "workload": f"flatquad PMP backward shooting, 2^{int(np.log2(n_per_gpu))} terminal samples per GPU, "
+                    f"{args.method} {'adaptive rtol=atol=1e-5' if args.method != 'rk4' else 'fixed dt=1/32'}, "
+                    f"T=3, max 128 attempts, {'dense SaveAt(steps) output' if args.workload == 'dense' else 'endpoints only'}"
+                    + (", all-gather of endpoints" if args.gpus > 1 else ""),
+        "system": "flatquad (nx=6, nu=2, box-clipped u*)", "trajectories_per_gpu": n_per_gpu,
+        "solver": args.method, "rtol": 1e-5, "atol": 1e-5, "T": 3.0, "max_steps": 128,
+        "parallelism": f"shard{args.gpus}" if args.gpus > 1 else "single",
+        "l2": "flushed between timed steps (256 MiB write); per-step working set 172 MB > 126 MB L2",
+    }
+
+
+# --------------------------------------------------------------------------------------------------
+def main():
+    args = parse_args()
+    if args.impl == "reference":
+        return run_reference(args)
+
+    import ctypes as C
+    import torch
+    import torch.distributed as dist
+    from approximate_optimal_control_b200 import _capi, flops, pontryagin_utils as pu, sharding, systems
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the PMP path has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    n_gpus = world
+
+    n = 1 << args.log2n
+    tdt = torch.float32 if args.dtype == "f32" else torch.float64
+    ndt = np.float32 if args.dtype == "f32" else np.float64
+    y_np, st_np = terminal_batch(n, 1 + rank, ndt)
+    pp, ap = systems.flatquad_problem_params(), systems.flatquad_algo_params()
+    problem = systems.to_c_problem(pp)
+    method = _capi.METHODS[args.method]
+    dense = args.workload == "dense"
+    opts = _capi.make_opts(method=method, dtype=_capi.F32 if args.dtype == "f32" else _capi.F64,
+                           adaptive=int(args.method != "rk4"), dt0=-0.1 if args.method != "rk4" else -1 / 32,
+                           save_dense=int(dense))
+    L = _capi.lib()
+
+    y_dev = torch.as_tensor(y_np, device=dev).contiguous()
+    out = {}
+    gathered = torch.empty((world * y_dev.shape[0], n), dtype=tdt, device=dev) if world > 1 else None
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+
+    def step():
+        pu.solve_batch_soa(problem, opts, y_dev, out)
+        if world > 1:
+            dist.all_gather_into_tensor(gathered, out["y_end"])
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- FMA peak (roofline denominator), measured in this process ---------------------------------
+    scratch = torch.zeros(16, dtype=torch.float64, device=dev)
+    pdt = _capi.F32 if args.dtype == "f32" else _capi.F64
+    peak_tflops = 0.0
+    for variant in (0, 1):
+        fl = C.c_double()
+        for it in range(5):
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            _capi.check(L.pmp_fma_peak_cuda(pdt, variant, 4096, scratch.data_ptr(), C.byref(fl),
+                                            C.c_void_p(torch.cuda.current_stream().cuda_stream)))
+            b.record()
+            torch.cuda.synchronize()
+            if it >= 1:
+                peak_tflops = max(peak_tflops, fl.value / (a.elapsed_time(b) * 1e-3) / 1e12)
+
+    # ---- warm-up, then K timed steps ----------------------------------------------------------------
+    sampler = ClockSampler(local_rank) if rank == 0 else None
+    for _ in range(max(args.warmup, 3)):
+        step()
+    barrier()
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
+          for _ in range(args.steps)]
+    attempts = 0
+    t_begin = time.time()
+    barrier()
+    for k in range(args.steps):
+        flush.fill_(k & 0xFF)  # L2 flush, outside the per-step event pair
+        a, m, b = ev[k]
+        a.record()
+        pu.solve_batch_soa(problem, opts, y_dev, out)
+        m.record()
+        if world > 1:
+            dist.all_gather_into_tensor(gathered, out["y_end"])
+        b.record()
+    barrier()
+    t_end = time.time()
+    step_ms = [a.elapsed_time(b) for (a, m, b) in ev]
+    solve_ms = [a.elapsed_time(m) for (a, m, b) in ev]
+    total_ms = torch.tensor([sum(step_ms)], dtype=torch.float64, device=dev)
+    total_solve_ms = torch.tensor([sum(solve_ms)], dtype=torch.float64, device=dev)
+    attempts_t = out["n_steps"].sum().to(torch.float64).reshape(1)
+    if world > 1:
+        dist.all_reduce(total_ms, op=dist.ReduceOp.MAX)
+        dist.all_reduce(total_solve_ms, op=dist.ReduceOp.MAX)
+        dist.all_reduce(attempts_t, op=dist.ReduceOp.SUM)
+    total_s = total_ms.item() * 1e-3
+    attempts_per_step = attempts_t.item()  # all ranks, one step
+    value = n * world * args.steps / total_s
+
+    # ---- roofline of the dominant kernel (rank 0's own launches) -------------------------------------
+    my_attempts = int(out["n_steps"].sum().item())
+    solve_s = float(np.mean(solve_ms)) * 1e-3
+    if dense:
+        peaks = {}
+        try:
+            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        except Exception:
+            pass
+        peak_gbs = peaks.get("hbm_gbs", 6650.0)
+        bytes_alg = flops.dense_bytes(n, 6, opts.max_steps, 4 if args.dtype == "f32" else 8) + 2 * y_dev.numel() * y_dev.element_size()
+        roof = {"bound": "hbm", "achieved": bytes_alg / solve_s / 1e9, "peak": peak_gbs, "unit": "GB/s",
+                "frac": bytes_alg / solve_s / 1e9 / peak_gbs, "traffic": None,
+                "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured)" if peaks else "6650 GB/s (of fallback)",
+                "algorithmic_bytes_per_launch": bytes_alg}
+    else:
+        fl_alg = flops.solve_flops(problem.system_id, method, my_attempts, n)
+        roof = {"bound": "fp32_fma" if args.dtype == "f32" else "fp64_fma", "achieved": fl_alg / solve_s / 1e12,
+                "peak": peak_tflops, "unit": "TFLOP/s", "frac": fl_alg / solve_s / 1e12 / peak_tflops, "traffic": None,
+                "peak_source": "FMA-chain microbenchmark (pmp_fma_peak_cuda) in this process, burst; "
+                               "MEASURED_PEAKS.json has no CUDA-core figure",
+                "algorithmic_flops_per_launch": fl_alg,
+                "flops_per_attempt": flops.ATTEMPT_FLOPS[(problem.system_id, method)],
+                "flops_per_rhs": flops.RHS_FLOPS[problem.system_id],
+                "kernel_ms": solve_s * 1e3}
+        traffic_file = os.path.join(ROOT, "profiles", "traffic.json")
+        if os.path.exists(traffic_file):
+            try:
+                roof["traffic"] = json.load(open(traffic_file)).get(f"{args.workload}_{args.dtype}_{args.method}")
+            except Exception:
+                pass
+
+    # ---- e2e: public API, host buffers ---------------------------------------------------------------
+    e2e = None
+    if not args.no_e2e:
+        solve_backward, _ = pu.define_backward_solver(pp, dict(ap, pontryagin_solver_method=args.method,
+                                                               pontryagin_solver_save_steps=dense,
+                                                               **({"pontryagin_solver_dt0": 1 / 32} if args.method == "rk4" else {})))
+        host_in = {k: torch.as_tensor(v).pin_memory() for k, v in st_np.items()}
+        host_out = {k: torch.empty(v.shape, dtype=tdt).pin_memory() for k, v in st_np.items()}
+        h2d = sum(v.numel() * v.element_size() for v in host_in.values())
+        d2h = sum(v.numel() * v.element_size() for v in host_out.values())
+
+        def e2e_step():
+            dev_in = {k: v.to(dev, non_blocking=True) for k, v in host_in.items()}
+            sol = solve_backward(dev_in)
+            ye = sol.y_end
+            if world > 1:
+                pass  # the gather is part of `value`; e2e measures the per-rank host round trip
+            for k in host_out:
+                host_out[k].copy_(ye[k], non_blocking=True)
+            torch.cuda.synchronize()
+
+        for _ in range(3):
+            e2e_step()
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            e2e_step()
+        barrier()
+        e_s = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(e_s, op=dist.ReduceOp.MAX)
+        e2e = {"value": n * world * args.steps / e_s.item(), "unit": "trajectories/s",
+               "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+               "api": "pontryagin_utils.define_backward_solver(...)[0](state dict) from pinned host tensors; "
+                      "endpoints copied back to pinned host memory"}
+
+    # clocks: the K-step region lasts tens of ms, shorter than nvidia-smi's sampling period, so the
+    # sampler runs from the first warm-up step to the end of the e2e loop (GPU busy throughout)
+    clocks = sampler.stop(t_begin, time.time()) if sampler else None
+    if clocks is not None:
+        clocks["window"] = "warm-up + timed steps + e2e loop"
+
+    # ---- cpu baseline (rank 0, N=1 only) --------------------------------------------------------------
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        from oracle import oracle as O
+        nc = 1 << args.cpu_log2n
+        oo = O.make_opts(method={"tsit5": O.TSIT5, "dopri5": O.DOPRI5, "rk4": O.RK4}[args.method],
+                         dtype=O.F32 if args.dtype == "f32" else O.F64, adaptive=int(args.method != "rk4"),
+                         dt0=-0.1 if args.method != "rk4" else -1 / 32)
+        ys = y_np[:, :nc] if nc <= n else y_np
+        O.solve_batch(O.flatquad_problem(), oo, ys[:, :4096])
+        t0 = time.perf_counter()
+        O.solve_batch(O.flatquad_problem(), oo, ys)
+        dtc = time.perf_counter() - t0
+        cpu = {"value": ys.shape[1] / dtc, "unit": "trajectories/s", "cores": O.num_threads(), "kind": "port",
+               "sample": f"first 2^{int(np.log2(ys.shape[1]))} trajectories of the same batch, same solver settings, "
+                         f"{dtc:.1f} s; C++ restatement of the reference (jax/diffrax not installable offline)"}
+
+    if rank == 0:
+        line = {
+            "metric": "PMP trajectories/sec", "value": value, "unit": "trajectories/s", "n_gpus": n_gpus,
+            "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": total_ms.item() / args.steps,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": args.dtype, "data": "synthetic",
+            "config": workload_config(args, n),
+            "rk_step_attempts_per_s": attempts_per_step * args.steps / total_s,
+            "mean_attempts_per_trajectory": attempts_per_step / (n * world),
+            "solve_ms_per_step": total_solve_ms.item() / args.steps,
+            "roofline": roof, "cpu_baseline": cpu, "e2e": e2e, "clocks": clocks,
+            "gpu_launches": args.steps * L.pmp_solve_launch_count(C.byref(problem), C.byref(opts), n),
+        }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

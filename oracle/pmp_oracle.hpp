@@ -490,15 +490,16 @@ TrajStats solve_one(const Sys& sys, const pmp_opts_t& o, const R* y_f, R* y_end,
     };
     // internal-time vector field.  time mode: dir * f_extended.  value mode: the same field divided
     // by dv/dtau so that v advances at unit rate (experiment_orbits.py:109-111).
+    const bool backward = r_val(dir) < 0;  // multiplying by dir = -1 is a sign flip, not a flop
     auto field = [&](const R* yy, R* k) {
         sys.rhs(yy, k);
         if (value_mode) {
             R vdot = k[IV];  // dv/dt = -l: dy/dv = (dy/dt) / (dv/dt)
-            for (int i = 0; i < NS; i++) k[i] = dir * (k[i] / vdot);
-            k[IV] = dir;
-        } else {
-            for (int i = 0; i < NS; i++) k[i] = dir * k[i];
+            for (int i = 0; i < NS; i++) k[i] = k[i] / vdot;
+            k[IV] = R(1);
         }
+        if (backward)
+            for (int i = 0; i < NS; i++) k[i] = -k[i];
     };
 
     save(0, tprev);
@@ -537,6 +538,7 @@ TrajStats solve_one(const Sys& sys, const pmp_opts_t& o, const R* y_f, R* y_end,
             }
         }
         bool keep = true;
+        bool err_nonfinite = false;
         R next_t0, next_t1;
         if (o.adaptive && tb.embedded) {
             for (int q = 0; q < NS; q++) {
@@ -562,6 +564,7 @@ TrajStats solve_one(const Sys& sys, const pmp_opts_t& o, const R* y_f, R* y_end,
             }
             R scaled = r_sqrt(sumsq / R(n_norm));  // rms_norm over the whole pytree (incl. the t leaf)
             keep = (r_val(scaled) < 1.0) || at_dtmin;
+            err_nonfinite = !(r_val(scaled) < std::numeric_limits<double>::infinity());
             R inv = R(1) / scaled;
             R factor = R(o.safety) * r_pow(inv, R(1.0 / tb.order));
             R fmin = keep ? R(1) : R(o.factormin);
@@ -600,9 +603,11 @@ TrajStats solve_one(const Sys& sys, const pmp_opts_t& o, const R* y_f, R* y_end,
         if (st.result == 0 && o.event == PMP_EVENT_VALUE_GE && r_val(y[IV]) >= o.event_level)
             st.result = PMP_RESULT_EVENT;
         if (keep && st.result == 0) {
-            bool bad = r_isnan(tnext);
+            // a force-accepted step (at dtmin) whose scaled error is not finite, or a NaN state:
+            // diffrax would idle (every later attempt rejected) until max_steps; we retire at once
+            bool bad = r_isnan(tnext) || err_nonfinite;
             for (int q = 0; q < NS; q++) bad = bad || r_isnan(y[q]);
-            if (bad) st.result = PMP_RESULT_NAN;  // diffrax would idle to max_steps; we retire
+            if (bad) st.result = PMP_RESULT_NAN;
         }
     }
     if (st.result == 0 && r_val(tprev) < r_val(T1)) st.result = PMP_RESULT_MAX_STEPS;

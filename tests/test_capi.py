@@ -1,0 +1,132 @@
+"""CPU tests of the drop-in boundary: the C-ABI library loads, exports every symbol include/b200pmp.h
+declares, shares its structs with the oracle byte-for-byte, validates arguments, and refuses to
+compute without a GPU (no CPU fallback)."""
+import ctypes as C
+import os
+import re
+
+import numpy as np
+import pytest
+
+from common import O, ROOT, _capi, as_oracle_opts, c_problem, oracle_problem
+from approximate_optimal_control_b200 import systems
+
+
+def header_functions():
+    src = open(os.path.join(ROOT, "include", "b200pmp.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(pmp_[a-z_0-9]+)\s*\(", src)))
+
+
+def test_library_exports_every_declared_symbol():
+    L = _capi.lib()
+    declared = header_functions()
+    assert set(declared) == set(_capi.EXPORTS)
+    for name in declared:
+        assert hasattr(L, name), name
+    assert L.pmp_abi_version() == _capi.ABI_VERSION
+
+
+def test_header_struct_layout_matches_ctypes():
+    """sizeof / field order of the ctypes mirrors equal what a C compiler lays out for the header."""
+    import subprocess, tempfile
+    prog = r'''
+#include <stdio.h>
+#include <stddef.h>
+#include "b200pmp.h"
+int main(void){
+  printf("%zu %zu %zu\n", sizeof(pmp_problem_t), sizeof(pmp_opts_t), sizeof(pmp_dense_t));
+  printf("%zu %zu %zu %zu\n", offsetof(pmp_problem_t,u_lo), offsetof(pmp_problem_t,params), offsetof(pmp_opts_t,t0), offsetof(pmp_opts_t,event_level));
+  return 0; }'''
+    with tempfile.TemporaryDirectory() as d:
+        open(f"{d}/a.c", "w").write(prog)
+        subprocess.run(["/usr/bin/gcc", "-I", f"{ROOT}/include", f"{d}/a.c", "-o", f"{d}/a"], check=True)
+        out = subprocess.run([f"{d}/a"], capture_output=True, text=True, check=True).stdout.split()
+    sizes = [int(x) for x in out]
+    assert sizes[:3] == [C.sizeof(_capi.Problem), C.sizeof(_capi.Opts), C.sizeof(_capi.Dense)]
+    assert sizes[3:] == [_capi.Problem.u_lo.offset, _capi.Problem.params.offset, _capi.Opts.t0.offset,
+                         _capi.Opts.event_level.offset]
+    assert C.sizeof(O.Problem) == C.sizeof(_capi.Problem) and C.sizeof(O.Opts) == C.sizeof(_capi.Opts)
+
+
+@pytest.mark.parametrize("name", ["flatquad", "orbits", "lqr"])
+def test_problem_records_identical_for_oracle_and_product(name):
+    prob, _ = c_problem(name)
+    assert bytes(prob) == bytes(oracle_problem(name))
+    o = _capi.make_opts()
+    assert bytes(as_oracle_opts(o)) == bytes(o) == bytes(O.make_opts())
+
+
+def test_state_rows_and_workspace():
+    L = _capi.lib()
+    prob, _ = c_problem("flatquad")
+    assert L.pmp_state_rows(C.byref(prob)) == 14
+    o = _capi.make_opts(dtype=_capi.F32)
+    assert L.pmp_solve_workspace_bytes(C.byref(prob), C.byref(o), 1000) == 256 + 13 * 1000 * 4
+    o = _capi.make_opts(dtype=_capi.F64)
+    assert L.pmp_solve_workspace_bytes(C.byref(prob), C.byref(o), 1000) == 256 + 13 * 1000 * 8
+    assert L.pmp_solve_launch_count(C.byref(prob), C.byref(o), 10) == 2
+    assert L.pmp_solve_launch_count(C.byref(prob), C.byref(o), 0) == 0
+
+
+def test_argument_validation_and_error_strings():
+    L = _capi.lib()
+    prob, _ = c_problem("flatquad")
+    bad = _capi.Problem(system_id=7, nx=6, nu=2)
+    assert L.pmp_state_rows(C.byref(bad)) == -2 and b"unknown system_id" in L.pmp_last_error()
+    bad = _capi.Problem.from_buffer_copy(bytes(prob)); bad.nx = 4
+    assert L.pmp_state_rows(C.byref(bad)) == -1
+    bad = _capi.Problem.from_buffer_copy(bytes(prob)); bad.u_hi[0] = -1.0
+    assert L.pmp_state_rows(C.byref(bad)) == -1 and b"U_interval" in L.pmp_last_error()
+    for kw, frag in ((dict(method=9), b"method"), (dict(max_steps=0), b"max_steps"), (dict(dt0=0.0), b"dt0"),
+                     (dict(dt0=+0.1), b"dt0"), (dict(method="rk4", adaptive=1), b"RK4"), (dict(rtol=-1.0), b"rtol"),
+                     (dict(dtype=5), b"dtype"), (dict(event=3), b"event")):
+        o = _capi.make_opts(**kw)
+        assert L.pmp_solve_workspace_bytes(C.byref(prob), C.byref(o), 8) < 0, kw
+        assert frag in L.pmp_last_error(), (kw, L.pmp_last_error())
+    o = _capi.make_opts()
+    # NULL buffers / missing workspace are rejected before anything touches a device
+    assert L.pmp_solve_batch_cuda(C.byref(prob), C.byref(o), 8, None, None, None, None, None, None, None, 0, None) == -1
+    buf = (C.c_float * (14 * 8))()
+    assert L.pmp_solve_batch_cuda(C.byref(prob), C.byref(o), 8, buf, buf, None, None, None, None, None, 0, None) == -1
+    assert b"workspace" in L.pmp_last_error()
+    assert L.pmp_solve_batch_cuda(C.byref(prob), C.byref(o), 0, None, None, None, None, None, None, None, 0, None) == 0
+    with pytest.raises(_capi.PmpError):
+        _capi.check(-1)
+
+
+def test_no_cpu_fallback_without_gpu():
+    """The product path must fail loudly when no CUDA device is present."""
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    L = _capi.lib()
+    assert L.pmp_device_count() == 0
+    prob, pp = c_problem("flatquad")
+    y = np.zeros((14, 8), np.float32)
+    assert L.pmp_rhs_batch_cuda(C.byref(prob), _capi.F32, 8, y.ctypes.data, y.ctypes.data, None) == _capi.lib().pmp_rhs_batch_cuda(
+        C.byref(prob), _capi.F32, 8, y.ctypes.data, y.ctypes.data, None) == -4
+    assert b"no CPU fallback" in L.pmp_last_error()
+    from approximate_optimal_control_b200 import pontryagin_utils as pu
+    solve_backward, f_extended = pu.define_backward_solver(pp, systems.flatquad_algo_params())
+    st = {"x": np.zeros(6, np.float32), "t": 0, "v": np.float32(0), "vx": np.zeros(6, np.float32)}
+    with pytest.raises(_capi.PmpError):
+        solve_backward(st)
+    with pytest.raises(_capi.PmpError):
+        pu.u_star_2d(st["x"], st["vx"], pp)
+
+
+def test_product_does_not_touch_the_oracle():
+    """Nothing under the package may import, link or execute oracle/."""
+    pkg = os.path.join(ROOT, "approximate_optimal_control_b200")
+    for dirpath, _, files in os.walk(pkg):
+        if os.path.basename(dirpath) == "build":
+            continue
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                txt = open(os.path.join(dirpath, f)).read()
+                assert "oracle/" not in txt.replace("oracle/opcount.hpp; u*", "") and "import oracle" not in txt \
+                    and "from oracle" not in txt and "pmp_oracle" not in txt, os.path.join(dirpath, f)
+    import subprocess
+    ldd = subprocess.run(["ldd", os.path.join(pkg, "libb200pmp.so")], capture_output=True, text=True).stdout
+    assert "oracle" not in ldd

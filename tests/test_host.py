@@ -1,0 +1,126 @@
+"""CPU tests of the host-side mirror of the reference interface (no GPU compute)."""
+import os
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+from common import ROOT, _capi, flatquad_P
+from approximate_optimal_control_b200 import pontryagin_utils as pu, sharding, systems, terminal
+
+
+def test_flatquad_linearisation_closed_form():
+    pp = systems.flatquad_problem_params()
+    A, B, Q, R = systems.linearise(pp)
+    m, g, r = 20.0, 9.81, 0.5
+    I = m * (r / 2) ** 2
+    A0 = np.zeros((6, 6)); A0[0, 3] = A0[1, 4] = A0[2, 5] = 1; A0[3, 2] = -g
+    B0 = np.zeros((6, 2)); B0[4, :] = 1 / m; B0[5, 0] = -r / I; B0[5, 1] = r / I
+    q = [1 / 0.3 ** 2, 1 / 0.3 ** 2, 1 / np.deg2rad(30) ** 2, 4.0, 4.0, 1 / np.deg2rad(120) ** 2]
+    Q0 = 2 * np.diag(q); Q0[2, 2] += 2 * g * g
+    R0 = 2 * np.array([[1 / m ** 2 + r ** 2 / I ** 2, 1 / m ** 2 - r ** 2 / I ** 2]] * 2); R0[1] = R0[1][::-1]
+    for got, want in ((A, A0), (B, B0), (Q, Q0), (R, R0)):
+        assert np.allclose(got, want, atol=1e-12)
+    # H_uu = [[.325, -.315], [-.315, .325]]
+    assert np.allclose(R, [[0.325, -0.315], [-0.315, 0.325]])
+    # finite-difference fallback agrees
+    A2, B2, Q2, R2 = systems._linearise_fd(pp["f"], pp["l"], pp["x_eq"], pp["u_eq"])
+    assert np.allclose(A2, A, atol=1e-6) and np.allclose(B2, B, atol=1e-6)
+    assert np.allclose(Q2, Q, rtol=1e-4, atol=1e-4) and np.allclose(R2, R, atol=1e-5)
+
+
+def test_get_terminal_lqr_known_values():
+    """P11 = 31.336, P22 = 21.773, P33 = 297.19, cond(P) = 93.4; stable closed loop."""
+    pp = systems.flatquad_problem_params()
+    K, P = pu.get_terminal_lqr(pp)
+    assert np.allclose(np.diag(P)[:3], [31.336, 21.773, 297.19], rtol=1e-4)
+    assert abs(np.linalg.cond(P) - 93.4) < 0.1
+    A, B, Q, R = systems.linearise(pp)
+    poles = np.linalg.eigvals(A - B @ K)
+    assert (poles.real < 0).all() and np.isclose(poles.real.min(), -2.04, atol=0.01)
+    assert K.shape == (2, 6)
+    bad = dict(pp, u_eq=np.zeros(2))
+    with pytest.raises(AssertionError):
+        pu.get_terminal_lqr(bad)
+    with pytest.raises(ValueError):
+        pu.lqr(np.eye(2), np.zeros((2, 1)), np.eye(2), np.eye(1))  # unstable, uncontrollable
+
+
+def test_terminal_samples_on_level_set():
+    P = flatquad_P()
+    st = terminal.sample_terminal_states(P, 1e-3, 1000, seed=1)
+    v = 0.5 * np.einsum("ni,ij,nj->n", st["x"], P, st["x"])
+    assert np.allclose(v, 1e-3) and np.allclose(st["v"], 1e-3)           # levelsets.py:562
+    assert np.allclose(st["vx"], st["x"] @ P.T) and (st["t"] == 0).all()  # levelsets.py:585-592
+    st2 = terminal.sample_terminal_states(P, 1e-3, 1000, seed=1)
+    assert np.array_equal(st["x"], st2["x"])
+
+
+def test_to_c_problem_and_errors():
+    p = systems.to_c_problem(systems.flatquad_problem_params())
+    assert (p.system_id, p.nx, p.nu) == (0, 6, 2) and np.isclose(p.u_hi[0], 117.72) and p.params[0] == 20.0
+    p = systems.to_c_problem(systems.orbits_problem_params())
+    assert (p.system_id, p.nx, p.nu, p.u_lo[0], p.u_hi[0]) == (1, 2, 1, -0.2, 0.2)
+    with pytest.raises(NotImplementedError):
+        systems.to_c_problem({"system_name": "pendulum", "nx": 2, "nu": 1, "U_interval": [-1, 1]})
+    pp = systems.flatquad_problem_params()
+    with pytest.raises(NotImplementedError):
+        pu.define_backward_solver(pp, dict(systems.flatquad_algo_params(), pontryagin_solver_vxx=True))
+    with pytest.raises(NotImplementedError):
+        pu.u_star_2d(np.zeros(2), np.zeros(2), systems.orbits_problem_params())  # nu != 2, as the reference
+    with pytest.raises(AssertionError):
+        pu.u_star_new(np.zeros(6), np.zeros(6), pp)  # nu != 1, as the reference
+
+
+def test_host_f_l_match_oracle_rhs_pieces():
+    """The numpy f, l of systems.py (kept for callers that evaluate costs on results) agree with the
+    oracle's f_extended at u = u*."""
+    from common import O
+    pp = systems.flatquad_problem_params()
+    rng = np.random.default_rng(0)
+    x = rng.standard_normal((50, 6)); lam = rng.standard_normal((50, 6)) * 5
+    u = O.ustar_batch(O.flatquad_problem(), O.F64, x.T, lam.T).T
+    dy = O.rhs_batch(O.flatquad_problem(), O.F64, np.concatenate([x.T, np.zeros((2, 50)), lam.T], 0))
+    assert np.allclose(pp["f"](x, u), dy[:6].T, atol=1e-12)
+    assert np.allclose(-pp["l"](x, u), dy[7], atol=1e-10)
+
+
+def test_shard_indices_cover_everything():
+    for n, w in ((10, 2), (11, 4), (1 << 10, 8), (5, 8)):
+        for inter in (False, True):
+            idx = torch.cat([sharding.shard_indices(n, r, w, inter) for r in range(w)])
+            real = idx[idx >= 0]
+            assert sorted(real.tolist()) == list(range(n))
+            assert idx.numel() == w * sharding.shard_size(n, w)
+
+
+def _worker(rank, world, n, inter, port, q):
+    import torch.distributed as dist
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    full = torch.arange(3 * n, dtype=torch.float64).reshape(3, n)
+    local = sharding.take_shard(full, n, rank, world, inter)
+    # "solve": every rank transforms its own shard, no communication
+    local = torch.where(torch.isnan(local), local, local * 2 + 1)
+    out = sharding.allgather_endpoints(local, n, inter)
+    q.put((rank, torch.equal(out, full * 2 + 1), tuple(out.shape)))
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("n,inter", [(64, False), (64, True), (37, False), (37, True)])
+def test_sharded_allgather_world2_gloo(n, inter):
+    """world_size-2 run on CPU (gloo) of the N>1 path: shard by index -> local work -> ONE all-gather
+    restores the global endpoint array in the original order on every rank."""
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29500 + (os.getpid() + n + int(inter)) % 2000
+    procs = [ctx.Process(target=_worker, args=(r, 2, n, inter, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=120) for _ in procs]
+    for p in procs:
+        p.join(60)
+    assert all(ok for (_, ok, _) in res), res
+    assert all(shape == (3, n) for (_, _, shape) in res)
