@@ -17,7 +17,8 @@ F32, F64 = 0, 1
 INDEP_TIME, INDEP_VALUE = 0, 1
 EVENT_NONE, EVENT_VALUE_GE = 0, 1
 RESULT_OK, RESULT_EVENT, RESULT_MAX_STEPS, RESULT_DT_MIN, RESULT_NAN = 0, 1, 2, 3, 4
-ABI_VERSION = 1
+ABI_VERSION = 2
+FLAG_USTAR_LITERAL = 1
 
 METHODS = {"rk4": METHOD_RK4, "tsit5": METHOD_TSIT5, "dopri5": METHOD_DOPRI5}
 
@@ -34,7 +35,8 @@ class Opts(C.Structure):
                 ("t0", C.c_double), ("t1", C.c_double), ("dt0", C.c_double),
                 ("rtol", C.c_double), ("atol", C.c_double), ("dtmin", C.c_double),
                 ("dtmax", C.c_double), ("safety", C.c_double), ("factormin", C.c_double),
-                ("factormax", C.c_double), ("event_level", C.c_double)]
+                ("factormax", C.c_double), ("event_level", C.c_double),
+                ("flags", C.c_int32), ("reserved", C.c_int32)]
 
 
 class Dense(C.Structure):
@@ -44,7 +46,7 @@ class Dense(C.Structure):
 
 EXPORTS = ("pmp_abi_version", "pmp_last_error", "pmp_state_rows", "pmp_device_count",
            "pmp_solve_workspace_bytes", "pmp_solve_batch_cuda", "pmp_solve_launch_count",
-           "pmp_rhs_batch_cuda", "pmp_ustar_batch_cuda", "pmp_fma_peak_cuda")
+           "pmp_rhs_batch_cuda", "pmp_ustar_batch_cuda", "pmp_ustar_batch_cuda_flags", "pmp_fma_peak_cuda")
 
 _lib = None
 
@@ -77,6 +79,8 @@ def lib() -> C.CDLL:
                                      C.c_void_p, C.c_void_p]
     L.pmp_ustar_batch_cuda.argtypes = [C.POINTER(Problem), C.c_int32, C.c_int64, C.c_void_p,
                                        C.c_void_p, C.c_void_p, C.c_void_p]
+    L.pmp_ustar_batch_cuda_flags.argtypes = [C.POINTER(Problem), C.c_int32, C.c_int32, C.c_int64, C.c_void_p,
+                                             C.c_void_p, C.c_void_p, C.c_void_p]
     L.pmp_fma_peak_cuda.argtypes = [C.c_int32, C.c_int32, C.c_int32, C.c_void_p,
                                     C.POINTER(C.c_double), C.c_void_p]
     if L.pmp_abi_version() != ABI_VERSION:
@@ -94,7 +98,7 @@ def check(rc: int) -> int:
 def make_opts(*, method=METHOD_TSIT5, dtype=F32, indep=INDEP_TIME, adaptive=1, max_steps=128,
               force_dtmin=1, event=EVENT_NONE, save_dense=0, t0=0.0, t1=-3.0, dt0=-0.1, rtol=1e-5,
               atol=1e-5, dtmin=0.0005, dtmax=0.5, safety=0.9, factormin=0.2, factormax=10.0,
-              event_level=0.0) -> Opts:
+              event_level=0.0, flags=0) -> Opts:
     """Defaults = the reference's flatquad solve (pontryagin_utils.py:496-525,
     flatquad_landing_experiment.py:368-382); controller constants are diffrax's PIDController defaults."""
     if isinstance(method, str):
@@ -102,4 +106,4 @@ def make_opts(*, method=METHOD_TSIT5, dtype=F32, indep=INDEP_TIME, adaptive=1, m
     return Opts(int(method), int(dtype), int(indep), int(adaptive), int(max_steps), int(force_dtmin),
                 int(event), int(save_dense), float(t0), float(t1), float(dt0), float(rtol),
                 float(atol), float(dtmin), float(dtmax), float(safety), float(factormin),
-                float(factormax), float(event_level))
+                float(factormax), float(event_level), int(flags), 0)

@@ -60,6 +60,7 @@ int check_opts(const pmp_opts_t* o) {
     } else if (!(o->dt0 > 0)) {
         return fail(PMP_ERR_BAD_ARG, "value-parameterised solve needs dt0 > 0");
     }
+    if ((o->flags & ~PMP_FLAG_USTAR_LITERAL) != 0 || o->reserved != 0) return fail(PMP_ERR_BAD_ARG, "unknown flags / reserved != 0");
     if (o->adaptive) {
         if (!(o->rtol >= 0) || !(o->atol >= 0) || !(o->rtol + o->atol > 0)) return fail(PMP_ERR_BAD_ARG, "bad rtol/atol");
         if (!(o->safety > 0) || !(o->factormin > 0) || !(o->factormax >= 1)) return fail(PMP_ERR_BAD_ARG, "bad controller factors");
@@ -144,6 +145,18 @@ int pmp_ustar_batch_cuda(const pmp_problem_t* p, int32_t dtype, int64_t n, const
     if (n == 0) return PMP_OK;
     if (pmp_device_count() <= 0) return fail(PMP_ERR_NO_DEVICE, "no CUDA device: libb200pmp has no CPU fallback");
     int rc = pmp::eval_batch(1, *p, dtype, n, x, lam, u, (cudaStream_t)cuda_stream);
+    return rc ? cuda_fail(rc) : PMP_OK;
+}
+
+int pmp_ustar_batch_cuda_flags(const pmp_problem_t* p, int32_t dtype, int32_t flags, int64_t n, const void* x,
+                               const void* lam, void* u, void* cuda_stream) {
+    if (int e = check_problem(p)) return e;
+    if (dtype != PMP_F32 && dtype != PMP_F64) return fail(PMP_ERR_BAD_ARG, "dtype must be 0 (f32) or 1 (f64)");
+    if ((flags & ~PMP_FLAG_USTAR_LITERAL) != 0) return fail(PMP_ERR_BAD_ARG, "unknown flags");
+    if (n < 0 || (n > 0 && (!x || !lam || !u))) return fail(PMP_ERR_BAD_ARG, "bad n or NULL buffers");
+    if (n == 0) return PMP_OK;
+    if (pmp_device_count() <= 0) return fail(PMP_ERR_NO_DEVICE, "no CUDA device: libb200pmp has no CPU fallback");
+    int rc = pmp::eval_batch((flags & PMP_FLAG_USTAR_LITERAL) ? 1 : 2, *p, dtype, n, x, lam, u, (cudaStream_t)cuda_stream);
     return rc ? cuda_fail(rc) : PMP_OK;
 }
 

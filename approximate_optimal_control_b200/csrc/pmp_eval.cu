@@ -16,14 +16,14 @@ __global__ void __launch_bounds__(256) rhs_kernel(const typename Sys::Consts sc,
     R x[NX], lam[NX], xd[NX], ld[NX], vd;
 #pragma unroll
     for (int q = 0; q < NX; q++) { x[q] = y[q * n + i]; lam[q] = y[(NX + 2 + q) * n + i]; }
-    Sys::template rhs<false>(sc, x, lam, xd, vd, ld);
+    Sys::template rhs<0>(sc, x, lam, xd, vd, ld);  // literal u*
 #pragma unroll
     for (int q = 0; q < NX; q++) { dy[q * n + i] = xd[q]; dy[(NX + 2 + q) * n + i] = ld[q]; }
     dy[NX * n + i] = R(1);  // state_dot['t'] = 1.   (pontryagin_utils.py:456)
     dy[(NX + 1) * n + i] = vd;
 }
 
-template <class Sys, class R>
+template <class Sys, class R, int UMODE>
 __global__ void __launch_bounds__(256) ustar_kernel(const typename Sys::Consts sc, const R* __restrict__ x_,
                                                     const R* __restrict__ lam_, R* __restrict__ u_, long long n) {
     constexpr int NX = Sys::NX, NU = Sys::NU;
@@ -32,7 +32,8 @@ __global__ void __launch_bounds__(256) ustar_kernel(const typename Sys::Consts s
     R x[NX], lam[NX], u[NU];
 #pragma unroll
     for (int q = 0; q < NX; q++) { x[q] = x_[q * n + i]; lam[q] = lam_[q * n + i]; }
-    Sys::ustar(sc, x, lam, u);
+    if (UMODE == 0) Sys::ustar(sc, x, lam, u);
+    else Sys::template ustar_mode<UMODE>(sc, x, lam, u);
 #pragma unroll
     for (int q = 0; q < NU; q++) u_[q * n + i] = u[q];
 }
@@ -45,11 +46,13 @@ int eval_dispatch(int what, const pmp_problem_t& p, int dtype, long long n, cons
     if (dtype == PMP_F32) {
         using S = SysT<float>;
         if (what == 0) rhs_kernel<S, float><<<grid, 256, 0, st>>>(S::make(p), (const float*)a, (float*)out, n);
-        else ustar_kernel<S, float><<<grid, 256, 0, st>>>(S::make(p), (const float*)a, (const float*)b, (float*)out, n);
+        else if (what == 1) ustar_kernel<S, float, 0><<<grid, 256, 0, st>>>(S::make(p), (const float*)a, (const float*)b, (float*)out, n);
+        else ustar_kernel<S, float, 2><<<grid, 256, 0, st>>>(S::make(p), (const float*)a, (const float*)b, (float*)out, n);
     } else {
         using S = SysT<double>;
         if (what == 0) rhs_kernel<S, double><<<grid, 256, 0, st>>>(S::make(p), (const double*)a, (double*)out, n);
-        else ustar_kernel<S, double><<<grid, 256, 0, st>>>(S::make(p), (const double*)a, (const double*)b, (double*)out, n);
+        else if (what == 1) ustar_kernel<S, double, 0><<<grid, 256, 0, st>>>(S::make(p), (const double*)a, (const double*)b, (double*)out, n);
+        else ustar_kernel<S, double, 2><<<grid, 256, 0, st>>>(S::make(p), (const double*)a, (const double*)b, (double*)out, n);
     }
     return (int)cudaGetLastError();
 }

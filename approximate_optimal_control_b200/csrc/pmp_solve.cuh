@@ -36,11 +36,12 @@ constexpr int kChunk = 64;   // trajectory indices claimed per atomicAdd
 // ---- forward-time field on the integrator's vector layout y = (x[NX], lam[NX], aux) -------------
 // time mode : aux = v,  k = (f, -dH/dx, -l)
 // value mode: aux = t,  k = (f, -dH/dx, 1) / (dv/dt)      (experiment_orbits.py:109-111)
-template <class Sys, class R, bool VALUE, bool WARP_VOTE>
+// UMODE: u* selection mode handed to Sys::rhs (bit 0 warp vote, bit 1 KKT form)
+template <class Sys, class R, bool VALUE, int UMODE>
 __device__ __forceinline__ void field(const typename Sys::Consts& sc, const R* y, R* k) {
     constexpr int NX = Sys::NX;
     R vd;
-    Sys::template rhs<WARP_VOTE>(sc, y, y + NX, k, vd, k + NX);
+    Sys::template rhs<UMODE>(sc, y, y + NX, k, vd, k + NX);
     if (VALUE) {
         const R iv = Math<R>::div(R(1), vd);
 #pragma unroll
@@ -65,7 +66,7 @@ __device__ __forceinline__ void load_state(const R* __restrict__ y_f, long long 
 }
 
 // ---- prep kernel: k1 = field(y_f) for every trajectory (coalesced), and reset of the work counter
-template <class Sys, class R, bool VALUE>
+template <class Sys, class R, bool VALUE, bool ULIT>
 __global__ void __launch_bounds__(kBlock) prep_kernel(const typename Sys::Consts sc, const R* __restrict__ y_f,
                                                       R* __restrict__ k1, long long n,
                                                       unsigned long long* counter) {
@@ -75,7 +76,7 @@ __global__ void __launch_bounds__(kBlock) prep_kernel(const typename Sys::Consts
     if (i >= n) return;
     R y[ND], k[ND], c0, af;
     load_state<R, NX, VALUE>(y_f, n, i, y, c0, af);
-    field<Sys, R, VALUE, false>(sc, y, k);
+    field<Sys, R, VALUE, ULIT ? 0 : 2>(sc, y, k);
 #pragma unroll
     for (int q = 0; q < ND; q++) k1[q * n + i] = k[q];
 }
@@ -83,7 +84,7 @@ __global__ void __launch_bounds__(kBlock) prep_kernel(const typename Sys::Consts
 static __global__ void reset_counter_kernel(unsigned long long* counter) { *counter = 0ull; }
 
 // ---- the integrator -----------------------------------------------------------------------------
-template <class Sys, class R, int METHOD, bool DENSE, bool VALUE, int MINB>
+template <class Sys, class R, int METHOD, bool DENSE, bool VALUE, bool ULIT, int MINB>
 __global__ void __launch_bounds__(kBlock, MINB)
 solve_kernel(const typename Sys::Consts sc, const SolveOpts<R> o, const SolveIO<R> io) {
     using M = Math<R>;
@@ -208,7 +209,7 @@ solve_kernel(const typename Sys::Consts sc, const SolveOpts<R> o, const SolveIO<
         // =============================== one step attempt ========================================
         const R dt = tnext - tprev;
         const R h = dt * o.dir;
-        if (!TB::FSAL) field<Sys, R, VALUE, true>(sc, y, k[0]);
+        if (!TB::FSAL) field<Sys, R, VALUE, ULIT ? 1 : 2>(sc, y, k[0]);
         R y1[ND];
 #pragma unroll
         for (int i = 1; i < S; i++) {
@@ -229,7 +230,7 @@ solve_kernel(const typename Sys::Consts sc, const SolveOpts<R> o, const SolveIO<
                     if (TB::a(i, j) != 0.0) acc = M::fma(ha[j], k[j][q], acc);
                 ys[q] = acc;
             }
-            field<Sys, R, VALUE, true>(sc, ys, k[i]);
+            field<Sys, R, VALUE, ULIT ? 1 : 2>(sc, ys, k[i]);
             if (last_fsal) {
 #pragma unroll
                 for (int q = 0; q < ND; q++) y1[q] = ys[q];
@@ -365,13 +366,13 @@ inline size_t workspace_bytes_for(int nd, long long n, size_t real_size) {
     return 256 + (size_t)nd * (size_t)n * real_size;
 }
 
-template <class Sys, class R, int METHOD, bool DENSE, bool VALUE, int MINB>
+template <class Sys, class R, int METHOD, bool DENSE, bool VALUE, bool ULIT, int MINB>
 int launch_one(const pmp_problem_t& p, const pmp_opts_t& o, long long n, const void* y_f, void* y_end,
                const pmp_dense_t* dense, int32_t* n_acc, int32_t* n_steps, int32_t* result,
                void* workspace, cudaStream_t st) {
     using TB = Tab<METHOD>;
     constexpr int ND = 2 * Sys::NX + 1;
-    auto kern = solve_kernel<Sys, R, METHOD, DENSE, VALUE, MINB>;
+    auto kern = solve_kernel<Sys, R, METHOD, DENSE, VALUE, ULIT, MINB>;
     int dev = 0, sms = 0, occ = 0;
     cudaError_t e = cudaGetDevice(&dev);
     if (e != cudaSuccess) return (int)e;
@@ -395,7 +396,7 @@ int launch_one(const pmp_problem_t& p, const pmp_opts_t& o, long long n, const v
     if (DENSE && dense)
         io.dense = DensePtrs<R>{(R*)dense->ts, (R*)dense->x, (R*)dense->t, (R*)dense->v, (R*)dense->vx};
     if (TB::FSAL) {
-        prep_kernel<Sys, R, VALUE><<<(unsigned)need, kBlock, 0, st>>>(sc, (const R*)y_f, (R*)((char*)workspace + 256), n,
+        prep_kernel<Sys, R, VALUE, ULIT><<<(unsigned)need, kBlock, 0, st>>>(sc, (const R*)y_f, (R*)((char*)workspace + 256), n,
                                                                     io.counter);
     } else {
         reset_counter_kernel<<<1, 1, 0, st>>>(io.counter);
@@ -409,8 +410,14 @@ template <template <class> class SysT, int MINB32, int MINB64>
 int launch_solve(const pmp_problem_t& p, const pmp_opts_t& o, long long n, const void* y_f, void* y_end,
                  const pmp_dense_t* dense, int32_t* a, int32_t* s, int32_t* r, void* ws, cudaStream_t st) {
     const bool dn = o.save_dense != 0, val = o.indep == PMP_INDEP_VALUE;
-#define PMP_GO(R, METHOD, DENSE, VALUE, MINB) \
-    return launch_one<SysT<R>, R, METHOD, DENSE, VALUE, MINB>(p, o, n, y_f, y_end, dense, a, s, r, ws, st)
+    // the literal two-pass u* only exists for nu = 2 systems
+    const bool ulit = (o.flags & PMP_FLAG_USTAR_LITERAL) != 0 && SysT<float>::NU == 2;
+#define PMP_GO(R, METHOD, DENSE, VALUE, MINB)                                                                      \
+    do {                                                                                                           \
+        if (SysT<float>::NU == 2 && ulit)                                                                          \
+            return launch_one<SysT<R>, R, METHOD, DENSE, VALUE, (SysT<float>::NU == 2), MINB>(p, o, n, y_f, y_end, dense, a, s, r, ws, st); \
+        return launch_one<SysT<R>, R, METHOD, DENSE, VALUE, false, MINB>(p, o, n, y_f, y_end, dense, a, s, r, ws, st); \
+    } while (0)
 #define PMP_BY_FLAGS(R, METHOD, MINB)                           \
     do {                                                        \
         if (dn && val) PMP_GO(R, METHOD, true, true, MINB);     \

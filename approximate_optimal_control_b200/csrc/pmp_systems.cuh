@@ -34,6 +34,9 @@ template <class R> struct Flatquad {
         // (lo,lo),(lo,hi),(hi,hi),(hi,lo) (pontryagin_utils.py:78-86).  Along the one moving axis:
         //   s = clip(eA*H_u[axis] + eB, 0, 1),   u[axis] = eb + s*ed
         R eA[4], eB[4], ed[4], eb[4];
+        // KKT form: edge minimiser coordinate = clip(kN*H_u[axis] + kQ[k], lo, hi); its multiplier
+        // = +-(h01*coordinate + H_u[other axis] + kM[k])
+        R kN, kQ[4], kM[4];
     };
 
     static __host__ Consts make(const pmp_problem_t& p) {
@@ -61,7 +64,13 @@ template <class R> struct Flatquad {
             c.eB[k] = R(-gk * dd * inv_den);
             c.ed[k] = R(dd);
             c.eb[k] = R(b[ax]);
+            // the fixed coordinate of edge k is a[1-ax]: minimiser of H along the edge in the moving
+            // coordinate w: d*w + o*fixed + Hu[ax] = 0; multiplier: d*fixed + o*w + Hu[1-ax]
+            const double fixed = a[1 - ax];
+            c.kQ[k] = R(-o * fixed / d);
+            c.kM[k] = R(d * fixed);
         }
+        c.kN = R(-1.0 / d);
         return c;
     }
 
@@ -74,10 +83,13 @@ template <class R> struct Flatquad {
         return M::fma(w0, t, w1 * r1);
     }
 
-    // u_star_2d with sin/cos of Phi already known.  WARP_VOTE: the caller guarantees all 32 lanes
-    // are converged, so the edge search is skipped when no lane leaves the box (warp-uniform branch).
-    template <bool WARP_VOTE>
+    // u_star_2d with sin/cos of Phi already known.
+    // MODE & 1 (literal only): the caller guarantees all 32 lanes are converged, so the edge search
+    //          is skipped when no lane leaves the box (warp-uniform branch).
+    // MODE & 2: KKT selection among the edge minimisers (PMP_FLAG_USTAR_LITERAL clear), branch-free.
+    template <int MODE>
     static __device__ __forceinline__ void ustar_sc(const Consts& c, const R* lam, R s, R co, R& u0, R& u1) {
+        constexpr bool WARP_VOTE = (MODE & 1) != 0;
         using M = Math<R>;
         // H_u at u=0 (pontryagin_utils.py:37)
         const R base = M::fma(M::fma(lam[4], co, -(lam[3] * s)), c.inv_m, -(c.two_g_m * co));
@@ -89,6 +101,32 @@ template <class R> struct Flatquad {
         // :129  outside the box?  NaN compares false => treated as inside => NaN u propagates
         const R viol = M::max(M::max(c.lo0 - u0, c.lo1 - u1), M::max(u0 - c.hi0, u1 - c.hi1));
         const bool outside = viol > R(0);
+        if (MODE & 2) {
+            // minimisers of H along the four edges (bottom u1=lo1, left u0=lo0, top u1=hi1, right
+            // u0=hi0 -- the reference's candidate order, pontryagin_utils.py:78-86), each the clipped
+            // root of the tangential derivative
+            const R xb = M::min(M::max(M::fma(c.kN, Hu0, c.kQ[0]), c.lo0), c.hi0);
+            const R yl = M::min(M::max(M::fma(c.kN, Hu1, c.kQ[1]), c.lo1), c.hi1);
+            const R xt = M::min(M::max(M::fma(c.kN, Hu0, c.kQ[2]), c.lo0), c.hi0);
+            const R yr = M::min(M::max(M::fma(c.kN, Hu1, c.kQ[3]), c.lo1), c.hi1);
+            // KKT multiplier of the active bound = outward-pointing component of -grad H; the edge
+            // minimiser that solves the box problem is the one whose multiplier is >= 0 (the others
+            // are negative), so take the largest: first maximum wins, like the reference's argmin
+            const R mb = M::fma(c.h01, xb, Hu1 + c.kM[0]);
+            const R ml = M::fma(c.h01, yl, Hu0 + c.kM[1]);
+            const R mt = -M::fma(c.h01, xt, Hu1 + c.kM[2]);
+            const R mr = -M::fma(c.h01, yr, Hu0 + c.kM[3]);
+            R bm = mb, bx = xb, by = c.lo1;
+            bool gt = ml > bm;
+            bm = gt ? ml : bm; bx = gt ? c.lo0 : bx; by = gt ? yl : by;
+            gt = mt > bm;
+            bm = gt ? mt : bm; bx = gt ? xt : bx; by = gt ? c.hi1 : by;
+            gt = mr > bm;
+            bx = gt ? c.hi0 : bx; by = gt ? yr : by;
+            u0 = outside ? bx : u0;
+            u1 = outside ? by : u1;
+            return;
+        }
         bool go = outside;
         if (WARP_VOTE) go = __any_sync(0xffffffffu, outside);
         if (go) {
@@ -127,17 +165,23 @@ template <class R> struct Flatquad {
     static __device__ __forceinline__ void ustar(const Consts& c, const R* x, const R* lam, R* u) {
         R s, co;
         Math<R>::sincos(x[2], &s, &co);
-        ustar_sc<false>(c, lam, s, co, u[0], u[1]);
+        ustar_sc<0>(c, lam, s, co, u[0], u[1]);  // literal two-pass form, no warp vote
+    }
+    template <int MODE>
+    static __device__ __forceinline__ void ustar_mode(const Consts& c, const R* x, const R* lam, R* u) {
+        R s, co;
+        Math<R>::sincos(x[2], &s, &co);
+        ustar_sc<MODE>(c, lam, s, co, u[0], u[1]);
     }
 
     // forward-time f_extended: xd = f(x,u*), vd = -l(x,u*), ld = -dH/dx
-    template <bool WARP_VOTE>
+    template <int MODE>
     static __device__ __forceinline__ void rhs(const Consts& c, const R* x, const R* lam, R* xd, R& vd, R* ld) {
         using M = Math<R>;
         R s, co;
         M::sincos(x[2], &s, &co);
         R u0, u1;
-        ustar_sc<WARP_VOTE>(c, lam, s, co, u0, u1);
+        ustar_sc<MODE>(c, lam, s, co, u0, u1);
         const R Sm = (u0 + u1) * c.inv_m;
         const R ax = -(s * Sm);
         const R ay = M::fma(co, Sm, -c.g);
@@ -181,7 +225,9 @@ template <class R> struct Orbits {
         using M = Math<R>;
         u[0] = clipf(M::fma(lam[0], x[0], lam[1] * x[1]) * c.neg_inv_2wu, c.lo, c.hi);
     }
-    template <bool WARP_VOTE>
+    template <int MODE>
+    static __device__ __forceinline__ void ustar_mode(const Consts& c, const R* x, const R* lam, R* u) { ustar(c, x, lam, u); }
+    template <int MODE>
     static __device__ __forceinline__ void rhs(const Consts& c, const R* x, const R* lam, R* xd, R& vd, R* ld) {
         using M = Math<R>;
         R u[1];
@@ -227,7 +273,9 @@ template <class R> struct LqrStatePenalty {
     static __device__ __forceinline__ void ustar(const Consts& c, const R* x, const R* lam, R* u) {
         u[0] = clipf(lam[1] * c.neg_inv_2ru, c.lo, c.hi);
     }
-    template <bool WARP_VOTE>
+    template <int MODE>
+    static __device__ __forceinline__ void ustar_mode(const Consts& c, const R* x, const R* lam, R* u) { ustar(c, x, lam, u); }
+    template <int MODE>
     static __device__ __forceinline__ void rhs(const Consts& c, const R* x, const R* lam, R* xd, R& vd, R* ld) {
         using M = Math<R>;
         R u[1];

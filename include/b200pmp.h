@@ -42,7 +42,7 @@
 extern "C" {
 #endif
 
-#define PMP_ABI_VERSION 1
+#define PMP_ABI_VERSION 2
 
 /* systems (dynamics are compile-time functors; problem_params['system_name'] selects one) */
 enum {
@@ -81,6 +81,17 @@ enum {
     PMP_RESULT_NAN = 4
 };
 
+/* pmp_opts_t.flags */
+enum {
+    /* nu = 2 systems: pick u* among the four box-edge minimisers exactly as u_star_2d does
+     * (pontryagin_utils.py:88-158: evaluate H at every candidate, argmin, re-expand about the winner,
+     * argmin again).  Default (flag clear): pick the edge minimiser whose KKT multiplier is
+     * non-negative -- the same point in exact arithmetic (the box-constrained minimiser of a strictly
+     * convex quadratic is the unique KKT point), better conditioned in floating point than comparing
+     * H values, and ~2.5x fewer instructions.  pmp_ustar_batch_cuda always uses the literal form. */
+    PMP_FLAG_USTAR_LITERAL = 1
+};
+
 /* error codes */
 enum {
     PMP_OK = 0,
@@ -116,6 +127,8 @@ typedef struct {
     double dtmin, dtmax; /* 0.0005, 0.5 hard-coded at pontryagin_utils.py:500-501; <=0 disables */
     double safety, factormin, factormax; /* diffrax defaults .9, .2, 10                   */
     double event_level;
+    int32_t flags;       /* PMP_FLAG_* bit mask (0 = defaults)                            */
+    int32_t reserved;    /* must be 0                                                     */
 } pmp_opts_t;
 
 /* Dense ("SaveAt(steps=True, t0=True)") output, the reference's Solution layout: slot 0 is the
@@ -163,6 +176,11 @@ int pmp_rhs_batch_cuda(const pmp_problem_t *problem, int32_t dtype, int64_t n, c
 /* u* = argmin_u H(x,u,lambda) over the input box: x [nx][n], lam [nx][n] -> u [nu][n] */
 int pmp_ustar_batch_cuda(const pmp_problem_t *problem, int32_t dtype, int64_t n, const void *x,
                          const void *lam, void *u, void *cuda_stream);
+
+/* Same with the selection rule the integrator uses for `flags` (PMP_FLAG_USTAR_LITERAL set: identical
+ * to pmp_ustar_batch_cuda; clear: KKT-multiplier selection).  For verification of the two rules. */
+int pmp_ustar_batch_cuda_flags(const pmp_problem_t *problem, int32_t dtype, int32_t flags, int64_t n,
+                               const void *x, const void *lam, void *u, void *cuda_stream);
 
 /* Register-resident dependent-FMA chains on every SM (roofline denominator of bench.py): enqueues
  * one kernel that executes *flops_out floating point operations (written on the host, may be

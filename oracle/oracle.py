@@ -39,7 +39,8 @@ class Opts(C.Structure):
                 ("t0", C.c_double), ("t1", C.c_double), ("dt0", C.c_double),
                 ("rtol", C.c_double), ("atol", C.c_double), ("dtmin", C.c_double),
                 ("dtmax", C.c_double), ("safety", C.c_double), ("factormin", C.c_double),
-                ("factormax", C.c_double), ("event_level", C.c_double)]
+                ("factormax", C.c_double), ("event_level", C.c_double),
+                ("flags", C.c_int32), ("reserved", C.c_int32)]
 
 
 class Dense(C.Structure):
@@ -117,10 +118,10 @@ def lqr_problem(u_lo=-1.0, u_hi=1.0, a=0.01) -> Problem:
 def make_opts(method=TSIT5, dtype=F32, indep=INDEP_TIME, adaptive=1, max_steps=128, force_dtmin=1,
               event=EVENT_NONE, save_dense=0, t0=0.0, t1=-3.0, dt0=-0.1, rtol=1e-5, atol=1e-5,
               dtmin=0.0005, dtmax=0.5, safety=0.9, factormin=0.2, factormax=10.0,
-              event_level=0.0) -> Opts:
+              event_level=0.0, flags=0) -> Opts:
     """Defaults = the flatquad solve (pontryagin_utils.py:496-525, flatquad_landing_experiment.py:368-382)."""
     return Opts(method, dtype, indep, adaptive, max_steps, force_dtmin, event, save_dense, t0, t1,
-                dt0, rtol, atol, dtmin, dtmax, safety, factormin, factormax, event_level)
+                dt0, rtol, atol, dtmin, dtmax, safety, factormin, factormax, event_level, flags, 0)
 
 
 def _np_dtype(dtype):

@@ -31,16 +31,14 @@ n = int(sys.argv[1]) if len(sys.argv) > 1 else 1 << 20
 y64 = flatquad_terminal(n)
 for dtype, tdt, name in ((_capi.F32, torch.float32, "f32"), (_capi.F64, torch.float64, "f64")):
     y = torch.as_tensor(y64, dtype=tdt, device="cuda").contiguous()
-    for method in ("tsit5", "dopri5", "rk4"):
-        for dense in (0, 1):
-            if dense and (method != "tsit5"): continue
-            if method == "rk4":
-                opts = _capi.make_opts(method=method, dtype=dtype, adaptive=0, dt0=-1/32, max_steps=128, save_dense=dense)
-            else:
-                opts = _capi.make_opts(method=method, dtype=dtype, save_dense=dense)
-            out = {}
-            run = lambda: pu.solve_batch_soa(prob, opts, y, out)
-            best, med = time_fn(run, reps=3, warm=1)
-            steps = int(out["n_steps"].sum().item())
-            print(f"{name} {method} dense={dense}: {best:.3f} ms best {med:.3f} med | {n/best/1e3:.2f} Mtraj/s | {steps/best/1e6:.2f} Gattempt/s | mean steps {steps/n:.2f}")
-            del out
+    for method, dense, flags in (("tsit5", 0, 0), ("tsit5", 0, 1), ("tsit5", 1, 0), ("dopri5", 0, 0), ("rk4", 0, 0)):
+        if method == "rk4":
+            opts = _capi.make_opts(method=method, dtype=dtype, adaptive=0, dt0=-1/32, max_steps=128, save_dense=dense, flags=flags)
+        else:
+            opts = _capi.make_opts(method=method, dtype=dtype, save_dense=dense, flags=flags)
+        out = {}
+        run = lambda: pu.solve_batch_soa(prob, opts, y, out)
+        best, med = time_fn(run, reps=3, warm=1)
+        steps = int(out["n_steps"].sum().item())
+        print(f"{name} {method} dense={dense} literal_ustar={flags}: {best:.3f} ms best {med:.3f} med | {n/best/1e3:.2f} Mtraj/s | {steps/best/1e6:.2f} Gattempt/s | mean steps {steps/n:.2f}")
+        del out

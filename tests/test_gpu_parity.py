@@ -284,3 +284,45 @@ def test_full_size_properties_2_20():
     ref = O.solve_batch(oracle_problem("flatquad"), as_oracle_opts(opts), y[:, sub])
     assert abs(a["n_steps"][sub].mean() - ref["n_steps"].mean()) < 0.3
     torch.cuda.synchronize()
+
+
+# ---- u* selection rules --------------------------------------------------------------------------------
+@pytest.mark.parametrize("dtype,tol", [(_capi.F64, 1e-9), (_capi.F32, 2e-3)])
+def test_ustar_kkt_selection_equals_literal_two_pass(dtype, tol):
+    """The integrator's default u* rule (largest KKT multiplier among the edge minimisers) picks the same
+    point as the literal u_star_2d restatement (two-pass argmin of H) on 2^20 random (x, lambda), and
+    both match the CPU oracle."""
+    import ctypes as C
+    import torch
+    n = 1 << 20
+    rng = np.random.Generator(np.random.PCG64(123))
+    x = rng.standard_normal((6, n)) * np.array([1, 1, 0.8, 2, 2, 1])[:, None]
+    lam = rng.standard_normal((6, n)) * 10.0 ** rng.uniform(-1, 3, size=(1, n))
+    dt = torch.float64 if dtype == _capi.F64 else torch.float32
+    xs = torch.as_tensor(x, dtype=dt, device="cuda").contiguous()
+    ls = torch.as_tensor(lam, dtype=dt, device="cuda").contiguous()
+    prob, _ = c_problem("flatquad")
+    L = _capi.lib()
+    us = []
+    for flags in (_capi.FLAG_USTAR_LITERAL, 0):
+        u = torch.empty((2, n), dtype=dt, device="cuda")
+        _capi.check(L.pmp_ustar_batch_cuda_flags(C.byref(prob), dtype, flags, n, xs.data_ptr(), ls.data_ptr(), u.data_ptr(), None))
+        torch.cuda.synchronize()
+        us.append(u.cpu().numpy().astype(np.float64))
+    lit, kkt = us
+    sat = ((lit <= 0) | (lit >= 117.72 - 1e-4)).any(0)
+    assert 0.3 < sat.mean() < 0.95                      # both regimes are exercised
+    assert np.abs(lit - kkt).max() <= tol, np.abs(lit - kkt).max()
+    sub = slice(0, 1 << 16)
+    ref = O.ustar_batch(oracle_problem("flatquad"), O.F64 if dtype == _capi.F64 else O.F32,
+                        xs[:, sub].cpu().numpy(), ls[:, sub].cpu().numpy()).astype(np.float64)
+    assert np.abs(lit[:, sub] - ref).max() <= tol and np.abs(kkt[:, sub] - ref).max() <= tol
+
+
+def test_literal_ustar_flag_gives_same_trajectories_fp64():
+    y = flatquad_terminal(1 << 13)
+    prob, _ = c_problem("flatquad")
+    a = cuda_solve(prob, _capi.make_opts(dtype=_capi.F64), y)
+    b = cuda_solve(prob, _capi.make_opts(dtype=_capi.F64, flags=_capi.FLAG_USTAR_LITERAL), y)
+    assert (a["n_steps"] == b["n_steps"]).mean() >= 0.999
+    assert np.percentile(scaled_err(a["y_end"], b["y_end"], 1e-5), 99.9) <= 0.1
