@@ -60,7 +60,7 @@ int check_opts(const pmp_opts_t* o) {
     } else if (!(o->dt0 > 0)) {
         return fail(PMP_ERR_BAD_ARG, "value-parameterised solve needs dt0 > 0");
     }
-    if ((o->flags & ~PMP_FLAG_USTAR_LITERAL) != 0 || o->reserved != 0) return fail(PMP_ERR_BAD_ARG, "unknown flags / reserved != 0");
+    if ((o->flags & ~(PMP_FLAG_USTAR_LITERAL | 0xff00)) != 0 || o->reserved != 0) return fail(PMP_ERR_BAD_ARG, "unknown flags / reserved != 0");
     if (o->adaptive) {
         if (!(o->rtol >= 0) || !(o->atol >= 0) || !(o->rtol + o->atol > 0)) return fail(PMP_ERR_BAD_ARG, "bad rtol/atol");
         if (!(o->safety > 0) || !(o->factormin > 0) || !(o->factormax >= 1)) return fail(PMP_ERR_BAD_ARG, "bad controller factors");
@@ -110,6 +110,15 @@ int pmp_solve_batch_cuda(const pmp_problem_t* p, const pmp_opts_t* o, int64_t n,
     if (n == 0) return PMP_OK;
     if (!y_f || !y_end) return fail(PMP_ERR_BAD_ARG, "y_f / y_end is NULL");
     if (o->save_dense && !dense) return fail(PMP_ERR_BAD_ARG, "save_dense set but dense is NULL");
+    if (o->save_dense) {
+        const void* ptrs[5] = {dense->ts, dense->x, dense->t, dense->v, dense->vx};
+        for (const void* q : ptrs)
+            if (!q || ((uintptr_t)q & 15u) != 0)
+                return fail(PMP_ERR_BAD_ARG, "dense output: all five leaves are required and must be 16-byte aligned");
+        // slot indices travel as 32-bit integers inside the staging buffer
+        if ((double)n * ((double)o->max_steps + 1.0) >= 4294967295.0)
+            return fail(PMP_ERR_UNSUPPORTED, "dense output: n * (max_steps + 1) must be < 2^32; split the batch");
+    }
     if (!workspace || workspace_bytes < pmp_solve_workspace_bytes(p, o, n))
         return fail(PMP_ERR_BAD_ARG, "workspace is NULL or smaller than pmp_solve_workspace_bytes()");
     if (((uintptr_t)workspace & 255u) != 0) return fail(PMP_ERR_BAD_ARG, "workspace must be 256-byte aligned");

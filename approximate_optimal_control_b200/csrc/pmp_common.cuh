@@ -102,12 +102,14 @@ template <class R> struct SolveOpts {
     R dir;          // +1 / -1
     R rtol, atol, dtmin, dtmax, safety, factormin, factormax, inv_order;
     R event_level;
-    int max_steps, adaptive, force_dtmin, event, use_dtmin, use_dtmax;
+    int max_steps, adaptive, force_dtmin, event, use_dtmin, use_dtmax, dbg;
 };
 
+// dense output leaves, indexable so that cold code can loop over them: 0 ts, 1 t, 2 v, 3 x, 4 vx
 template <class R> struct DensePtrs {
-    R *ts, *x, *t, *v, *vx;
+    R* p[5];
 };
+enum { kDenseTs = 0, kDenseT = 1, kDenseV = 2, kDenseX = 3, kDenseVx = 4 };
 
 template <class R> struct SolveIO {
     const R* y_f;   // [NS][n]

@@ -83,6 +83,112 @@ __global__ void __launch_bounds__(kBlock) prep_kernel(const typename Sys::Consts
 
 static __global__ void reset_counter_kernel(unsigned long long* counter) { *counter = 0ull; }
 
+
+// ---- dense ("SaveAt(steps=True)") write-out through shared memory -----------------------------------
+// One thread owns one trajectory, so its accepted steps land 24 B (x), 24 B (vx) and 3 x 4 B apart
+// from every other lane's: written directly, each warp store instruction touches 32 different
+// sectors with 4 bytes each (the L1 processes that at 1-2 cycles per sector; it dominated the first
+// version of this kernel: 8880 sector writes per trajectory).  Instead every lane appends its
+// accepted nodes to a small per-warp staging buffer in shared memory (kStageB entries per lane, each
+// tagged with its destination slot index), and when any lane's buffer is full the WARP flushes all
+// buffers: one store instruction then covers all buffered nodes of one owner lane, which are
+// consecutive slots of the same trajectory, i.e. one contiguous run in global memory.
+// The +inf tail of a retiring trajectory is written by the warp with 16-byte streaming stores.
+constexpr int kStageB = 4;   // staged nodes per lane
+constexpr int kStageXW = 8;  // words per staged x / vx row (nx <= 8)
+constexpr unsigned kSlotInvalid = 0xffffffffu;
+
+template <class R> struct StageLayout {
+    static constexpr int XS = kStageB * kStageXW + 1;  // per-owner stride (odd: conflict-free owner writes)
+    static constexpr int SS = kStageB * 4 + 1;         // per-owner stride of the scalar rows (ts, t, v, slot)
+    static constexpr int WORDS_PER_WARP = 32 * (2 * XS + SS);
+    static constexpr size_t bytes_per_warp() { return (size_t)WORDS_PER_WARP * sizeof(R); }
+};
+
+__device__ __forceinline__ float pack_slot(unsigned g, float) { return __uint_as_float(g); }
+__device__ __forceinline__ double pack_slot(unsigned g, double) { return __longlong_as_double((long long)g); }
+__device__ __forceinline__ unsigned unpack_slot(float v) { return __float_as_uint(v); }
+__device__ __forceinline__ unsigned unpack_slot(double v) { return (unsigned)__double_as_longlong(v); }
+
+// p[0, len) = val, written by the whole warp with 16-byte stores where alignment allows (p is only
+// element-aligned; len is small: at most (max_steps+1)*nx).  32-bit index arithmetic throughout;
+// cache-streaming stores (evict-first in L2): the tail is never read back by this kernel and must not
+// push the partially written node lines out of L2.
+template <class R>
+__device__ __forceinline__ void warp_fill(R* __restrict__ p, int len, int lane, R val) {
+    constexpr int V = 16 / sizeof(R);
+    int head = (int)((V - (((uintptr_t)p / sizeof(R)) & (V - 1))) & (V - 1));  // elements to the next 16-B boundary
+    head = head < len ? head : len;
+    if (lane < head) __stcs(p + lane, val);
+    R* const pb = p + head;
+    const int body = (len - head) & ~(V - 1);
+    if (sizeof(R) == 4) {
+        const float4 v = make_float4((float)val, (float)val, (float)val, (float)val);
+#pragma unroll 1
+        for (int e = 4 * lane; e < body; e += 128) __stcs(reinterpret_cast<float4*>(pb + e), v);
+    } else {
+        const double2 v = make_double2((double)val, (double)val);
+#pragma unroll 1
+        for (int e = 2 * lane; e < body; e += 64) __stcs(reinterpret_cast<double2*>(pb + e), v);
+    }
+    const int rest = len - head - body;
+    if (lane < rest) __stcs(pb + body + lane, val);
+}
+
+// append one node (global slot g) of this lane's trajectory to its staging rows
+template <class R, int NX>
+__device__ __forceinline__ void stage_push(R* sX, R* sVX, R* sSC, int lane, int& cnt, unsigned g, const R* x, const R* vx,
+                                           R ts, R t, R v) {
+    using SL = StageLayout<R>;
+    R* px = sX + lane * SL::XS + cnt * kStageXW;
+    R* pv = sVX + lane * SL::XS + cnt * kStageXW;
+#pragma unroll
+    for (int q = 0; q < NX; q++) { px[q] = x[q]; pv[q] = vx[q]; }
+    R* ps = sSC + lane * SL::SS + cnt * 4;
+    ps[0] = ts; ps[1] = t; ps[2] = v; ps[3] = pack_slot(g, R(0));
+    cnt += 1;
+}
+
+// the warp writes every staged node of every lane to global memory, then empties the buffers
+template <class R, int NX>
+__device__ __forceinline__ void stage_flush(const DensePtrs<R>& d, R* sX, R* sVX, R* sSC, int lane, int& cnt) {
+    using SL = StageLayout<R>;
+    static_assert(kStageB * kStageXW == 32, "one staged x row set per warp store");
+    __syncwarp();
+    {   // x and vx: iteration o handles owner lane o; lane -> (node j = lane/8, component q = lane%8)
+        const int j = lane >> 3, q = lane & 7;
+        R* const gx = d.p[kDenseX];
+        R* const gvx = d.p[kDenseVx];
+#pragma unroll 1
+        for (int o = 0; o < 32; o++) {
+            const unsigned g = unpack_slot(sSC[o * SL::SS + j * 4 + 3]);
+            if (g != kSlotInvalid && q < NX) {
+                const size_t off = (size_t)g * NX + q;
+                gx[off] = sX[o * SL::XS + lane];
+                gvx[off] = sVX[o * SL::XS + lane];
+            }
+        }
+    }
+    {   // ts, t, v: iteration handles 8 owner lanes; lane -> (owner = 8*it + lane/4, node j = lane%4)
+        const int j = lane & 3;
+#pragma unroll 1
+        for (int it = 0; it < 4; it++) {
+            const R* row = sSC + (8 * it + (lane >> 2)) * SL::SS + j * 4;
+            const unsigned g = unpack_slot(row[3]);
+            if (g != kSlotInvalid) {
+                d.p[kDenseTs][g] = row[0];
+                d.p[kDenseT][g] = row[1];
+                d.p[kDenseV][g] = row[2];
+            }
+        }
+    }
+    __syncwarp();
+#pragma unroll
+    for (int j = 0; j < kStageB; j++) sSC[lane * SL::SS + j * 4 + 3] = pack_slot(kSlotInvalid, R(0));
+    cnt = 0;
+    __syncwarp();
+}
+
 // ---- the integrator -----------------------------------------------------------------------------
 template <class Sys, class R, int METHOD, bool DENSE, bool VALUE, bool ULIT, int MINB>
 __global__ void __launch_bounds__(kBlock, MINB)
@@ -114,7 +220,29 @@ solve_kernel(const typename Sys::Consts sc, const SolveOpts<R> o, const SolveIO<
     long long w_next = 0, w_end = 0;
     bool exhausted = false;
 
+    // dense write-out staging (shared memory, one private region per warp)
+    extern __shared__ __align__(16) unsigned char pmp_smem[];
+    R* sX = nullptr; R* sVX = nullptr; R* sSC = nullptr;
+    int stage_cnt = 0;
+    if (DENSE) {
+        using SL = StageLayout<R>;
+        static_assert(NX <= kStageXW, "staging rows hold at most 8 state components");
+        R* wbase = reinterpret_cast<R*>(pmp_smem) + (size_t)(threadIdx.x >> 5) * SL::WORDS_PER_WARP;
+        sX = wbase; sVX = wbase + 32 * SL::XS; sSC = wbase + 64 * SL::XS;
+#pragma unroll
+        for (int j = 0; j < kStageB; j++) sSC[lane * SL::SS + j * 4 + 3] = pack_slot(kSlotInvalid, R(0));
+        __syncwarp();
+    }
+
+    bool drain = false;  // DENSE: no work left, flush the staging buffers once more and leave
     while (true) {
+        // a lane appends at most one node per iteration (an accepted step): make room first.  This is
+        // the only call site of the flush (code size: the loop body must stay inside the I-cache).
+        if (DENSE && (drain || __any_sync(FULL, stage_cnt >= kStageB))) {
+            if (o.dbg & 2) stage_cnt = 0;
+            else stage_flush<R, NX>(io.dense, sX, sVX, sSC, lane, stage_cnt);
+        }
+        if (DENSE && drain) break;
         // =============================== retire + refill =========================================
         const bool fin = has_work && finished;
         unsigned want = __ballot_sync(FULL, fin || !has_work);
@@ -134,24 +262,11 @@ solve_kernel(const typename Sys::Consts sc, const SolveOpts<R> o, const SolveIO<
                 if (io.result) io.result[idx] = result;
                 has_work = false;
             }
-            if (DENSE) {
-                // pad the unused slots of every retiring trajectory with +inf (ts: dir*inf), the warp
-                // writing each tail cooperatively so that the stores coalesce.
-                unsigned rm = __ballot_sync(FULL, fin);
-                while (rm) {
-                    const int src = __ffs(rm) - 1;
-                    rm &= rm - 1;
-                    const long long ti = __shfl_sync(FULL, idx, src);
-                    const int first = __shfl_sync(FULL, nacc, src) + 1;
-                    const R inf = M::inf();
-                    const int tail = S1 - first;
-                    if (io.dense.ts) { R* p = io.dense.ts + ti * S1 + first; for (int e = lane; e < tail; e += 32) p[e] = inf * o.dir; }
-                    if (io.dense.t) { R* p = io.dense.t + ti * S1 + first; for (int e = lane; e < tail; e += 32) p[e] = inf; }
-                    if (io.dense.v) { R* p = io.dense.v + ti * S1 + first; for (int e = lane; e < tail; e += 32) p[e] = inf; }
-                    if (io.dense.x) { R* p = io.dense.x + (ti * S1 + first) * NX; for (int e = lane; e < tail * NX; e += 32) p[e] = inf; }
-                    if (io.dense.vx) { R* p = io.dense.vx + (ti * S1 + first) * NX; for (int e = lane; e < tail * NX; e += 32) p[e] = inf; }
-                }
-            }
+            // DENSE: the +inf tails of the retiring trajectories are written after the refill below, so
+            // that the refill's loads are in flight while the padding stores are issued
+            const unsigned pad_mask = DENSE ? __ballot_sync(FULL, fin) : 0u;
+            const long long pad_idx = idx;
+            const int pad_first = nacc + 1;
             // hand out new trajectories to the lanes in `want`, in rank order
             while (want && !exhausted) {
                 if (w_next >= w_end) {
@@ -186,15 +301,17 @@ solve_kernel(const typename Sys::Consts sc, const SolveOpts<R> o, const SolveIO<
                     // NaN terminal state (levelsets.py:1233): retire at once with result 4
                     finished = bad || !(tprev < o.T1);
                     if (bad) result = PMP_RESULT_NAN;
-                    if (DENSE) {  // slot 0 = the terminal state (SaveAt(t0=True))
-                        const long long s0 = idx * S1;
-                        if (io.dense.ts) io.dense.ts[s0] = tprev * o.dir;
-                        if (io.dense.t) io.dense.t[s0] = VALUE ? y[AUX] : aux_fixed;
-                        if (io.dense.v) io.dense.v[s0] = VALUE ? tprev * o.dir : y[AUX];
+                    if (DENSE) {  // slot 0 = the terminal state (SaveAt(t0=True)); written directly (1 node
+                                  // in ~20, not worth a second staging slot per iteration)
+                        const size_t s0 = (size_t)idx * S1;
+                        const R c0 = tprev * o.dir;
+                        io.dense.p[kDenseTs][s0] = c0;
+                        io.dense.p[kDenseT][s0] = VALUE ? y[AUX] : aux_fixed;
+                        io.dense.p[kDenseV][s0] = VALUE ? c0 : y[AUX];
 #pragma unroll
                         for (int q = 0; q < NX; q++) {
-                            if (io.dense.x) io.dense.x[s0 * NX + q] = y[q];
-                            if (io.dense.vx) io.dense.vx[s0 * NX + q] = y[NX + q];
+                            io.dense.p[kDenseX][s0 * NX + q] = y[q];
+                            io.dense.p[kDenseVx][s0 * NX + q] = y[NX + q];
                         }
                     }
                 }
@@ -202,8 +319,29 @@ solve_kernel(const typename Sys::Consts sc, const SolveOpts<R> o, const SolveIO<
                 want &= ~took;
                 w_next += __popc(took);
             }
+            if (DENSE) {
+                // pad the unused slots of every retired trajectory with +inf (ts: dir*inf): the warp
+                // writes each tail with 16-byte stores; every slot of the output is written once.
+                unsigned rm = (o.dbg & 1) ? 0u : pad_mask;
+                const R inf = M::inf();
+                while (rm) {
+                    const int src = __ffs(rm) - 1;
+                    rm &= rm - 1;
+                    const size_t first = (size_t)__shfl_sync(FULL, pad_idx, src) * S1 + __shfl_sync(FULL, pad_first, src);
+                    const int tail = S1 - __shfl_sync(FULL, pad_first, src);
+                    warp_fill<R>(io.dense.p[kDenseTs] + first, tail, lane, inf * o.dir);
+                    warp_fill<R>(io.dense.p[kDenseT] + first, tail, lane, inf);
+                    warp_fill<R>(io.dense.p[kDenseV] + first, tail, lane, inf);
+                    warp_fill<R>(io.dense.p[kDenseX] + first * NX, tail * NX, lane, inf);
+                    warp_fill<R>(io.dense.p[kDenseVx] + first * NX, tail * NX, lane, inf);
+                }
+            }
         }
-        if (!__any_sync(FULL, has_work)) break;
+        if (!__any_sync(FULL, has_work)) {
+            if (!DENSE) break;
+            drain = true;
+            continue;
+        }
         const bool live = has_work && !finished;
 
         // =============================== one step attempt ========================================
@@ -315,16 +453,9 @@ solve_kernel(const typename Sys::Consts sc, const SolveOpts<R> o, const SolveIO<
                     if (TB::FSAL) k[0][q] = k[S - 1][q];
                 }
                 if (DENSE && nacc < S1) {
-                    const long long s = idx * S1 + nacc;
                     const R clock = tprev * o.dir;
-                    if (io.dense.ts) io.dense.ts[s] = clock;
-                    if (io.dense.t) io.dense.t[s] = VALUE ? y[AUX] : aux_fixed + (clock - clock0);
-                    if (io.dense.v) io.dense.v[s] = VALUE ? clock : y[AUX];
-#pragma unroll
-                    for (int q = 0; q < NX; q++) {
-                        if (io.dense.x) io.dense.x[s * NX + q] = y[q];
-                        if (io.dense.vx) io.dense.vx[s * NX + q] = y[NX + q];
-                    }
+                    stage_push<R, NX>(sX, sVX, sSC, lane, stage_cnt, (unsigned)(idx * S1 + nacc), y, y + NX, clock,
+                                      VALUE ? y[AUX] : aux_fixed + (clock - clock0), VALUE ? clock : y[AUX]);
                 }
                 nan_state = bad;
             }
@@ -353,6 +484,7 @@ template <class R> inline SolveOpts<R> make_solve_opts(const pmp_opts_t& o, int 
     s.safety = R(o.safety); s.factormin = R(o.factormin); s.factormax = R(o.factormax);
     s.inv_order = R(1.0 / order);
     s.event_level = R(o.event_level);
+    s.dbg = o.flags >> 8;
     s.max_steps = o.max_steps; s.adaptive = o.adaptive; s.force_dtmin = o.force_dtmin; s.event = o.event;
     return s;
 }
@@ -377,7 +509,12 @@ int launch_one(const pmp_problem_t& p, const pmp_opts_t& o, long long n, const v
     cudaError_t e = cudaGetDevice(&dev);
     if (e != cudaSuccess) return (int)e;
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, kBlock, 0);
+    const size_t smem = DENSE ? (size_t)(kBlock / 32) * StageLayout<R>::bytes_per_warp() : 0;
+    if (smem > 48 * 1024) {
+        e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return (int)e;
+    }
+    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, kBlock, smem);
     if (e != cudaSuccess) return (int)e;
     if (occ < 1) occ = 1;
     long long need = (n + kBlock - 1) / kBlock;
@@ -392,9 +529,9 @@ int launch_one(const pmp_problem_t& p, const pmp_opts_t& o, long long n, const v
     io.y_end = (R*)y_end;
     io.n_accepted = n_acc; io.n_steps = n_steps; io.result = result;
     io.n = n;
-    io.dense = DensePtrs<R>{nullptr, nullptr, nullptr, nullptr, nullptr};
+    io.dense = DensePtrs<R>{{nullptr, nullptr, nullptr, nullptr, nullptr}};
     if (DENSE && dense)
-        io.dense = DensePtrs<R>{(R*)dense->ts, (R*)dense->x, (R*)dense->t, (R*)dense->v, (R*)dense->vx};
+        io.dense = DensePtrs<R>{{(R*)dense->ts, (R*)dense->t, (R*)dense->v, (R*)dense->x, (R*)dense->vx}};
     if (TB::FSAL) {
         prep_kernel<Sys, R, VALUE, ULIT><<<(unsigned)need, kBlock, 0, st>>>(sc, (const R*)y_f, (R*)((char*)workspace + 256), n,
                                                                     io.counter);
@@ -402,7 +539,7 @@ int launch_one(const pmp_problem_t& p, const pmp_opts_t& o, long long n, const v
         reset_counter_kernel<<<1, 1, 0, st>>>(io.counter);
     }
     const SolveOpts<R> so = make_solve_opts<R>(o, TB::ORDER);
-    kern<<<grid, kBlock, 0, st>>>(sc, so, io);
+    kern<<<grid, kBlock, smem, st>>>(sc, so, io);
     return (int)cudaGetLastError();
 }
 

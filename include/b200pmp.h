@@ -133,8 +133,8 @@ typedef struct {
 
 /* Dense ("SaveAt(steps=True, t0=True)") output, the reference's Solution layout: slot 0 is the
  * terminal state, one slot per ACCEPTED step, unused slots are +inf (ts: -inf when integrating
- * backward, cf. visualiser.py:76-99).  S1 = max_steps + 1 slots per trajectory.  Any pointer may
- * be NULL to skip that leaf. */
+ * backward, cf. visualiser.py:76-99).  S1 = max_steps + 1 slots per trajectory.  All five leaves are
+ * required, 16-byte aligned, and n * S1 must be < 2^32. */
 typedef struct {
     void *ts; /* [n][S1]     */
     void *x;  /* [n][S1][nx] */
