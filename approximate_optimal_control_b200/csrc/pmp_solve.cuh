@@ -86,29 +86,31 @@ static __global__ void reset_counter_kernel(unsigned long long* counter) { *coun
 
 // ---- dense ("SaveAt(steps=True)") write-out through shared memory -----------------------------------
 // One thread owns one trajectory, so its accepted steps land 24 B (x), 24 B (vx) and 3 x 4 B apart
-// from every other lane's: written directly, each warp store instruction touches 32 different
-// sectors with 4 bytes each (the L1 processes that at 1-2 cycles per sector; it dominated the first
-// version of this kernel: 8880 sector writes per trajectory).  Instead every lane appends its
-// accepted nodes to a small per-warp staging buffer in shared memory (kStageB entries per lane, each
-// tagged with its destination slot index), and when any lane's buffer is full the WARP flushes all
-// buffers: one store instruction then covers all buffered nodes of one owner lane, which are
-// consecutive slots of the same trajectory, i.e. one contiguous run in global memory.
-// The +inf tail of a retiring trajectory is written by the warp with 16-byte streaming stores.
-constexpr int kStageB = 4;   // staged nodes per lane
-constexpr int kStageXW = 8;  // words per staged x / vx row (nx <= 8)
-constexpr unsigned kSlotInvalid = 0xffffffffu;
+// from every other lane's.  Written directly, each warp store instruction touches 32 different
+// sectors with 4 bytes each -- and, worse, every such store is a PARTIAL-sector write to a sector
+// that is not in L2: with ECC the L2 must first fetch the sector from DRAM, the store occupies a
+// miss slot for a DRAM round trip, the L1/LSU backs up behind it and even the refill loads of the
+// other warps stall for microseconds (measured: 2.9 us per refill, 17-28 M sector fills per launch).
+// So nodes are written in SECTOR-ALIGNED GROUPS instead.  Slots are numbered globally
+// (g = trajectory * S1 + slot); 4 consecutive slots of a vector leaf (x, vx) and 8 of a scalar leaf
+// (ts, t, v) start on a 32-byte boundary whenever g is a multiple of 4 / 8.  Each lane keeps the
+// nodes of its current group in a shared-memory ring; when a lane completes a group the WARP writes
+// it with one store instruction per leaf (whole sectors, no fill).  When a trajectory retires, its
+// last, partial group is completed with the +inf padding that follows it anyway, and the rest of
+// the tail is written with 16-byte streaming stores.  Only the first and last sector of a
+// trajectory's row can be partial (rows of S1 slots are not sector aligned).
+constexpr int kGrpV = 4;  // slots per vector-leaf group
+constexpr int kGrpS = 8;  // slots per scalar-leaf group
 
-template <class R> struct StageLayout {
-    static constexpr int XS = kStageB * kStageXW + 1;  // per-owner stride (odd: conflict-free owner writes)
-    static constexpr int SS = kStageB * 4 + 1;         // per-owner stride of the scalar rows (ts, t, v, slot)
+template <class R, int NX> struct StageLayout {
+    static_assert((NX * sizeof(R) * kGrpV) % 32 == 0, "vector groups must be whole sectors");
+    static_assert((sizeof(R) * kGrpS) % 32 == 0, "scalar groups must be whole sectors");
+    static_assert(kGrpV * NX <= 32 && 3 * kGrpS <= 32, "one warp store per group");
+    static constexpr int XS = (kGrpV * NX) | 1;  // per-owner stride, odd => conflict-free owner writes
+    static constexpr int SS = (kGrpS * 3) | 1;
     static constexpr int WORDS_PER_WARP = 32 * (2 * XS + SS);
     static constexpr size_t bytes_per_warp() { return (size_t)WORDS_PER_WARP * sizeof(R); }
 };
-
-__device__ __forceinline__ float pack_slot(unsigned g, float) { return __uint_as_float(g); }
-__device__ __forceinline__ double pack_slot(unsigned g, double) { return __longlong_as_double((long long)g); }
-__device__ __forceinline__ unsigned unpack_slot(float v) { return __float_as_uint(v); }
-__device__ __forceinline__ unsigned unpack_slot(double v) { return (unsigned)__double_as_longlong(v); }
 
 // p[0, len) = val, written by the whole warp with 16-byte stores where alignment allows (p is only
 // element-aligned; len is small: at most (max_steps+1)*nx).  32-bit index arithmetic throughout;
@@ -135,58 +137,48 @@ __device__ __forceinline__ void warp_fill(R* __restrict__ p, int len, int lane, 
     if (lane < rest) __stcs(pb + body + lane, val);
 }
 
-// append one node (global slot g) of this lane's trajectory to its staging rows
+// store one node (global slot g) of this lane's trajectory in its rings
 template <class R, int NX>
-__device__ __forceinline__ void stage_push(R* sX, R* sVX, R* sSC, int lane, int& cnt, unsigned g, const R* x, const R* vx,
-                                           R ts, R t, R v) {
-    using SL = StageLayout<R>;
-    R* px = sX + lane * SL::XS + cnt * kStageXW;
-    R* pv = sVX + lane * SL::XS + cnt * kStageXW;
+__device__ __forceinline__ void stage_put(R* sX, R* sVX, R* sSC, int lane, unsigned g, const R* x, const R* vx, R ts, R t, R v) {
+    using SL = StageLayout<R, NX>;
+    R* px = sX + lane * SL::XS + (g & (kGrpV - 1)) * NX;
+    R* pv = sVX + lane * SL::XS + (g & (kGrpV - 1)) * NX;
 #pragma unroll
     for (int q = 0; q < NX; q++) { px[q] = x[q]; pv[q] = vx[q]; }
-    R* ps = sSC + lane * SL::SS + cnt * 4;
-    ps[0] = ts; ps[1] = t; ps[2] = v; ps[3] = pack_slot(g, R(0));
-    cnt += 1;
+    R* ps = sSC + lane * SL::SS + (g & (kGrpS - 1)) * 3;
+    ps[0] = ts; ps[1] = t; ps[2] = v;
 }
 
-// the warp writes every staged node of every lane to global memory, then empties the buffers
+// the warp writes vector-leaf group G (slots 4G..4G+3) of owner lane o: one store per leaf.
+// Slots outside [row_lo, row_hi) belong to a neighbouring trajectory and are skipped; slots >= valid_hi
+// are past the last node and get +inf (this is how a partial last group is closed).
 template <class R, int NX>
-__device__ __forceinline__ void stage_flush(const DensePtrs<R>& d, R* sX, R* sVX, R* sSC, int lane, int& cnt) {
-    using SL = StageLayout<R>;
-    static_assert(kStageB * kStageXW == 32, "one staged x row set per warp store");
-    __syncwarp();
-    {   // x and vx: iteration o handles owner lane o; lane -> (node j = lane/8, component q = lane%8)
-        const int j = lane >> 3, q = lane & 7;
-        R* const gx = d.p[kDenseX];
-        R* const gvx = d.p[kDenseVx];
-#pragma unroll 1
-        for (int o = 0; o < 32; o++) {
-            const unsigned g = unpack_slot(sSC[o * SL::SS + j * 4 + 3]);
-            if (g != kSlotInvalid && q < NX) {
-                const size_t off = (size_t)g * NX + q;
-                gx[off] = sX[o * SL::XS + lane];
-                gvx[off] = sVX[o * SL::XS + lane];
-            }
+__device__ __forceinline__ void write_group_v(const DensePtrs<R>& d, const R* sX, const R* sVX, int lane, int o, unsigned G,
+                                              unsigned row_lo, unsigned row_hi, unsigned valid_hi, R inf) {
+    using SL = StageLayout<R, NX>;
+    if (lane < kGrpV * NX) {
+        const unsigned slot = G * kGrpV + lane / NX;
+        if (slot >= row_lo && slot < row_hi) {
+            const size_t off = (size_t)G * (kGrpV * NX) + lane;
+            const bool have = slot < valid_hi;
+            d.p[kDenseX][off] = have ? sX[o * SL::XS + lane] : inf;
+            d.p[kDenseVx][off] = have ? sVX[o * SL::XS + lane] : inf;
         }
     }
-    {   // ts, t, v: iteration handles 8 owner lanes; lane -> (owner = 8*it + lane/4, node j = lane%4)
-        const int j = lane & 3;
-#pragma unroll 1
-        for (int it = 0; it < 4; it++) {
-            const R* row = sSC + (8 * it + (lane >> 2)) * SL::SS + j * 4;
-            const unsigned g = unpack_slot(row[3]);
-            if (g != kSlotInvalid) {
-                d.p[kDenseTs][g] = row[0];
-                d.p[kDenseT][g] = row[1];
-                d.p[kDenseV][g] = row[2];
-            }
+}
+// scalar-leaf group G (slots 8G..8G+7) of owner o: lanes 0-7 -> ts, 8-15 -> t, 16-23 -> v
+template <class R, int NX>
+__device__ __forceinline__ void write_group_s(const DensePtrs<R>& d, const R* sSC, int lane, int o, unsigned G,
+                                              unsigned row_lo, unsigned row_hi, unsigned valid_hi, R inf, R inf_ts) {
+    using SL = StageLayout<R, NX>;
+    if (lane < 3 * kGrpS) {
+        const int f = lane >> 3, j = lane & (kGrpS - 1);
+        const unsigned slot = G * kGrpS + j;
+        if (slot >= row_lo && slot < row_hi) {
+            const R pad = f == 0 ? inf_ts : inf;
+            d.p[f][slot] = slot < valid_hi ? sSC[o * SL::SS + j * 3 + f] : pad;  // leaves 0,1,2 = ts,t,v
         }
     }
-    __syncwarp();
-#pragma unroll
-    for (int j = 0; j < kStageB; j++) sSC[lane * SL::SS + j * 4 + 3] = pack_slot(kSlotInvalid, R(0));
-    cnt = 0;
-    __syncwarp();
 }
 
 // ---- the integrator -----------------------------------------------------------------------------
@@ -223,26 +215,15 @@ solve_kernel(const typename Sys::Consts sc, const SolveOpts<R> o, const SolveIO<
     // dense write-out staging (shared memory, one private region per warp)
     extern __shared__ __align__(16) unsigned char pmp_smem[];
     R* sX = nullptr; R* sVX = nullptr; R* sSC = nullptr;
-    int stage_cnt = 0;
+    unsigned g_cur = 0, row0 = 0;           // global slot of the newest node; first slot of the row
+    bool ready_v = false, ready_s = false;  // the newest node completed a vector / scalar group
     if (DENSE) {
-        using SL = StageLayout<R>;
-        static_assert(NX <= kStageXW, "staging rows hold at most 8 state components");
+        using SL = StageLayout<R, NX>;
         R* wbase = reinterpret_cast<R*>(pmp_smem) + (size_t)(threadIdx.x >> 5) * SL::WORDS_PER_WARP;
         sX = wbase; sVX = wbase + 32 * SL::XS; sSC = wbase + 64 * SL::XS;
-#pragma unroll
-        for (int j = 0; j < kStageB; j++) sSC[lane * SL::SS + j * 4 + 3] = pack_slot(kSlotInvalid, R(0));
-        __syncwarp();
     }
 
-    bool drain = false;  // DENSE: no work left, flush the staging buffers once more and leave
     while (true) {
-        // a lane appends at most one node per iteration (an accepted step): make room first.  This is
-        // the only call site of the flush (code size: the loop body must stay inside the I-cache).
-        if (DENSE && (drain || __any_sync(FULL, stage_cnt >= kStageB))) {
-            if (o.dbg & 2) stage_cnt = 0;
-            else stage_flush<R, NX>(io.dense, sX, sVX, sSC, lane, stage_cnt);
-        }
-        if (DENSE && drain) break;
         // =============================== retire + refill =========================================
         const bool fin = has_work && finished;
         unsigned want = __ballot_sync(FULL, fin || !has_work);
@@ -261,12 +242,27 @@ solve_kernel(const typename Sys::Consts sc, const SolveOpts<R> o, const SolveIO<
                 if (io.n_steps) io.n_steps[idx] = nsteps;
                 if (io.result) io.result[idx] = result;
                 has_work = false;
+                ready_v = false; ready_s = false;  // DENSE: the retirement code writes the last group
             }
             // DENSE: the +inf tails of the retiring trajectories are written after the refill below, so
             // that the refill's loads are in flight while the padding stores are issued
             const unsigned pad_mask = DENSE ? __ballot_sync(FULL, fin) : 0u;
-            const long long pad_idx = idx;
-            const int pad_first = nacc + 1;
+            const unsigned pad_g = g_cur, pad_row0 = row0;  // newest node and row start of the retiring lane
+            if (DENSE) {
+                // The last group of a retiring trajectory (complete or not) is written by the retirement
+                // code below: it must leave the rings before the refill reuses them.
+                const R inf = M::inf();
+                __syncwarp();
+                unsigned rm = (o.dbg & 1) ? 0u : pad_mask;
+                while (rm) {
+                    const int src = __ffs(rm) - 1;
+                    rm &= rm - 1;
+                    const unsigned gl = __shfl_sync(FULL, pad_g, src), r0 = __shfl_sync(FULL, pad_row0, src);
+                    write_group_v<R, NX>(io.dense, sX, sVX, lane, src, gl / kGrpV, r0, r0 + S1, gl + 1, inf);
+                    write_group_s<R, NX>(io.dense, sSC, lane, src, gl / kGrpS, r0, r0 + S1, gl + 1, inf, inf * o.dir);
+                }
+                __syncwarp();
+            }
             // hand out new trajectories to the lanes in `want`, in rank order
             while (want && !exhausted) {
                 if (w_next >= w_end) {
@@ -301,18 +297,13 @@ solve_kernel(const typename Sys::Consts sc, const SolveOpts<R> o, const SolveIO<
                     // NaN terminal state (levelsets.py:1233): retire at once with result 4
                     finished = bad || !(tprev < o.T1);
                     if (bad) result = PMP_RESULT_NAN;
-                    if (DENSE) {  // slot 0 = the terminal state (SaveAt(t0=True)); written directly (1 node
-                                  // in ~20, not worth a second staging slot per iteration)
-                        const size_t s0 = (size_t)idx * S1;
+                    if (DENSE) {  // slot 0 = the terminal state (SaveAt(t0=True))
+                        row0 = (unsigned)(idx * S1);
+                        g_cur = row0;
                         const R c0 = tprev * o.dir;
-                        io.dense.p[kDenseTs][s0] = c0;
-                        io.dense.p[kDenseT][s0] = VALUE ? y[AUX] : aux_fixed;
-                        io.dense.p[kDenseV][s0] = VALUE ? c0 : y[AUX];
-#pragma unroll
-                        for (int q = 0; q < NX; q++) {
-                            io.dense.p[kDenseX][s0 * NX + q] = y[q];
-                            io.dense.p[kDenseVx][s0 * NX + q] = y[NX + q];
-                        }
+                        stage_put<R, NX>(sX, sVX, sSC, lane, g_cur, y, y + NX, c0, VALUE ? y[AUX] : aux_fixed, VALUE ? c0 : y[AUX]);
+                        ready_v = (g_cur & (kGrpV - 1)) == kGrpV - 1;
+                        ready_s = (g_cur & (kGrpS - 1)) == kGrpS - 1;
                     }
                 }
                 const unsigned took = __ballot_sync(FULL, take);
@@ -320,29 +311,46 @@ solve_kernel(const typename Sys::Consts sc, const SolveOpts<R> o, const SolveIO<
                 w_next += __popc(took);
             }
             if (DENSE) {
-                // pad the unused slots of every retired trajectory with +inf (ts: dir*inf): the warp
-                // writes each tail with 16-byte stores; every slot of the output is written once.
+                // +inf tails of the retired trajectories (ts: dir*inf), from the end of their last group to
+                // the end of the row, 16-byte streaming stores; every slot of the output is written once.
+                __syncwarp();
                 unsigned rm = (o.dbg & 1) ? 0u : pad_mask;
                 const R inf = M::inf();
                 while (rm) {
                     const int src = __ffs(rm) - 1;
                     rm &= rm - 1;
-                    const size_t first = (size_t)__shfl_sync(FULL, pad_idx, src) * S1 + __shfl_sync(FULL, pad_first, src);
-                    const int tail = S1 - __shfl_sync(FULL, pad_first, src);
-                    warp_fill<R>(io.dense.p[kDenseTs] + first, tail, lane, inf * o.dir);
-                    warp_fill<R>(io.dense.p[kDenseT] + first, tail, lane, inf);
-                    warp_fill<R>(io.dense.p[kDenseV] + first, tail, lane, inf);
-                    warp_fill<R>(io.dense.p[kDenseX] + first * NX, tail * NX, lane, inf);
-                    warp_fill<R>(io.dense.p[kDenseVx] + first * NX, tail * NX, lane, inf);
+                    const unsigned gl = __shfl_sync(FULL, pad_g, src), row_hi = __shfl_sync(FULL, pad_row0, src) + S1;
+                    const unsigned pv = min((gl / kGrpV + 1) * kGrpV, row_hi), ps = min((gl / kGrpS + 1) * kGrpS, row_hi);
+                    warp_fill<R>(io.dense.p[kDenseTs] + ps, (int)(row_hi - ps), lane, inf * o.dir);
+                    warp_fill<R>(io.dense.p[kDenseT] + ps, (int)(row_hi - ps), lane, inf);
+                    warp_fill<R>(io.dense.p[kDenseV] + ps, (int)(row_hi - ps), lane, inf);
+                    warp_fill<R>(io.dense.p[kDenseX] + (size_t)pv * NX, (int)(row_hi - pv) * NX, lane, inf);
+                    warp_fill<R>(io.dense.p[kDenseVx] + (size_t)pv * NX, (int)(row_hi - pv) * NX, lane, inf);
                 }
             }
         }
-        if (!__any_sync(FULL, has_work)) {
-            if (!DENSE) break;
-            drain = true;
-            continue;
-        }
+        if (!__any_sync(FULL, has_work)) break;
         const bool live = has_work && !finished;
+        if (DENSE && !(o.dbg & 2)) {
+            // write the groups completed by the previous attempt or by the refill above.  This is the
+            // only in-loop call site (code size: the loop body must stay inside the I-cache).
+            const R inf = M::inf();
+            __syncwarp();  // the owners' ring stores must be visible to the lanes that write the group
+            unsigned mv = __ballot_sync(FULL, ready_v), ms = __ballot_sync(FULL, ready_s);
+            while (mv) {
+                const int src = __ffs(mv) - 1;
+                mv &= mv - 1;
+                write_group_v<R, NX>(io.dense, sX, sVX, lane, src, __shfl_sync(FULL, g_cur, src) / kGrpV,
+                                     __shfl_sync(FULL, row0, src), 0xffffffffu, 0xffffffffu, inf);
+            }
+            while (ms) {
+                const int src = __ffs(ms) - 1;
+                ms &= ms - 1;
+                write_group_s<R, NX>(io.dense, sSC, lane, src, __shfl_sync(FULL, g_cur, src) / kGrpS,
+                                     __shfl_sync(FULL, row0, src), 0xffffffffu, 0xffffffffu, inf, inf * o.dir);
+            }
+        }
+        ready_v = false; ready_s = false;
 
         // =============================== one step attempt ========================================
         const R dt = tnext - tprev;
@@ -454,8 +462,11 @@ solve_kernel(const typename Sys::Consts sc, const SolveOpts<R> o, const SolveIO<
                 }
                 if (DENSE && nacc < S1) {
                     const R clock = tprev * o.dir;
-                    stage_push<R, NX>(sX, sVX, sSC, lane, stage_cnt, (unsigned)(idx * S1 + nacc), y, y + NX, clock,
-                                      VALUE ? y[AUX] : aux_fixed + (clock - clock0), VALUE ? clock : y[AUX]);
+                    g_cur = row0 + (unsigned)nacc;
+                    stage_put<R, NX>(sX, sVX, sSC, lane, g_cur, y, y + NX, clock,
+                                     VALUE ? y[AUX] : aux_fixed + (clock - clock0), VALUE ? clock : y[AUX]);
+                    ready_v = (g_cur & (kGrpV - 1)) == kGrpV - 1;
+                    ready_s = (g_cur & (kGrpS - 1)) == kGrpS - 1;
                 }
                 nan_state = bad;
             }
@@ -509,7 +520,7 @@ int launch_one(const pmp_problem_t& p, const pmp_opts_t& o, long long n, const v
     cudaError_t e = cudaGetDevice(&dev);
     if (e != cudaSuccess) return (int)e;
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    const size_t smem = DENSE ? (size_t)(kBlock / 32) * StageLayout<R>::bytes_per_warp() : 0;
+    const size_t smem = DENSE ? (size_t)(kBlock / 32) * StageLayout<R, Sys::NX>::bytes_per_warp() : 0;
     if (smem > 48 * 1024) {
         e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return (int)e;
