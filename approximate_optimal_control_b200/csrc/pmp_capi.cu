@@ -60,7 +60,7 @@ int check_opts(const pmp_opts_t* o) {
     } else if (!(o->dt0 > 0)) {
         return fail(PMP_ERR_BAD_ARG, "value-parameterised solve needs dt0 > 0");
     }
-    if ((o->flags & ~(PMP_FLAG_USTAR_LITERAL | 0xff00)) != 0 || o->reserved != 0) return fail(PMP_ERR_BAD_ARG, "unknown flags / reserved != 0");
+    if ((o->flags & ~PMP_FLAG_USTAR_LITERAL) != 0 || o->reserved != 0) return fail(PMP_ERR_BAD_ARG, "unknown flags / reserved != 0");
     if (o->adaptive) {
         if (!(o->rtol >= 0) || !(o->atol >= 0) || !(o->rtol + o->atol > 0)) return fail(PMP_ERR_BAD_ARG, "bad rtol/atol");
         if (!(o->safety > 0) || !(o->factormin > 0) || !(o->factormax >= 1)) return fail(PMP_ERR_BAD_ARG, "bad controller factors");

@@ -102,7 +102,7 @@ template <class R> struct SolveOpts {
     R dir;          // +1 / -1
     R rtol, atol, dtmin, dtmax, safety, factormin, factormax, inv_order;
     R event_level;
-    int max_steps, adaptive, force_dtmin, event, use_dtmin, use_dtmax, dbg;
+    int max_steps, adaptive, force_dtmin, event, use_dtmin, use_dtmax;
 };
 
 // dense output leaves, indexable so that cold code can loop over them: 0 ts, 1 t, 2 v, 3 x, 4 vx

@@ -253,7 +253,7 @@ solve_kernel(const typename Sys::Consts sc, const SolveOpts<R> o, const SolveIO<
                 // code below: it must leave the rings before the refill reuses them.
                 const R inf = M::inf();
                 __syncwarp();
-                unsigned rm = (o.dbg & 1) ? 0u : pad_mask;
+                unsigned rm = pad_mask;
                 while (rm) {
                     const int src = __ffs(rm) - 1;
                     rm &= rm - 1;
@@ -314,7 +314,7 @@ solve_kernel(const typename Sys::Consts sc, const SolveOpts<R> o, const SolveIO<
                 // +inf tails of the retired trajectories (ts: dir*inf), from the end of their last group to
                 // the end of the row, 16-byte streaming stores; every slot of the output is written once.
                 __syncwarp();
-                unsigned rm = (o.dbg & 1) ? 0u : pad_mask;
+                unsigned rm = pad_mask;
                 const R inf = M::inf();
                 while (rm) {
                     const int src = __ffs(rm) - 1;
@@ -331,7 +331,7 @@ solve_kernel(const typename Sys::Consts sc, const SolveOpts<R> o, const SolveIO<
         }
         if (!__any_sync(FULL, has_work)) break;
         const bool live = has_work && !finished;
-        if (DENSE && !(o.dbg & 2)) {
+        if (DENSE) {
             // write the groups completed by the previous attempt or by the refill above.  This is the
             // only in-loop call site (code size: the loop body must stay inside the I-cache).
             const R inf = M::inf();
@@ -495,7 +495,6 @@ template <class R> inline SolveOpts<R> make_solve_opts(const pmp_opts_t& o, int 
     s.safety = R(o.safety); s.factormin = R(o.factormin); s.factormax = R(o.factormax);
     s.inv_order = R(1.0 / order);
     s.event_level = R(o.event_level);
-    s.dbg = o.flags >> 8;
     s.max_steps = o.max_steps; s.adaptive = o.adaptive; s.force_dtmin = o.force_dtmin; s.event = o.event;
     return s;
 }

@@ -292,12 +292,14 @@ def main():
                 "flops_per_attempt": flops.ATTEMPT_FLOPS[(problem.system_id, method)],
                 "flops_per_rhs": flops.RHS_FLOPS[problem.system_id],
                 "kernel_ms": solve_s * 1e3}
-        traffic_file = os.path.join(ROOT, "profiles", "traffic.json")
-        if os.path.exists(traffic_file):
-            try:
-                roof["traffic"] = json.load(open(traffic_file)).get(f"{args.workload}_{args.dtype}_{args.method}")
-            except Exception:
-                pass
+    # measured DRAM traffic of one launch (ncu --set full capture of this same configuration, committed under
+    # profiles/); null when no capture exists for the configuration
+    traffic_file = os.path.join(ROOT, "profiles", "traffic.json")
+    if os.path.exists(traffic_file) and args.log2n == 20:
+        try:
+            roof["traffic"] = json.load(open(traffic_file)).get(f"{args.workload}_{args.dtype}_{args.method}")
+        except Exception:
+            pass
 
     # ---- e2e: public API, host buffers ---------------------------------------------------------------
     e2e = None
