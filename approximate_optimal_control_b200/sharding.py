@@ -54,3 +54,102 @@ def allgather_endpoints(local: torch.Tensor, n: int, interleaved: bool = False, 
     else:
         full = gathered.permute(1, 0, 2).reshape(rows, world * m)  # column r*m + j
     return full[:, :n].contiguous()
+
+
+class PipelinedGather:
+    """Solve a rank's shard in `chunks` pieces and gather the endpoints of piece k on every rank while
+    piece k+1 is being integrated.  Only the gather of the LAST piece is exposed.  Buffers are
+    allocated once and reused across calls.
+
+    transport="p2p" (default when torch symmetric memory is available): every rank pushes its piece
+        straight into the peers' gather buffers with peer-to-peer cudaMemcpyAsync over NVLink
+        (copy engines: no SM is taken from the integrator, which is a persistent kernel that owns
+        all of them), followed by one symmetric-memory barrier per step.
+    transport="nccl": all_gather_into_tensor on a side stream (NCCL's kernels need SMs, so they only
+        partly overlap with the integrator).
+
+        pg = PipelinedGather(problem, opts, n_local, dtype, device, chunks=2)
+        pieces = pg.run(y_local)        # list of [world, NS, n_piece] tensors, rank-major, on every rank
+    """
+
+    def __init__(self, problem, opts, n_local: int, dtype, device, chunks: int = 2, group=None, transport: str = "auto"):
+        from . import pontryagin_utils as pu
+        self._pu = pu
+        self.problem, self.opts, self.group = problem, opts, group
+        self.world = dist.get_world_size(group) if dist.is_initialized() else 1
+        self.rank = dist.get_rank(group) if dist.is_initialized() else 0
+        self.ns = 2 * problem.nx + 2
+        self.n_local = n_local
+        chunks = max(1, min(chunks, n_local))
+        edges = [n_local * c // chunks for c in range(chunks + 1)]
+        self.slices = [(edges[c], edges[c + 1]) for c in range(chunks) if edges[c + 1] > edges[c]]
+        self.inputs = [torch.empty((self.ns, b - a), dtype=dtype, device=device) for a, b in self.slices]
+        self.outs = [{} for _ in self.slices]
+        self.side = torch.cuda.Stream(device=device) if self.world > 1 else None
+        self.transport = "none" if self.world == 1 else transport
+        self.peer = None
+        if self.world > 1 and transport in ("auto", "p2p"):
+            try:
+                self._init_p2p(dtype, device)
+                self.transport = "p2p"
+            except Exception as e:  # symmetric memory unavailable: NCCL does the same job
+                if transport == "p2p":
+                    raise
+                self.transport = "nccl"
+                self.p2p_error = repr(e)
+        if self.transport == "nccl":
+            # per-piece gather buffers, rank-major: [world * NS, n_piece]
+            self.gathered = [torch.empty((self.world * self.ns, b - a), dtype=dtype, device=device) for a, b in self.slices]
+
+    def _init_p2p(self, dtype, device):
+        import torch.distributed._symmetric_memory as symm_mem
+        grp = self.group if self.group is not None else dist.group.WORLD
+        total = sum((b - a) for a, b in self.slices) * self.world * self.ns
+        flat = symm_mem.empty(total, dtype=dtype, device=device)
+        self.hdl = symm_mem.rendezvous(flat, grp)
+        # carve the symmetric allocation into per-piece [world*NS, n_piece] buffers; the same offsets are
+        # valid in every peer's copy
+        self.gathered, self.peer = [], []
+        off = 0
+        for a, b in self.slices:
+            m = self.world * self.ns * (b - a)
+            self.gathered.append(flat[off:off + m].view(self.world * self.ns, b - a))
+            self.peer.append([self.hdl.get_buffer(r, (self.world * self.ns, b - a), dtype, off) for r in range(self.world)])
+            off += m
+        # the integrator writes this rank's endpoints directly into its own slot of the gather buffer
+        for o, g in zip(self.outs, self.gathered):
+            o["y_end"] = g[self.rank * self.ns:(self.rank + 1) * self.ns]
+
+    def run(self, y_local: torch.Tensor):
+        """y_local [NS, n_local] -> list of per-piece gathered endpoint arrays [world, NS, n_piece]
+        (asynchronous: the current stream waits for the transfers before returning control)."""
+        main = torch.cuda.current_stream()
+        works = []
+        rows = slice(self.rank * self.ns, (self.rank + 1) * self.ns)
+        for c, ((a, b), y_in, out) in enumerate(zip(self.slices, self.inputs, self.outs)):
+            y_in.copy_(y_local[:, a:b])
+            self._pu.solve_batch_soa(self.problem, self.opts, y_in, out)
+            if self.world == 1:
+                continue
+            ev = torch.cuda.Event()
+            ev.record(main)
+            with torch.cuda.stream(self.side):
+                self.side.wait_event(ev)
+                if self.transport == "p2p":
+                    for d in range(1, self.world):  # staggered so that not everybody hits the same peer
+                        r = (self.rank + d) % self.world
+                        self.peer[c][r][rows].copy_(out["y_end"], non_blocking=True)
+                else:
+                    works.append(dist.all_gather_into_tensor(self.gathered[c], out["y_end"], group=self.group, async_op=True))
+        if self.world == 1:
+            return [o["y_end"].view(1, self.ns, -1) for o in self.outs]
+        if self.transport == "p2p":
+            with torch.cuda.stream(self.side):
+                self.hdl.barrier(channel=0)  # every rank's pushes have been issued and completed
+        for w in works:
+            w.wait()
+        main.wait_stream(self.side)
+        return [g.view(self.world, self.ns, -1) for g in self.gathered]
+
+    def attempts(self) -> torch.Tensor:
+        return sum(o["n_steps"].sum() for o in self.outs)

@@ -53,6 +53,10 @@ def parse_args():
     ap.add_argument("--method", default="tsit5", choices=["tsit5", "dopri5", "rk4"])
     ap.add_argument("--log2n", type=int, default=20, help="log2 of trajectories per GPU")
     ap.add_argument("--cpu-log2n", type=int, default=19, help="log2 of the cpu_baseline sample")
+    ap.add_argument("--gather-chunks", type=int, default=0,
+                    help="N>1: pieces of the shard; the all-gather of piece k overlaps the solve of piece k+1")
+    ap.add_argument("--gather", default="auto", choices=["auto", "p2p", "nccl"],
+                    help="N>1 endpoint gather transport: peer-to-peer copies over NVLink (symmetric memory) or NCCL")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     return ap.parse_args()
@@ -204,13 +208,17 @@ def main():
 
     y_dev = torch.as_tensor(y_np, device=dev).contiguous()
     out = {}
-    gathered = torch.empty((world * y_dev.shape[0], n), dtype=tdt, device=dev) if world > 1 else None
+    # N > 1: the shard is integrated in pieces and the endpoint all-gather of piece k overlaps piece k+1
+    # (0 = auto: every extra piece costs one more kernel tail, ~50 us; worth it only when the gather is long)
+    chunks = args.gather_chunks if args.gather_chunks > 0 else (1 if world <= 2 else 2)
+    pg = sharding.PipelinedGather(problem, opts, n, tdt, dev, chunks=chunks, transport=args.gather) if world > 1 else None
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
 
     def step():
-        pu.solve_batch_soa(problem, opts, y_dev, out)
         if world > 1:
-            dist.all_gather_into_tensor(gathered, out["y_end"])
+            pg.run(y_dev)
+        else:
+            pu.solve_batch_soa(problem, opts, y_dev, out)
 
     def barrier():
         if world > 1:
@@ -247,10 +255,8 @@ def main():
         flush.fill_(k & 0xFF)  # L2 flush, outside the per-step event pair
         a, m, b = ev[k]
         a.record()
-        pu.solve_batch_soa(problem, opts, y_dev, out)
+        step()
         m.record()
-        if world > 1:
-            dist.all_gather_into_tensor(gathered, out["y_end"])
         b.record()
     barrier()
     t_end = time.time()
@@ -258,7 +264,8 @@ def main():
     solve_ms = [a.elapsed_time(m) for (a, m, b) in ev]
     total_ms = torch.tensor([sum(step_ms)], dtype=torch.float64, device=dev)
     total_solve_ms = torch.tensor([sum(solve_ms)], dtype=torch.float64, device=dev)
-    attempts_t = out["n_steps"].sum().to(torch.float64).reshape(1)
+    my_attempts_t = (pg.attempts() if world > 1 else out["n_steps"].sum()).to(torch.float64).reshape(1)
+    attempts_t = my_attempts_t.clone()
     if world > 1:
         dist.all_reduce(total_ms, op=dist.ReduceOp.MAX)
         dist.all_reduce(total_solve_ms, op=dist.ReduceOp.MAX)
@@ -268,8 +275,21 @@ def main():
     value = n * world * args.steps / total_s
 
     # ---- roofline of the dominant kernel (rank 0's own launches) -------------------------------------
-    my_attempts = int(out["n_steps"].sum().item())
-    solve_s = float(np.mean(solve_ms)) * 1e-3
+    my_attempts = int(my_attempts_t.item())
+    if world > 1:
+        # kernel-only time of this rank's solve launches: re-time the same pieces without the collective
+        t_solo = []
+        for _ in range(3):
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            for y_in, o_ in zip(pg.inputs, pg.outs):
+                pu.solve_batch_soa(problem, opts, y_in, o_)
+            b.record()
+            torch.cuda.synchronize()
+            t_solo.append(a.elapsed_time(b))
+        solve_s = min(t_solo) * 1e-3
+    else:
+        solve_s = float(np.mean(solve_ms)) * 1e-3
     if dense:
         peaks = {}
         try:
@@ -368,9 +388,13 @@ def main():
             "config": workload_config(args, n),
             "rk_step_attempts_per_s": attempts_per_step * args.steps / total_s,
             "mean_attempts_per_trajectory": attempts_per_step / (n * world),
-            "solve_ms_per_step": total_solve_ms.item() / args.steps,
+            "solve_ms_per_step": (total_solve_ms.item() / args.steps) if world == 1 else solve_s * 1e3,
             "roofline": roof, "cpu_baseline": cpu, "e2e": e2e, "clocks": clocks,
-            "gpu_launches": args.steps * L.pmp_solve_launch_count(C.byref(problem), C.byref(opts), n),
+            "gpu_launches": args.steps * L.pmp_solve_launch_count(C.byref(problem), C.byref(opts), n) *
+                            (len(pg.slices) if world > 1 else 1),
+            "gather": ({"chunks": len(pg.slices), "transport": pg.transport, "bytes_per_rank_per_step": int(y_dev.numel() * y_dev.element_size()),
+                        "overlap": "all-gather of piece k on a side stream while piece k+1 is integrated"}
+                       if world > 1 else None),
         }
         print(json.dumps(line), flush=True)
     if world > 1:

@@ -1,0 +1,56 @@
+"""N>1 path on real GPUs (skipped with fewer than 2 devices): shard by terminal-sample index, integrate
+locally, gather the endpoints on every rank -- peer-to-peer (symmetric memory + copy engines) and
+NCCL transports must give the same, correct, global endpoint array."""
+import os
+
+import numpy as np
+import pytest
+
+from common import _capi, c_problem, flatquad_terminal
+
+pytestmark = pytest.mark.gpu
+
+
+def _worker(rank, world, port, n_local, q):
+    import torch
+    import torch.distributed as dist
+    from approximate_optimal_control_b200 import pontryagin_utils as pu, sharding
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    torch.cuda.set_device(rank)
+    dev = torch.device("cuda", rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
+    prob, _ = c_problem("flatquad")
+    opts = _capi.make_opts(dtype=_capi.F64)
+    n = n_local * world
+    y_all = torch.as_tensor(flatquad_terminal(n), device=dev)
+    y_loc = sharding.take_shard(y_all, n, rank, world)
+    ref = pu.solve_batch_soa(prob, opts, y_all.contiguous())["y_end"]  # every rank solves everything once
+    res = {}
+    for transport, chunks in (("nccl", 1), ("p2p", 1), ("p2p", 3)):
+        pg = sharding.PipelinedGather(prob, opts, n_local, torch.float64, dev, chunks=chunks, transport=transport)
+        for _ in range(2):  # twice: buffers are reused across steps
+            pieces = pg.run(y_loc)
+        torch.cuda.synchronize()
+        full = torch.cat([p for p in pieces], dim=2)              # [world, NS, n_local]
+        full = full.permute(1, 0, 2).reshape(14, n)               # contiguous sharding: column r*n_local + j
+        res[(transport, chunks)] = bool(torch.equal(full, ref))
+    q.put((rank, res))
+    dist.destroy_process_group()
+
+
+def test_sharded_solve_and_gather_two_gpus():
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29600 + os.getpid() % 300
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, 3001, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    out = [q.get(timeout=300) for _ in procs]
+    for p in procs:
+        p.join(60)
+    for rank, res in out:
+        assert all(res.values()), (rank, res)
