@@ -57,22 +57,26 @@ def allgather_endpoints(local: torch.Tensor, n: int, interleaved: bool = False, 
 
 
 class PipelinedGather:
-    """Solve a rank's shard in `chunks` pieces and gather the endpoints of piece k on every rank while
-    piece k+1 is being integrated.  Only the gather of the LAST piece is exposed.  Buffers are
-    allocated once and reused across calls.
+    """Integrate this rank's shard and gather the endpoint records of all ranks on every rank, with the
+    transfer hidden behind compute:
+
+      * within a step the shard can be cut into `chunks` pieces; the gather of piece k runs while piece
+        k+1 is integrated (costs one extra kernel tail, ~50 us, per piece);
+      * across steps (`run(..., wait=False)`): the gather of step s runs while step s+1 is integrated;
+        two sets of gather buffers alternate, so the result of step s stays valid until step s+2 is issued.
 
     transport="p2p" (default when torch symmetric memory is available): every rank pushes its piece
         straight into the peers' gather buffers with peer-to-peer cudaMemcpyAsync over NVLink
-        (copy engines: no SM is taken from the integrator, which is a persistent kernel that owns
-        all of them), followed by one symmetric-memory barrier per step.
+        (copy engines: no SM is taken from the integrator, a persistent kernel that owns all of them),
+        followed by one symmetric-memory barrier per step.
     transport="nccl": all_gather_into_tensor on a side stream (NCCL's kernels need SMs, so they only
         partly overlap with the integrator).
 
-        pg = PipelinedGather(problem, opts, n_local, dtype, device, chunks=2)
+        pg = PipelinedGather(problem, opts, n_local, dtype, device)
         pieces = pg.run(y_local)        # list of [world, NS, n_piece] tensors, rank-major, on every rank
     """
 
-    def __init__(self, problem, opts, n_local: int, dtype, device, chunks: int = 2, group=None, transport: str = "auto"):
+    def __init__(self, problem, opts, n_local: int, dtype, device, chunks: int = 1, group=None, transport: str = "auto"):
         from . import pontryagin_utils as pu
         self._pu = pu
         self.problem, self.opts, self.group = problem, opts, group
@@ -84,10 +88,14 @@ class PipelinedGather:
         edges = [n_local * c // chunks for c in range(chunks + 1)]
         self.slices = [(edges[c], edges[c + 1]) for c in range(chunks) if edges[c + 1] > edges[c]]
         self.inputs = [torch.empty((self.ns, b - a), dtype=dtype, device=device) for a, b in self.slices]
-        self.outs = [{} for _ in self.slices]
+        self.nsets = 2 if self.world > 1 else 1
+        self.outs = [[{} for _ in self.slices] for _ in range(self.nsets)]
         self.side = torch.cuda.Stream(device=device) if self.world > 1 else None
         self.transport = "none" if self.world == 1 else transport
         self.peer = None
+        self.step = 0
+        self._copied = [None] * self.nsets   # event: this set's local slot has been read by the pushes
+        self._pending = False
         if self.world > 1 and transport in ("auto", "p2p"):
             try:
                 self._init_p2p(dtype, device)
@@ -99,34 +107,45 @@ class PipelinedGather:
                 self.p2p_error = repr(e)
         if self.transport == "nccl":
             # per-piece gather buffers, rank-major: [world * NS, n_piece]
-            self.gathered = [torch.empty((self.world * self.ns, b - a), dtype=dtype, device=device) for a, b in self.slices]
+            self.gathered = [[torch.empty((self.world * self.ns, b - a), dtype=dtype, device=device) for a, b in self.slices]
+                             for _ in range(self.nsets)]
+        self._works = []
 
     def _init_p2p(self, dtype, device):
         import torch.distributed._symmetric_memory as symm_mem
         grp = self.group if self.group is not None else dist.group.WORLD
-        total = sum((b - a) for a, b in self.slices) * self.world * self.ns
-        flat = symm_mem.empty(total, dtype=dtype, device=device)
+        per_set = sum((b - a) for a, b in self.slices) * self.world * self.ns
+        flat = symm_mem.empty(per_set * self.nsets, dtype=dtype, device=device)
         self.hdl = symm_mem.rendezvous(flat, grp)
-        # carve the symmetric allocation into per-piece [world*NS, n_piece] buffers; the same offsets are
-        # valid in every peer's copy
+        # carve the symmetric allocation into per-set, per-piece [world*NS, n_piece] buffers; the same
+        # offsets are valid in every peer's copy
         self.gathered, self.peer = [], []
         off = 0
-        for a, b in self.slices:
-            m = self.world * self.ns * (b - a)
-            self.gathered.append(flat[off:off + m].view(self.world * self.ns, b - a))
-            self.peer.append([self.hdl.get_buffer(r, (self.world * self.ns, b - a), dtype, off) for r in range(self.world)])
-            off += m
-        # the integrator writes this rank's endpoints directly into its own slot of the gather buffer
-        for o, g in zip(self.outs, self.gathered):
-            o["y_end"] = g[self.rank * self.ns:(self.rank + 1) * self.ns]
+        for s in range(self.nsets):
+            gs, ps = [], []
+            for a, b in self.slices:
+                m = self.world * self.ns * (b - a)
+                gs.append(flat[off:off + m].view(self.world * self.ns, b - a))
+                ps.append([self.hdl.get_buffer(r, (self.world * self.ns, b - a), dtype, off) for r in range(self.world)])
+                off += m
+            self.gathered.append(gs)
+            self.peer.append(ps)
+            # the integrator writes this rank's endpoints directly into its own slot of the gather buffer
+            for o, g in zip(self.outs[s], gs):
+                o["y_end"] = g[self.rank * self.ns:(self.rank + 1) * self.ns]
 
-    def run(self, y_local: torch.Tensor):
-        """y_local [NS, n_local] -> list of per-piece gathered endpoint arrays [world, NS, n_piece]
-        (asynchronous: the current stream waits for the transfers before returning control)."""
+    def run(self, y_local: torch.Tensor, wait: bool = True):
+        """y_local [NS, n_local] -> list of per-piece gathered endpoint arrays [world, NS, n_piece].
+        wait=True: the current stream waits for the transfers of this step.  wait=False: the transfers
+        keep running on the side stream (call wait() before reading the result / at the end)."""
         main = torch.cuda.current_stream()
-        works = []
+        s = self.step % self.nsets
+        self.step += 1
+        outs = self.outs[s]
         rows = slice(self.rank * self.ns, (self.rank + 1) * self.ns)
-        for c, ((a, b), y_in, out) in enumerate(zip(self.slices, self.inputs, self.outs)):
+        if self._copied[s] is not None:  # the pushes of step-2 must have finished reading this set's local slot
+            main.wait_event(self._copied[s])
+        for c, ((a, b), y_in, out) in enumerate(zip(self.slices, self.inputs, outs)):
             y_in.copy_(y_local[:, a:b])
             self._pu.solve_batch_soa(self.problem, self.opts, y_in, out)
             if self.world == 1:
@@ -138,18 +157,32 @@ class PipelinedGather:
                 if self.transport == "p2p":
                     for d in range(1, self.world):  # staggered so that not everybody hits the same peer
                         r = (self.rank + d) % self.world
-                        self.peer[c][r][rows].copy_(out["y_end"], non_blocking=True)
+                        self.peer[s][c][r][rows].copy_(out["y_end"], non_blocking=True)
                 else:
-                    works.append(dist.all_gather_into_tensor(self.gathered[c], out["y_end"], group=self.group, async_op=True))
+                    self._works.append(dist.all_gather_into_tensor(self.gathered[s][c], out["y_end"], group=self.group,
+                                                                   async_op=True))
         if self.world == 1:
-            return [o["y_end"].view(1, self.ns, -1) for o in self.outs]
-        if self.transport == "p2p":
-            with torch.cuda.stream(self.side):
-                self.hdl.barrier(channel=0)  # every rank's pushes have been issued and completed
-        for w in works:
+            return [o["y_end"].view(1, self.ns, -1) for o in outs]
+        with torch.cuda.stream(self.side):
+            done = torch.cuda.Event()
+            done.record(self.side)
+            self._copied[s] = done
+            if self.transport == "p2p":
+                self.hdl.barrier(channel=0)  # every rank's pushes of this step have completed
+        self._pending = True
+        if wait:
+            self.wait()
+        return [g.view(self.world, self.ns, -1) for g in self.gathered[s]]
+
+    def wait(self):
+        """Make the current stream wait for every transfer issued so far."""
+        if not self._pending:
+            return
+        for w in self._works:
             w.wait()
-        main.wait_stream(self.side)
-        return [g.view(self.world, self.ns, -1) for g in self.gathered]
+        self._works = []
+        torch.cuda.current_stream().wait_stream(self.side)
+        self._pending = False
 
     def attempts(self) -> torch.Tensor:
-        return sum(o["n_steps"].sum() for o in self.outs)
+        return sum(o["n_steps"].sum() for o in self.outs[(self.step - 1) % self.nsets])
