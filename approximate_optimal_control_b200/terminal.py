@@ -28,3 +28,19 @@ def sample_terminal_states(P_lqr, V_f: float, n: int, seed: int = 1, x_eq=None, 
     assert np.allclose(v, V_f), "wrong terminal value..."  # levelsets.py:562
     x = dx if x_eq is None else dx + np.asarray(x_eq, dtype=np.float64)[None]
     return {"x": x.astype(dtype), "t": np.zeros(n, dtype), "v": v.astype(dtype), "vx": (dx @ P.T).astype(dtype)}
+
+
+def ellipse_terminal_states(P0, n: int, radius: float, x_eq=None, dtype=np.float64):
+    """Terminal states of the two 2-state experiments (experiment_orbits.py:121-129,
+    experiment_lqr_statepenalty.py:123-129): n points on the ellipse
+        x_f = x_eq + radius * sqrtm(P0)^-1 (sin th, cos th),  th = 2 pi i / n,
+    with the terminal value function V(x) = (x-x_eq)' P0 (x-x_eq): v_f = V(x_f), lambda_f = 2 P0 (x_f - x_eq).
+    Returns the state dict with a leading batch axis."""
+    import scipy.linalg
+    P0 = np.asarray(P0, dtype=np.float64)
+    th = 2 * np.pi * np.arange(n) / n
+    circ = np.stack([np.sin(th), np.cos(th)], axis=1)                       # (n, 2)
+    dx = radius * circ @ np.linalg.inv(scipy.linalg.sqrtm(P0).real).T
+    v = np.einsum("ni,ij,nj->n", dx, P0, dx)
+    x = dx if x_eq is None else dx + np.asarray(x_eq, dtype=np.float64)[None]
+    return {"x": x.astype(dtype), "t": np.zeros(n, dtype), "v": v.astype(dtype), "vx": (2 * dx @ P0.T).astype(dtype)}

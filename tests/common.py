@@ -56,17 +56,13 @@ def lqr_P():
     return scipy.linalg.solve_continuous_are(A, B, np.eye(2), np.eye(1))
 
 
+def _soa(st, dtype):
+    return np.ascontiguousarray(np.concatenate([st["x"].T, st["t"][None], st["v"][None], st["vx"].T], 0), dtype=dtype)
+
+
 def lqr_terminal(n=1024, radius=0.1, dtype=np.float64):
     """experiment_lqr_statepenalty.py:123-125: x_f = radius * sqrtm(P)^-1 (sin th, cos th)."""
-    import scipy.linalg
-    P = lqr_P()
-    th = 2 * np.pi * np.arange(n) / n
-    circ = np.stack([np.sin(th), np.cos(th)])
-    xf = radius * np.linalg.inv(scipy.linalg.sqrtm(P).real) @ circ
-    lam = 2 * P @ xf
-    v = np.einsum("in,ij,jn->n", xf, P, xf)
-    y = np.concatenate([xf, np.zeros((1, n)), v[None], lam], 0)
-    return np.ascontiguousarray(y, dtype=dtype)
+    return _soa(terminal.ellipse_terminal_states(lqr_P(), n, radius), dtype)
 
 
 def orbits_P0():
@@ -78,16 +74,7 @@ def orbits_P0():
 
 def orbits_terminal(n, radius=0.01, dtype=np.float64):
     """experiment_orbits.py:121-129: x_f = x_eq + radius * sqrtm(P0)^-1 (sin th, cos th)."""
-    import scipy.linalg
-    P0 = orbits_P0()
-    xeq = np.array([0.0, 1.0])[:, None]
-    th = 2 * np.pi * np.arange(n) / n
-    circ = np.stack([np.sin(th), np.cos(th)])
-    dx = radius * np.linalg.inv(scipy.linalg.sqrtm(P0).real) @ circ
-    lam = 2 * P0 @ dx
-    v = np.einsum("in,ij,jn->n", dx, P0, dx)
-    y = np.concatenate([dx + xeq, np.zeros((1, n)), v[None], lam], 0)
-    return np.ascontiguousarray(y, dtype=dtype)
+    return _soa(terminal.ellipse_terminal_states(orbits_P0(), n, radius, x_eq=[0.0, 1.0]), dtype)
 
 
 def scaled_err(a, b, tol, rows=None):
