@@ -46,7 +46,8 @@ class Dense(C.Structure):
 
 EXPORTS = ("pmp_abi_version", "pmp_last_error", "pmp_state_rows", "pmp_device_count",
            "pmp_solve_workspace_bytes", "pmp_solve_batch_cuda", "pmp_solve_launch_count",
-           "pmp_rhs_batch_cuda", "pmp_ustar_batch_cuda", "pmp_ustar_batch_cuda_flags", "pmp_fma_peak_cuda")
+           "pmp_rhs_batch_cuda", "pmp_ustar_batch_cuda", "pmp_ustar_batch_cuda_flags", "pmp_interp_batch_cuda",
+           "pmp_fma_peak_cuda")
 
 _lib = None
 
@@ -81,6 +82,8 @@ def lib() -> C.CDLL:
                                        C.c_void_p, C.c_void_p, C.c_void_p]
     L.pmp_ustar_batch_cuda_flags.argtypes = [C.POINTER(Problem), C.c_int32, C.c_int32, C.c_int64, C.c_void_p,
                                              C.c_void_p, C.c_void_p, C.c_void_p]
+    L.pmp_interp_batch_cuda.argtypes = [C.POINTER(Problem), C.POINTER(Opts), C.c_int64, C.c_void_p, C.c_void_p,
+                                        C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p]
     L.pmp_fma_peak_cuda.argtypes = [C.c_int32, C.c_int32, C.c_int32, C.c_void_p,
                                     C.POINTER(C.c_double), C.c_void_p]
     if L.pmp_abi_version() != ABI_VERSION:

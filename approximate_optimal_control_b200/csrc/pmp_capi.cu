@@ -16,6 +16,8 @@ int solve_lqr(const pmp_problem_t&, const pmp_opts_t&, long long, const void*, v
 int eval_batch(int what, const pmp_problem_t& p, int dtype, long long n, const void* a, const void* b, void* out,
                cudaStream_t st);
 int fma_peak(int dtype, int variant, int iters, void* scratch, double* flops_out, cudaStream_t st);
+int interp_batch(const pmp_problem_t& p, const pmp_opts_t& o, long long nq, const void* y0, const void* t1,
+                 const void* target, void* y_out, int mode, cudaStream_t st);
 }  // namespace pmp
 
 namespace {
@@ -154,6 +156,20 @@ int pmp_ustar_batch_cuda(const pmp_problem_t* p, int32_t dtype, int64_t n, const
     if (n == 0) return PMP_OK;
     if (pmp_device_count() <= 0) return fail(PMP_ERR_NO_DEVICE, "no CUDA device: libb200pmp has no CPU fallback");
     int rc = pmp::eval_batch(1, *p, dtype, n, x, lam, u, (cudaStream_t)cuda_stream);
+    return rc ? cuda_fail(rc) : PMP_OK;
+}
+
+int pmp_interp_batch_cuda(const pmp_problem_t* p, const pmp_opts_t* o, int64_t nq, const void* y0, const void* t1,
+                          const void* target, int32_t mode, void* y_out, void* cuda_stream) {
+    if (int e = check_problem(p)) return e;
+    if (int e = check_opts(o)) return e;
+    if (mode != 0 && mode != 1) return fail(PMP_ERR_BAD_ARG, "mode must be 0 (evaluate) or 1 (value level)");
+    if (mode == 1 && o->indep != PMP_INDEP_TIME) return fail(PMP_ERR_UNSUPPORTED, "mode 1 needs a time-parameterised solve");
+    if (nq < 0 || (nq > 0 && (!y0 || !t1 || !target || !y_out))) return fail(PMP_ERR_BAD_ARG, "bad nq or NULL buffers");
+    if (nq == 0) return PMP_OK;
+    if (pmp_device_count() <= 0) return fail(PMP_ERR_NO_DEVICE, "no CUDA device: libb200pmp has no CPU fallback");
+    int rc = pmp::interp_batch(*p, *o, nq, y0, t1, target, y_out, mode, (cudaStream_t)cuda_stream);
+    if (rc == -1000) return fail(PMP_ERR_UNSUPPORTED, "no kernel for this (system, dtype, method) combination");
     return rc ? cuda_fail(rc) : PMP_OK;
 }
 

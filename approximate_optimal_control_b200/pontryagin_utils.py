@@ -152,7 +152,63 @@ def solve_batch_soa(problem: _capi.Problem, opts: _capi.Opts, y_f: torch.Tensor,
     return out
 
 
-def _wrap_solution(out, nx, batched, t0, t1, opts) -> Solution:
+def _interp(problem, opts, nx, sol: Solution, target, mode: int):
+    """Solution.evaluate / state_at_value on pmp_interp_batch_cuda: locate the accepted step that contains
+    each query (torch.searchsorted on the saved ts / v), gather its start node, let the kernel recompute
+    the step's stage derivatives and evaluate the interpolant."""
+    value_mode = opts.indep == _capi.INDEP_VALUE
+    ts = sol.ts
+    ysd = sol.extra.get("ys_dict", sol.ys)
+    batched = ts.dim() == 2
+    if not batched:
+        ts = ts[None]
+        ysd = {k: v[None] for k, v in ysd.items()}
+    acc = sol.stats["num_accepted_steps"].reshape(-1).long()
+    N, S1 = ts.shape
+    dev, dtype = ts.device, ts.dtype
+    tq = _as_tensor(target, dtype, dev)
+    if batched:
+        if tq.dim() == 0:
+            tq = tq.expand(N)
+        multi = tq.dim() == 2
+        q = tq.reshape(N, -1)
+    else:
+        multi = tq.dim() == 1
+        q = tq.reshape(1, -1)
+    M = q.shape[1]
+    # keys increase along the slots; unused slots are +inf
+    if mode == 0:
+        direction = 1.0 if value_mode or (opts.t0 < opts.t1) else -1.0
+        keys, kq = ts * direction, q * direction
+    else:
+        keys, kq = ysd["v"], q
+    idx = torch.searchsorted(keys.contiguous(), kq.contiguous(), right=True) - 1
+    last = (acc - 1).clamp(min=0)[:, None]
+    inside = (kq >= keys[:, :1]) & (kq <= keys.gather(1, acc[:, None])) & (acc[:, None] > 0)
+    idx = idx.clamp(min=0).minimum(last)
+    rows = torch.arange(N, device=dev)[:, None].expand(N, M)
+    y0 = torch.empty((2 * nx + 2, N * M), dtype=dtype, device=dev)
+    y0[:nx] = ysd["x"][rows, idx].reshape(N * M, nx).t()
+    y0[nx] = ysd["t"][rows, idx].reshape(-1)
+    y0[nx + 1] = ysd["v"][rows, idx].reshape(-1)
+    y0[nx + 2:] = ysd["vx"][rows, idx].reshape(N * M, nx).t()
+    t1 = ts[rows, idx + 1].reshape(-1).contiguous()
+    tgt = q.reshape(-1).contiguous()
+    out = torch.empty_like(y0)
+    with torch.cuda.device(dev):
+        _capi.check(_capi.lib().pmp_interp_batch_cuda(C.byref(problem), C.byref(opts), N * M, y0.data_ptr(),
+                                                      t1.data_ptr(), tgt.data_ptr(), mode, out.data_ptr(),
+                                                      _stream_ptr(dev)))
+    out = torch.where(inside.reshape(1, -1), out, torch.full_like(out, float("nan")))
+    d = unpack_state(out, nx)
+    shape = (N, M) if (batched and multi) else ((N,) if batched else ((M,) if multi else ()))
+    d = {k: v.reshape(*shape, *v.shape[1:]) for k, v in d.items()}
+    if value_mode:  # flat [x, lambda, t] vector of the value-parameterised solver (rrt_sampler.py:62)
+        return torch.cat([d["x"], d["vx"], d["t"][..., None]], dim=-1)
+    return d
+
+
+def _wrap_solution(out, nx, batched, t0, t1, opts, problem=None) -> Solution:
     ys = None
     ts = None
     if opts.save_dense:
@@ -162,6 +218,9 @@ def _wrap_solution(out, nx, batched, t0, t1, opts) -> Solution:
              "num_rejected_steps": out["n_steps"] - out["n_accepted"]}
     sol = Solution(t0=t0, t1=t1, ts=ts, ys=ys, y_end=unpack_state(out["y_end"], nx), stats=stats,
                    result=out["result"], batched=True)
+    if problem is not None:
+        import functools
+        sol.extra["interp"] = functools.partial(_interp, problem, opts, nx)
     return sol if batched else sol[0]
 
 
@@ -219,7 +278,7 @@ def define_backward_solver(problem_params: dict, algo_params: dict):
         opts = _solver_opts(algo_params, dtype, t0=0.0, t1=-T, dt0=-abs(dt0), adaptive=int(adaptive),
                             save_dense=int(save_steps))
         out = solve_batch_soa(problem, opts, y)
-        return _wrap_solution(out, nx, batched, 0.0, -T, opts)
+        return _wrap_solution(out, nx, batched, 0.0, -T, opts, problem)
 
     return solve_backward, f_extended
 
@@ -321,7 +380,7 @@ def make_pontryagin_solver_reparam(problem_params: dict, algo_params: dict):
                             dtmin=float(algo_params.get("pontryagin_solver_dtmin", 0.0)),
                             dtmax=float(algo_params.get("pontryagin_solver_dtmax", 0.0)))
         out = solve_batch_soa(problem, opts, y)
-        sol = _wrap_solution(out, nx, True, None, float(v1), opts)
+        sol = _wrap_solution(out, nx, True, None, float(v1), opts, problem)
         if sol.ys is not None:  # flat (.., 2nx+1) layout of the missing solver
             sol.extra["ys_dict"] = sol.ys
             sol.ys = torch.cat([sol.ys["x"], sol.ys["vx"], sol.ys["t"][..., None]], dim=-1)

@@ -31,9 +31,22 @@ class Solution:
     extra: dict = field(default_factory=dict)
 
     def evaluate(self, t):
-        raise NotImplementedError(
-            "dense interpolation (diffrax Solution.evaluate) is not part of the accelerated path yet; "
-            "use .ts/.ys (every accepted step) or .y_end")
+        """diffrax Solution.evaluate (SaveAt(dense=True)): the solver's interpolant at time(s) `t`
+        (value level(s) for a value-parameterised solution).  Batched solution: `t` is a scalar, (N,) or
+        (N, M); single solution: scalar or (M,) -- the latter replaces jax.vmap(sol.evaluate)(ts)
+        (experiment_orbits.py:183-184).  Queries outside the integrated interval give NaN."""
+        fn = self.extra.get("interp")
+        if fn is None or self.ys is None:
+            raise RuntimeError("evaluate() needs the saved steps: solve with save_steps=True")
+        return fn(self, t, 0)
+
+    def state_at_value(self, v_k):
+        """State on the trajectory at which v == v_k (the bisection on sol.evaluate of misc.py:47-91), found
+        inside the accepted step that brackets the level.  Time-parameterised solutions only."""
+        fn = self.extra.get("interp")
+        if fn is None or self.ys is None:
+            raise RuntimeError("state_at_value() needs the saved steps: solve with save_steps=True")
+        return fn(self, v_k, 1)
 
     def numpy(self) -> "Solution":
         """Copy every tensor to host numpy arrays (same structure)."""

@@ -177,6 +177,18 @@ int pmp_rhs_batch_cuda(const pmp_problem_t *problem, int32_t dtype, int64_t n, c
 int pmp_ustar_batch_cuda(const pmp_problem_t *problem, int32_t dtype, int64_t n, const void *x,
                          const void *lam, void *u, void *cuda_stream);
 
+/* Dense output, diffrax Solution.evaluate (SaveAt(dense=True), pontryagin_utils.py:504; used at
+ * experiment_orbits.py:183-184, misc.py:40-95).  For every query q: y0[:, q] is the saved node at the
+ * START of the accepted step that contains the query (rows x, t, v, vx as everywhere), t1[q] the saved
+ * time at the END of that step (the value, for PMP_INDEP_VALUE solves).  The step's stage derivatives are
+ * recomputed with opts->method / dtype / indep / flags and the solver's interpolant is evaluated:
+ *   mode 0: at the independent variable target[q]                      -> y_out [NS][nq]
+ *   mode 1: at the point of the step where v == target[q] (bisection; time-parameterised solves only;
+ *           NaN if the level is not bracketed by the step)            -> y_out [NS][nq] */
+int pmp_interp_batch_cuda(const pmp_problem_t *problem, const pmp_opts_t *opts, int64_t nq,
+                          const void *y0, const void *t1, const void *target, int32_t mode,
+                          void *y_out, void *cuda_stream);
+
 /* Same with the selection rule the integrator uses for `flags` (PMP_FLAG_USTAR_LITERAL set: identical
  * to pmp_ustar_batch_cuda; clear: KKT-multiplier selection).  For verification of the two rules. */
 int pmp_ustar_batch_cuda_flags(const pmp_problem_t *problem, int32_t dtype, int32_t flags, int64_t n,

@@ -74,6 +74,8 @@ def lib():
                                            C.c_void_p, C.c_int]
         L.pmp_oracle_ustar_batch.argtypes = [C.POINTER(Problem), C.c_int32, C.c_int64, C.c_void_p,
                                              C.c_void_p, C.c_void_p, C.c_int]
+        L.pmp_oracle_interp_batch.argtypes = [C.POINTER(Problem), C.POINTER(Opts), C.c_int64, C.c_void_p, C.c_void_p,
+                                              C.c_void_p, C.c_int32, C.c_void_p]
         L.pmp_oracle_opcount.argtypes = [C.POINTER(Problem), C.POINTER(Opts), C.c_void_p, C.c_void_p]
         _lib = L
     return _lib
@@ -175,6 +177,19 @@ def ustar_batch(problem: Problem, dtype: int, x: np.ndarray, lam: np.ndarray,
     _check(lib().pmp_oracle_ustar_batch(C.byref(problem), dtype, x.shape[1], x.ctypes.data,
                                         lam.ctypes.data, u.ctypes.data, int(model_pass1)))
     return u
+
+
+def interp_batch(problem: Problem, opts: Opts, y0: np.ndarray, t1: np.ndarray, target: np.ndarray, mode: int = 0) -> np.ndarray:
+    """Dense output on one step per query (diffrax Solution.evaluate): y0 [NS, nq] node at the start of the
+    step, t1 [nq] end of the step, target [nq] query time (mode 0) or value level (mode 1) -> [NS, nq]."""
+    dt = _np_dtype(opts.dtype)
+    y0 = np.ascontiguousarray(y0, dtype=dt)
+    t1 = np.ascontiguousarray(t1, dtype=dt)
+    target = np.ascontiguousarray(target, dtype=dt)
+    out = np.empty_like(y0)
+    _check(lib().pmp_oracle_interp_batch(C.byref(problem), C.byref(opts), y0.shape[1], y0.ctypes.data, t1.ctypes.data,
+                                         target.ctypes.data, int(mode), out.ctypes.data))
+    return out
 
 
 def opcount(problem: Problem, opts: Opts, y0: np.ndarray) -> dict:

@@ -162,6 +162,30 @@ int pmp_oracle_ustar_batch(const pmp_problem_t* p, int32_t dtype, int64_t n, con
     return fail(PMP_ERR_UNSUPPORTED, "unknown system_id");
 }
 
+// dense output (diffrax Solution.evaluate) on one step per query; same contract as pmp_interp_batch_cuda
+int pmp_oracle_interp_batch(const pmp_problem_t* p, const pmp_opts_t* o, int64_t nq, const void* y0, const void* t1,
+                            const void* target, int32_t mode, void* y_out) {
+    if (int e = check(p, o)) return e;
+    auto run = [&](auto sys, auto zero) {
+        using Sys = decltype(sys);
+        using R = decltype(zero);
+        constexpr int NS = 2 * Sys::NX + 2;
+        for (int64_t i = 0; i < nq; i++) {
+            R a[NS], b[NS];
+            for (int q = 0; q < NS; q++) a[q] = ((const R*)y0)[q * nq + i];
+            interp_one<R, Sys>(sys, *o, a, ((const R*)t1)[i], ((const R*)target)[i], mode, b);
+            for (int q = 0; q < NS; q++) ((R*)y_out)[q * nq + i] = b[q];
+        }
+    };
+    const bool f32 = o->dtype == PMP_F32;
+    switch (p->system_id) {
+        case PMP_SYS_FLATQUAD: if (f32) run(Flatquad<float>(*p), 0.0f); else run(Flatquad<double>(*p), 0.0); return 0;
+        case PMP_SYS_ORBITS: if (f32) run(Orbits<float>(*p), 0.0f); else run(Orbits<double>(*p), 0.0); return 0;
+        case PMP_SYS_LQR_STATEPENALTY: if (f32) run(LqrStatePenalty<float>(*p), 0.0f); else run(LqrStatePenalty<double>(*p), 0.0); return 0;
+    }
+    return fail(PMP_ERR_UNSUPPORTED, "unknown system_id");
+}
+
 // Algorithmic work.  out[0..1] = flops, specials of ONE f_extended evaluation
 // (u* scored with the quadratic model, i.e. the cheaper reading of the reference's algorithm);
 // out[2..3] = flops, specials of ONE step attempt of opts->method excluding nothing (stages, RHS

@@ -616,4 +616,95 @@ TrajStats solve_one(const Sys& sys, const pmp_opts_t& o, const R* y_f, R* y_end,
     return st;
 }
 
+
+// =================================================================================================
+// Dense output: diffrax Solution.evaluate on one step.  Recomputes the stage derivatives of the
+// step [t0, t1] that starts at the saved node y0 and evaluates the interpolant (Tsit5: Tsitouras'
+// free interpolant, constants as in SURVEY.md 8(c); Dopri5: Hairer's contd5; RK4: cubic Hermite).
+// mode 0: evaluate at the independent variable `target`; mode 1: at the point where v == target.
+// =================================================================================================
+template <class R> void interp_weights(int method, R th, R* w) {
+    const R t2 = th * th;
+    if (method == PMP_METHOD_TSIT5) {
+        w[0] = R(-1.0530884977290216) * th * (th - R(1.3299890189751412)) * (t2 - R(1.4364028541716351) * th + R(0.7139816917074209));
+        w[1] = R(0.1017) * t2 * (t2 - R(2.1966568338249754) * th + R(1.2949852507374631));
+        w[2] = R(2.490627285651252793) * t2 * (t2 - R(2.38535645472061657) * th + R(1.57803468208092486));
+        w[3] = R(-16.54810288924490272) * (th - R(1.21712927295533244)) * (th - R(0.61620406037800089)) * t2;
+        w[4] = R(47.37952196281928122) * (th - R(1.203071208372362603)) * (th - R(0.658047292653547382)) * t2;
+        w[5] = R(-34.87065786149660974) * (th - R(1.2)) * (th - R(2.0 / 3.0)) * t2;
+        w[6] = R(2.5) * (th - R(1.0)) * (th - R(0.6)) * t2;
+    } else {
+        const R om = th - R(1), a = t2 * (R(3) - R(2) * th), c = t2 * om * om;
+        w[0] = a * R(35.0 / 384) + th * om * om - c * R(5) * (R(2558722523.0) - R(31403016.0) * th) / R(11282082432.0);
+        w[1] = R(0);
+        w[2] = a * R(500.0 / 1113) + c * R(100) * (R(882725551.0) - R(15701508.0) * th) / R(32700410799.0);
+        w[3] = a * R(125.0 / 192) - c * R(25) * (R(443332067.0) - R(31403016.0) * th) / R(1880347072.0);
+        w[4] = a * R(-2187.0 / 6784) + c * R(32805) * (R(23143187.0) - R(3489224.0) * th) / R(199316789632.0);
+        w[5] = a * R(11.0 / 84) - c * R(55) * (R(29972135.0) - R(7076736.0) * th) / R(822651844.0);
+        w[6] = t2 * om + c * R(10) * (R(7414447.0) - R(829305.0) * th) / R(29380423.0);
+    }
+}
+
+template <class R, class Sys>
+void interp_one(const Sys& sys, const pmp_opts_t& o, const R* y0, R t1, R target, int mode, R* out) {
+    constexpr int NX = Sys::NX, NS = 2 * NX + 2, IT = NX, IV = NX + 1;
+    const Tableau& tb = *tableau_for(o.method);
+    const bool value_mode = o.indep == PMP_INDEP_VALUE;
+    const int IC = value_mode ? IV : IT;  // the row that holds the independent variable
+    const R h = t1 - y0[IC];
+    auto field = [&](const R* yy, R* k) {  // forward-time field (signed h carries the direction)
+        sys.rhs(yy, k);
+        if (value_mode) {
+            R vdot = k[IV];
+            for (int i = 0; i < NS; i++) k[i] = k[i] / vdot;
+            k[IV] = R(1);
+        }
+    };
+    R k[8][NS], ys[NS], y1[NS];
+    field(y0, k[0]);
+    for (int i = 1; i < tb.stages; i++) {
+        for (int q = 0; q < NS; q++) {
+            R acc = y0[q];
+            for (int j = 0; j < i; j++) acc = acc + (h * R(tb.a[i][j])) * k[j][q];
+            ys[q] = acc;
+        }
+        field(ys, k[i]);
+    }
+    for (int q = 0; q < NS; q++) {
+        R acc = y0[q];
+        for (int j = 0; j < tb.stages; j++) acc = acc + (h * R(tb.b[j])) * k[j][q];
+        y1[q] = acc;
+    }
+    if (!tb.fsal) field(y1, k[tb.stages]);
+    auto eval = [&](R th, int q) -> R {
+        if (tb.fsal) {
+            R w[7];
+            interp_weights<R>(o.method, th, w);
+            R acc = R(0);
+            for (int j = 0; j < 7; j++) acc = acc + w[j] * k[j][q];
+            return y0[q] + h * acc;
+        }
+        const R d = y1[q] - y0[q];
+        return (R(1) - th) * y0[q] + th * y1[q] +
+               th * (th - R(1)) * ((R(1) - R(2) * th) * d + (th - R(1)) * h * k[0][q] + th * h * k[tb.stages][q]);
+    };
+    R th;
+    if (mode == 0) {
+        th = (target - y0[IC]) / h;
+    } else {
+        R lo = R(0), hi = R(1);
+        const R f0 = y0[IV] - target, f1 = eval(R(1), IV) - target;
+        const bool ok = (r_val(f0) <= 0 && r_val(f1) >= 0) || (r_val(f0) >= 0 && r_val(f1) <= 0);
+        for (int it = 0; it < (std::is_same<R, float>::value ? 26 : 54); it++) {
+            const R mid = R(0.5) * (lo + hi);
+            const R fm = eval(mid, IV) - target;
+            const bool same = (r_val(fm) >= 0) == (r_val(f0) >= 0);
+            if (same) lo = mid; else hi = mid;
+        }
+        th = ok ? R(0.5) * (lo + hi) : r_nan<R>();
+    }
+    for (int q = 0; q < NS; q++) out[q] = eval(th, q);
+    out[IC] = y0[IC] + th * h;
+}
+
 }  // namespace pmpo

@@ -326,3 +326,74 @@ def test_literal_ustar_flag_gives_same_trajectories_fp64():
     b = cuda_solve(prob, _capi.make_opts(dtype=_capi.F64, flags=_capi.FLAG_USTAR_LITERAL), y)
     assert (a["n_steps"] == b["n_steps"]).mean() >= 0.999
     assert np.percentile(scaled_err(a["y_end"], b["y_end"], 1e-5), 99.9) <= 0.1
+
+
+# ---- dense output: Solution.evaluate / value-level root finding -------------------------
+@pytest.mark.parametrize("method,adaptive,dt0", [("tsit5", 1, -0.1), ("dopri5", 1, -0.1), ("rk4", 0, -1 / 16)])
+def test_interp_kernel_matches_oracle_and_step_ends(method, adaptive, dt0):
+    import ctypes as C
+    import torch
+    prob, _ = c_problem("flatquad")
+    y = flatquad_terminal(512)
+    opts = _capi.make_opts(method=method, dtype=_capi.F64, adaptive=adaptive, dt0=dt0, save_dense=1, max_steps=128)
+    ref = O.solve_batch(oracle_problem("flatquad"), as_oracle_opts(opts), y)
+    n = y.shape[1]
+    i = np.arange(n)
+    s = ref["n_accepted"] // 2
+    node = np.concatenate([ref["x"][i, s].T, ref["t"][i, s][None], ref["v"][i, s][None], ref["vx"][i, s].T], 0)
+    nxt = np.concatenate([ref["x"][i, s + 1].T, ref["t"][i, s + 1][None], ref["v"][i, s + 1][None], ref["vx"][i, s + 1].T], 0)
+    t1 = ref["ts"][i, s + 1]
+    L = _capi.lib()
+    for frac in (0.0, 0.37, 1.0):
+        tq = node[6] + frac * (t1 - node[6])
+        want = O.interp_batch(oracle_problem("flatquad"), as_oracle_opts(opts), node, t1, tq, 0)
+        a = [torch.as_tensor(np.ascontiguousarray(v), device="cuda") for v in (node, t1, tq)]
+        out = torch.empty_like(a[0])
+        _capi.check(L.pmp_interp_batch_cuda(C.byref(prob), C.byref(opts), n, a[0].data_ptr(), a[1].data_ptr(),
+                                            a[2].data_ptr(), 0, out.data_ptr(), None))
+        torch.cuda.synchronize()
+        got = out.cpu().numpy()
+        assert np.allclose(got, want, rtol=1e-9, atol=1e-11), np.abs(got - want).max()
+        if frac == 0.0:
+            assert np.allclose(got, node, rtol=1e-12, atol=1e-13)
+        if frac == 1.0:  # the interpolant reproduces the step the integrator took
+            assert np.allclose(got, nxt, rtol=1e-9, atol=1e-10)
+
+
+def test_solution_evaluate_and_state_at_value_public_api():
+    """sol.evaluate(t) through the public API against a tight oracle solve to the same times, and
+    sol.state_at_value(v_k) lands on the level."""
+    import torch
+    from approximate_optimal_control_b200 import pontryagin_utils as pu, systems, terminal
+    pp = systems.flatquad_problem_params()
+    ap = dict(systems.flatquad_algo_params(), pontryagin_solver_rtol=1e-7, pontryagin_solver_atol=1e-7,
+              pontryagin_solver_maxsteps=400)
+    _, P = pu.get_terminal_lqr(pp)
+    st = terminal.sample_terminal_states(P, pp["V_f"], 64, seed=4)
+    solve_backward, _ = pu.define_backward_solver(pp, ap)
+    sol = solve_backward(st)
+    tq = torch.linspace(-0.05, -2.95, 7, dtype=torch.float64, device="cuda")[None].expand(64, 7).contiguous()
+    ev = sol.evaluate(tq)
+    assert ev["x"].shape == (64, 7, 6) and ev["v"].shape == (64, 7)
+    y = flatquad_terminal(64, seed=4)
+    for m in (0, 3, 6):
+        truth = O.solve_batch(oracle_problem("flatquad"),
+                              O.make_opts(dtype=O.F64, rtol=1e-12, atol=1e-12, dtmin=0.0, max_steps=100000, t1=float(tq[0, m])), y)["y_end"]
+        got = np.concatenate([ev["x"][:, m].cpu().numpy().T, ev["t"][:, m].cpu().numpy()[None], ev["v"][:, m].cpu().numpy()[None],
+                              ev["vx"][:, m].cpu().numpy().T], 0)
+        # node global error at rtol=atol=1e-7 is amplified to ~1e-5..1e-4 by the unstable backward dynamics
+        assert (np.abs(got - truth) / (1 + np.abs(truth))).max() <= 3e-4
+        assert np.allclose(got[6], tq[0, m].item())
+    # a scalar time, a single (unbatched) solution with many query times, and out-of-range queries
+    assert sol.evaluate(-1.0)["x"].shape == (64, 6)
+    one = sol[3]
+    e1 = one.evaluate(torch.tensor([-0.5, -1.5, -5.0], dtype=torch.float64))
+    assert e1["x"].shape == (3, 6) and torch.isnan(e1["v"][2]) and torch.isfinite(e1["v"][:2]).all()
+    assert torch.allclose(e1["x"][0], sol.evaluate(-0.5)["x"][3])
+    # value level
+    lvl = 5.0
+    sv = sol.state_at_value(lvl)
+    reach = sol.y_end["v"] >= lvl
+    assert reach.any() and torch.allclose(sv["v"][reach], torch.full_like(sv["v"][reach], lvl), atol=1e-9)
+    assert torch.isnan(sv["v"][~reach]).all()
+    assert ((sv["t"][reach] < 0) & (sv["t"][reach] > -3.0)).all()
