@@ -10,6 +10,7 @@ reference's own Python call signatures.  See DESIGN.md.
 """
 from . import _capi, build, sharding, systems  # noqa: F401
 from . import pontryagin_utils  # noqa: F401
+from . import levelsets  # noqa: F401
 from .solution import Solution  # noqa: F401
 from .terminal import sample_terminal_states  # noqa: F401
 

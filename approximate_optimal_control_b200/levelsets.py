@@ -1,0 +1,62 @@
+"""Device-side mirrors of the data-selection helpers that sit right after the hot path in
+levelsets.testbed (/root/reference/levelsets.py): they consume the dense `Solution` the backward
+solve returns and would otherwise round-trip ~8 GB of saved nodes through the host.
+
+    select_train_pts(value_interval, sols[, vxx_max_norm])      levelsets.py:667-709
+    find_min_l(ys, v_lower, v_upper, problem_params)            levelsets.py:604-628
+
+Array work is torch on the GPU; the running cost l(x, u*(x, lambda)) comes from the CUDA f_extended
+kernel (v' = -l, pontryagin_utils.py:449), i.e. from pmp_rhs_batch_cuda.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import torch
+
+from . import _capi, systems
+from . import pontryagin_utils as pu
+
+
+def select_train_pts(value_interval, sols):
+    """levelsets.py:667-709: all saved nodes whose value lies in [v_lower, v_upper] (inf/NaN padding
+    drops out of the comparison), as a dict of flat arrays {'x','t','v','vx'}."""
+    v_lower, v_upper = value_interval
+    v = sols.ys["v"]
+    v_finite = torch.isfinite(v)
+    bool_train_idx = (v >= v_lower) & (v <= v_upper)
+    all_ys = {k: node[bool_train_idx] for k, node in sols.ys.items()}
+    n_sel, n_fin = int(bool_train_idx.sum()), int(v_finite.sum())
+    perc = 100.0 * n_sel / max(n_fin, 1)
+    print(f"full (train+test) dataset size: {n_sel} points (= {perc:.2f}% of valid points)")
+    if any(bool(torch.isnan(a).any()) for a in all_ys.values()):
+        raise RuntimeError("There are still NaNs in training data.")
+    return all_ys
+
+
+def running_cost(ys: dict, problem_params: dict) -> torch.Tensor:
+    """l(x, u*(x, vx)) at every saved node, shape of ys['v']; padding slots give NaN."""
+    problem = systems.to_c_problem(problem_params)
+    nx = problem.nx
+    x, vx = ys["x"], ys["vx"]
+    shape = x.shape[:-1]
+    dev, dtype = x.device, x.dtype
+    n = x.numel() // nx
+    y = torch.zeros((2 * nx + 2, n), dtype=dtype, device=dev)
+    y[:nx] = x.reshape(n, nx).t()
+    y[nx + 2:] = vx.reshape(n, nx).t()
+    dy = torch.empty_like(y)
+    with torch.cuda.device(dev):
+        _capi.check(_capi.lib().pmp_rhs_batch_cuda(C.byref(problem), pu._code(dtype), n, y.data_ptr(), dy.data_ptr(),
+                                                   pu._stream_ptr(dev)))
+    l = -dy[nx + 1]
+    return torch.where(torch.isfinite(l), l, torch.full_like(l, float("nan"))).reshape(shape)
+
+
+def find_min_l(ys: dict, v_lower, v_upper, problem_params: dict):
+    """levelsets.py:604-628: smallest running cost l(x, u*) over the saved nodes in the value band."""
+    all_ls = running_cost(ys, problem_params)
+    inside = (ys["v"] >= v_lower) & (ys["v"] <= v_upper) & ~torch.isnan(all_ls)
+    if not bool(inside.any()):
+        return torch.tensor(float("nan"), dtype=all_ls.dtype, device=all_ls.device)
+    return all_ls[inside].min()

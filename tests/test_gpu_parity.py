@@ -397,3 +397,28 @@ def test_solution_evaluate_and_state_at_value_public_api():
     assert reach.any() and torch.allclose(sv["v"][reach], torch.full_like(sv["v"][reach], lvl), atol=1e-9)
     assert torch.isnan(sv["v"][~reach]).all()
     assert ((sv["t"][reach] < 0) & (sv["t"][reach] > -3.0)).all()
+
+
+# ---- the data-selection step right after the path -----------------------------------------
+def test_select_train_pts_and_find_min_l_on_device():
+    import torch
+    from approximate_optimal_control_b200 import levelsets, pontryagin_utils as pu, systems, terminal
+    pp, ap = systems.flatquad_problem_params(), systems.flatquad_algo_params()
+    _, P = pu.get_terminal_lqr(pp)
+    st = terminal.sample_terminal_states(P, pp["V_f"], 300, seed=2)
+    sol = pu.define_backward_solver(pp, ap)[0](st)
+    band = (5 / 1000, 5.0)  # levelsets.py:716-719: v_k = 5, [v_k/1000, v_k]
+    sel = levelsets.select_train_pts(band, sol)
+    v = sol.ys["v"].cpu().numpy()
+    mask = (v >= band[0]) & (v <= band[1])
+    assert sel["x"].shape == (mask.sum(), 6) and sel["v"].shape == (mask.sum(),)
+    assert np.array_equal(sel["vx"].cpu().numpy(), sol.ys["vx"].cpu().numpy()[mask])
+    # running cost at every node against the oracle's f_extended (l = -v')
+    x = sol.ys["x"].cpu().numpy()[mask].T.astype(np.float64)
+    lam = sol.ys["vx"].cpu().numpy()[mask].T.astype(np.float64)
+    dy = O.rhs_batch(oracle_problem("flatquad"), O.F64, np.concatenate([x, np.zeros((2, x.shape[1])), lam], 0))
+    want = (-dy[7]).min()
+    got = float(levelsets.find_min_l(sol.ys, band[0], band[1], pp))
+    assert abs(got - want) <= 1e-4 * max(1.0, abs(want)), (got, want)
+    l_all = levelsets.running_cost(sol.ys, pp)
+    assert l_all.shape == sol.ys["v"].shape and torch.isnan(l_all[torch.isinf(sol.ys["v"])]).all()

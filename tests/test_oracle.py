@@ -303,3 +303,49 @@ def test_flop_constants_match_oracle():
     assert c["attempt_flops"] == flops.ATTEMPT_FLOPS[(_capi.SYS_ORBITS, _capi.METHOD_TSIT5)]
     # SURVEY.md 8(d) hand count: ~181 flop per RHS, ~2056 per Tsit5 attempt, within ~+-12 %
     assert abs(flops.RHS_FLOPS[0] / 181 - 1) < 0.15 and abs(flops.ATTEMPT_FLOPS[(0, 1)] / 2056 - 1) < 0.10
+
+
+# ---- dense output restatement -----------------------------------------------------------------------------------
+@pytest.mark.parametrize("method,order", [(O.TSIT5, 4), (O.DOPRI5, 4), (O.RK4, 3)])
+def test_interpolant_continuity_and_order(method, order):
+    """From an (almost) exact node, the interpolant over ONE step of size h reproduces y0 at theta=0, the
+    step result at theta=1, and its mid-step error falls like h^(order+1)."""
+    prob = O.flatquad_problem()
+    y = flatquad_terminal(16)
+    tight = lambda t1, y0: O.solve_batch(prob, O.make_opts(dtype=O.F64, rtol=1e-13, atol=1e-13, dtmin=0.0, max_steps=100000,
+                                                            t0=float(y0[6, 0]), t1=t1, dt0=-0.01), y0)["y_end"]
+    node = tight(-1.0, y)  # state at t = -1
+    errs = []
+    for h in (0.2, 0.1):
+        opts = O.make_opts(method=method, dtype=O.F64, adaptive=0, dt0=-h)
+        t1 = node[6] - h
+        e0 = O.interp_batch(prob, opts, node, t1, node[6], 0)
+        assert np.allclose(e0, node, rtol=1e-13, atol=1e-14)
+        one = O.solve_batch(prob, O.make_opts(method=method, dtype=O.F64, adaptive=0, t0=-1.0, t1=-1.0 - h, dt0=-h, max_steps=1), node)
+        e1 = O.interp_batch(prob, opts, node, t1, t1, 0)
+        assert np.allclose(e1, one["y_end"], rtol=1e-10, atol=1e-12)
+        mid = O.interp_batch(prob, opts, node, t1, node[6] - 0.5 * h, 0)
+        errs.append(np.abs(mid - tight(-1.0 - 0.5 * h, node)).max())
+    rate = np.log2(errs[0] / errs[1])
+    assert rate >= order + 0.3, (rate, errs)
+
+
+def test_value_mode_interpolation_oracle():
+    y = orbits_terminal(32)
+    prob = O.orbits_problem()
+    opts = O.make_opts(dtype=O.F64, indep=O.INDEP_VALUE, t1=4.2, dt0=1 / 16, rtol=1e-8, atol=1e-10, dtmin=0.0, dtmax=0.0,
+                       max_steps=2000, save_dense=1)
+    out = O.solve_batch(prob, opts, y)
+    i = np.arange(32)
+    s = out["n_accepted"] // 2
+    node = np.concatenate([out["x"][i, s].T, out["t"][i, s][None], out["v"][i, s][None], out["vx"][i, s].T], 0)
+    v1 = out["ts"][i, s + 1]
+    assert np.allclose(node[3], out["ts"][i, s])  # ts of a value-parameterised solve are the value levels
+    vq = 0.5 * (node[3] + v1)
+    got = O.interp_batch(prob, opts, node, v1, vq, 0)
+    assert np.allclose(got[3], vq)
+    # same point reached by integrating in value from the terminal state to vq
+    for k in range(0, 32, 8):
+        ref = O.solve_batch(prob, O.make_opts(dtype=O.F64, indep=O.INDEP_VALUE, t1=float(vq[k]), dt0=1 / 64, rtol=1e-12,
+                                              atol=1e-13, dtmin=0.0, dtmax=0.0, max_steps=20000), y[:, k:k + 1])["y_end"][:, 0]
+        assert np.allclose(got[:, k], ref, rtol=1e-5, atol=1e-6)
