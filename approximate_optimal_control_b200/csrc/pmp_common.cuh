@@ -62,9 +62,40 @@ template <> struct Math<float> {
     static __device__ __forceinline__ float clip_tol() { return 1e-6f; }  // diffrax _clip_to_end
 };
 
+// Branch-free sin & cos for fp64 (same scheme as pmp_sincosf): Cody-Waite reduction by pi/2 with the
+// 1.5*2^52 magic-number quotient (|x| < ~1e9 rad), fdlibm's __kernel_sin / __kernel_cos minimax
+// polynomials on [-pi/4, pi/4] (< 1 ulp).  CUDA's sincos(double) costs ~2.5x the instructions plus a
+// Payne-Hanek slow path behind a branch, 6 times per step attempt.
+__device__ __forceinline__ void pmp_sincos(double x, double* sn_out, double* cs_out) {
+    const double magic = 6755399441055744.0;  // 1.5 * 2^52
+    const double kf_biased = ::fma(x, 0.63661977236758138, magic);
+    const int k = __double2loint(kf_biased);
+    const double kf = kf_biased - magic;
+    double r = ::fma(kf, -1.5707963267948966, x);     // pi/2 = hi + mid + lo; the fma products are exact
+    r = ::fma(kf, -6.123233995736766e-17, r);
+    r = ::fma(kf, 1.4973849048591698e-33, r);
+    const double z = r * r;
+    double sp = ::fma(z, 1.58969099521155010221e-10, -2.50507602534068634195e-08);
+    sp = ::fma(sp, z, 2.75573137070700676789e-06);
+    sp = ::fma(sp, z, -1.98412698298579493134e-04);
+    sp = ::fma(sp, z, 8.33333333332248946124e-03);
+    sp = ::fma(sp, z, -1.66666666666666324348e-01);
+    const double sn = ::fma(z * r, sp, r);
+    double cp = ::fma(z, -1.13596475577881948265e-11, 2.08757232129817482790e-09);
+    cp = ::fma(cp, z, -2.75573143513906633035e-07);
+    cp = ::fma(cp, z, 2.48015872894767294178e-05);
+    cp = ::fma(cp, z, -1.38888888888741095749e-03);
+    cp = ::fma(cp, z, 4.16666666666666019037e-02);
+    const double cs = ::fma(z * z, cp, ::fma(z, -0.5, 1.0));
+    const bool swap = (k & 1) != 0;
+    const double s0 = swap ? cs : sn, c0 = swap ? sn : cs;
+    *sn_out = __hiloint2double(__double2hiint(s0) ^ ((k & 2) << 30), __double2loint(s0));
+    *cs_out = __hiloint2double(__double2hiint(c0) ^ (((k + 1) & 2) << 30), __double2loint(c0));
+}
+
 template <> struct Math<double> {
     static __device__ __forceinline__ double fma(double a, double b, double c) { return ::fma(a, b, c); }
-    static __device__ __forceinline__ void sincos(double x, double* s, double* c) { ::sincos(x, s, c); }
+    static __device__ __forceinline__ void sincos(double x, double* s, double* c) { pmp_sincos(x, s, c); }
     static __device__ __forceinline__ double abs(double x) { return fabs(x); }
     static __device__ __forceinline__ double max(double a, double b) { return fmax(a, b); }
     static __device__ __forceinline__ double min(double a, double b) { return fmin(a, b); }
@@ -105,7 +136,32 @@ template <class R> struct SolveOpts {
     int max_steps, adaptive, force_dtmin, event, use_dtmin, use_dtmax;
 };
 
-// dense output leaves, indexable so that cold code can loop over them: 0 ts, 1 t, 2 v, 3 x, 4 vx
+// Butcher tableau in the kernel's precision, used by the fp64 instantiations only: 64-bit immediates do
+// not exist, so a compile-time double coefficient costs two register moves per use, while a
+// parameter-bank entry is a c[][] operand of the DMUL that consumes it.  fp32 keeps the compile-time
+// immediates (measured 4 % faster than the parameter bank), so its record is empty.
+template <class R> struct TabParams {
+    R ta[7][7], tb[7], te[7];
+    template <class TB> static TabParams make() {
+        TabParams t;
+        for (int i = 0; i < 7; i++) {
+            t.tb[i] = i < TB::S ? R(TB::b(i)) : R(0);
+            t.te[i] = i < TB::S ? R(TB::berr(i)) : R(0);
+            for (int j = 0; j < 7; j++) t.ta[i][j] = (i < TB::S && j < TB::S) ? R(TB::a(i, j)) : R(0);
+        }
+        return t;
+    }
+    template <class TB> __device__ __forceinline__ R a(int i, int j) const { return ta[i][j]; }
+    template <class TB> __device__ __forceinline__ R b(int j) const { return tb[j]; }
+    template <class TB> __device__ __forceinline__ R e(int j) const { return te[j]; }
+};
+template <> struct TabParams<float> {
+    template <class TB> static TabParams make() { return TabParams(); }
+    template <class TB> __device__ __forceinline__ float a(int i, int j) const { return float(TB::a(i, j)); }
+    template <class TB> __device__ __forceinline__ float b(int j) const { return float(TB::b(j)); }
+    template <class TB> __device__ __forceinline__ float e(int j) const { return float(TB::berr(j)); }
+};
+
 template <class R> struct DensePtrs {
     R* p[5];
 };

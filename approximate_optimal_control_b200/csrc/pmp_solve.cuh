@@ -184,7 +184,7 @@ __device__ __forceinline__ void write_group_s(const DensePtrs<R>& d, const R* sS
 // ---- the integrator -----------------------------------------------------------------------------
 template <class Sys, class R, int METHOD, bool DENSE, bool VALUE, bool ULIT, int MINB>
 __global__ void __launch_bounds__(kBlock, MINB)
-solve_kernel(const typename Sys::Consts sc, const SolveOpts<R> o, const SolveIO<R> io) {
+solve_kernel(const typename Sys::Consts sc, const SolveOpts<R> o, const SolveIO<R> io, const TabParams<R> tp) {
     using M = Math<R>;
     using TB = Tab<METHOD>;
     constexpr int NX = Sys::NX, ND = 2 * NX + 1, NS = 2 * NX + 2, S = TB::S;
@@ -365,7 +365,7 @@ solve_kernel(const typename Sys::Consts sc, const SolveOpts<R> o, const SolveIO<
             // ys = y + sum_j (h a_ij) k_j : i scalar products, then i FMAs per component
             R ha[S];
 #pragma unroll
-            for (int j = 0; j < i; j++) ha[j] = h * R(TB::a(i, j));
+            for (int j = 0; j < i; j++) ha[j] = h * tp.template a<TB>(i, j);
 #pragma unroll
             for (int q = 0; q < ND; q++) {
                 // the field does not depend on the aux scalar: skip it for intermediate stages
@@ -385,7 +385,7 @@ solve_kernel(const typename Sys::Consts sc, const SolveOpts<R> o, const SolveIO<
         if (!TB::FSAL) {
             R hb[S];
 #pragma unroll
-            for (int j = 0; j < S; j++) hb[j] = h * R(TB::b(j));
+            for (int j = 0; j < S; j++) hb[j] = h * tp.template b<TB>(j);
 #pragma unroll
             for (int q = 0; q < ND; q++) {
                 R acc = y[q];
@@ -406,7 +406,7 @@ solve_kernel(const typename Sys::Consts sc, const SolveOpts<R> o, const SolveIO<
             R sumsq = R(0);
             R he[S];
 #pragma unroll
-            for (int j = 0; j < S; j++) he[j] = h * R(TB::berr(j));
+            for (int j = 0; j < S; j++) he[j] = h * tp.template e<TB>(j);
 #pragma unroll
             for (int q = 0; q < ND; q++) {
                 R e = he[0] * k[0][q];
@@ -482,7 +482,7 @@ solve_kernel(const typename Sys::Consts sc, const SolveOpts<R> o, const SolveIO<
 }
 
 // ---- host-side launcher for one system ----------------------------------------------------------
-template <class R> inline SolveOpts<R> make_solve_opts(const pmp_opts_t& o, int order) {
+template <class R, class TB> inline SolveOpts<R> make_solve_opts(const pmp_opts_t& o, int order) {
     SolveOpts<R> s;
     const double dir = (o.indep == PMP_INDEP_VALUE) ? 1.0 : ((o.t0 < o.t1) ? 1.0 : -1.0);
     s.dir = R(dir);
@@ -548,8 +548,8 @@ int launch_one(const pmp_problem_t& p, const pmp_opts_t& o, long long n, const v
     } else {
         reset_counter_kernel<<<1, 1, 0, st>>>(io.counter);
     }
-    const SolveOpts<R> so = make_solve_opts<R>(o, TB::ORDER);
-    kern<<<grid, kBlock, smem, st>>>(sc, so, io);
+    const SolveOpts<R> so = make_solve_opts<R, TB>(o, TB::ORDER);
+    kern<<<grid, kBlock, smem, st>>>(sc, so, io, TabParams<R>::template make<TB>());
     return (int)cudaGetLastError();
 }
 

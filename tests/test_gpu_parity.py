@@ -422,3 +422,38 @@ def test_select_train_pts_and_find_min_l_on_device():
     assert abs(got - want) <= 1e-4 * max(1.0, abs(want)), (got, want)
     l_all = levelsets.running_cost(sol.ys, pp)
     assert l_all.shape == sol.ys["v"].shape and torch.isnan(l_all[torch.isinf(sol.ys["v"])]).all()
+
+
+def test_dense_and_endpoint_writes_stay_inside_their_buffers():
+    """compute-sanitizer is closed on this GPU pool, so out-of-bounds writes are hunted with guard bands:
+    every output is a view into a larger allocation filled with a sentinel; after the solve (ragged n,
+    NaN lanes, early max_steps) the bands must be untouched and every in-range slot written."""
+    import torch
+    from approximate_optimal_control_b200 import pontryagin_utils as pu
+    prob, _ = c_problem("flatquad")
+    G = 4096  # guard elements on each side (multiple of 4: keeps the 16-byte alignment the ABI requires)
+    for dtype, tdt in ((_capi.F32, torch.float32), (_capi.F64, torch.float64)):
+        for n, max_steps in ((1, 128), (777, 128), (4099, 21)):
+            y = flatquad_terminal(n)
+            y[:, n // 2] = np.nan
+            yd = torch.as_tensor(y, dtype=tdt, device="cuda").contiguous()
+            s1 = max_steps + 1
+            sentinel = -12345.0
+            shapes = {"y_end": (14, n), "ts": (n, s1), "x": (n, s1, 6), "t": (n, s1), "v": (n, s1), "vx": (n, s1, 6)}
+            big, out = {}, {}
+            for k, shp in shapes.items():
+                m = int(np.prod(shp))
+                big[k] = torch.full((m + 2 * G,), sentinel, dtype=tdt, device="cuda")
+                out[k] = big[k][G:G + m].view(shp)
+            ints = {}
+            for k in ("n_accepted", "n_steps", "result"):
+                ints[k] = torch.full((n + 2 * G,), -777, dtype=torch.int32, device="cuda")
+                out[k] = ints[k][G:G + n]
+            pu.solve_batch_soa(prob, _capi.make_opts(dtype=dtype, save_dense=1, max_steps=max_steps), yd, out)
+            torch.cuda.synchronize()
+            for k, b in big.items():
+                assert (b[:G] == sentinel).all() and (b[-G:] == sentinel).all(), (k, n)
+                inner = b[G:-G]
+                assert not (inner == sentinel).any(), (k, n)  # every slot written exactly (at least) once
+            for k, b in ints.items():
+                assert (b[:G] == -777).all() and (b[-G:] == -777).all() and not (b[G:-G] == -777).any(), (k, n)
