@@ -15,10 +15,12 @@ SYS_FLATQUAD, SYS_ORBITS, SYS_LQR_STATEPENALTY = 0, 1, 2
 METHOD_RK4, METHOD_TSIT5, METHOD_DOPRI5 = 0, 1, 2
 F32, F64 = 0, 1
 INDEP_TIME, INDEP_VALUE = 0, 1
-EVENT_NONE, EVENT_VALUE_GE = 0, 1
+EVENT_NONE, EVENT_VALUE_GE, EVENT_VXX_NORM = 0, 1, 2
 RESULT_OK, RESULT_EVENT, RESULT_MAX_STEPS, RESULT_DT_MIN, RESULT_NAN = 0, 1, 2, 3, 4
-ABI_VERSION = 2
+ABI_VERSION = 3
 FLAG_USTAR_LITERAL = 1
+FLAG_VXX = 2
+FLAG_VXX_SYMMETRIC = 4
 
 METHODS = {"rk4": METHOD_RK4, "tsit5": METHOD_TSIT5, "dopri5": METHOD_DOPRI5}
 
@@ -41,12 +43,12 @@ class Opts(C.Structure):
 
 class Dense(C.Structure):
     _fields_ = [("ts", C.c_void_p), ("x", C.c_void_p), ("t", C.c_void_p), ("v", C.c_void_p),
-                ("vx", C.c_void_p)]
+                ("vx", C.c_void_p), ("vxx", C.c_void_p)]
 
 
-EXPORTS = ("pmp_abi_version", "pmp_last_error", "pmp_state_rows", "pmp_device_count",
+EXPORTS = ("pmp_abi_version", "pmp_last_error", "pmp_state_rows", "pmp_state_rows_flags", "pmp_device_count",
            "pmp_solve_workspace_bytes", "pmp_solve_batch_cuda", "pmp_solve_launch_count",
-           "pmp_rhs_batch_cuda", "pmp_ustar_batch_cuda", "pmp_ustar_batch_cuda_flags", "pmp_interp_batch_cuda",
+           "pmp_rhs_batch_cuda", "pmp_rhs_batch_cuda_flags", "pmp_ustar_batch_cuda", "pmp_ustar_batch_cuda_flags", "pmp_interp_batch_cuda",
            "pmp_fma_peak_cuda")
 
 _lib = None
@@ -78,6 +80,9 @@ def lib() -> C.CDLL:
                                        C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]
     L.pmp_rhs_batch_cuda.argtypes = [C.POINTER(Problem), C.c_int32, C.c_int64, C.c_void_p,
                                      C.c_void_p, C.c_void_p]
+    L.pmp_state_rows_flags.argtypes = [C.POINTER(Problem), C.c_int32]
+    L.pmp_rhs_batch_cuda_flags.argtypes = [C.POINTER(Problem), C.c_int32, C.c_int32, C.c_int64, C.c_void_p,
+                                           C.c_void_p, C.c_void_p]
     L.pmp_ustar_batch_cuda.argtypes = [C.POINTER(Problem), C.c_int32, C.c_int64, C.c_void_p,
                                        C.c_void_p, C.c_void_p, C.c_void_p]
     L.pmp_ustar_batch_cuda_flags.argtypes = [C.POINTER(Problem), C.c_int32, C.c_int32, C.c_int64, C.c_void_p,

@@ -9,6 +9,8 @@
 namespace pmp {
 int solve_flatquad(const pmp_problem_t&, const pmp_opts_t&, long long, const void*, void*, const pmp_dense_t*,
                    int32_t*, int32_t*, int32_t*, void*, cudaStream_t);
+int solve_flatquad_vxx(const pmp_problem_t&, const pmp_opts_t&, long long, const void*, void*, const pmp_dense_t*,
+                       int32_t*, int32_t*, int32_t*, void*, cudaStream_t);
 int solve_orbits(const pmp_problem_t&, const pmp_opts_t&, long long, const void*, void*, const pmp_dense_t*,
                  int32_t*, int32_t*, int32_t*, void*, cudaStream_t);
 int solve_lqr(const pmp_problem_t&, const pmp_opts_t&, long long, const void*, void*, const pmp_dense_t*,
@@ -52,7 +54,9 @@ int check_opts(const pmp_opts_t* o) {
     if (o->dtype != PMP_F32 && o->dtype != PMP_F64) return fail(PMP_ERR_BAD_ARG, "dtype must be 0 (f32) or 1 (f64)");
     if (o->indep != PMP_INDEP_TIME && o->indep != PMP_INDEP_VALUE) return fail(PMP_ERR_BAD_ARG, "bad indep");
     if (o->max_steps < 1) return fail(PMP_ERR_BAD_ARG, "max_steps must be >= 1");
-    if (o->event != PMP_EVENT_NONE && o->event != PMP_EVENT_VALUE_GE) return fail(PMP_ERR_UNSUPPORTED, "unknown event");
+    if (o->event < PMP_EVENT_NONE || o->event > PMP_EVENT_VXX_NORM) return fail(PMP_ERR_UNSUPPORTED, "unknown event");
+    if (o->event == PMP_EVENT_VXX_NORM && !(o->flags & PMP_FLAG_VXX))
+        return fail(PMP_ERR_BAD_ARG, "PMP_EVENT_VXX_NORM needs PMP_FLAG_VXX");
     if (o->adaptive && o->method == PMP_METHOD_RK4)
         return fail(PMP_ERR_UNSUPPORTED, "RK4 has no embedded error estimate: adaptive must be 0");
     if (!(o->dt0 != 0.0) || o->dt0 != o->dt0) return fail(PMP_ERR_BAD_ARG, "dt0 must be non-zero");
@@ -62,13 +66,28 @@ int check_opts(const pmp_opts_t* o) {
     } else if (!(o->dt0 > 0)) {
         return fail(PMP_ERR_BAD_ARG, "value-parameterised solve needs dt0 > 0");
     }
-    if ((o->flags & ~PMP_FLAG_USTAR_LITERAL) != 0 || o->reserved != 0) return fail(PMP_ERR_BAD_ARG, "unknown flags / reserved != 0");
+    if ((o->flags & ~(PMP_FLAG_USTAR_LITERAL | PMP_FLAG_VXX | PMP_FLAG_VXX_SYMMETRIC)) != 0 || o->reserved != 0)
+        return fail(PMP_ERR_BAD_ARG, "unknown flags / reserved != 0");
+    if ((o->flags & PMP_FLAG_VXX_SYMMETRIC) && !(o->flags & PMP_FLAG_VXX))
+        return fail(PMP_ERR_BAD_ARG, "PMP_FLAG_VXX_SYMMETRIC needs PMP_FLAG_VXX");
+    if (o->flags & PMP_FLAG_VXX) {
+        if (o->indep != PMP_INDEP_TIME) return fail(PMP_ERR_UNSUPPORTED, "PMP_FLAG_VXX: time-parameterised solves only");
+        if (o->flags & PMP_FLAG_USTAR_LITERAL)
+            return fail(PMP_ERR_UNSUPPORTED, "PMP_FLAG_VXX differentiates the KKT form of u*: clear PMP_FLAG_USTAR_LITERAL");
+    }
     if (o->adaptive) {
         if (!(o->rtol >= 0) || !(o->atol >= 0) || !(o->rtol + o->atol > 0)) return fail(PMP_ERR_BAD_ARG, "bad rtol/atol");
         if (!(o->safety > 0) || !(o->factormin > 0) || !(o->factormax >= 1)) return fail(PMP_ERR_BAD_ARG, "bad controller factors");
     }
     return 0;
 }
+// options that need a particular system
+int check_pair(const pmp_problem_t* p, const pmp_opts_t* o) {
+    if ((o->flags & PMP_FLAG_VXX) && p->system_id != PMP_SYS_FLATQUAD)
+        return fail(PMP_ERR_UNSUPPORTED, "PMP_FLAG_VXX: only the flatquad functor carries the Jacobians through u*");
+    return 0;
+}
+int64_t vxx_rows(const pmp_problem_t* p, int32_t flags) { return (flags & PMP_FLAG_VXX) ? (int64_t)p->nx * p->nx : 0; }
 }  // namespace
 
 extern "C" {
@@ -79,6 +98,12 @@ const char* pmp_last_error(void) { return g_err.c_str(); }
 int pmp_state_rows(const pmp_problem_t* p) {
     if (int e = check_problem(p)) return e;
     return 2 * p->nx + 2;
+}
+
+int pmp_state_rows_flags(const pmp_problem_t* p, int32_t flags) {
+    if (int e = check_problem(p)) return e;
+    if ((flags & PMP_FLAG_VXX) && p->system_id != PMP_SYS_FLATQUAD) return fail(PMP_ERR_UNSUPPORTED, "PMP_FLAG_VXX: flatquad only");
+    return 2 * p->nx + 2 + (int)vxx_rows(p, flags);
 }
 
 int pmp_device_count(void) {
@@ -92,14 +117,16 @@ int pmp_device_count(void) {
 int64_t pmp_solve_workspace_bytes(const pmp_problem_t* p, const pmp_opts_t* o, int64_t n) {
     if (int e = check_problem(p)) return e;
     if (int e = check_opts(o)) return e;
+    if (int e = check_pair(p, o)) return e;
     if (n < 0) return fail(PMP_ERR_BAD_ARG, "n < 0");
-    const int64_t nd = 2 * p->nx + 1;
+    const int64_t nd = 2 * p->nx + 1 + vxx_rows(p, o->flags);
     return 256 + nd * n * (o->dtype == PMP_F32 ? 4 : 8);
 }
 
 int pmp_solve_launch_count(const pmp_problem_t* p, const pmp_opts_t* o, int64_t n) {
     if (int e = check_problem(p)) return e;
     if (int e = check_opts(o)) return e;
+    if (int e = check_pair(p, o)) return e;
     return n > 0 ? 2 : 0;  // prep (k1 / counter reset) + integrator
 }
 
@@ -108,6 +135,7 @@ int pmp_solve_batch_cuda(const pmp_problem_t* p, const pmp_opts_t* o, int64_t n,
                          void* workspace, int64_t workspace_bytes, void* cuda_stream) {
     if (int e = check_problem(p)) return e;
     if (int e = check_opts(o)) return e;
+    if (int e = check_pair(p, o)) return e;
     if (n < 0) return fail(PMP_ERR_BAD_ARG, "n < 0");
     if (n == 0) return PMP_OK;
     if (!y_f || !y_end) return fail(PMP_ERR_BAD_ARG, "y_f / y_end is NULL");
@@ -117,6 +145,8 @@ int pmp_solve_batch_cuda(const pmp_problem_t* p, const pmp_opts_t* o, int64_t n,
         for (const void* q : ptrs)
             if (!q || ((uintptr_t)q & 15u) != 0)
                 return fail(PMP_ERR_BAD_ARG, "dense output: all five leaves are required and must be 16-byte aligned");
+        if ((o->flags & PMP_FLAG_VXX) && (!dense->vxx || ((uintptr_t)dense->vxx & 15u) != 0))
+            return fail(PMP_ERR_BAD_ARG, "dense output with PMP_FLAG_VXX: the vxx leaf is required and must be 16-byte aligned");
         // slot indices travel as 32-bit integers inside the staging buffer
         if ((double)n * ((double)o->max_steps + 1.0) >= 4294967295.0)
             return fail(PMP_ERR_UNSUPPORTED, "dense output: n * (max_steps + 1) must be < 2^32; split the batch");
@@ -129,7 +159,10 @@ int pmp_solve_batch_cuda(const pmp_problem_t* p, const pmp_opts_t* o, int64_t n,
     cudaStream_t st = (cudaStream_t)cuda_stream;
     int rc = -1000;
     switch (p->system_id) {
-        case PMP_SYS_FLATQUAD: rc = pmp::solve_flatquad(*p, *o, n, y_f, y_end, dense, n_accepted, n_steps, result, workspace, st); break;
+        case PMP_SYS_FLATQUAD:
+            if (o->flags & PMP_FLAG_VXX) rc = pmp::solve_flatquad_vxx(*p, *o, n, y_f, y_end, dense, n_accepted, n_steps, result, workspace, st);
+            else rc = pmp::solve_flatquad(*p, *o, n, y_f, y_end, dense, n_accepted, n_steps, result, workspace, st);
+            break;
         case PMP_SYS_ORBITS: rc = pmp::solve_orbits(*p, *o, n, y_f, y_end, dense, n_accepted, n_steps, result, workspace, st); break;
         case PMP_SYS_LQR_STATEPENALTY: rc = pmp::solve_lqr(*p, *o, n, y_f, y_end, dense, n_accepted, n_steps, result, workspace, st); break;
     }
@@ -145,6 +178,23 @@ int pmp_rhs_batch_cuda(const pmp_problem_t* p, int32_t dtype, int64_t n, const v
     if (n == 0) return PMP_OK;
     if (pmp_device_count() <= 0) return fail(PMP_ERR_NO_DEVICE, "no CUDA device: libb200pmp has no CPU fallback");
     int rc = pmp::eval_batch(0, *p, dtype, n, y, nullptr, dy, (cudaStream_t)cuda_stream);
+    return rc ? cuda_fail(rc) : PMP_OK;
+}
+
+int pmp_rhs_batch_cuda_flags(const pmp_problem_t* p, int32_t dtype, int32_t flags, int64_t n, const void* y, void* dy,
+                             void* cuda_stream) {
+    if (!(flags & PMP_FLAG_VXX)) {
+        if (flags != 0) return fail(PMP_ERR_BAD_ARG, "pmp_rhs_batch_cuda_flags: only PMP_FLAG_VXX is meaningful here");
+        return pmp_rhs_batch_cuda(p, dtype, n, y, dy, cuda_stream);
+    }
+    if (int e = check_problem(p)) return e;
+    if (flags != PMP_FLAG_VXX) return fail(PMP_ERR_BAD_ARG, "pmp_rhs_batch_cuda_flags: only PMP_FLAG_VXX is meaningful here");
+    if (p->system_id != PMP_SYS_FLATQUAD) return fail(PMP_ERR_UNSUPPORTED, "PMP_FLAG_VXX: flatquad only");
+    if (dtype != PMP_F32 && dtype != PMP_F64) return fail(PMP_ERR_BAD_ARG, "dtype must be 0 (f32) or 1 (f64)");
+    if (n < 0 || (n > 0 && (!y || !dy))) return fail(PMP_ERR_BAD_ARG, "bad n or NULL buffers");
+    if (n == 0) return PMP_OK;
+    if (pmp_device_count() <= 0) return fail(PMP_ERR_NO_DEVICE, "no CUDA device: libb200pmp has no CPU fallback");
+    int rc = pmp::eval_batch(3, *p, dtype, n, y, nullptr, dy, (cudaStream_t)cuda_stream);
     return rc ? cuda_fail(rc) : PMP_OK;
 }
 

@@ -163,9 +163,9 @@ template <> struct TabParams<float> {
 };
 
 template <class R> struct DensePtrs {
-    R* p[5];
+    R* p[6];
 };
-enum { kDenseTs = 0, kDenseT = 1, kDenseV = 2, kDenseX = 3, kDenseVx = 4 };
+enum { kDenseTs = 0, kDenseT = 1, kDenseV = 2, kDenseX = 3, kDenseVx = 4, kDenseVxx = 5 };
 
 template <class R> struct SolveIO {
     const R* y_f;   // [NS][n]

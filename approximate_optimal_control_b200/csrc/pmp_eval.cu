@@ -23,6 +23,27 @@ __global__ void __launch_bounds__(256) rhs_kernel(const typename Sys::Consts sc,
     dy[(NX + 1) * n + i] = vd;
 }
 
+// f_extended with algo_params['pontryagin_solver_vxx'] (pontryagin_utils.py:460-467): y, dy [NS + nx*nx][n]
+template <class Sys, class R>
+__global__ void __launch_bounds__(128) rhs_vxx_kernel(const typename Sys::Consts sc, const R* __restrict__ y,
+                                                      R* __restrict__ dy, long long n) {
+    constexpr int NX = Sys::NX, NS = 2 * NX + 2, NV = NX * NX;
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    R x[NX], lam[NX], xd[NX], ld[NX], vd, V[NV];
+#pragma unroll
+    for (int q = 0; q < NX; q++) { x[q] = y[q * n + i]; lam[q] = y[(NX + 2 + q) * n + i]; }
+#pragma unroll
+    for (int q = 0; q < NV; q++) V[q] = y[(NS + q) * n + i];
+    typename Sys::JacCoef jc;
+    Sys::rhs_jac(sc, x, lam, xd, vd, ld, jc);
+#pragma unroll
+    for (int q = 0; q < NX; q++) { dy[q * n + i] = xd[q]; dy[(NX + 2 + q) * n + i] = ld[q]; }
+    dy[NX * n + i] = R(1);
+    dy[(NX + 1) * n + i] = vd;
+    Sys::template vxx_dot<1>(sc, jc, V, [&](int q, R val) { dy[(NS + q) * n + i] = val; });
+}
+
 template <class Sys, class R, int UMODE>
 __global__ void __launch_bounds__(256) ustar_kernel(const typename Sys::Consts sc, const R* __restrict__ x_,
                                                     const R* __restrict__ lam_, R* __restrict__ u_, long long n) {
@@ -59,6 +80,13 @@ int eval_dispatch(int what, const pmp_problem_t& p, int dtype, long long n, cons
 
 int eval_batch(int what, const pmp_problem_t& p, int dtype, long long n, const void* a, const void* b, void* out,
                cudaStream_t st) {
+    if (what == 3) {  // f_extended with the vxx leaf: flatquad only (checked by the caller)
+        if (n == 0) return 0;
+        const unsigned grid = (unsigned)((n + 127) / 128);
+        if (dtype == PMP_F32) rhs_vxx_kernel<Flatquad<float>, float><<<grid, 128, 0, st>>>(Flatquad<float>::make(p), (const float*)a, (float*)out, n);
+        else rhs_vxx_kernel<Flatquad<double>, double><<<grid, 128, 0, st>>>(Flatquad<double>::make(p), (const double*)a, (double*)out, n);
+        return (int)cudaGetLastError();
+    }
     switch (p.system_id) {
         case PMP_SYS_FLATQUAD: return eval_dispatch<Flatquad>(what, p, dtype, n, a, b, out, st);
         case PMP_SYS_ORBITS: return eval_dispatch<Orbits>(what, p, dtype, n, a, b, out, st);

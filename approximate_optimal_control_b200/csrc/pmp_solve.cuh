@@ -33,6 +33,36 @@ namespace pmp {
 constexpr int kBlock = 128;  // threads per CTA
 constexpr int kChunk = 64;   // trajectory indices claimed per atomicAdd
 
+// ---- value-Hessian branch (PMP_FLAG_VXX, pontryagin_utils.py:460-467) ---------------------------------
+// The state gains NV = nx*nx scalars (50 in all for flatquad): with seven stage derivatives that is 288
+// more values per trajectory, which no register file holds.  The base state (x, lambda, v and its k's)
+// stays in registers exactly as above; V_xx and its stage derivatives live in SHARED memory, laid out
+// [entry][thread] so that a warp's access to one entry is one conflict-free 128-byte row.  Per stage the
+// thread forms the stage matrix in 36 registers, evaluates vxx' (sparse Jacobians, ~200 FMAs, see
+// Flatquad::vxx_dot) and streams the result back.  (1 + stages) * NV reals per thread bound the CTA size:
+// 64 threads (fp32) / 32 threads (fp64) = 72 KB per CTA, three CTAs per SM (six / three warps).  Shared-memory
+// BANDWIDTH is what bounds this kernel (43 word accesses per entry and attempt against ~90 flops), which is why
+// the symmetric storage (VXX = 2, VxxMap: 21 instead of 36 entries, 42 KB per CTA, five CTAs per SM) exists.
+template <class R, int VXX> struct BlockOf { static constexpr int value = VXX ? (sizeof(R) == 4 ? 64 : 32) : kBlock; };
+
+// stage-field evaluation for the VXX instantiation: base RHS + Jacobian coefficients first (the stage state
+// dies here), then the stage matrix Vs is formed in registers by load_v and vxx' goes to the shared-memory
+// column kv (stride BLK)
+template <class Sys, class R, int BLK, int VXX, class LoadV>
+__device__ __forceinline__ void field_vxx(const typename Sys::Consts& sc, const R* y, R* k, R* Vs, R* kv, LoadV&& load_v) {
+    constexpr int NX = Sys::NX;
+    typename Sys::JacCoef jc;
+    R vd;
+    Sys::rhs_jac(sc, y, y + NX, k, vd, k + NX, jc);
+    k[2 * NX] = vd;
+    // compiler fences: without them nvcc forwards every value stored to the shared-memory columns to its later
+    // loads, i.e. tries to keep all (1 + stages) * NV entries in registers and spills them to local memory
+    asm volatile("" ::: "memory");
+    load_v(Vs);
+    Sys::template vxx_dot<VXX>(sc, jc, Vs, [&](int q, R val) { kv[q * BLK] = val; });
+    asm volatile("" ::: "memory");
+}
+
 // ---- forward-time field on the integrator's vector layout y = (x[NX], lam[NX], aux) -------------
 // time mode : aux = v,  k = (f, -dH/dx, -l)
 // value mode: aux = t,  k = (f, -dH/dx, 1) / (dv/dt)      (experiment_orbits.py:109-111)
@@ -66,17 +96,30 @@ __device__ __forceinline__ void load_state(const R* __restrict__ y_f, long long 
 }
 
 // ---- prep kernel: k1 = field(y_f) for every trajectory (coalesced), and reset of the work counter
-template <class Sys, class R, bool VALUE, bool ULIT>
+template <class Sys, class R, bool VALUE, bool ULIT, int VXX>
 __global__ void __launch_bounds__(kBlock) prep_kernel(const typename Sys::Consts sc, const R* __restrict__ y_f,
                                                       R* __restrict__ k1, long long n,
                                                       unsigned long long* counter) {
-    constexpr int NX = Sys::NX, ND = 2 * NX + 1;
+    constexpr int NX = Sys::NX, ND = 2 * NX + 1, NS = 2 * NX + 2;
     const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i == 0) *counter = 0ull;
     if (i >= n) return;
     R y[ND], k[ND], c0, af;
     load_state<R, NX, VALUE>(y_f, n, i, y, c0, af);
-    field<Sys, R, VALUE, ULIT ? 0 : 2>(sc, y, k);
+    if constexpr (VXX != 0) {
+        using MP = VxxMap<NX, VXX>;
+        constexpr int NV = MP::NV;
+        R V[NV];
+#pragma unroll
+        for (int q = 0; q < NV; q++) V[q] = __ldg(y_f + (NS + MP::pub(q)) * n + i);
+        typename Sys::JacCoef jc;
+        R vd;
+        Sys::rhs_jac(sc, y, y + NX, k, vd, k + NX, jc);
+        k[2 * NX] = vd;
+        Sys::template vxx_dot<VXX>(sc, jc, V, [&](int q, R val) { k1[(ND + q) * n + i] = val; });  // storage order
+    } else {
+        field<Sys, R, VALUE, ULIT ? 0 : 2>(sc, y, k);
+    }
 #pragma unroll
     for (int q = 0; q < ND; q++) k1[q * n + i] = k[q];
 }
@@ -182,19 +225,24 @@ __device__ __forceinline__ void write_group_s(const DensePtrs<R>& d, const R* sS
 }
 
 // ---- the integrator -----------------------------------------------------------------------------
-template <class Sys, class R, int METHOD, bool DENSE, bool VALUE, bool ULIT, int MINB>
-__global__ void __launch_bounds__(kBlock, MINB)
+template <class Sys, class R, int METHOD, bool DENSE, bool VALUE, bool ULIT, int MINB, int VXX = 0>
+__global__ void __launch_bounds__((BlockOf<R, VXX>::value), MINB)
 solve_kernel(const typename Sys::Consts sc, const SolveOpts<R> o, const SolveIO<R> io, const TabParams<R> tp) {
     using M = Math<R>;
     using TB = Tab<METHOD>;
     constexpr int NX = Sys::NX, ND = 2 * NX + 1, NS = 2 * NX + 2, S = TB::S;
     constexpr int AUX = 2 * NX;
+    constexpr int BLK = BlockOf<R, VXX>::value;
+    using MP = VxxMap<NX, VXX>;
+    constexpr int NV = MP::NV;    // stored entries of V_xx
+    constexpr int NVP = VXX ? NX * NX : 0;  // entries of the public layout (rows NS.., dense leaf)
+    static_assert(!(VXX && VALUE), "the vxx branch exists for time-parameterised solves only");
     constexpr unsigned FULL = 0xffffffffu;
     const int lane = threadIdx.x & 31;
     const long long n = io.n;
     const int S1 = o.max_steps + 1;
-    // leaves of the RMS norm: x, t, v, vx in time mode (NS); x, lambda, t in value mode (NS-1)
-    const R inv_nleaf = VALUE ? R(1.0 / (NS - 1)) : R(1.0 / NS);
+    // leaves of the RMS norm: x, t, v, vx (, vxx) in time mode (NS + NV); x, lambda, t in value mode (NS-1)
+    const R inv_nleaf = VALUE ? R(1.0 / (NS - 1)) : R(1.0 / (NS + NVP));
 
     // per-lane trajectory state
     R y[ND], k[S][ND];
@@ -222,6 +270,27 @@ solve_kernel(const typename Sys::Consts sc, const SolveOpts<R> o, const SolveIO<
         R* wbase = reinterpret_cast<R*>(pmp_smem) + (size_t)(threadIdx.x >> 5) * SL::WORDS_PER_WARP;
         sX = wbase; sVX = wbase + 32 * SL::XS; sSC = wbase + 64 * SL::XS;
     }
+    // VXX: this thread's column of [V | k1 .. kS] (entry e at sV[e * BLK]); the newest V is a pending dense node
+    R* sV = nullptr;
+    R vnorm2 = R(0);
+    bool new_node = false;
+    if (VXX) {
+        const size_t off = DENSE ? (size_t)(BLK / 32) * StageLayout<R, NX>::WORDS_PER_WARP : 0;
+        sV = reinterpret_cast<R*>(pmp_smem) + off + threadIdx.x;
+    }
+    // the warp writes the pending V_xx nodes of the lanes in `mask` (slot g_cur of each): 36 contiguous reals
+    auto write_vxx_nodes = [&](unsigned mask) {
+        __syncwarp();
+        const R* col0 = sV - lane;  // column of lane 0 of this warp
+        while (mask) {
+            const int src = __ffs(mask) - 1;
+            mask &= mask - 1;
+            const unsigned g = __shfl_sync(FULL, g_cur, src);
+            R* dst = io.dense.p[kDenseVxx] + (size_t)g * NVP;
+            for (int q = lane; q < NVP; q += 32) dst[q] = col0[MP::ent(q / NX, q % NX) * BLK + src];
+        }
+        __syncwarp();
+    };
 
     while (true) {
         // =============================== retire + refill =========================================
@@ -238,6 +307,10 @@ solve_kernel(const typename Sys::Consts sc, const SolveOpts<R> o, const SolveIO<
                 for (int q = 0; q < NX; q++) ye[(NX + 2 + q) * n + idx] = y[NX + q];
                 if (VALUE) { ye[NX * n + idx] = y[AUX]; ye[(NX + 1) * n + idx] = clock; }
                 else { ye[NX * n + idx] = aux_fixed + (clock - clock0); ye[(NX + 1) * n + idx] = y[AUX]; }
+                if (VXX) {
+#pragma unroll
+                    for (int q = 0; q < NVP; q++) ye[(NS + q) * n + idx] = sV[MP::ent(q / NX, q % NX) * BLK];
+                }
                 if (io.n_accepted) io.n_accepted[idx] = nacc;
                 if (io.n_steps) io.n_steps[idx] = nsteps;
                 if (io.result) io.result[idx] = result;
@@ -248,6 +321,10 @@ solve_kernel(const typename Sys::Consts sc, const SolveOpts<R> o, const SolveIO<
             // that the refill's loads are in flight while the padding stores are issued
             const unsigned pad_mask = DENSE ? __ballot_sync(FULL, fin) : 0u;
             const unsigned pad_g = g_cur, pad_row0 = row0;  // newest node and row start of the retiring lane
+            if (DENSE && VXX) {  // the last V_xx node of a retiring lane must leave its column before the refill
+                write_vxx_nodes(__ballot_sync(FULL, fin && new_node));
+                if (fin) new_node = false;
+            }
             if (DENSE) {
                 // The last group of a retiring trajectory (complete or not) is written by the retirement
                 // code below: it must leave the rings before the refill reuses them.
@@ -294,6 +371,19 @@ solve_kernel(const typename Sys::Consts sc, const SolveOpts<R> o, const SolveIO<
                     bool bad = false;
 #pragma unroll
                     for (int q = 0; q < ND; q++) bad = bad || (y[q] != y[q]);
+                    if (VXX) {
+                        R n2 = R(0);
+#pragma unroll
+                        for (int q = 0; q < NV; q++) {
+                            const R v = __ldg(io.y_f + (NS + MP::pub(q)) * n + idx);
+                            sV[q * BLK] = v;
+                            n2 = M::fma(MP::offdiag(q) ? v + v : v, v, n2);
+                            if (TB::FSAL) sV[(NV + q) * BLK] = __ldg(io.k1 + (ND + q) * n + idx);
+                        }
+                        bad = bad || (n2 != n2);
+                        vnorm2 = n2;
+                        new_node = DENSE;
+                    }
                     // NaN terminal state (levelsets.py:1233): retire at once with result 4
                     finished = bad || !(tprev < o.T1);
                     if (bad) result = PMP_RESULT_NAN;
@@ -326,6 +416,7 @@ solve_kernel(const typename Sys::Consts sc, const SolveOpts<R> o, const SolveIO<
                     warp_fill<R>(io.dense.p[kDenseV] + ps, (int)(row_hi - ps), lane, inf);
                     warp_fill<R>(io.dense.p[kDenseX] + (size_t)pv * NX, (int)(row_hi - pv) * NX, lane, inf);
                     warp_fill<R>(io.dense.p[kDenseVx] + (size_t)pv * NX, (int)(row_hi - pv) * NX, lane, inf);
+                    if (VXX) warp_fill<R>(io.dense.p[kDenseVxx] + (size_t)(gl + 1) * NVP, (int)(row_hi - gl - 1) * NVP, lane, inf);
                 }
             }
         }
@@ -351,11 +442,30 @@ solve_kernel(const typename Sys::Consts sc, const SolveOpts<R> o, const SolveIO<
             }
         }
         ready_v = false; ready_s = false;
+        if (DENSE && VXX) {  // V_xx nodes accepted by the previous attempt and the slot-0 nodes of the refill
+            write_vxx_nodes(__ballot_sync(FULL, new_node));
+            new_node = false;
+        }
 
         // =============================== one step attempt ========================================
         const R dt = tnext - tprev;
         const R h = dt * o.dir;
-        if (!TB::FSAL) field<Sys, R, VALUE, ULIT ? 1 : 2>(sc, y, k[0]);
+        // VXX: the candidate V_xx of this attempt.  FSAL methods: it is the last stage matrix; it goes to the
+        // column of k2 and the error partial sum_{j<S-1} (h e_j) k_j to the column of k3 while the last stage is
+        // formed (k2..k6 of an entry are dead once its last-stage value exists), so no register holds it across
+        // the last RHS.  Others (RK4): registers.
+        R V1[(VXX && !TB::FSAL) ? NV : 1];
+        if (!TB::FSAL) {
+            if constexpr (VXX) {
+                R Vs[NV];
+                field_vxx<Sys, R, BLK, VXX>(sc, y, k[0], Vs, sV + NV * BLK, [&](R* W) {
+#pragma unroll
+                    for (int q = 0; q < NV; q++) W[q] = sV[q * BLK];
+                });
+            } else {
+                field<Sys, R, VALUE, ULIT ? 1 : 2>(sc, y, k[0]);
+            }
+        }
         R y1[ND];
 #pragma unroll
         for (int i = 1; i < S; i++) {
@@ -376,7 +486,31 @@ solve_kernel(const typename Sys::Consts sc, const SolveOpts<R> o, const SolveIO<
                     if (TB::a(i, j) != 0.0) acc = M::fma(ha[j], k[j][q], acc);
                 ys[q] = acc;
             }
-            field<Sys, R, VALUE, ULIT ? 1 : 2>(sc, ys, k[i]);
+            if constexpr (VXX) {
+                R Vs[NV];
+                field_vxx<Sys, R, BLK, VXX>(sc, ys, k[i], Vs, sV + NV * (1 + i) * BLK, [&](R* W) {
+                    R hev[S];
+#pragma unroll
+                    for (int j = 0; j < S; j++) hev[j] = h * tp.template e<TB>(j);
+#pragma unroll
+                    for (int q = 0; q < NV; q++) {
+                        R acc = sV[q * BLK], ep = R(0);
+#pragma unroll
+                        for (int j = 0; j < i; j++) {
+                            const R kj = sV[(NV * (1 + j) + q) * BLK];
+                            if (TB::a(i, j) != 0.0) acc = M::fma(ha[j], kj, acc);
+                            if (last_fsal && TB::berr(j) != 0.0) ep = M::fma(hev[j], kj, ep);
+                        }
+                        W[q] = acc;
+                        if (last_fsal) {
+                            sV[(NV * 2 + q) * BLK] = acc;
+                            sV[(NV * 3 + q) * BLK] = ep;
+                        }
+                    }
+                });
+            } else {
+                field<Sys, R, VALUE, ULIT ? 1 : 2>(sc, ys, k[i]);
+            }
             if (last_fsal) {
 #pragma unroll
                 for (int q = 0; q < ND; q++) y1[q] = ys[q];
@@ -393,6 +527,16 @@ solve_kernel(const typename Sys::Consts sc, const SolveOpts<R> o, const SolveIO<
                 for (int j = 0; j < S; j++)
                     if (TB::b(j) != 0.0) acc = M::fma(hb[j], k[j][q], acc);
                 y1[q] = acc;
+            }
+            if constexpr (VXX) {
+#pragma unroll
+                for (int q = 0; q < NV; q++) {
+                    R acc = sV[q * BLK];
+#pragma unroll
+                    for (int j = 0; j < S; j++)
+                        if (TB::b(j) != 0.0) acc = M::fma(hb[j], sV[(NV * (1 + j) + q) * BLK], acc);
+                    V1[q] = acc;
+                }
             }
         }
 
@@ -417,6 +561,16 @@ solve_kernel(const typename Sys::Consts sc, const SolveOpts<R> o, const SolveIO<
                 const R scale = M::fma(o.rtol, M::max(M::abs(y[q]), M::abs(y1[q])), o.atol);
                 const R ratio = M::ctl_div(e, scale);
                 sumsq = M::fma(ratio, ratio, sumsq);
+            }
+            if constexpr (VXX) {  // fifth leaf of the norm (embedded methods are FSAL: see V1 above)
+                static_assert(!VXX || !TB::EMBEDDED || (TB::FSAL && S >= 4), "column reuse needs an FSAL method");
+#pragma unroll
+                for (int q = 0; q < NV; q++) {
+                    const R e = M::fma(he[S - 1], sV[(NV * S + q) * BLK], sV[(NV * 3 + q) * BLK]);
+                    const R scale = M::fma(o.rtol, M::max(M::abs(sV[q * BLK]), M::abs(sV[(NV * 2 + q) * BLK])), o.atol);
+                    const R ratio = M::ctl_div(e, scale);
+                    sumsq = M::fma(MP::offdiag(q) ? ratio + ratio : ratio, ratio, sumsq);
+                }
             }
             // integrate.py maps a NaN error estimate to +inf (=> reject, shrink by factormin); a NaN
             // in any component makes the whole sum NaN, so one test on the sum is equivalent
@@ -460,6 +614,19 @@ solve_kernel(const typename Sys::Consts sc, const SolveOpts<R> o, const SolveIO<
                     if (!(TB::EMBEDDED)) bad = bad || (y1[q] != y1[q]);
                     if (TB::FSAL) k[0][q] = k[S - 1][q];
                 }
+                if constexpr (VXX) {
+                    R n2 = R(0);
+#pragma unroll
+                    for (int q = 0; q < NV; q++) {
+                        const R v1 = TB::FSAL ? sV[(NV * 2 + q) * BLK] : V1[q];
+                        sV[q * BLK] = v1;
+                        n2 = M::fma(MP::offdiag(q) ? v1 + v1 : v1, v1, n2);
+                        if (TB::FSAL) sV[(NV + q) * BLK] = sV[(NV * S + q) * BLK];
+                    }
+                    vnorm2 = n2;
+                    if (!(TB::EMBEDDED)) bad = bad || (n2 != n2);
+                    new_node = DENSE && nacc < S1;
+                }
                 if (DENSE && nacc < S1) {
                     const R clock = tprev * o.dir;
                     g_cur = row0 + (unsigned)nacc;
@@ -472,6 +639,9 @@ solve_kernel(const typename Sys::Consts sc, const SolveOpts<R> o, const SolveIO<
             }
             // DiscreteTerminatingEvent, evaluated on the post-step state after every attempt
             if (!VALUE && result == 0 && o.event == PMP_EVENT_VALUE_GE && y[AUX] >= o.event_level)
+                result = PMP_RESULT_EVENT;
+            // np.linalg.norm(state.y['vxx']) > vxx_max_norm  (pontryagin_utils.py:508-512)
+            if (VXX && result == 0 && o.event == PMP_EVENT_VXX_NORM && M::sqrt(vnorm2) > o.event_level)
                 result = PMP_RESULT_EVENT;
             if (result == 0 && nan_state) result = PMP_RESULT_NAN;  // diffrax would idle to max_steps
             const bool more = tprev < o.T1;
@@ -508,26 +678,28 @@ inline size_t workspace_bytes_for(int nd, long long n, size_t real_size) {
     return 256 + (size_t)nd * (size_t)n * real_size;
 }
 
-template <class Sys, class R, int METHOD, bool DENSE, bool VALUE, bool ULIT, int MINB>
+template <class Sys, class R, int METHOD, bool DENSE, bool VALUE, bool ULIT, int MINB, int VXX = 0>
 int launch_one(const pmp_problem_t& p, const pmp_opts_t& o, long long n, const void* y_f, void* y_end,
                const pmp_dense_t* dense, int32_t* n_acc, int32_t* n_steps, int32_t* result,
                void* workspace, cudaStream_t st) {
     using TB = Tab<METHOD>;
-    constexpr int ND = 2 * Sys::NX + 1;
-    auto kern = solve_kernel<Sys, R, METHOD, DENSE, VALUE, ULIT, MINB>;
+    constexpr int ND = 2 * Sys::NX + 1, BLK = BlockOf<R, VXX>::value, NV = VxxMap<Sys::NX, VXX>::NV;
+    auto kern = solve_kernel<Sys, R, METHOD, DENSE, VALUE, ULIT, MINB, VXX>;
     int dev = 0, sms = 0, occ = 0;
     cudaError_t e = cudaGetDevice(&dev);
     if (e != cudaSuccess) return (int)e;
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    const size_t smem = DENSE ? (size_t)(kBlock / 32) * StageLayout<R, Sys::NX>::bytes_per_warp() : 0;
+    const size_t smem = (DENSE ? (size_t)(BLK / 32) * StageLayout<R, Sys::NX>::bytes_per_warp() : 0) +
+                        (size_t)BLK * NV * (1 + TB::S) * sizeof(R);
     if (smem > 48 * 1024) {
         e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return (int)e;
     }
-    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, kBlock, smem);
+    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, BLK, smem);
     if (e != cudaSuccess) return (int)e;
     if (occ < 1) occ = 1;
-    long long need = (n + kBlock - 1) / kBlock;
+    const long long need_prep = (n + kBlock - 1) / kBlock;
+    long long need = (n + BLK - 1) / BLK;
     long long cap = (long long)sms * occ;
     const int grid = (int)(need < cap ? need : cap);
 
@@ -539,18 +711,44 @@ int launch_one(const pmp_problem_t& p, const pmp_opts_t& o, long long n, const v
     io.y_end = (R*)y_end;
     io.n_accepted = n_acc; io.n_steps = n_steps; io.result = result;
     io.n = n;
-    io.dense = DensePtrs<R>{{nullptr, nullptr, nullptr, nullptr, nullptr}};
+    io.dense = DensePtrs<R>{{nullptr, nullptr, nullptr, nullptr, nullptr, nullptr}};
     if (DENSE && dense)
-        io.dense = DensePtrs<R>{{(R*)dense->ts, (R*)dense->t, (R*)dense->v, (R*)dense->x, (R*)dense->vx}};
+        io.dense = DensePtrs<R>{{(R*)dense->ts, (R*)dense->t, (R*)dense->v, (R*)dense->x, (R*)dense->vx,
+                                 VXX ? (R*)dense->vxx : nullptr}};
     if (TB::FSAL) {
-        prep_kernel<Sys, R, VALUE, ULIT><<<(unsigned)need, kBlock, 0, st>>>(sc, (const R*)y_f, (R*)((char*)workspace + 256), n,
-                                                                    io.counter);
+        prep_kernel<Sys, R, VALUE, ULIT, VXX><<<(unsigned)need_prep, kBlock, 0, st>>>(
+            sc, (const R*)y_f, (R*)((char*)workspace + 256), n, io.counter);
     } else {
         reset_counter_kernel<<<1, 1, 0, st>>>(io.counter);
     }
     const SolveOpts<R> so = make_solve_opts<R, TB>(o, TB::ORDER);
-    kern<<<grid, kBlock, smem, st>>>(sc, so, io, TabParams<R>::template make<TB>());
+    kern<<<grid, BLK, smem, st>>>(sc, so, io, TabParams<R>::template make<TB>());
     return (int)cudaGetLastError();
+}
+
+// PMP_FLAG_VXX instantiations (time-parameterised, KKT-form u*): a compile unit of their own
+template <template <class> class SysT>
+int launch_solve_vxx(const pmp_problem_t& p, const pmp_opts_t& o, long long n, const void* y_f, void* y_end,
+                     const pmp_dense_t* dense, int32_t* a, int32_t* s, int32_t* r, void* ws, cudaStream_t st) {
+    const bool dn = o.save_dense != 0, sym = (o.flags & PMP_FLAG_VXX_SYMMETRIC) != 0;
+#define PMP_GOV(R, METHOD)                                                                                          \
+    do {                                                                                                            \
+        if (dn && sym) return launch_one<SysT<R>, R, METHOD, true, false, false, 1, 2>(p, o, n, y_f, y_end, dense, a, s, r, ws, st);  \
+        if (dn) return launch_one<SysT<R>, R, METHOD, true, false, false, 1, 1>(p, o, n, y_f, y_end, dense, a, s, r, ws, st);         \
+        if (sym) return launch_one<SysT<R>, R, METHOD, false, false, false, 1, 2>(p, o, n, y_f, y_end, dense, a, s, r, ws, st);       \
+        return launch_one<SysT<R>, R, METHOD, false, false, false, 1, 1>(p, o, n, y_f, y_end, dense, a, s, r, ws, st);                \
+    } while (0)
+#define PMP_BY_METHODV(R)                                              \
+    do {                                                               \
+        if (o.method == PMP_METHOD_RK4) PMP_GOV(R, PMP_METHOD_RK4);       \
+        if (o.method == PMP_METHOD_TSIT5) PMP_GOV(R, PMP_METHOD_TSIT5);   \
+        if (o.method == PMP_METHOD_DOPRI5) PMP_GOV(R, PMP_METHOD_DOPRI5); \
+    } while (0)
+    if (o.dtype == PMP_F32) PMP_BY_METHODV(float);
+    if (o.dtype == PMP_F64) PMP_BY_METHODV(double);
+#undef PMP_BY_METHODV
+#undef PMP_GOV
+    return -1000;
 }
 
 template <template <class> class SysT, int MINB32, int MINB64>

@@ -14,6 +14,29 @@
 
 namespace pmp {
 
+// ---- storage of the value Hessian V_xx (PMP_FLAG_VXX) -------------------------------------------------
+// VXX = 1: all nx*nx entries, row-major (the reference's layout).  VXX = 2 (PMP_FLAG_VXX_SYMMETRIC): the
+// caller states that the terminal V_xx is symmetric; V_xx^T obeys the same Riccati equation (gx and flam
+// are symmetric, glam = -fx^T), so the solution stays symmetric and only the upper triangle is stored and
+// integrated (21 of 36 entries for nx = 6); off-diagonal entries count twice in the norms.
+template <int NX, int VXX> struct VxxMap {
+    static constexpr int NV = VXX == 1 ? NX * NX : (VXX == 2 ? NX * (NX + 1) / 2 : 0);
+    // storage entry of V[i][j]
+    __host__ __device__ static constexpr int ent(int i, int j) {
+        if (VXX != 2) return i * NX + j;
+        const int a = i < j ? i : j, b = i < j ? j : i;
+        return a * NX - a * (a - 1) / 2 + (b - a);
+    }
+    // (i, j), i <= j for VXX = 2, of storage entry e, as the public row-major index i*NX + j
+    __host__ __device__ static constexpr int pub(int e) {
+        if (VXX != 2) return e;
+        int i = 0, rem = e;
+        while (rem >= NX - i) { rem -= NX - i; i++; }
+        return i * NX + i + rem;
+    }
+    __host__ __device__ static constexpr bool offdiag(int e) { return VXX == 2 && (pub(e) / NX != pub(e) % NX); }
+};
+
 // =================================================================================================
 // flat (planar) quadrotor -- flatquad_landing_experiment.py:269-329
 //   x = (px, py, Phi, vx, vy, omega), u = (Fl, Fr) in [0, umax]^2
@@ -37,6 +60,8 @@ template <class R> struct Flatquad {
         // KKT form: edge minimiser coordinate = clip(kN*H_u[axis] + kQ[k], lo, hi); its multiplier
         // = +-(h01*coordinate + H_u[other axis] + kM[k])
         R kN, kQ[4], kM[4];
+        // vxx branch (rhs_jac): d(u0+u1)/dH_u and d(u1-u0)/d(lam5) of the unconstrained minimiser, kN r/I
+        R jMS, jD3, kN_rI;
     };
 
     static __host__ Consts make(const pmp_problem_t& p) {
@@ -71,6 +96,9 @@ template <class R> struct Flatquad {
             c.kM[k] = R(d * fixed);
         }
         c.kN = R(-1.0 / d);
+        c.jMS = R(-2.0 * (d - o) / det);
+        c.jD3 = R(-2.0 * (r / I) * (d + o) / det);
+        c.kN_rI = R(-(r / I) / d);
         return c;
     }
 
@@ -202,6 +230,139 @@ template <class R> struct Flatquad {
         ld[3] = -M::fma(c.two_qvel, x[3], lam[0]);
         ld[4] = -M::fma(c.two_qvel, x[4], lam[1]);
         ld[5] = -M::fma(c.two_qom, x[5], lam[2]);
+    }
+
+    // ---- value-Hessian branch: algo_params['pontryagin_solver_vxx'], pontryagin_utils.py:460-467 ----
+    //   vxx' = gx + glam vxx - vxx fx - vxx flam vxx,  (fx, flam), (gx, glam) = d pmp_rhs / d(x, lambda)
+    // differentiated THROUGH u_star_2d as jax does: the active set (which candidate wins) is piecewise
+    // constant, the winning candidate is differentiable in z = (Phi, lam3, lam4, lam5):
+    //   interior: du = -H_uu^-1 dH_u;  on an edge: only the moving coordinate, d/dz clip(kN H_u[ax] + kQ)
+    //   = kN dH_u[ax] strictly inside the edge and 0 in a corner.
+    // The four 6x6 Jacobians are sparse and flam has rank <= 2 (flam = f_u du/dlam), so the record below
+    // holds every entry that is not a structural 0 / +-1 / cost constant and one vxx' costs ~200 FMAs
+    // instead of the 864 of four dense 6x6 products:
+    //   fx  : [0][3] = [1][4] = [2][5] = 1, [3..5][2] = f32, f42, f52
+    //   gx  : -diag(2q_pos, 2q_pos, ., 2q_vel, 2q_vel, 2q_om), [2][2] = g22
+    //   glam: [3][0] = [4][1] = [5][2] = -1, [2][3..5] = l23, l24, l25
+    //   flam[a][b] = al[a] sg[b] + be[a] dl[b]  (a, b in 3..5), al = (-s/m, c/m, 0), be = (0, 0, r/I)
+    struct JacCoef {
+        R f32, f42, f52, g22, l23, l24, l25;
+        R al3, al4;  // al[3], al[4]
+        R sg[3], dl[3];
+    };
+
+    // rhs<2> (KKT-form u*) that also reports the Jacobian coefficients
+    static __device__ __forceinline__ void rhs_jac(const Consts& c, const R* x, const R* lam, R* xd, R& vd, R* ld,
+                                                   JacCoef& j) {
+        using M = Math<R>;
+        R s, co;
+        M::sincos(x[2], &s, &co);
+        const R base = M::fma(M::fma(lam[4], co, -(lam[3] * s)), c.inv_m, -(c.two_g_m * co));
+        const R rot = lam[5] * c.r_I;
+        const R Hu0 = base - rot, Hu1 = base + rot;
+        R u0 = -M::fma(c.hi00, Hu0, c.hi01 * Hu1);
+        R u1 = -M::fma(c.hi01, Hu0, c.hi00 * Hu1);
+        const R viol = M::max(M::max(c.lo0 - u0, c.lo1 - u1), M::max(u0 - c.hi0, u1 - c.hi1));
+        const bool outside = viol > R(0);
+        // same selection as ustar_sc<2>, additionally tracking which coordinate moves along the winning edge
+        const R xb = M::min(M::max(M::fma(c.kN, Hu0, c.kQ[0]), c.lo0), c.hi0);
+        const R yl = M::min(M::max(M::fma(c.kN, Hu1, c.kQ[1]), c.lo1), c.hi1);
+        const R xt = M::min(M::max(M::fma(c.kN, Hu0, c.kQ[2]), c.lo0), c.hi0);
+        const R yr = M::min(M::max(M::fma(c.kN, Hu1, c.kQ[3]), c.lo1), c.hi1);
+        const R mb = M::fma(c.h01, xb, Hu1 + c.kM[0]);
+        const R ml = M::fma(c.h01, yl, Hu0 + c.kM[1]);
+        const R mt = -M::fma(c.h01, xt, Hu1 + c.kM[2]);
+        const R mr = -M::fma(c.h01, yr, Hu0 + c.kM[3]);
+        R bm = mb, bx = xb, by = c.lo1;
+        bool axis1 = false;
+        bool gt = ml > bm;
+        bm = gt ? ml : bm; bx = gt ? c.lo0 : bx; by = gt ? yl : by; axis1 = gt ? true : axis1;
+        gt = mt > bm;
+        bm = gt ? mt : bm; bx = gt ? xt : bx; by = gt ? c.hi1 : by; axis1 = gt ? false : axis1;
+        gt = mr > bm;
+        bx = gt ? c.hi0 : bx; by = gt ? yr : by; axis1 = gt ? true : axis1;
+        u0 = outside ? bx : u0;
+        u1 = outside ? by : u1;
+        const bool free_edge = axis1 ? (by > c.lo1 && by < c.hi1) : (bx > c.lo0 && bx < c.hi0);
+        // d(u0+u1)/dz = MS dbase_z, d(u1-u0)/dz = MD dbase_z for z = Phi, lam3, lam4 (dH_u[0] = dH_u[1] = dbase);
+        // z = lam5 (dH_u = -+ r/I): S3, D3
+        const R ek = free_edge ? c.kN : R(0), ekr = free_edge ? c.kN_rI : R(0);
+        const R MS = outside ? ek : c.jMS, MD = outside ? (axis1 ? ek : -ek) : R(0);
+        const R S3 = outside ? (axis1 ? ekr : -ekr) : R(0), D3 = outside ? ekr : c.jD3;
+
+        const R Sm = (u0 + u1) * c.inv_m;
+        const R ax = -(s * Sm);
+        const R ay = M::fma(co, Sm, -c.g);
+        const R aw = (u1 - u0) * c.r_I;
+        xd[0] = x[3]; xd[1] = x[4]; xd[2] = x[5]; xd[3] = ax; xd[4] = ay; xd[5] = aw;
+        const R cm1 = co - R(1);
+        R l = c.q_pos * M::fma(x[0], x[0], x[1] * x[1]);
+        l = M::fma(c.q_ang, M::fma(cm1, cm1, s * s), l);
+        l = M::fma(c.q_vel, M::fma(x[3], x[3], x[4] * x[4]), l);
+        l = M::fma(c.q_om * x[5], x[5], l);
+        l = M::fma(ax, ax, l);
+        l = M::fma(ay, ay, l);
+        l = M::fma(aw, aw, l);
+        vd = -l;
+        const R lcs = M::fma(lam[3], co, lam[4] * s);
+        ld[0] = -(c.two_qpos * x[0]);
+        ld[1] = -(c.two_qpos * x[1]);
+        ld[2] = M::fma(Sm, lcs, -(s * M::fma(c.two_g, Sm, c.two_qang)));
+        ld[3] = -M::fma(c.two_qvel, x[3], lam[0]);
+        ld[4] = -M::fma(c.two_qvel, x[4], lam[1]);
+        ld[5] = -M::fma(c.two_qom, x[5], lam[2]);
+
+        // dbase_z: z = Phi equals H_xu[2] (symmetry of the Hessian of H), lam3, lam4
+        const R sm = s * c.inv_m, cm = co * c.inv_m;
+        const R hxu2 = M::fma(c.two_g, s, -lcs) * c.inv_m;
+        const R sum0 = MS * hxu2, dif0 = MD * hxu2;
+        j.al3 = -sm; j.al4 = cm;
+        j.sg[0] = -(MS * sm); j.sg[1] = MS * cm; j.sg[2] = S3;
+        j.dl[0] = -(MD * sm); j.dl[1] = MD * cm; j.dl[2] = D3;
+        j.f32 = -M::fma(co, Sm, sm * sum0);
+        j.f42 = M::fma(cm, sum0, -(s * Sm));
+        j.f52 = c.r_I * dif0;
+        const R hxx22 = M::fma(co, M::fma(c.two_g, Sm, c.two_qang), -(Sm * M::fma(lam[4], co, -(lam[3] * s))));
+        j.g22 = -M::fma(hxu2, sum0, hxx22);
+        j.l23 = M::fma(co, Sm, -(hxu2 * j.sg[0]));
+        j.l24 = M::fma(s, Sm, -(hxu2 * j.sg[1]));
+        j.l25 = -(hxu2 * j.sg[2]);
+    }
+
+    // vxx' for V stored as VxxMap<6, VXX> says (VXX = 2: upper triangle in, upper triangle out); every entry
+    // is handed to put(storage entry, value) as soon as it is complete
+    template <int VXX, class Put>
+    static __device__ __forceinline__ void vxx_dot(const Consts& c, const JacCoef& j, const R* V, Put&& put) {
+        using M = Math<R>;
+        using MP = VxxMap<6, VXX>;
+        R Z1[6], Z2[6], G2[6];
+#pragma unroll
+        for (int q = 0; q < 6; q++) {
+            const R v3 = V[MP::ent(3, q)], v4 = V[MP::ent(4, q)], v5 = V[MP::ent(5, q)];
+            Z1[q] = M::fma(j.sg[0], v3, M::fma(j.sg[1], v4, j.sg[2] * v5));
+            Z2[q] = M::fma(j.dl[0], v3, M::fma(j.dl[1], v4, j.dl[2] * v5));
+            G2[q] = M::fma(j.l23, v3, M::fma(j.l24, v4, j.l25 * v5));
+        }
+#pragma unroll
+        for (int i = 0; i < 6; i++) {
+            const R vi3 = V[MP::ent(i, 3)], vi4 = V[MP::ent(i, 4)], vi5 = V[MP::ent(i, 5)];
+            const R W1 = M::fma(j.al3, vi3, j.al4 * vi4), W2 = c.r_I * vi5;
+            const R vf2 = M::fma(vi3, j.f32, M::fma(vi4, j.f42, vi5 * j.f52));
+#pragma unroll
+            for (int q = (VXX == 2 ? i : 0); q < 6; q++) {
+                // gx + glam V - V fx
+                R a = (q == 2) ? -vf2 : (q > 2 ? -V[MP::ent(i, q - 3)] : R(0));
+                if (i == 2) a += G2[q];
+                if (i > 2) a -= V[MP::ent(i - 3, q)];
+                if (i == q) {
+                    const R gd = i == 2 ? j.g22 : (i < 2 ? -c.two_qpos : (i < 5 ? -c.two_qvel : -c.two_qom));
+                    a += gd;
+                }
+                a = M::fma(-W1, Z1[q], a);
+                a = M::fma(-W2, Z2[q], a);
+                put(MP::ent(i, q), a);
+            }
+        }
     }
 };
 

@@ -30,6 +30,18 @@ ATTEMPT_SPECIAL = {
 }
 
 
+# value-Hessian branch (PMP_FLAG_VXX), flatquad: one f_extended with the vxx leaf as the ORACLE evaluates it (closed-form
+# Jacobians through u*, then gx + glam vxx - vxx fx - vxx flam vxx with four dense 6x6 products) and one step attempt on
+# the 50-scalar state.  The CUDA kernel exploits the sparsity of the Jacobians (Flatquad::vxx_dot, ~1/4 of these flops),
+# so a rate quoted on these constants is "reference-algorithm flops", not FMA-pipe utilisation.
+RHS_FLOPS_VXX = 2205
+ATTEMPT_FLOPS_VXX = {_capi.METHOD_TSIT5: 16593, _capi.METHOD_DOPRI5: 16593, _capi.METHOD_RK4: 10028}
+
+
+def solve_flops_vxx(method: int, total_attempts: int, n_traj: int) -> int:
+    return total_attempts * ATTEMPT_FLOPS_VXX[method] + n_traj * RHS_FLOPS_VXX
+
+
 def solve_flops(system_id: int, method: int, total_attempts: int, n_traj: int) -> int:
     """flops_total = sum_traj (n_steps_traj * F_attempt + F_rhs)   (the F_rhs is the FSAL start-up)."""
     return total_attempts * ATTEMPT_FLOPS[(system_id, method)] + n_traj * RHS_FLOPS[system_id]

@@ -18,13 +18,19 @@ from . import _capi, systems
 from . import pontryagin_utils as pu
 
 
-def select_train_pts(value_interval, sols):
+def select_train_pts(value_interval, sols, vxx_max_norm=None):
     """levelsets.py:667-709: all saved nodes whose value lies in [v_lower, v_upper] (inf/NaN padding
-    drops out of the comparison), as a dict of flat arrays {'x','t','v','vx'}."""
+    drops out of the comparison), as a dict of flat arrays {'x','t','v','vx'[,'vxx']}.  With a 'vxx' leaf
+    (pontryagin_solver_vxx) nodes with ||vxx||_F >= vxx_max_norm are dropped as well (:684-689; the reference
+    reads algo_params['vxx_max_norm'] from its closure, here it is an argument)."""
     v_lower, v_upper = value_interval
     v = sols.ys["v"]
     v_finite = torch.isfinite(v)
     bool_train_idx = (v >= v_lower) & (v <= v_upper)
+    if "vxx" in sols.ys:
+        if vxx_max_norm is None:
+            raise ValueError("sols carries a 'vxx' leaf: pass vxx_max_norm (algo_params['vxx_max_norm'])")
+        bool_train_idx = bool_train_idx & (torch.linalg.matrix_norm(sols.ys["vxx"]) < vxx_max_norm)
     all_ys = {k: node[bool_train_idx] for k, node in sols.ys.items()}
     n_sel, n_fin = int(bool_train_idx.sum()), int(v_finite.sum())
     perc = 100.0 * n_sel / max(n_fin, 1)
@@ -44,7 +50,7 @@ def running_cost(ys: dict, problem_params: dict) -> torch.Tensor:
     n = x.numel() // nx
     y = torch.zeros((2 * nx + 2, n), dtype=dtype, device=dev)
     y[:nx] = x.reshape(n, nx).t()
-    y[nx + 2:] = vx.reshape(n, nx).t()
+    y[nx + 2:] = vx.reshape(n, nx).t()  # (a 'vxx' leaf does not enter the running cost)
     dy = torch.empty_like(y)
     with torch.cuda.device(dev):
         _capi.check(_capi.lib().pmp_rhs_batch_cuda(C.byref(problem), pu._code(dtype), n, y.data_ptr(), dy.data_ptr(),

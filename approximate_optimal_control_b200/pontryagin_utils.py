@@ -92,26 +92,31 @@ def _workspace(device: torch.device, nbytes: int) -> torch.Tensor:
     return ws
 
 
-def pack_state(state: dict, nx: int, dtype: torch.dtype, device) -> Tuple[torch.Tensor, bool]:
-    """The reference's state dict {'x','t','v','vx'} (pontryagin_utils.py:421-423, levelsets.py:588-593)
-    -> struct-of-arrays [NS, n].  Returns (y, batched)."""
-    if "vxx" in state:
-        raise NotImplementedError("the vxx (Hessian) branch of f_extended is not on the accelerated path")
+def pack_state(state: dict, nx: int, dtype: torch.dtype, device, vxx: bool = False) -> Tuple[torch.Tensor, bool]:
+    """The reference's state dict {'x','t','v','vx'[,'vxx']} (pontryagin_utils.py:421-427, levelsets.py:588-597)
+    -> struct-of-arrays [NS (+ nx*nx), n].  Returns (y, batched)."""
     x = _as_tensor(state["x"], dtype, device)
     batched = x.dim() == 2
     x = x.reshape(-1, nx)
     n = x.shape[0]
-    y = torch.empty((2 * nx + 2, n), dtype=dtype, device=device)
+    ns = 2 * nx + 2
+    y = torch.empty((ns + (nx * nx if vxx else 0), n), dtype=dtype, device=device)
     y[:nx] = x.t()
     y[nx] = _as_tensor(state.get("t", 0.0), dtype, device).reshape(-1).expand(n)
     y[nx + 1] = _as_tensor(state["v"], dtype, device).reshape(-1).expand(n)
-    y[nx + 2:] = _as_tensor(state["vx"], dtype, device).reshape(-1, nx).t()
+    y[nx + 2:ns] = _as_tensor(state["vx"], dtype, device).reshape(-1, nx).t()
+    if vxx:  # algo_params['pontryagin_solver_vxx']: rows ns + i*nx + j = vxx[i][j]
+        y[ns:] = _as_tensor(state["vxx"], dtype, device).reshape(-1, nx * nx).expand(n, nx * nx).t()
     return y, batched
 
 
 def unpack_state(y: torch.Tensor, nx: int, batched: bool = True) -> dict:
-    """[NS, n] -> {'x': (n,nx), 't': (n,), 'v': (n,), 'vx': (n,nx)} (leading axis dropped if single)."""
-    d = {"x": y[:nx].t(), "t": y[nx], "v": y[nx + 1], "vx": y[nx + 2:].t()}
+    """[NS, n] -> {'x': (n,nx), 't': (n,), 'v': (n,), 'vx': (n,nx)[, 'vxx': (n,nx,nx)]} (leading axis dropped
+    if single)."""
+    ns = 2 * nx + 2
+    d = {"x": y[:nx].t(), "t": y[nx], "v": y[nx + 1], "vx": y[nx + 2:ns].t()}
+    if y.shape[0] > ns:
+        d["vxx"] = y[ns:].t().reshape(-1, nx, nx)
     if not batched:
         d = {k: v[0] for k, v in d.items()}
     return d
@@ -121,7 +126,7 @@ def unpack_state(y: torch.Tensor, nx: int, batched: bool = True) -> dict:
 def solve_batch_soa(problem: _capi.Problem, opts: _capi.Opts, y_f: torch.Tensor, out=None):
     """Thin wrapper of pmp_solve_batch_cuda on struct-of-arrays CUDA tensors.  Asynchronous on the
     current stream.  `out` may carry preallocated outputs (keys y_end, n_accepted, n_steps, result,
-    and ts, x, t, v, vx when opts.save_dense)."""
+    and ts, x, t, v, vx (, vxx) when opts.save_dense)."""
     L = _capi.lib()
     assert y_f.is_cuda and y_f.is_contiguous()
     ns, n = y_f.shape
@@ -137,10 +142,13 @@ def solve_batch_soa(problem: _capi.Problem, opts: _capi.Opts, y_f: torch.Tensor,
     if opts.save_dense:
         s1 = opts.max_steps + 1
         shapes = {"ts": (n, s1), "x": (n, s1, nx), "t": (n, s1), "v": (n, s1), "vx": (n, s1, nx)}
+        if opts.flags & _capi.FLAG_VXX:
+            shapes["vxx"] = (n, s1, nx, nx)
         for k, shp in shapes.items():
             if k not in out:
                 out[k] = torch.empty(shp, dtype=y_f.dtype, device=dev)
-        dense = _capi.Dense(*(out[k].data_ptr() for k in ("ts", "x", "t", "v", "vx")))
+        dense = _capi.Dense(*(out[k].data_ptr() for k in ("ts", "x", "t", "v", "vx")),
+                            out["vxx"].data_ptr() if "vxx" in shapes else None)
     nbytes = _capi.check(L.pmp_solve_workspace_bytes(C.byref(problem), C.byref(opts), n))
     ws = _workspace(dev, nbytes)
     with torch.cuda.device(dev):
@@ -214,6 +222,8 @@ def _wrap_solution(out, nx, batched, t0, t1, opts, problem=None) -> Solution:
     if opts.save_dense:
         ts = out["ts"]
         ys = {"x": out["x"], "t": out["t"], "v": out["v"], "vx": out["vx"]}
+        if "vxx" in out:
+            ys["vxx"] = out["vxx"]
     stats = {"num_steps": out["n_steps"], "num_accepted_steps": out["n_accepted"],
              "num_rejected_steps": out["n_steps"] - out["n_accepted"]}
     sol = Solution(t0=t0, t1=t1, ts=ts, ys=ys, y_end=unpack_state(out["y_end"], nx), stats=stats,
@@ -248,35 +258,49 @@ def define_backward_solver(problem_params: dict, algo_params: dict):
     True; RK4 is fixed-step), 'pontryagin_solver_dt0', '..._dtmin', '..._dtmax',
     'pontryagin_solver_save_steps' (default True = SaveAt(steps=True)), 'dtype'.
     """
-    if algo_params.get("pontryagin_solver_vxx", False):
-        raise NotImplementedError("pontryagin_solver_vxx=True (Hessian propagation, pontryagin_utils.py:"
-                                  "460-467) is not on the accelerated path")
     problem = systems.to_c_problem(problem_params)
     nx = problem.nx
+    # pontryagin_utils.py:425,460: also propagate the value Hessian ('vxx' leaf of the state)
+    with_vxx = bool(algo_params.get("pontryagin_solver_vxx", False))
+    if with_vxx and problem.system_id != _capi.SYS_FLATQUAD:
+        raise NotImplementedError("pontryagin_solver_vxx=True: only the flatquad functor carries the Jacobians "
+                                  "of the PMP right hand side through u*")
 
     def f_extended(t, state, args=None):
         """RHS of the extended system in forward time (pontryagin_utils.py:418-482)."""
         dev = _device(state["x"])
         dtype = _infer_dtype(algo_params, state["x"])
-        y, batched = pack_state(state, nx, dtype, dev)
+        y, batched = pack_state(state, nx, dtype, dev, with_vxx)
         dy = torch.empty_like(y)
         with torch.cuda.device(dev):
-            _capi.check(_capi.lib().pmp_rhs_batch_cuda(C.byref(problem), _code(dtype), y.shape[1],
-                                                       y.data_ptr(), dy.data_ptr(), _stream_ptr(dev)))
+            _capi.check(_capi.lib().pmp_rhs_batch_cuda_flags(
+                C.byref(problem), _code(dtype), _capi.FLAG_VXX if with_vxx else 0, y.shape[1], y.data_ptr(),
+                dy.data_ptr(), _stream_ptr(dev)))
         return unpack_state(dy, nx, batched)
 
     def solve_backward(y_f, save_steps=None):
         dev = _device(y_f["x"])
         dtype = _infer_dtype(algo_params, y_f["x"])
-        y, batched = pack_state(y_f, nx, dtype, dev)
+        y, batched = pack_state(y_f, nx, dtype, dev, with_vxx)
         T = float(algo_params["pontryagin_solver_T"])
         method = algo_params.get("pontryagin_solver_method", _DEFAULTS["method"])
         adaptive = bool(algo_params.get("pontryagin_solver_adaptive", True)) and str(method).lower() != "rk4"
         if save_steps is None:
             save_steps = bool(algo_params.get("pontryagin_solver_save_steps", True))
         dt0 = float(algo_params.get("pontryagin_solver_dt0", _DEFAULTS["dt0"]))
+        over = {}
+        if with_vxx:
+            flags = _capi.FLAG_VXX
+            # a symmetric terminal Hessian (the reference starts from P_lqr, levelsets.py:595) stays symmetric:
+            # the kernel then integrates the upper triangle only
+            vf = y[2 * nx + 2:].reshape(nx, nx, -1)
+            if bool(algo_params.get("pontryagin_solver_vxx_symmetric", torch.equal(vf, vf.transpose(0, 1)))):
+                flags |= _capi.FLAG_VXX_SYMMETRIC
+            over["flags"] = flags
+            if "vxx_max_norm" in algo_params:  # pontryagin_utils.py:508-512
+                over.update(event=_capi.EVENT_VXX_NORM, event_level=float(algo_params["vxx_max_norm"]))
         opts = _solver_opts(algo_params, dtype, t0=0.0, t1=-T, dt0=-abs(dt0), adaptive=int(adaptive),
-                            save_dense=int(save_steps))
+                            save_dense=int(save_steps), **over)
         out = solve_batch_soa(problem, opts, y)
         return _wrap_solution(out, nx, batched, 0.0, -T, opts, problem)
 

@@ -42,7 +42,7 @@
 extern "C" {
 #endif
 
-#define PMP_ABI_VERSION 2
+#define PMP_ABI_VERSION 3
 
 /* systems (dynamics are compile-time functors; problem_params['system_name'] selects one) */
 enum {
@@ -69,7 +69,9 @@ enum {
 /* terminating events (diffrax.DiscreteTerminatingEvent, evaluated after every step attempt) */
 enum {
     PMP_EVENT_NONE = 0,
-    PMP_EVENT_VALUE_GE = 1 /* stop once v >= event_level (value level set, problem_params['V_max']) */
+    PMP_EVENT_VALUE_GE = 1, /* stop once v >= event_level (value level set, problem_params['V_max']) */
+    PMP_EVENT_VXX_NORM = 2  /* stop once ||vxx||_F > event_level (algo_params['vxx_max_norm'],
+                               pontryagin_utils.py:508-519); needs PMP_FLAG_VXX */
 };
 
 /* per-trajectory result codes, diffrax-compatible (levelsets.py:1218 tests result == 1) */
@@ -89,7 +91,18 @@ enum {
      * non-negative -- the same point in exact arithmetic (the box-constrained minimiser of a strictly
      * convex quadratic is the unique KKT point), better conditioned in floating point than comparing
      * H values, and ~2.5x fewer instructions.  pmp_ustar_batch_cuda always uses the literal form. */
-    PMP_FLAG_USTAR_LITERAL = 1
+    PMP_FLAG_USTAR_LITERAL = 1,
+    /* algo_params['pontryagin_solver_vxx']: also propagate the value Hessian V_xx along the characteristic,
+     * vxx' = gx + glam vxx - vxx fx - vxx flam vxx with (fx, flam, gx, glam) the Jacobians of the PMP right
+     * hand side THROUGH u* (pontryagin_utils.py:460-467).  The state gains nx*nx rows after vx (row-major
+     * vxx[i][j] at row 2nx+2 + i*nx + j), the error norm one more leaf.  flatquad only. */
+    PMP_FLAG_VXX = 2,
+    /* with PMP_FLAG_VXX: the caller guarantees that every terminal vxx is symmetric (vxx[i][j] == vxx[j][i]
+     * bit for bit; the reference starts from the LQR solution P, levelsets.py:595).  vxx^T obeys the same
+     * Riccati equation, so the solution stays symmetric: the kernel then reads, integrates and stores only
+     * the upper triangle (21 of 36 entries; off-diagonal entries count twice in the error norm and in
+     * ||vxx||_F) and mirrors it on output.  Differs from the general path by rounding only. */
+    PMP_FLAG_VXX_SYMMETRIC = 4
 };
 
 /* error codes */
@@ -141,17 +154,19 @@ typedef struct {
     void *t;  /* [n][S1]     */
     void *v;  /* [n][S1]     */
     void *vx; /* [n][S1][nx] */
+    void *vxx; /* [n][S1][nx][nx], required with PMP_FLAG_VXX, ignored (may be NULL) otherwise */
 } pmp_dense_t;
 
 int pmp_abi_version(void);
 const char *pmp_last_error(void);
 int pmp_state_rows(const pmp_problem_t *problem); /* NS = 2*nx+2 */
+int pmp_state_rows_flags(const pmp_problem_t *problem, int32_t flags); /* + nx*nx with PMP_FLAG_VXX */
 
 /* number of CUDA devices visible to this process (<0: error, 0: none) */
 int pmp_device_count(void);
 
 /* Scratch the solve needs for n trajectories (work-queue counter + the first-stage derivative
- * k1 = F(y_f) of every trajectory, [2nx+1][n] reals).  The caller allocates it on the device. */
+ * k1 = F(y_f) of every trajectory, [2nx+1 (+ nx*nx with PMP_FLAG_VXX)][n] reals).  The caller allocates it on the device. */
 int64_t pmp_solve_workspace_bytes(const pmp_problem_t *problem, const pmp_opts_t *opts, int64_t n);
 
 /* Integrate n trajectories from their terminal states y_f [NS][n].
@@ -172,6 +187,11 @@ int pmp_solve_launch_count(const pmp_problem_t *problem, const pmp_opts_t *opts,
 /* forward-time extended RHS f_extended(t, state) for n states: y [NS][n] -> dy [NS][n] */
 int pmp_rhs_batch_cuda(const pmp_problem_t *problem, int32_t dtype, int64_t n, const void *y,
                        void *dy, void *cuda_stream);
+
+/* Same with opts-style flags: PMP_FLAG_VXX adds the vxx rows (f_extended with
+ * algo_params['pontryagin_solver_vxx'], pontryagin_utils.py:460-467): y, dy [NS + nx*nx][n]; flatquad only */
+int pmp_rhs_batch_cuda_flags(const pmp_problem_t *problem, int32_t dtype, int32_t flags, int64_t n,
+                             const void *y, void *dy, void *cuda_stream);
 
 /* u* = argmin_u H(x,u,lambda) over the input box: x [nx][n], lam [nx][n] -> u [nu][n] */
 int pmp_ustar_batch_cuda(const pmp_problem_t *problem, int32_t dtype, int64_t n, const void *x,

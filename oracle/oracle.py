@@ -24,7 +24,8 @@ SYS_FLATQUAD, SYS_ORBITS, SYS_LQR = 0, 1, 2
 RK4, TSIT5, DOPRI5 = 0, 1, 2
 F32, F64 = 0, 1
 INDEP_TIME, INDEP_VALUE = 0, 1
-EVENT_NONE, EVENT_VALUE_GE = 0, 1
+EVENT_NONE, EVENT_VALUE_GE, EVENT_VXX_NORM = 0, 1, 2
+FLAG_USTAR_LITERAL, FLAG_VXX = 1, 2
 
 
 class Problem(C.Structure):
@@ -45,7 +46,7 @@ class Opts(C.Structure):
 
 class Dense(C.Structure):
     _fields_ = [("ts", C.c_void_p), ("x", C.c_void_p), ("t", C.c_void_p), ("v", C.c_void_p),
-                ("vx", C.c_void_p)]
+                ("vx", C.c_void_p), ("vxx", C.c_void_p)]
 
 
 def build(force: bool = False) -> str:
@@ -142,7 +143,8 @@ def solve_batch(problem: Problem, opts: Opts, y_f: np.ndarray, n_threads: int = 
     y_f = np.ascontiguousarray(y_f, dtype=dt)
     ns, n = y_f.shape
     nx = problem.nx
-    assert ns == 2 * nx + 2
+    vxx = bool(opts.flags & FLAG_VXX)
+    assert ns == 2 * nx + 2 + (nx * nx if vxx else 0)
     out = {"y_end": np.empty((ns, n), dt), "n_accepted": np.empty(n, np.int32),
            "n_steps": np.empty(n, np.int32), "result": np.empty(n, np.int32)}
     dense = None
@@ -150,7 +152,9 @@ def solve_batch(problem: Problem, opts: Opts, y_f: np.ndarray, n_threads: int = 
         s1 = opts.max_steps + 1
         out.update(ts=np.empty((n, s1), dt), x=np.empty((n, s1, nx), dt), t=np.empty((n, s1), dt),
                    v=np.empty((n, s1), dt), vx=np.empty((n, s1, nx), dt))
-        dense = Dense(*(out[k].ctypes.data for k in ("ts", "x", "t", "v", "vx")))
+        if vxx:
+            out["vxx"] = np.empty((n, s1, nx, nx), dt)
+        dense = Dense(*(out[k].ctypes.data for k in ("ts", "x", "t", "v", "vx")), out["vxx"].ctypes.data if vxx else None)
     _check(lib().pmp_oracle_solve_batch(C.byref(problem), C.byref(opts), n, y_f.ctypes.data,
                                         out["y_end"].ctypes.data,
                                         C.byref(dense) if dense is not None else None,
@@ -190,6 +194,18 @@ def interp_batch(problem: Problem, opts: Opts, y0: np.ndarray, t1: np.ndarray, t
     _check(lib().pmp_oracle_interp_batch(C.byref(problem), C.byref(opts), y0.shape[1], y0.ctypes.data, t1.ctypes.data,
                                          target.ctypes.data, int(mode), out.ctypes.data))
     return out
+
+
+def vxx_rhs(problem: Problem, x, lam, vxx):
+    """flatquad: (fx, flam, gx, glam, vxx_dot) of pontryagin_utils.py:460-467 for one state (fp64)."""
+    x = np.ascontiguousarray(x, np.float64); lam = np.ascontiguousarray(lam, np.float64)
+    vxx = np.ascontiguousarray(vxx, np.float64)
+    jac = np.zeros((4, 6, 6)); out = np.zeros((6, 6))
+    L = lib()
+    L.pmp_oracle_vxx_rhs.argtypes = [C.POINTER(Problem), C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+    _check(L.pmp_oracle_vxx_rhs(C.byref(problem), x.ctypes.data, lam.ctypes.data, vxx.ctypes.data, jac.ctypes.data,
+                                out.ctypes.data))
+    return jac[0], jac[1], jac[2], jac[3], out
 
 
 def opcount(problem: Problem, opts: Opts, y0: np.ndarray) -> dict:

@@ -21,11 +21,11 @@ int fail(int code, const char* msg) {
     return code;
 }
 
-template <class R, class Sys>
+template <class R, class Sys, bool VXX = false>
 int solve_batch_t(const pmp_problem_t& p, const pmp_opts_t& o, int64_t n, const R* y_f, R* y_end,
                   const pmp_dense_t* dense, int32_t* n_acc, int32_t* n_steps, int32_t* result,
                   int n_threads, int model_pass1) {
-    constexpr int NX = Sys::NX, NS = 2 * NX + 2;
+    constexpr int NX = Sys::NX, NS = 2 * NX + 2 + (VXX ? NX * NX : 0);
     Sys sys(p);
     if constexpr (Sys::NU == 2) sys.model_pass1 = model_pass1 != 0;
     const int64_t S1 = o.max_steps + 1;
@@ -44,8 +44,9 @@ int solve_batch_t(const pmp_problem_t& p, const pmp_opts_t& o, int64_t n, const 
             if (dense->t) sink.t = (R*)dense->t + i * S1;
             if (dense->v) sink.v = (R*)dense->v + i * S1;
             if (dense->vx) sink.vx = (R*)dense->vx + i * S1 * NX;
+            if (VXX && dense->vxx) sink.vxx = (R*)dense->vxx + i * S1 * NX * NX;
         }
-        TrajStats st = solve_one<R, Sys>(sys, o, y0, y1, sink);
+        TrajStats st = solve_one<R, Sys, VXX>(sys, o, y0, y1, sink);
         for (int q = 0; q < NS; q++) y_end[q * n + i] = y1[q];
         if (n_acc) n_acc[i] = st.n_accepted;
         if (n_steps) n_steps[i] = st.n_steps;
@@ -119,6 +120,12 @@ int pmp_oracle_solve_batch(const pmp_problem_t* p, const pmp_opts_t* o, int64_t 
     if (int e = check(p, o)) return e;
     if (!o) return fail(PMP_ERR_BAD_ARG, "opts is NULL");
     if (n < 0 || (n > 0 && (!y_f || !y_end))) return fail(PMP_ERR_BAD_ARG, "bad n / NULL buffers");
+    if (o->flags & PMP_FLAG_VXX) {
+        if (p->system_id != PMP_SYS_FLATQUAD) return fail(PMP_ERR_UNSUPPORTED, "vxx branch: flatquad only");
+        if (o->dtype == PMP_F32)
+            return solve_batch_t<float, Flatquad<float>, true>(*p, *o, n, (const float*)y_f, (float*)y_end, dense, n_accepted, n_steps, result, n_threads, model_pass1);
+        return solve_batch_t<double, Flatquad<double>, true>(*p, *o, n, (const double*)y_f, (double*)y_end, dense, n_accepted, n_steps, result, n_threads, model_pass1);
+    }
     switch (p->system_id) {
         case PMP_SYS_FLATQUAD:
             return solve_dispatch<Flatquad<float>, Flatquad<double>>(*p, *o, n, y_f, y_end, dense, n_accepted, n_steps, result, n_threads, model_pass1);
@@ -160,6 +167,24 @@ int pmp_oracle_ustar_batch(const pmp_problem_t* p, int32_t dtype, int64_t n, con
     }
 #undef US_CASE
     return fail(PMP_ERR_UNSUPPORTED, "unknown system_id");
+}
+
+// flatquad only: Jacobians of pmp_rhs through u* and vxx_dot (pontryagin_utils.py:460-467), fp64, one state per call.
+// jac_out = fx, flam, gx, glam (4 x 36, row-major), vxx_dot_out 36.
+int pmp_oracle_vxx_rhs(const pmp_problem_t* p, const double* x, const double* lam, const double* vxx, double* jac_out,
+                       double* vxx_dot_out) {
+    if (int e = check(p, nullptr)) return e;
+    if (p->system_id != PMP_SYS_FLATQUAD) return fail(PMP_ERR_UNSUPPORTED, "vxx branch: flatquad only");
+    Flatquad<double> sys(*p);
+    double fx[6][6], flam[6][6], gx[6][6], glam[6][6];
+    sys.pmp_jacobians(x, lam, fx, flam, gx, glam);
+    for (int i = 0; i < 6; i++)
+        for (int j = 0; j < 6; j++) {
+            jac_out[i * 6 + j] = fx[i][j]; jac_out[36 + i * 6 + j] = flam[i][j];
+            jac_out[72 + i * 6 + j] = gx[i][j]; jac_out[108 + i * 6 + j] = glam[i][j];
+        }
+    sys.vxx_dot(x, lam, vxx, vxx_dot_out);
+    return 0;
 }
 
 // dense output (diffrax Solution.evaluate) on one step per query; same contract as pmp_interp_batch_cuda
@@ -212,6 +237,30 @@ int pmp_oracle_opcount(const pmp_problem_t* p, const pmp_opts_t* o, const double
         out[2] = op_counts().flops - out[0];
         out[3] = op_counts().special - out[1];
     };
+    if (o->flags & PMP_FLAG_VXX) {
+        // value-Hessian branch: y0 holds 50 doubles; out[0..1] = f_extended INCLUDING vxx_dot as the oracle
+        // evaluates it (closed-form Jacobians, four dense 6x6 products, pontryagin_utils.py:465)
+        if (p->system_id != PMP_SYS_FLATQUAD) return fail(PMP_ERR_UNSUPPORTED, "vxx branch: flatquad only");
+        Flatquad<Counted> sys(*p);
+        sys.model_pass1 = true;
+        constexpr int NS = 50;
+        Counted y[NS], dy[NS], ye[NS];
+        for (int q = 0; q < NS; q++) y[q] = Counted(y0[q]);
+        op_counts() = OpCounts{};
+        sys.rhs(y, dy);
+        sys.vxx_dot(y, y + 8, y + 14, dy + 14);
+        out[0] = op_counts().flops;
+        out[1] = op_counts().special;
+        pmp_opts_t one = *o;
+        one.max_steps = 1;
+        one.save_dense = 0;
+        one.event = PMP_EVENT_NONE;
+        op_counts() = OpCounts{};
+        solve_one<Counted, Flatquad<Counted>, true>(sys, one, y, ye, DenseSink<Counted>{});
+        out[2] = op_counts().flops - out[0];
+        out[3] = op_counts().special - out[1];
+        return 0;
+    }
     switch (p->system_id) {
         case PMP_SYS_FLATQUAD: run(Flatquad<Counted>(*p)); return 0;
         case PMP_SYS_ORBITS: run(Orbits<Counted>(*p)); return 0;

@@ -163,7 +163,15 @@ template <class R> struct Flatquad {
         ustar_sc(x, lam, s, c, u);
     }
     void ustar_sc(const R* x, const R* lam, R s, R c, R* u) const {
+        int best;
+        bool moving_free;
+        ustar_active(x, lam, s, c, u, best, moving_free);
+    }
+    // same, also reporting which candidate won (0 = unconstrained, k = edge k) and, for an edge, whether its
+    // line-search parameter is strictly inside (0,1) (else the point sits in a corner)
+    void ustar_active(const R* x, const R* lam, R s, R c, R* u, int& best_out, bool& moving_free) const {
         R Hu[2];
+        bool edge_free[5] = {false, false, false, false, false};
         hu0(lam, s, c, Hu);
         R cand[5][2];
         // :41  unconstrained minimiser solve(H_uu, -H_u)
@@ -176,6 +184,7 @@ template <class R> struct Flatquad {
             const R* b = hull[(k + 3) % 4];
             const int ax = edge_axis[k];
             R sc = r_clip(-((Hu[ax] + edge_g[k]) * edge_d[k]) * edge_inv_den[k], R(0), R(1));
+            edge_free[k + 1] = r_val(sc) > 0.0 && r_val(sc) < 1.0;
             cand[k + 1][ax] = sc * a[ax] + (R(1) - sc) * b[ax];
             cand[k + 1][1 - ax] = a[1 - ax];
         }
@@ -210,6 +219,77 @@ template <class R> struct Flatquad {
         best = argmin5(Hs);
         u[0] = cand[best][0];
         u[1] = cand[best][1];
+        best_out = best;
+        moving_free = edge_free[best];
+    }
+
+    // Jacobians of pmp_rhs(x, lam) = (f(x, u*), -H_x(x, u*, lam)) with respect to (x, lam), differentiated
+    // THROUGH u_star_2d as jax does at pontryagin_utils.py:462-463: the argmin index is piecewise constant, the
+    // winning candidate is differentiable (unconstrained: -H_uu^-1 H_u; edge: d/dz of the clipped line search,
+    // zero when clipped).  (fx, flam), (gx, glam) in the reference's naming.
+    void pmp_jacobians(const R* x, const R* lam, R fx[6][6], R flam[6][6], R gx[6][6], R glam[6][6]) const {
+        R s = r_sin(x[2]), c = r_cos(x[2]);
+        R u[2];
+        int best;
+        bool moving_free;
+        ustar_active(x, lam, s, c, u, best, moving_free);
+        // H_u(u=0) depends on z in {Phi, lam3, lam4, lam5} only: dHu[z][component]
+        const R dbase[4] = {(-(lam[4] * s) - lam[3] * c) * inv_m + two_g_m * s, -(s * inv_m), c * inv_m, R(0)};
+        const R drot[4] = {R(0), R(0), R(0), r_I};
+        R du[4][2];  // du*/dz
+        for (int z = 0; z < 4; z++) {
+            const R d0 = dbase[z] - drot[z], d1 = dbase[z] + drot[z];
+            if (best == 0) {
+                du[z][0] = -(Hinv[0][0] * d0 + Hinv[0][1] * d1);
+                du[z][1] = -(Hinv[1][0] * d0 + Hinv[1][1] * d1);
+            } else {
+                const int ax = edge_axis[best - 1];
+                du[z][0] = R(0); du[z][1] = R(0);
+                if (moving_free) du[z][ax] = -((ax == 0 ? d0 : d1) / Huu[ax][ax]);
+            }
+        }
+        const R Sm = (u[0] + u[1]) * inv_m;
+        const R fu[6][2] = {{R(0), R(0)}, {R(0), R(0)}, {R(0), R(0)}, {-(s * inv_m), -(s * inv_m)},
+                            {c * inv_m, c * inv_m}, {-r_I, r_I}};
+        const R hxu2 = (two_g * s - (lam[3] * c + lam[4] * s)) * inv_m;  // d(H_x[2])/dFl = d/dFr
+        for (int i = 0; i < 6; i++)
+            for (int j = 0; j < 6; j++) { fx[i][j] = R(0); flam[i][j] = R(0); gx[i][j] = R(0); glam[i][j] = R(0); }
+        // f_x
+        fx[0][3] = R(1); fx[1][4] = R(1); fx[2][5] = R(1);
+        fx[3][2] = -(c * Sm); fx[4][2] = -(s * Sm);
+        // + f_u u_x (u depends on x through Phi only), f_u u_lam
+        const int lcol[4] = {-1, 3, 4, 5};
+        for (int i = 3; i < 6; i++) {
+            fx[i][2] = fx[i][2] + (fu[i][0] * du[0][0] + fu[i][1] * du[0][1]);
+            for (int z = 1; z < 4; z++) flam[i][lcol[z]] = fu[i][0] * du[z][0] + fu[i][1] * du[z][1];
+        }
+        // gx = -(H_xx + H_xu u_x)
+        gx[0][0] = -two_qpos; gx[1][1] = -two_qpos; gx[3][3] = -two_qvel; gx[4][4] = -two_qvel; gx[5][5] = -two_qom;
+        const R hxx22 = two_qang * c + two_g * c * Sm - Sm * (lam[4] * c - lam[3] * s);
+        gx[2][2] = -(hxx22 + hxu2 * (du[0][0] + du[0][1]));
+        // glam = -(f_x' + H_xu u_lam)
+        glam[3][0] = R(-1); glam[4][1] = R(-1); glam[5][2] = R(-1);
+        glam[2][3] = c * Sm; glam[2][4] = s * Sm;
+        for (int z = 1; z < 4; z++) glam[2][lcol[z]] = glam[2][lcol[z]] - hxu2 * (du[z][0] + du[z][1]);
+    }
+    // vxx_dot = gx + glam vxx - vxx fx - vxx flam vxx        pontryagin_utils.py:465 (forward time)
+    void vxx_dot(const R* x, const R* lam, const R* vxx /*[6][6] row-major*/, R* out) const {
+        R fx[6][6], flam[6][6], gx[6][6], glam[6][6], t1[6][6];
+        pmp_jacobians(x, lam, fx, flam, gx, glam);
+        for (int i = 0; i < 6; i++)
+            for (int j = 0; j < 6; j++) {
+                R a = R(0);
+                for (int k = 0; k < 6; k++) a = a + flam[i][k] * vxx[k * 6 + j];
+                t1[i][j] = a;  // flam vxx
+            }
+        for (int i = 0; i < 6; i++)
+            for (int j = 0; j < 6; j++) {
+                R a = gx[i][j];
+                for (int k = 0; k < 6; k++) a = a + glam[i][k] * vxx[k * 6 + j];
+                for (int k = 0; k < 6; k++) a = a - vxx[i * 6 + k] * fx[k][j];
+                for (int k = 0; k < 6; k++) a = a - vxx[i * 6 + k] * t1[k][j];
+                out[i * 6 + j] = a;
+            }
     }
     // numpy/jax argmin: the first NaN wins, else the first minimum
     static int argmin5(const R* Hs) {
@@ -444,16 +524,19 @@ inline const Tableau* tableau_for(int method) {
 // as called at pontryagin_utils.py:492-525, with diffrax 0.4.1 semantics.
 // =================================================================================================
 template <class R> struct DenseSink {  // one trajectory's rows of the dense buffers (may be null)
-    R* ts = nullptr; R* x = nullptr; R* t = nullptr; R* v = nullptr; R* vx = nullptr;
+    R* ts = nullptr; R* x = nullptr; R* t = nullptr; R* v = nullptr; R* vx = nullptr; R* vxx = nullptr;
 };
 
 struct TrajStats {
     int32_t n_accepted = 0, n_steps = 0, result = 0;
 };
 
-template <class R, class Sys>
+// VXX: the state carries the value Hessian as well (pontryagin_utils.py:460-467): NV = NX*NX more scalars
+// after vx, one more leaf of the error norm, optional ||vxx||_F event.  The code below calls the total
+// state length NS.
+template <class R, class Sys, bool VXX = false>
 TrajStats solve_one(const Sys& sys, const pmp_opts_t& o, const R* y_f, R* y_end, DenseSink<R> sink) {
-    constexpr int NX = Sys::NX, NS = 2 * NX + 2, IT = NX, IV = NX + 1;
+    constexpr int NX = Sys::NX, NB = 2 * NX + 2, NV = VXX ? NX * NX : 0, NS = NB + NV, IT = NX, IV = NX + 1;
     const Tableau& tb = *tableau_for(o.method);
     const bool value_mode = o.indep == PMP_INDEP_VALUE;
     const int S1 = o.max_steps + 1;
@@ -478,6 +561,7 @@ TrajStats solve_one(const Sys& sys, const pmp_opts_t& o, const R* y_f, R* y_end,
         if (sink.t) sink.t[slot] = y[IT];
         if (sink.v) sink.v[slot] = y[IV];
         if (sink.vx) for (int i = 0; i < NX; i++) sink.vx[slot * NX + i] = y[NX + 2 + i];
+        if (VXX && sink.vxx) for (int i = 0; i < NV; i++) sink.vxx[slot * NV + i] = y[NB + i];
     };
     auto pad = [&](int from) {
         for (int slot = from; slot < S1; slot++) {
@@ -486,6 +570,7 @@ TrajStats solve_one(const Sys& sys, const pmp_opts_t& o, const R* y_f, R* y_end,
             if (sink.t) sink.t[slot] = inf;
             if (sink.v) sink.v[slot] = inf;
             if (sink.vx) for (int i = 0; i < NX; i++) sink.vx[slot * NX + i] = inf;
+            if (VXX && sink.vxx) for (int i = 0; i < NV; i++) sink.vxx[slot * NV + i] = inf;
         }
     };
     // internal-time vector field.  time mode: dir * f_extended.  value mode: the same field divided
@@ -493,6 +578,7 @@ TrajStats solve_one(const Sys& sys, const pmp_opts_t& o, const R* y_f, R* y_end,
     const bool backward = r_val(dir) < 0;  // multiplying by dir = -1 is a sign flip, not a flop
     auto field = [&](const R* yy, R* k) {
         sys.rhs(yy, k);
+        if constexpr (VXX) sys.vxx_dot(yy, yy + NX + 2, yy + NB, k + NB);
         if (value_mode) {
             R vdot = k[IV];  // dv/dt = -l: dy/dv = (dy/dt) / (dv/dt)
             for (int i = 0; i < NS; i++) k[i] = k[i] / vdot;
@@ -548,8 +634,8 @@ TrajStats solve_one(const Sys& sys, const pmp_opts_t& o, const R* y_f, R* y_end,
                 if (r_isnan(yerr[q])) yerr[q] = inf;  // integrate.py: nan error -> inf
             }
             // per-leaf NaN guard of the scale (leaves: x, t, v, vx)
-            auto leaf_of = [&](int q) { return q < NX ? 0 : (q == IT ? 1 : (q == IV ? 2 : 3)); };
-            bool leaf_nan[4] = {false, false, false, false};
+            auto leaf_of = [&](int q) { return q < NX ? 0 : (q == IT ? 1 : (q == IV ? 2 : (q < NB ? 3 : 4))); };
+            bool leaf_nan[5] = {false, false, false, false, false};
             for (int q = 0; q < NS; q++) leaf_nan[leaf_of(q)] = leaf_nan[leaf_of(q)] || r_isnan(y1[q]);
             R sumsq = R(0);
             // value mode: the missing solver's state was y=[x, lambda, t] (rrt_sampler.py:62), v is
@@ -602,6 +688,11 @@ TrajStats solve_one(const Sys& sys, const pmp_opts_t& o, const R* y_f, R* y_end,
         }
         if (st.result == 0 && o.event == PMP_EVENT_VALUE_GE && r_val(y[IV]) >= o.event_level)
             st.result = PMP_RESULT_EVENT;
+        if (VXX && st.result == 0 && o.event == PMP_EVENT_VXX_NORM) {  // np.linalg.norm(state.y['vxx']) > vxx_max_norm
+            double fro = 0;
+            for (int q = NB; q < NS; q++) fro += r_val(y[q]) * r_val(y[q]);
+            if (std::sqrt(fro) > o.event_level) st.result = PMP_RESULT_EVENT;
+        }
         if (keep && st.result == 0) {
             // a force-accepted step (at dtmin) whose scaled error is not finite, or a NaN state:
             // diffrax would idle (every later attempt rejected) until max_steps; we retire at once

@@ -92,3 +92,16 @@ def cuda_solve(problem, opts, y_np):
     out = pu.solve_batch_soa(problem, opts, y)
     torch.cuda.synchronize()
     return {k: v.cpu().numpy() for k, v in out.items()}
+
+
+def flatquad_terminal_vxx(n, seed=1, dtype=np.float64, asym=0.0):
+    """[14 + 36, n]: flatquad_terminal plus the terminal Hessian vxx = P_lqr on every trajectory
+    (levelsets.py:595-597), row 14 + 6i + j = vxx[i][j].  asym > 0 adds a seeded non-symmetric perturbation
+    (exercises the general 36-entry path)."""
+    y = flatquad_terminal(n, seed=seed, dtype=np.float64)
+    P = np.asarray(flatquad_P(), dtype=np.float64)
+    P = 0.5 * (P + P.T)
+    V = np.repeat(P.reshape(36, 1), n, axis=1)
+    if asym > 0:
+        V = V + asym * np.random.Generator(np.random.PCG64(seed + 7)).standard_normal((36, n))
+    return np.ascontiguousarray(np.concatenate([y, V], 0), dtype=dtype)

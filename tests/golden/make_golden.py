@@ -220,6 +220,33 @@ def gen_traj_flatquad(jnp, n=8):
     onp.savez(os.path.join(OUT, "traj_flatquad_f64.npz"), P=P, A=A, B=B, Q=Q, R=R, y0=y0, t_eval=t_eval, ys=ys)
 
 
+def gen_vxx_flatquad(jnp, n=192):
+    """f_extended with pontryagin_solver_vxx=True (pontryagin_utils.py:460-467): vxx_dot and the four
+    Jacobians of pmp_rhs THROUGH u_star_2d (args='debug' returns them), fp64."""
+    import pontryagin_utils as ref
+    torch.set_default_dtype(torch.float64)
+    pp = flatquad_ref(jnp)
+    _, f_extended = ref.define_backward_solver(pp, {"pontryagin_solver_vxx": True})
+    rng = onp.random.Generator(onp.random.PCG64(21))
+    xs, lams = flatquad_inputs(n, rng)
+    A = rng.standard_normal((n, 6, 6))
+    vxxs = onp.einsum("nij,nkj->nik", A, A) * 3.0 + 5.0 * onp.eye(6)[None]
+    vxxs[n // 2:] += 0.3 * rng.standard_normal((n - n // 2, 6, 6))  # not exactly symmetric, as after integration
+    out = {k: onp.zeros((n, 6, 6)) for k in ("vxx_dot", "fx", "flam", "gx", "glam")}
+    us = onp.zeros((n, 2))
+    for i in range(n):
+        st = {"x": torch.as_tensor(xs[i]), "t": 0, "v": torch.zeros(()), "vx": torch.as_tensor(lams[i]),
+              "vxx": torch.as_tensor(vxxs[i])}
+        sd, aux = f_extended(0.0, st, "debug")
+        out["vxx_dot"][i] = sd["vxx"].numpy()
+        for k in ("fx", "flam", "gx", "glam"):
+            out[k][i] = aux[k].numpy()
+        us[i] = aux["u_star"].numpy()
+    onp.savez(os.path.join(OUT, "vxx_flatquad_f64.npz"), x=xs, lam=lams, vxx=vxxs, u=us, **out)
+    sat = ((us <= 1e-9) | (us >= 117.72 - 1e-6))
+    print("vxx golden: both free", (~sat).all(1).mean(), "one clipped", (sat.sum(1) == 1).mean(), "corner", sat.all(1).mean())
+
+
 if __name__ == "__main__":
     jnp = install_shim()
     only = sys.argv[1:]
@@ -230,3 +257,5 @@ if __name__ == "__main__":
         gen_rhs_2d(jnp, "lqr")
     if not only or "traj" in only:
         gen_traj_flatquad(jnp)
+    if not only or "vxx" in only:
+        gen_vxx_flatquad(jnp)

@@ -69,6 +69,34 @@ def test_state_rows_and_workspace():
     assert L.pmp_solve_launch_count(C.byref(prob), C.byref(o), 0) == 0
 
 
+def test_vxx_flag_rows_workspace_and_validation():
+    """PMP_FLAG_VXX: 36 more rows for flatquad, refused for the nx = 2 functors, for value-parameterised solves
+    and together with the literal u* form; the vxx event and the symmetric storage need the flag."""
+    L = _capi.lib()
+    prob, _ = c_problem("flatquad")
+    V, S, LIT = _capi.FLAG_VXX, _capi.FLAG_VXX_SYMMETRIC, _capi.FLAG_USTAR_LITERAL
+    assert L.pmp_state_rows_flags(C.byref(prob), 0) == 14 and L.pmp_state_rows_flags(C.byref(prob), V) == 50
+    for flags in (V, V | S):
+        o = _capi.make_opts(dtype=_capi.F64, flags=flags)
+        assert L.pmp_solve_workspace_bytes(C.byref(prob), C.byref(o), 100) == 256 + (13 + 36) * 100 * 8
+    orb, _ = c_problem("orbits")
+    assert L.pmp_state_rows_flags(C.byref(orb), V) == -2
+    assert L.pmp_solve_workspace_bytes(C.byref(orb), C.byref(_capi.make_opts(flags=V)), 8) == -2
+    assert b"flatquad" in L.pmp_last_error()
+    for kw, frag in ((dict(flags=S), b"needs PMP_FLAG_VXX"), (dict(flags=V | LIT), b"KKT"),
+                     (dict(flags=V, indep=_capi.INDEP_VALUE, dt0=0.1), b"time-parameterised"),
+                     (dict(event=_capi.EVENT_VXX_NORM), b"needs PMP_FLAG_VXX"), (dict(flags=8), b"unknown flags")):
+        o = _capi.make_opts(**kw)
+        assert L.pmp_solve_workspace_bytes(C.byref(prob), C.byref(o), 8) < 0, kw
+        assert frag in L.pmp_last_error(), (kw, L.pmp_last_error())
+    # dense output with the flag needs the sixth leaf
+    o = _capi.make_opts(flags=V, save_dense=1)
+    buf = (C.c_float * (50 * 8))()
+    d = _capi.Dense(*(C.addressof(buf),) * 5, None)
+    assert L.pmp_solve_batch_cuda(C.byref(prob), C.byref(o), 8, buf, buf, C.byref(d), None, None, None, None, 0, None) == -1
+    assert b"vxx leaf" in L.pmp_last_error()
+
+
 def test_argument_validation_and_error_strings():
     L = _capi.lib()
     prob, _ = c_problem("flatquad")

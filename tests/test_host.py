@@ -65,8 +65,9 @@ def test_to_c_problem_and_errors():
     with pytest.raises(NotImplementedError):
         systems.to_c_problem({"system_name": "pendulum", "nx": 2, "nu": 1, "U_interval": [-1, 1]})
     pp = systems.flatquad_problem_params()
-    with pytest.raises(NotImplementedError):
-        pu.define_backward_solver(pp, dict(systems.flatquad_algo_params(), pontryagin_solver_vxx=True))
+    pu.define_backward_solver(pp, dict(systems.flatquad_algo_params(), pontryagin_solver_vxx=True))  # flatquad: built
+    with pytest.raises(NotImplementedError):  # the Jacobians through u* exist for the flatquad functor only
+        pu.define_backward_solver(systems.orbits_problem_params(), {"pontryagin_solver_vxx": True})
     with pytest.raises(NotImplementedError):
         pu.u_star_2d(np.zeros(2), np.zeros(2), systems.orbits_problem_params())  # nu != 2, as the reference
     with pytest.raises(AssertionError):

@@ -301,6 +301,11 @@ def test_flop_constants_match_oracle():
     assert c["attempt_flops"] == flops.ATTEMPT_FLOPS[(_capi.SYS_LQR_STATEPENALTY, _capi.METHOD_RK4)]
     c = O.opcount(O.orbits_problem(), O.make_opts(dtype=O.F64), orbits_terminal(4)[:, 0])
     assert c["attempt_flops"] == flops.ATTEMPT_FLOPS[(_capi.SYS_ORBITS, _capi.METHOD_TSIT5)]
+    from common import flatquad_terminal_vxx
+    yv = flatquad_terminal_vxx(4)
+    for m, name, ad in ((O.TSIT5, _capi.METHOD_TSIT5, 1), (O.DOPRI5, _capi.METHOD_DOPRI5, 1), (O.RK4, _capi.METHOD_RK4, 0)):
+        c = O.opcount(O.flatquad_problem(), O.make_opts(method=m, adaptive=ad, dtype=O.F64, flags=O.FLAG_VXX), yv[:, 1])
+        assert c["rhs_flops"] == flops.RHS_FLOPS_VXX and c["attempt_flops"] == flops.ATTEMPT_FLOPS_VXX[name]
     # SURVEY.md 8(d) hand count: ~181 flop per RHS, ~2056 per Tsit5 attempt, within ~+-12 %
     assert abs(flops.RHS_FLOPS[0] / 181 - 1) < 0.15 and abs(flops.ATTEMPT_FLOPS[(0, 1)] / 2056 - 1) < 0.10
 
@@ -349,3 +354,66 @@ def test_value_mode_interpolation_oracle():
         ref = O.solve_batch(prob, O.make_opts(dtype=O.F64, indep=O.INDEP_VALUE, t1=float(vq[k]), dt0=1 / 64, rtol=1e-12,
                                               atol=1e-13, dtmin=0.0, dtmax=0.0, max_steps=20000), y[:, k:k + 1])["y_end"][:, 0]
         assert np.allclose(got[:, k], ref, rtol=1e-5, atol=1e-6)
+
+
+# ---- value-Hessian branch (pontryagin_solver_vxx, pontryagin_utils.py:460-467) ------------------------
+def test_vxx_rhs_matches_reference_golden():
+    """vxx_dot and the Jacobians (fx, flam, gx, glam) of pmp_rhs THROUGH u_star_2d against the reference's
+    own f_extended(..., 'debug') (tests/golden/make_golden.py::gen_vxx_flatquad): interior, edge and corner
+    active sets, symmetric and non-symmetric vxx."""
+    g = np.load(f"{GOLDEN}/vxx_flatquad_f64.npz")
+    p = O.flatquad_problem()
+    for i in range(g["x"].shape[0]):
+        fx, flam, gx, glam, vd = O.vxx_rhs(p, g["x"][i], g["lam"][i], g["vxx"][i])
+        for name, got in (("fx", fx), ("flam", flam), ("gx", gx), ("glam", glam), ("vxx_dot", vd)):
+            ref = g[name][i]
+            assert np.abs(got - ref).max() <= 1e-12 * (1 + np.abs(ref).max()), (i, name)
+
+
+def test_vxx_is_the_sensitivity_of_the_costate():
+    """Independent check of the whole Riccati propagation: along a characteristic V_xx(t) = d lambda(t) / d x(t).
+    Integrate neighbouring characteristics from x_f + d, lambda_f = P (x_f + d): the end-point differences must
+    satisfy d lambda_end = V_xx,end d x_end (trajectories that never touch the input constraints' kinks)."""
+    from common import flatquad_terminal_vxx
+    n, eps = 64, 1e-6
+    P = 0.5 * (flatquad_P() + flatquad_P().T)
+    y0 = flatquad_terminal_vxx(n)
+    opts = O.make_opts(method=O.TSIT5, dtype=O.F64, rtol=1e-11, atol=1e-11, t1=-1.0, max_steps=4096, flags=O.FLAG_VXX)
+    base = O.solve_batch(O.flatquad_problem(), opts, y0)
+    assert (base["result"] == 0).all()
+    Vend = base["y_end"][14:].T.reshape(n, 6, 6)
+    assert np.abs(Vend - Vend.transpose(0, 2, 1)).max() <= 1e-9 * np.abs(Vend).max()  # stays symmetric
+    rng = np.random.Generator(np.random.PCG64(5))
+    worst = []
+    for _ in range(3):
+        d = rng.standard_normal((6, n)); d /= np.linalg.norm(d, axis=0)
+        y1 = y0.copy()
+        y1[:6] += eps * d
+        y1[8:14] += eps * (P @ d)
+        pert = O.solve_batch(O.flatquad_problem(), opts, y1)
+        dx = (pert["y_end"][:6] - base["y_end"][:6]).T
+        dl = (pert["y_end"][8:14] - base["y_end"][8:14]).T
+        pred = np.einsum("nij,nj->ni", Vend, dx)
+        worst.append(np.linalg.norm(dl - pred, axis=1) / np.linalg.norm(dl, axis=1))
+    worst = np.max(worst, axis=0)
+    assert np.median(worst) <= 1e-4, np.median(worst)
+    assert np.mean(worst <= 1e-3) >= 0.9, np.sort(worst)[-8:]
+
+
+def test_vxx_changes_the_step_sequence_only_through_the_norm():
+    """The base leaves (x, v, vx) obey the same ODE with or without the vxx leaf; at a tight tolerance both
+    runs converge to the same end point, and the vxx event stops trajectories with result 1."""
+    from common import flatquad_terminal_vxx
+    y0 = flatquad_terminal_vxx(256)
+    o1 = O.make_opts(method=O.TSIT5, dtype=O.F64, rtol=1e-10, atol=1e-10, max_steps=4096, flags=O.FLAG_VXX)
+    o0 = O.make_opts(method=O.TSIT5, dtype=O.F64, rtol=1e-10, atol=1e-10, max_steps=4096)
+    a = O.solve_batch(O.flatquad_problem(), o1, y0)
+    b = O.solve_batch(O.flatquad_problem(), o0, y0[:14])
+    ok = (a["result"] == 0) & (b["result"] == 0)
+    assert ok.mean() > 0.9
+    assert np.abs(a["y_end"][:14, ok] - b["y_end"][:, ok]).max() <= 1e-6 * (1 + np.abs(b["y_end"][:, ok]).max())
+    oe = O.make_opts(method=O.TSIT5, dtype=O.F64, flags=O.FLAG_VXX, event=O.EVENT_VXX_NORM, event_level=345.0)
+    e = O.solve_batch(O.flatquad_problem(), oe, y0)
+    fro = np.linalg.norm(e["y_end"][14:], axis=0)
+    assert (e["result"] == 1).any() and (e["result"] == 0).any()
+    assert (fro[e["result"] == 1] > 345.0).all() and (fro[e["result"] == 0] <= 345.0).all()
