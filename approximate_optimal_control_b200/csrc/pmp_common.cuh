@@ -134,6 +134,7 @@ template <class R> struct SolveOpts {
     R rtol, atol, dtmin, dtmax, safety, factormin, factormax, inv_order;
     R event_level;
     int max_steps, adaptive, force_dtmin, event, use_dtmin, use_dtmax;
+    int refill_min;  // lanes of a warp that must be waiting before the retire + refill detour is taken
 };
 
 // Butcher tableau in the kernel's precision, used by the fp64 instantiations only: 64-bit immediates do

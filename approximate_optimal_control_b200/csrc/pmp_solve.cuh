@@ -24,6 +24,8 @@
 //   * The reference's 't' leaf (dt/dt = 1) is not integrated numerically: t = t_f + dir*(tau - T0).
 //     It still counts as one leaf of the RMS error norm (its own error is ~1e-9 of the tolerance).
 #pragma once
+#include <cstdlib>
+
 #include "pmp_common.cuh"
 #include "pmp_systems.cuh"
 #include "pmp_tableau.cuh"
@@ -32,6 +34,10 @@ namespace pmp {
 
 constexpr int kBlock = 128;  // threads per CTA
 constexpr int kChunk = 64;   // trajectory indices claimed per atomicAdd
+// lanes that must wait before a warp takes the retire + refill detour (measured on 2^20 flatquad trajectories:
+// fp32 1.41 ms at 1, 1.33 at 4, 1.38 at 8; fp64 4.09 / 4.03 at 3 / 4.27 at 8; vxx 5.49 / 4.90 at 6 / 5.11 at 12)
+constexpr int kRefillMin32 = 4, kRefillMin64 = 3;
+constexpr int kRefillMinVxx = 6;  // with the vxx leaf the detour is heavier: 72 more loads, 36 more stores
 
 // ---- value-Hessian branch (PMP_FLAG_VXX, pontryagin_utils.py:460-467) ---------------------------------
 // The state gains NV = nx*nx scalars (50 in all for flatquad): with seven stage derivatives that is 288
@@ -45,20 +51,76 @@ constexpr int kChunk = 64;   // trajectory indices claimed per atomicAdd
 // the symmetric storage (VXX = 2, VxxMap: 21 instead of 36 entries, 42 KB per CTA, five CTAs per SM) exists.
 template <class R, int VXX> struct BlockOf { static constexpr int value = VXX ? (sizeof(R) == 4 ? 64 : 32) : kBlock; };
 
-// stage-field evaluation for the VXX instantiation: base RHS + Jacobian coefficients first (the stage state
-// dies here), then the stage matrix Vs is formed in registers by load_v and vxx' goes to the shared-memory
-// column kv (stride BLK)
-template <class Sys, class R, int BLK, int VXX, class LoadV>
-__device__ __forceinline__ void field_vxx(const typename Sys::Consts& sc, const R* y, R* k, R* Vs, R* kv, LoadV&& load_v) {
-    constexpr int NX = Sys::NX;
-    typename Sys::JacCoef jc;
-    R vd;
-    Sys::rhs_jac(sc, y, y + NX, k, vd, k + NX, jc);
-    k[2 * NX] = vd;
-    // compiler fences: without them nvcc forwards every value stored to the shared-memory columns to its later
-    // loads, i.e. tries to keep all (1 + stages) * NV entries in registers and spills them to local memory
+// Runtime-indexable Butcher tableau for the V_xx stage loop (kernel parameter bank; empty without VXX)
+template <class R, int VXX> struct VTab {
+    R a[7][7], b[7], e[7];
+    template <class TB> static VTab make() {
+        VTab t;
+        for (int i = 0; i < 7; i++) {
+            t.b[i] = i < TB::S ? R(TB::b(i)) : R(0);
+            t.e[i] = i < TB::S ? R(TB::berr(i)) : R(0);
+            for (int j = 0; j < 7; j++) t.a[i][j] = (i < TB::S && j < TB::S) ? R(TB::a(i, j)) : R(0);
+        }
+        return t;
+    }
+};
+template <class R> struct VTab<R, 0> {
+    template <class TB> static VTab make() { return VTab(); }
+};
+
+// a[i] for a runtime i with `a` in registers (select chain)
+template <class R, int S> __device__ __forceinline__ R pick(const R (&a)[S], int i) {
+    R r = a[0];
+#pragma unroll
+    for (int m = 1; m < S; m++) r = (i == m) ? a[m] : r;
+    return r;
+}
+
+// One V_xx stage on this thread's shared-memory column (entry e of [V | k1 .. kS] at sV[e * BLK]):
+//     Vs = V + sum_{j<i} (h a_ij) k_j,   k_{i+1} = vxx'(jc, Vs).
+// The stage index i is a RUNTIME value and the sum over j a runtime loop (coefficients from the parameter
+// bank): the integrator runs ONE copy of this code for all stages.  Fully unrolled, the seven-stage body was
+// 6000 instructions (96 KB) -- three times the instruction cache -- and ran 8x slower than this.
+// last (FSAL methods, i = S-1; warp-uniform): Vs is the candidate V_xx of the attempt; it is parked in the
+// column of k2 and the error partial sum_{j<i} (h e_j) k_j in the column of k3 (k2..k6 are dead once the last
+// stage matrix exists), so nothing of it has to stay in registers across the error estimate.
+template <class Sys, class R, int BLK, int VXX>
+__device__ __forceinline__ void vxx_stage(const typename Sys::Consts& sc, const typename Sys::JacCoef& jc, R* sV, int i,
+                                          bool last, R h, const VTab<R, VXX>& vt) {
+    using M = Math<R>;
+    constexpr int NV = VxxMap<Sys::NX, VXX>::NV;
+    // compiler fences: without them nvcc forwards values stored to the columns to their later loads, i.e. tries
+    // to keep all (1 + stages) * NV entries in registers and spills them to local memory
     asm volatile("" ::: "memory");
-    load_v(Vs);
+    R Vs[NV], ep[NV];
+#pragma unroll
+    for (int q = 0; q < NV; q++) {
+        Vs[q] = sV[q * BLK];
+        ep[q] = R(0);
+    }
+    const R* col = sV + NV * BLK;
+#pragma unroll 1
+    for (int j = 0; j < i; j++, col += NV * BLK) {
+        const R ha = h * vt.a[i][j], hej = h * vt.e[j];
+        R kj[NV];
+#pragma unroll
+        for (int q = 0; q < NV; q++) {
+            kj[q] = col[q * BLK];
+            Vs[q] = M::fma(ha, kj[q], Vs[q]);
+        }
+        if (last) {
+#pragma unroll
+            for (int q = 0; q < NV; q++) ep[q] = M::fma(hej, kj[q], ep[q]);
+        }
+    }
+    if (last) {
+#pragma unroll
+        for (int q = 0; q < NV; q++) {
+            sV[(NV * 2 + q) * BLK] = Vs[q];
+            sV[(NV * 3 + q) * BLK] = ep[q];
+        }
+    }
+    R* kv = sV + NV * (1 + i) * BLK;
     Sys::template vxx_dot<VXX>(sc, jc, Vs, [&](int q, R val) { kv[q * BLK] = val; });
     asm volatile("" ::: "memory");
 }
@@ -227,7 +289,8 @@ __device__ __forceinline__ void write_group_s(const DensePtrs<R>& d, const R* sS
 // ---- the integrator -----------------------------------------------------------------------------
 template <class Sys, class R, int METHOD, bool DENSE, bool VALUE, bool ULIT, int MINB, int VXX = 0>
 __global__ void __launch_bounds__((BlockOf<R, VXX>::value), MINB)
-solve_kernel(const typename Sys::Consts sc, const SolveOpts<R> o, const SolveIO<R> io, const TabParams<R> tp) {
+solve_kernel(const typename Sys::Consts sc, const SolveOpts<R> o, const SolveIO<R> io, const TabParams<R> tp,
+             const VTab<R, VXX> vt) {
     using M = Math<R>;
     using TB = Tab<METHOD>;
     constexpr int NX = Sys::NX, ND = 2 * NX + 1, NS = 2 * NX + 2, S = TB::S;
@@ -294,9 +357,14 @@ solve_kernel(const typename Sys::Consts sc, const SolveOpts<R> o, const SolveIO<
 
     while (true) {
         // =============================== retire + refill =========================================
+        // Retiring and refilling is a divergent detour of a few hundred instructions for the whole warp, and with
+        // ~25 attempts per trajectory some lane of a warp finishes in almost every iteration.  So finished lanes
+        // are parked (they run the next attempts as dummies, `live` is false) until at least o.refill_min lanes
+        // wait, or nothing else is left to do: fewer, fuller detours for a few percent of idle lanes.
         const bool fin = has_work && finished;
         unsigned want = __ballot_sync(FULL, fin || !has_work);
-        if (want) {
+        const bool any_live = __any_sync(FULL, has_work && !finished);
+        if (want && (__popc(want) >= o.refill_min || !any_live || exhausted)) {
             if (fin) {
                 // endpoint = last accepted state (== ys[num_accepted_steps], levelsets.py:1215)
                 const R clock = tprev * o.dir;  // t (time mode) or v (value mode)
@@ -448,30 +516,103 @@ solve_kernel(const typename Sys::Consts sc, const SolveOpts<R> o, const SolveIO<
         }
 
         // =============================== one step attempt ========================================
-        const R dt = tnext - tprev;
+        // parked / idle lanes run the attempt as dummies: give them an ordinary step length (their own interval
+        // is empty, and a zero step sends the fp64 pow() and divisions of the controller down their slow paths)
+        const R dt = live ? tnext - tprev : o.dt0;
         const R h = dt * o.dir;
-        // VXX: the candidate V_xx of this attempt.  FSAL methods: it is the last stage matrix; it goes to the
-        // column of k2 and the error partial sum_{j<S-1} (h e_j) k_j to the column of k3 while the last stage is
-        // formed (k2..k6 of an entry are dead once its last-stage value exists), so no register holds it across
-        // the last RHS.  Others (RK4): registers.
-        R V1[(VXX && !TB::FSAL) ? NV : 1];
-        if (!TB::FSAL) {
-            if constexpr (VXX) {
-                R Vs[NV];
-                field_vxx<Sys, R, BLK, VXX>(sc, y, k[0], Vs, sV + NV * BLK, [&](R* W) {
-#pragma unroll
-                    for (int q = 0; q < NV; q++) W[q] = sV[q * BLK];
-                });
-            } else {
-                field<Sys, R, VALUE, ULIT ? 1 : 2>(sc, y, k[0]);
-            }
-        }
         R y1[ND];
+        R V1[(VXX && !TB::FSAL) ? NV : 1];  // VXX, non-FSAL methods (RK4): the candidate V_xx (FSAL: see vxx_stage)
+        R sumsq_base = R(0);                // VXX: base leaves' share of the squared error norm
+        if constexpr (VXX != 0) {
+            // ---- phase A: every base stage, in registers, exactly as without the vxx leaf; one JacPrim per stage
+            R ps[S], pc[S], pm[S], pu[S], px[S];
+            int acts = 0;
+            auto base_stage = [&](int i, const R* yy) {
+                typename Sys::JacPrim p;
+                R vd;
+                Sys::rhs_prim(sc, yy, yy + NX, k[i], vd, k[i] + NX, p);
+                k[i][AUX] = vd;
+                ps[i] = p.s; pc[i] = p.co; pm[i] = p.Sm; pu[i] = p.hxu2; px[i] = p.hxx22;
+                acts |= p.act << (2 * i);
+            };
+            if (!TB::FSAL) base_stage(0, y);
+#pragma unroll
+            for (int i = 1; i < S; i++) {
+                R ys[ND], ha[S];
+                const bool last_fsal = TB::FSAL && i == S - 1;
+#pragma unroll
+                for (int j = 0; j < i; j++) ha[j] = h * tp.template a<TB>(i, j);
+#pragma unroll
+                for (int q = 0; q < ND; q++) {
+                    if (q == AUX && !last_fsal) { ys[q] = y[q]; continue; }
+                    R acc = y[q];
+#pragma unroll
+                    for (int j = 0; j < i; j++)
+                        if (TB::a(i, j) != 0.0) acc = M::fma(ha[j], k[j][q], acc);
+                    ys[q] = acc;
+                }
+                base_stage(i, ys);
+                if (last_fsal) {
+#pragma unroll
+                    for (int q = 0; q < ND; q++) y1[q] = ys[q];
+                }
+            }
+            if (!TB::FSAL) {
+#pragma unroll
+                for (int q = 0; q < ND; q++) {
+                    R acc = y[q];
+#pragma unroll
+                    for (int j = 0; j < S; j++)
+                        if (TB::b(j) != 0.0) acc = M::fma(h * tp.template b<TB>(j), k[j][q], acc);
+                    y1[q] = acc;
+                }
+            }
+            if (TB::EMBEDDED) {  // the base leaves' error terms now, so that k2..k6 are dead during phase B
+                R sumsq_odd = R(0);
+#pragma unroll
+                for (int q = 0; q < ND; q++) {
+                    R e = (h * tp.template e<TB>(0)) * k[0][q];
+#pragma unroll
+                    for (int j = 1; j < S; j++)
+                        if (TB::berr(j) != 0.0) e = M::fma(h * tp.template e<TB>(j), k[j][q], e);
+                    const R scale = M::fma(o.rtol, M::max(M::abs(y[q]), M::abs(y1[q])), o.atol);
+                    const R ratio = M::ctl_div(e, scale);
+                    if (q & 1) sumsq_odd = M::fma(ratio, ratio, sumsq_odd);
+                    else sumsq_base = M::fma(ratio, ratio, sumsq_base);
+                }
+                sumsq_base += sumsq_odd;
+            }
+            // ---- phase B: the V_xx stages, a RUNTIME loop over one copy of the stage code (see vxx_stage)
+            auto coef_of = [&](int i, typename Sys::JacCoef& jc) {
+                typename Sys::JacPrim p;
+                p.s = pick<R, S>(ps, i); p.co = pick<R, S>(pc, i); p.Sm = pick<R, S>(pm, i);
+                p.hxu2 = pick<R, S>(pu, i); p.hxx22 = pick<R, S>(px, i);
+                p.act = (acts >> (2 * i)) & 3;
+                Sys::jac_from_prim(sc, p, jc);
+            };
+#pragma unroll 1
+            for (int i = (TB::FSAL ? 1 : 0); i < S; i++) {
+                typename Sys::JacCoef jc;
+                coef_of(i, jc);
+                vxx_stage<Sys, R, BLK, VXX>(sc, jc, sV, i, TB::FSAL && i == S - 1, h, vt);
+            }
+            if (!TB::FSAL) {
+#pragma unroll
+                for (int q = 0; q < NV; q++) V1[q] = sV[q * BLK];
+                const R* col = sV + NV * BLK;
+#pragma unroll 1
+                for (int j = 0; j < S; j++, col += NV * BLK) {
+                    const R hb = h * vt.b[j];
+#pragma unroll
+                    for (int q = 0; q < NV; q++) V1[q] = M::fma(hb, col[q * BLK], V1[q]);
+                }
+            }
+        } else {
+        if (!TB::FSAL) field<Sys, R, VALUE, ULIT ? 1 : 2>(sc, y, k[0]);
 #pragma unroll
         for (int i = 1; i < S; i++) {
             R ys[ND];
             const bool last_fsal = TB::FSAL && i == S - 1;
-#pragma unroll
             // ys = y + sum_j (h a_ij) k_j : i scalar products, then i FMAs per component
             R ha[S];
 #pragma unroll
@@ -486,31 +627,7 @@ solve_kernel(const typename Sys::Consts sc, const SolveOpts<R> o, const SolveIO<
                     if (TB::a(i, j) != 0.0) acc = M::fma(ha[j], k[j][q], acc);
                 ys[q] = acc;
             }
-            if constexpr (VXX) {
-                R Vs[NV];
-                field_vxx<Sys, R, BLK, VXX>(sc, ys, k[i], Vs, sV + NV * (1 + i) * BLK, [&](R* W) {
-                    R hev[S];
-#pragma unroll
-                    for (int j = 0; j < S; j++) hev[j] = h * tp.template e<TB>(j);
-#pragma unroll
-                    for (int q = 0; q < NV; q++) {
-                        R acc = sV[q * BLK], ep = R(0);
-#pragma unroll
-                        for (int j = 0; j < i; j++) {
-                            const R kj = sV[(NV * (1 + j) + q) * BLK];
-                            if (TB::a(i, j) != 0.0) acc = M::fma(ha[j], kj, acc);
-                            if (last_fsal && TB::berr(j) != 0.0) ep = M::fma(hev[j], kj, ep);
-                        }
-                        W[q] = acc;
-                        if (last_fsal) {
-                            sV[(NV * 2 + q) * BLK] = acc;
-                            sV[(NV * 3 + q) * BLK] = ep;
-                        }
-                    }
-                });
-            } else {
-                field<Sys, R, VALUE, ULIT ? 1 : 2>(sc, ys, k[i]);
-            }
+            field<Sys, R, VALUE, ULIT ? 1 : 2>(sc, ys, k[i]);
             if (last_fsal) {
 #pragma unroll
                 for (int q = 0; q < ND; q++) y1[q] = ys[q];
@@ -528,16 +645,7 @@ solve_kernel(const typename Sys::Consts sc, const SolveOpts<R> o, const SolveIO<
                     if (TB::b(j) != 0.0) acc = M::fma(hb[j], k[j][q], acc);
                 y1[q] = acc;
             }
-            if constexpr (VXX) {
-#pragma unroll
-                for (int q = 0; q < NV; q++) {
-                    R acc = sV[q * BLK];
-#pragma unroll
-                    for (int j = 0; j < S; j++)
-                        if (TB::b(j) != 0.0) acc = M::fma(hb[j], sV[(NV * (1 + j) + q) * BLK], acc);
-                    V1[q] = acc;
-                }
-            }
+        }
         }
 
         // ---- error estimate + I-controller (diffrax PIDController, pcoeff=dcoeff=0) --------------
@@ -547,12 +655,12 @@ solve_kernel(const typename Sys::Consts sc, const SolveOpts<R> o, const SolveIO<
         bool step_nonfinite = false;
         R next_t0, next_t1;
         if (TB::EMBEDDED && o.adaptive) {
-            R sumsq = R(0);
+            R sumsq = sumsq_base;
             R he[S];
 #pragma unroll
             for (int j = 0; j < S; j++) he[j] = h * tp.template e<TB>(j);
 #pragma unroll
-            for (int q = 0; q < ND; q++) {
+            for (int q = 0; q < (VXX ? 0 : ND); q++) {
                 R e = he[0] * k[0][q];
 #pragma unroll
                 for (int j = 1; j < S; j++)
@@ -562,15 +670,17 @@ solve_kernel(const typename Sys::Consts sc, const SolveOpts<R> o, const SolveIO<
                 const R ratio = M::ctl_div(e, scale);
                 sumsq = M::fma(ratio, ratio, sumsq);
             }
-            if constexpr (VXX) {  // fifth leaf of the norm (embedded methods are FSAL: see V1 above)
+            if constexpr (VXX) {  // fifth leaf of the norm (embedded methods are FSAL: see vxx_stage)
                 static_assert(!VXX || !TB::EMBEDDED || (TB::FSAL && S >= 4), "column reuse needs an FSAL method");
+                R part[4] = {R(0), R(0), R(0), R(0)};  // four partial sums: a single chain is latency bound
 #pragma unroll
                 for (int q = 0; q < NV; q++) {
                     const R e = M::fma(he[S - 1], sV[(NV * S + q) * BLK], sV[(NV * 3 + q) * BLK]);
                     const R scale = M::fma(o.rtol, M::max(M::abs(sV[q * BLK]), M::abs(sV[(NV * 2 + q) * BLK])), o.atol);
                     const R ratio = M::ctl_div(e, scale);
-                    sumsq = M::fma(MP::offdiag(q) ? ratio + ratio : ratio, ratio, sumsq);
+                    part[q & 3] = M::fma(MP::offdiag(q) ? ratio + ratio : ratio, ratio, part[q & 3]);
                 }
+                sumsq += (part[0] + part[1]) + (part[2] + part[3]);
             }
             // integrate.py maps a NaN error estimate to +inf (=> reject, shrink by factormin); a NaN
             // in any component makes the whole sum NaN, so one test on the sum is equivalent
@@ -615,14 +725,15 @@ solve_kernel(const typename Sys::Consts sc, const SolveOpts<R> o, const SolveIO<
                     if (TB::FSAL) k[0][q] = k[S - 1][q];
                 }
                 if constexpr (VXX) {
-                    R n2 = R(0);
+                    R np[4] = {R(0), R(0), R(0), R(0)};
 #pragma unroll
                     for (int q = 0; q < NV; q++) {
                         const R v1 = TB::FSAL ? sV[(NV * 2 + q) * BLK] : V1[q];
                         sV[q * BLK] = v1;
-                        n2 = M::fma(MP::offdiag(q) ? v1 + v1 : v1, v1, n2);
+                        np[q & 3] = M::fma(MP::offdiag(q) ? v1 + v1 : v1, v1, np[q & 3]);
                         if (TB::FSAL) sV[(NV + q) * BLK] = sV[(NV * S + q) * BLK];
                     }
+                    const R n2 = (np[0] + np[1]) + (np[2] + np[3]);
                     vnorm2 = n2;
                     if (!(TB::EMBEDDED)) bad = bad || (n2 != n2);
                     new_node = DENSE && nacc < S1;
@@ -666,6 +777,10 @@ template <class R, class TB> inline SolveOpts<R> make_solve_opts(const pmp_opts_
     s.inv_order = R(1.0 / order);
     s.event_level = R(o.event_level);
     s.max_steps = o.max_steps; s.adaptive = o.adaptive; s.force_dtmin = o.force_dtmin; s.event = o.event;
+    s.refill_min = (o.flags & PMP_FLAG_VXX) ? kRefillMinVxx : (sizeof(R) == 4 ? kRefillMin32 : kRefillMin64);
+    if (const char* e = getenv("B200PMP_REFILL_MIN")) s.refill_min = atoi(e);  // tuning knob, 1 = retire at once
+    if (s.refill_min < 1) s.refill_min = 1;
+    if (s.refill_min > 32) s.refill_min = 32;
     return s;
 }
 
@@ -695,6 +810,10 @@ int launch_one(const pmp_problem_t& p, const pmp_opts_t& o, long long n, const v
         e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return (int)e;
     }
+    if (VXX) {  // shared memory bounds the residency of the vxx kernels: take the largest carve-out
+        e = cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxShared);
+        if (e != cudaSuccess) return (int)e;
+    }
     e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, BLK, smem);
     if (e != cudaSuccess) return (int)e;
     if (occ < 1) occ = 1;
@@ -722,7 +841,7 @@ int launch_one(const pmp_problem_t& p, const pmp_opts_t& o, long long n, const v
         reset_counter_kernel<<<1, 1, 0, st>>>(io.counter);
     }
     const SolveOpts<R> so = make_solve_opts<R, TB>(o, TB::ORDER);
-    kern<<<grid, BLK, smem, st>>>(sc, so, io, TabParams<R>::template make<TB>());
+    kern<<<grid, BLK, smem, st>>>(sc, so, io, TabParams<R>::template make<TB>(), VTab<R, VXX>::template make<TB>());
     return (int)cudaGetLastError();
 }
 
@@ -733,9 +852,10 @@ int launch_solve_vxx(const pmp_problem_t& p, const pmp_opts_t& o, long long n, c
     const bool dn = o.save_dense != 0, sym = (o.flags & PMP_FLAG_VXX_SYMMETRIC) != 0;
 #define PMP_GOV(R, METHOD)                                                                                          \
     do {                                                                                                            \
-        if (dn && sym) return launch_one<SysT<R>, R, METHOD, true, false, false, 1, 2>(p, o, n, y_f, y_end, dense, a, s, r, ws, st);  \
+        /* symmetric fp32: 42 KB per CTA lets five CTAs share an SM if they stay within 204 registers */            \
+        if (dn && sym) return launch_one<SysT<R>, R, METHOD, true, false, false, (sizeof(R) == 4 ? 5 : 1), 2>(p, o, n, y_f, y_end, dense, a, s, r, ws, st);  \
         if (dn) return launch_one<SysT<R>, R, METHOD, true, false, false, 1, 1>(p, o, n, y_f, y_end, dense, a, s, r, ws, st);         \
-        if (sym) return launch_one<SysT<R>, R, METHOD, false, false, false, 1, 2>(p, o, n, y_f, y_end, dense, a, s, r, ws, st);       \
+        if (sym) return launch_one<SysT<R>, R, METHOD, false, false, false, (sizeof(R) == 4 ? 5 : 1), 2>(p, o, n, y_f, y_end, dense, a, s, r, ws, st);       \
         return launch_one<SysT<R>, R, METHOD, false, false, false, 1, 1>(p, o, n, y_f, y_end, dense, a, s, r, ws, st);                \
     } while (0)
 #define PMP_BY_METHODV(R)                                              \

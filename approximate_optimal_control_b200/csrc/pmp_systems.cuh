@@ -251,9 +251,16 @@ template <class R> struct Flatquad {
         R sg[3], dl[3];
     };
 
-    // rhs<2> (KKT-form u*) that also reports the Jacobian coefficients
-    static __device__ __forceinline__ void rhs_jac(const Consts& c, const R* x, const R* lam, R* xd, R& vd, R* ld,
-                                                   JacCoef& j) {
+    // What the Jacobian coefficients depend on, 5 reals + the active set of u*: the integrator evaluates all
+    // base stages first (registers) and keeps one JacPrim per stage for the V_xx stage loop that follows.
+    struct JacPrim {
+        R s, co, Sm, hxu2, hxx22;  // sin, cos, (u0+u1)/m, H_xu[2][.] = dH_u/dPhi, H_xx[2][2] at fixed u
+        int act;                   // 0 interior, 1 / 2 edge with u0 / u1 moving freely, 3 corner
+    };
+
+    // rhs<2> (KKT-form u*) that also reports the Jacobian primitives
+    static __device__ __forceinline__ void rhs_prim(const Consts& c, const R* x, const R* lam, R* xd, R& vd, R* ld,
+                                                    JacPrim& p) {
         using M = Math<R>;
         R s, co;
         M::sincos(x[2], &s, &co);
@@ -284,11 +291,7 @@ template <class R> struct Flatquad {
         u0 = outside ? bx : u0;
         u1 = outside ? by : u1;
         const bool free_edge = axis1 ? (by > c.lo1 && by < c.hi1) : (bx > c.lo0 && bx < c.hi0);
-        // d(u0+u1)/dz = MS dbase_z, d(u1-u0)/dz = MD dbase_z for z = Phi, lam3, lam4 (dH_u[0] = dH_u[1] = dbase);
-        // z = lam5 (dH_u = -+ r/I): S3, D3
-        const R ek = free_edge ? c.kN : R(0), ekr = free_edge ? c.kN_rI : R(0);
-        const R MS = outside ? ek : c.jMS, MD = outside ? (axis1 ? ek : -ek) : R(0);
-        const R S3 = outside ? (axis1 ? ekr : -ekr) : R(0), D3 = outside ? ekr : c.jD3;
+        p.act = outside ? (free_edge ? (axis1 ? 2 : 1) : 3) : 0;
 
         const R Sm = (u0 + u1) * c.inv_m;
         const R ax = -(s * Sm);
@@ -311,10 +314,22 @@ template <class R> struct Flatquad {
         ld[3] = -M::fma(c.two_qvel, x[3], lam[0]);
         ld[4] = -M::fma(c.two_qvel, x[4], lam[1]);
         ld[5] = -M::fma(c.two_qom, x[5], lam[2]);
+        p.s = s; p.co = co; p.Sm = Sm;
+        p.hxu2 = M::fma(c.two_g, s, -lcs) * c.inv_m;
+        p.hxx22 = M::fma(co, M::fma(c.two_g, Sm, c.two_qang), -(Sm * M::fma(lam[4], co, -(lam[3] * s))));
+    }
 
-        // dbase_z: z = Phi equals H_xu[2] (symmetry of the Hessian of H), lam3, lam4
+    static __device__ __forceinline__ void jac_from_prim(const Consts& c, const JacPrim& p, JacCoef& j) {
+        using M = Math<R>;
+        // d(u0+u1)/dz = MS dbase_z, d(u1-u0)/dz = MD dbase_z for z = Phi, lam3, lam4 (dH_u[0] = dH_u[1] = dbase);
+        // z = lam5 (dH_u = -+ r/I): S3, D3
+        const bool edge = p.act == 1 || p.act == 2, axis1 = p.act == 2;
+        const R ek = edge ? c.kN : R(0), ekr = edge ? c.kN_rI : R(0);
+        const R MS = p.act == 0 ? c.jMS : ek, MD = axis1 ? ek : -ek;
+        const R S3 = axis1 ? ekr : -ekr, D3 = p.act == 0 ? c.jD3 : ekr;
+        const R s = p.s, co = p.co, Sm = p.Sm, hxu2 = p.hxu2;
+        // dbase_z: z = Phi equals H_xu[2] (symmetry of the Hessian of H), lam3: -s/m, lam4: c/m
         const R sm = s * c.inv_m, cm = co * c.inv_m;
-        const R hxu2 = M::fma(c.two_g, s, -lcs) * c.inv_m;
         const R sum0 = MS * hxu2, dif0 = MD * hxu2;
         j.al3 = -sm; j.al4 = cm;
         j.sg[0] = -(MS * sm); j.sg[1] = MS * cm; j.sg[2] = S3;
@@ -322,11 +337,17 @@ template <class R> struct Flatquad {
         j.f32 = -M::fma(co, Sm, sm * sum0);
         j.f42 = M::fma(cm, sum0, -(s * Sm));
         j.f52 = c.r_I * dif0;
-        const R hxx22 = M::fma(co, M::fma(c.two_g, Sm, c.two_qang), -(Sm * M::fma(lam[4], co, -(lam[3] * s))));
-        j.g22 = -M::fma(hxu2, sum0, hxx22);
+        j.g22 = -M::fma(hxu2, sum0, p.hxx22);
         j.l23 = M::fma(co, Sm, -(hxu2 * j.sg[0]));
         j.l24 = M::fma(s, Sm, -(hxu2 * j.sg[1]));
         j.l25 = -(hxu2 * j.sg[2]);
+    }
+
+    static __device__ __forceinline__ void rhs_jac(const Consts& c, const R* x, const R* lam, R* xd, R& vd, R* ld,
+                                                   JacCoef& j) {
+        JacPrim p;
+        rhs_prim(c, x, lam, xd, vd, ld, p);
+        jac_from_prim(c, p, j);
     }
 
     // vxx' for V stored as VxxMap<6, VXX> says (VXX = 2: upper triangle in, upper triangle out); every entry
