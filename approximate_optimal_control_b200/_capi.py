@@ -11,7 +11,7 @@ import os
 from . import build as _build
 
 # ---- enums (include/b200pmp.h) ---------------------------------------------------------------------
-SYS_FLATQUAD, SYS_ORBITS, SYS_LQR_STATEPENALTY = 0, 1, 2
+SYS_FLATQUAD, SYS_ORBITS, SYS_LQR_STATEPENALTY, SYS_GENERATED = 0, 1, 2, 3
 METHOD_RK4, METHOD_TSIT5, METHOD_DOPRI5 = 0, 1, 2
 F32, F64 = 0, 1
 INDEP_TIME, INDEP_VALUE = 0, 1
@@ -28,6 +28,8 @@ METHODS = {"rk4": METHOD_RK4, "tsit5": METHOD_TSIT5, "dopri5": METHOD_DOPRI5}
 class Problem(C.Structure):
     _fields_ = [("system_id", C.c_int32), ("nx", C.c_int32), ("nu", C.c_int32),
                 ("u_lo", C.c_double * 2), ("u_hi", C.c_double * 2), ("params", C.c_double * 16)]
+    # python-side only: the library that serves this problem (None = libb200pmp.so; a codegen plug-in otherwise)
+    lib_path = None
 
 
 class Opts(C.Structure):
@@ -52,6 +54,7 @@ EXPORTS = ("pmp_abi_version", "pmp_last_error", "pmp_state_rows", "pmp_state_row
            "pmp_fma_peak_cuda")
 
 _lib = None
+_libs = {}
 
 
 class PmpError(RuntimeError):
@@ -66,6 +69,21 @@ def lib() -> C.CDLL:
     path = _build.LIB_PATH
     if not os.path.exists(path) or os.environ.get("B200PMP_REBUILD"):
         path = _build.build(force=bool(os.environ.get("B200PMP_REBUILD")))
+    _lib = load(path)
+    return _lib
+
+
+def lib_of(problem: "Problem") -> C.CDLL:
+    """The library that serves `problem`: libb200pmp.so for the compiled systems, the codegen plug-in that was
+    built for it otherwise (codegen.plugin_problem sets problem.lib_path)."""
+    path = getattr(problem, "lib_path", None)
+    return lib() if path is None else load(path)
+
+
+def load(path: str) -> C.CDLL:
+    """dlopen a library exporting the C ABI of include/b200pmp.h and declare its signatures."""
+    if path in _libs:
+        return _libs[path]
     try:
         L = C.CDLL(path)
     except OSError as e:  # pragma: no cover
@@ -93,13 +111,16 @@ def lib() -> C.CDLL:
                                     C.POINTER(C.c_double), C.c_void_p]
     if L.pmp_abi_version() != ABI_VERSION:
         raise PmpError(f"{path}: ABI version {L.pmp_abi_version()} != {ABI_VERSION}; rebuild")
-    _lib = L
+    _libs[path] = L
     return L
 
 
-def check(rc: int) -> int:
+def check(rc: int, L: C.CDLL = None) -> int:
     if rc < 0:
-        raise PmpError(f"libb200pmp error {rc}: {lib().pmp_last_error().decode()}")
+        msg = (L or lib()).pmp_last_error().decode()
+        if L is None and not msg:  # the failing call may have gone to a plug-in library
+            msg = "; ".join(m for m in (l.pmp_last_error().decode() for l in _libs.values()) if m)
+        raise PmpError(f"libb200pmp error {rc}: {msg}")
     return rc
 
 

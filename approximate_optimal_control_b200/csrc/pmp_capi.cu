@@ -7,6 +7,7 @@
 #include "../../include/b200pmp.h"
 
 namespace pmp {
+#ifndef PMP_PLUGIN
 int solve_flatquad(const pmp_problem_t&, const pmp_opts_t&, long long, const void*, void*, const pmp_dense_t*,
                    int32_t*, int32_t*, int32_t*, void*, cudaStream_t);
 int solve_flatquad_vxx(const pmp_problem_t&, const pmp_opts_t&, long long, const void*, void*, const pmp_dense_t*,
@@ -15,6 +16,13 @@ int solve_orbits(const pmp_problem_t&, const pmp_opts_t&, long long, const void*
                  int32_t*, int32_t*, int32_t*, void*, cudaStream_t);
 int solve_lqr(const pmp_problem_t&, const pmp_opts_t&, long long, const void*, void*, const pmp_dense_t*,
               int32_t*, int32_t*, int32_t*, void*, cudaStream_t);
+#endif
+#ifdef PMP_PLUGIN
+int generated_nx();
+int generated_nu();
+int solve_generated(const pmp_problem_t&, const pmp_opts_t&, long long, const void*, void*, const pmp_dense_t*,
+                    int32_t*, int32_t*, int32_t*, void*, cudaStream_t);
+#endif
 int eval_batch(int what, const pmp_problem_t& p, int dtype, long long n, const void* a, const void* b, void* out,
                cudaStream_t st);
 int fma_peak(int dtype, int variant, int iters, void* scratch, double* flops_out, cudaStream_t st);
@@ -33,14 +41,25 @@ int cuda_fail(int e) {
     return fail(PMP_ERR_CUDA, std::string("CUDA error: ") + cudaGetErrorString((cudaError_t)e));
 }
 
+#ifdef PMP_PLUGIN
+int expected_nx(int) { return pmp::generated_nx(); }
+int expected_nu(int) { return pmp::generated_nu(); }
+#else
 int expected_nx(int sys) { return sys == PMP_SYS_FLATQUAD ? 6 : 2; }
 int expected_nu(int sys) { return sys == PMP_SYS_FLATQUAD ? 2 : 1; }
+#endif
 
 int check_problem(const pmp_problem_t* p) {
     if (!p) return fail(PMP_ERR_BAD_ARG, "problem is NULL");
+#ifdef PMP_PLUGIN
+    if (p->system_id != PMP_SYS_GENERATED)
+        return fail(PMP_ERR_UNSUPPORTED, "this library is a codegen plug-in: it serves system_id PMP_SYS_GENERATED only");
+#else
     if (p->system_id < 0 || p->system_id > PMP_SYS_LQR_STATEPENALTY)
         return fail(PMP_ERR_UNSUPPORTED, "unknown system_id " + std::to_string(p->system_id) +
-                                             " (compiled systems: 0 flatquad, 1 orbits, 2 lqr_statepenalty)");
+                                             " (compiled systems: 0 flatquad, 1 orbits, 2 lqr_statepenalty; "
+                                             "PMP_SYS_GENERATED lives in the plug-in library codegen.py builds)");
+#endif
     if (p->nx != expected_nx(p->system_id) || p->nu != expected_nu(p->system_id))
         return fail(PMP_ERR_BAD_ARG, "nx/nu do not match system_id");
     for (int i = 0; i < p->nu; i++)
@@ -83,7 +102,7 @@ int check_opts(const pmp_opts_t* o) {
 }
 // options that need a particular system
 int check_pair(const pmp_problem_t* p, const pmp_opts_t* o) {
-    if ((o->flags & PMP_FLAG_VXX) && p->system_id != PMP_SYS_FLATQUAD)
+    if ((o->flags & PMP_FLAG_VXX) && p->system_id != PMP_SYS_FLATQUAD)  // (a plug-in never is)
         return fail(PMP_ERR_UNSUPPORTED, "PMP_FLAG_VXX: only the flatquad functor carries the Jacobians through u*");
     return 0;
 }
@@ -158,6 +177,9 @@ int pmp_solve_batch_cuda(const pmp_problem_t* p, const pmp_opts_t* o, int64_t n,
     if (ndev <= 0) return fail(PMP_ERR_NO_DEVICE, "no CUDA device: libb200pmp has no CPU fallback");
     cudaStream_t st = (cudaStream_t)cuda_stream;
     int rc = -1000;
+#ifdef PMP_PLUGIN
+    rc = pmp::solve_generated(*p, *o, n, y_f, y_end, dense, n_accepted, n_steps, result, workspace, st);
+#else
     switch (p->system_id) {
         case PMP_SYS_FLATQUAD:
             if (o->flags & PMP_FLAG_VXX) rc = pmp::solve_flatquad_vxx(*p, *o, n, y_f, y_end, dense, n_accepted, n_steps, result, workspace, st);
@@ -166,6 +188,7 @@ int pmp_solve_batch_cuda(const pmp_problem_t* p, const pmp_opts_t* o, int64_t n,
         case PMP_SYS_ORBITS: rc = pmp::solve_orbits(*p, *o, n, y_f, y_end, dense, n_accepted, n_steps, result, workspace, st); break;
         case PMP_SYS_LQR_STATEPENALTY: rc = pmp::solve_lqr(*p, *o, n, y_f, y_end, dense, n_accepted, n_steps, result, workspace, st); break;
     }
+#endif
     if (rc == -1000) return fail(PMP_ERR_UNSUPPORTED, "no kernel for this (system, dtype, method) combination");
     if (rc != 0) return cuda_fail(rc);
     return PMP_OK;

@@ -80,6 +80,7 @@ int eval_dispatch(int what, const pmp_problem_t& p, int dtype, long long n, cons
 
 int eval_batch(int what, const pmp_problem_t& p, int dtype, long long n, const void* a, const void* b, void* out,
                cudaStream_t st) {
+#ifndef PMP_PLUGIN
     if (what == 3) {  // f_extended with the vxx leaf: flatquad only (checked by the caller)
         if (n == 0) return 0;
         const unsigned grid = (unsigned)((n + 127) / 128);
@@ -87,12 +88,17 @@ int eval_batch(int what, const pmp_problem_t& p, int dtype, long long n, const v
         else rhs_vxx_kernel<Flatquad<double>, double><<<grid, 128, 0, st>>>(Flatquad<double>::make(p), (const double*)a, (double*)out, n);
         return (int)cudaGetLastError();
     }
+#endif
+#ifdef PMP_PLUGIN
+    return eval_dispatch<Generated>(what, p, dtype, n, a, b, out, st);
+#else
     switch (p.system_id) {
         case PMP_SYS_FLATQUAD: return eval_dispatch<Flatquad>(what, p, dtype, n, a, b, out, st);
         case PMP_SYS_ORBITS: return eval_dispatch<Orbits>(what, p, dtype, n, a, b, out, st);
         case PMP_SYS_LQR_STATEPENALTY: return eval_dispatch<LqrStatePenalty>(what, p, dtype, n, a, b, out, st);
     }
     return -1000;
+#endif
 }
 
 // ---- FMA peak probe: 16 independent dependent-FMA chains per thread, all in registers ------------

@@ -11,6 +11,10 @@
 // Vector layout used by the integrator: x[NX], lam[NX] and one scalar (v) are separate arguments.
 #pragma once
 #include "pmp_common.cuh"
+#ifdef PMP_PLUGIN
+#include "pmp_ustar2d.cuh"
+#include PMP_GENERATED_HEADER  // template <class R> struct pmp::Generated, PMP_GEN_MINB32 / 64 (codegen.py)
+#endif
 
 namespace pmp {
 

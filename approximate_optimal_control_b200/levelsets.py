@@ -53,7 +53,7 @@ def running_cost(ys: dict, problem_params: dict) -> torch.Tensor:
     y[nx + 2:] = vx.reshape(n, nx).t()  # (a 'vxx' leaf does not enter the running cost)
     dy = torch.empty_like(y)
     with torch.cuda.device(dev):
-        _capi.check(_capi.lib().pmp_rhs_batch_cuda(C.byref(problem), pu._code(dtype), n, y.data_ptr(), dy.data_ptr(),
+        _capi.check(_capi.lib_of(problem).pmp_rhs_batch_cuda(C.byref(problem), pu._code(dtype), n, y.data_ptr(), dy.data_ptr(),
                                                    pu._stream_ptr(dev)))
     l = -dy[nx + 1]
     return torch.where(torch.isfinite(l), l, torch.full_like(l, float("nan"))).reshape(shape)

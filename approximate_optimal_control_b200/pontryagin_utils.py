@@ -16,7 +16,9 @@ Differences, all forced by the move from "jax closure traced on CPU" to "compile
     torch CUDA tensors (numpy / CPU tensors are accepted and copied to the current CUDA device);
   * `jax.vmap(solve_backward)` is replaced by passing a leading batch axis: every function accepts
     either one state (the reference's shapes) or a batch;
-  * dynamics are selected by problem_params['system_name'] (compiled functors), not by tracing f, l;
+  * dynamics are compiled functors: the three systems of the reference's experiments are hand-written
+    (problem_params['system_name'] selects one); any other f, l -- or problem_params['codegen'] = True --
+    goes through codegen.py (sympy derivatives in place of jax autodiff, nvcc, a plug-in library);
   * there is no CPU fallback: without the library or a CUDA device the calls raise.
 """
 from __future__ import annotations
@@ -127,7 +129,7 @@ def solve_batch_soa(problem: _capi.Problem, opts: _capi.Opts, y_f: torch.Tensor,
     """Thin wrapper of pmp_solve_batch_cuda on struct-of-arrays CUDA tensors.  Asynchronous on the
     current stream.  `out` may carry preallocated outputs (keys y_end, n_accepted, n_steps, result,
     and ts, x, t, v, vx (, vxx) when opts.save_dense)."""
-    L = _capi.lib()
+    L = _capi.lib_of(problem)
     assert y_f.is_cuda and y_f.is_contiguous()
     ns, n = y_f.shape
     nx = problem.nx
@@ -204,9 +206,9 @@ def _interp(problem, opts, nx, sol: Solution, target, mode: int):
     tgt = q.reshape(-1).contiguous()
     out = torch.empty_like(y0)
     with torch.cuda.device(dev):
-        _capi.check(_capi.lib().pmp_interp_batch_cuda(C.byref(problem), C.byref(opts), N * M, y0.data_ptr(),
-                                                      t1.data_ptr(), tgt.data_ptr(), mode, out.data_ptr(),
-                                                      _stream_ptr(dev)))
+        _capi.check(_capi.lib_of(problem).pmp_interp_batch_cuda(C.byref(problem), C.byref(opts), N * M, y0.data_ptr(),
+                                                                t1.data_ptr(), tgt.data_ptr(), mode, out.data_ptr(),
+                                                                _stream_ptr(dev)))
     out = torch.where(inside.reshape(1, -1), out, torch.full_like(out, float("nan")))
     d = unpack_state(out, nx)
     shape = (N, M) if (batched and multi) else ((N,) if batched else ((M,) if multi else ()))
@@ -262,7 +264,7 @@ def define_backward_solver(problem_params: dict, algo_params: dict):
     nx = problem.nx
     # pontryagin_utils.py:425,460: also propagate the value Hessian ('vxx' leaf of the state)
     with_vxx = bool(algo_params.get("pontryagin_solver_vxx", False))
-    if with_vxx and problem.system_id != _capi.SYS_FLATQUAD:
+    if with_vxx and problem.system_id != _capi.SYS_FLATQUAD:  # (generated functors included)
         raise NotImplementedError("pontryagin_solver_vxx=True: only the flatquad functor carries the Jacobians "
                                   "of the PMP right hand side through u*")
 
@@ -273,7 +275,7 @@ def define_backward_solver(problem_params: dict, algo_params: dict):
         y, batched = pack_state(state, nx, dtype, dev, with_vxx)
         dy = torch.empty_like(y)
         with torch.cuda.device(dev):
-            _capi.check(_capi.lib().pmp_rhs_batch_cuda_flags(
+            _capi.check(_capi.lib_of(problem).pmp_rhs_batch_cuda_flags(
                 C.byref(problem), _code(dtype), _capi.FLAG_VXX if with_vxx else 0, y.shape[1], y.data_ptr(),
                 dy.data_ptr(), _stream_ptr(dev)))
         return unpack_state(dy, nx, batched)
@@ -318,9 +320,9 @@ def _ustar(x, costate, problem_params):
     ls = _as_tensor(costate, dtype, dev).reshape(-1, nx).t().contiguous()
     u = torch.empty((nu, xs.shape[1]), dtype=dtype, device=dev)
     with torch.cuda.device(dev):
-        _capi.check(_capi.lib().pmp_ustar_batch_cuda(C.byref(problem), _code(dtype), xs.shape[1],
-                                                     xs.data_ptr(), ls.data_ptr(), u.data_ptr(),
-                                                     _stream_ptr(dev)))
+        _capi.check(_capi.lib_of(problem).pmp_ustar_batch_cuda(C.byref(problem), _code(dtype), xs.shape[1],
+                                                               xs.data_ptr(), ls.data_ptr(), u.data_ptr(),
+                                                               _stream_ptr(dev)))
     u = u.t()
     return u if batched else u[0]
 

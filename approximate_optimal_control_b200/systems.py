@@ -37,10 +37,10 @@ def _is_sym(*args) -> bool:
 
 
 def _m(*args):
-    """math namespace matching the argument type (numpy or sympy)."""
+    """math namespace matching the argument type: numpy, or symnp (the jax.numpy subset on sympy objects)."""
     if _is_sym(*args):
-        import sympy
-        return sympy
+        from . import symnp
+        return symnp
     return np
 
 
@@ -195,10 +195,7 @@ def _lqr_fl(a=0.01, r_u=1.0):
         M = _m(x, u)
         x = np.asarray(x, dtype=object if M is not np else float)
         u = np.asarray(u, dtype=object if M is not np else float)
-        if M is np:
-            z1, z0 = np.maximum(0, x[..., 1] - 1), np.maximum(0, x[..., 0] - 1)
-        else:
-            z1, z0 = M.Max(0, x[..., 1] - 1), M.Max(0, x[..., 0] - 1)
+        z1, z0 = M.maximum(0, x[..., 1] - 1), M.maximum(0, x[..., 0] - 1)
         return x[..., 0] ** 2 + x[..., 1] ** 2 + r_u * u[..., 0] ** 2 + z1 ** 2 / a + z0 ** 2 / a
 
     return f, l
@@ -240,13 +237,17 @@ def lqr_statepenalty_algo_params() -> dict:
 # mapping to the C ABI
 # =====================================================================================================
 def to_c_problem(problem_params: dict) -> _capi.Problem:
-    """problem_params -> pmp_problem_t.  The dynamics are compiled functors selected by
-    problem_params['system_name']; arbitrary user-supplied f, l are not supported (no codegen yet)."""
+    """problem_params -> pmp_problem_t.  problem_params['system_name'] selects one of the hand-written functors;
+    any other system (or problem_params['codegen'] = True) is generated from problem_params['f'], ['l'] and
+    compiled into a plug-in library (codegen.py) -- cached, so only the first call pays for sympy + nvcc."""
     name = problem_params.get("system_name")
-    if name not in SYSTEM_IDS:
-        raise NotImplementedError(
-            f"system_name={name!r}: only the compiled systems {sorted(SYSTEM_IDS)} are available on the "
-            "CUDA path (plug-in dynamics need a compiled functor, see csrc/pmp_systems.cuh)")
+    if problem_params.get("codegen", name not in SYSTEM_IDS):
+        if problem_params.get("codegen") is False or "f" not in problem_params or "l" not in problem_params:
+            raise NotImplementedError(
+                f"system_name={name!r}: not one of the compiled systems {sorted(SYSTEM_IDS)}, and no f, l to "
+                "generate a functor from (or problem_params['codegen'] is False)")
+        from . import codegen
+        return codegen.plugin_problem(problem_params)
     sid = SYSTEM_IDS[name]
     nx, nu = int(problem_params["nx"]), int(problem_params["nu"])
     p = _capi.Problem(system_id=sid, nx=nx, nu=nu)

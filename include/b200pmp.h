@@ -48,7 +48,12 @@ extern "C" {
 enum {
     PMP_SYS_FLATQUAD = 0,         /* flatquad_landing_experiment.py:269-365   nx=6 nu=2 */
     PMP_SYS_ORBITS = 1,           /* experiment_orbits.py:24-40,83-104        nx=2 nu=1 */
-    PMP_SYS_LQR_STATEPENALTY = 2  /* experiment_lqr_statepenalty.py:23-38     nx=2 nu=1 */
+    PMP_SYS_LQR_STATEPENALTY = 2, /* experiment_lqr_statepenalty.py:23-38     nx=2 nu=1 */
+    /* plug-in dynamics: a functor generated from the user's problem_params['f'], ['l'] (sympy derivatives in
+     * place of jax autodiff, pontryagin_utils.py:35-38,438-439) and compiled, with the same kernels, into a
+     * library of its own that exports this same ABI (approximate_optimal_control_b200/codegen.py).  Only that
+     * library accepts this id; nx <= 16, nu in {1, 2}; params[] unused (constants are baked into the code). */
+    PMP_SYS_GENERATED = 3
 };
 
 /* integrators */
