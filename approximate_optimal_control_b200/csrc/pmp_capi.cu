@@ -25,6 +25,9 @@ int solve_generated(const pmp_problem_t&, const pmp_opts_t&, long long, const vo
 #endif
 int eval_batch(int what, const pmp_problem_t& p, int dtype, long long n, const void* a, const void* b, void* out,
                cudaStream_t st);
+int forward_batch(const pmp_problem_t& p, const pmp_opts_t& o, long long n, const void* x0, const double* P,
+                  const double* x_eq, void* z_end, void* ts, void* xs, void* cost, int32_t* a, int32_t* s, int32_t* r,
+                  cudaStream_t st);
 int fma_peak(int dtype, int variant, int iters, void* scratch, double* flops_out, cudaStream_t st);
 int interp_batch(const pmp_problem_t& p, const pmp_opts_t& o, long long nq, const void* y0, const void* t1,
                  const void* target, void* y_out, int mode, cudaStream_t st);
@@ -73,7 +76,7 @@ int check_opts(const pmp_opts_t* o) {
     if (o->dtype != PMP_F32 && o->dtype != PMP_F64) return fail(PMP_ERR_BAD_ARG, "dtype must be 0 (f32) or 1 (f64)");
     if (o->indep != PMP_INDEP_TIME && o->indep != PMP_INDEP_VALUE) return fail(PMP_ERR_BAD_ARG, "bad indep");
     if (o->max_steps < 1) return fail(PMP_ERR_BAD_ARG, "max_steps must be >= 1");
-    if (o->event < PMP_EVENT_NONE || o->event > PMP_EVENT_VXX_NORM) return fail(PMP_ERR_UNSUPPORTED, "unknown event");
+    if (o->event < PMP_EVENT_NONE || o->event > PMP_EVENT_LQR_VALUE_LE) return fail(PMP_ERR_UNSUPPORTED, "unknown event");
     if (o->event == PMP_EVENT_VXX_NORM && !(o->flags & PMP_FLAG_VXX))
         return fail(PMP_ERR_BAD_ARG, "PMP_EVENT_VXX_NORM needs PMP_FLAG_VXX");
     if (o->adaptive && o->method == PMP_METHOD_RK4)
@@ -102,6 +105,8 @@ int check_opts(const pmp_opts_t* o) {
 }
 // options that need a particular system
 int check_pair(const pmp_problem_t* p, const pmp_opts_t* o) {
+    if (o->event == PMP_EVENT_LQR_VALUE_LE)
+        return fail(PMP_ERR_BAD_ARG, "PMP_EVENT_LQR_VALUE_LE belongs to pmp_forward_batch_cuda (the backward solve has no P)");
     if ((o->flags & PMP_FLAG_VXX) && p->system_id != PMP_SYS_FLATQUAD)  // (a plug-in never is)
         return fail(PMP_ERR_UNSUPPORTED, "PMP_FLAG_VXX: only the flatquad functor carries the Jacobians through u*");
     return 0;
@@ -229,6 +234,28 @@ int pmp_ustar_batch_cuda(const pmp_problem_t* p, int32_t dtype, int64_t n, const
     if (n == 0) return PMP_OK;
     if (pmp_device_count() <= 0) return fail(PMP_ERR_NO_DEVICE, "no CUDA device: libb200pmp has no CPU fallback");
     int rc = pmp::eval_batch(1, *p, dtype, n, x, lam, u, (cudaStream_t)cuda_stream);
+    return rc ? cuda_fail(rc) : PMP_OK;
+}
+
+int pmp_forward_batch_cuda(const pmp_problem_t* p, const pmp_opts_t* o, int64_t n, const void* x0, const double* P,
+                           const double* x_eq, void* z_end, void* dense_ts, void* dense_x, void* dense_cost,
+                           int32_t* n_accepted, int32_t* n_steps, int32_t* result, void* cuda_stream) {
+    if (int e = check_problem(p)) return e;
+    if (int e = check_opts(o)) return e;
+    if (o->indep != PMP_INDEP_TIME || o->flags != 0) return fail(PMP_ERR_BAD_ARG, "forward simulation: indep must be TIME, flags 0");
+    if (o->event != PMP_EVENT_NONE && o->event != PMP_EVENT_LQR_VALUE_LE)
+        return fail(PMP_ERR_BAD_ARG, "forward simulation: event must be NONE or PMP_EVENT_LQR_VALUE_LE");
+    if (!(o->t0 < o->t1)) return fail(PMP_ERR_BAD_ARG, "forward simulation: need t0 < t1");
+    if (n < 0) return fail(PMP_ERR_BAD_ARG, "n < 0");
+    if (n == 0) return PMP_OK;
+    if (!x0 || !P || !z_end) return fail(PMP_ERR_BAD_ARG, "x0 / P / z_end is NULL");
+    const bool dense = dense_ts && dense_x && dense_cost;
+    if (o->save_dense ? !dense : (dense_ts || dense_x || dense_cost))
+        return fail(PMP_ERR_BAD_ARG, "dense_ts, dense_x, dense_cost: all three iff save_dense");
+    if (pmp_device_count() <= 0) return fail(PMP_ERR_NO_DEVICE, "no CUDA device: libb200pmp has no CPU fallback");
+    int rc = pmp::forward_batch(*p, *o, n, x0, P, x_eq, z_end, dense_ts, dense_x, dense_cost, n_accepted, n_steps, result,
+                                (cudaStream_t)cuda_stream);
+    if (rc == -1000) return fail(PMP_ERR_UNSUPPORTED, "no kernel for this (system, dtype, method) combination");
     return rc ? cuda_fail(rc) : PMP_OK;
 }
 

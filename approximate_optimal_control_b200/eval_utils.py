@@ -1,0 +1,48 @@
+"""Host-side mirror of the reference's `eval_utils` (closed-loop cost evaluation, /root/reference/eval_utils.py) for
+costate laws the CUDA path can evaluate.
+
+    closed_loop_eval_lqr(problem_params, algo_params, P_lqr, x0s)     eval_utils.py:10-45 with lambda(x) = P (x - x_eq)
+                                                                      in place of the NN-ensemble costate
+    compute_controlcost(problem_params, all_sols)                     eval_utils.py:101-107
+    closed_loop_eval_general(..., ustar_fct, ...)                     eval_utils.py:48-99: an arbitrary jax u*(x) callable
+                                                                      cannot enter a compiled kernel -> NotImplementedError
+
+z = (x, cost), z' = (f(x,u*), l(x,u*)), Tsit5 with the CONSTANT step algo_params['sim_dt'] from 0 to
+algo_params['sim_T'], max_steps = T/dt, SaveAt(steps=True): all_sols.ys has shape (N, T/dt, nx+1).
+"""
+from __future__ import annotations
+
+import torch
+
+from . import _capi, systems
+from . import pontryagin_utils as pu
+from .solution import Solution
+
+
+def closed_loop_eval_general(problem_params, algo_params, ustar_fct, x0s):
+    raise NotImplementedError("closed_loop_eval_general takes an arbitrary jax u*(x) callable; the CUDA path evaluates costate "
+                              "laws it has compiled: use closed_loop_eval_lqr (lambda = P (x - x_eq))")
+
+
+def closed_loop_eval_lqr(problem_params, algo_params, P_lqr, x0s):
+    problem = systems.to_c_problem(problem_params)
+    nx = problem.nx
+    T, dt = float(algo_params["sim_T"]), float(algo_params["sim_dt"])
+    max_steps = int(T / dt)
+    dev = pu._device(x0s)
+    dtype = pu._infer_dtype(algo_params, x0s)
+    xs = pu._as_tensor(x0s, dtype, dev).reshape(-1, nx).t().contiguous()
+    opts = _capi.make_opts(method=algo_params.get("pontryagin_solver_method", "tsit5"), dtype=pu._code(dtype), adaptive=0,
+                           t0=0.0, t1=T, dt0=dt, max_steps=max_steps, save_dense=1, dtmin=0.0, dtmax=0.0)
+    out = pu.forward_batch_soa(problem, opts, xs, P_lqr, problem_params.get("x_eq"))
+    ys = torch.cat([out["x"], out["cost"][..., None]], dim=-1)[:, 1:]  # SaveAt(steps=True): no t0 slot
+    stats = {"num_steps": out["n_steps"], "num_accepted_steps": out["n_accepted"],
+             "num_rejected_steps": out["n_steps"] - out["n_accepted"]}
+    return Solution(t0=0.0, t1=T, ts=out["ts"][:, 1:], ys=ys, y_end={"x": out["z_end"][:nx].t(), "cost": out["z_end"][nx]},
+                    stats=stats, result=out["result"], batched=True)
+
+
+def compute_controlcost(problem_params, all_sols):
+    """eval_utils.py:101-107: mean over the initial states of the cost recorded at the last saved step."""
+    control_costs = all_sols.ys[:, -1, problem_params["nx"]]
+    return control_costs.mean()

@@ -34,7 +34,7 @@ from . import _capi, systems
 from .solution import Solution
 
 __all__ = ["define_backward_solver", "u_star_2d", "u_star_new", "lqr", "get_terminal_lqr",
-           "make_pontryagin_solver_reparam", "solve_batch_soa", "pack_state", "unpack_state"]
+           "make_pontryagin_solver_reparam", "solve_batch_soa", "forward_batch_soa", "pack_state", "unpack_state"]
 
 # solver constants hard-coded in the reference (pontryagin_utils.py:500-501,515); overridable through
 # optional algo_params keys of the same name prefixed with 'pontryagin_solver_'
@@ -159,6 +159,35 @@ def solve_batch_soa(problem: _capi.Problem, opts: _capi.Opts, y_f: torch.Tensor,
             C.byref(dense) if dense is not None else None, out["n_accepted"].data_ptr(),
             out["n_steps"].data_ptr(), out["result"].data_ptr(), ws.data_ptr(), ws.numel(),
             _stream_ptr(dev)))
+    return out
+
+
+def forward_batch_soa(problem: _capi.Problem, opts: _capi.Opts, x0: torch.Tensor, P, x_eq=None, out=None):
+    """Thin wrapper of pmp_forward_batch_cuda: closed-loop forward simulation under lambda(x) = P (x - x_eq) with the
+    running cost accumulated as an extra state.  x0 [nx, n] CUDA tensor -> dict(z_end [nx+1, n], n_accepted, n_steps,
+    result [, ts (n, S+1), x (n, S+1, nx), cost (n, S+1)]).  Asynchronous on the current stream."""
+    L = _capi.lib_of(problem)
+    assert x0.is_cuda and x0.is_contiguous()
+    nx, n = x0.shape
+    dev = x0.device
+    Ph = np.ascontiguousarray(np.asarray(P.detach().cpu() if isinstance(P, torch.Tensor) else P, dtype=np.float64).reshape(nx, nx))
+    xe = None if x_eq is None else np.ascontiguousarray(np.asarray(x_eq, dtype=np.float64).reshape(nx))
+    out = {} if out is None else out
+    out.setdefault("z_end", torch.empty((nx + 1, n), dtype=x0.dtype, device=dev))
+    for k in ("n_accepted", "n_steps", "result"):
+        out.setdefault(k, torch.empty(n, dtype=torch.int32, device=dev))
+    dp = [None, None, None]
+    if opts.save_dense:
+        s1 = opts.max_steps + 1
+        out.setdefault("ts", torch.empty((n, s1), dtype=x0.dtype, device=dev))
+        out.setdefault("x", torch.empty((n, s1, nx), dtype=x0.dtype, device=dev))
+        out.setdefault("cost", torch.empty((n, s1), dtype=x0.dtype, device=dev))
+        dp = [out["ts"].data_ptr(), out["x"].data_ptr(), out["cost"].data_ptr()]
+    with torch.cuda.device(dev):
+        _capi.check(L.pmp_forward_batch_cuda(
+            C.byref(problem), C.byref(opts), n, x0.data_ptr(), Ph.ctypes.data, None if xe is None else xe.ctypes.data,
+            out["z_end"].data_ptr(), *dp, out["n_accepted"].data_ptr(), out["n_steps"].data_ptr(),
+            out["result"].data_ptr(), _stream_ptr(dev)), L)
     return out
 
 

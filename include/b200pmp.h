@@ -11,6 +11,8 @@
  *   pmp_rhs_batch_cuda     <- jax.vmap(f_extended)                pontryagin_utils.py:418-482
  *   pmp_ustar_batch_cuda   <- jax.vmap(u_star_2d) / u_star_new    pontryagin_utils.py:11-216, :532-562
  *                             (batched at levelsets.py:604-628 find_min_l)
+ *   pmp_forward_batch_cuda <- jax.vmap(forward_sim_lqr)           levelsets.py:818-836, and
+ *                             closed_loop_eval_general              eval_utils.py:48-99 (linear costate law)
  *   pmp_fma_peak_cuda      <- (no reference counterpart) register-resident FMA chain used as the
  *                             roofline denominator of bench.py
  *
@@ -75,8 +77,10 @@ enum {
 enum {
     PMP_EVENT_NONE = 0,
     PMP_EVENT_VALUE_GE = 1, /* stop once v >= event_level (value level set, problem_params['V_max']) */
-    PMP_EVENT_VXX_NORM = 2  /* stop once ||vxx||_F > event_level (algo_params['vxx_max_norm'],
+    PMP_EVENT_VXX_NORM = 2, /* stop once ||vxx||_F > event_level (algo_params['vxx_max_norm'],
                                pontryagin_utils.py:508-519); needs PMP_FLAG_VXX */
+    PMP_EVENT_LQR_VALUE_LE = 3 /* pmp_forward_batch_cuda only: stop once 1/2 (x-x_eq)'P(x-x_eq) <= event_level
+                                  (inside the value level set; LQR analogue of levelsets.py:897-915) */
 };
 
 /* per-trajectory result codes, diffrax-compatible (levelsets.py:1218 tests result == 1) */
@@ -201,6 +205,22 @@ int pmp_rhs_batch_cuda_flags(const pmp_problem_t *problem, int32_t dtype, int32_
 /* u* = argmin_u H(x,u,lambda) over the input box: x [nx][n], lam [nx][n] -> u [nu][n] */
 int pmp_ustar_batch_cuda(const pmp_problem_t *problem, int32_t dtype, int64_t n, const void *x,
                          const void *lam, void *u, void *cuda_stream);
+
+/* Forward closed-loop simulation x' = f(x, u*(x, lambda(x))) under the LINEAR costate law lambda(x) = P (x - x_eq)
+ * (levelsets.py:818-836 forward_sim_lqr), with the accumulated running cost as an extra state, cost' = l(x, u*)
+ * (eval_utils.py:48-99 closed_loop_eval_general).  opts: method, dtype, adaptive (0 = the constant step dt0 of
+ * eval_utils), t0 < t1, dt0 > 0, rtol / atol / dtmin / dtmax / controller factors, max_steps, event (NONE or
+ * PMP_EVENT_LQR_VALUE_LE), save_dense; indep must be PMP_INDEP_TIME and flags 0.  The error norm runs over the x leaf.
+ *   x0      [nx][n]    initial states (device)
+ *   P, x_eq HOST arrays of doubles, nx*nx row-major and nx (x_eq may be NULL = 0); read during the call
+ *   z_end   [nx+1][n]  final state and accumulated cost (device)
+ *   dense_ts [n][S1], dense_x [n][S1][nx], dense_cost [n][S1]: required iff opts->save_dense; slot 0 = x0, one slot
+ *           per accepted step, +inf padded
+ *   n_accepted, n_steps, result [n] int32 (any may be NULL); result codes as for pmp_solve_batch_cuda */
+int pmp_forward_batch_cuda(const pmp_problem_t *problem, const pmp_opts_t *opts, int64_t n, const void *x0,
+                           const double *P, const double *x_eq, void *z_end, void *dense_ts, void *dense_x,
+                           void *dense_cost, int32_t *n_accepted, int32_t *n_steps, int32_t *result,
+                           void *cuda_stream);
 
 /* Dense output, diffrax Solution.evaluate (SaveAt(dense=True), pontryagin_utils.py:504; used at
  * experiment_orbits.py:183-184, misc.py:40-95).  For every query q: y0[:, q] is the saved node at the

@@ -24,7 +24,7 @@ SYS_FLATQUAD, SYS_ORBITS, SYS_LQR = 0, 1, 2
 RK4, TSIT5, DOPRI5 = 0, 1, 2
 F32, F64 = 0, 1
 INDEP_TIME, INDEP_VALUE = 0, 1
-EVENT_NONE, EVENT_VALUE_GE, EVENT_VXX_NORM = 0, 1, 2
+EVENT_NONE, EVENT_VALUE_GE, EVENT_VXX_NORM, EVENT_LQR_VALUE_LE = 0, 1, 2, 3
 FLAG_USTAR_LITERAL, FLAG_VXX = 1, 2
 
 
@@ -206,6 +206,28 @@ def vxx_rhs(problem: Problem, x, lam, vxx):
     _check(L.pmp_oracle_vxx_rhs(C.byref(problem), x.ctypes.data, lam.ctypes.data, vxx.ctypes.data, jac.ctypes.data,
                                 out.ctypes.data))
     return jac[0], jac[1], jac[2], jac[3], out
+
+
+def forward_batch(problem: Problem, opts: Opts, x0: np.ndarray, P: np.ndarray, x_eq=None) -> dict:
+    """Forward closed-loop simulation under lambda(x) = P (x - x_eq): x0 [nx, n] -> dict(z_end [nx+1, n],
+    n_accepted, n_steps, result [, ts, x, cost])   (levelsets.py:818-836, eval_utils.py:48-99)."""
+    dt = _np_dtype(opts.dtype)
+    x0 = np.ascontiguousarray(x0, dtype=dt)
+    nx, n = x0.shape
+    P = np.ascontiguousarray(P, dtype=np.float64)
+    xe = None if x_eq is None else np.ascontiguousarray(x_eq, dtype=np.float64)
+    out = {"z_end": np.empty((nx + 1, n), dt), "n_accepted": np.empty(n, np.int32), "n_steps": np.empty(n, np.int32),
+           "result": np.empty(n, np.int32)}
+    ptr = lambda a: None if a is None else a.ctypes.data
+    if opts.save_dense:
+        s1 = opts.max_steps + 1
+        out.update(ts=np.empty((n, s1), dt), x=np.empty((n, s1, nx), dt), cost=np.empty((n, s1), dt))
+    L = lib()
+    L.pmp_oracle_forward_batch.argtypes = [C.POINTER(Problem), C.POINTER(Opts), C.c_int64] + [C.c_void_p] * 10
+    _check(L.pmp_oracle_forward_batch(C.byref(problem), C.byref(opts), n, ptr(x0), ptr(P), ptr(xe), ptr(out["z_end"]),
+                                      ptr(out.get("ts")), ptr(out.get("x")), ptr(out.get("cost")), ptr(out["n_accepted"]),
+                                      ptr(out["n_steps"]), ptr(out["result"])))
+    return out
 
 
 def opcount(problem: Problem, opts: Opts, y0: np.ndarray) -> dict:

@@ -98,6 +98,31 @@ void ustar_batch_t(const pmp_problem_t& p, int64_t n, const R* x, const R* lam, 
         for (int q = 0; q < NU; q++) u[q * n + i] = uu[q];
     }
 }
+// forward closed-loop simulation (levelsets.py:818-836, eval_utils.py:48-99); same contract as pmp_forward_batch_cuda
+// with host pointers: x0 [nx][n], z_end [nx+1][n], dense ts [n][S1], x [n][S1][nx], cost [n][S1] (all or none)
+template <class R, class Sys>
+int forward_batch_t(const pmp_problem_t& p, const pmp_opts_t& o, int64_t n, const R* x0, const double* P, const double* x_eq,
+                    R* z_end, R* ts, R* xs, R* cost, int32_t* n_acc, int32_t* n_steps, int32_t* result) {
+    constexpr int NX = Sys::NX;
+    Sys sys(p);
+    const int64_t S1 = o.max_steps + 1;
+#ifdef _OPENMP
+#pragma omp parallel for schedule(dynamic, 64)
+#endif
+    for (int64_t i = 0; i < n; i++) {
+        R a[NX], e[NX + 1];
+        for (int q = 0; q < NX; q++) a[q] = x0[q * n + i];
+        ForwardSink<R> sink;
+        if (ts) { sink.ts = ts + i * S1; sink.x = xs + i * S1 * NX; sink.cost = cost + i * S1; }
+        TrajStats st = forward_one<R, Sys>(sys, o, P, x_eq, a, e, sink);
+        for (int q = 0; q <= NX; q++) z_end[q * n + i] = e[q];
+        if (n_acc) n_acc[i] = st.n_accepted;
+        if (n_steps) n_steps[i] = st.n_steps;
+        if (result) result[i] = st.result;
+    }
+    return 0;
+}
+
 }  // namespace
 
 extern "C" {
@@ -185,6 +210,29 @@ int pmp_oracle_vxx_rhs(const pmp_problem_t* p, const double* x, const double* la
         }
     sys.vxx_dot(x, lam, vxx, vxx_dot_out);
     return 0;
+}
+
+int pmp_oracle_forward_batch(const pmp_problem_t* p, const pmp_opts_t* o, int64_t n, const void* x0, const double* P,
+                             const double* x_eq, void* z_end, void* ts, void* xs, void* cost, int32_t* n_accepted,
+                             int32_t* n_steps, int32_t* result) {
+    if (int e = check(p, o)) return e;
+    if (!o || !x0 || !P || !z_end || n < 0) return fail(PMP_ERR_BAD_ARG, "bad arguments");
+#define FWD(R, SYS) return forward_batch_t<R, SYS<R>>(*p, *o, n, (const R*)x0, P, x_eq, (R*)z_end, (R*)ts, (R*)xs, (R*)cost, n_accepted, n_steps, result)
+    if (o->dtype == PMP_F32) {
+        switch (p->system_id) {
+            case PMP_SYS_FLATQUAD: FWD(float, Flatquad);
+            case PMP_SYS_ORBITS: FWD(float, Orbits);
+            case PMP_SYS_LQR_STATEPENALTY: FWD(float, LqrStatePenalty);
+        }
+    } else {
+        switch (p->system_id) {
+            case PMP_SYS_FLATQUAD: FWD(double, Flatquad);
+            case PMP_SYS_ORBITS: FWD(double, Orbits);
+            case PMP_SYS_LQR_STATEPENALTY: FWD(double, LqrStatePenalty);
+        }
+    }
+#undef FWD
+    return fail(PMP_ERR_UNSUPPORTED, "unknown system_id");
 }
 
 // dense output (diffrax Solution.evaluate) on one step per query; same contract as pmp_interp_batch_cuda

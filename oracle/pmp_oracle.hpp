@@ -709,6 +709,150 @@ TrajStats solve_one(const Sys& sys, const pmp_opts_t& o, const R* y_f, R* y_end,
 
 
 // =================================================================================================
+// Forward closed-loop simulation under the linear costate law lambda(x) = P (x - x_eq):
+//   levelsets.py:818-836 forward_sim_lqr   (x' = f(x, u_star_2d(x, P x)), Tsit5 + PIDController, t: 0 -> T)
+//   eval_utils.py:48-99  closed_loop_eval_general  (one more state records the cost, cost' = l(x, u*))
+// State z = (x, cost); the rms error norm runs over the x leaf only (forward_sim_lqr has no cost state; the
+// constant-step evaluation has no error control).  Same diffrax step-control flow as solve_one.
+// Optional event: 1/2 dx'P dx <= event_level (PMP_EVENT_LQR_VALUE_LE).
+// =================================================================================================
+template <class R> struct ForwardSink {
+    R* ts = nullptr; R* x = nullptr; R* cost = nullptr;
+};
+
+template <class R, class Sys>
+TrajStats forward_one(const Sys& sys, const pmp_opts_t& o, const double* P, const double* x_eq, const R* x0, R* z_end,
+                      ForwardSink<R> sink) {
+    constexpr int NX = Sys::NX, NZ = NX + 1, NS = 2 * NX + 2, IV = NX + 1;
+    const Tableau& tb = *tableau_for(o.method);
+    const int S1 = o.max_steps + 1;
+    const R inf = r_inf<R>();
+    TrajStats st;
+    R z[NZ];
+    for (int i = 0; i < NX; i++) z[i] = x0[i];
+    z[NX] = R(0);
+    const R dir = (o.t0 < o.t1) ? R(1) : R(-1);
+    const R T0 = R(o.t0) * dir, T1 = R(o.t1) * dir;
+    R tprev = T0, tnext = r_min(T0 + R(o.dt0) * dir, T1);
+    const R clip_tol = std::is_same<R, float>::value ? R(1e-6) : R(1e-10);
+    R vlqr = R(0);
+    auto field = [&](const R* zz, R* k, R& v) {
+        R y[NS], dy[NS], v2 = R(0);
+        for (int i = 0; i < NS; i++) y[i] = R(0);
+        for (int r = 0; r < NX; r++) {
+            R a = R(0);
+            for (int q = 0; q < NX; q++) a = a + R(P[r * NX + q]) * (zz[q] - R(x_eq ? x_eq[q] : 0.0));
+            y[NX + 2 + r] = a;
+            v2 = v2 + a * (zz[r] - R(x_eq ? x_eq[r] : 0.0));
+            y[r] = zz[r];
+        }
+        v = R(0.5) * v2;
+        sys.rhs(y, dy);
+        for (int i = 0; i < NX; i++) k[i] = dy[i] * dir;
+        k[NX] = -dy[IV] * dir;
+    };
+    auto save = [&](int slot) {
+        if (slot >= S1) return;
+        if (sink.ts) sink.ts[slot] = tprev * dir;
+        if (sink.x) for (int i = 0; i < NX; i++) sink.x[slot * NX + i] = z[i];
+        if (sink.cost) sink.cost[slot] = z[NX];
+    };
+    save(0);
+    bool bad0 = false;
+    for (int i = 0; i < NX; i++) bad0 = bad0 || r_isnan(z[i]);
+    if (bad0) st.result = PMP_RESULT_NAN;
+    R k[7][NZ];
+    field(z, k[0], vlqr);
+    bool at_dtmin = false;
+    while (r_val(tprev) < r_val(T1) && st.result == 0 && st.n_steps < o.max_steps) {
+        const R dt = tnext - tprev;
+        R zs[NZ], z1[NZ], v1 = R(0);
+        const int last = tb.stages - 1;
+        for (int i = 1; i < tb.stages; i++) {
+            for (int q = 0; q < NZ; q++) {
+                R acc = R(tb.a[i][0]) * k[0][q];
+                for (int j = 1; j < i; j++) acc = acc + R(tb.a[i][j]) * k[j][q];
+                zs[q] = z[q] + dt * acc;
+            }
+            field(zs, k[i], v1);
+            if (tb.fsal && i == last)
+                for (int q = 0; q < NZ; q++) z1[q] = zs[q];
+        }
+        if (!tb.fsal) {
+            for (int q = 0; q < NZ; q++) {
+                R acc = R(tb.b[0]) * k[0][q];
+                for (int j = 1; j < tb.stages; j++) acc = acc + R(tb.b[j]) * k[j][q];
+                z1[q] = z[q] + dt * acc;
+            }
+        }
+        bool keep = true, err_nonfinite = false;
+        R next_t0, next_t1;
+        if (o.adaptive && tb.embedded) {
+            R sumsq = R(0);
+            bool nan1 = false;
+            for (int q = 0; q < NX; q++) nan1 = nan1 || r_isnan(z1[q]);
+            for (int q = 0; q < NX; q++) {
+                R acc = R(tb.berr[0]) * k[0][q];
+                for (int j = 1; j < tb.stages; j++) acc = acc + R(tb.berr[j]) * k[j][q];
+                R e = dt * acc;
+                if (r_isnan(e)) e = inf;
+                R sc = R(o.atol) + r_max(r_abs(z[q]), r_abs(nan1 ? z[q] : z1[q])) * R(o.rtol);
+                R r = e / sc;
+                sumsq = sumsq + r * r;
+            }
+            R scaled = r_sqrt(sumsq / R(NX));
+            keep = (r_val(scaled) < 1.0) || at_dtmin;
+            err_nonfinite = !(r_val(scaled) < std::numeric_limits<double>::infinity());
+            R factor = R(o.safety) * r_pow(R(1) / scaled, R(1.0 / tb.order));
+            factor = r_clip(factor, keep ? R(1) : R(o.factormin), R(o.factormax));
+            R dtn = dt * factor;
+            if (o.dtmax > 0) dtn = r_min(dtn, R(o.dtmax));
+            if (o.dtmin > 0) {
+                if (!o.force_dtmin && r_val(dtn) < o.dtmin) st.result = PMP_RESULT_DT_MIN;
+                at_dtmin = r_val(dtn) <= o.dtmin;
+                dtn = r_max(dtn, R(o.dtmin));
+            } else {
+                at_dtmin = false;
+            }
+            next_t0 = keep ? tnext : tprev;
+            next_t1 = next_t0 + dtn;
+        } else {
+            next_t0 = tnext;
+            next_t1 = tnext + dt;
+        }
+        tprev = r_min(next_t0, T1);
+        if (r_val(next_t1) > r_val(T1 - clip_tol)) next_t1 = keep ? T1 : tprev + R(0.5) * (T1 - tprev);
+        tnext = next_t1;
+        st.n_steps += 1;
+        if (keep) {
+            for (int q = 0; q < NZ; q++) z[q] = z1[q];
+            if (tb.fsal) {
+                for (int q = 0; q < NZ; q++) k[0][q] = k[last][q];
+                vlqr = v1;
+            } else {
+                field(z, k[0], vlqr);
+            }
+            st.n_accepted += 1;
+            save(st.n_accepted);
+        }
+        if (st.result == 0 && o.event == PMP_EVENT_LQR_VALUE_LE && r_val(vlqr) <= o.event_level) st.result = PMP_RESULT_EVENT;
+        if (keep && st.result == 0) {
+            bool bad = err_nonfinite;
+            for (int q = 0; q < NZ; q++) bad = bad || r_isnan(z[q]);
+            if (bad) st.result = PMP_RESULT_NAN;
+        }
+    }
+    if (st.result == 0 && r_val(tprev) < r_val(T1)) st.result = PMP_RESULT_MAX_STEPS;
+    for (int i = 0; i < NZ; i++) z_end[i] = z[i];
+    for (int slot = st.n_accepted + 1; slot < S1; slot++) {
+        if (sink.ts) sink.ts[slot] = inf * dir;
+        if (sink.x) for (int i = 0; i < NX; i++) sink.x[slot * NX + i] = inf;
+        if (sink.cost) sink.cost[slot] = inf;
+    }
+    return st;
+}
+
+// =================================================================================================
 // Dense output: diffrax Solution.evaluate on one step.  Recomputes the stage derivatives of the
 // step [t0, t1] that starts at the saved node y0 and evaluates the interpolant (Tsit5: Tsitouras'
 // free interpolant, constants as in SURVEY.md 8(c); Dopri5: Hairer's contd5; RK4: cubic Hermite).

@@ -108,7 +108,7 @@ def test_argument_validation_and_error_strings():
     assert L.pmp_state_rows(C.byref(bad)) == -1 and b"U_interval" in L.pmp_last_error()
     for kw, frag in ((dict(method=9), b"method"), (dict(max_steps=0), b"max_steps"), (dict(dt0=0.0), b"dt0"),
                      (dict(dt0=+0.1), b"dt0"), (dict(method="rk4", adaptive=1), b"RK4"), (dict(rtol=-1.0), b"rtol"),
-                     (dict(dtype=5), b"dtype"), (dict(event=3), b"event")):
+                     (dict(dtype=5), b"dtype"), (dict(event=4), b"event"), (dict(event=3), b"pmp_forward_batch_cuda")):
         o = _capi.make_opts(**kw)
         assert L.pmp_solve_workspace_bytes(C.byref(prob), C.byref(o), 8) < 0, kw
         assert frag in L.pmp_last_error(), (kw, L.pmp_last_error())

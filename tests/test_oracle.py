@@ -417,3 +417,45 @@ def test_vxx_changes_the_step_sequence_only_through_the_norm():
     fro = np.linalg.norm(e["y_end"][14:], axis=0)
     assert (e["result"] == 1).any() and (e["result"] == 0).any()
     assert (fro[e["result"] == 1] > 345.0).all() and (fro[e["result"] == 0] <= 345.0).all()
+
+
+# ---- forward closed-loop simulation (levelsets.py:818-836, eval_utils.py:48-99) ------------------------------
+def test_forward_simulation_lqr_known_answer():
+    """Double integrator, l = |x|^2 + u^2 (penalties inactive for |x| < 1), U unbounded: under lambda = 2 P x the
+    closed loop is x' = (A - B K) x, so x(T) = expm((A - BK) T) x0, and the accumulated cost is V(x0) - V(x(T)),
+    V = x'Px (the LQR value function is exact here)."""
+    A = np.array([[0.0, 1.0], [0.0, 0.0]]); B = np.array([[0.0], [1.0]])
+    P = lqr_P()
+    K = B.T @ P
+    prob = O.lqr_problem()
+    prob.u_lo[0], prob.u_hi[0] = -1e9, 1e9
+    rng = np.random.Generator(np.random.PCG64(2))
+    x0 = 0.3 * rng.standard_normal((2, 64))
+    T = 4.0
+    for kw in (dict(method=O.TSIT5, rtol=1e-10, atol=1e-12, max_steps=4096, dtmin=0.0, dtmax=0.0),
+               dict(method=O.RK4, adaptive=0, dt0=1 / 256, max_steps=1024, dtmin=0.0, dtmax=0.0)):
+        o = O.make_opts(dtype=O.F64, t0=0.0, t1=T, **{"dt0": 0.1, **kw})
+        out = O.forward_batch(prob, o, x0, 2 * P)
+        assert (out["result"] == 0).all()
+        xT = scipy.linalg.expm((A - B @ K) * T) @ x0
+        assert np.abs(out["z_end"][:2] - xT).max() <= 1e-8
+        V = lambda x: np.einsum("in,ij,jn->n", x, P, x)
+        assert np.abs(out["z_end"][2] - (V(x0) - V(xT))).max() <= 1e-8
+
+
+def test_forward_simulation_event_and_dense_layout():
+    y = flatquad_terminal(64)
+    P = flatquad_P()
+    x0 = 40.0 * y[:6]  # V_lqr = 1e-3 * 1600 = 1.6
+    o = O.make_opts(dtype=O.F64, t0=0.0, t1=10.0, dt0=0.1, dtmin=0.05, dtmax=0.0, max_steps=256, save_dense=1,
+                    event=O.EVENT_LQR_VALUE_LE, event_level=0.2)
+    out = O.forward_batch(O.flatquad_problem(), o, x0, P)
+    assert (out["result"] == 1).all()
+    xe = out["z_end"][:6]
+    v_end = 0.5 * np.einsum("in,ij,jn->n", xe, P, xe)
+    assert (v_end <= 0.2).all() and (v_end > 0.02).all()
+    i = np.arange(64)
+    acc = out["n_accepted"]
+    assert np.array_equal(out["x"][i, acc].T, xe) and np.array_equal(out["cost"][i, acc], out["z_end"][6])
+    assert np.isinf(out["x"][0, acc[0] + 1:]).all() and np.array_equal(out["x"][:, 0].T, x0) and (out["cost"][:, 0] == 0).all()
+    assert (np.diff(out["cost"][0, :acc[0] + 1]) > 0).all()  # the running cost is positive
