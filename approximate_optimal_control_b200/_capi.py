@@ -15,7 +15,7 @@ SYS_FLATQUAD, SYS_ORBITS, SYS_LQR_STATEPENALTY, SYS_GENERATED = 0, 1, 2, 3
 METHOD_RK4, METHOD_TSIT5, METHOD_DOPRI5 = 0, 1, 2
 F32, F64 = 0, 1
 INDEP_TIME, INDEP_VALUE = 0, 1
-EVENT_NONE, EVENT_VALUE_GE, EVENT_VXX_NORM, EVENT_LQR_VALUE_LE = 0, 1, 2, 3
+EVENT_NONE, EVENT_VALUE_GE, EVENT_VXX_NORM, EVENT_LQR_VALUE_LE, EVENT_NN_VALUE_UCB_LE = 0, 1, 2, 3, 4
 RESULT_OK, RESULT_EVENT, RESULT_MAX_STEPS, RESULT_DT_MIN, RESULT_NAN = 0, 1, 2, 3, 4
 ABI_VERSION = 3
 FLAG_USTAR_LITERAL = 1
@@ -48,9 +48,15 @@ class Dense(C.Structure):
                 ("vx", C.c_void_p), ("vxx", C.c_void_p)]
 
 
+class NnCostate(C.Structure):
+    _fields_ = [("n_nets", C.c_int32), ("n_hidden_layers", C.c_int32), ("width", C.c_int32), ("reserved", C.c_int32),
+                ("weights", C.c_void_p), ("x_mean", C.c_double * 16), ("x_std", C.c_double * 16),
+                ("v_mean", C.c_double), ("v_std", C.c_double), ("n_sigma", C.c_double), ("sigma_max", C.c_double)]
+
+
 EXPORTS = ("pmp_abi_version", "pmp_last_error", "pmp_state_rows", "pmp_state_rows_flags", "pmp_device_count",
            "pmp_solve_workspace_bytes", "pmp_solve_batch_cuda", "pmp_solve_launch_count",
-           "pmp_rhs_batch_cuda", "pmp_rhs_batch_cuda_flags", "pmp_ustar_batch_cuda", "pmp_ustar_batch_cuda_flags", "pmp_interp_batch_cuda", "pmp_forward_batch_cuda",
+           "pmp_rhs_batch_cuda", "pmp_rhs_batch_cuda_flags", "pmp_ustar_batch_cuda", "pmp_ustar_batch_cuda_flags", "pmp_interp_batch_cuda", "pmp_forward_batch_cuda", "pmp_forward_nn_batch_cuda", "pmp_nn_value_batch_cuda",
            "pmp_fma_peak_cuda")
 
 _lib = None
@@ -110,6 +116,8 @@ def load(path: str) -> C.CDLL:
     L.pmp_forward_batch_cuda.argtypes = [C.POINTER(Problem), C.POINTER(Opts), C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p,
                                          C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
                                          C.c_void_p]
+    L.pmp_forward_nn_batch_cuda.argtypes = [C.POINTER(Problem), C.POINTER(Opts), C.POINTER(NnCostate), C.c_int64] + [C.c_void_p] * 9
+    L.pmp_nn_value_batch_cuda.argtypes = [C.POINTER(Problem), C.POINTER(NnCostate), C.c_int32, C.c_int64] + [C.c_void_p] * 5
     L.pmp_fma_peak_cuda.argtypes = [C.c_int32, C.c_int32, C.c_int32, C.c_void_p,
                                     C.POINTER(C.c_double), C.c_void_p]
     if L.pmp_abi_version() != ABI_VERSION:

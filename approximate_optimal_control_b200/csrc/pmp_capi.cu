@@ -26,8 +26,10 @@ int solve_generated(const pmp_problem_t&, const pmp_opts_t&, long long, const vo
 int eval_batch(int what, const pmp_problem_t& p, int dtype, long long n, const void* a, const void* b, void* out,
                cudaStream_t st);
 int forward_batch(const pmp_problem_t& p, const pmp_opts_t& o, long long n, const void* x0, const double* P,
-                  const double* x_eq, void* z_end, void* ts, void* xs, void* cost, int32_t* a, int32_t* s, int32_t* r,
-                  cudaStream_t st);
+                  const double* x_eq, const pmp_nn_costate_t* nn, void* z_end, void* ts, void* xs, void* cost, int32_t* a,
+                  int32_t* s, int32_t* r, cudaStream_t st);
+int nn_value_batch(const pmp_problem_t& p, const pmp_nn_costate_t* nn, int dtype, long long n, const void* x, void* lam,
+                   void* vm, void* vs, cudaStream_t st);
 int fma_peak(int dtype, int variant, int iters, void* scratch, double* flops_out, cudaStream_t st);
 int interp_batch(const pmp_problem_t& p, const pmp_opts_t& o, long long nq, const void* y0, const void* t1,
                  const void* target, void* y_out, int mode, cudaStream_t st);
@@ -76,7 +78,7 @@ int check_opts(const pmp_opts_t* o) {
     if (o->dtype != PMP_F32 && o->dtype != PMP_F64) return fail(PMP_ERR_BAD_ARG, "dtype must be 0 (f32) or 1 (f64)");
     if (o->indep != PMP_INDEP_TIME && o->indep != PMP_INDEP_VALUE) return fail(PMP_ERR_BAD_ARG, "bad indep");
     if (o->max_steps < 1) return fail(PMP_ERR_BAD_ARG, "max_steps must be >= 1");
-    if (o->event < PMP_EVENT_NONE || o->event > PMP_EVENT_LQR_VALUE_LE) return fail(PMP_ERR_UNSUPPORTED, "unknown event");
+    if (o->event < PMP_EVENT_NONE || o->event > PMP_EVENT_NN_VALUE_UCB_LE) return fail(PMP_ERR_UNSUPPORTED, "unknown event");
     if (o->event == PMP_EVENT_VXX_NORM && !(o->flags & PMP_FLAG_VXX))
         return fail(PMP_ERR_BAD_ARG, "PMP_EVENT_VXX_NORM needs PMP_FLAG_VXX");
     if (o->adaptive && o->method == PMP_METHOD_RK4)
@@ -105,8 +107,9 @@ int check_opts(const pmp_opts_t* o) {
 }
 // options that need a particular system
 int check_pair(const pmp_problem_t* p, const pmp_opts_t* o) {
-    if (o->event == PMP_EVENT_LQR_VALUE_LE)
-        return fail(PMP_ERR_BAD_ARG, "PMP_EVENT_LQR_VALUE_LE belongs to pmp_forward_batch_cuda (the backward solve has no P)");
+    if (o->event == PMP_EVENT_LQR_VALUE_LE || o->event == PMP_EVENT_NN_VALUE_UCB_LE)
+        return fail(PMP_ERR_BAD_ARG, "this event belongs to pmp_forward_batch_cuda / pmp_forward_nn_batch_cuda (the backward "
+                                     "solve has no costate law)");
     if ((o->flags & PMP_FLAG_VXX) && p->system_id != PMP_SYS_FLATQUAD)  // (a plug-in never is)
         return fail(PMP_ERR_UNSUPPORTED, "PMP_FLAG_VXX: only the flatquad functor carries the Jacobians through u*");
     return 0;
@@ -237,26 +240,70 @@ int pmp_ustar_batch_cuda(const pmp_problem_t* p, int32_t dtype, int64_t n, const
     return rc ? cuda_fail(rc) : PMP_OK;
 }
 
-int pmp_forward_batch_cuda(const pmp_problem_t* p, const pmp_opts_t* o, int64_t n, const void* x0, const double* P,
-                           const double* x_eq, void* z_end, void* dense_ts, void* dense_x, void* dense_cost,
-                           int32_t* n_accepted, int32_t* n_steps, int32_t* result, void* cuda_stream) {
+static int check_nn(const pmp_problem_t* p, const pmp_nn_costate_t* nn) {
+    if (!nn) return fail(PMP_ERR_BAD_ARG, "nn is NULL");
+    if (nn->width != 32 && nn->width != 64) return fail(PMP_ERR_UNSUPPORTED, "NN costate: width must be 32 or 64");
+    if (nn->n_hidden_layers < 1 || nn->n_hidden_layers > 4) return fail(PMP_ERR_UNSUPPORTED, "NN costate: 1..4 hidden layers");
+    if (nn->n_nets < 1 || nn->n_nets > 16) return fail(PMP_ERR_UNSUPPORTED, "NN costate: 1..16 ensemble members");
+    if (!nn->weights || ((uintptr_t)nn->weights & 15u) != 0) return fail(PMP_ERR_BAD_ARG, "NN costate: weights NULL or not 16-byte aligned");
+    if (nn->reserved != 0) return fail(PMP_ERR_BAD_ARG, "NN costate: reserved != 0");
+    for (int q = 0; q < p->nx; q++)
+        if (!(nn->x_std[q] > 0)) return fail(PMP_ERR_BAD_ARG, "NN costate: x_std must be > 0");
+    return 0;
+}
+
+static int forward_common(const pmp_problem_t* p, const pmp_opts_t* o, int64_t n, const void* x0, const double* P,
+                          const double* x_eq, const pmp_nn_costate_t* nn, void* z_end, void* dense_ts, void* dense_x,
+                          void* dense_cost, int32_t* n_accepted, int32_t* n_steps, int32_t* result, void* cuda_stream) {
     if (int e = check_problem(p)) return e;
     if (int e = check_opts(o)) return e;
     if (o->indep != PMP_INDEP_TIME || o->flags != 0) return fail(PMP_ERR_BAD_ARG, "forward simulation: indep must be TIME, flags 0");
-    if (o->event != PMP_EVENT_NONE && o->event != PMP_EVENT_LQR_VALUE_LE)
-        return fail(PMP_ERR_BAD_ARG, "forward simulation: event must be NONE or PMP_EVENT_LQR_VALUE_LE");
+    const int own_event = nn ? PMP_EVENT_NN_VALUE_UCB_LE : PMP_EVENT_LQR_VALUE_LE;
+    if (o->event != PMP_EVENT_NONE && o->event != own_event)
+        return fail(PMP_ERR_BAD_ARG, nn ? "forward simulation (NN costate): event must be NONE or PMP_EVENT_NN_VALUE_UCB_LE"
+                                        : "forward simulation: event must be NONE or PMP_EVENT_LQR_VALUE_LE");
     if (!(o->t0 < o->t1)) return fail(PMP_ERR_BAD_ARG, "forward simulation: need t0 < t1");
     if (n < 0) return fail(PMP_ERR_BAD_ARG, "n < 0");
+    if (nn)
+        if (int e = check_nn(p, nn)) return e;
     if (n == 0) return PMP_OK;
-    if (!x0 || !P || !z_end) return fail(PMP_ERR_BAD_ARG, "x0 / P / z_end is NULL");
+    if (!x0 || (!P && !nn) || !z_end) return fail(PMP_ERR_BAD_ARG, "x0 / P / z_end is NULL");
     const bool dense = dense_ts && dense_x && dense_cost;
     if (o->save_dense ? !dense : (dense_ts || dense_x || dense_cost))
         return fail(PMP_ERR_BAD_ARG, "dense_ts, dense_x, dense_cost: all three iff save_dense");
     if (pmp_device_count() <= 0) return fail(PMP_ERR_NO_DEVICE, "no CUDA device: libb200pmp has no CPU fallback");
-    int rc = pmp::forward_batch(*p, *o, n, x0, P, x_eq, z_end, dense_ts, dense_x, dense_cost, n_accepted, n_steps, result,
+    int rc = pmp::forward_batch(*p, *o, n, x0, P, x_eq, nn, z_end, dense_ts, dense_x, dense_cost, n_accepted, n_steps, result,
                                 (cudaStream_t)cuda_stream);
     if (rc == -1000) return fail(PMP_ERR_UNSUPPORTED, "no kernel for this (system, dtype, method) combination");
     return rc ? cuda_fail(rc) : PMP_OK;
+}
+
+int pmp_forward_batch_cuda(const pmp_problem_t* p, const pmp_opts_t* o, int64_t n, const void* x0, const double* P,
+                           const double* x_eq, void* z_end, void* dense_ts, void* dense_x, void* dense_cost,
+                           int32_t* n_accepted, int32_t* n_steps, int32_t* result, void* cuda_stream) {
+    return forward_common(p, o, n, x0, P, x_eq, nullptr, z_end, dense_ts, dense_x, dense_cost, n_accepted, n_steps, result,
+                          cuda_stream);
+}
+
+int pmp_nn_value_batch_cuda(const pmp_problem_t* p, const pmp_nn_costate_t* nn, int32_t dtype, int64_t n, const void* x,
+                            void* lam, void* v_mean, void* v_std, void* cuda_stream) {
+    if (int e = check_problem(p)) return e;
+    if (int e = check_nn(p, nn)) return e;
+    if (dtype != PMP_F32 && dtype != PMP_F64) return fail(PMP_ERR_BAD_ARG, "dtype must be 0 (f32) or 1 (f64)");
+    if (n < 0 || (n > 0 && (!x || !lam || !v_mean || !v_std))) return fail(PMP_ERR_BAD_ARG, "bad n or NULL buffers");
+    if (n == 0) return PMP_OK;
+    if (pmp_device_count() <= 0) return fail(PMP_ERR_NO_DEVICE, "no CUDA device: libb200pmp has no CPU fallback");
+    int rc = pmp::nn_value_batch(*p, nn, dtype, n, x, lam, v_mean, v_std, (cudaStream_t)cuda_stream);
+    if (rc == -1000) return fail(PMP_ERR_UNSUPPORTED, "no kernel for this (nx, width) combination");
+    return rc ? cuda_fail(rc) : PMP_OK;
+}
+
+int pmp_forward_nn_batch_cuda(const pmp_problem_t* p, const pmp_opts_t* o, const pmp_nn_costate_t* nn, int64_t n,
+                              const void* x0, void* z_end, void* dense_ts, void* dense_x, void* dense_cost,
+                              int32_t* n_accepted, int32_t* n_steps, int32_t* result, void* cuda_stream) {
+    if (!nn) return fail(PMP_ERR_BAD_ARG, "nn is NULL");
+    return forward_common(p, o, n, x0, nullptr, nullptr, nn, z_end, dense_ts, dense_x, dense_cost, n_accepted, n_steps, result,
+                          cuda_stream);
 }
 
 int pmp_interp_batch_cuda(const pmp_problem_t* p, const pmp_opts_t* o, int64_t nq, const void* y0, const void* t1,

@@ -1,29 +1,192 @@
-// pmp_forward.cuh -- batched FORWARD closed-loop simulation under a costate feedback law (SURVEY.md 8(f) N3,
-// first slice).
+// pmp_forward.cuh -- batched FORWARD closed-loop simulation under a costate feedback law.
 //
 // The reference simulates the closed loop x' = f(x, u*(x, lambda(x))) forward in time in two places:
 //   * levelsets.py:818-836  forward_sim_lqr: lambda(x) = P_lqr x, Tsit5 + PIDController(rtol, atol, dtmin=.05),
 //     t: 0 -> 10, SaveAt(steps, t0), max_steps, throw=False  (the NN variants :838-933 differ in lambda(x) only);
 //   * eval_utils.py:48-99   closed_loop_eval_general: one extra state records the control cost,
 //     z = (x, cost), z' = (f(x,u*), l(x,u*)), Tsit5 with a constant step dt, max_steps = T/dt.
-// This kernel covers both for a LINEAR costate law lambda(x) = P (x - x_eq) (the LQR value function): the state
-// is z = (x, cost); the error norm runs over the x leaf only (forward_sim_lqr has no cost state, and the
-// constant-step evaluation has no error control), so either call site sees its own step sequence.  The neural
-// costate law (gradient of an MLP ensemble) is a different kernel (a batched small-GEMM) and is not built.
-// Optional terminating event: 1/2 (x-x_eq)'P(x-x_eq) <= level, the LQR analogue of the reference's "inside the
-// value level set" stop (levelsets.py:897-915).
+// This kernel covers both, for two costate laws (the `Pol` template parameter):
+//   * LinearCostate  lambda(x) = P (x - x_eq), the LQR value function (forward_sim_lqr);
+//   * NnCostate      lambda(x) = gradient of the mean of an ensemble of value networks (forward_sim_nn,
+//                    forward_sim_nn_until_value levelsets.py:838-933; closed_loop_eval_nn_ensemble eval_utils.py:10-45).
+// The state is z = (x, cost); the error norm runs over the x leaf only (the forward_sim_* calls have no cost state,
+// and the constant-step evaluation has no error control), so either call site sees its own step sequence.
+// Optional terminating event ("inside the value level set"): LinearCostate 1/2 dx'P dx <= level; NnCostate the
+// reference's v_mean + 2 v_std <= v_k and v_std <= 0.5 over the ensemble (levelsets.py:897-913).
 //
 // One thread per trajectory, state and stage derivatives in registers, the same diffrax step-control
 // semantics as pmp_solve.cuh.  Forward simulations run by the hundred, not by the million
 // (levelsets.py:1201-1215): no work queue, no staging of the dense output.
 #pragma once
+#include <type_traits>
+
 #include "pmp_solve.cuh"
 
 namespace pmp {
 
+// ---- costate laws lambda(x): eval() also reports an estimate of the value and its spread ------------------
 template <class R, int NX> struct LinearCostate {
     R P[NX * NX];  // row-major
     R x_eq[NX];
+    // lambda = P (x - x_eq), value 1/2 dx'P dx
+    __device__ __forceinline__ void eval(const R* x, R* lam, R& vmean, R& vstd) const {
+        using M = Math<R>;
+        R dx[NX];
+#pragma unroll
+        for (int q = 0; q < NX; q++) dx[q] = x[q] - x_eq[q];
+        R v2 = R(0);
+#pragma unroll
+        for (int r = 0; r < NX; r++) {
+            R a = R(0);
+#pragma unroll
+            for (int q = 0; q < NX; q++) a = M::fma(P[r * NX + q], dx[q], a);
+            lam[r] = a;
+            v2 = M::fma(a, dx[r], v2);
+        }
+        vmean = R(0.5) * v2;
+        vstd = R(0);
+    }
+    __device__ __forceinline__ bool inside(R vmean, R, R level) const { return vmean <= level; }
+};
+
+// 16-byte vector load of four consecutive reals (weights are read at warp-uniform addresses: one broadcast)
+__device__ __forceinline__ void load4(const float* p, float* o) {
+    const float4 v = __ldg(reinterpret_cast<const float4*>(p));
+    o[0] = v.x; o[1] = v.y; o[2] = v.z; o[3] = v.w;
+}
+__device__ __forceinline__ void load4(const double* p, double* o) {
+    const double2 a = __ldg(reinterpret_cast<const double2*>(p)), b = __ldg(reinterpret_cast<const double2*>(p) + 1);
+    o[0] = a.x; o[1] = a.y; o[2] = b.x; o[3] = b.y;
+}
+
+// Ensemble of value-function networks (levelsets.py:726-778, nn_utils.py:182-199): each member is the flax MLP
+// Dense(nx -> W) softplus, (L-1) x [Dense(W -> W) softplus], Dense(W -> 1), applied to the normalised state,
+//     V_e(x) = v_std * MLP_e((x - x_mean) / x_std) + v_mean            (data_normaliser, nn_utils.py:119-152).
+// lambda(x) = gradient of the ensemble MEAN (levelsets.py:843-852), by one forward and one backward sweep per
+// member; vmean / vstd = mean and (population) standard deviation of V_e(x) over the ensemble (v_meanstd, :789-798).
+// Weights: one flat device array, per member K1[nx][W], b1[W], (L-1) x {K[W][W], b[W]}, Kout[W], bout, 3 pad reals
+// (flax kernels are [in][out]); W % 4 == 0 and nx*W % 4 == 0 keep every row 16-byte aligned.
+// One thread evaluates all members for its own state: the W accumulators live in registers, the hidden activations
+// and their sigmoids in local memory (L1), a weight row is one broadcast vector load per four FMAs.
+constexpr int kNnMaxLayers = 4, kNnMaxNets = 16;
+template <class R, int NX, int W> struct NnCostate {
+    const R* w;
+    int n_nets, n_layers;
+    R x_mean[NX], inv_x_std[NX], v_mean, v_std, n_sigma, sigma_max;
+    static __host__ __device__ constexpr int net_stride(int L) { return NX * W + W + (L - 1) * (W * W + W) + W + 4; }
+
+    static __device__ __forceinline__ void act(R a, R& sp, R& sg) {  // softplus = logaddexp(a, 0) and its derivative
+        const R e = ::exp(-Math<R>::abs(a)), d = Math<R>::div(R(1), R(1) + e);
+        sp = Math<R>::max(a, R(0)) + ::log1p(e);
+        sg = a >= R(0) ? d : e * d;
+    }
+
+    // NOT inlined: the integrator calls it once per stage (7 call sites); inlined, every forward kernel carries seven
+    // copies of the unrolled sweeps and the library takes a quarter of an hour to compile
+    __device__ __noinline__ void eval(const R* x, R* lam, R& vmean, R& vstd) const {
+        using M = Math<R>;
+        R xn[NX], gsum[NX], ve[kNnMaxNets];
+#pragma unroll
+        for (int q = 0; q < NX; q++) { xn[q] = (x[q] - x_mean[q]) * inv_x_std[q]; gsum[q] = R(0); }
+        R h[W], sg[kNnMaxLayers][W];  // dynamically indexed: local memory
+        const int L = n_layers;
+        for (int e = 0; e < n_nets; e++) {
+            const R* p = w + (size_t)e * net_stride(L);
+            R acc[W];
+            // ---- forward
+#pragma unroll
+            for (int j = 0; j < W; j += 4) load4(p + NX * W + j, acc + j);  // bias
+#pragma unroll
+            for (int q = 0; q < NX; q++) {
+#pragma unroll
+                for (int j = 0; j < W; j += 4) {
+                    R k4[4];
+                    load4(p + q * W + j, k4);
+#pragma unroll
+                    for (int c = 0; c < 4; c++) acc[j + c] = M::fma(xn[q], k4[c], acc[j + c]);
+                }
+            }
+#pragma unroll
+            for (int j = 0; j < W; j++) act(acc[j], h[j], sg[0][j]);
+            const R* pl = p + NX * W + W;
+            for (int l = 1; l < L; l++, pl += W * W + W) {
+#pragma unroll
+                for (int j = 0; j < W; j += 4) load4(pl + W * W + j, acc + j);
+#pragma unroll 2
+                for (int i = 0; i < W; i++) {
+                    const R hi = h[i];
+#pragma unroll
+                    for (int j = 0; j < W; j += 4) {
+                        R k4[4];
+                        load4(pl + i * W + j, k4);
+#pragma unroll
+                        for (int c = 0; c < 4; c++) acc[j + c] = M::fma(hi, k4[c], acc[j + c]);
+                    }
+                }
+#pragma unroll
+                for (int j = 0; j < W; j++) act(acc[j], h[j], sg[l][j]);
+            }
+            // output layer (pl now points at Kout) and the seed of the backward sweep g = Kout * softplus'(a_L)
+            R v = __ldg(pl + W);
+#pragma unroll
+            for (int j = 0; j < W; j += 4) {
+                R k4[4];
+                load4(pl + j, k4);
+#pragma unroll
+                for (int c = 0; c < 4; c++) {
+                    v = M::fma(h[j + c], k4[c], v);
+                    acc[j + c] = k4[c] * sg[L - 1][j + c];
+                }
+            }
+            // ---- backward through the hidden layers: g_{l-1}[i] = softplus'(a_{l-1})[i] * sum_j K_l[i][j] g_l[j]
+            for (int l = L - 1; l >= 1; l--) {
+                pl -= W * W + W;
+#pragma unroll 2
+                for (int i = 0; i < W; i++) {
+                    R d0 = R(0), d1 = R(0);
+#pragma unroll
+                    for (int j = 0; j < W; j += 4) {
+                        R k4[4];
+                        load4(pl + i * W + j, k4);
+                        d0 = M::fma(k4[0], acc[j], d0); d1 = M::fma(k4[1], acc[j + 1], d1);
+                        d0 = M::fma(k4[2], acc[j + 2], d0); d1 = M::fma(k4[3], acc[j + 3], d1);
+                    }
+                    h[i] = (d0 + d1) * sg[l - 1][i];
+                }
+#pragma unroll
+                for (int j = 0; j < W; j++) acc[j] = h[j];
+            }
+            // input layer: dMLP/dxn[q] = sum_j K1[q][j] g_0[j]; chain rule of the normaliser
+#pragma unroll
+            for (int q = 0; q < NX; q++) {
+                R d0 = R(0), d1 = R(0);
+#pragma unroll
+                for (int j = 0; j < W; j += 4) {
+                    R k4[4];
+                    load4(p + q * W + j, k4);
+                    d0 = M::fma(k4[0], acc[j], d0); d1 = M::fma(k4[1], acc[j + 1], d1);
+                    d0 = M::fma(k4[2], acc[j + 2], d0); d1 = M::fma(k4[3], acc[j + 3], d1);
+                }
+                gsum[q] += (d0 + d1) * (v_std * inv_x_std[q]);
+            }
+            ve[e] = M::fma(v_std, v, v_mean);
+        }
+        const R inv_e = M::div(R(1), R(n_nets));
+        R m = R(0);
+        for (int e = 0; e < n_nets; e++) m += ve[e];
+        m *= inv_e;
+        R var = R(0);
+        for (int e = 0; e < n_nets; e++) var = M::fma(ve[e] - m, ve[e] - m, var);
+        vmean = m;
+        vstd = M::sqrt(var * inv_e);
+#pragma unroll
+        for (int q = 0; q < NX; q++) lam[q] = gsum[q] * inv_e;
+    }
+    // levelsets.py:897-913: very likely inside the value level set AND the ensemble agrees
+    __device__ __forceinline__ bool inside(R vmean, R vstd, R level) const {
+        return (M_fma(vmean, vstd) <= level) && (vstd <= sigma_max);
+    }
+    __device__ __forceinline__ R M_fma(R vmean, R vstd) const { return Math<R>::fma(n_sigma, vstd, vmean); }
 };
 
 template <class R> struct ForwardIO {
@@ -34,10 +197,10 @@ template <class R> struct ForwardIO {
     long long n;
 };
 
-template <class Sys, class R, int METHOD>
+template <class Sys, class R, int METHOD, class Pol>
 __global__ void __launch_bounds__(128)
-forward_kernel(const typename Sys::Consts sc, const SolveOpts<R> o, const ForwardIO<R> io,
-               const LinearCostate<R, Sys::NX> pol, const TabParams<R> tp) {
+forward_kernel(const typename Sys::Consts sc, const SolveOpts<R> o, const ForwardIO<R> io, const Pol pol,
+               const TabParams<R> tp) {
     using M = Math<R>;
     using TB = Tab<METHOD>;
     constexpr int NX = Sys::NX, NZ = NX + 1, S = TB::S;
@@ -45,21 +208,10 @@ forward_kernel(const typename Sys::Consts sc, const SolveOpts<R> o, const Forwar
     if (i >= n) return;
     const int S1 = o.max_steps + 1;
 
-    // z' = (f(x, u*(x, P (x - x_eq))), l(x, u*)); also the LQR value 1/2 dx'P dx of the state
-    auto field = [&](const R* z, R* k, R& vlqr) {
-        R dx[NX], lam[NX], ld[NX], vd;
-#pragma unroll
-        for (int q = 0; q < NX; q++) dx[q] = z[q] - pol.x_eq[q];
-        R v2 = R(0);
-#pragma unroll
-        for (int r = 0; r < NX; r++) {
-            R a = R(0);
-#pragma unroll
-            for (int q = 0; q < NX; q++) a = M::fma(pol.P[r * NX + q], dx[q], a);
-            lam[r] = a;
-            v2 = M::fma(a, dx[r], v2);
-        }
-        vlqr = R(0.5) * v2;
+    // z' = (f(x, u*(x, lambda(x))), l(x, u*)); also the law's value estimate (mean, spread) at the state
+    auto field = [&](const R* z, R* k, R& vm, R& vs) {
+        R lam[NX], ld[NX], vd;
+        pol.eval(z, lam, vm, vs);
         Sys::template rhs<2>(sc, z, lam, k, vd, ld);
         k[NX] = -vd;
     };
@@ -68,7 +220,7 @@ forward_kernel(const typename Sys::Consts sc, const SolveOpts<R> o, const Forwar
 #pragma unroll
     for (int q = 0; q < NX; q++) z[q] = io.x0[q * n + i];
     z[NX] = R(0);
-    R tprev = o.T0, tnext = M::min(o.T0 + o.dt0, o.T1), vlqr = R(0);
+    R tprev = o.T0, tnext = M::min(o.T0 + o.dt0, o.T1), vlqr = R(0), vsig = R(0);
     int nsteps = 0, nacc = 0, result = 0;
     bool at_dtmin = false;
     const R inf = M::inf();
@@ -84,12 +236,12 @@ forward_kernel(const typename Sys::Consts sc, const SolveOpts<R> o, const Forwar
     for (int q = 0; q < NX; q++) bad = bad || (z[q] != z[q]);
     if (bad) result = PMP_RESULT_NAN;
     save(0);
-    if (TB::FSAL) field(z, k[0], vlqr);
+    if (TB::FSAL) field(z, k[0], vlqr, vsig);
 
     while (tprev < o.T1 && result == 0 && nsteps < o.max_steps) {
         const R dt = tnext - tprev, h = dt * o.dir;
-        if (!TB::FSAL) field(z, k[0], vlqr);
-        R z1[NZ], v1 = R(0);
+        if (!TB::FSAL) field(z, k[0], vlqr, vsig);
+        R z1[NZ], v1 = R(0), s1 = R(0);
 #pragma unroll
         for (int s = 1; s < S; s++) {
             R zs[NZ];
@@ -101,7 +253,7 @@ forward_kernel(const typename Sys::Consts sc, const SolveOpts<R> o, const Forwar
                     if (TB::a(s, j) != 0.0) acc = M::fma(h * tp.template a<TB>(s, j), k[j][q], acc);
                 zs[q] = acc;
             }
-            field(zs, k[s], v1);
+            field(zs, k[s], v1, s1);
             if (TB::FSAL && s == S - 1) {
 #pragma unroll
                 for (int q = 0; q < NZ; q++) z1[q] = zs[q];
@@ -166,14 +318,14 @@ forward_kernel(const typename Sys::Consts sc, const SolveOpts<R> o, const Forwar
                 nan_state = nan_state || (z1[q] != z1[q]);
                 if (TB::FSAL) k[0][q] = k[S - 1][q];
             }
-            if (TB::FSAL) vlqr = v1;
+            if (TB::FSAL) { vlqr = v1; vsig = s1; }
             save(nacc);
         }
-        if (!TB::FSAL && o.event == PMP_EVENT_LQR_VALUE_LE) {  // RK4: the value of the post-step state
+        if (!TB::FSAL && o.event != PMP_EVENT_NONE) {  // RK4: the value of the post-step state
             R kk[NZ];
-            field(z, kk, vlqr);
+            field(z, kk, vlqr, vsig);
         }
-        if (result == 0 && o.event == PMP_EVENT_LQR_VALUE_LE && vlqr <= o.event_level) result = PMP_RESULT_EVENT;
+        if (result == 0 && o.event != PMP_EVENT_NONE && pol.inside(vlqr, vsig, o.event_level)) result = PMP_RESULT_EVENT;
         if (result == 0 && nan_state) result = PMP_RESULT_NAN;
     }
     if (result == 0 && tprev < o.T1) result = PMP_RESULT_MAX_STEPS;
@@ -192,34 +344,117 @@ forward_kernel(const typename Sys::Consts sc, const SolveOpts<R> o, const Forwar
     }
 }
 
+// v_meanstds / vx_meanstd (levelsets.py:789-815): the ensemble at n states
+template <class R, class Pol, int NX>
+__global__ void __launch_bounds__(128) nn_value_kernel(const Pol pol, const R* __restrict__ x_, R* __restrict__ lam_,
+                                                       R* __restrict__ vm_, R* __restrict__ vs_, long long n) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    R x[NX], lam[NX], vm, vs;
+#pragma unroll
+    for (int q = 0; q < NX; q++) x[q] = x_[q * n + i];
+    pol.eval(x, lam, vm, vs);
+#pragma unroll
+    for (int q = 0; q < NX; q++) lam_[q * n + i] = lam[q];
+    vm_[i] = vm;
+    vs_[i] = vs;
+}
+
+template <class R, int NX, class Fill>
+int launch_nn_value_r(const pmp_nn_costate_t* nn, long long n, const void* x, void* lam, void* vm, void* vs, Fill&& fill,
+                      cudaStream_t st) {
+    const unsigned grid = (unsigned)((n + 127) / 128);
+    if (nn->width == 64) {
+        NnCostate<R, NX, 64> pol; fill(pol);
+        nn_value_kernel<R, NnCostate<R, NX, 64>, NX><<<grid, 128, 0, st>>>(pol, (const R*)x, (R*)lam, (R*)vm, (R*)vs, n);
+    } else if (nn->width == 32) {
+        NnCostate<R, NX, 32> pol; fill(pol);
+        nn_value_kernel<R, NnCostate<R, NX, 32>, NX><<<grid, 128, 0, st>>>(pol, (const R*)x, (R*)lam, (R*)vm, (R*)vs, n);
+    } else {
+        return -1000;
+    }
+    return (int)cudaGetLastError();
+}
+
+template <int NX>
+int launch_nn_value(const pmp_nn_costate_t* nn, int dtype, long long n, const void* x, void* lam, void* vm, void* vs,
+                    cudaStream_t st) {
+    if (n == 0) return 0;
+    auto fill = [&](auto& pol) {
+        using R = std::remove_cv_t<std::remove_reference_t<decltype(pol.v_mean)>>;
+        pol.w = (const R*)nn->weights;
+        pol.n_nets = nn->n_nets; pol.n_layers = nn->n_hidden_layers;
+        for (int q = 0; q < NX; q++) { pol.x_mean[q] = R(nn->x_mean[q]); pol.inv_x_std[q] = R(1.0 / nn->x_std[q]); }
+        pol.v_mean = R(nn->v_mean); pol.v_std = R(nn->v_std); pol.n_sigma = R(nn->n_sigma); pol.sigma_max = R(nn->sigma_max);
+    };
+    if (dtype == PMP_F32) return launch_nn_value_r<float, NX>(nn, n, x, lam, vm, vs, fill, st);
+    return launch_nn_value_r<double, NX>(nn, n, x, lam, vm, vs, fill, st);
+}
+
+template <class Sys, class R, class Pol>
+int launch_forward_pol(const pmp_problem_t& p, const pmp_opts_t& o, long long n, const ForwardIO<R>& io, const Pol& pol,
+                       cudaStream_t st) {
+    const unsigned grid = (unsigned)((n + 127) / 128);
+#define PMP_FGO(METHOD)                                                                                          \
+    do {                                                                                                          \
+        using TB = Tab<METHOD>;                                                                                   \
+        forward_kernel<Sys, R, METHOD, Pol><<<grid, 128, 0, st>>>(Sys::make(p), make_solve_opts<R, TB>(o, TB::ORDER, Sys::NX), \
+                                                                  io, pol, TabParams<R>::template make<TB>());   \
+        return (int)cudaGetLastError();                                                                           \
+    } while (0)
+    if (o.method == PMP_METHOD_RK4) PMP_FGO(PMP_METHOD_RK4);
+    if (o.method == PMP_METHOD_TSIT5) PMP_FGO(PMP_METHOD_TSIT5);
+    if (o.method == PMP_METHOD_DOPRI5) PMP_FGO(PMP_METHOD_DOPRI5);
+#undef PMP_FGO
+    return -1000;
+}
+
+template <template <class> class SysT, class R>
+int launch_forward_r(const pmp_problem_t& p, const pmp_opts_t& o, long long n, const void* x0, const double* P,
+                     const double* x_eq, void* z_end, void* ts, void* xs, void* cost, int32_t* a, int32_t* s, int32_t* r,
+                     cudaStream_t st) {
+    using Sys = SysT<R>;
+    constexpr int NX = Sys::NX;
+    ForwardIO<R> io{(const R*)x0, (R*)z_end, (R*)ts, (R*)xs, (R*)cost, a, s, r, n};
+    LinearCostate<R, NX> pol;
+    for (int q = 0; q < NX * NX; q++) pol.P[q] = R(P[q]);
+    for (int q = 0; q < NX; q++) pol.x_eq[q] = R(x_eq ? x_eq[q] : 0.0);
+    return launch_forward_pol<Sys, R>(p, o, n, io, pol, st);
+}
+
+template <template <class> class SysT, class R>
+int launch_forward_nn_r(const pmp_problem_t& p, const pmp_opts_t& o, long long n, const void* x0, const pmp_nn_costate_t* nn,
+                        void* z_end, void* ts, void* xs, void* cost, int32_t* a, int32_t* s, int32_t* r, cudaStream_t st) {
+    using Sys = SysT<R>;
+    constexpr int NX = Sys::NX;
+    ForwardIO<R> io{(const R*)x0, (R*)z_end, (R*)ts, (R*)xs, (R*)cost, a, s, r, n};
+    auto fill = [&](auto& pol) {
+        pol.w = (const R*)nn->weights;
+        pol.n_nets = nn->n_nets; pol.n_layers = nn->n_hidden_layers;
+        for (int q = 0; q < NX; q++) { pol.x_mean[q] = R(nn->x_mean[q]); pol.inv_x_std[q] = R(1.0 / nn->x_std[q]); }
+        pol.v_mean = R(nn->v_mean); pol.v_std = R(nn->v_std); pol.n_sigma = R(nn->n_sigma); pol.sigma_max = R(nn->sigma_max);
+    };
+    if (nn->width == 64) { NnCostate<R, NX, 64> pol; fill(pol); return launch_forward_pol<Sys, R>(p, o, n, io, pol, st); }
+    if (nn->width == 32) { NnCostate<R, NX, 32> pol; fill(pol); return launch_forward_pol<Sys, R>(p, o, n, io, pol, st); }
+    return -1000;
+}
+
 template <template <class> class SysT>
 int launch_forward(const pmp_problem_t& p, const pmp_opts_t& o, long long n, const void* x0, const double* P,
                    const double* x_eq, void* z_end, void* ts, void* xs, void* cost, int32_t* a, int32_t* s, int32_t* r,
                    cudaStream_t st) {
     if (n == 0) return 0;
-    const unsigned grid = (unsigned)((n + 127) / 128);
-#define PMP_FGO(R, METHOD)                                                                                        \
-    do {                                                                                                          \
-        using Sys = SysT<R>;                                                                                      \
-        using TB = Tab<METHOD>;                                                                                   \
-        LinearCostate<R, Sys::NX> pol;                                                                            \
-        for (int q = 0; q < Sys::NX * Sys::NX; q++) pol.P[q] = R(P[q]);                                           \
-        for (int q = 0; q < Sys::NX; q++) pol.x_eq[q] = R(x_eq ? x_eq[q] : 0.0);                                  \
-        ForwardIO<R> io{(const R*)x0, (R*)z_end, (R*)ts, (R*)xs, (R*)cost, a, s, r, n};                          \
-        forward_kernel<Sys, R, METHOD><<<grid, 128, 0, st>>>(Sys::make(p), make_solve_opts<R, TB>(o, TB::ORDER, Sys::NX), \
-                                                             io, pol, TabParams<R>::template make<TB>());        \
-        return (int)cudaGetLastError();                                                                           \
-    } while (0)
-#define PMP_FMETH(R)                                                  \
-    do {                                                              \
-        if (o.method == PMP_METHOD_RK4) PMP_FGO(R, PMP_METHOD_RK4);   \
-        if (o.method == PMP_METHOD_TSIT5) PMP_FGO(R, PMP_METHOD_TSIT5); \
-        if (o.method == PMP_METHOD_DOPRI5) PMP_FGO(R, PMP_METHOD_DOPRI5); \
-    } while (0)
-    if (o.dtype == PMP_F32) PMP_FMETH(float);
-    if (o.dtype == PMP_F64) PMP_FMETH(double);
-#undef PMP_FMETH
-#undef PMP_FGO
+    if (o.dtype == PMP_F32) return launch_forward_r<SysT, float>(p, o, n, x0, P, x_eq, z_end, ts, xs, cost, a, s, r, st);
+    if (o.dtype == PMP_F64) return launch_forward_r<SysT, double>(p, o, n, x0, P, x_eq, z_end, ts, xs, cost, a, s, r, st);
+    return -1000;
+}
+
+template <template <class> class SysT>
+int launch_forward_nn(const pmp_problem_t& p, const pmp_opts_t& o, long long n, const void* x0, const pmp_nn_costate_t* nn,
+                      void* z_end, void* ts, void* xs, void* cost, int32_t* a, int32_t* s, int32_t* r, cudaStream_t st) {
+    if (n == 0) return 0;
+    if (o.dtype == PMP_F32) return launch_forward_nn_r<SysT, float>(p, o, n, x0, nn, z_end, ts, xs, cost, a, s, r, st);
+    if (o.dtype == PMP_F64) return launch_forward_nn_r<SysT, double>(p, o, n, x0, nn, z_end, ts, xs, cost, a, s, r, st);
     return -1000;
 }
 

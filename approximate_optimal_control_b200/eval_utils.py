@@ -1,8 +1,8 @@
 """Host-side mirror of the reference's `eval_utils` (closed-loop cost evaluation, /root/reference/eval_utils.py) for
 costate laws the CUDA path can evaluate.
 
-    closed_loop_eval_lqr(problem_params, algo_params, P_lqr, x0s)     eval_utils.py:10-45 with lambda(x) = P (x - x_eq)
-                                                                      in place of the NN-ensemble costate
+    closed_loop_eval_nn_ensemble(problem_params, algo_params, V_nn, nn_params, x0s)   eval_utils.py:10-45
+    closed_loop_eval_lqr(problem_params, algo_params, P_lqr, x0s)     the same with lambda(x) = P (x - x_eq)
     compute_controlcost(problem_params, all_sols)                     eval_utils.py:101-107
     closed_loop_eval_general(..., ustar_fct, ...)                     eval_utils.py:48-99: an arbitrary jax u*(x) callable
                                                                       cannot enter a compiled kernel -> NotImplementedError
@@ -24,17 +24,33 @@ def closed_loop_eval_general(problem_params, algo_params, ustar_fct, x0s):
                               "laws it has compiled: use closed_loop_eval_lqr (lambda = P (x - x_eq))")
 
 
+def closed_loop_eval_nn_ensemble(problem_params, algo_params, V_nn, nn_params, x0s):
+    """eval_utils.py:10-45: u* from the mean over the ensemble of the networks' input gradients (V_nn.apply_grad: no
+    normaliser).  V_nn is unused (the architecture is read off nn_params); nn_params: flax params with a leading
+    ensemble axis, or a ready nn_costate.NnEnsemble."""
+    from .nn_costate import DataNormaliser, NnEnsemble
+    nx = int(problem_params["nx"])
+    dev = pu._device(x0s)
+    dtype = pu._infer_dtype(algo_params, x0s)
+    ens = nn_params if isinstance(nn_params, NnEnsemble) else NnEnsemble.from_flax(nn_params, DataNormaliser.identity(nx), dev, dtype)
+    return _closed_loop_eval(problem_params, algo_params, x0s, nn=ens)
+
+
 def closed_loop_eval_lqr(problem_params, algo_params, P_lqr, x0s):
+    return _closed_loop_eval(problem_params, algo_params, x0s, P=P_lqr)
+
+
+def _closed_loop_eval(problem_params, algo_params, x0s, P=None, nn=None):
     problem = systems.to_c_problem(problem_params)
     nx = problem.nx
     T, dt = float(algo_params["sim_T"]), float(algo_params["sim_dt"])
     max_steps = int(T / dt)
-    dev = pu._device(x0s)
-    dtype = pu._infer_dtype(algo_params, x0s)
+    dev = pu._device(x0s) if nn is None else nn.weights.device
+    dtype = pu._infer_dtype(algo_params, x0s) if nn is None else nn.weights.dtype
     xs = pu._as_tensor(x0s, dtype, dev).reshape(-1, nx).t().contiguous()
     opts = _capi.make_opts(method=algo_params.get("pontryagin_solver_method", "tsit5"), dtype=pu._code(dtype), adaptive=0,
                            t0=0.0, t1=T, dt0=dt, max_steps=max_steps, save_dense=1, dtmin=0.0, dtmax=0.0)
-    out = pu.forward_batch_soa(problem, opts, xs, P_lqr, problem_params.get("x_eq"))
+    out = pu.forward_batch_soa(problem, opts, xs, P, problem_params.get("x_eq"), nn=nn)
     ys = torch.cat([out["x"], out["cost"][..., None]], dim=-1)[:, 1:]  # SaveAt(steps=True): no t0 slot
     stats = {"num_steps": out["n_steps"], "num_accepted_steps": out["n_accepted"],
              "num_rejected_steps": out["n_steps"] - out["n_accepted"]}

@@ -4,8 +4,9 @@ solve returns and would otherwise round-trip ~8 GB of saved nodes through the ho
 
     select_train_pts(value_interval, sols[, vxx_max_norm])      levelsets.py:667-709
     find_min_l(ys, v_lower, v_upper, problem_params)            levelsets.py:604-628
-    forward_sim_lqr(problem_params, algo_params, P_lqr)(x0)     levelsets.py:818-836 (the step BEFORE the backward solve
-                                                                in batched_oracle, :1201-1215, with the LQR costate)
+    forward_sim_lqr(problem_params, algo_params, P_lqr)(x0)     levelsets.py:818-836
+    forward_sim_nn(problem_params, algo_params, ensemble)(x0)   levelsets.py:838-870   (the step BEFORE the backward solve
+    forward_sim_nn_until_value(..., ensemble, v_k)(x0)          levelsets.py:873-933    in batched_oracle, :1201-1215)
 
 Array work is torch on the GPU; the running cost l(x, u*(x, lambda)) comes from the CUDA f_extended
 kernel (v' = -l, pontryagin_utils.py:449), i.e. from pmp_rhs_batch_cuda.
@@ -70,28 +71,22 @@ def find_min_l(ys: dict, v_lower, v_upper, problem_params: dict):
     return all_ls[inside].min()
 
 
-def forward_sim_lqr(problem_params: dict, algo_params: dict, P_lqr, v_k=None):
-    """levelsets.py:818-836: closed-loop forward simulation x' = f(x, u_star_2d(x, P_lqr (x - x_eq))) with
-    Tsit5 + PIDController(rtol, atol, dtmin=.05), t: 0 -> 10, dt0 = .1, SaveAt(steps, t0), max_steps, throw=False.
-    Returns forward_sim(x0): x0 (nx,) or (N, nx) [replaces jax.vmap] -> Solution with ys (N, S+1, nx), ts, stats, result,
-    y_end = {'x', 'cost'}.  v_k: stop once 1/2 dx'P dx <= v_k (the LQR analogue of forward_sim_nn_until_value,
-    :873-933; result == 1).  Optional algo_params: 'forward_sim_T' (10), 'forward_sim_dtmin' (.05)."""
+def _forward_sim(problem_params, algo_params, *, P=None, nn=None, event=None, level=0.0):
     from .solution import Solution
     problem = systems.to_c_problem(problem_params)
     nx = problem.nx
-    x_eq = problem_params.get("x_eq")
 
     def forward_sim(x0):
-        dev = pu._device(x0)
-        dtype = pu._infer_dtype(algo_params, x0)
+        dev = pu._device(x0) if nn is None else nn.weights.device
+        dtype = pu._infer_dtype(algo_params, x0) if nn is None else nn.weights.dtype
         xt = pu._as_tensor(x0, dtype, dev)
         batched = xt.dim() == 2
         xs = xt.reshape(-1, nx).t().contiguous()
         T = float(algo_params.get("forward_sim_T", 10.0))
-        over = {} if v_k is None else dict(event=_capi.EVENT_LQR_VALUE_LE, event_level=float(v_k))
+        over = {} if event is None else dict(event=event, event_level=float(level))
         opts = pu._solver_opts(algo_params, dtype, t0=0.0, t1=T, dt0=0.1, adaptive=1, save_dense=1,
                                dtmin=float(algo_params.get("forward_sim_dtmin", 0.05)), dtmax=0.0, **over)
-        out = pu.forward_batch_soa(problem, opts, xs, P_lqr, x_eq)
+        out = pu.forward_batch_soa(problem, opts, xs, P, problem_params.get("x_eq"), nn=nn)
         stats = {"num_steps": out["n_steps"], "num_accepted_steps": out["n_accepted"],
                  "num_rejected_steps": out["n_steps"] - out["n_accepted"]}
         sol = Solution(t0=0.0, t1=T, ts=out["ts"], ys=out["x"], y_end={"x": out["z_end"][:nx].t(), "cost": out["z_end"][nx]},
@@ -100,3 +95,25 @@ def forward_sim_lqr(problem_params: dict, algo_params: dict, P_lqr, v_k=None):
         return sol if batched else sol[0]
 
     return forward_sim
+
+
+def forward_sim_lqr(problem_params: dict, algo_params: dict, P_lqr, v_k=None):
+    """levelsets.py:818-836: closed-loop forward simulation x' = f(x, u_star_2d(x, P_lqr (x - x_eq))) with
+    Tsit5 + PIDController(rtol, atol, dtmin=.05), t: 0 -> 10, dt0 = .1, SaveAt(steps, t0), max_steps, throw=False.
+    Returns forward_sim(x0): x0 (nx,) or (N, nx) [replaces jax.vmap] -> Solution with ys (N, S+1, nx), ts, stats, result,
+    y_end = {'x', 'cost'}.  v_k: stop once 1/2 dx'P dx <= v_k (result == 1).  Optional algo_params: 'forward_sim_T' (10),
+    'forward_sim_dtmin' (.05)."""
+    return _forward_sim(problem_params, algo_params, P=P_lqr, event=None if v_k is None else _capi.EVENT_LQR_VALUE_LE,
+                        level=0.0 if v_k is None else v_k)
+
+
+def forward_sim_nn(problem_params: dict, algo_params: dict, ensemble):
+    """levelsets.py:838-870 (vmap=True): as forward_sim_lqr with lambda(x) = gradient of the MEAN of the value-network
+    ensemble (`ensemble`: nn_costate.NnEnsemble, built from the flax params and the data normaliser)."""
+    return _forward_sim(problem_params, algo_params, nn=ensemble)
+
+
+def forward_sim_nn_until_value(problem_params: dict, algo_params: dict, ensemble, v_k):
+    """levelsets.py:873-933: additionally stops (result == 1) once the state is very likely inside the value level set v_k:
+    v_mean + 2 v_std <= v_k and v_std <= 0.5 over the ensemble (ensemble.n_sigma, ensemble.sigma_max)."""
+    return _forward_sim(problem_params, algo_params, nn=ensemble, event=_capi.EVENT_NN_VALUE_UCB_LE, level=v_k)

@@ -162,16 +162,20 @@ def solve_batch_soa(problem: _capi.Problem, opts: _capi.Opts, y_f: torch.Tensor,
     return out
 
 
-def forward_batch_soa(problem: _capi.Problem, opts: _capi.Opts, x0: torch.Tensor, P, x_eq=None, out=None):
-    """Thin wrapper of pmp_forward_batch_cuda: closed-loop forward simulation under lambda(x) = P (x - x_eq) with the
+def forward_batch_soa(problem: _capi.Problem, opts: _capi.Opts, x0: torch.Tensor, P=None, x_eq=None, out=None, nn=None):
+    """Thin wrapper of pmp_forward_batch_cuda / pmp_forward_nn_batch_cuda: closed-loop forward simulation under
+    lambda(x) = P (x - x_eq), or under the costate law of a value-network ensemble (nn: nn_costate.NnEnsemble), with the
     running cost accumulated as an extra state.  x0 [nx, n] CUDA tensor -> dict(z_end [nx+1, n], n_accepted, n_steps,
     result [, ts (n, S+1), x (n, S+1, nx), cost (n, S+1)]).  Asynchronous on the current stream."""
     L = _capi.lib_of(problem)
     assert x0.is_cuda and x0.is_contiguous()
     nx, n = x0.shape
     dev = x0.device
-    Ph = np.ascontiguousarray(np.asarray(P.detach().cpu() if isinstance(P, torch.Tensor) else P, dtype=np.float64).reshape(nx, nx))
-    xe = None if x_eq is None else np.ascontiguousarray(np.asarray(x_eq, dtype=np.float64).reshape(nx))
+    if nn is None:
+        Ph = np.ascontiguousarray(np.asarray(P.detach().cpu() if isinstance(P, torch.Tensor) else P, dtype=np.float64).reshape(nx, nx))
+        xe = None if x_eq is None else np.ascontiguousarray(np.asarray(x_eq, dtype=np.float64).reshape(nx))
+    else:
+        assert nn.weights.dtype == x0.dtype and nn.weights.device == dev and nn.nx == nx
     out = {} if out is None else out
     out.setdefault("z_end", torch.empty((nx + 1, n), dtype=x0.dtype, device=dev))
     for k in ("n_accepted", "n_steps", "result"):
@@ -184,10 +188,16 @@ def forward_batch_soa(problem: _capi.Problem, opts: _capi.Opts, x0: torch.Tensor
         out.setdefault("cost", torch.empty((n, s1), dtype=x0.dtype, device=dev))
         dp = [out["ts"].data_ptr(), out["x"].data_ptr(), out["cost"].data_ptr()]
     with torch.cuda.device(dev):
-        _capi.check(L.pmp_forward_batch_cuda(
-            C.byref(problem), C.byref(opts), n, x0.data_ptr(), Ph.ctypes.data, None if xe is None else xe.ctypes.data,
-            out["z_end"].data_ptr(), *dp, out["n_accepted"].data_ptr(), out["n_steps"].data_ptr(),
-            out["result"].data_ptr(), _stream_ptr(dev)), L)
+        if nn is None:
+            _capi.check(L.pmp_forward_batch_cuda(
+                C.byref(problem), C.byref(opts), n, x0.data_ptr(), Ph.ctypes.data, None if xe is None else xe.ctypes.data,
+                out["z_end"].data_ptr(), *dp, out["n_accepted"].data_ptr(), out["n_steps"].data_ptr(),
+                out["result"].data_ptr(), _stream_ptr(dev)), L)
+        else:
+            c = nn.to_c()
+            _capi.check(L.pmp_forward_nn_batch_cuda(
+                C.byref(problem), C.byref(opts), C.byref(c), n, x0.data_ptr(), out["z_end"].data_ptr(), *dp,
+                out["n_accepted"].data_ptr(), out["n_steps"].data_ptr(), out["result"].data_ptr(), _stream_ptr(dev)), L)
     return out
 
 

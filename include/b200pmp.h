@@ -13,6 +13,8 @@
  *                             (batched at levelsets.py:604-628 find_min_l)
  *   pmp_forward_batch_cuda <- jax.vmap(forward_sim_lqr)           levelsets.py:818-836, and
  *                             closed_loop_eval_general              eval_utils.py:48-99 (linear costate law)
+ *   pmp_forward_nn_batch_cuda <- jax.vmap(forward_sim_nn / forward_sim_nn_until_value)  levelsets.py:838-933,
+ *                             closed_loop_eval_nn_ensemble          eval_utils.py:10-45
  *   pmp_fma_peak_cuda      <- (no reference counterpart) register-resident FMA chain used as the
  *                             roofline denominator of bench.py
  *
@@ -79,8 +81,10 @@ enum {
     PMP_EVENT_VALUE_GE = 1, /* stop once v >= event_level (value level set, problem_params['V_max']) */
     PMP_EVENT_VXX_NORM = 2, /* stop once ||vxx||_F > event_level (algo_params['vxx_max_norm'],
                                pontryagin_utils.py:508-519); needs PMP_FLAG_VXX */
-    PMP_EVENT_LQR_VALUE_LE = 3 /* pmp_forward_batch_cuda only: stop once 1/2 (x-x_eq)'P(x-x_eq) <= event_level
-                                  (inside the value level set; LQR analogue of levelsets.py:897-915) */
+    PMP_EVENT_LQR_VALUE_LE = 3, /* pmp_forward_batch_cuda only: stop once 1/2 (x-x_eq)'P(x-x_eq) <= event_level
+                                   (inside the value level set; LQR analogue of levelsets.py:897-915) */
+    PMP_EVENT_NN_VALUE_UCB_LE = 4 /* pmp_forward_nn_batch_cuda only: stop once v_mean + n_sigma v_std <= event_level
+                                     AND v_std <= sigma_max over the ensemble (levelsets.py:897-913) */
 };
 
 /* per-trajectory result codes, diffrax-compatible (levelsets.py:1218 tests result == 1) */
@@ -221,6 +225,33 @@ int pmp_forward_batch_cuda(const pmp_problem_t *problem, const pmp_opts_t *opts,
                            const double *P, const double *x_eq, void *z_end, void *dense_ts, void *dense_x,
                            void *dense_cost, int32_t *n_accepted, int32_t *n_steps, int32_t *result,
                            void *cuda_stream);
+
+/* Ensemble of value-function networks as a costate law (levelsets.py:726-778,838-933; nn_utils.py:119-199): member e is
+ * the flax MLP Dense(nx -> width) softplus, (n_hidden_layers - 1) x [Dense(width -> width) softplus], Dense(width -> 1)
+ * on the normalised state, V_e(x) = v_std * MLP_e((x - x_mean) / x_std) + v_mean; lambda(x) = grad of mean_e V_e(x).
+ * weights: DEVICE array of the dtype of opts, per member (flax kernels are [in][out], row-major):
+ *     K1 [nx][width], b1 [width], (n_hidden_layers - 1) x { K [width][width], b [width] }, Kout [width], bout, 3 pad reals
+ * 16-byte aligned; width in {32, 64}; n_hidden_layers in 1..4; n_nets in 1..16. */
+typedef struct {
+    int32_t n_nets, n_hidden_layers, width, reserved;
+    const void *weights;
+    double x_mean[16], x_std[16]; /* data_normaliser: first nx entries (identity: 0 and 1)   */
+    double v_mean, v_std;         /* (identity: 0 and 1)                                      */
+    double n_sigma, sigma_max;    /* PMP_EVENT_NN_VALUE_UCB_LE: 2 and 0.5 in the reference    */
+} pmp_nn_costate_t;
+
+/* pmp_forward_batch_cuda with the costate law of a value-network ensemble in place of P (x - x_eq):
+ * jax.vmap(forward_sim_nn) / forward_sim_nn_until_value (levelsets.py:838-933) and, with a constant step,
+ * closed_loop_eval_nn_ensemble (eval_utils.py:10-45).  event: NONE or PMP_EVENT_NN_VALUE_UCB_LE. */
+int pmp_forward_nn_batch_cuda(const pmp_problem_t *problem, const pmp_opts_t *opts, const pmp_nn_costate_t *nn,
+                              int64_t n, const void *x0, void *z_end, void *dense_ts, void *dense_x, void *dense_cost,
+                              int32_t *n_accepted, int32_t *n_steps, int32_t *result, void *cuda_stream);
+
+/* The ensemble itself at n states (v_meanstds / vx_meanstd, levelsets.py:789-815): x [nx][n] -> lam [nx][n] (gradient of
+ * the ensemble mean), v_mean [n], v_std [n] (population std over the members); dtype selects float / double buffers and
+ * weights; problem supplies nx. */
+int pmp_nn_value_batch_cuda(const pmp_problem_t *problem, const pmp_nn_costate_t *nn, int32_t dtype, int64_t n,
+                            const void *x, void *lam, void *v_mean, void *v_std, void *cuda_stream);
 
 /* Dense output, diffrax Solution.evaluate (SaveAt(dense=True), pontryagin_utils.py:504; used at
  * experiment_orbits.py:183-184, misc.py:40-95).  For every query q: y0[:, q] is the saved node at the

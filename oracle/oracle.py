@@ -24,7 +24,7 @@ SYS_FLATQUAD, SYS_ORBITS, SYS_LQR = 0, 1, 2
 RK4, TSIT5, DOPRI5 = 0, 1, 2
 F32, F64 = 0, 1
 INDEP_TIME, INDEP_VALUE = 0, 1
-EVENT_NONE, EVENT_VALUE_GE, EVENT_VXX_NORM, EVENT_LQR_VALUE_LE = 0, 1, 2, 3
+EVENT_NONE, EVENT_VALUE_GE, EVENT_VXX_NORM, EVENT_LQR_VALUE_LE, EVENT_NN_VALUE_UCB_LE = 0, 1, 2, 3, 4
 FLAG_USTAR_LITERAL, FLAG_VXX = 1, 2
 
 
@@ -208,13 +208,41 @@ def vxx_rhs(problem: Problem, x, lam, vxx):
     return jac[0], jac[1], jac[2], jac[3], out
 
 
-def forward_batch(problem: Problem, opts: Opts, x0: np.ndarray, P: np.ndarray, x_eq=None) -> dict:
+class NnCostate(C.Structure):
+    _fields_ = [("n_nets", C.c_int32), ("n_hidden_layers", C.c_int32), ("width", C.c_int32), ("reserved", C.c_int32),
+                ("weights", C.c_void_p), ("x_mean", C.c_double * 16), ("x_std", C.c_double * 16),
+                ("v_mean", C.c_double), ("v_std", C.c_double), ("n_sigma", C.c_double), ("sigma_max", C.c_double)]
+
+
+def nn_struct(weights: np.ndarray, nx, width, n_hidden, n_nets, x_mean=None, x_std=None, v_mean=0.0, v_std=1.0, n_sigma=2.0,
+              sigma_max=0.5) -> NnCostate:
+    """pmp_nn_costate_t over a HOST weight array (keep `weights` alive while the struct is in use)."""
+    c = NnCostate(n_nets=n_nets, n_hidden_layers=n_hidden, width=width, reserved=0, weights=weights.ctypes.data,
+                  v_mean=v_mean, v_std=v_std, n_sigma=n_sigma, sigma_max=sigma_max)
+    for q in range(16):
+        c.x_mean[q] = float(x_mean[q]) if x_mean is not None and q < nx else 0.0
+        c.x_std[q] = float(x_std[q]) if x_std is not None and q < nx else 1.0
+    return c
+
+
+def nn_costate(nn: NnCostate, x: np.ndarray):
+    """x [nx, n] (fp64 weights) -> lam [nx, n], v_mean [n], v_std [n]: the ensemble law of levelsets.py:789-852."""
+    x = np.ascontiguousarray(x, dtype=np.float64)
+    nx, n = x.shape
+    lam, vm, vs = np.empty_like(x), np.empty(n), np.empty(n)
+    L = lib()
+    L.pmp_oracle_nn_costate.argtypes = [C.POINTER(NnCostate), C.c_int32, C.c_int64] + [C.c_void_p] * 4
+    _check(L.pmp_oracle_nn_costate(C.byref(nn), nx, n, x.ctypes.data, lam.ctypes.data, vm.ctypes.data, vs.ctypes.data))
+    return lam, vm, vs
+
+
+def forward_batch(problem: Problem, opts: Opts, x0: np.ndarray, P: np.ndarray = None, x_eq=None, nn: NnCostate = None) -> dict:
     """Forward closed-loop simulation under lambda(x) = P (x - x_eq): x0 [nx, n] -> dict(z_end [nx+1, n],
     n_accepted, n_steps, result [, ts, x, cost])   (levelsets.py:818-836, eval_utils.py:48-99)."""
     dt = _np_dtype(opts.dtype)
     x0 = np.ascontiguousarray(x0, dtype=dt)
     nx, n = x0.shape
-    P = np.ascontiguousarray(P, dtype=np.float64)
+    P = None if P is None else np.ascontiguousarray(P, dtype=np.float64)
     xe = None if x_eq is None else np.ascontiguousarray(x_eq, dtype=np.float64)
     out = {"z_end": np.empty((nx + 1, n), dt), "n_accepted": np.empty(n, np.int32), "n_steps": np.empty(n, np.int32),
            "result": np.empty(n, np.int32)}
@@ -223,8 +251,10 @@ def forward_batch(problem: Problem, opts: Opts, x0: np.ndarray, P: np.ndarray, x
         s1 = opts.max_steps + 1
         out.update(ts=np.empty((n, s1), dt), x=np.empty((n, s1, nx), dt), cost=np.empty((n, s1), dt))
     L = lib()
-    L.pmp_oracle_forward_batch.argtypes = [C.POINTER(Problem), C.POINTER(Opts), C.c_int64] + [C.c_void_p] * 10
-    _check(L.pmp_oracle_forward_batch(C.byref(problem), C.byref(opts), n, ptr(x0), ptr(P), ptr(xe), ptr(out["z_end"]),
+    L.pmp_oracle_forward_batch.argtypes = [C.POINTER(Problem), C.POINTER(Opts), C.c_int64] + [C.c_void_p] * 3 + \
+        [C.POINTER(NnCostate)] + [C.c_void_p] * 7
+    _check(L.pmp_oracle_forward_batch(C.byref(problem), C.byref(opts), n, ptr(x0), ptr(P), ptr(xe),
+                                      None if nn is None else C.byref(nn), ptr(out["z_end"]),
                                       ptr(out.get("ts")), ptr(out.get("x")), ptr(out.get("cost")), ptr(out["n_accepted"]),
                                       ptr(out["n_steps"]), ptr(out["result"])))
     return out

@@ -102,7 +102,8 @@ void ustar_batch_t(const pmp_problem_t& p, int64_t n, const R* x, const R* lam, 
 // with host pointers: x0 [nx][n], z_end [nx+1][n], dense ts [n][S1], x [n][S1][nx], cost [n][S1] (all or none)
 template <class R, class Sys>
 int forward_batch_t(const pmp_problem_t& p, const pmp_opts_t& o, int64_t n, const R* x0, const double* P, const double* x_eq,
-                    R* z_end, R* ts, R* xs, R* cost, int32_t* n_acc, int32_t* n_steps, int32_t* result) {
+                    const pmp_nn_costate_t* nn, R* z_end, R* ts, R* xs, R* cost, int32_t* n_acc, int32_t* n_steps,
+                    int32_t* result) {
     constexpr int NX = Sys::NX;
     Sys sys(p);
     const int64_t S1 = o.max_steps + 1;
@@ -114,7 +115,8 @@ int forward_batch_t(const pmp_problem_t& p, const pmp_opts_t& o, int64_t n, cons
         for (int q = 0; q < NX; q++) a[q] = x0[q * n + i];
         ForwardSink<R> sink;
         if (ts) { sink.ts = ts + i * S1; sink.x = xs + i * S1 * NX; sink.cost = cost + i * S1; }
-        TrajStats st = forward_one<R, Sys>(sys, o, P, x_eq, a, e, sink);
+        TrajStats st = nn ? forward_one<R, Sys>(sys, o, NnLaw<R, NX>{nn}, a, e, sink)
+                          : forward_one<R, Sys>(sys, o, LinearLaw<R, NX>{P, x_eq}, a, e, sink);
         for (int q = 0; q <= NX; q++) z_end[q * n + i] = e[q];
         if (n_acc) n_acc[i] = st.n_accepted;
         if (n_steps) n_steps[i] = st.n_steps;
@@ -212,12 +214,28 @@ int pmp_oracle_vxx_rhs(const pmp_problem_t* p, const double* x, const double* la
     return 0;
 }
 
+// costate law of the ensemble at n points: x [nx][n] -> lam [nx][n], vmean [n], vstd [n]   (fp64 weights)
+int pmp_oracle_nn_costate(const pmp_nn_costate_t* nn, int32_t nx, int64_t n, const double* x, double* lam, double* vmean,
+                          double* vstd) {
+    if (!nn || !x || !lam || !vmean || !vstd) return fail(PMP_ERR_BAD_ARG, "NULL argument");
+    for (int64_t i = 0; i < n; i++) {
+        double xi[16], li[16];
+        for (int q = 0; q < nx; q++) xi[q] = x[q * n + i];
+        if (nx == 6) NnLaw<double, 6>{nn}.eval(xi, li, vmean[i], vstd[i]);
+        else if (nx == 2) NnLaw<double, 2>{nn}.eval(xi, li, vmean[i], vstd[i]);
+        else return fail(PMP_ERR_UNSUPPORTED, "nx must be 2 or 6");
+        for (int q = 0; q < nx; q++) lam[q * n + i] = li[q];
+    }
+    return 0;
+}
+
+// nn != NULL: the costate law of the value-network ensemble (weights in HOST memory, dtype of opts) replaces P (x - x_eq)
 int pmp_oracle_forward_batch(const pmp_problem_t* p, const pmp_opts_t* o, int64_t n, const void* x0, const double* P,
-                             const double* x_eq, void* z_end, void* ts, void* xs, void* cost, int32_t* n_accepted,
-                             int32_t* n_steps, int32_t* result) {
+                             const double* x_eq, const pmp_nn_costate_t* nn, void* z_end, void* ts, void* xs, void* cost,
+                             int32_t* n_accepted, int32_t* n_steps, int32_t* result) {
     if (int e = check(p, o)) return e;
-    if (!o || !x0 || !P || !z_end || n < 0) return fail(PMP_ERR_BAD_ARG, "bad arguments");
-#define FWD(R, SYS) return forward_batch_t<R, SYS<R>>(*p, *o, n, (const R*)x0, P, x_eq, (R*)z_end, (R*)ts, (R*)xs, (R*)cost, n_accepted, n_steps, result)
+    if (!o || !x0 || (!P && !nn) || !z_end || n < 0) return fail(PMP_ERR_BAD_ARG, "bad arguments");
+#define FWD(R, SYS) return forward_batch_t<R, SYS<R>>(*p, *o, n, (const R*)x0, P, x_eq, nn, (R*)z_end, (R*)ts, (R*)xs, (R*)cost, n_accepted, n_steps, result)
     if (o->dtype == PMP_F32) {
         switch (p->system_id) {
             case PMP_SYS_FLATQUAD: FWD(float, Flatquad);

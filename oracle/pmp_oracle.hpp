@@ -19,6 +19,7 @@
 // the op-counting scalar of opcount.hpp (the algorithmic-flop contract of SURVEY.md section 8(d)).
 #pragma once
 #include <cmath>
+#include <vector>
 #include <cstdint>
 #include <limits>
 #include <type_traits>
@@ -720,9 +721,88 @@ template <class R> struct ForwardSink {
     R* ts = nullptr; R* x = nullptr; R* cost = nullptr;
 };
 
-template <class R, class Sys>
-TrajStats forward_one(const Sys& sys, const pmp_opts_t& o, const double* P, const double* x_eq, const R* x0, R* z_end,
-                      ForwardSink<R> sink) {
+// costate law of the LQR value function: lambda = P (x - x_eq), value 1/2 dx'P dx, no spread
+template <class R, int NX> struct LinearLaw {
+    const double* P; const double* x_eq;
+    void eval(const R* x, R* lam, R& vmean, R& vstd) const {
+        R v2 = R(0);
+        for (int r = 0; r < NX; r++) {
+            R a = R(0);
+            for (int q = 0; q < NX; q++) a = a + R(P[r * NX + q]) * (x[q] - R(x_eq ? x_eq[q] : 0.0));
+            lam[r] = a;
+            v2 = v2 + a * (x[r] - R(x_eq ? x_eq[r] : 0.0));
+        }
+        vmean = R(0.5) * v2;
+        vstd = R(0);
+    }
+    bool inside(R vmean, R, double level) const { return r_val(vmean) <= level; }
+};
+
+// costate law of a value-network ensemble (levelsets.py:726-778,838-933; nn_utils.py:119-199), weights in HOST memory with
+// the layout of pmp_nn_costate_t: V_e(x) = v_std MLP_e((x - x_mean)/x_std) + v_mean, MLP = Dense softplus ... Dense(1);
+// lambda = grad of the ensemble mean (forward + backward sweep per member), vmean / vstd = mean / population std of V_e.
+template <class R, int NX> struct NnLaw {
+    const pmp_nn_costate_t* nn;
+    static R softplus(R a) { return r_max(a, R(0)) + R(std::log1p(std::exp(-std::fabs(r_val(a))))); }  // logaddexp(a, 0)
+    static R sigmoid(R a) { return R(1) / (R(1) + R(std::exp(-r_val(a)))); }
+    void eval(const R* x, R* lam, R& vmean, R& vstd) const {
+        const int W = nn->width, L = nn->n_hidden_layers, E = nn->n_nets;
+        const int stride = NX * W + W + (L - 1) * (W * W + W) + W + 4;
+        const R* w = (const R*)nn->weights;
+        std::vector<R> h(W), a(W), g(W), gn(W), sg((size_t)L * W);
+        R xn[NX], gsum[NX], ve[16];
+        for (int q = 0; q < NX; q++) { xn[q] = (x[q] - R(nn->x_mean[q])) / R(nn->x_std[q]); gsum[q] = R(0); }
+        for (int e = 0; e < E; e++) {
+            const R* p = w + (size_t)e * stride;
+            for (int j = 0; j < W; j++) {
+                R acc = p[NX * W + j];
+                for (int q = 0; q < NX; q++) acc = acc + xn[q] * p[q * W + j];
+                h[j] = softplus(acc); sg[j] = sigmoid(acc);
+            }
+            const R* pl = p + NX * W + W;
+            for (int l = 1; l < L; l++, pl += W * W + W) {
+                for (int j = 0; j < W; j++) {
+                    R acc = pl[W * W + j];
+                    for (int i = 0; i < W; i++) acc = acc + h[i] * pl[i * W + j];
+                    a[j] = acc;
+                }
+                for (int j = 0; j < W; j++) { h[j] = softplus(a[j]); sg[(size_t)l * W + j] = sigmoid(a[j]); }
+            }
+            R v = pl[W];
+            for (int j = 0; j < W; j++) { v = v + h[j] * pl[j]; g[j] = pl[j] * sg[(size_t)(L - 1) * W + j]; }
+            for (int l = L - 1; l >= 1; l--) {
+                pl -= W * W + W;
+                for (int i = 0; i < W; i++) {
+                    R d = R(0);
+                    for (int j = 0; j < W; j++) d = d + pl[i * W + j] * g[j];
+                    gn[i] = d * sg[(size_t)(l - 1) * W + i];
+                }
+                g = gn;
+            }
+            for (int q = 0; q < NX; q++) {
+                R d = R(0);
+                for (int j = 0; j < W; j++) d = d + p[q * W + j] * g[j];
+                gsum[q] = gsum[q] + d * (R(nn->v_std) / R(nn->x_std[q]));
+            }
+            ve[e] = R(nn->v_std) * v + R(nn->v_mean);
+        }
+        R m = R(0);
+        for (int e = 0; e < E; e++) m = m + ve[e];
+        m = m / R(E);
+        R var = R(0);
+        for (int e = 0; e < E; e++) var = var + (ve[e] - m) * (ve[e] - m);
+        vmean = m;
+        vstd = r_sqrt(var / R(E));
+        for (int q = 0; q < NX; q++) lam[q] = gsum[q] / R(E);
+    }
+    // levelsets.py:897-913
+    bool inside(R vmean, R vstd, double level) const {
+        return r_val(vmean) + nn->n_sigma * r_val(vstd) <= level && r_val(vstd) <= nn->sigma_max;
+    }
+};
+
+template <class R, class Sys, class Law>
+TrajStats forward_one(const Sys& sys, const pmp_opts_t& o, const Law& law, const R* x0, R* z_end, ForwardSink<R> sink) {
     constexpr int NX = Sys::NX, NZ = NX + 1, NS = 2 * NX + 2, IV = NX + 1;
     const Tableau& tb = *tableau_for(o.method);
     const int S1 = o.max_steps + 1;
@@ -735,18 +815,12 @@ TrajStats forward_one(const Sys& sys, const pmp_opts_t& o, const double* P, cons
     const R T0 = R(o.t0) * dir, T1 = R(o.t1) * dir;
     R tprev = T0, tnext = r_min(T0 + R(o.dt0) * dir, T1);
     const R clip_tol = std::is_same<R, float>::value ? R(1e-6) : R(1e-10);
-    R vlqr = R(0);
-    auto field = [&](const R* zz, R* k, R& v) {
-        R y[NS], dy[NS], v2 = R(0);
+    R vlqr = R(0), vsig = R(0);
+    auto field = [&](const R* zz, R* k, R& v, R& sd) {
+        R y[NS], dy[NS];
         for (int i = 0; i < NS; i++) y[i] = R(0);
-        for (int r = 0; r < NX; r++) {
-            R a = R(0);
-            for (int q = 0; q < NX; q++) a = a + R(P[r * NX + q]) * (zz[q] - R(x_eq ? x_eq[q] : 0.0));
-            y[NX + 2 + r] = a;
-            v2 = v2 + a * (zz[r] - R(x_eq ? x_eq[r] : 0.0));
-            y[r] = zz[r];
-        }
-        v = R(0.5) * v2;
+        for (int r = 0; r < NX; r++) y[r] = zz[r];
+        law.eval(zz, y + NX + 2, v, sd);
         sys.rhs(y, dy);
         for (int i = 0; i < NX; i++) k[i] = dy[i] * dir;
         k[NX] = -dy[IV] * dir;
@@ -762,11 +836,11 @@ TrajStats forward_one(const Sys& sys, const pmp_opts_t& o, const double* P, cons
     for (int i = 0; i < NX; i++) bad0 = bad0 || r_isnan(z[i]);
     if (bad0) st.result = PMP_RESULT_NAN;
     R k[7][NZ];
-    field(z, k[0], vlqr);
+    field(z, k[0], vlqr, vsig);
     bool at_dtmin = false;
     while (r_val(tprev) < r_val(T1) && st.result == 0 && st.n_steps < o.max_steps) {
         const R dt = tnext - tprev;
-        R zs[NZ], z1[NZ], v1 = R(0);
+        R zs[NZ], z1[NZ], v1 = R(0), s1 = R(0);
         const int last = tb.stages - 1;
         for (int i = 1; i < tb.stages; i++) {
             for (int q = 0; q < NZ; q++) {
@@ -774,7 +848,7 @@ TrajStats forward_one(const Sys& sys, const pmp_opts_t& o, const double* P, cons
                 for (int j = 1; j < i; j++) acc = acc + R(tb.a[i][j]) * k[j][q];
                 zs[q] = z[q] + dt * acc;
             }
-            field(zs, k[i], v1);
+            field(zs, k[i], v1, s1);
             if (tb.fsal && i == last)
                 for (int q = 0; q < NZ; q++) z1[q] = zs[q];
         }
@@ -828,14 +902,14 @@ TrajStats forward_one(const Sys& sys, const pmp_opts_t& o, const double* P, cons
             for (int q = 0; q < NZ; q++) z[q] = z1[q];
             if (tb.fsal) {
                 for (int q = 0; q < NZ; q++) k[0][q] = k[last][q];
-                vlqr = v1;
+                vlqr = v1; vsig = s1;
             } else {
-                field(z, k[0], vlqr);
+                field(z, k[0], vlqr, vsig);
             }
             st.n_accepted += 1;
             save(st.n_accepted);
         }
-        if (st.result == 0 && o.event == PMP_EVENT_LQR_VALUE_LE && r_val(vlqr) <= o.event_level) st.result = PMP_RESULT_EVENT;
+        if (st.result == 0 && o.event != PMP_EVENT_NONE && law.inside(vlqr, vsig, o.event_level)) st.result = PMP_RESULT_EVENT;
         if (keep && st.result == 0) {
             bool bad = err_nonfinite;
             for (int q = 0; q < NZ; q++) bad = bad || r_isnan(z[q]);

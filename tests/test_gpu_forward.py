@@ -110,3 +110,98 @@ def test_forward_public_api_and_generated_functor():
     assert float((sol_g.stats["num_steps"] == sol.stats["num_steps"]).float().mean()) >= 0.98
     same = sol_g.stats["num_steps"] == sol.stats["num_steps"]
     assert float((sol_g.y_end["cost"] - sol.y_end["cost"]).abs()[same].max()) <= 1e-6
+
+
+# ---- value-network ensemble as the costate law (levelsets.py:838-933, eval_utils.py:10-45) -------------------------
+def _ensemble(nx, dims, E, dtype, seed=0, scale=1.0):
+    """Random flax-layout parameters (trained weights come out of the reference's training loop, which is out of scope):
+    parity of the simulation does not depend on what the networks represent -- as long as the closed loop is well
+    conditioned: with 3x larger random weights u* chatters between the edges of the input box, a third of the attempts
+    is rejected and two runs of ANY implementation disagree by hundreds of tolerance units."""
+    import torch
+    from approximate_optimal_control_b200 import nn_costate as NC
+    p = NC.init_flax_params(seed, nx, dims, E, scale=scale)
+    norm = NC.DataNormaliser(x_means=np.linspace(-0.1, 0.1, nx), x_stds=np.linspace(0.5, 1.5, nx), v_mean=2.0, v_std=5.0)
+    ens = NC.NnEnsemble.from_flax(p, norm, "cuda", dtype)
+    host = NC.NnEnsemble.from_flax(p, norm, "cpu", dtype).weights.numpy().copy()
+    onn = O.nn_struct(host, nx, dims[0], len(dims), E, norm.x_means, norm.x_stds, norm.v_mean, norm.v_std)
+    return ens, onn, host
+
+
+@pytest.mark.parametrize("nx,dims,E", [(6, (64, 64, 64), 8), (2, (32, 32), 5)])
+def test_nn_value_batch_vs_oracle(nx, dims, E):
+    import torch
+    prob, _ = c_problem("flatquad" if nx == 6 else "orbits")
+    x = np.random.Generator(np.random.PCG64(4)).standard_normal((1000, nx))
+    ens, onn, _w = _ensemble(nx, dims, E, torch.float64)
+    lam, vm, vs = ens.meanstd(prob, x)
+    rl, rm, rs = O.nn_costate(onn, x.T)
+    assert np.allclose(lam.cpu().numpy(), rl.T, rtol=1e-10, atol=1e-11)
+    assert np.allclose(vm.cpu().numpy(), rm, rtol=1e-11, atol=1e-11) and np.allclose(vs.cpu().numpy(), rs, rtol=1e-9, atol=1e-11)
+    ens32, _, _w32 = _ensemble(nx, dims, E, torch.float32)
+    l32, m32, s32 = ens32.meanstd(prob, x)
+    assert np.allclose(l32.cpu().numpy(), rl.T, rtol=2e-4, atol=2e-4) and np.allclose(m32.cpu().numpy(), rm, rtol=1e-5, atol=1e-4)
+    one = ens.meanstd(prob, x[7])
+    assert one[0].shape == (nx,) and torch.allclose(one[0], lam[7])
+
+
+def test_forward_nn_ensemble_fp64_vs_oracle():
+    import torch
+    tol = 1e-6
+    prob, _ = c_problem("flatquad")
+    ens, onn, _w = _ensemble(6, (64, 64, 64), 8, torch.float64)
+    x0 = 0.5 * np.random.Generator(np.random.PCG64(8)).standard_normal((6, 256))
+    opts = _capi.make_opts(method="tsit5", dtype=_capi.F64, rtol=tol, atol=tol, t0=0.0, t1=1.5, dt0=0.1, dtmin=0.0, dtmax=0.0,
+                           max_steps=256, save_dense=1)
+    out = pu.forward_batch_soa(prob, opts, torch.as_tensor(x0, device="cuda").contiguous(), nn=ens)
+    torch.cuda.synchronize()
+    got = {k: v.cpu().numpy() for k, v in out.items()}
+    ref = O.forward_batch(oracle_problem("flatquad"), as_oracle_opts(opts), x0, nn=onn)
+    same = (got["n_steps"] == ref["n_steps"]) & (got["n_accepted"] == ref["n_accepted"])
+    assert same.mean() >= 0.99 and (got["result"] == ref["result"]).all() and (ref["result"] == 0).all()
+    assert scaled_err(got["z_end"], ref["z_end"], tol)[same].max() <= 10.0
+    fin = np.isfinite(ref["x"]) & same[:, None, None]
+    assert (np.isinf(got["x"]) == np.isinf(ref["x"]))[same].all() and np.allclose(got["x"][fin], ref["x"][fin], rtol=1e-5, atol=1e-5)
+
+
+def test_forward_nn_until_value_and_public_api():
+    import torch
+    from approximate_optimal_control_b200 import nn_costate as NC
+    pp, ap = systems.flatquad_problem_params(), dict(systems.flatquad_algo_params(), forward_sim_T=1.5)
+    ens, onn, _w = _ensemble(6, (64, 64, 64), 8, torch.float32, seed=2)
+    x0 = 0.5 * np.random.Generator(np.random.PCG64(9)).standard_normal((200, 6))
+    sol = levelsets.forward_sim_nn(pp, ap, ens)(x0)
+    assert sol.ys.shape == (200, ap["pontryagin_solver_maxsteps"] + 1, 6) and bool((sol.result == 0).all())
+    # the ensemble's upper confidence band along the trajectories decides where forward_sim_nn_until_value stops
+    # (the event is evaluated at the step ends = the saved nodes: v_k = median over the trajectories of the smallest
+    # band any of their nodes reaches, so about half of them stop)
+    nodes = sol.ys.reshape(-1, 6)
+    fin = torch.isfinite(nodes).all(1)
+    lam, vm, vs = ens.meanstd(systems.to_c_problem(pp), nodes[fin])
+    ens.sigma_max = float(vs.max()) * 2
+    ucb = torch.full((nodes.shape[0],), float("inf"), device="cuda")
+    ucb[fin] = vm + 2 * vs
+    ucb[:: sol.ys.shape[1]] = float("inf")  # slot 0 (t0) is not an event point
+    v_k = float(ucb.reshape(200, -1).min(1).values.median()) + 1e-3
+    stop = levelsets.forward_sim_nn_until_value(pp, ap, ens, v_k)(x0)
+    res = stop.result.cpu().numpy()
+    assert (res == 1).any() and (res == 0).any()
+    l2, m2, s2 = ens.meanstd(systems.to_c_problem(pp), stop.y_end["x"])
+    assert bool(((m2 + 2 * s2)[stop.result == 1] <= v_k + 1e-4).all())
+    onn.sigma_max = ens.sigma_max
+    o = _capi.make_opts(dtype=_capi.F32, rtol=ap["pontryagin_solver_rtol"], atol=ap["pontryagin_solver_atol"], t0=0.0, t1=1.5,
+                        dt0=0.1, dtmin=0.05, dtmax=0.0, max_steps=ap["pontryagin_solver_maxsteps"], event=_capi.EVENT_NN_VALUE_UCB_LE,
+                        event_level=v_k)
+    ref = O.forward_batch(oracle_problem("flatquad"), as_oracle_opts(o), x0.T.astype(np.float32), nn=onn)
+    assert (res == ref["result"]).mean() >= 0.97
+    # eval_utils.closed_loop_eval_nn_ensemble on a nu = 1 system: raw input gradients (apply_grad), constant step
+    po = systems.orbits_problem_params()
+    fl = NC.init_flax_params(5, 2, (32, 32), 4, scale=2.0)
+    xo = np.array([0.0, 1.0]) + 0.2 * np.random.Generator(np.random.PCG64(3)).standard_normal((64, 2))
+    ev = {"sim_T": 2.0, "sim_dt": 1 / 32, "dtype": "float64", "nn_ensemble_size": 4}
+    all_sols = eval_utils.closed_loop_eval_nn_ensemble(po, ev, None, fl, xo)
+    assert all_sols.ys.shape == (64, 64, 3)
+    host = NC.NnEnsemble.from_flax(fl, NC.DataNormaliser.identity(2), "cpu", torch.float64).weights.numpy().copy()
+    r2 = O.forward_batch(O.orbits_problem(), O.make_opts(dtype=O.F64, adaptive=0, t0=0.0, t1=2.0, dt0=1 / 32, max_steps=64, dtmin=0.0,
+                                                         dtmax=0.0), xo.T, nn=O.nn_struct(host, 2, 32, 2, 4))
+    assert abs(float(eval_utils.compute_controlcost(po, all_sols)) - r2["z_end"][2].mean()) <= 1e-9 * abs(r2["z_end"][2].mean())

@@ -459,3 +459,38 @@ def test_forward_simulation_event_and_dense_layout():
     assert np.array_equal(out["x"][i, acc].T, xe) and np.array_equal(out["cost"][i, acc], out["z_end"][6])
     assert np.isinf(out["x"][0, acc[0] + 1:]).all() and np.array_equal(out["x"][:, 0].T, x0) and (out["cost"][:, 0] == 0).all()
     assert (np.diff(out["cost"][0, :acc[0] + 1]) > 0).all()  # the running cost is positive
+
+
+def test_nn_costate_law_matches_torch_autograd():
+    """The ensemble costate law (levelsets.py:843-852: gradient of the mean of unnormalise_v(nn(params_e, normalise_x(x))),
+    flax Dense/softplus MLPs, nn_utils.py:182-199) and v_meanstd (:789-798) against torch autograd on the same weights."""
+    import torch
+    from approximate_optimal_control_b200 import nn_costate as NC
+    for nx, dims, E in ((6, (64, 64, 64), 8), (2, (32,), 3), (6, (32, 32, 32, 32), 16)):
+        p = NC.init_flax_params(nx, nx, dims, E)
+        norm = NC.DataNormaliser(x_means=np.linspace(-0.2, 0.3, nx), x_stds=np.linspace(0.5, 2.0, nx), v_mean=3.0, v_std=7.0)
+        ens = NC.NnEnsemble.from_flax(p, norm, "cpu", torch.float64)
+        w = ens.weights.numpy().copy()
+        nn = O.nn_struct(w, nx, dims[0], len(dims), E, norm.x_means, norm.x_stds, norm.v_mean, norm.v_std)
+        x = np.random.Generator(np.random.PCG64(1)).standard_normal((nx, 16))
+        lam, vm, vs = O.nn_costate(nn, x)
+        P = p["params"]
+
+        def V(xx):
+            h0 = (xx - torch.tensor(norm.x_means)) / torch.tensor(norm.x_stds)
+            outs = []
+            for e in range(E):
+                h = h0
+                for i in range(len(dims)):
+                    h = torch.nn.functional.softplus(h @ torch.tensor(P[f"Dense_{i}"]["kernel"][e]) + torch.tensor(P[f"Dense_{i}"]["bias"][e]))
+                o = h @ torch.tensor(P[f"Dense_{len(dims)}"]["kernel"][e]) + torch.tensor(P[f"Dense_{len(dims)}"]["bias"][e])
+                outs.append(o.squeeze() * norm.v_std + norm.v_mean)
+            return torch.stack(outs)
+
+        for i in range(16):
+            xx = torch.tensor(x[:, i], requires_grad=True)
+            ve = V(xx)
+            g, = torch.autograd.grad(ve.mean(), xx)
+            assert np.allclose(g.numpy(), lam[:, i], rtol=1e-10, atol=1e-12)
+            assert abs(ve.mean().item() - vm[i]) <= 1e-11 * (1 + abs(vm[i]))
+            assert abs(ve.std(unbiased=False).item() - vs[i]) <= 1e-10 * (1 + abs(vs[i]))
