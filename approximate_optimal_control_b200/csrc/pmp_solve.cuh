@@ -25,6 +25,7 @@
 //     It still counts as one leaf of the RMS error norm (its own error is ~1e-9 of the tolerance).
 #pragma once
 #include <cstdlib>
+#include <type_traits>
 
 #include "pmp_common.cuh"
 #include "pmp_systems.cuh"
@@ -145,16 +146,21 @@ __device__ __forceinline__ void field(const typename Sys::Consts& sc, const R* y
 }
 
 // rows of the public [NS][n] layout: x -> 0.., t -> NX, v -> NX+1, vx -> NX+2..
+// rd(row) reads one row of the trajectory's terminal state (from global memory, or from its prefetch slot)
+template <class R, int NX, bool VALUE, class Rd>
+__device__ __forceinline__ void load_state_rd(Rd&& rd, R* y, R& clock0, R& aux_fixed) {
+#pragma unroll
+    for (int q = 0; q < NX; q++) y[q] = rd(q);
+#pragma unroll
+    for (int q = 0; q < NX; q++) y[NX + q] = rd(NX + 2 + q);
+    const R t = rd(NX), v = rd(NX + 1);
+    if (VALUE) { y[2 * NX] = t; clock0 = v; aux_fixed = R(0); }
+    else { y[2 * NX] = v; clock0 = R(0); aux_fixed = t; }
+}
 template <class R, int NX, bool VALUE>
 __device__ __forceinline__ void load_state(const R* __restrict__ y_f, long long n, long long i, R* y, R& clock0,
                                            R& aux_fixed) {
-#pragma unroll
-    for (int q = 0; q < NX; q++) y[q] = __ldg(y_f + q * n + i);
-#pragma unroll
-    for (int q = 0; q < NX; q++) y[NX + q] = __ldg(y_f + (NX + 2 + q) * n + i);
-    const R t = __ldg(y_f + NX * n + i), v = __ldg(y_f + (NX + 1) * n + i);
-    if (VALUE) { y[2 * NX] = t; clock0 = v; aux_fixed = R(0); }
-    else { y[2 * NX] = v; clock0 = R(0); aux_fixed = t; }
+    load_state_rd<R, NX, VALUE>([&](int row) { return __ldg(y_f + row * n + i); }, y, clock0, aux_fixed);
 }
 
 // ---- prep kernel: k1 = field(y_f) for every trajectory (coalesced), and reset of the work counter
@@ -202,7 +208,7 @@ static __global__ void reset_counter_kernel(unsigned long long* counter) { *coun
 // nodes of its current group in a shared-memory ring; when a lane completes a group the WARP writes
 // it with one store instruction per leaf (whole sectors, no fill).  When a trajectory retires, its
 // last, partial group is completed with the +inf padding that follows it anyway, and the rest of
-// the tail is written with 16-byte streaming stores.  Only the first and last sector of a
+// the tail leaves as bulk copies executed by the TMA unit (bulk_fill below).  Only the first and last sector of a
 // trajectory's row can be partial (rows of S1 slots are not sector aligned).
 constexpr int kGrpV = 4;  // slots per vector-leaf group
 constexpr int kGrpS = 8;  // slots per scalar-leaf group
@@ -213,34 +219,10 @@ template <class R, int NX> struct StageLayout {
     static_assert(kGrpV * NX <= 32 && 3 * kGrpS <= 32, "one warp store per group");
     static constexpr int XS = (kGrpV * NX) | 1;  // per-owner stride, odd => conflict-free owner writes
     static constexpr int SS = (kGrpS * 3) | 1;
-    static constexpr int WORDS_PER_WARP = 32 * (2 * XS + SS);
+    static constexpr int ORD = 2 * 32 * sizeof(int) / sizeof(R);  // two rank -> owner-lane tables (see flush_groups)
+    static constexpr int WORDS_PER_WARP = 32 * (2 * XS + SS) + ORD;
     static constexpr size_t bytes_per_warp() { return (size_t)WORDS_PER_WARP * sizeof(R); }
 };
-
-// p[0, len) = val, written by the whole warp with 16-byte stores where alignment allows (p is only
-// element-aligned; len is small: at most (max_steps+1)*nx).  32-bit index arithmetic throughout;
-// cache-streaming stores (evict-first in L2): the tail is never read back by this kernel and must not
-// push the partially written node lines out of L2.
-template <class R>
-__device__ __forceinline__ void warp_fill(R* __restrict__ p, int len, int lane, R val) {
-    constexpr int V = 16 / sizeof(R);
-    int head = (int)((V - (((uintptr_t)p / sizeof(R)) & (V - 1))) & (V - 1));  // elements to the next 16-B boundary
-    head = head < len ? head : len;
-    if (lane < head) __stcs(p + lane, val);
-    R* const pb = p + head;
-    const int body = (len - head) & ~(V - 1);
-    if (sizeof(R) == 4) {
-        const float4 v = make_float4((float)val, (float)val, (float)val, (float)val);
-#pragma unroll 1
-        for (int e = 4 * lane; e < body; e += 128) __stcs(reinterpret_cast<float4*>(pb + e), v);
-    } else {
-        const double2 v = make_double2((double)val, (double)val);
-#pragma unroll 1
-        for (int e = 2 * lane; e < body; e += 64) __stcs(reinterpret_cast<double2*>(pb + e), v);
-    }
-    const int rest = len - head - body;
-    if (lane < rest) __stcs(pb + body + lane, val);
-}
 
 // store one node (global slot g) of this lane's trajectory in its rings
 template <class R, int NX>
@@ -281,9 +263,103 @@ __device__ __forceinline__ void write_group_s(const DensePtrs<R>& d, const R* sS
         const unsigned slot = G * kGrpS + j;
         if (slot >= row_lo && slot < row_hi) {
             const R pad = f == 0 ? inf_ts : inf;
-            d.p[f][slot] = slot < valid_hi ? sSC[o * SL::SS + j * 3 + f] : pad;  // leaves 0,1,2 = ts,t,v
+            // (select, not d.p[f]: a dynamically indexed kernel parameter is copied to LOCAL memory, and those loads
+            //  were 8 % of the dense kernel's stall samples)
+            R* const leaf = f == 0 ? d.p[0] : (f == 1 ? d.p[1] : d.p[2]);  // leaves 0,1,2 = ts,t,v
+            leaf[slot] = slot < valid_hi ? sSC[o * SL::SS + j * 3 + f] : pad;
         }
     }
+}
+
+// ---- +inf padding by the TMA unit ------------------------------------------------------------------------
+// 85 % of the dense output is padding (mean 26 of 129 slots hold nodes).  Written by the warp with 16-byte stores it
+// cost ~370 instructions per step attempt (five fills per retiring trajectory, each with its own address and
+// remainder logic) and every one of those stores went through the SM's load/store path in front of the refill's
+// loads.  Instead every CTA keeps two 4 KB shared-memory blocks of +inf (and dir*inf for `ts`) and a retiring
+// trajectory's tails leave as BULK ASYNC COPIES shared -> global (cp.async.bulk, SASS UBLKCP): one instruction per
+// leaf, issued by one lane each, executed by the TMA unit.  Tails start on 16-byte boundaries (they begin where
+// the last sector-aligned group ends); the <= 3 reals that do not fill a 16-byte unit at the end of a row are stored
+// directly.
+constexpr int kInfBytes = 4096;
+// (L2 evict-first: the padding is never read back by this kernel and must not push the inputs of the refill out of L2)
+__device__ __forceinline__ void bulk_s2g(void* dst, const void* src_smem, unsigned bytes) {
+    const unsigned s = (unsigned)__cvta_generic_to_shared(src_smem);
+    unsigned long long pol;
+    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group.L2::cache_hint [%0], [%1], %2, %3;" ::"l"(dst), "r"(s),
+                 "r"(bytes), "l"(pol)
+                 : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+// dst[0, len) = val for one thread: 16-byte units by bulk copies from the shared-memory block `blk` (kInfBytes of
+// val), the remainder directly.  dst must be 16-byte aligned.
+template <class R> __device__ __forceinline__ void bulk_fill(R* dst, int len, const R* blk, R val) {
+    constexpr int VEC = 16 / sizeof(R), BLKW = kInfBytes / sizeof(R);
+    const int body = len & ~(VEC - 1);
+    for (int e = 0; e < body; e += BLKW) {
+        const int m = body - e < BLKW ? body - e : BLKW;
+        bulk_s2g(dst + e, blk, (unsigned)(m * sizeof(R)));
+    }
+    for (int e = body; e < len; e++) __stcs(dst + e, val);
+}
+
+// In-loop flush of the groups completed by the last attempt.  About 7 of a warp's 32 lanes complete a vector group
+// and 3.4 a scalar group per attempt; written one owner at a time (write_group_*: 24 lanes, 4-byte stores) those
+// loops were 40 % of the dense kernel's stall samples and a third of its instructions.  Here a group leaves as
+// 16-byte chunks: CH chunks per owner and leaf, 32 / CH owners per store instruction (fp32 flatquad: a 96-byte vector
+// group = 6 chunks, 5 owners at once).  Owners publish their lane in a rank table; lane (k, c) then serves chunk c of
+// the k-th ready owner.  Only groups that lie wholly inside their row may come here.
+template <class R, int NX>
+__device__ __forceinline__ void flush_groups(const DensePtrs<R>& d, const R* sX, const R* sVX, const R* sSC, int* sOrd,
+                                             int lane, bool rdy_v, bool rdy_s, unsigned g_cur) {
+    using SL = StageLayout<R, NX>;
+    constexpr unsigned FULL = 0xffffffffu;
+    constexpr int VEC = 16 / sizeof(R);                       // reals per chunk
+    constexpr int CHV = kGrpV * NX / VEC, OWV = 32 / CHV;     // vector leaves: chunks per owner, owners per instruction
+    constexpr int CHL = kGrpS / VEC, CHS = 3 * CHL, OWS = 32 / CHS;  // scalar leaves: ts, t, v together
+    static_assert((kGrpV * NX) % VEC == 0 && kGrpS % VEC == 0 && CHV <= 32 && CHS <= 32, "16-byte chunks");
+    const unsigned mv = __ballot_sync(FULL, rdy_v), ms = __ballot_sync(FULL, rdy_s);
+    if (!(mv | ms)) return;
+    const unsigned lt = (1u << lane) - 1u;
+    if (rdy_v) sOrd[__popc(mv & lt)] = lane;
+    if (rdy_s) sOrd[32 + __popc(ms & lt)] = lane;
+    __syncwarp();  // rank tables and the owners' ring stores are visible to the serving lanes
+    typedef typename std::conditional<sizeof(R) == 4, float4, double2>::type V16;
+    {
+        const int nv = __popc(mv), k = lane / CHV, c = lane - k * CHV;
+        for (int base = 0; base < nv; base += OWV) {
+            const bool act = k < OWV && base + k < nv;
+            const int o = act ? sOrd[base + k] : lane;
+            const unsigned G = __shfl_sync(FULL, g_cur, o) / kGrpV;
+            if (act) {
+                R a[VEC], b[VEC];
+#pragma unroll
+                for (int e = 0; e < VEC; e++) { a[e] = sX[o * SL::XS + VEC * c + e]; b[e] = sVX[o * SL::XS + VEC * c + e]; }
+                const size_t off = (size_t)G * (kGrpV * NX) + VEC * c;
+                *reinterpret_cast<V16*>(d.p[kDenseX] + off) = *reinterpret_cast<const V16*>(a);
+                *reinterpret_cast<V16*>(d.p[kDenseVx] + off) = *reinterpret_cast<const V16*>(b);
+            }
+        }
+    }
+    {
+        const int ns = __popc(ms), k = lane / CHS, i = lane - k * CHS, f = i / CHL, c = i - f * CHL;
+        R* const leaf = f == 0 ? d.p[0] : (f == 1 ? d.p[1] : d.p[2]);  // ts, t, v
+        for (int base = 0; base < ns; base += OWS) {
+            const bool act = k < OWS && base + k < ns;
+            const int o = act ? sOrd[32 + base + k] : lane;
+            const unsigned G = __shfl_sync(FULL, g_cur, o) / kGrpS;
+            if (act) {
+                R a[VEC];
+#pragma unroll
+                for (int e = 0; e < VEC; e++) a[e] = sSC[o * SL::SS + (VEC * c + e) * 3 + f];
+                *reinterpret_cast<V16*>(leaf + (size_t)G * kGrpS + VEC * c) = *reinterpret_cast<const V16*>(a);
+            }
+        }
+    }
+    __syncwarp();  // the rings may be overwritten by the next attempt's nodes only after every chunk has been read
 }
 
 // ---- the integrator -----------------------------------------------------------------------------
@@ -326,12 +402,26 @@ solve_kernel(const typename Sys::Consts sc, const SolveOpts<R> o, const SolveIO<
     // dense write-out staging (shared memory, one private region per warp)
     extern __shared__ __align__(16) unsigned char pmp_smem[];
     R* sX = nullptr; R* sVX = nullptr; R* sSC = nullptr;
+    int* sOrd = nullptr;
     unsigned g_cur = 0, row0 = 0;           // global slot of the newest node; first slot of the row
     bool ready_v = false, ready_s = false;  // the newest node completed a vector / scalar group
+    const R* sInf = nullptr;  // DENSE: kInfBytes of +inf, then kInfBytes of dir*inf (the padding of ts)
+    constexpr size_t kInfWords = DENSE ? 2 * kInfBytes / sizeof(R) : 0;
+    if (DENSE) {
+        R* blk = reinterpret_cast<R*>(pmp_smem);
+        for (int e = threadIdx.x; e < kInfBytes / (int)sizeof(R); e += BLK) {
+            blk[e] = M::inf();
+            blk[kInfBytes / sizeof(R) + e] = M::inf() * o.dir;
+        }
+        fence_async_smem();  // generic-proxy writes -> visible to the async proxy (TMA) that reads the blocks
+        __syncthreads();
+        sInf = blk;
+    }
     if (DENSE) {
         using SL = StageLayout<R, NX>;
-        R* wbase = reinterpret_cast<R*>(pmp_smem) + (size_t)(threadIdx.x >> 5) * SL::WORDS_PER_WARP;
+        R* wbase = reinterpret_cast<R*>(pmp_smem) + kInfWords + (size_t)(threadIdx.x >> 5) * SL::WORDS_PER_WARP;
         sX = wbase; sVX = wbase + 32 * SL::XS; sSC = wbase + 64 * SL::XS;
+        sOrd = reinterpret_cast<int*>(wbase + 32 * (2 * SL::XS + SL::SS));
     }
     // VXX: this thread's column of [V | k1 .. kS] (entry e at sV[e * BLK]); the newest V is a pending dense node
     R* sV = nullptr;
@@ -339,7 +429,7 @@ solve_kernel(const typename Sys::Consts sc, const SolveOpts<R> o, const SolveIO<
     bool new_node = false;
     if (VXX) {
         const size_t off = DENSE ? (size_t)(BLK / 32) * StageLayout<R, NX>::WORDS_PER_WARP : 0;
-        sV = reinterpret_cast<R*>(pmp_smem) + off + threadIdx.x;
+        sV = reinterpret_cast<R*>(pmp_smem) + kInfWords + off + threadIdx.x;
     }
     // the warp writes the pending V_xx nodes of the lanes in `mask` (slot g_cur of each): 36 contiguous reals
     auto write_vxx_nodes = [&](unsigned mask) {
@@ -408,6 +498,49 @@ solve_kernel(const typename Sys::Consts sc, const SolveOpts<R> o, const SolveIO<
                 }
                 __syncwarp();
             }
+            // start trajectory i on this lane
+            auto start_traj = [&](long long i) {
+                idx = i;
+                load_state<R, NX, VALUE>(io.y_f, n, idx, y, clock0, aux_fixed);
+                if (TB::FSAL) {
+#pragma unroll
+                    for (int q = 0; q < ND; q++) k[0][q] = __ldg(io.k1 + q * n + idx);
+                }
+                // diffrax: t0, t1, dt0 are multiplied by the direction; tnext = min(t0+dt0, t1)
+                const R T0 = VALUE ? clock0 * o.dir : o.T0;
+                clock0 = T0 * o.dir;  // keep the un-normalised start for the t output
+                tprev = T0;
+                tnext = M::min(T0 + o.dt0, o.T1);
+                nsteps = 0; nacc = 0; result = 0; at_dtmin = false;
+                has_work = true;
+                bool bad = false;
+#pragma unroll
+                for (int q = 0; q < ND; q++) bad = bad || (y[q] != y[q]);
+                if (VXX) {
+                    R n2 = R(0);
+#pragma unroll
+                    for (int q = 0; q < NV; q++) {
+                        const R v = __ldg(io.y_f + (NS + MP::pub(q)) * n + idx);
+                        sV[q * BLK] = v;
+                        n2 = M::fma(MP::offdiag(q) ? v + v : v, v, n2);
+                        if (TB::FSAL) sV[(NV + q) * BLK] = __ldg(io.k1 + (ND + q) * n + idx);
+                    }
+                    bad = bad || (n2 != n2);
+                    vnorm2 = n2;
+                    new_node = DENSE;
+                }
+                // NaN terminal state (levelsets.py:1233): retire at once with result 4
+                finished = bad || !(tprev < o.T1);
+                if (bad) result = PMP_RESULT_NAN;
+                if (DENSE) {  // slot 0 = the terminal state (SaveAt(t0=True))
+                    row0 = (unsigned)(idx * S1);
+                    g_cur = row0;
+                    const R c0 = tprev * o.dir;
+                    stage_put<R, NX>(sX, sVX, sSC, lane, g_cur, y, y + NX, c0, VALUE ? y[AUX] : aux_fixed, VALUE ? c0 : y[AUX]);
+                    ready_v = (g_cur & (kGrpV - 1)) == kGrpV - 1;
+                    ready_s = (g_cur & (kGrpS - 1)) == kGrpS - 1;
+                }
+            };
             // hand out new trajectories to the lanes in `want`, in rank order
             while (want && !exhausted) {
                 if (w_next >= w_end) {
@@ -417,75 +550,50 @@ solve_kernel(const typename Sys::Consts sc, const SolveOpts<R> o, const SolveIO<
                     w_next = (long long)base;
                     w_end = w_next + kChunk < n ? w_next + kChunk : n;
                     if (w_next >= n) { exhausted = true; break; }
+                    if (DENSE) {
+                        // the chunk's terminal states and k1 rows are needed over the next ~50 attempts: pull them
+                        // into L2 now (the refill's loads otherwise miss to DRAM behind the padding's write traffic)
+                        constexpr int PER = kChunk * sizeof(R) / 128;  // 128-byte lines per row of the chunk
+                        for (int q = lane; q < (NS + ND) * PER; q += 32) {
+                            const int row = q / PER, part = q - row * PER;
+                            const R* a = row < NS ? io.y_f + (size_t)row * n : io.k1 + (size_t)(row - NS) * n;
+                            if (w_next + part * (long long)(128 / sizeof(R)) < n)
+                                asm volatile("prefetch.global.L2::evict_last [%0];" ::"l"(a + w_next + part * (128 / sizeof(R))));
+                        }
+                    }
                 }
                 const int avail = (int)(w_end - w_next);
                 const bool mine = (want >> lane) & 1u;
                 const int rank = __popc(want & ((1u << lane) - 1u));
                 const bool take = mine && rank < avail;
-                if (take) {
-                    idx = w_next + rank;
-                    load_state<R, NX, VALUE>(io.y_f, n, idx, y, clock0, aux_fixed);
-                    if (TB::FSAL) {
-#pragma unroll
-                        for (int q = 0; q < ND; q++) k[0][q] = __ldg(io.k1 + q * n + idx);
-                    }
-                    // diffrax: t0, t1, dt0 are multiplied by the direction; tnext = min(t0+dt0, t1)
-                    const R T0 = VALUE ? clock0 * o.dir : o.T0;
-                    clock0 = T0 * o.dir;  // keep the un-normalised start for the t output
-                    tprev = T0;
-                    tnext = M::min(T0 + o.dt0, o.T1);
-                    nsteps = 0; nacc = 0; result = 0; at_dtmin = false;
-                    has_work = true;
-                    bool bad = false;
-#pragma unroll
-                    for (int q = 0; q < ND; q++) bad = bad || (y[q] != y[q]);
-                    if (VXX) {
-                        R n2 = R(0);
-#pragma unroll
-                        for (int q = 0; q < NV; q++) {
-                            const R v = __ldg(io.y_f + (NS + MP::pub(q)) * n + idx);
-                            sV[q * BLK] = v;
-                            n2 = M::fma(MP::offdiag(q) ? v + v : v, v, n2);
-                            if (TB::FSAL) sV[(NV + q) * BLK] = __ldg(io.k1 + (ND + q) * n + idx);
-                        }
-                        bad = bad || (n2 != n2);
-                        vnorm2 = n2;
-                        new_node = DENSE;
-                    }
-                    // NaN terminal state (levelsets.py:1233): retire at once with result 4
-                    finished = bad || !(tprev < o.T1);
-                    if (bad) result = PMP_RESULT_NAN;
-                    if (DENSE) {  // slot 0 = the terminal state (SaveAt(t0=True))
-                        row0 = (unsigned)(idx * S1);
-                        g_cur = row0;
-                        const R c0 = tprev * o.dir;
-                        stage_put<R, NX>(sX, sVX, sSC, lane, g_cur, y, y + NX, c0, VALUE ? y[AUX] : aux_fixed, VALUE ? c0 : y[AUX]);
-                        ready_v = (g_cur & (kGrpV - 1)) == kGrpV - 1;
-                        ready_s = (g_cur & (kGrpS - 1)) == kGrpS - 1;
-                    }
-                }
+                if (take) start_traj(w_next + rank);
                 const unsigned took = __ballot_sync(FULL, take);
                 want &= ~took;
                 w_next += __popc(took);
             }
             if (DENSE) {
-                // +inf tails of the retired trajectories (ts: dir*inf), from the end of their last group to
-                // the end of the row, 16-byte streaming stores; every slot of the output is written once.
+                // +inf tails of the retired trajectories (ts: dir*inf), from the end of their last group to the end of
+                // the row: lane f issues the bulk copy of leaf f (bulk_fill); every slot of the output is written once.
                 __syncwarp();
                 unsigned rm = pad_mask;
                 const R inf = M::inf();
+                constexpr int NLEAF = VXX ? 6 : 5;
                 while (rm) {
                     const int src = __ffs(rm) - 1;
                     rm &= rm - 1;
                     const unsigned gl = __shfl_sync(FULL, pad_g, src), row_hi = __shfl_sync(FULL, pad_row0, src) + S1;
                     const unsigned pv = min((gl / kGrpV + 1) * kGrpV, row_hi), ps = min((gl / kGrpS + 1) * kGrpS, row_hi);
-                    warp_fill<R>(io.dense.p[kDenseTs] + ps, (int)(row_hi - ps), lane, inf * o.dir);
-                    warp_fill<R>(io.dense.p[kDenseT] + ps, (int)(row_hi - ps), lane, inf);
-                    warp_fill<R>(io.dense.p[kDenseV] + ps, (int)(row_hi - ps), lane, inf);
-                    warp_fill<R>(io.dense.p[kDenseX] + (size_t)pv * NX, (int)(row_hi - pv) * NX, lane, inf);
-                    warp_fill<R>(io.dense.p[kDenseVx] + (size_t)pv * NX, (int)(row_hi - pv) * NX, lane, inf);
-                    if (VXX) warp_fill<R>(io.dense.p[kDenseVxx] + (size_t)(gl + 1) * NVP, (int)(row_hi - gl - 1) * NVP, lane, inf);
+                    if (lane < NLEAF) {
+                        const bool sc = lane < 3, vx = lane == 5;  // leaves 0..2 = ts, t, v; 3, 4 = x, vx; 5 = vxx
+                        const size_t start = sc ? (size_t)ps : (vx ? (size_t)(gl + 1) * NVP : (size_t)pv * NX);
+                        const int len = sc ? (int)(row_hi - ps) : (vx ? (int)(row_hi - gl - 1) * NVP : (int)(row_hi - pv) * NX);
+                        R* const leaf = lane == 0 ? io.dense.p[0] : lane == 1 ? io.dense.p[1] : lane == 2 ? io.dense.p[2]
+                                      : lane == 3 ? io.dense.p[3] : lane == 4 ? io.dense.p[4] : io.dense.p[5];
+                        bulk_fill<R>(leaf + start, len, lane == 0 ? sInf + kInfBytes / sizeof(R) : sInf,
+                                     lane == 0 ? inf * o.dir : inf);
+                    }
                 }
+                if (pad_mask) bulk_commit();
             }
         }
         if (!__any_sync(FULL, has_work)) break;
@@ -494,8 +602,12 @@ solve_kernel(const typename Sys::Consts sc, const SolveOpts<R> o, const SolveIO<
             // write the groups completed by the previous attempt or by the refill above.  This is the
             // only in-loop call site (code size: the loop body must stay inside the I-cache).
             const R inf = M::inf();
-            __syncwarp();  // the owners' ring stores must be visible to the lanes that write the group
-            unsigned mv = __ballot_sync(FULL, ready_v), ms = __ballot_sync(FULL, ready_s);
+            // Groups that lie wholly inside their trajectory's row (all but the first of a row) leave with 16-byte
+            // stores, several owners per instruction (flush_groups); the others take the per-owner path below.
+            const bool edge_v = ready_v && (g_cur / kGrpV) * kGrpV < row0, edge_s = ready_s && (g_cur / kGrpS) * kGrpS < row0;
+            flush_groups<R, NX>(io.dense, sX, sVX, sSC, sOrd, lane, ready_v && !edge_v, ready_s && !edge_s, g_cur);
+            unsigned mv = __ballot_sync(FULL, edge_v), ms = __ballot_sync(FULL, edge_s);
+            if (mv | ms) __syncwarp();  // the owners' ring stores must be visible to the lanes that write the group
             while (mv) {
                 const int src = __ffs(mv) - 1;
                 mv &= mv - 1;
@@ -760,6 +872,7 @@ solve_kernel(const typename Sys::Consts sc, const SolveOpts<R> o, const SolveIO<
             finished = !more || result != 0;
         }
     }
+    if (DENSE) bulk_wait_all();  // the CTA's +inf blocks must outlive every bulk copy that reads them
 }
 
 // ---- host-side launcher for one system ----------------------------------------------------------
@@ -805,7 +918,7 @@ int launch_one(const pmp_problem_t& p, const pmp_opts_t& o, long long n, const v
     cudaError_t e = cudaGetDevice(&dev);
     if (e != cudaSuccess) return (int)e;
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    const size_t smem = (DENSE ? (size_t)(BLK / 32) * StageLayout<R, Sys::NX>::bytes_per_warp() : 0) +
+    const size_t smem = (DENSE ? 2 * kInfBytes + (size_t)(BLK / 32) * StageLayout<R, Sys::NX>::bytes_per_warp() : 0) +
                         (size_t)BLK * NV * (1 + TB::S) * sizeof(R);
     if (smem > 48 * 1024) {
         e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
