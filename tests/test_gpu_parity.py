@@ -457,3 +457,32 @@ def test_dense_and_endpoint_writes_stay_inside_their_buffers():
                 assert not (inner == sentinel).any(), (k, n)  # every slot written exactly (at least) once
             for k, b in ints.items():
                 assert (b[:G] == -777).all() and (b[-G:] == -777).all() and not (b[G:-G] == -777).any(), (k, n)
+
+
+def test_host_in_host_out_pipeline_equals_device_path():
+    """solve_backward on HOST tensors (pinned or not, torch or numpy) cuts the batch into pieces and overlaps the copies
+    with the integration; every trajectory must come back bit-for-bit as from the one-launch device path."""
+    import torch
+    from approximate_optimal_control_b200 import pontryagin_utils as pu, systems, terminal
+    pp = systems.flatquad_problem_params()
+    ap = dict(systems.flatquad_algo_params(), pontryagin_solver_save_steps=False)
+    n = (1 << 18) + 12345  # ragged last piece
+    st = terminal.sample_terminal_states(flatquad_P_(), pp["V_f"], n, seed=4, dtype=np.float32)
+    solve, _ = pu.define_backward_solver(pp, ap)
+    ref = solve({k: torch.as_tensor(v, device="cuda") for k, v in st.items()})
+    torch.cuda.synchronize()
+    for chunks, pinned in ((4, True), (3, False)):
+        host = {k: (torch.as_tensor(v).pin_memory() if pinned else v) for k, v in st.items()}
+        sol = pu.define_backward_solver(pp, dict(ap, pontryagin_solver_host_chunks=chunks))[0](host)
+        assert not sol.y_end["x"].is_cuda and sol.ys is None
+        for k in ("x", "t", "v", "vx"):
+            assert torch.equal(sol.y_end[k], ref.y_end[k].cpu()), (k, chunks)
+        assert torch.equal(sol.stats["num_steps"], ref.stats["num_steps"].cpu()) and torch.equal(sol.result, ref.result.cpu())
+    # small batches and device inputs keep the one-launch path (results on the device)
+    small = pu.define_backward_solver(pp, ap)[0]({k: v[:1000] for k, v in st.items()})
+    assert small.y_end["x"].is_cuda
+
+
+def flatquad_P_():
+    from common import flatquad_P
+    return flatquad_P()
