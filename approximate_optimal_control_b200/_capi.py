@@ -17,7 +17,7 @@ F32, F64 = 0, 1
 INDEP_TIME, INDEP_VALUE = 0, 1
 EVENT_NONE, EVENT_VALUE_GE, EVENT_VXX_NORM, EVENT_LQR_VALUE_LE, EVENT_NN_VALUE_UCB_LE = 0, 1, 2, 3, 4
 RESULT_OK, RESULT_EVENT, RESULT_MAX_STEPS, RESULT_DT_MIN, RESULT_NAN = 0, 1, 2, 3, 4
-ABI_VERSION = 3
+ABI_VERSION = 4
 FLAG_USTAR_LITERAL = 1
 FLAG_VXX = 2
 FLAG_VXX_SYMMETRIC = 4

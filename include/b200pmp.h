@@ -46,7 +46,7 @@
 extern "C" {
 #endif
 
-#define PMP_ABI_VERSION 3
+#define PMP_ABI_VERSION 4
 
 /* systems (dynamics are compile-time functors; problem_params['system_name'] selects one) */
 enum {
