@@ -47,6 +47,8 @@ template <class R, int NX> struct LinearCostate {
         vstd = R(0);
     }
     __device__ __forceinline__ bool inside(R vmean, R, R level) const { return vmean <= level; }
+    __device__ __forceinline__ int group_lanes() const { return 1; }
+    int group_lanes_host() const { return 1; }
 };
 
 // 16-byte vector load of four consecutive reals (weights are read at warp-uniform addresses: one broadcast)
@@ -66,13 +68,21 @@ __device__ __forceinline__ void load4(const double* p, double* o) {
 // member; vmean / vstd = mean and (population) standard deviation of V_e(x) over the ensemble (v_meanstd, :789-798).
 // Weights: one flat device array, per member K1[nx][W], b1[W], (L-1) x {K[W][W], b[W]}, Kout[W], bout, 3 pad reals
 // (flax kernels are [in][out]); W % 4 == 0 and nx*W % 4 == 0 keep every row 16-byte aligned.
-// One thread evaluates all members for its own state: the W accumulators live in registers, the hidden activations
-// and their sigmoids in local memory (L1), a weight row is one broadcast vector load per four FMAs.
+// A GROUP of `group` lanes (a power of two <= 16, normally the ensemble size) serves one trajectory: every lane of
+// the group carries the same state through the same integrator arithmetic, but evaluates only the members
+// e = sub, sub + group, ...; gradients and values are then summed over the group by xor-shuffles (all lanes end up
+// with bit-identical sums, so the group never diverges).  Forward simulations come by the hundred or thousand
+// (levelsets.py:1201-1215): one thread per trajectory filled a fifth of the machine at one warp per scheduler and
+// waited on its own weight loads (21 % issue utilisation); eight lanes per trajectory give 8x the threads and 1/8 of the
+// serial work.  Per member: the W accumulators live in registers, the hidden activations and their sigmoids in
+// local memory (L1), a weight row is one group-uniform 16-byte load per four FMAs.
 constexpr int kNnMaxLayers = 4, kNnMaxNets = 16;
 template <class R, int NX, int W> struct NnCostate {
     const R* w;
-    int n_nets, n_layers;
+    int n_nets, n_layers, group;
     R x_mean[NX], inv_x_std[NX], v_mean, v_std, n_sigma, sigma_max;
+    __device__ __forceinline__ int group_lanes() const { return group; }
+    int group_lanes_host() const { return group; }
     static __host__ __device__ constexpr int net_stride(int L) { return NX * W + W + (L - 1) * (W * W + W) + W + 4; }
 
     static __device__ __forceinline__ void act(R a, R& sp, R& sg) {  // softplus = logaddexp(a, 0) and its derivative
@@ -90,7 +100,10 @@ template <class R, int NX, int W> struct NnCostate {
         for (int q = 0; q < NX; q++) { xn[q] = (x[q] - x_mean[q]) * inv_x_std[q]; gsum[q] = R(0); }
         R h[W], sg[kNnMaxLayers][W];  // dynamically indexed: local memory
         const int L = n_layers;
-        for (int e = 0; e < n_nets; e++) {
+        const int G = group, lane = threadIdx.x & 31, sub = lane & (G - 1);
+        const unsigned gmask = G >= 32 ? 0xffffffffu : (((1u << G) - 1u) << (lane & ~(G - 1)));
+        int mine = 0;
+        for (int e = sub; e < n_nets; e += G) {
             const R* p = w + (size_t)e * net_stride(L);
             R acc[W];
             // ---- forward
@@ -169,14 +182,21 @@ template <class R, int NX, int W> struct NnCostate {
                 }
                 gsum[q] += (d0 + d1) * (v_std * inv_x_std[q]);
             }
-            ve[e] = M::fma(v_std, v, v_mean);
+            ve[mine++] = M::fma(v_std, v, v_mean);
         }
+        // sums over the group (xor butterfly: every lane of the group ends with the same bits)
         const R inv_e = M::div(R(1), R(n_nets));
         R m = R(0);
-        for (int e = 0; e < n_nets; e++) m += ve[e];
+        for (int e = 0; e < mine; e++) m += ve[e];
+        for (int off = G >> 1; off > 0; off >>= 1) {
+            m += __shfl_xor_sync(gmask, m, off);
+#pragma unroll
+            for (int q = 0; q < NX; q++) gsum[q] += __shfl_xor_sync(gmask, gsum[q], off);
+        }
         m *= inv_e;
         R var = R(0);
-        for (int e = 0; e < n_nets; e++) var = M::fma(ve[e] - m, ve[e] - m, var);
+        for (int e = 0; e < mine; e++) var = M::fma(ve[e] - m, ve[e] - m, var);
+        for (int off = G >> 1; off > 0; off >>= 1) var += __shfl_xor_sync(gmask, var, off);
         vmean = m;
         vstd = M::sqrt(var * inv_e);
 #pragma unroll
@@ -204,8 +224,11 @@ forward_kernel(const typename Sys::Consts sc, const SolveOpts<R> o, const Forwar
     using M = Math<R>;
     using TB = Tab<METHOD>;
     constexpr int NX = Sys::NX, NZ = NX + 1, S = TB::S;
-    const long long n = io.n, i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
+    // G lanes per trajectory (1 for the linear law); only the first lane of a group writes
+    const int G = pol.group_lanes();
+    const long long n = io.n, gtid = (long long)blockIdx.x * blockDim.x + threadIdx.x, i = gtid / G;
+    if (i >= n) return;  // (n * G threads are launched: whole groups leave together)
+    const bool writer = (gtid - i * G) == 0;
     const int S1 = o.max_steps + 1;
 
     // z' = (f(x, u*(x, lambda(x))), l(x, u*)); also the law's value estimate (mean, spread) at the state
@@ -225,7 +248,7 @@ forward_kernel(const typename Sys::Consts sc, const SolveOpts<R> o, const Forwar
     bool at_dtmin = false;
     const R inf = M::inf();
     auto save = [&](int slot) {
-        if (!io.ts || slot >= S1) return;
+        if (!io.ts || slot >= S1 || !writer) return;
         io.ts[i * S1 + slot] = tprev * o.dir;
 #pragma unroll
         for (int q = 0; q < NX; q++) io.xs[(i * S1 + slot) * NX + q] = z[q];
@@ -329,6 +352,7 @@ forward_kernel(const typename Sys::Consts sc, const SolveOpts<R> o, const Forwar
         if (result == 0 && nan_state) result = PMP_RESULT_NAN;
     }
     if (result == 0 && tprev < o.T1) result = PMP_RESULT_MAX_STEPS;
+    if (!writer) return;
 #pragma unroll
     for (int q = 0; q < NZ; q++) io.z_end[q * n + i] = z[q];
     if (io.n_accepted) io.n_accepted[i] = nacc;
@@ -348,12 +372,14 @@ forward_kernel(const typename Sys::Consts sc, const SolveOpts<R> o, const Forwar
 template <class R, class Pol, int NX>
 __global__ void __launch_bounds__(128) nn_value_kernel(const Pol pol, const R* __restrict__ x_, R* __restrict__ lam_,
                                                        R* __restrict__ vm_, R* __restrict__ vs_, long long n) {
-    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const int G = pol.group_lanes();
+    const long long gtid = (long long)blockIdx.x * blockDim.x + threadIdx.x, i = gtid / G;
     if (i >= n) return;
     R x[NX], lam[NX], vm, vs;
 #pragma unroll
     for (int q = 0; q < NX; q++) x[q] = x_[q * n + i];
     pol.eval(x, lam, vm, vs);
+    if (gtid - i * G != 0) return;
 #pragma unroll
     for (int q = 0; q < NX; q++) lam_[q * n + i] = lam[q];
     vm_[i] = vm;
@@ -363,7 +389,9 @@ __global__ void __launch_bounds__(128) nn_value_kernel(const Pol pol, const R* _
 template <class R, int NX, class Fill>
 int launch_nn_value_r(const pmp_nn_costate_t* nn, long long n, const void* x, void* lam, void* vm, void* vs, Fill&& fill,
                       cudaStream_t st) {
-    const unsigned grid = (unsigned)((n + 127) / 128);
+    int G = 1;
+    while (2 * G <= nn->n_nets && 2 * G <= 16) G *= 2;
+    const unsigned grid = (unsigned)((n * G + 127) / 128);
     if (nn->width == 64) {
         NnCostate<R, NX, 64> pol; fill(pol);
         nn_value_kernel<R, NnCostate<R, NX, 64>, NX><<<grid, 128, 0, st>>>(pol, (const R*)x, (R*)lam, (R*)vm, (R*)vs, n);
@@ -384,6 +412,8 @@ int launch_nn_value(const pmp_nn_costate_t* nn, int dtype, long long n, const vo
         using R = std::remove_cv_t<std::remove_reference_t<decltype(pol.v_mean)>>;
         pol.w = (const R*)nn->weights;
         pol.n_nets = nn->n_nets; pol.n_layers = nn->n_hidden_layers;
+        pol.group = 1;
+        while (2 * pol.group <= nn->n_nets && 2 * pol.group <= 16) pol.group *= 2;
         for (int q = 0; q < NX; q++) { pol.x_mean[q] = R(nn->x_mean[q]); pol.inv_x_std[q] = R(1.0 / nn->x_std[q]); }
         pol.v_mean = R(nn->v_mean); pol.v_std = R(nn->v_std); pol.n_sigma = R(nn->n_sigma); pol.sigma_max = R(nn->sigma_max);
     };
@@ -394,7 +424,7 @@ int launch_nn_value(const pmp_nn_costate_t* nn, int dtype, long long n, const vo
 template <class Sys, class R, class Pol>
 int launch_forward_pol(const pmp_problem_t& p, const pmp_opts_t& o, long long n, const ForwardIO<R>& io, const Pol& pol,
                        cudaStream_t st) {
-    const unsigned grid = (unsigned)((n + 127) / 128);
+    const unsigned grid = (unsigned)((n * pol.group_lanes_host() + 127) / 128);
 #define PMP_FGO(METHOD)                                                                                          \
     do {                                                                                                          \
         using TB = Tab<METHOD>;                                                                                   \
@@ -431,6 +461,8 @@ int launch_forward_nn_r(const pmp_problem_t& p, const pmp_opts_t& o, long long n
     auto fill = [&](auto& pol) {
         pol.w = (const R*)nn->weights;
         pol.n_nets = nn->n_nets; pol.n_layers = nn->n_hidden_layers;
+        pol.group = 1;
+        while (2 * pol.group <= nn->n_nets && 2 * pol.group <= 16) pol.group *= 2;
         for (int q = 0; q < NX; q++) { pol.x_mean[q] = R(nn->x_mean[q]); pol.inv_x_std[q] = R(1.0 / nn->x_std[q]); }
         pol.v_mean = R(nn->v_mean); pol.v_std = R(nn->v_std); pol.n_sigma = R(nn->n_sigma); pol.sigma_max = R(nn->sigma_max);
     };
