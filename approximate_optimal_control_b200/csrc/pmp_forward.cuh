@@ -91,97 +91,192 @@ template <class R, int NX, int W> struct NnCostate {
         sg = a >= R(0) ? d : e * d;
     }
 
-    // NOT inlined: the integrator calls it once per stage (7 call sites); inlined, every forward kernel carries seven
-    // copies of the unrolled sweeps and the library takes a quarter of an hour to compile
-    __device__ __noinline__ void eval(const R* x, R* lam, R& vmean, R& vstd) const {
-        using M = Math<R>;
-        R xn[NX], gsum[NX], ve[kNnMaxNets];
-#pragma unroll
-        for (int q = 0; q < NX; q++) { xn[q] = (x[q] - x_mean[q]) * inv_x_std[q]; gsum[q] = R(0); }
-        R h[W], sg[kNnMaxLayers][W];  // dynamically indexed: local memory
-        const int L = n_layers;
-        const int G = group, lane = threadIdx.x & 31, sub = lane & (G - 1);
-        const unsigned gmask = G >= 32 ? 0xffffffffu : (((1u << G) - 1u) << (lane & ~(G - 1)));
-        int mine = 0;
-        for (int e = sub; e < n_nets; e += G) {
-            const R* p = w + (size_t)e * net_stride(L);
-            R acc[W];
-            // ---- forward
-#pragma unroll
-            for (int j = 0; j < W; j += 4) load4(p + NX * W + j, acc + j);  // bias
-#pragma unroll
-            for (int q = 0; q < NX; q++) {
-#pragma unroll
-                for (int j = 0; j < W; j += 4) {
-                    R k4[4];
-                    load4(p + q * W + j, k4);
-#pragma unroll
-                    for (int c = 0; c < 4; c++) acc[j + c] = M::fma(xn[q], k4[c], acc[j + c]);
-                }
+    // four consecutive weights: from shared memory (one 16-byte LDS) or from global memory (__ldg)
+    template <bool SMEM> static __device__ __forceinline__ void ld4(const R* a, R* o) {
+        if (SMEM) {
+            typedef typename std::conditional<sizeof(R) == 4, float4, double2>::type V16;
+            if (sizeof(R) == 4) {
+                const V16 v = *reinterpret_cast<const V16*>(a);
+                const R* e = reinterpret_cast<const R*>(&v);
+                o[0] = e[0]; o[1] = e[1]; o[2] = e[2]; o[3] = e[3];
+            } else {
+                const V16 u = *reinterpret_cast<const V16*>(a), v = *(reinterpret_cast<const V16*>(a) + 1);
+                const R* e = reinterpret_cast<const R*>(&u);
+                const R* f = reinterpret_cast<const R*>(&v);
+                o[0] = e[0]; o[1] = e[1]; o[2] = f[0]; o[3] = f[1];
             }
+        } else {
+            load4(a, o);
+        }
+    }
+
+    template <bool SMEM> static __device__ __forceinline__ void load_row(const R* a, R* w) {
 #pragma unroll
-            for (int j = 0; j < W; j++) act(acc[j], h[j], sg[0][j]);
-            const R* pl = p + NX * W + W;
-            for (int l = 1; l < L; l++, pl += W * W + W) {
+        for (int j = 0; j < W; j += 4) ld4<SMEM>(a + j, w + j);
+    }
+    static __device__ __forceinline__ R dot_row(const R* w, const R* g) {  // four partial sums
+        using M = Math<R>;
+        R d0 = R(0), d1 = R(0), d2 = R(0), d3 = R(0);
 #pragma unroll
-                for (int j = 0; j < W; j += 4) load4(pl + W * W + j, acc + j);
+        for (int j = 0; j < W; j += 4) {
+            d0 = M::fma(w[j], g[j], d0); d1 = M::fma(w[j + 1], g[j + 1], d1);
+            d2 = M::fma(w[j + 2], g[j + 2], d2); d3 = M::fma(w[j + 3], g[j + 3], d3);
+        }
+        return (d0 + d1) + (d2 + d3);
+    }
+
+    // h = softplus(acc), sg = softplus'(acc) for one layer.  The accumulators are registers (compile-time indices), so
+    // they are first parked in local memory and the activation runs as a ROLLED loop: unrolled, 64 inlined copies of
+    // exp + log1p per layer made a sweep 250-500 KB of code, and the kernels ran at ~20 cycles per instruction out of
+    // the instruction cache.
+    static __device__ __forceinline__ void activate(const R* acc, R* h, R* sg) {
+#pragma unroll
+        for (int j = 0; j < W; j++) h[j] = acc[j];
+#pragma unroll 1
+        for (int j = 0; j < W; j++) {
+            R sp, s;
+            act(h[j], sp, s);
+            h[j] = sp;
+            sg[j] = s;
+        }
+    }
+
+    // One member's forward + backward sweep at the normalised state xn: v = MLP(xn), gx = dMLP/dxn.  p = the member's
+    // weights; SMEM: they sit in shared memory (cluster kernel, plain vector loads) instead of global memory (__ldg).
+    // NOT inlined: the integrator calls the law once per stage (7 call sites); inlined, every forward kernel carries
+    // seven copies of the unrolled sweeps and the library takes a quarter of an hour to compile.
+    template <bool SMEM>
+    static __device__ __noinline__ void member_sweep(const R* p, const R* xn, int L, R* gx, R& v_out) {
+        using M = Math<R>;
+        R h[W], sg[kNnMaxLayers][W];  // dynamically indexed: local memory
+        R acc[W];
+        // ---- forward
+#pragma unroll
+        for (int j = 0; j < W; j += 4) ld4<SMEM>(p + NX * W + j, acc + j);  // bias
+#pragma unroll
+        for (int q = 0; q < NX; q++) {
+#pragma unroll
+            for (int j = 0; j < W; j += 4) {
+                R k4[4];
+                ld4<SMEM>(p + q * W + j, k4);
+#pragma unroll
+                for (int c = 0; c < 4; c++) acc[j + c] = M::fma(xn[q], k4[c], acc[j + c]);
+            }
+        }
+        activate(acc, h, sg[0]);
+        const R* pl = p + NX * W + W;
+        for (int l = 1; l < L; l++, pl += W * W + W) {
+#pragma unroll
+            for (int j = 0; j < W; j += 4) ld4<SMEM>(pl + W * W + j, acc + j);
+            if (sizeof(R) == 4) {
+                // software pipeline, two weight rows in flight: the loads of row i+1 are issued before the 64 FMAs of
+                // row i (one warp per scheduler cannot hide a 30-cycle shared-memory load behind 4 FMAs)
+                R wa[W], wb[W];
+                load_row<SMEM>(pl, wa);
+                R ha = h[0], hb;
+#pragma unroll 1
+                for (int i = 0; i < W; i += 2) {
+                    load_row<SMEM>(pl + (i + 1) * W, wb);
+                    hb = h[i + 1];
+#pragma unroll
+                    for (int j = 0; j < W; j++) acc[j] = M::fma(ha, wa[j], acc[j]);
+                    if (i + 2 < W) {
+                        load_row<SMEM>(pl + (i + 2) * W, wa);
+                        ha = h[i + 2];
+                    }
+#pragma unroll
+                    for (int j = 0; j < W; j++) acc[j] = M::fma(hb, wb[j], acc[j]);
+                }
+            } else {
 #pragma unroll 2
                 for (int i = 0; i < W; i++) {
                     const R hi = h[i];
 #pragma unroll
                     for (int j = 0; j < W; j += 4) {
                         R k4[4];
-                        load4(pl + i * W + j, k4);
+                        ld4<SMEM>(pl + i * W + j, k4);
 #pragma unroll
                         for (int c = 0; c < 4; c++) acc[j + c] = M::fma(hi, k4[c], acc[j + c]);
                     }
                 }
-#pragma unroll
-                for (int j = 0; j < W; j++) act(acc[j], h[j], sg[l][j]);
             }
-            // output layer (pl now points at Kout) and the seed of the backward sweep g = Kout * softplus'(a_L)
-            R v = __ldg(pl + W);
+            activate(acc, h, sg[l]);
+        }
+        // output layer (pl now points at Kout) and the seed of the backward sweep g = Kout * softplus'(a_L)
+        R v = pl[W];
 #pragma unroll
-            for (int j = 0; j < W; j += 4) {
-                R k4[4];
-                load4(pl + j, k4);
+        for (int j = 0; j < W; j += 4) {
+            R k4[4];
+            ld4<SMEM>(pl + j, k4);
 #pragma unroll
-                for (int c = 0; c < 4; c++) {
-                    v = M::fma(h[j + c], k4[c], v);
-                    acc[j + c] = k4[c] * sg[L - 1][j + c];
+            for (int c = 0; c < 4; c++) {
+                v = M::fma(h[j + c], k4[c], v);
+                acc[j + c] = k4[c] * sg[L - 1][j + c];
+            }
+        }
+        // ---- backward through the hidden layers: g_{l-1}[i] = softplus'(a_{l-1})[i] * sum_j K_l[i][j] g_l[j]
+        for (int l = L - 1; l >= 1; l--) {
+            pl -= W * W + W;
+            if (sizeof(R) == 4) {
+                R wa[W], wb[W];
+                load_row<SMEM>(pl, wa);
+#pragma unroll 1
+                for (int i = 0; i < W; i += 2) {
+                    load_row<SMEM>(pl + (i + 1) * W, wb);
+                    const R s0 = sg[l - 1][i], s1 = sg[l - 1][i + 1];
+                    const R da = dot_row(wa, acc);
+                    if (i + 2 < W) load_row<SMEM>(pl + (i + 2) * W, wa);
+                    const R db = dot_row(wb, acc);
+                    h[i] = da * s0;
+                    h[i + 1] = db * s1;
                 }
-            }
-            // ---- backward through the hidden layers: g_{l-1}[i] = softplus'(a_{l-1})[i] * sum_j K_l[i][j] g_l[j]
-            for (int l = L - 1; l >= 1; l--) {
-                pl -= W * W + W;
+            } else {
 #pragma unroll 2
                 for (int i = 0; i < W; i++) {
                     R d0 = R(0), d1 = R(0);
 #pragma unroll
                     for (int j = 0; j < W; j += 4) {
                         R k4[4];
-                        load4(pl + i * W + j, k4);
+                        ld4<SMEM>(pl + i * W + j, k4);
                         d0 = M::fma(k4[0], acc[j], d0); d1 = M::fma(k4[1], acc[j + 1], d1);
                         d0 = M::fma(k4[2], acc[j + 2], d0); d1 = M::fma(k4[3], acc[j + 3], d1);
                     }
                     h[i] = (d0 + d1) * sg[l - 1][i];
                 }
-#pragma unroll
-                for (int j = 0; j < W; j++) acc[j] = h[j];
             }
-            // input layer: dMLP/dxn[q] = sum_j K1[q][j] g_0[j]; chain rule of the normaliser
 #pragma unroll
-            for (int q = 0; q < NX; q++) {
-                R d0 = R(0), d1 = R(0);
+            for (int j = 0; j < W; j++) acc[j] = h[j];
+        }
+        // input layer: dMLP/dxn[q] = sum_j K1[q][j] g_0[j]
 #pragma unroll
-                for (int j = 0; j < W; j += 4) {
-                    R k4[4];
-                    load4(p + q * W + j, k4);
-                    d0 = M::fma(k4[0], acc[j], d0); d1 = M::fma(k4[1], acc[j + 1], d1);
-                    d0 = M::fma(k4[2], acc[j + 2], d0); d1 = M::fma(k4[3], acc[j + 3], d1);
-                }
-                gsum[q] += (d0 + d1) * (v_std * inv_x_std[q]);
+        for (int q = 0; q < NX; q++) {
+            R d0 = R(0), d1 = R(0);
+#pragma unroll
+            for (int j = 0; j < W; j += 4) {
+                R k4[4];
+                ld4<SMEM>(p + q * W + j, k4);
+                d0 = M::fma(k4[0], acc[j], d0); d1 = M::fma(k4[1], acc[j + 1], d1);
+                d0 = M::fma(k4[2], acc[j + 2], d0); d1 = M::fma(k4[3], acc[j + 3], d1);
             }
+            gx[q] = d0 + d1;
+        }
+        v_out = v;
+    }
+
+    __device__ __forceinline__ void eval(const R* x, R* lam, R& vmean, R& vstd) const {
+        using M = Math<R>;
+        R xn[NX], gsum[NX], ve[kNnMaxNets];
+#pragma unroll
+        for (int q = 0; q < NX; q++) { xn[q] = (x[q] - x_mean[q]) * inv_x_std[q]; gsum[q] = R(0); }
+        const int L = n_layers;
+        const int G = group, lane = threadIdx.x & 31, sub = lane & (G - 1);
+        const unsigned gmask = G >= 32 ? 0xffffffffu : (((1u << G) - 1u) << (lane & ~(G - 1)));
+        int mine = 0;
+        for (int e = sub; e < n_nets; e += G) {
+            R gx[NX], v;
+            member_sweep<false>(w + (size_t)e * net_stride(L), xn, L, gx, v);
+#pragma unroll
+            for (int q = 0; q < NX; q++) gsum[q] = M::fma(gx[q], v_std * inv_x_std[q], gsum[q]);  // chain rule of the normaliser
             ve[mine++] = M::fma(v_std, v, v_mean);
         }
         // sums over the group (xor butterfly: every lane of the group ends with the same bits)
@@ -452,6 +547,11 @@ int launch_forward_r(const pmp_problem_t& p, const pmp_opts_t& o, long long n, c
     return launch_forward_pol<Sys, R>(p, o, n, io, pol, st);
 }
 
+// defined in a compile unit of its own (pmp_forward_cluster.cu) for every (system, dtype, width)
+template <class Sys, class R, int W>
+int launch_forward_cluster(const pmp_problem_t& p, const pmp_opts_t& o, long long n, const ForwardIO<R>& io,
+                           const NnCostate<R, Sys::NX, W>& pol, cudaStream_t st);
+
 template <template <class> class SysT, class R>
 int launch_forward_nn_r(const pmp_problem_t& p, const pmp_opts_t& o, long long n, const void* x0, const pmp_nn_costate_t* nn,
                         void* z_end, void* ts, void* xs, void* cost, int32_t* a, int32_t* s, int32_t* r, cudaStream_t st) {
@@ -466,8 +566,21 @@ int launch_forward_nn_r(const pmp_problem_t& p, const pmp_opts_t& o, long long n
         for (int q = 0; q < NX; q++) { pol.x_mean[q] = R(nn->x_mean[q]); pol.inv_x_std[q] = R(1.0 / nn->x_std[q]); }
         pol.v_mean = R(nn->v_mean); pol.v_std = R(nn->v_std); pol.n_sigma = R(nn->n_sigma); pol.sigma_max = R(nn->sigma_max);
     };
-    if (nn->width == 64) { NnCostate<R, NX, 64> pol; fill(pol); return launch_forward_pol<Sys, R>(p, o, n, io, pol, st); }
-    if (nn->width == 32) { NnCostate<R, NX, 32> pol; fill(pol); return launch_forward_pol<Sys, R>(p, o, n, io, pol, st); }
+    // Two kernels serve an ensemble: the lane-group kernel above (default) and, with B200PMP_NN_CLUSTER=1, the cluster
+    // kernel (pmp_forward_cluster.cuh: weights in shared memory, partial results exchanged through distributed shared
+    // memory).  Measured on 2^14 flatquad simulations (8 x 6-64-64-64-1, fp32): 93 ms against 109 ms -- the cluster kernel's
+    // sweeps run from shared memory, but its trajectories advance in lockstep to the slowest of 128 (51 attempts
+    // against a mean of 18); it needs a refill of finished slots before it can win.
+    const char* env = getenv("B200PMP_NN_CLUSTER");
+    const bool use_cluster = nn->n_nets >= 2 && env && env[0] == '1';
+    if (nn->width == 64) {
+        NnCostate<R, NX, 64> pol; fill(pol);
+        return use_cluster ? launch_forward_cluster<Sys, R, 64>(p, o, n, io, pol, st) : launch_forward_pol<Sys, R>(p, o, n, io, pol, st);
+    }
+    if (nn->width == 32) {
+        NnCostate<R, NX, 32> pol; fill(pol);
+        return use_cluster ? launch_forward_cluster<Sys, R, 32>(p, o, n, io, pol, st) : launch_forward_pol<Sys, R>(p, o, n, io, pol, st);
+    }
     return -1000;
 }
 

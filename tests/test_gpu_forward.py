@@ -145,8 +145,11 @@ def test_nn_value_batch_vs_oracle(nx, dims, E):
     assert one[0].shape == (nx,) and torch.allclose(one[0], lam[7])
 
 
-def test_forward_nn_ensemble_fp64_vs_oracle():
+@pytest.mark.parametrize("cluster", ["0", "1"])
+def test_forward_nn_ensemble_fp64_vs_oracle(cluster, monkeypatch):
+    """both kernels: lane groups (default) and thread-block clusters with distributed shared memory"""
     import torch
+    monkeypatch.setenv("B200PMP_NN_CLUSTER", cluster)
     tol = 1e-6
     prob, _ = c_problem("flatquad")
     ens, onn, _w = _ensemble(6, (64, 64, 64), 8, torch.float64)
@@ -164,8 +167,10 @@ def test_forward_nn_ensemble_fp64_vs_oracle():
     assert (np.isinf(got["x"]) == np.isinf(ref["x"]))[same].all() and np.allclose(got["x"][fin], ref["x"][fin], rtol=1e-5, atol=1e-5)
 
 
-def test_forward_nn_until_value_and_public_api():
+@pytest.mark.parametrize("cluster", ["0", "1"])
+def test_forward_nn_until_value_and_public_api(cluster, monkeypatch):
     import torch
+    monkeypatch.setenv("B200PMP_NN_CLUSTER", cluster)
     from approximate_optimal_control_b200 import nn_costate as NC
     pp, ap = systems.flatquad_problem_params(), dict(systems.flatquad_algo_params(), forward_sim_T=1.5)
     ens, onn, _w = _ensemble(6, (64, 64, 64), 8, torch.float32, seed=2)
