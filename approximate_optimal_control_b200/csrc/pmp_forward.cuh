@@ -566,13 +566,11 @@ int launch_forward_nn_r(const pmp_problem_t& p, const pmp_opts_t& o, long long n
         for (int q = 0; q < NX; q++) { pol.x_mean[q] = R(nn->x_mean[q]); pol.inv_x_std[q] = R(1.0 / nn->x_std[q]); }
         pol.v_mean = R(nn->v_mean); pol.v_std = R(nn->v_std); pol.n_sigma = R(nn->n_sigma); pol.sigma_max = R(nn->sigma_max);
     };
-    // Two kernels serve an ensemble: the lane-group kernel above (default) and, with B200PMP_NN_CLUSTER=1, the cluster
-    // kernel (pmp_forward_cluster.cuh: weights in shared memory, partial results exchanged through distributed shared
-    // memory).  Measured on 2^14 flatquad simulations (8 x 6-64-64-64-1, fp32): 93 ms against 109 ms -- the cluster kernel's
-    // sweeps run from shared memory, but its trajectories advance in lockstep to the slowest of 128 (51 attempts
-    // against a mean of 18); it needs a refill of finished slots before it can win.
+    // Two kernels serve an ensemble: the cluster kernel (pmp_forward_cluster.cuh: weights in shared memory, partial results
+    // exchanged through distributed shared memory, slots refilled from a per-cluster queue; default) and, with
+    // B200PMP_NN_CLUSTER=0, the lane-group kernel above.  2^14 flatquad simulations (8 x 6-64-64-64-1, fp32): 70 ms / 94 ms.
     const char* env = getenv("B200PMP_NN_CLUSTER");
-    const bool use_cluster = nn->n_nets >= 2 && env && env[0] == '1';
+    const bool use_cluster = nn->n_nets >= 2 && !(env && env[0] == '0');
     if (nn->width == 64) {
         NnCostate<R, NX, 64> pol; fill(pol);
         return use_cluster ? launch_forward_cluster<Sys, R, 64>(p, o, n, io, pol, st) : launch_forward_pol<Sys, R>(p, o, n, io, pol, st);

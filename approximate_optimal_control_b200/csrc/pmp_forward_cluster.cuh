@@ -9,8 +9,11 @@
 //     16-byte loads, ~4 FMAs per load, nothing leaves the SM), publishes (sum of gradients, values) in its CTA's
 //     exchange buffer, the cluster synchronises, and every thread adds up the C partial results through DISTRIBUTED
 //     SHARED MEMORY in rank order -- so all CTAs hold bit-identical costates and take identical steps;
-//   * the trajectories of a CTA advance in lockstep (one step attempt per iteration for everybody; a trajectory that
-//     has finished idles, `live` gates every update), because the cluster barrier needs all threads;
+//   * the 128 slots of a CTA advance in lockstep (one step attempt per iteration for everybody, `live` gates every
+//     update), because the cluster barrier needs all threads; a slot whose trajectory has ended is REFILLED from the
+//     cluster's queue of trajectories -- in rounds (at least kClusterRefillMin waiting slots, each round costs one extra
+//     sweep for the fresh trajectories' first stage), with ranks from a block-wide scan, so that every CTA of the
+//     cluster takes the same decisions;
 //   * CTA 0 of the cluster writes the outputs.
 #pragma once
 #include <cooperative_groups.h>
@@ -22,18 +25,24 @@ namespace cg = cooperative_groups;
 
 constexpr int kClusterMaxMembers = 2;  // members per CTA: up to 16 members on clusters of 8
 
+constexpr int kClusterRefillMin = 16;  // idle slots of a CTA that trigger a refill round (each costs one extra sweep)
+
 template <class Sys, class R, int METHOD, int W>
 __global__ void __launch_bounds__(128, 1)
 forward_cluster_kernel(const typename Sys::Consts sc, const SolveOpts<R> o, const ForwardIO<R> io,
-                       const NnCostate<R, Sys::NX, W> pol, const TabParams<R> tp) {
+                       const NnCostate<R, Sys::NX, W> pol, const TabParams<R> tp, const long long chunk, const int refill_min) {
     using M = Math<R>;
     using TB = Tab<METHOD>;
     using Pol = NnCostate<R, Sys::NX, W>;
     constexpr int NX = Sys::NX, NZ = NX + 1, S = TB::S, BLK = 128;
     cg::cluster_group cluster = cg::this_cluster();
     const int C = (int)cluster.num_blocks(), rank = (int)cluster.block_rank();
-    const long long n = io.n, i = (long long)(blockIdx.x / C) * BLK + threadIdx.x;
-    const bool valid = i < n, writer = valid && rank == 0;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const long long n = io.n;
+    // this cluster's trajectories [cb, ce): 128 slots, refilled from `next` as trajectories end
+    const long long cb = (long long)(blockIdx.x / C) * chunk, ce = cb + chunk < n ? cb + chunk : n;
+    long long next = cb;
+    const bool is_writer_cta = rank == 0;
     const int S1 = o.max_steps + 1, L = pol.n_layers, E = pol.n_nets;
     const int stride = Pol::net_stride(L);
 
@@ -42,6 +51,7 @@ forward_cluster_kernel(const typename Sys::Consts sc, const SolveOpts<R> o, cons
     int my = 0;
     for (int e = rank; e < E; e += C) my++;
     R* xch = sW + (size_t)kClusterMaxMembers * stride;            // [NX + kClusterMaxMembers][BLK]
+    __shared__ int s_cnt[BLK / 32];
     for (int m = 0; m < my; m++) {
         const R* src = pol.w + (size_t)(rank + m * C) * stride;
         for (int q = threadIdx.x; q < stride; q += BLK) sW[(size_t)m * stride + q] = __ldg(src + q);
@@ -93,31 +103,89 @@ forward_cluster_kernel(const typename Sys::Consts sc, const SolveOpts<R> o, cons
         k[NX] = -vd;
     };
 
+    long long i = -1;  // the slot's trajectory (-1: none)
     R z[NZ], k[S][NZ];
 #pragma unroll
-    for (int q = 0; q < NX; q++) z[q] = valid ? io.x0[q * n + i] : R(0);
-    z[NX] = R(0);
-    R tprev = o.T0, tnext = M::min(o.T0 + o.dt0, o.T1), vcur = R(0), scur = R(0);
+    for (int q = 0; q < NZ; q++) z[q] = R(0);
+    R tprev = o.T1, tnext = o.T1, vcur = R(0), scur = R(0);
     int nsteps = 0, nacc = 0, result = 0;
     bool at_dtmin = false;
     const R inf = M::inf();
     auto save = [&](int slot) {
-        if (!io.ts || slot >= S1 || !writer) return;
+        if (!io.ts || slot >= S1 || !is_writer_cta) return;
         io.ts[i * S1 + slot] = tprev * o.dir;
 #pragma unroll
         for (int q = 0; q < NX; q++) io.xs[(i * S1 + slot) * NX + q] = z[q];
         io.cost[i * S1 + slot] = z[NX];
     };
-    bool bad = false;
-#pragma unroll
-    for (int q = 0; q < NX; q++) bad = bad || (z[q] != z[q]);
-    if (bad) result = PMP_RESULT_NAN;  // retires at once (it keeps sweeping its NaN state with everybody else)
-    save(0);
-    if (TB::FSAL) field(z, k[0], vcur, scur);
+    auto is_live = [&]() { return i >= 0 && tprev < o.T1 && result == 0 && nsteps < o.max_steps; };
 
     while (true) {
-        const bool live = valid && tprev < o.T1 && result == 0 && nsteps < o.max_steps;
-        if (!__syncthreads_or(live)) break;  // (identical in every CTA of the cluster: they hold identical states)
+        // ---- retire + refill round: when enough slots wait, or nothing is live (identical decisions in every CTA of
+        // the cluster: they hold identical states)
+        const bool live0 = is_live();
+        const bool want = !live0;
+        const int n_want = __syncthreads_count(want);
+        const bool any_left = next < ce;
+        if (n_want == BLK || (n_want >= refill_min && any_left) || (n_want > 0 && !any_left)) {
+            const unsigned bal = __ballot_sync(0xffffffffu, want);
+            if (lane == 0) s_cnt[warp] = __popc(bal);
+            __syncthreads();
+            int before = 0;
+            for (int w = 0; w < warp; w++) before += s_cnt[w];
+            const int my_rank = before + __popc(bal & ((1u << lane) - 1u));
+            __syncthreads();
+            bool fresh = false;
+            if (want) {
+                if (i >= 0 && is_writer_cta) {  // retire
+                    if (result == 0 && tprev < o.T1) result = PMP_RESULT_MAX_STEPS;
+#pragma unroll
+                    for (int q = 0; q < NZ; q++) io.z_end[q * n + i] = z[q];
+                    if (io.n_accepted) io.n_accepted[i] = nacc;
+                    if (io.n_steps) io.n_steps[i] = nsteps;
+                    if (io.result) io.result[i] = result;
+                    if (io.ts) {
+                        for (int slot = nacc + 1; slot < S1; slot++) {
+                            io.ts[i * S1 + slot] = inf * o.dir;
+#pragma unroll
+                            for (int q = 0; q < NX; q++) io.xs[(i * S1 + slot) * NX + q] = inf;
+                            io.cost[i * S1 + slot] = inf;
+                        }
+                    }
+                }
+                i = -1;
+                if (next + my_rank < ce) {
+                    i = next + my_rank;
+                    fresh = true;
+#pragma unroll
+                    for (int q = 0; q < NX; q++) z[q] = io.x0[q * n + i];
+                    z[NX] = R(0);
+                    tprev = o.T0; tnext = M::min(o.T0 + o.dt0, o.T1);
+                    nsteps = 0; nacc = 0; result = 0; at_dtmin = false;
+                    bool bad = false;
+#pragma unroll
+                    for (int q = 0; q < NX; q++) bad = bad || (z[q] != z[q]);
+                    if (bad) result = PMP_RESULT_NAN;  // retires in the next round (it sweeps its NaN state meanwhile)
+                    save(0);
+                }
+            }
+            const long long left = ce - next;
+            next += n_want < left ? n_want : left;
+            if (TB::FSAL && __syncthreads_or(fresh)) {  // k1 of the fresh trajectories: one collective sweep for everybody
+                R kf[NZ], vf, sf;
+                field(z, kf, vf, sf);
+                if (fresh) {
+#pragma unroll
+                    for (int q = 0; q < NZ; q++) k[0][q] = kf[q];
+                    vcur = vf; scur = sf;
+                }
+            }
+        }
+        const bool live = is_live();
+        if (!__syncthreads_or(live)) {
+            if (next >= ce && __syncthreads_count(i >= 0) == 0) break;  // nothing live, nothing waiting, nothing left
+            continue;                                                  // finished slots wait for the retire round above
+        }
         const R dt = live ? tnext - tprev : o.dt0, h = dt * o.dir;
         if (!TB::FSAL) field(z, k[0], vcur, scur);
         R z1[NZ], v1 = R(0), s1 = R(0);
@@ -213,21 +281,6 @@ forward_cluster_kernel(const typename Sys::Consts sc, const SolveOpts<R> o, cons
         if (live && result == 0 && o.event != PMP_EVENT_NONE && pol.inside(vcur, scur, o.event_level)) result = PMP_RESULT_EVENT;
         if (live && result == 0 && nan_state) result = PMP_RESULT_NAN;
     }
-    if (!writer) return;
-    if (result == 0 && tprev < o.T1) result = PMP_RESULT_MAX_STEPS;
-#pragma unroll
-    for (int q = 0; q < NZ; q++) io.z_end[q * n + i] = z[q];
-    if (io.n_accepted) io.n_accepted[i] = nacc;
-    if (io.n_steps) io.n_steps[i] = nsteps;
-    if (io.result) io.result[i] = result;
-    if (io.ts) {
-        for (int slot = nacc + 1; slot < S1; slot++) {
-            io.ts[i * S1 + slot] = inf * o.dir;
-#pragma unroll
-            for (int q = 0; q < NX; q++) io.xs[(i * S1 + slot) * NX + q] = inf;
-            io.cost[i * S1 + slot] = inf;
-        }
-    }
 }
 
 // smem bytes of one CTA
@@ -240,8 +293,18 @@ int launch_forward_cluster_w(const pmp_problem_t& p, const pmp_opts_t& o, long l
                              const NnCostate<R, Sys::NX, W>& pol, cudaStream_t st) {
     const int C = pol.n_nets < 8 ? pol.n_nets : 8;
     const size_t smem = cluster_smem_bytes<R, Sys::NX, W>(pol.n_layers);
+    // trajectories per cluster: 128 slots, refilled; enough clusters to fill the machine twice over, then longer queues
+    int dev = 0, sms = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    const long long clusters_target = (long long)(2 * sms / C > 1 ? 2 * sms / C : 1);
+    long long chunk = ((n + clusters_target - 1) / clusters_target + 127) / 128 * 128;
+    if (chunk < 128) chunk = 128;
+    if (const char* e = getenv("B200PMP_NN_CHUNK")) chunk = (atoll(e) + 127) / 128 * 128 > 0 ? (atoll(e) + 127) / 128 * 128 : chunk;  // tuning
+    int refill_min = kClusterRefillMin;
+    if (const char* e = getenv("B200PMP_NN_REFILL")) refill_min = atoi(e) > 0 ? atoi(e) : refill_min;  // tuning
     cudaLaunchConfig_t cfg = {};
-    cfg.gridDim = dim3((unsigned)(((n + 127) / 128) * C), 1, 1);
+    cfg.gridDim = dim3((unsigned)(((n + chunk - 1) / chunk) * C), 1, 1);
     cfg.blockDim = dim3(128, 1, 1);
     cfg.dynamicSmemBytes = smem;
     cfg.stream = st;
@@ -257,7 +320,7 @@ int launch_forward_cluster_w(const pmp_problem_t& p, const pmp_opts_t& o, long l
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);         \
         if (e != cudaSuccess) return (int)e;                                                                        \
         e = cudaLaunchKernelEx(&cfg, kern, Sys::make(p), make_solve_opts<R, TB>(o, TB::ORDER, Sys::NX), io, pol,     \
-                               TabParams<R>::template make<TB>());                                                  \
+                               TabParams<R>::template make<TB>(), chunk, refill_min);                               \
         return (int)e;                                                                                              \
     } while (0)
     if (o.method == PMP_METHOD_RK4) PMP_CGO(PMP_METHOD_RK4);
