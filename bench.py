@@ -121,6 +121,15 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
+def host_cores() -> int:
+    """Host threads the CPU arms use: every core this process may be scheduled on (not OMP_NUM_THREADS, which
+    torch.distributed.run sets to 1)."""
+    try:
+        return max(1, len(os.sched_getaffinity(0)))
+    except AttributeError:
+        return os.cpu_count() or 1
+
+
 # --------------------------------------------------------------------------------------------------
 def run_reference(args):
     """--impl reference: the reference's algorithm on the host cores.  The reference itself (jax 0.4.23 +
@@ -137,13 +146,13 @@ def run_reference(args):
     opts = O.make_opts(method=method, dtype=odt, adaptive=int(args.method != "rk4"),
                        dt0=-0.1 if args.method != "rk4" else -1 / 32, save_dense=int(args.workload == "dense"))
     prob = O.flatquad_problem()
-    cores = O.num_threads()
+    cores = host_cores()  # torchrun exports OMP_NUM_THREADS=1: ask for every core this process may run on explicitly
     for _ in range(args.warmup):
-        O.solve_batch(prob, opts, y)
+        O.solve_batch(prob, opts, y, n_threads=cores)
     t0 = time.perf_counter()
     attempts = 0
     for _ in range(args.steps):
-        out = O.solve_batch(prob, opts, y)
+        out = O.solve_batch(prob, opts, y, n_threads=cores)
         attempts += int(out["n_steps"].sum())
     dt = time.perf_counter() - t0
     value = n * args.steps / dt
@@ -396,18 +405,19 @@ def main():
                          dtype=O.F32 if args.dtype == "f32" else O.F64, adaptive=int(args.method != "rk4"),
                          dt0=-0.1 if args.method != "rk4" else -1 / 32)
         ys = y_np[:, :nc] if nc <= n else y_np
-        O.solve_batch(O.flatquad_problem(), oo, ys[:, :4096])
+        ncores = host_cores()
+        O.solve_batch(O.flatquad_problem(), oo, ys[:, :4096], n_threads=ncores)
         t0 = time.perf_counter()
         passes = 0
         while True:  # bounded sample: whole passes over the batch until ~10 s of wall time on all host threads
-            O.solve_batch(O.flatquad_problem(), oo, ys)
+            O.solve_batch(O.flatquad_problem(), oo, ys, n_threads=ncores)
             passes += 1
             dtc = time.perf_counter() - t0
             if dtc >= args.cpu_seconds or passes >= 64:
                 break
-        cpu = {"value": passes * ys.shape[1] / dtc, "unit": "trajectories/s", "cores": O.num_threads(), "kind": "port",
+        cpu = {"value": passes * ys.shape[1] / dtc, "unit": "trajectories/s", "cores": ncores, "kind": "port",
                "sample": f"{passes} passes over the first 2^{int(np.log2(ys.shape[1]))} trajectories of the same batch, same "
-                         f"solver settings, {dtc:.1f} s wall on {O.num_threads()} threads; C++ restatement of the reference "
+                         f"solver settings, {dtc:.1f} s wall on {ncores} threads; C++ restatement of the reference "
                          "(jax/diffrax not installable offline)"}
 
     if rank == 0:
