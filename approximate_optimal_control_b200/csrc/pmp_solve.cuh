@@ -8,14 +8,16 @@
 // Design (one thread per trajectory, everything in registers):
 //   * y (2nx+1 dynamic scalars), the stage derivatives k1..kS and the stage state live in registers;
 //     tableau coefficients are compile-time immediates (pmp_tableau.cuh), system constants sit in
-//     the kernel parameter bank.  No shared memory, no local memory for the fp32 flatquad kernel.
+//     the kernel parameter bank.  No shared memory, no local memory for the fp32 flatquad kernel
+//     (the dense write-out and the value-Hessian branch add shared-memory staging, see below).
 //   * Adaptive step control is per lane: every lane of a warp executes one step ATTEMPT per loop
 //     iteration (accept/reject are selects, not branches), so the only divergence is trajectories
 //     finishing at different attempt counts.
 //   * Lane refill: a persistent grid pulls trajectory indices from a global counter in warp-sized
 //     chunks.  After every attempt the warp ballots the lanes whose trajectory finished (reached
-//     t1, event, max_steps, NaN), retires them (endpoint + stats written) and hands each a new
-//     trajectory, so all 32 lanes stay busy until the queue is empty.  The first-stage derivative
+//     t1, event, max_steps, NaN); once refill_min of them wait (parked lanes run dummy attempts
+//     meanwhile) it retires them (endpoint + stats written) and hands each a new trajectory, so
+//     the lanes stay busy until the queue is empty.  The first-stage derivative
 //     k1 = F(y_f) of a fresh trajectory (FSAL) is NOT computed in the divergent refill branch: a
 //     coalesced prep kernel evaluates it for the whole batch up front (1 RHS per trajectory,
 //     ~0.7 % of the work) and the refill just loads it.
