@@ -125,3 +125,60 @@ def test_sharded_allgather_world2_gloo(n, inter):
         p.join(60)
     assert all(ok for (_, ok, _) in res), res
     assert all(shape == (3, n) for (_, _, shape) in res)
+
+
+# ---- host logic of the rows around the path ---------------------------------------------------------------------
+def test_symnp_matches_numpy_on_numbers_and_traces_symbols():
+    """symnp (the jax.numpy stand-in the dynamics are traced with) falls through to numpy on numbers and builds sympy
+    expressions on symbols; both views of the same function agree."""
+    import sympy as sp
+    from approximate_optimal_control_b200 import symnp
+    rng = np.random.Generator(np.random.PCG64(0))
+
+    def g(x, u):  # jax.numpy style, as the reference writes its dynamics
+        M = symnp.array([[symnp.cos(x[2]), -symnp.sin(x[2])], [symnp.sin(x[2]), symnp.cos(x[2])]])
+        v = M @ symnp.array([x[0], x[1]])
+        return symnp.concatenate([v, symnp.array([symnp.maximum(0, x[0] - 1) ** 2 + symnp.exp(-u[0] ** 2) + symnp.tanh(x[1])])])
+
+    xs, us = sp.symbols("a0:3"), sp.symbols("b0:1")
+    expr = g(symnp.SymArray(xs), symnp.SymArray(us))
+    f = sp.lambdify([xs, us], [sp.sympify(e.item() if isinstance(e, np.ndarray) else e) for e in expr], modules="numpy")
+    for _ in range(20):
+        x, u = rng.standard_normal(3) * 2, rng.standard_normal(1)
+        assert np.allclose(np.asarray(f(x, u), dtype=float), np.asarray(g(x, u), dtype=float), rtol=1e-13, atol=1e-13)
+    # jax's 0-d array semantics on symbols: x[0] keeps .reshape() / .T, reshape() without arguments gives a scalar
+    s = symnp.SymArray(xs)
+    assert (s[0] ** 2).reshape((1,)).shape == (1,) and (s[:1] * 2).reshape().shape == ()
+
+
+def test_nn_ensemble_packing_and_normaliser():
+    """flax parameter pytrees -> the flat layout of pmp_nn_costate_t (K1 [nx][W], b1, hidden {K [W][W], b}, Kout [W], bout,
+    3 pad reals per member); data_normaliser statistics and their inverses."""
+    import torch
+    from approximate_optimal_control_b200 import nn_costate as NC
+    nx, W, E = 6, 32, 3
+    p = NC.init_flax_params(1, nx, (W, W), E)
+    rng = np.random.Generator(np.random.PCG64(1))
+    data = {"x": rng.standard_normal((500, nx)) * np.arange(1, nx + 1), "v": rng.standard_normal(500) * 3 + 7}
+    norm = NC.DataNormaliser(data)
+    assert np.allclose(norm.normalise_x(data["x"]).mean(0), 0, atol=1e-12) and np.allclose(norm.normalise_x(data["x"]).std(0), 1)
+    assert np.allclose(norm.unnormalise_v(norm.normalise_v(data["v"])), data["v"])
+    vx = rng.standard_normal((5, nx))
+    assert np.allclose(norm.unnormalise_vx(norm.normalise_vx(vx)), vx)
+    ens = NC.NnEnsemble.from_flax(p, norm, "cpu", torch.float64)
+    stride = nx * W + W + (W * W + W) + W + 4
+    w = ens.weights.numpy().reshape(E, stride)
+    L = p["params"]
+    for e in range(E):
+        assert np.array_equal(w[e, :nx * W].reshape(nx, W), L["Dense_0"]["kernel"][e])
+        assert np.array_equal(w[e, nx * W:nx * W + W], L["Dense_0"]["bias"][e])
+        o = nx * W + W
+        assert np.array_equal(w[e, o:o + W * W].reshape(W, W), L["Dense_1"]["kernel"][e])
+        assert np.array_equal(w[e, o + W * W + W:o + W * W + 2 * W], L["Dense_2"]["kernel"][e][:, 0])
+        assert w[e, o + W * W + 2 * W] == L["Dense_2"]["bias"][e][0] and (w[e, -3:] == 0).all()
+    c = ens.to_c()
+    assert (c.n_nets, c.n_hidden_layers, c.width) == (E, 2, W) and np.isclose(c.x_std[2], norm.x_stds[2]) and c.x_std[10] == 1.0
+    with pytest.raises(NotImplementedError):
+        NC.NnEnsemble.from_flax(NC.init_flax_params(0, nx, (48,), 2), norm, "cpu")  # width not in {32, 64}
+    with pytest.raises(NotImplementedError):
+        NC.NnEnsemble.from_flax(NC.init_flax_params(0, nx, (32, 64), 2), norm, "cpu")  # ragged hidden widths
