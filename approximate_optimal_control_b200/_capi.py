@@ -17,7 +17,7 @@ F32, F64 = 0, 1
 INDEP_TIME, INDEP_VALUE = 0, 1
 EVENT_NONE, EVENT_VALUE_GE, EVENT_VXX_NORM, EVENT_LQR_VALUE_LE, EVENT_NN_VALUE_UCB_LE = 0, 1, 2, 3, 4
 RESULT_OK, RESULT_EVENT, RESULT_MAX_STEPS, RESULT_DT_MIN, RESULT_NAN = 0, 1, 2, 3, 4
-ABI_VERSION = 4
+ABI_VERSION = 5
 FLAG_USTAR_LITERAL = 1
 FLAG_VXX = 2
 FLAG_VXX_SYMMETRIC = 4
@@ -55,7 +55,7 @@ class NnCostate(C.Structure):
 
 
 EXPORTS = ("pmp_abi_version", "pmp_last_error", "pmp_state_rows", "pmp_state_rows_flags", "pmp_device_count",
-           "pmp_solve_workspace_bytes", "pmp_solve_batch_cuda", "pmp_solve_launch_count",
+           "pmp_solve_workspace_bytes", "pmp_solve_batch_cuda", "pmp_solve_launch_count", "pmp_solve_host", "pmp_solve_host_plan", "pmp_host_release",
            "pmp_rhs_batch_cuda", "pmp_rhs_batch_cuda_flags", "pmp_ustar_batch_cuda", "pmp_ustar_batch_cuda_flags", "pmp_interp_batch_cuda", "pmp_forward_batch_cuda", "pmp_forward_nn_batch_cuda", "pmp_nn_value_batch_cuda",
            "pmp_fma_peak_cuda")
 
@@ -102,6 +102,10 @@ def load(path: str) -> C.CDLL:
     L.pmp_solve_batch_cuda.argtypes = [C.POINTER(Problem), C.POINTER(Opts), C.c_int64, C.c_void_p,
                                        C.c_void_p, C.POINTER(Dense), C.c_void_p, C.c_void_p,
                                        C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]
+    L.pmp_solve_host.argtypes = [C.POINTER(Problem), C.POINTER(Opts), C.c_int64] + [C.c_void_p] * 11 + [C.c_int32]
+    L.pmp_solve_host_plan.argtypes = [C.POINTER(Problem), C.POINTER(Opts), C.c_int64, C.c_int32, C.POINTER(C.c_int32),
+                                      C.POINTER(C.c_int32)]
+    L.pmp_host_release.argtypes = []
     L.pmp_rhs_batch_cuda.argtypes = [C.POINTER(Problem), C.c_int32, C.c_int64, C.c_void_p,
                                      C.c_void_p, C.c_void_p]
     L.pmp_state_rows_flags.argtypes = [C.POINTER(Problem), C.c_int32]

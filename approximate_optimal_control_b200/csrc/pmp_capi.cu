@@ -3,6 +3,7 @@
 
 #include <cstdio>
 #include <string>
+#include <vector>
 
 #include "../../include/b200pmp.h"
 
@@ -30,6 +31,11 @@ int forward_batch(const pmp_problem_t& p, const pmp_opts_t& o, long long n, cons
                   int32_t* s, int32_t* r, cudaStream_t st);
 int nn_value_batch(const pmp_problem_t& p, const pmp_nn_costate_t* nn, int dtype, long long n, const void* x, void* lam,
                    void* vm, void* vs, cudaStream_t st);
+int solve_host(const pmp_problem_t& p, const pmp_opts_t& o, long long n, const void* x_f, const void* t_f, const void* v_f,
+               const void* vx_f, void* x_end, void* t_end, void* v_end, void* vx_end, int32_t* n_accepted, int32_t* n_steps,
+               int32_t* result, int n_pieces);
+int host_plan(long long n, int n_pieces, std::vector<long long>* bounds, long long* cs_max);
+int host_release();
 int fma_peak(int dtype, int variant, int iters, void* scratch, double* flops_out, cudaStream_t st);
 int interp_batch(const pmp_problem_t& p, const pmp_opts_t& o, long long nq, const void* y0, const void* t1,
                  const void* target, void* y_out, int mode, cudaStream_t st);
@@ -200,6 +206,44 @@ int pmp_solve_batch_cuda(const pmp_problem_t* p, const pmp_opts_t* o, int64_t n,
     if (rc == -1000) return fail(PMP_ERR_UNSUPPORTED, "no kernel for this (system, dtype, method) combination");
     if (rc != 0) return cuda_fail(rc);
     return PMP_OK;
+}
+
+static int check_host(const pmp_problem_t* p, const pmp_opts_t* o, int64_t n, int32_t n_pieces) {
+    if (int e = check_problem(p)) return e;
+    if (int e = check_opts(o)) return e;
+    if (int e = check_pair(p, o)) return e;
+    if (o->save_dense || (o->flags & PMP_FLAG_VXX))
+        return fail(PMP_ERR_UNSUPPORTED, "pmp_solve_host returns endpoints only: save_dense / PMP_FLAG_VXX go through "
+                                         "pmp_solve_batch_cuda with device buffers");
+    if (n < 0) return fail(PMP_ERR_BAD_ARG, "n < 0");
+    if (n_pieces < 0 || n_pieces > 1024) return fail(PMP_ERR_BAD_ARG, "n_pieces must be in 0..1024");
+    return 0;
+}
+
+int pmp_solve_host(const pmp_problem_t* p, const pmp_opts_t* o, int64_t n, const void* x_f, const void* t_f, const void* v_f,
+                   const void* vx_f, void* x_end, void* t_end, void* v_end, void* vx_end, int32_t* n_accepted,
+                   int32_t* n_steps, int32_t* result, int32_t n_pieces) {
+    if (int e = check_host(p, o, n, n_pieces)) return e;
+    if (n == 0) return PMP_OK;
+    if (!x_f || !v_f || !vx_f) return fail(PMP_ERR_BAD_ARG, "x_f / v_f / vx_f is NULL");
+    if (pmp_device_count() <= 0) return fail(PMP_ERR_NO_DEVICE, "no CUDA device: libb200pmp has no CPU fallback");
+    int rc = pmp::solve_host(*p, *o, n, x_f, t_f, v_f, vx_f, x_end, t_end, v_end, vx_end, n_accepted, n_steps, result, n_pieces);
+    if (rc > 0) return cuda_fail(rc);
+    return rc;  // < 0: recorded by pmp_solve_batch_cuda
+}
+
+int pmp_solve_host_plan(const pmp_problem_t* p, const pmp_opts_t* o, int64_t n, int32_t n_pieces, int32_t* kernels,
+                        int32_t* copies) {
+    if (int e = check_host(p, o, n, n_pieces)) return e;
+    const int pieces = n > 0 ? pmp::host_plan(n, n_pieces, nullptr, nullptr) : 0;
+    if (kernels) *kernels = pieces * (2 + pmp_solve_launch_count(p, o, 1));  // pack + solve + unpack
+    if (copies) *copies = pieces * (4 + 7);  // leaves in, leaves + counters out (all outputs requested, t_f given)
+    return pieces;
+}
+
+int pmp_host_release(void) {
+    int rc = pmp::host_release();
+    return rc ? cuda_fail(rc) : PMP_OK;
 }
 
 int pmp_rhs_batch_cuda(const pmp_problem_t* p, int32_t dtype, int64_t n, const void* y, void* dy, void* cuda_stream) {

@@ -257,74 +257,49 @@ def _interp(problem, opts, nx, sol: Solution, target, mode: int):
     return d
 
 
-# ---- host in -> host out: chunked pipeline ----------------------------------------------------------------------
-_pipes: Dict[int, dict] = {}
-
-
+# ---- host in -> host out: pmp_solve_host ------------------------------------------------------------------------
 def _host_leaf(a) -> bool:
     return isinstance(a, np.ndarray) or (isinstance(a, torch.Tensor) and not a.is_cuda)
 
 
-def _solve_host_pipelined(problem, opts, nx, y_f, dtype, dev, n_chunks):
-    """solve_backward for HOST inputs (the reference's habitat: everything lives in host memory): the batch is cut into
-    n_chunks pieces; the host->device copy of piece c+1 and the device->host copy of piece c-1's endpoints run on their
-    own streams (copy engines, both PCIe directions at once) while piece c is integrated.  Endpoints, step counts and
-    result codes come back in pinned host tensors.  Measured on 2^20 flatquad rollouts from pinned tensors: 2.0 ms per
-    call instead of 3.6 ms for copy-in, solve, copy-out one after the other."""
-    host = lambda a: a if isinstance(a, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(a))
-    x, vx = host(y_f["x"]).to(dtype), host(y_f["vx"]).to(dtype)
+def _solve_host_pipelined(problem, opts, nx, y_f, dtype, dev, n_pieces=0):
+    """solve_backward for HOST inputs (the reference's habitat: everything lives in host memory): one call of
+    pmp_solve_host (csrc/pmp_host.cu), which cuts the batch into pieces and overlaps the host->device copy, the
+    integration and the device->host copy of neighbouring pieces on its own streams.  Endpoints, step counts and result
+    codes come back in pinned host tensors.  Inputs overlap only if they are pinned too (torch pin_memory); pageable
+    numpy arrays work, the copies then serialise."""
+    host = lambda a: (a if isinstance(a, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(a))).to(dtype).contiguous()
+    x, vx = host(y_f["x"]), host(y_f["vx"])
     n = x.shape[0]
-    full = lambda a: host(np.asarray(a) if not isinstance(a, torch.Tensor) else a).to(dtype).reshape(-1).expand(n)
-    t, v = full(y_f.get("t", 0.0)), full(y_f["v"])
-    key = dev.index or 0
-    pipe = _pipes.get(key)
-    if pipe is None:
-        pipe = _pipes[key] = {"s": [torch.cuda.Stream(dev) for _ in range(3)], "buf": {}}
-    s_in, s_comp, s_out = pipe["s"]
-    cs = (n + n_chunks - 1) // n_chunks
-    bkey = (cs, dtype)
-    if bkey not in pipe["buf"]:  # two sets of device staging buffers
-        mk = lambda *shape, dt=dtype: torch.empty(shape, dtype=dt, device=dev)
-        pipe["buf"] = {bkey: [dict(x=mk(cs, nx), vx=mk(cs, nx), t=mk(cs), v=mk(cs), y=mk(2 * nx + 2, cs), y_end=mk(2 * nx + 2, cs),
-                                   ox=mk(cs, nx), ovx=mk(cs, nx), n_accepted=mk(cs, dt=torch.int32), n_steps=mk(cs, dt=torch.int32),
-                                   result=mk(cs, dt=torch.int32)) for _ in range(2)]}
-    bufs = pipe["buf"][bkey]
+    if x.shape != (n, nx) or vx.shape != (n, nx):
+        raise ValueError(f"'x', 'vx' must be [n, {nx}]")
+
+    def per_traj(a, name):  # [n] leaf; scalars are broadcast
+        a = host(np.asarray(a) if not isinstance(a, torch.Tensor) else a).reshape(-1)
+        if a.numel() == 1 and n != 1:
+            a = a.expand(n).contiguous()
+        if a.numel() != n:
+            raise ValueError(f"'{name}' must be a scalar or [n]")
+        return a
+
+    v = per_traj(y_f["v"], "v")
+    t = None
+    if "t" in y_f:
+        t_in = y_f["t"]
+        if np.ndim(t_in) == 0 or np.size(t_in) == 1 and n != 1:
+            if float(np.asarray(t_in).reshape(-1)[0]) != float(opts.t0):
+                t = per_traj(t_in, "t")
+        else:
+            t = per_traj(t_in, "t")
     pin = lambda *shape, dt=dtype: torch.empty(shape, dtype=dt, pin_memory=True)
     ho = dict(x=pin(n, nx), t=pin(n), v=pin(n), vx=pin(n, nx), n_accepted=pin(n, dt=torch.int32), n_steps=pin(n, dt=torch.int32),
               result=pin(n, dt=torch.int32))
-    ev_in = [torch.cuda.Event() for _ in range(2)]
-    ev_comp = [torch.cuda.Event() for _ in range(2)]
-    ev_out = [torch.cuda.Event() for _ in range(2)]
-    for c in range(n_chunks):
-        a, b = c * cs, min(n, (c + 1) * cs)
-        m = b - a
-        B = bufs[c % 2]
-        with torch.cuda.stream(s_in):
-            if c >= 2:
-                s_in.wait_event(ev_comp[c % 2])  # the solve of piece c-2 has consumed this staging set
-            B["x"][:m].copy_(x[a:b], non_blocking=True); B["vx"][:m].copy_(vx[a:b], non_blocking=True)
-            B["t"][:m].copy_(t[a:b], non_blocking=True); B["v"][:m].copy_(v[a:b], non_blocking=True)
-            ev_in[c % 2].record(s_in)
-        with torch.cuda.stream(s_comp):
-            s_comp.wait_event(ev_in[c % 2])
-            if c >= 2:
-                s_comp.wait_event(ev_out[c % 2])  # piece c-2's endpoints have left this staging set
-            y = B["y"][:, :m] if m == cs else torch.empty((2 * nx + 2, m), dtype=dtype, device=dev)
-            y[:nx] = B["x"][:m].t(); y[nx] = B["t"][:m]; y[nx + 1] = B["v"][:m]; y[nx + 2:] = B["vx"][:m].t()
-            out = dict(y_end=B["y_end"][:, :m] if m == cs else torch.empty_like(y), n_accepted=B["n_accepted"][:m],
-                       n_steps=B["n_steps"][:m], result=B["result"][:m])
-            solve_batch_soa(problem, opts, y.contiguous(), out)
-            ye = out["y_end"]
-            B["ox"][:m] = ye[:nx].t(); B["ovx"][:m] = ye[nx + 2:].t()
-            ev_comp[c % 2].record(s_comp)
-        with torch.cuda.stream(s_out):
-            s_out.wait_event(ev_comp[c % 2])
-            ho["x"][a:b].copy_(B["ox"][:m], non_blocking=True); ho["vx"][a:b].copy_(B["ovx"][:m], non_blocking=True)
-            ho["t"][a:b].copy_(ye[nx], non_blocking=True); ho["v"][a:b].copy_(ye[nx + 1], non_blocking=True)
-            for k in ("n_accepted", "n_steps", "result"):
-                ho[k][a:b].copy_(out[k], non_blocking=True)
-            ev_out[c % 2].record(s_out)
-    s_out.synchronize()
+    L = _capi.lib_of(problem)
+    with torch.cuda.device(dev):
+        _capi.check(L.pmp_solve_host(C.byref(problem), C.byref(opts), n, x.data_ptr(), t.data_ptr() if t is not None else None,
+                                     v.data_ptr(), vx.data_ptr(), ho["x"].data_ptr(), ho["t"].data_ptr(), ho["v"].data_ptr(),
+                                     ho["vx"].data_ptr(), ho["n_accepted"].data_ptr(), ho["n_steps"].data_ptr(),
+                                     ho["result"].data_ptr(), int(n_pieces)), L)
     stats = {"num_steps": ho["n_steps"], "num_accepted_steps": ho["n_accepted"],
              "num_rejected_steps": ho["n_steps"] - ho["n_accepted"]}
     return Solution(t0=opts.t0, t1=opts.t1, ts=None, ys=None, y_end={k: ho[k] for k in ("x", "t", "v", "vx")}, stats=stats,
@@ -402,12 +377,13 @@ def define_backward_solver(problem_params: dict, algo_params: dict):
         if save_steps is None:
             save_steps = bool(algo_params.get("pontryagin_solver_save_steps", True))
         dt0 = float(algo_params.get("pontryagin_solver_dt0", _DEFAULTS["dt0"]))
-        # host in -> host out: large endpoint-only batches handed over in host memory go through the chunked pipeline
-        # (results in pinned host tensors); 'pontryagin_solver_host_chunks': 0 disables, k forces k pieces
+        # host in -> host out: endpoint-only batches handed over in host memory go through pmp_solve_host (results in
+        # pinned host tensors); 'pontryagin_solver_host_chunks': -1 disables (device tensors come back), 0 lets the
+        # library choose the number of pieces, k forces k
         if (not with_vxx and not save_steps and _host_leaf(y_f["x"]) and _host_leaf(y_f["vx"]) and np.ndim(y_f["x"]) == 2):
             n_all = int(np.shape(y_f["x"])[0])
-            chunks = int(algo_params.get("pontryagin_solver_host_chunks", 4 if n_all >= (1 << 19) else (2 if n_all >= (1 << 18) else 0)))
-            if chunks >= 2:
+            chunks = int(algo_params.get("pontryagin_solver_host_chunks", 0 if n_all >= (1 << 16) else -1))
+            if chunks >= 0:
                 opts = _solver_opts(algo_params, dtype, t0=0.0, t1=-T, dt0=-abs(dt0), adaptive=int(adaptive), save_dense=0)
                 return _solve_host_pipelined(problem, opts, nx, y_f, dtype, dev, chunks)
         y, batched = pack_state(y_f, nx, dtype, dev, with_vxx)

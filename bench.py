@@ -358,6 +358,8 @@ def main():
         host_out = {k: torch.empty(v.shape, dtype=tdt).pin_memory() for k, v in st_np.items()}
         h2d = sum(v.numel() * v.element_size() for v in host_in.values())
         d2h = sum(v.numel() * v.element_size() for v in host_out.values())
+        if not dense:
+            d2h += 3 * n * 4  # num_accepted_steps, num_steps, result come back with the endpoints
 
         def e2e_step():
             if dense:  # dense solutions stay on the device (8 GB per step); only the endpoints travel back
@@ -367,9 +369,9 @@ def main():
                     host_out[k].copy_(ye[k], non_blocking=True)
                 torch.cuda.synchronize()
                 return
-            # host in -> host out: the public call with pinned host tensors; it cuts the batch into pieces and overlaps
-            # the copies of neighbouring pieces with the integration (pontryagin_utils._solve_host_pipelined); the
-            # endpoints come back in pinned host memory
+            # host in -> host out: the public call with pinned host tensors goes to pmp_solve_host (csrc/pmp_host.cu),
+            # which cuts the batch into pieces and overlaps the copies of neighbouring pieces with the integration; the
+            # endpoints and per-trajectory counters come back in pinned host memory
             sol = solve_backward(host_in)
             assert not sol.y_end["x"].is_cuda and sol.y_end["x"].shape == host_in["x"].shape
 
@@ -386,7 +388,8 @@ def main():
         e2e = {"value": n * world * args.steps / e_s.item(), "unit": "trajectories/s",
                "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                "api": "pontryagin_utils.define_backward_solver(...)[0](state dict of pinned host tensors) -> endpoints in pinned "
-                      "host tensors; the call pipelines host->device copy, integration and device->host copy over 4 pieces"
+                      "host tensors through the C entry pmp_solve_host (host pointers), which pipelines host->device copy, integration "
+                      "and device->host copy over pieces on its own streams"
                       if not dense else "define_backward_solver(...)[0](device state dict) after an explicit host->device copy; "
                       "endpoints copied back to pinned host memory, dense nodes stay on the device"}
 

@@ -8,6 +8,8 @@
  *   pmp_solve_batch_cuda   <- jax.vmap(solve_backward)            pontryagin_utils.py:488-527 as
  *                             vmapped at levelsets.py:601,1254; and the missing value-reparameterised
  *                             solver called at experiment_orbits.py:117,182, rrt_sampler.py:64-70
+ *   pmp_solve_host         <- the same call as a host-language binding makes it: the reference's state dict
+ *                             leaves in HOST memory in, endpoints in HOST memory out (levelsets.py:595-601,1215)
  *   pmp_rhs_batch_cuda     <- jax.vmap(f_extended)                pontryagin_utils.py:418-482
  *   pmp_ustar_batch_cuda   <- jax.vmap(u_star_2d) / u_star_new    pontryagin_utils.py:11-216, :532-562
  *                             (batched at levelsets.py:604-628 find_min_l)
@@ -23,7 +25,8 @@
  *     passed as void*; NULL = the legacy default stream).
  *   - every *_cuda pointer argument is a DEVICE pointer owned by the caller; nothing is allocated,
  *     nothing is freed, no hidden host<->device copy, no synchronisation: the call enqueues work on
- *     `cuda_stream` and returns.
+ *     `cuda_stream` and returns.  The one exception is pmp_solve_host (host pointers, synchronous, owns its
+ *     staging memory and streams).
  *   - return value 0 = ok, <0 = error (PMP_ERR_*); pmp_last_error() gives a thread-local message.
  *     Functions never throw and never abort.
  *   - real arrays are float (dtype 0) or double (dtype 1), chosen by pmp_opts_t.dtype.
@@ -46,7 +49,7 @@
 extern "C" {
 #endif
 
-#define PMP_ABI_VERSION 4
+#define PMP_ABI_VERSION 5
 
 /* systems (dynamics are compile-time functors; problem_params['system_name'] selects one) */
 enum {
@@ -193,6 +196,25 @@ int pmp_solve_batch_cuda(const pmp_problem_t *problem, const pmp_opts_t *opts, i
                          const void *y_f, void *y_end, const pmp_dense_t *dense,
                          int32_t *n_accepted, int32_t *n_steps, int32_t *result,
                          void *workspace, int64_t workspace_bytes, void *cuda_stream);
+
+/* Host in -> host out.  The terminal states arrive as the leaves of the reference's state dict (pontryagin_utils.py:
+ * 454-458), row-major in HOST memory: x_f [n][nx], t_f [n] (NULL: every trajectory starts at opts->t0), v_f [n],
+ * vx_f [n][nx]; the endpoints (ys[num_accepted_steps], levelsets.py:1215) come back the same way in x_end, t_end,
+ * v_end, vx_end, with n_accepted, n_steps, result [n] int32 (any output may be NULL).  The batch is cut into n_pieces
+ * pieces (0 = choose: a small first piece, growing to n/8) whose host->device copies, integration and device->host copies overlap on the library's own
+ * streams of the CURRENT device; the copies overlap only from/to page-locked memory (cudaHostAlloc / cudaHostRegister,
+ * torch pin_memory), pageable buffers work but serialise.  Returns when every output is in host memory.  Device
+ * staging (~(8nx+7) reals per trajectory of three pieces) is kept between calls; pmp_host_release() frees it.
+ * Concurrent calls on one device are serialised.  Endpoints only: save_dense and PMP_FLAG_VXX are refused.
+ * Results are bit-identical to pmp_solve_batch_cuda on the same states. */
+int pmp_solve_host(const pmp_problem_t *problem, const pmp_opts_t *opts, int64_t n,
+                   const void *x_f, const void *t_f, const void *v_f, const void *vx_f,
+                   void *x_end, void *t_end, void *v_end, void *vx_end,
+                   int32_t *n_accepted, int32_t *n_steps, int32_t *result, int32_t n_pieces);
+/* kernels + copies one pmp_solve_host call enqueues: *kernels, *copies (bench bookkeeping); returns the piece count */
+int pmp_solve_host_plan(const pmp_problem_t *problem, const pmp_opts_t *opts, int64_t n, int32_t n_pieces,
+                        int32_t *kernels, int32_t *copies);
+int pmp_host_release(void);
 
 /* number of kernels one pmp_solve_batch_cuda call launches with these options (bench bookkeeping) */
 int pmp_solve_launch_count(const pmp_problem_t *problem, const pmp_opts_t *opts, int64_t n);

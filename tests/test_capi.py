@@ -123,6 +123,26 @@ def test_argument_validation_and_error_strings():
         _capi.check(-1)
 
 
+def test_solve_host_validation_and_plan():
+    """pmp_solve_host: argument checks run before any CUDA call; the plan (pieces, kernels, copies) is host logic."""
+    L = _capi.lib()
+    prob, _ = c_problem("flatquad")
+    o = _capi.make_opts()
+    nul = [None] * 11
+    assert L.pmp_solve_host(C.byref(prob), C.byref(o), -1, *nul, 0) == -1
+    assert L.pmp_solve_host(C.byref(prob), C.byref(o), 0, *nul, 0) == 0
+    assert L.pmp_solve_host(C.byref(prob), C.byref(o), 8, *nul, 0) == -1 and b"x_f" in L.pmp_last_error()
+    assert L.pmp_solve_host(C.byref(prob), C.byref(o), 8, *nul, -2) == -1 and b"n_pieces" in L.pmp_last_error()
+    for kw in (dict(save_dense=1), dict(flags=_capi.FLAG_VXX)):
+        ob = _capi.make_opts(**kw)
+        assert L.pmp_solve_host(C.byref(prob), C.byref(ob), 8, *nul, 0) == -2 and b"endpoints only" in L.pmp_last_error()
+    k, c = C.c_int32(), C.c_int32()
+    for n, req, pieces in ((1 << 20, 0, 10), (1 << 18, 0, 5), (1000, 0, 1), (1 << 20, 3, 3), (100, 8, 1), (0, 0, 0)):
+        assert L.pmp_solve_host_plan(C.byref(prob), C.byref(o), n, req, C.byref(k), C.byref(c)) == pieces, (n, req)
+        assert k.value == 4 * pieces and c.value == 11 * pieces
+    assert L.pmp_host_release() == 0  # nothing allocated: a no-op
+
+
 def test_no_cpu_fallback_without_gpu():
     """The product path must fail loudly when no CUDA device is present."""
     import torch
@@ -135,6 +155,9 @@ def test_no_cpu_fallback_without_gpu():
     assert L.pmp_rhs_batch_cuda(C.byref(prob), _capi.F32, 8, y.ctypes.data, y.ctypes.data, None) == _capi.lib().pmp_rhs_batch_cuda(
         C.byref(prob), _capi.F32, 8, y.ctypes.data, y.ctypes.data, None) == -4
     assert b"no CPU fallback" in L.pmp_last_error()
+    x = np.zeros((8, 6), np.float32)
+    o = _capi.make_opts()
+    assert L.pmp_solve_host(C.byref(prob), C.byref(o), 8, x.ctypes.data, None, x.ctypes.data, x.ctypes.data, *([None] * 7), 0) == -4
     from approximate_optimal_control_b200 import pontryagin_utils as pu
     solve_backward, f_extended = pu.define_backward_solver(pp, systems.flatquad_algo_params())
     st = {"x": np.zeros(6, np.float32), "t": 0, "v": np.float32(0), "vx": np.zeros(6, np.float32)}

@@ -483,6 +483,51 @@ def test_host_in_host_out_pipeline_equals_device_path():
     assert small.y_end["x"].is_cuda
 
 
+@pytest.mark.parametrize("name,dtype,n,pieces", [("flatquad", _capi.F32, 100003, 0), ("flatquad", _capi.F32, 100003, 7),
+                                                  ("flatquad", _capi.F64, 40001, 3), ("orbits", _capi.F64, 5000, 5),
+                                                  ("lqr", _capi.F32, 129, 2), ("flatquad", _capi.F32, 1 << 19, 0)])
+def test_solve_host_c_abi_bit_identical_to_device_solve(name, dtype, n, pieces):
+    """pmp_solve_host (host pointers in the reference's state-dict layout, pipelined pieces) returns exactly what
+    pmp_solve_batch_cuda returns for the same terminal states; ragged last piece, NULL t_f, NULL outputs."""
+    import ctypes as C
+    import torch
+    from common import c_problem
+    mk = {"flatquad": flatquad_terminal, "orbits": orbits_terminal, "lqr": lqr_terminal}[name]
+    npdt = np.float32 if dtype == _capi.F32 else np.float64
+    y = np.ascontiguousarray(mk(n), dtype=npdt)
+    prob, _ = c_problem(name)
+    nx = prob.nx
+    kw = dict(method="tsit5", dtype=dtype, rtol=1e-5, atol=1e-5, max_steps=512)
+    if name != "flatquad":
+        kw.update(t1=-3.0)
+    opts = _capi.make_opts(**kw)
+    ref = cuda_solve(prob, opts, y)
+    L = _capi.lib_of(prob)
+    pin = lambda a: torch.as_tensor(np.ascontiguousarray(a)).pin_memory()
+    x, vx, t, v = pin(y[:nx].T), pin(y[nx + 2:].T), pin(y[nx]), pin(y[nx + 1])
+    assert (y[nx] == opts.t0).all()
+    o = {k: torch.empty(s, dtype=d).pin_memory() for k, s, d in (("x", (n, nx), x.dtype), ("vx", (n, nx), x.dtype), ("t", (n,), x.dtype),
+         ("v", (n,), x.dtype), ("na", (n,), torch.int32), ("ns", (n,), torch.int32), ("res", (n,), torch.int32))}
+    for with_t in (True, False):  # t_f = NULL starts every trajectory at opts.t0
+        for q in o.values():
+            q.fill_(-7)
+        _capi.check(L.pmp_solve_host(C.byref(prob), C.byref(opts), n, x.data_ptr(), t.data_ptr() if with_t else None, v.data_ptr(),
+                                     vx.data_ptr(), o["x"].data_ptr(), o["t"].data_ptr(), o["v"].data_ptr(), o["vx"].data_ptr(),
+                                     o["na"].data_ptr(), o["ns"].data_ptr(), o["res"].data_ptr(), pieces), L)
+        ye = ref["y_end"]
+        assert np.array_equal(o["x"].numpy(), ye[:nx].T, equal_nan=True) and np.array_equal(o["vx"].numpy(), ye[nx + 2:].T, equal_nan=True)
+        assert np.array_equal(o["t"].numpy(), ye[nx], equal_nan=True) and np.array_equal(o["v"].numpy(), ye[nx + 1], equal_nan=True)
+        assert np.array_equal(o["na"].numpy(), ref["n_accepted"]) and np.array_equal(o["ns"].numpy(), ref["n_steps"])
+        assert np.array_equal(o["res"].numpy(), ref["result"])
+    # pageable numpy inputs, only the value leaf requested
+    v_only = np.full(n, -7, npdt)
+    xa, vxa, va = (np.ascontiguousarray(a) for a in (y[:nx].T, y[nx + 2:].T, y[nx + 1]))
+    _capi.check(L.pmp_solve_host(C.byref(prob), C.byref(opts), n, xa.ctypes.data, None, va.ctypes.data, vxa.ctypes.data,
+                                 None, None, v_only.ctypes.data, None, None, None, None, pieces), L)
+    assert np.array_equal(v_only, ref["y_end"][nx + 1], equal_nan=True)
+    assert L.pmp_host_release() == 0
+
+
 def flatquad_P_():
     from common import flatquad_P
     return flatquad_P()
