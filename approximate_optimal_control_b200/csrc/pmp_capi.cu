@@ -237,7 +237,9 @@ int pmp_solve_host_plan(const pmp_problem_t* p, const pmp_opts_t* o, int64_t n, 
     if (int e = check_host(p, o, n, n_pieces)) return e;
     const int pieces = n > 0 ? pmp::host_plan(n, n_pieces, nullptr, nullptr) : 0;
     if (kernels) *kernels = pieces * (2 + pmp_solve_launch_count(p, o, 1));  // pack + solve + unpack
-    if (copies) *copies = pieces * (4 + 7);  // leaves in, leaves + counters out (all outputs requested, t_f given)
+    // leaves in; leaves + counters out (all outputs requested, t_f given; the counters travel as one packed word when
+    // max_steps < 2^14)
+    if (copies) *copies = pieces * (4 + (o->max_steps < (1 << 14) ? 5 : 7));
     return pieces;
 }
 

@@ -33,6 +33,9 @@ struct HostPipe {
     cudaEvent_t ev_in[kSets], ev_pack[kSets], ev_comp[kSets], ev_out[kSets];
     char* buf[kSets] = {nullptr, nullptr, nullptr};
     size_t cap = 0;  // bytes per set
+    uint32_t* h_packed = nullptr;  // pinned host staging of the packed counters, [n]
+    size_t h_cap = 0;
+    std::vector<cudaEvent_t> ev_piece;  // device->host copies of piece c have landed
 };
 HostPipe g_pipe[kMaxDev];
 std::mutex g_mu;
@@ -53,14 +56,38 @@ __global__ void pack_kernel(int nx, long long m, const R* __restrict__ x, const 
     y[(nx + 1) * m + i] = v[i];
 }
 
+// also folds the three per-trajectory counters into one word (accepted: bits 0-13, attempts: 14-27, result: 28-31;
+// max_steps < 2^14) so that they cross the link as 4 bytes instead of 12; unpack_counters() undoes it on the host
+constexpr int kPackBits = 14;
 template <typename R>
-__global__ void unpack_kernel(int nx, long long m, const R* __restrict__ y, R* __restrict__ x, R* __restrict__ vx) {
+__global__ void unpack_kernel(int nx, long long m, const R* __restrict__ y, R* __restrict__ x, R* __restrict__ vx,
+                              const int32_t* __restrict__ na, const int32_t* __restrict__ ns, const int32_t* __restrict__ res,
+                              uint32_t* __restrict__ packed) {
     const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
     if (i >= m) return;
-    for (int q = 0; q < nx; q++) {
-        x[i * nx + q] = y[q * m + i];
-        vx[i * nx + q] = y[(nx + 2 + q) * m + i];
+    if (x)
+        for (int q = 0; q < nx; q++) {
+            x[i * nx + q] = y[q * m + i];
+            vx[i * nx + q] = y[(nx + 2 + q) * m + i];
+        }
+    if (packed) packed[i] = (uint32_t)na[i] | ((uint32_t)ns[i] << kPackBits) | ((uint32_t)res[i] << (2 * kPackBits));
+}
+
+void unpack_counters(const uint32_t* __restrict__ packed, long long m, int32_t* __restrict__ na, int32_t* __restrict__ ns,
+                     int32_t* __restrict__ res) {
+    constexpr uint32_t mask = (1u << kPackBits) - 1u;
+    if (na && ns && res) {  // one pass: a load and three stores per trajectory
+        for (long long i = 0; i < m; i++) {
+            const uint32_t w = packed[i];
+            na[i] = (int32_t)(w & mask);
+            ns[i] = (int32_t)((w >> kPackBits) & mask);
+            res[i] = (int32_t)(w >> (2 * kPackBits));
+        }
+        return;
     }
+    if (na) for (long long i = 0; i < m; i++) na[i] = (int32_t)(packed[i] & mask);
+    if (ns) for (long long i = 0; i < m; i++) ns[i] = (int32_t)((packed[i] >> kPackBits) & mask);
+    if (res) for (long long i = 0; i < m; i++) res[i] = (int32_t)(packed[i] >> (2 * kPackBits));
 }
 
 #define PMP_TRY(call)                               \
@@ -68,6 +95,21 @@ __global__ void unpack_kernel(int nx, long long m, const R* __restrict__ y, R* _
         cudaError_t e_ = (call);                    \
         if (e_ != cudaSuccess) return (int)e_;      \
     } while (0)
+
+int ensure_packed(HostPipe& P, size_t n, int pieces) {
+    if (n * 4 > P.h_cap) {
+        if (P.h_packed) PMP_TRY(cudaFreeHost(P.h_packed));
+        P.h_packed = nullptr; P.h_cap = 0;
+        PMP_TRY(cudaHostAlloc((void**)&P.h_packed, n * 4, cudaHostAllocDefault));
+        P.h_cap = n * 4;
+    }
+    while ((int)P.ev_piece.size() < pieces) {
+        cudaEvent_t e;
+        PMP_TRY(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+        P.ev_piece.push_back(e);
+    }
+    return 0;
+}
 
 int ensure(HostPipe& P, size_t need) {
     if (!P.ready) {
@@ -97,29 +139,33 @@ int ensure(HostPipe& P, size_t need) {
 }  // namespace
 
 // Piece boundaries for a batch of n (sizes are multiples of 128 trajectories).  n_pieces > 0: that many equal pieces.
-// n_pieces == 0: the device->host stream is the bottleneck of the pipeline and idles until the first piece has been
-// copied in and integrated, so the first piece is small (n/32, at least 2^15) and the sizes double up to n/8 (at least 2^16).
+// n_pieces == 0: the device->host stream is the bottleneck of the pipeline; it idles until the first piece has been
+// copied in and integrated, and the call ends with the last piece's copy-out and counter unfolding.  So the plan starts
+// and ends with small pieces (a = n/32, at least 2^15): a, 2a, [pieces of <= n/8], 2a, a.
 int host_plan(long long n, int n_pieces, std::vector<long long>* bounds, long long* cs_max) {
     auto up128 = [](long long v) { return std::max<long long>(128, (v + 127) & ~127LL); };
+    std::vector<long long> sizes;
+    const long long a = std::max<long long>(1LL << 15, up128(n / 32));
+    if (n_pieces > 0 || n < 8 * a) {
+        if (n_pieces <= 0) n_pieces = (int)std::max<long long>(1, n >> 16);  // 2^16 .. 2^18: pieces of 2^16
+        const long long cs = up128((n + n_pieces - 1) / n_pieces);
+        for (long long done = 0; done < n; done += cs) sizes.push_back(std::min(cs, n - done));
+    } else {
+        const long long cap = std::max<long long>(1LL << 16, up128(n / 8)), mid = n - 6 * a;
+        const long long k = (mid + cap - 1) / cap, cs = up128((mid + k - 1) / k);
+        sizes = {a, 2 * a};
+        for (long long done = 0; done < mid; done += cs) sizes.push_back(std::min(cs, mid - done));
+        sizes.push_back(2 * a);
+        sizes.push_back(a);
+    }
     std::vector<long long> b{0};
     long long biggest = 0;
-    if (n_pieces > 0 || n < (1LL << 17)) {
-        const long long cs = up128((n + std::max(1, n_pieces) - 1) / std::max(1, n_pieces));
-        for (long long a = 0; a < n; a += cs) b.push_back(std::min(n, a + cs));
-        biggest = std::min(cs, n);
-    } else {
-        const long long cap = std::max<long long>(1LL << 16, up128(n / 8));
-        long long cs = std::min(cap, std::max<long long>(1LL << 15, up128(n / 32)));
-        for (long long a = 0; a < n;) {
-            const long long m = std::min(cs, n - a);
-            a += m;
-            b.push_back(a);
-            biggest = std::max(biggest, m);
-            cs = std::min(cap, 2 * cs);
-        }
+    for (long long m : sizes) {
+        b.push_back(b.back() + m);
+        biggest = std::max(biggest, m);
     }
     if (cs_max) *cs_max = up128(biggest);
-    const int count = (int)b.size() - 1;
+    const int count = (int)sizes.size();
     if (bounds) *bounds = std::move(b);
     return count;
 }
@@ -141,11 +187,15 @@ int solve_host(const pmp_problem_t& p, const pmp_opts_t& o, long long n, const v
     if (ws_bytes < 0) return (int)ws_bytes;
     // one staging set: leaves in, y, y_end, leaves out (x, vx), three int arrays, solver workspace
     const size_t o_in = 0, o_y = o_in + up256(NS * cs * es), o_ye = o_y + up256(NS * cs * es), o_ox = o_ye + up256(NS * cs * es),
-                 o_int = o_ox + up256(2 * nx * cs * es), o_ws = o_int + up256(3 * cs * 4), total = o_ws + up256((size_t)ws_bytes);
+                 o_int = o_ox + up256(2 * nx * cs * es), o_ws = o_int + up256(4 * cs * 4), total = o_ws + up256((size_t)ws_bytes);
 
     std::lock_guard<std::mutex> lock(g_mu);
     HostPipe& P = g_pipe[dev];
     if (int e = ensure(P, total)) return e;
+    // counters travel packed when at least two of them are wanted and they fit the fields
+    const bool pack = ((n_accepted != nullptr) + (n_steps != nullptr) + (result != nullptr)) >= 2 && o.max_steps < (1 << kPackBits);
+    if (pack)
+        if (int e = ensure_packed(P, (size_t)n, n_pieces)) return e;
 
     // B200PMP_HOST_TRACE=1: timestamps of every piece's stages on stderr (diagnostics; adds timed events)
     const bool trace = getenv("B200PMP_HOST_TRACE") != nullptr;
@@ -167,6 +217,7 @@ int solve_host(const pmp_problem_t& p, const pmp_opts_t& o, long long n, const v
         char *d_x = B + o_in, *d_vx = d_x + cs * nx * es, *d_t = d_vx + cs * nx * es, *d_v = d_t + cs * es;
         char *d_y = B + o_y, *d_ye = B + o_ye, *d_ox = B + o_ox, *d_ovx = d_ox + cs * nx * es;
         int32_t *d_na = (int32_t*)(B + o_int), *d_ns = d_na + cs, *d_res = d_ns + cs;
+        uint32_t* d_pk = (uint32_t*)(d_res + cs);
 
         // host -> device; the leaves-in area of this set is free once piece c - kSets has been packed
         if (c >= kSets) PMP_TRY(cudaStreamWaitEvent(P.s_in, P.ev_pack[k], 0));
@@ -191,11 +242,14 @@ int solve_host(const pmp_problem_t& p, const pmp_opts_t& o, long long n, const v
         PMP_TRY(cudaGetLastError());
         PMP_TRY(cudaEventRecord(P.ev_pack[k], sc));
         if (int rc = pmp_solve_batch_cuda(&p, &o, m, d_y, d_ye, nullptr, d_na, d_ns, d_res, B + o_ws, ws_bytes, sc)) return rc;
-        if (x_end || vx_end) {
+        if (x_end || vx_end || pack) {
+            const bool xs = x_end || vx_end;
             if (o.dtype == PMP_F32)
-                unpack_kernel<float><<<blocks, 256, 0, sc>>>(nx, m, (const float*)d_ye, (float*)d_ox, (float*)d_ovx);
+                unpack_kernel<float><<<blocks, 256, 0, sc>>>(nx, m, (const float*)d_ye, xs ? (float*)d_ox : nullptr, (float*)d_ovx,
+                                                              d_na, d_ns, d_res, pack ? d_pk : nullptr);
             else
-                unpack_kernel<double><<<blocks, 256, 0, sc>>>(nx, m, (const double*)d_ye, (double*)d_ox, (double*)d_ovx);
+                unpack_kernel<double><<<blocks, 256, 0, sc>>>(nx, m, (const double*)d_ye, xs ? (double*)d_ox : nullptr,
+                                                               (double*)d_ovx, d_na, d_ns, d_res, pack ? d_pk : nullptr);
             PMP_TRY(cudaGetLastError());
         }
         PMP_TRY(cudaEventRecord(P.ev_comp[k], sc));
@@ -208,12 +262,25 @@ int solve_host(const pmp_problem_t& p, const pmp_opts_t& o, long long n, const v
         if (vx_end) PMP_TRY(cudaMemcpyAsync((char*)vx_end + a * nx * es, d_ovx, m * nx * es, cudaMemcpyDeviceToHost, P.s_out));
         if (t_end) PMP_TRY(cudaMemcpyAsync((char*)t_end + a * es, d_ye + nx * m * es, m * es, cudaMemcpyDeviceToHost, P.s_out));
         if (v_end) PMP_TRY(cudaMemcpyAsync((char*)v_end + a * es, d_ye + (nx + 1) * m * es, m * es, cudaMemcpyDeviceToHost, P.s_out));
-        if (n_accepted) PMP_TRY(cudaMemcpyAsync(n_accepted + a, d_na, m * 4, cudaMemcpyDeviceToHost, P.s_out));
-        if (n_steps) PMP_TRY(cudaMemcpyAsync(n_steps + a, d_ns, m * 4, cudaMemcpyDeviceToHost, P.s_out));
-        if (result) PMP_TRY(cudaMemcpyAsync(result + a, d_res, m * 4, cudaMemcpyDeviceToHost, P.s_out));
+        if (pack) {
+            PMP_TRY(cudaMemcpyAsync(P.h_packed + a, d_pk, m * 4, cudaMemcpyDeviceToHost, P.s_out));
+            PMP_TRY(cudaEventRecord(P.ev_piece[c], P.s_out));
+        } else {
+            if (n_accepted) PMP_TRY(cudaMemcpyAsync(n_accepted + a, d_na, m * 4, cudaMemcpyDeviceToHost, P.s_out));
+            if (n_steps) PMP_TRY(cudaMemcpyAsync(n_steps + a, d_ns, m * 4, cudaMemcpyDeviceToHost, P.s_out));
+            if (result) PMP_TRY(cudaMemcpyAsync(result + a, d_res, m * 4, cudaMemcpyDeviceToHost, P.s_out));
+        }
         PMP_TRY(cudaEventRecord(P.ev_out[k], P.s_out));
         stamp(P.s_out);
     }
+    // the waiting host thread unfolds the counters of each piece as soon as its copies have landed
+    if (pack)
+        for (int c = 0; c < n_pieces; c++) {
+            PMP_TRY(cudaEventSynchronize(P.ev_piece[c]));
+            const long long a = bounds[c], m = bounds[c + 1] - a;
+            unpack_counters(P.h_packed + a, m, n_accepted ? n_accepted + a : nullptr, n_steps ? n_steps + a : nullptr,
+                            result ? result + a : nullptr);
+        }
     // every stream's work precedes the last record on s_out, except the tail of s_in/s_comp when all outputs are NULL
     PMP_TRY(cudaStreamSynchronize(P.s_out));
     for (auto& s : P.s_comp) PMP_TRY(cudaStreamSynchronize(s));
@@ -239,6 +306,10 @@ int host_release() {
         PMP_TRY(cudaSetDevice(d));
         for (auto& b : P.buf) { if (b) cudaFree(b); b = nullptr; }
         P.cap = 0;
+        if (P.h_packed) cudaFreeHost(P.h_packed);
+        P.h_packed = nullptr; P.h_cap = 0;
+        for (auto e : P.ev_piece) cudaEventDestroy(e);
+        P.ev_piece.clear();
         cudaStreamDestroy(P.s_in); cudaStreamDestroy(P.s_out);
         for (auto& s : P.s_comp) cudaStreamDestroy(s);
         for (int k = 0; k < kSets; k++) {

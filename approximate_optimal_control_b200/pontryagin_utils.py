@@ -382,7 +382,7 @@ def define_backward_solver(problem_params: dict, algo_params: dict):
         # library choose the number of pieces, k forces k
         if (not with_vxx and not save_steps and _host_leaf(y_f["x"]) and _host_leaf(y_f["vx"]) and np.ndim(y_f["x"]) == 2):
             n_all = int(np.shape(y_f["x"])[0])
-            chunks = int(algo_params.get("pontryagin_solver_host_chunks", 0 if n_all >= (1 << 17) else -1))
+            chunks = int(algo_params.get("pontryagin_solver_host_chunks", 0 if n_all >= (1 << 18) else -1))
             if chunks >= 0:
                 opts = _solver_opts(algo_params, dtype, t0=0.0, t1=-T, dt0=-abs(dt0), adaptive=int(adaptive), save_dense=0)
                 return _solve_host_pipelined(problem, opts, nx, y_f, dtype, dev, chunks)

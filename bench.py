@@ -359,7 +359,7 @@ def main():
         h2d = sum(v.numel() * v.element_size() for v in host_in.values())
         d2h = sum(v.numel() * v.element_size() for v in host_out.values())
         if not dense:
-            d2h += 3 * n * 4  # num_accepted_steps, num_steps, result come back with the endpoints
+            d2h += n * 4  # num_accepted_steps, num_steps, result come back with the endpoints, one packed word each
 
         def e2e_step():
             if dense:  # dense solutions stay on the device (8 GB per step); only the endpoints travel back

@@ -205,7 +205,8 @@ int pmp_solve_batch_cuda(const pmp_problem_t *problem, const pmp_opts_t *opts, i
  * streams of the CURRENT device; the copies overlap only from/to page-locked memory (cudaHostAlloc / cudaHostRegister,
  * torch pin_memory), pageable buffers work but serialise.  Returns when every output is in host memory.  Device
  * staging (~(8nx+7) reals per trajectory of three pieces) is kept between calls; pmp_host_release() frees it.
- * Concurrent calls on one device are serialised.  Endpoints only: save_dense and PMP_FLAG_VXX are refused.
+ * The three counters cross the link as one packed word per trajectory (max_steps < 2^14) and are unfolded by the
+ * calling thread while later pieces are in flight.  Concurrent calls on one device are serialised.  Endpoints only: save_dense and PMP_FLAG_VXX are refused.
  * Results are bit-identical to pmp_solve_batch_cuda on the same states. */
 int pmp_solve_host(const pmp_problem_t *problem, const pmp_opts_t *opts, int64_t n,
                    const void *x_f, const void *t_f, const void *v_f, const void *vx_f,

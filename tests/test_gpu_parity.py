@@ -483,10 +483,12 @@ def test_host_in_host_out_pipeline_equals_device_path():
     assert small.y_end["x"].is_cuda
 
 
-@pytest.mark.parametrize("name,dtype,n,pieces", [("flatquad", _capi.F32, 100003, 0), ("flatquad", _capi.F32, 100003, 7),
-                                                  ("flatquad", _capi.F64, 40001, 3), ("orbits", _capi.F64, 5000, 5),
-                                                  ("lqr", _capi.F32, 129, 2), ("flatquad", _capi.F32, 1 << 19, 0)])
-def test_solve_host_c_abi_bit_identical_to_device_solve(name, dtype, n, pieces):
+@pytest.mark.parametrize("name,dtype,n,pieces,max_steps", [
+    ("flatquad", _capi.F32, 100003, 0, 512), ("flatquad", _capi.F32, 100003, 7, 512), ("flatquad", _capi.F64, 40001, 3, 512),
+    ("orbits", _capi.F64, 5000, 5, 512), ("lqr", _capi.F32, 129, 2, 512), ("flatquad", _capi.F32, 1 << 19, 0, 512),
+    ("flatquad", _capi.F32, 3000, 2, 7),         # every trajectory runs out of steps (result 2)
+    ("lqr", _capi.F32, 1000, 3, 1 << 14)])       # counters do not fit the packed word: three separate copies
+def test_solve_host_c_abi_bit_identical_to_device_solve(name, dtype, n, pieces, max_steps):
     """pmp_solve_host (host pointers in the reference's state-dict layout, pipelined pieces) returns exactly what
     pmp_solve_batch_cuda returns for the same terminal states; ragged last piece, NULL t_f, NULL outputs."""
     import ctypes as C
@@ -497,7 +499,7 @@ def test_solve_host_c_abi_bit_identical_to_device_solve(name, dtype, n, pieces):
     y = np.ascontiguousarray(mk(n), dtype=npdt)
     prob, _ = c_problem(name)
     nx = prob.nx
-    kw = dict(method="tsit5", dtype=dtype, rtol=1e-5, atol=1e-5, max_steps=512)
+    kw = dict(method="tsit5", dtype=dtype, rtol=1e-5, atol=1e-5, max_steps=max_steps)
     if name != "flatquad":
         kw.update(t1=-3.0)
     opts = _capi.make_opts(**kw)
