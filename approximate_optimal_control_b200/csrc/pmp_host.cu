@@ -185,7 +185,7 @@ int solve_host(const pmp_problem_t& p, const pmp_opts_t& o, long long n, const v
 
     const int64_t ws_bytes = pmp_solve_workspace_bytes(&p, &o, cs);
     if (ws_bytes < 0) return (int)ws_bytes;
-    // one staging set: leaves in, y, y_end, leaves out (x, vx), three int arrays, solver workspace
+    // one staging set: leaves in, y, y_end, leaves out (x, vx), three int arrays + their packed form, solver workspace
     const size_t o_in = 0, o_y = o_in + up256(NS * cs * es), o_ye = o_y + up256(NS * cs * es), o_ox = o_ye + up256(NS * cs * es),
                  o_int = o_ox + up256(2 * nx * cs * es), o_ws = o_int + up256(4 * cs * 4), total = o_ws + up256((size_t)ws_bytes);
 
