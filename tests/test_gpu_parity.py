@@ -508,10 +508,13 @@ def test_solve_host_c_abi_bit_identical_to_device_solve(name, dtype, n, pieces, 
     pin = lambda a: torch.as_tensor(np.ascontiguousarray(a)).pin_memory()
     x, vx, t, v = pin(y[:nx].T), pin(y[nx + 2:].T), pin(y[nx]), pin(y[nx + 1])
     assert (y[nx] == opts.t0).all()
-    o = {k: torch.empty(s, dtype=d).pin_memory() for k, s, d in (("x", (n, nx), x.dtype), ("vx", (n, nx), x.dtype), ("t", (n,), x.dtype),
-         ("v", (n,), x.dtype), ("na", (n,), torch.int32), ("ns", (n,), torch.int32), ("res", (n,), torch.int32))}
+    G = 16  # guard rows before and after every output: the piece-wise copies must stay inside [0, n)
+    full = {k: torch.empty((n + 2 * G,) + s, dtype=d).pin_memory() for k, s, d in (
+        ("x", (nx,), x.dtype), ("vx", (nx,), x.dtype), ("t", (), x.dtype), ("v", (), x.dtype), ("na", (), torch.int32),
+        ("ns", (), torch.int32), ("res", (), torch.int32))}
+    o = {k: a[G:G + n] for k, a in full.items()}
     for with_t in (True, False):  # t_f = NULL starts every trajectory at opts.t0
-        for q in o.values():
+        for q in full.values():
             q.fill_(-7)
         _capi.check(L.pmp_solve_host(C.byref(prob), C.byref(opts), n, x.data_ptr(), t.data_ptr() if with_t else None, v.data_ptr(),
                                      vx.data_ptr(), o["x"].data_ptr(), o["t"].data_ptr(), o["v"].data_ptr(), o["vx"].data_ptr(),
@@ -521,6 +524,8 @@ def test_solve_host_c_abi_bit_identical_to_device_solve(name, dtype, n, pieces, 
         assert np.array_equal(o["t"].numpy(), ye[nx], equal_nan=True) and np.array_equal(o["v"].numpy(), ye[nx + 1], equal_nan=True)
         assert np.array_equal(o["na"].numpy(), ref["n_accepted"]) and np.array_equal(o["ns"].numpy(), ref["n_steps"])
         assert np.array_equal(o["res"].numpy(), ref["result"])
+        for k, a in full.items():
+            assert bool((a[:G] == -7).all()) and bool((a[G + n:] == -7).all()), k
     # pageable numpy inputs, only the value leaf requested
     v_only = np.full(n, -7, npdt)
     xa, vxa, va = (np.ascontiguousarray(a) for a in (y[:nx].T, y[nx + 2:].T, y[nx + 1]))
