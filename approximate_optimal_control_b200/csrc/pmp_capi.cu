@@ -380,7 +380,7 @@ int pmp_ustar_batch_cuda_flags(const pmp_problem_t* p, int32_t dtype, int32_t fl
 
 int pmp_fma_peak_cuda(int32_t dtype, int32_t variant, int32_t iters, void* scratch, double* flops_out, void* cuda_stream) {
     if (dtype != PMP_F32 && dtype != PMP_F64) return fail(PMP_ERR_BAD_ARG, "dtype must be 0 (f32) or 1 (f64)");
-    if (variant < 0 || variant > 1 || iters < 1 || !scratch) return fail(PMP_ERR_BAD_ARG, "bad variant / iters / scratch");
+    if (variant < 0 || variant > 2 || iters < 1 || !scratch) return fail(PMP_ERR_BAD_ARG, "bad variant / iters / scratch");
     if (pmp_device_count() <= 0) return fail(PMP_ERR_NO_DEVICE, "no CUDA device");
     int rc = pmp::fma_peak(dtype, variant, iters, scratch, flops_out, (cudaStream_t)cuda_stream);
     return rc ? cuda_fail(rc) : PMP_OK;

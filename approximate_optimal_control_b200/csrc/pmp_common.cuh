@@ -57,6 +57,16 @@ template <> struct Math<float> {
     static __device__ __forceinline__ float pow_neg_inv(float x, float inv_order) {
         return exp2f(-inv_order * __log2f(x));
     }
+    // Packed pairs: Blackwell's FFMA2 / FMUL2 (fma.rn.f32x2) do two IEEE FMAs per lane and ISSUE SLOT, each
+    // component rounded exactly like fmaf; the scalar coefficient is a broadcast operand (R.F32), so it costs no
+    // extra register.  The integrator is issue-bound, not FMA-pipe-bound: its stage combinations and error
+    // estimate (one coefficient times a vector of 2nx+1 components) run on these.
+    typedef float2 V2;
+    static __device__ __forceinline__ V2 mk2(float a, float b) { return make_float2(a, b); }
+    static __device__ __forceinline__ V2 fma2(float c, V2 a, V2 b) { return __ffma2_rn(make_float2(c, c), a, b); }
+    static __device__ __forceinline__ V2 fma2v(V2 c, V2 a, V2 b) { return __ffma2_rn(c, a, b); }
+    static __device__ __forceinline__ V2 mul2(float c, V2 a) { return __fmul2_rn(make_float2(c, c), a); }
+    static __device__ __forceinline__ V2 mul2v(V2 c, V2 a) { return __fmul2_rn(c, a); }
     static __device__ __forceinline__ float inf() { return __int_as_float(0x7f800000); }
     static __device__ __forceinline__ float nan() { return __int_as_float(0x7fffffff); }
     static __device__ __forceinline__ float clip_tol() { return 1e-6f; }  // diffrax _clip_to_end
@@ -106,6 +116,13 @@ template <> struct Math<double> {
     static __device__ __forceinline__ double pow_neg_inv(double x, double inv_order) {
         return ::pow(x, -inv_order);
     }
+    // pairs are two scalar operations in fp64 (no packed DFMA exists); same interface as Math<float>
+    typedef double2 V2;
+    static __device__ __forceinline__ V2 mk2(double a, double b) { return make_double2(a, b); }
+    static __device__ __forceinline__ V2 fma2(double c, V2 a, V2 b) { return make_double2(::fma(c, a.x, b.x), ::fma(c, a.y, b.y)); }
+    static __device__ __forceinline__ V2 fma2v(V2 c, V2 a, V2 b) { return make_double2(::fma(c.x, a.x, b.x), ::fma(c.y, a.y, b.y)); }
+    static __device__ __forceinline__ V2 mul2(double c, V2 a) { return make_double2(c * a.x, c * a.y); }
+    static __device__ __forceinline__ V2 mul2v(V2 c, V2 a) { return make_double2(c.x * a.x, c.y * a.y); }
     static __device__ __forceinline__ double inf() { return __longlong_as_double(0x7ff0000000000000LL); }
     static __device__ __forceinline__ double nan() { return __longlong_as_double(0x7fffffffffffffffLL); }
     static __device__ __forceinline__ double clip_tol() { return 1e-10; }

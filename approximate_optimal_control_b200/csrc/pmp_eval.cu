@@ -125,6 +125,26 @@ __global__ void __launch_bounds__(kPeakBlock) fma_peak_kernel(int iters, R b, R 
     if (s == R(-12345.678)) *sink = s;  // never true; keeps the chains alive
 }
 
+// VARIANT 2: the same 16 chains as 8 packed pairs (FFMA2, fma.rn.f32x2): same flops, half the issue slots.
+// Answers "does FFMA2 raise the FMA peak or only free issue slots?" -- see DESIGN.md 3.5.
+__global__ void __launch_bounds__(kPeakBlock) fma2_peak_kernel(int iters, float b, float c, float* sink) {
+    float2 a[kPeakChains / 2];
+#pragma unroll
+    for (int j = 0; j < kPeakChains / 2; j++) a[j] = make_float2((threadIdx.x + 2 * j) * 1e-3f, (threadIdx.x + 2 * j + 1) * 1e-3f);
+    const float2 bb = make_float2(b, b), cc = make_float2(c, c);
+    for (int it = 0; it < iters; it++) {
+#pragma unroll
+        for (int rep = 0; rep < 8; rep++) {
+#pragma unroll
+            for (int j = 0; j < kPeakChains / 2; j++) a[j] = __ffma2_rn(a[j], bb, cc);
+        }
+    }
+    float s = 0.f;
+#pragma unroll
+    for (int j = 0; j < kPeakChains / 2; j++) s += a[j].x + a[j].y;
+    if (s == -12345.678f) *sink = s;
+}
+
 int fma_peak(int dtype, int variant, int iters, void* scratch, double* flops_out, cudaStream_t st) {
     int dev = 0, sms = 0;
     cudaError_t e = cudaGetDevice(&dev);
@@ -134,6 +154,7 @@ int fma_peak(int dtype, int variant, int iters, void* scratch, double* flops_out
     if (flops_out) *flops_out = 2.0 * kPeakChains * 8.0 * (double)iters * (double)grid * kPeakBlock;
     if (dtype == PMP_F32) {
         if (variant == 0) fma_peak_kernel<float, 0><<<grid, kPeakBlock, 0, st>>>(iters, 0.999999f, 1e-7f, (float*)scratch);
+        else if (variant == 2) fma2_peak_kernel<<<grid, kPeakBlock, 0, st>>>(iters, 0.999999f, 1e-7f, (float*)scratch);
         else fma_peak_kernel<float, 1><<<grid, kPeakBlock, 0, st>>>(iters, 0.f, 0.f, (float*)scratch);
     } else {
         if (variant == 0) fma_peak_kernel<double, 0><<<grid, kPeakBlock, 0, st>>>(iters, 0.999999, 1e-7, (double*)scratch);

@@ -364,6 +364,79 @@ __device__ __forceinline__ void flush_groups(const DensePtrs<R>& d, const R* sX,
     __syncwarp();  // the rings may be overwritten by the next attempt's nodes only after every chunk has been read
 }
 
+// Which two components of the integrator's vector y = (x[NX], lam[NX], aux) share a packed pair: position p of the
+// pair sequence holds component PairMap<Sys>::idx(p), pairs are positions (0,1), (2,3), ...  Any pairing gives the same
+// numbers; a good one makes the copies inside the field (x' = velocity components of x) land on whole pairs, so that they
+// stay register aliases instead of becoming MOVs.  Flatquad: x' = (x3, x4, x5, ..) => pairs (0,1) (3,4) (2,5), same for lambda.
+template <class Sys> struct PairMap {
+    __host__ __device__ static constexpr int idx(int p) { return p; }
+};
+template <class R> struct PairMap<Flatquad<R>> {
+    __host__ __device__ static constexpr int idx(int p) {
+        constexpr int m[12] = {0, 1, 3, 4, 2, 5, 6, 7, 9, 10, 8, 11};
+        return m[p];
+    }
+};
+
+// Stage state ys = y + sum_{j<i} (h a_ij) k_j of stage i (ha[j] = h a_ij).  The 2nx dynamic components of x and lambda
+// go through packed pairs (Math<R>::fma2: one FFMA2 per pair and coefficient in fp32, half the issue slots of the scalar
+// form, identical rounding); the aux scalar (v, or t in value mode) does not enter the field, so only the last stage of
+// an FSAL method (whose stage state is the candidate y1) forms it.
+template <class Sys, class R, class TB, int ND>
+__device__ __forceinline__ void stage_state(int i, bool with_aux, const R* ha, const R* y, const R (*k)[ND], R* ys) {
+    using M = Math<R>;
+    using PM = PairMap<Sys>;
+    constexpr int AUX = ND - 1;
+    static_assert(AUX % 2 == 0, "x and lambda make an even number of components");
+#pragma unroll
+    for (int p = 0; p < AUX; p += 2) {
+        const int a = PM::idx(p), b = PM::idx(p + 1);
+        typename M::V2 acc = M::mk2(y[a], y[b]);
+#pragma unroll
+        for (int j = 0; j < TB::S; j++)
+            if (j < i && TB::a(i, j) != 0.0) acc = M::fma2(ha[j], M::mk2(k[j][a], k[j][b]), acc);
+        ys[a] = acc.x; ys[b] = acc.y;
+    }
+    R acc = y[AUX];
+    if (with_aux) {
+#pragma unroll
+        for (int j = 0; j < TB::S; j++)
+            if (j < i && TB::a(i, j) != 0.0) acc = M::fma(ha[j], k[j][AUX], acc);
+    }
+    ys[AUX] = acc;
+}
+
+// Squared scaled error of the embedded pair, summed over the components of y (diffrax rms_norm numerator):
+//   e_q = sum_j (h (b_j - bhat_j)) k_j[q],  scale_q = atol + rtol max(|y_q|, |y1_q|),  sum_q (e_q / scale_q)^2
+// x and lambda in packed pairs (two partial sums, even and odd members), the aux scalar on its own.
+template <class Sys, class R, class TB, int ND>
+__device__ __forceinline__ R error_sumsq(const R* he, const R* y, const R* y1, const R (*k)[ND], R rtol, R atol) {
+    using M = Math<R>;
+    using PM = PairMap<Sys>;
+    constexpr int AUX = ND - 1, S = TB::S;
+    typename M::V2 part = M::mk2(R(0), R(0));
+#pragma unroll
+    for (int p = 0; p < AUX; p += 2) {
+        const int a = PM::idx(p), b = PM::idx(p + 1);
+        typename M::V2 e = M::mul2(he[0], M::mk2(k[0][a], k[0][b]));
+#pragma unroll
+        for (int j = 1; j < S; j++)
+            if (TB::berr(j) != 0.0) e = M::fma2(he[j], M::mk2(k[j][a], k[j][b]), e);
+        // scale = atol + rtol*max(|y0|,|y1|); fmax drops a NaN y1 (diffrax substitutes y0)
+        const typename M::V2 mx = M::mk2(M::max(M::abs(y[a]), M::abs(y1[a])), M::max(M::abs(y[b]), M::abs(y1[b])));
+        const typename M::V2 scale = M::fma2(rtol, mx, M::mk2(atol, atol));
+        const typename M::V2 ratio = M::mk2(M::ctl_div(e.x, scale.x), M::ctl_div(e.y, scale.y));
+        part = M::fma2v(ratio, ratio, part);
+    }
+    R e = he[0] * k[0][AUX];
+#pragma unroll
+    for (int j = 1; j < S; j++)
+        if (TB::berr(j) != 0.0) e = M::fma(he[j], k[j][AUX], e);
+    const R scale = M::fma(rtol, M::max(M::abs(y[AUX]), M::abs(y1[AUX])), atol);
+    const R ratio = M::ctl_div(e, scale);
+    return M::fma(ratio, ratio, part.x + part.y);
+}
+
 // ---- the integrator -----------------------------------------------------------------------------
 template <class Sys, class R, int METHOD, bool DENSE, bool VALUE, bool ULIT, int MINB, int VXX = 0>
 __global__ void __launch_bounds__((BlockOf<R, VXX>::value), MINB)
@@ -656,15 +729,7 @@ solve_kernel(const typename Sys::Consts sc, const SolveOpts<R> o, const SolveIO<
                 const bool last_fsal = TB::FSAL && i == S - 1;
 #pragma unroll
                 for (int j = 0; j < i; j++) ha[j] = h * tp.template a<TB>(i, j);
-#pragma unroll
-                for (int q = 0; q < ND; q++) {
-                    if (q == AUX && !last_fsal) { ys[q] = y[q]; continue; }
-                    R acc = y[q];
-#pragma unroll
-                    for (int j = 0; j < i; j++)
-                        if (TB::a(i, j) != 0.0) acc = M::fma(ha[j], k[j][q], acc);
-                    ys[q] = acc;
-                }
+                stage_state<Sys, R, TB, ND>(i, last_fsal, ha, y, k, ys);
                 base_stage(i, ys);
                 if (last_fsal) {
 #pragma unroll
@@ -682,19 +747,10 @@ solve_kernel(const typename Sys::Consts sc, const SolveOpts<R> o, const SolveIO<
                 }
             }
             if (TB::EMBEDDED) {  // the base leaves' error terms now, so that k2..k6 are dead during phase B
-                R sumsq_odd = R(0);
+                R he[S];
 #pragma unroll
-                for (int q = 0; q < ND; q++) {
-                    R e = (h * tp.template e<TB>(0)) * k[0][q];
-#pragma unroll
-                    for (int j = 1; j < S; j++)
-                        if (TB::berr(j) != 0.0) e = M::fma(h * tp.template e<TB>(j), k[j][q], e);
-                    const R scale = M::fma(o.rtol, M::max(M::abs(y[q]), M::abs(y1[q])), o.atol);
-                    const R ratio = M::ctl_div(e, scale);
-                    if (q & 1) sumsq_odd = M::fma(ratio, ratio, sumsq_odd);
-                    else sumsq_base = M::fma(ratio, ratio, sumsq_base);
-                }
-                sumsq_base += sumsq_odd;
+                for (int j = 0; j < S; j++) he[j] = h * tp.template e<TB>(j);
+                sumsq_base = error_sumsq<Sys, R, TB, ND>(he, y, y1, k, o.rtol, o.atol);
             }
             // ---- phase B: the V_xx stages, a RUNTIME loop over one copy of the stage code (see vxx_stage)
             auto coef_of = [&](int i, typename Sys::JacCoef& jc) {
@@ -731,16 +787,7 @@ solve_kernel(const typename Sys::Consts sc, const SolveOpts<R> o, const SolveIO<
             R ha[S];
 #pragma unroll
             for (int j = 0; j < i; j++) ha[j] = h * tp.template a<TB>(i, j);
-#pragma unroll
-            for (int q = 0; q < ND; q++) {
-                // the field does not depend on the aux scalar: skip it for intermediate stages
-                if (q == AUX && !last_fsal) { ys[q] = y[q]; continue; }
-                R acc = y[q];
-#pragma unroll
-                for (int j = 0; j < i; j++)
-                    if (TB::a(i, j) != 0.0) acc = M::fma(ha[j], k[j][q], acc);
-                ys[q] = acc;
-            }
+            stage_state<Sys, R, TB, ND>(i, last_fsal, ha, y, k, ys);
             field<Sys, R, VALUE, ULIT ? 1 : 2>(sc, ys, k[i]);
             if (last_fsal) {
 #pragma unroll
@@ -773,17 +820,7 @@ solve_kernel(const typename Sys::Consts sc, const SolveOpts<R> o, const SolveIO<
             R he[S];
 #pragma unroll
             for (int j = 0; j < S; j++) he[j] = h * tp.template e<TB>(j);
-#pragma unroll
-            for (int q = 0; q < (VXX ? 0 : ND); q++) {
-                R e = he[0] * k[0][q];
-#pragma unroll
-                for (int j = 1; j < S; j++)
-                    if (TB::berr(j) != 0.0) e = M::fma(he[j], k[j][q], e);
-                // scale = atol + rtol*max(|y0|,|y1|); fmax drops a NaN y1 (diffrax substitutes y0)
-                const R scale = M::fma(o.rtol, M::max(M::abs(y[q]), M::abs(y1[q])), o.atol);
-                const R ratio = M::ctl_div(e, scale);
-                sumsq = M::fma(ratio, ratio, sumsq);
-            }
+            if constexpr (VXX == 0) sumsq = error_sumsq<Sys, R, TB, ND>(he, y, y1, k, o.rtol, o.atol);
             if constexpr (VXX) {  // fifth leaf of the norm (embedded methods are FSAL: see vxx_stage)
                 static_assert(!VXX || !TB::EMBEDDED || (TB::FSAL && S >= 4), "column reuse needs an FSAL method");
                 R part[4] = {R(0), R(0), R(0), R(0)};  // four partial sums: a single chain is latency bound

@@ -51,6 +51,7 @@ def _closed_loop_eval(problem_params, algo_params, x0s, P=None, nn=None):
     opts = _capi.make_opts(method=algo_params.get("pontryagin_solver_method", "tsit5"), dtype=pu._code(dtype), adaptive=0,
                            t0=0.0, t1=T, dt0=dt, max_steps=max_steps, save_dense=1, dtmin=0.0, dtmax=0.0)
     out = pu.forward_batch_soa(problem, opts, xs, P, problem_params.get("x_eq"), nn=nn)
+    pu.raise_if_failed(out["result"], {"throw": True}, "closed_loop_eval")  # eval_utils.py:86-89: diffeqsolve's default throw=True
     ys = torch.cat([out["x"], out["cost"][..., None]], dim=-1)[:, 1:]  # SaveAt(steps=True): no t0 slot
     stats = {"num_steps": out["n_steps"], "num_accepted_steps": out["n_accepted"],
              "num_rejected_steps": out["n_steps"] - out["n_accepted"]}

@@ -87,6 +87,7 @@ def _forward_sim(problem_params, algo_params, *, P=None, nn=None, event=None, le
         opts = pu._solver_opts(algo_params, dtype, t0=0.0, t1=T, dt0=0.1, adaptive=1, save_dense=1,
                                dtmin=float(algo_params.get("forward_sim_dtmin", 0.05)), dtmax=0.0, **over)
         out = pu.forward_batch_soa(problem, opts, xs, P, problem_params.get("x_eq"), nn=nn)
+        pu.raise_if_failed(out["result"], algo_params, "forward_sim")  # levelsets.py:834,867,929: throw=algo_params['throw']
         stats = {"num_steps": out["n_steps"], "num_accepted_steps": out["n_accepted"],
                  "num_rejected_steps": out["n_steps"] - out["n_accepted"]}
         sol = Solution(t0=0.0, t1=T, ts=out["ts"], ys=out["x"], y_end={"x": out["z_end"][:nx].t(), "cost": out["z_end"][nx]},

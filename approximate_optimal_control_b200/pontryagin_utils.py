@@ -58,9 +58,20 @@ def _as_tensor(x, dtype, device) -> torch.Tensor:
     return torch.as_tensor(np.asarray(x), dtype=dtype, device=device)
 
 
+_X64 = False
+
+
+def enable_x64(on: bool = True) -> None:
+    """Mirror of jax.config.update("jax_enable_x64", True) (experiment_orbits.py:18-19): without it jax computes in fp32
+    whatever the dtype of the numpy inputs (flatquad_landing_experiment.py:26-27 leaves it commented out)."""
+    global _X64
+    _X64 = bool(on)
+
+
 def _infer_dtype(algo_params, *xs) -> torch.dtype:
-    """algo_params['dtype'] ('float32'/'float64') wins; else float64 inputs select fp64 (the
-    reference's jax_enable_x64, experiment_orbits.py:18-19), anything else fp32 (jax default)."""
+    """algo_params['dtype'] ('float32'/'float64') wins.  Else, like jax: float64 NUMPY / python inputs are computed in
+    fp32 unless enable_x64() was called (jax downcasts them; the reference's flatquad path runs fp32 although
+    numpy defaults to float64), while an explicit float64 torch tensor -- which cannot arise by accident -- selects fp64."""
     d = (algo_params or {}).get("dtype")
     if d is not None:
         return {"float32": torch.float32, "float64": torch.float64, torch.float32: torch.float32,
@@ -68,9 +79,30 @@ def _infer_dtype(algo_params, *xs) -> torch.dtype:
     for x in xs:
         if isinstance(x, torch.Tensor) and x.dtype == torch.float64:
             return torch.float64
-        if isinstance(x, np.ndarray) and x.dtype == np.float64:
+        if _X64 and isinstance(x, np.ndarray) and x.dtype == np.float64:
             return torch.float64
     return torch.float32
+
+
+_RESULT_TEXT = {2: "the maximum number of solver steps was reached (max_steps)",
+                3: "the minimum step size was reached (dt_min)",
+                4: "NaN / infinite state or time encountered"}
+
+
+def raise_if_failed(result: torch.Tensor, algo_params: dict, what: str = "solve_backward") -> None:
+    """diffrax `throw` semantics (pontryagin_utils.py:515-524, levelsets.py:834,867,929 pass throw=algo_params['throw']):
+    with throw=True a solve that ends with max_steps_reached / dt_min_reached / nan raises; with throw=False (the value in
+    flatquad_landing_experiment.py:392) failures are per-trajectory `result` codes and inf/NaN payloads.  A terminating
+    event (result 1) is a success either way.  The check reads the result codes back (one sync), so it only runs for throw=True."""
+    if not (algo_params or {}).get("throw", False):
+        return
+    r = result.reshape(-1)
+    bad = torch.nonzero(r >= 2)
+    if bad.numel():
+        i = int(bad[0])
+        code = int(r[i])
+        raise _capi.PmpError(f"{what} (throw=True): trajectory {i} of {r.numel()} failed with result {code}: "
+                             f"{_RESULT_TEXT.get(code, 'unknown')}; {int(bad.numel())} trajectories failed in all")
 
 
 def _code(dtype: torch.dtype) -> int:
@@ -343,7 +375,8 @@ def define_backward_solver(problem_params: dict, algo_params: dict):
     batch axis N on every leaf (replaces jax.vmap, levelsets.py:601,1254).  Integrates the extended
     characteristic system from t0=0 to t1=-T with Tsit5 + PIDController(rtol, atol, dtmin=5e-4,
     dtmax=.5), dt0=-0.1, at most `pontryagin_solver_maxsteps` step attempts, throw=False semantics
-    (per-trajectory `result` codes, inf padding).  Optional algo_params keys:
+    (per-trajectory `result` codes, inf padding); algo_params['throw'] = True raises PmpError naming the first trajectory
+    that ended with max_steps / dt_min / NaN instead (raise_if_failed).  Optional algo_params keys:
     'pontryagin_solver_method' ('tsit5' | 'dopri5' | 'rk4'), 'pontryagin_solver_adaptive' (default
     True; RK4 is fixed-step), 'pontryagin_solver_dt0', '..._dtmin', '..._dtmax',
     'pontryagin_solver_save_steps' (default True = SaveAt(steps=True)), 'dtype'.
@@ -385,7 +418,9 @@ def define_backward_solver(problem_params: dict, algo_params: dict):
             chunks = int(algo_params.get("pontryagin_solver_host_chunks", 0 if n_all >= (1 << 18) else -1))
             if chunks >= 0:
                 opts = _solver_opts(algo_params, dtype, t0=0.0, t1=-T, dt0=-abs(dt0), adaptive=int(adaptive), save_dense=0)
-                return _solve_host_pipelined(problem, opts, nx, y_f, dtype, dev, chunks)
+                sol = _solve_host_pipelined(problem, opts, nx, y_f, dtype, dev, chunks)
+                raise_if_failed(sol.result, algo_params)
+                return sol
         y, batched = pack_state(y_f, nx, dtype, dev, with_vxx)
         over = {}
         if with_vxx:
@@ -401,6 +436,7 @@ def define_backward_solver(problem_params: dict, algo_params: dict):
         opts = _solver_opts(algo_params, dtype, t0=0.0, t1=-T, dt0=-abs(dt0), adaptive=int(adaptive),
                             save_dense=int(save_steps), **over)
         out = solve_batch_soa(problem, opts, y)
+        raise_if_failed(out["result"], algo_params)
         return _wrap_solution(out, nx, batched, 0.0, -T, opts, problem)
 
     return solve_backward, f_extended
@@ -503,6 +539,7 @@ def make_pontryagin_solver_reparam(problem_params: dict, algo_params: dict):
                             dtmin=float(algo_params.get("pontryagin_solver_dtmin", 0.0)),
                             dtmax=float(algo_params.get("pontryagin_solver_dtmax", 0.0)))
         out = solve_batch_soa(problem, opts, y)
+        raise_if_failed(out["result"], algo_params, "pontryagin_solver_reparam")
         sol = _wrap_solution(out, nx, True, None, float(v1), opts, problem)
         if sol.ys is not None:  # flat (.., 2nx+1) layout of the missing solver
             sol.extra["ys_dict"] = sol.ys

@@ -297,7 +297,8 @@ int pmp_ustar_batch_cuda_flags(const pmp_problem_t *problem, int32_t dtype, int3
  * one kernel that executes *flops_out floating point operations (written on the host, may be
  * NULL); the caller times it with events on cuda_stream.  dtype selects FFMA / DFMA.
  * variant 0: a = fma(a, b, c) with register operands; variant 1: multiplier/addend as
- * compile-time immediates (the form the integrator's tableau FMAs take). */
+ * compile-time immediates (the form the integrator's tableau FMAs take); variant 2 (fp32 only; fp64 runs
+ * variant 1): the same chains as packed pairs (FFMA2 / fma.rn.f32x2), half the issue slots per flop. */
 int pmp_fma_peak_cuda(int32_t dtype, int32_t variant, int32_t iters, void *scratch /* >= 8 B device */,
                       double *flops_out, void *cuda_stream);
 

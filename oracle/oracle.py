@@ -196,6 +196,32 @@ def interp_batch(problem: Problem, opts: Opts, y0: np.ndarray, t1: np.ndarray, t
     return out
 
 
+def solve_batch_to_times(problem: Problem, y_f: np.ndarray, tq: np.ndarray, rtol=1e-12, atol=1e-12, t1=-3.0,
+                         max_steps=4096, chunk=256) -> np.ndarray:
+    """Converged fp64 state of trajectory i at ITS OWN time tq[i] (between t0 = 0 and t1): a tight Tsit5 solve with
+    SaveAt(steps) output, then the interpolant on the step that contains tq[i] (its error, O(h^5) with h ~ 5e-3, is far
+    below any tolerance the tests use).  y_f [NS, n], tq [n] -> [NS, n].  Test infrastructure (dense-node parity)."""
+    y_f = np.ascontiguousarray(y_f, dtype=np.float64)
+    tq = np.asarray(tq, dtype=np.float64)
+    ns, n = y_f.shape
+    nx = problem.nx
+    opts = make_opts(dtype=F64, rtol=rtol, atol=atol, dtmin=0.0, max_steps=max_steps, t1=t1, save_dense=1)
+    sgn = 1.0 if t1 > 0 else -1.0
+    out = np.empty((ns, n))
+    for a in range(0, n, chunk):
+        b = min(n, a + chunk)
+        d = solve_batch(problem, opts, y_f[:, a:b])
+        assert (d["result"] == 0).all(), "truth solve ran out of steps"
+        m = b - a
+        i = np.arange(m)
+        key = sgn * d["ts"]                       # increasing along the slots, +inf padding
+        s = np.array([np.searchsorted(key[j], sgn * tq[a + j], side="right") - 1 for j in range(m)])
+        s = np.clip(s, 0, d["n_accepted"] - 1)
+        node = np.concatenate([d["x"][i, s].T, d["t"][i, s][None], d["v"][i, s][None], d["vx"][i, s].T], 0)
+        out[:, a:b] = interp_batch(problem, opts, node, d["ts"][i, s + 1], tq[a:b], 0)
+    return out
+
+
 def vxx_rhs(problem: Problem, x, lam, vxx):
     """flatquad: (fx, flam, gx, glam, vxx_dot) of pontryagin_utils.py:460-467 for one state (fp64)."""
     x = np.ascontiguousarray(x, np.float64); lam = np.ascontiguousarray(lam, np.float64)

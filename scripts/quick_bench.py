@@ -19,7 +19,7 @@ def time_fn(fn, reps=5, warm=2):
 L = _capi.lib()
 scratch = torch.zeros(16, dtype=torch.float64, device="cuda")
 for dtype, name in ((_capi.F32, "f32"), (_capi.F64, "f64")):
-    for variant in (0, 1):
+    for variant in (0, 1, 2):
         fl = C.c_double()
         def run():
             _capi.check(L.pmp_fma_peak_cuda(dtype, variant, 4096, scratch.data_ptr(), C.byref(fl), None))

@@ -182,3 +182,32 @@ def test_nn_ensemble_packing_and_normaliser():
         NC.NnEnsemble.from_flax(NC.init_flax_params(0, nx, (48,), 2), norm, "cpu")  # width not in {32, 64}
     with pytest.raises(NotImplementedError):
         NC.NnEnsemble.from_flax(NC.init_flax_params(0, nx, (32, 64), 2), norm, "cpu")  # ragged hidden widths
+
+
+def test_throw_semantics_host_logic():
+    """algo_params['throw'] (pontryagin_utils.py:517,524): True raises on result codes 2/3/4 naming the first failing
+    trajectory; event terminations (1) and throw=False never raise."""
+    import torch
+    from approximate_optimal_control_b200 import _capi, pontryagin_utils as pu
+    r = torch.tensor([0, 1, 0, 2, 4], dtype=torch.int32)
+    pu.raise_if_failed(r, {"throw": False})
+    pu.raise_if_failed(r, {})
+    pu.raise_if_failed(torch.tensor([0, 1, 1], dtype=torch.int32), {"throw": True})
+    with pytest.raises(_capi.PmpError, match=r"trajectory 3 of 5 .* result 2.*max_steps.*2 trajectories"):
+        pu.raise_if_failed(r, {"throw": True})
+
+
+def test_dtype_inference_follows_jax_x64_switch():
+    """jax computes float64 numpy inputs in fp32 unless jax_enable_x64 is set (flatquad_landing_experiment.py:26-27 vs
+    experiment_orbits.py:18-19): same rule here; algo_params['dtype'] and float64 torch tensors are explicit requests."""
+    import torch
+    from approximate_optimal_control_b200 import pontryagin_utils as pu
+    x64, x32 = np.zeros(3), np.zeros(3, np.float32)
+    assert pu._infer_dtype({}, x64) == torch.float32 and pu._infer_dtype({}, x32) == torch.float32
+    assert pu._infer_dtype({"dtype": "float64"}, x32) == torch.float64
+    assert pu._infer_dtype({}, torch.zeros(3, dtype=torch.float64)) == torch.float64
+    pu.enable_x64()
+    try:
+        assert pu._infer_dtype({}, x64) == torch.float64 and pu._infer_dtype({}, x32) == torch.float32
+    finally:
+        pu.enable_x64(False)
