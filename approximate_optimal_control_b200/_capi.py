@@ -72,7 +72,7 @@ def lib() -> C.CDLL:
     global _lib
     if _lib is not None:
         return _lib
-    path = _build.LIB_PATH
+    path = os.environ.get("B200PMP_LIB") or _build.LIB_PATH  # B200PMP_LIB: a tuning variant built by scripts/build_variant.py
     if not os.path.exists(path) or os.environ.get("B200PMP_REBUILD"):
         path = _build.build(force=bool(os.environ.get("B200PMP_REBUILD")))
     _lib = load(path)

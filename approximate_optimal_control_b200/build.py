@@ -31,6 +31,10 @@ NVCC_FLAGS = [
 ]
 
 
+# developer knob: extra nvcc flags (e.g. -DPMP_MINB32=4) for tuning experiments
+NVCC_FLAGS += os.environ.get("B200PMP_NVCC_EXTRA", "").split()
+
+
 def _nvcc() -> str:
     exe = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
     if not os.path.exists(exe):

@@ -51,7 +51,13 @@ template <> struct Math<float> {
     static __device__ __forceinline__ float div(float a, float b) { return __fdiv_rn(a, b); }
     // error / scale in the step-size controller: MUFU.RCP + FMUL (2 ulp).  Only the accept decision
     // at |scaled error - 1| < 1e-7 can differ from an IEEE division; the state never sees it.
-    static __device__ __forceinline__ float ctl_div(float a, float b) { return __fdividef(a, b); }
+    // (MUFU.RCP + FMUL: __fdividef adds range checks and rescaling around them, 5 instructions instead of 2; the divisor is
+    //  the error scale atol + rtol |y| >= atol, never denormal or near overflow)
+    static __device__ __forceinline__ float ctl_div(float a, float b) {
+        float r;
+        asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(b));
+        return a * r;
+    }
     // x^(-1/order) for x > 0 through log2/exp2 (MUFU.LG2 / MUFU.EX2): relative error ~1e-6, used
     // only for the step-size factor.
     static __device__ __forceinline__ float pow_neg_inv(float x, float inv_order) {
@@ -67,6 +73,7 @@ template <> struct Math<float> {
     static __device__ __forceinline__ V2 fma2v(V2 c, V2 a, V2 b) { return __ffma2_rn(c, a, b); }
     static __device__ __forceinline__ V2 mul2(float c, V2 a) { return __fmul2_rn(make_float2(c, c), a); }
     static __device__ __forceinline__ V2 mul2v(V2 c, V2 a) { return __fmul2_rn(c, a); }
+    static __device__ __forceinline__ V2 add2(float c, V2 a) { return __fadd2_rn(make_float2(c, c), a); }
     static __device__ __forceinline__ float inf() { return __int_as_float(0x7f800000); }
     static __device__ __forceinline__ float nan() { return __int_as_float(0x7fffffff); }
     static __device__ __forceinline__ float clip_tol() { return 1e-6f; }  // diffrax _clip_to_end
@@ -123,6 +130,7 @@ template <> struct Math<double> {
     static __device__ __forceinline__ V2 fma2v(V2 c, V2 a, V2 b) { return make_double2(::fma(c.x, a.x, b.x), ::fma(c.y, a.y, b.y)); }
     static __device__ __forceinline__ V2 mul2(double c, V2 a) { return make_double2(c * a.x, c * a.y); }
     static __device__ __forceinline__ V2 mul2v(V2 c, V2 a) { return make_double2(c.x * a.x, c.y * a.y); }
+    static __device__ __forceinline__ V2 add2(double c, V2 a) { return make_double2(c + a.x, c + a.y); }
     static __device__ __forceinline__ double inf() { return __longlong_as_double(0x7ff0000000000000LL); }
     static __device__ __forceinline__ double nan() { return __longlong_as_double(0x7fffffffffffffffLL); }
     static __device__ __forceinline__ double clip_tol() { return 1e-10; }

@@ -14,6 +14,7 @@
 
 #include <algorithm>
 #include <mutex>
+#include <type_traits>
 
 #include <cstdio>
 #include <cstdlib>
@@ -38,7 +39,7 @@ struct HostPipe {
     std::vector<cudaEvent_t> ev_piece;  // device->host copies of piece c have landed
 };
 HostPipe g_pipe[kMaxDev];
-std::mutex g_mu;
+std::mutex g_mu[kMaxDev];  // one per device: calls on different GPUs of one process run concurrently
 
 inline size_t up256(size_t b) { return (b + 255) & ~(size_t)255; }
 
@@ -48,9 +49,20 @@ __global__ void pack_kernel(int nx, long long m, const R* __restrict__ x, const 
                             const R* __restrict__ v, R t_fill, R* __restrict__ y) {
     const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
     if (i >= m) return;
-    for (int q = 0; q < nx; q++) {
-        y[q * m + i] = x[i * nx + q];
-        y[(nx + 2 + q) * m + i] = vx[i * nx + q];
+    if ((nx & 1) == 0) {  // rows of an even number of reals: two per load (a warp covers whole 128-byte lines in nx/2 loads)
+        typedef typename std::conditional<sizeof(R) == 4, float2, double2>::type V2;
+        const V2* x2 = reinterpret_cast<const V2*>(x + i * nx);
+        const V2* v2 = reinterpret_cast<const V2*>(vx + i * nx);
+        for (int q = 0; q < nx; q += 2) {
+            const V2 a = x2[q >> 1], b = v2[q >> 1];
+            y[q * m + i] = a.x; y[(q + 1) * m + i] = a.y;
+            y[(nx + 2 + q) * m + i] = b.x; y[(nx + 3 + q) * m + i] = b.y;
+        }
+    } else {
+        for (int q = 0; q < nx; q++) {
+            y[q * m + i] = x[i * nx + q];
+            y[(nx + 2 + q) * m + i] = vx[i * nx + q];
+        }
     }
     y[nx * m + i] = t ? t[i] : t_fill;
     y[(nx + 1) * m + i] = v[i];
@@ -65,11 +77,24 @@ __global__ void unpack_kernel(int nx, long long m, const R* __restrict__ y, R* _
                               uint32_t* __restrict__ packed) {
     const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
     if (i >= m) return;
-    if (x)
-        for (int q = 0; q < nx; q++) {
-            x[i * nx + q] = y[q * m + i];
-            vx[i * nx + q] = y[(nx + 2 + q) * m + i];
+    if (x) {
+        if ((nx & 1) == 0) {
+            typedef typename std::conditional<sizeof(R) == 4, float2, double2>::type V2;
+            V2* x2 = reinterpret_cast<V2*>(x + i * nx);
+            V2* v2 = reinterpret_cast<V2*>(vx + i * nx);
+            for (int q = 0; q < nx; q += 2) {
+                V2 a, b;
+                a.x = y[q * m + i]; a.y = y[(q + 1) * m + i];
+                b.x = y[(nx + 2 + q) * m + i]; b.y = y[(nx + 3 + q) * m + i];
+                x2[q >> 1] = a; v2[q >> 1] = b;
+            }
+        } else {
+            for (int q = 0; q < nx; q++) {
+                x[i * nx + q] = y[q * m + i];
+                vx[i * nx + q] = y[(nx + 2 + q) * m + i];
+            }
         }
+    }
     if (packed) packed[i] = (uint32_t)na[i] | ((uint32_t)ns[i] << kPackBits) | ((uint32_t)res[i] << (2 * kPackBits));
 }
 
@@ -189,7 +214,7 @@ int solve_host(const pmp_problem_t& p, const pmp_opts_t& o, long long n, const v
     const size_t o_in = 0, o_y = o_in + up256(NS * cs * es), o_ye = o_y + up256(NS * cs * es), o_ox = o_ye + up256(NS * cs * es),
                  o_int = o_ox + up256(2 * nx * cs * es), o_ws = o_int + up256(4 * cs * 4), total = o_ws + up256((size_t)ws_bytes);
 
-    std::lock_guard<std::mutex> lock(g_mu);
+    std::lock_guard<std::mutex> lock(g_mu[dev]);
     HostPipe& P = g_pipe[dev];
     if (int e = ensure(P, total)) return e;
     // counters travel packed when at least two of them are wanted and they fit the fields
@@ -198,7 +223,7 @@ int solve_host(const pmp_problem_t& p, const pmp_opts_t& o, long long n, const v
         if (int e = ensure_packed(P, (size_t)n, n_pieces)) return e;
 
     // B200PMP_HOST_TRACE=1: timestamps of every piece's stages on stderr (diagnostics; adds timed events)
-    const bool trace = getenv("B200PMP_HOST_TRACE") != nullptr;
+    static const bool trace = getenv("B200PMP_HOST_TRACE") != nullptr;  // read once per process
     std::vector<cudaEvent_t> tev;
     auto stamp = [&](cudaStream_t s) {
         if (!trace) return;
@@ -209,6 +234,24 @@ int solve_host(const pmp_problem_t& p, const pmp_opts_t& o, long long n, const v
     };
     stamp(P.s_in);
     const char *hx = (const char*)x_f, *hvx = (const char*)vx_f, *ht = (const char*)t_f, *hv = (const char*)v_f;
+    // Any failure after the first enqueue must not return while copies of earlier pieces are still in flight: the caller
+    // frees or reuses its host buffers as soon as the call returns.  `drain` waits for all three kinds of streams (errors
+    // ignored: the first error is what the caller sees) and drops the trace events.
+    auto drain = [&](int rc) {
+        cudaStreamSynchronize(P.s_in);
+        for (auto& s : P.s_comp) cudaStreamSynchronize(s);
+        cudaStreamSynchronize(P.s_out);
+        for (auto e : tev) cudaEventDestroy(e);
+        tev.clear();
+        cudaGetLastError();
+        return rc;
+    };
+#undef PMP_TRY
+#define PMP_TRY(call)                                  \
+    do {                                               \
+        cudaError_t e_ = (call);                       \
+        if (e_ != cudaSuccess) return drain((int)e_);  \
+    } while (0)
     for (int c = 0; c < n_pieces; c++) {
         const long long a = bounds[c], m = bounds[c + 1] - a;
         const int k = c % kSets;
@@ -241,7 +284,7 @@ int solve_host(const pmp_problem_t& p, const pmp_opts_t& o, long long n, const v
                                                          ht ? (const double*)d_t : nullptr, (const double*)d_v, o.t0, (double*)d_y);
         PMP_TRY(cudaGetLastError());
         PMP_TRY(cudaEventRecord(P.ev_pack[k], sc));
-        if (int rc = pmp_solve_batch_cuda(&p, &o, m, d_y, d_ye, nullptr, d_na, d_ns, d_res, B + o_ws, ws_bytes, sc)) return rc;
+        if (int rc = pmp_solve_batch_cuda(&p, &o, m, d_y, d_ye, nullptr, d_na, d_ns, d_res, B + o_ws, ws_bytes, sc)) return drain(rc);
         if (x_end || vx_end || pack) {
             const bool xs = x_end || vx_end;
             if (o.dtype == PMP_F32)
@@ -295,12 +338,18 @@ int solve_host(const pmp_problem_t& p, const pmp_opts_t& o, long long n, const v
     }
     return 0;
 }
+#undef PMP_TRY
+#define PMP_TRY(call)                               \
+    do {                                            \
+        cudaError_t e_ = (call);                    \
+        if (e_ != cudaSuccess) return (int)e_;      \
+    } while (0)
 
 int host_release() {
-    std::lock_guard<std::mutex> lock(g_mu);
     int cur = 0;
     if (cudaGetDevice(&cur) != cudaSuccess) { cudaGetLastError(); return 0; }
     for (int d = 0; d < kMaxDev; d++) {
+        std::lock_guard<std::mutex> lock(g_mu[d]);
         HostPipe& P = g_pipe[d];
         if (!P.ready) continue;
         PMP_TRY(cudaSetDevice(d));

@@ -35,7 +35,10 @@
 
 namespace pmp {
 
-constexpr int kBlock = 128;  // threads per CTA
+#ifndef PMP_KBLOCK
+#define PMP_KBLOCK 128
+#endif
+constexpr int kBlock = PMP_KBLOCK;  // threads per CTA
 constexpr int kChunk = 64;   // trajectory indices claimed per atomicAdd
 // lanes that must wait before a warp takes the retire + refill detour (measured on 2^20 flatquad trajectories:
 // fp32 1.41 ms at 1, 1.33 at 4, 1.38 at 8; fp64 4.09 / 4.03 at 3 / 4.27 at 8; vxx 5.49 / 4.90 at 6 / 5.11 at 12)
@@ -439,7 +442,11 @@ __device__ __forceinline__ R error_sumsq(const R* he, const R* y, const R* y1, c
 
 // ---- the integrator -----------------------------------------------------------------------------
 template <class Sys, class R, int METHOD, bool DENSE, bool VALUE, bool ULIT, int MINB, int VXX = 0>
+#ifdef PMP_MAXNREG  /* tuning builds: an explicit register cap instead of the residency hint */
+__global__ void __maxnreg__(PMP_MAXNREG)
+#else
 __global__ void __launch_bounds__((BlockOf<R, VXX>::value), MINB)
+#endif
 solve_kernel(const typename Sys::Consts sc, const SolveOpts<R> o, const SolveIO<R> io, const TabParams<R> tp,
              const VTab<R, VXX> vt) {
     using M = Math<R>;

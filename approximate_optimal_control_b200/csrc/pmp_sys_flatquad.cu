@@ -3,6 +3,9 @@
 namespace pmp {
 int solve_flatquad(const pmp_problem_t& p, const pmp_opts_t& o, long long n, const void* y_f, void* y_end,
                    const pmp_dense_t* dense, int32_t* a, int32_t* s, int32_t* r, void* ws, cudaStream_t st) {
-    return launch_solve<Flatquad, 3, 1>(p, o, n, y_f, y_end, dense, a, s, r, ws, st);
+    #ifndef PMP_MINB32
+#define PMP_MINB32 3
+#endif
+    return launch_solve<Flatquad, PMP_MINB32, 1>(p, o, n, y_f, y_end, dense, a, s, r, ws, st);
 }
 }  // namespace pmp

@@ -64,8 +64,16 @@ template <class R> struct Flatquad {
         // KKT form: edge minimiser coordinate = clip(kN*H_u[axis] + kQ[k], lo, hi); its multiplier
         // = +-(h01*coordinate + H_u[other axis] + kM[k])
         R kN, kQ[4], kM[4];
+        R kNo;  // -h01/h00: slope of an edge minimiser in the fixed coordinate
         // vxx branch (rhs_jac): d(u0+u1)/dH_u and d(u1-u0)/d(lam5) of the unconstrained minimiser, kN r/I
         R jMS, jD3, kN_rI;
+        // the same constants as PAIRS for the packed (FFMA2) form of the KKT selection: the two edges that move along
+        // u0 (bottom, top) and the two that move along u1 (left, right) are evaluated together; pairs sit on 8-byte
+        // boundaries so that they reach the FFMA2 as one 64-bit uniform-register operand
+        alignas(2 * sizeof(R)) R pN[2];           // (kN, kN)
+        alignas(2 * sizeof(R)) R pQ0[2], pQ1[2];  // (kQ[0], kQ[2]), (kQ[1], kQ[3])
+        alignas(2 * sizeof(R)) R pM0[2], pM1[2];  // (kM[0], kM[2]), (kM[1], kM[3])
+        alignas(2 * sizeof(R)) R pUa[2], pUb[2];  // (-hi00, -hi01), (-hi01, -hi00): (u0, u1) = Hu0 pUa + Hu1 pUb
     };
 
     static __host__ Consts make(const pmp_problem_t& p) {
@@ -100,9 +108,14 @@ template <class R> struct Flatquad {
             c.kM[k] = R(d * fixed);
         }
         c.kN = R(-1.0 / d);
+        c.kNo = R(-o / d);
         c.jMS = R(-2.0 * (d - o) / det);
         c.jD3 = R(-2.0 * (r / I) * (d + o) / det);
         c.kN_rI = R(-(r / I) / d);
+        c.pN[0] = c.pN[1] = c.kN;
+        c.pQ0[0] = c.kQ[0]; c.pQ0[1] = c.kQ[2]; c.pQ1[0] = c.kQ[1]; c.pQ1[1] = c.kQ[3];
+        c.pM0[0] = c.kM[0]; c.pM0[1] = c.kM[2]; c.pM1[0] = c.kM[1]; c.pM1[1] = c.kM[3];
+        c.pUa[0] = -c.hi00; c.pUa[1] = -c.hi01; c.pUb[0] = -c.hi01; c.pUb[1] = -c.hi00;
         return c;
     }
 
@@ -127,38 +140,41 @@ template <class R> struct Flatquad {
         const R base = M::fma(M::fma(lam[4], co, -(lam[3] * s)), c.inv_m, -(c.two_g_m * co));
         const R rot = lam[5] * c.r_I;
         const R Hu0 = base - rot, Hu1 = base + rot;
+        if (MODE & 2) {
+            // ---- KKT form (integrator default).  Cost model measured on B200: compares, selects and
+            // min/max run on the half-rate ALU pipe and cost two issue cycles each, FMA-pipe instructions one, so this
+            // path minimises ALU instructions.
+            using V2 = typename M::V2;
+            // unconstrained minimiser solve(H_uu, -H_u) (:41): (u0, u1) = Hu0 (-hi00, -hi01) + Hu1 (-hi01, -hi00)
+            const V2 uu = M::fma2(Hu0, M::mk2(c.pUa[0], c.pUa[1]), M::mul2(Hu1, M::mk2(c.pUb[0], c.pUb[1])));
+            // If uu leaves the box, the constrained minimiser lies on an edge whose bound uu violates: at the minimiser
+            // u* the direction towards uu is a descent direction, so it must leave the box through an active bound,
+            // i.e. uu is beyond that bound.  b = clip(uu) is that bound on every violated axis (and uu itself on the
+            // others), so there are at most two candidates instead of the reference's four (pontryagin_utils.py:78-86;
+            // the other two can never win):
+            //   A: u1 = b1 fixed, u0 = minimiser along that edge = clip(-(Hu0 + h01 b1)/h00)   (only if axis 1 is violated)
+            //   B: u0 = b0 fixed, u1 = clip(-(Hu1 + h01 b0)/h00)                               (only if axis 0 is violated)
+            // With both axes violated the one whose KKT multiplier has the right sign wins: dH/du1 at A must push
+            // outwards, i.e. have the sign of (uu1 - b1) negated.  Inside the box b == uu and neither test fires.
+            const R b0 = M::min(M::max(uu.x, c.lo0), c.hi0), b1 = M::min(M::max(uu.y, c.lo1), c.hi1);
+            const bool viol0 = b0 != uu.x, viol1 = b1 != uu.y;
+            const V2 t = M::mul2(c.kN, M::mk2(Hu0, Hu1));                 // -Hu / h00
+            const R u0A = M::min(M::max(M::fma(c.kNo, b1, t.x), c.lo0), c.hi0);
+            const R u1B = M::min(M::max(M::fma(c.kNo, b0, t.y), c.lo1), c.hi1);
+            const R gA = M::fma(c.h00, b1, M::fma(c.h01, u0A, Hu1));      // dH/du1 at candidate A
+            const bool okA = gA * (b1 - uu.y) >= R(0);
+            const bool useA = viol1 && (okA || !viol0);
+            const bool useB = viol0 && !useA;
+            u0 = useA ? u0A : b0;
+            u1 = useB ? u1B : b1;
+            return;
+        }
         // unconstrained minimiser solve(H_uu, -H_u)  (:41)
         u0 = -M::fma(c.hi00, Hu0, c.hi01 * Hu1);
         u1 = -M::fma(c.hi01, Hu0, c.hi00 * Hu1);
         // :129  outside the box?  NaN compares false => treated as inside => NaN u propagates
-        const R viol = M::max(M::max(c.lo0 - u0, c.lo1 - u1), M::max(u0 - c.hi0, u1 - c.hi1));
-        const bool outside = viol > R(0);
-        if (MODE & 2) {
-            // minimisers of H along the four edges (bottom u1=lo1, left u0=lo0, top u1=hi1, right
-            // u0=hi0 -- the reference's candidate order, pontryagin_utils.py:78-86), each the clipped
-            // root of the tangential derivative
-            const R xb = M::min(M::max(M::fma(c.kN, Hu0, c.kQ[0]), c.lo0), c.hi0);
-            const R yl = M::min(M::max(M::fma(c.kN, Hu1, c.kQ[1]), c.lo1), c.hi1);
-            const R xt = M::min(M::max(M::fma(c.kN, Hu0, c.kQ[2]), c.lo0), c.hi0);
-            const R yr = M::min(M::max(M::fma(c.kN, Hu1, c.kQ[3]), c.lo1), c.hi1);
-            // KKT multiplier of the active bound = outward-pointing component of -grad H; the edge
-            // minimiser that solves the box problem is the one whose multiplier is >= 0 (the others
-            // are negative), so take the largest: first maximum wins, like the reference's argmin
-            const R mb = M::fma(c.h01, xb, Hu1 + c.kM[0]);
-            const R ml = M::fma(c.h01, yl, Hu0 + c.kM[1]);
-            const R mt = -M::fma(c.h01, xt, Hu1 + c.kM[2]);
-            const R mr = -M::fma(c.h01, yr, Hu0 + c.kM[3]);
-            R bm = mb, bx = xb, by = c.lo1;
-            bool gt = ml > bm;
-            bm = gt ? ml : bm; bx = gt ? c.lo0 : bx; by = gt ? yl : by;
-            gt = mt > bm;
-            bm = gt ? mt : bm; bx = gt ? xt : bx; by = gt ? c.hi1 : by;
-            gt = mr > bm;
-            bx = gt ? c.hi0 : bx; by = gt ? yr : by;
-            u0 = outside ? bx : u0;
-            u1 = outside ? by : u1;
-            return;
-        }
+        // (four chained compares -- FSETP folds the OR -- instead of four subtractions, three max and a compare)
+        const bool outside = (u0 < c.lo0) | (u1 < c.lo1) | (u0 > c.hi0) | (u1 > c.hi1);
         bool go = outside;
         if (WARP_VOTE) go = __any_sync(0xffffffffu, outside);
         if (go) {
@@ -220,19 +236,24 @@ template <class R> struct Flatquad {
         const R aw = (u1 - u0) * c.r_I;
         xd[0] = x[3]; xd[1] = x[4]; xd[2] = x[5]; xd[3] = ax; xd[4] = ay; xd[5] = aw;
         const R cm1 = co - R(1);
-        R l = c.q_pos * M::fma(x[0], x[0], x[1] * x[1]);
+        // running cost and -dH/dx with the (x0,x1), (x3,x4) terms on packed pairs (the pairs of PairMap<Flatquad>)
+        using V2 = typename M::V2;
+        const V2 x01 = M::mk2(x[0], x[1]), x34 = M::mk2(x[3], x[4]), a34 = M::mk2(ax, ay);
+        V2 acc = M::mul2v(M::mul2(c.q_pos, x01), x01);
+        acc = M::fma2v(M::mul2(c.q_vel, x34), x34, acc);
+        acc = M::fma2v(a34, a34, acc);
+        R l = acc.x + acc.y;
         l = M::fma(c.q_ang, M::fma(cm1, cm1, s * s), l);
-        l = M::fma(c.q_vel, M::fma(x[3], x[3], x[4] * x[4]), l);
         l = M::fma(c.q_om * x[5], x[5], l);
-        l = M::fma(ax, ax, l);
-        l = M::fma(ay, ay, l);
         l = M::fma(aw, aw, l);
         vd = -l;
-        ld[0] = -(c.two_qpos * x[0]);
-        ld[1] = -(c.two_qpos * x[1]);
+        const V2 l01 = M::mul2(-c.two_qpos, x01);
+        const V2 l34 = M::fma2(-c.two_qvel, x34, M::mk2(-lam[0], -lam[1]));
+        ld[0] = l01.x;
+        ld[1] = l01.y;
         ld[2] = M::fma(Sm, M::fma(lam[3], co, lam[4] * s), -(s * M::fma(c.two_g, Sm, c.two_qang)));
-        ld[3] = -M::fma(c.two_qvel, x[3], lam[0]);
-        ld[4] = -M::fma(c.two_qvel, x[4], lam[1]);
+        ld[3] = l34.x;
+        ld[4] = l34.y;
         ld[5] = -M::fma(c.two_qom, x[5], lam[2]);
     }
 
@@ -273,8 +294,7 @@ template <class R> struct Flatquad {
         const R Hu0 = base - rot, Hu1 = base + rot;
         R u0 = -M::fma(c.hi00, Hu0, c.hi01 * Hu1);
         R u1 = -M::fma(c.hi01, Hu0, c.hi00 * Hu1);
-        const R viol = M::max(M::max(c.lo0 - u0, c.lo1 - u1), M::max(u0 - c.hi0, u1 - c.hi1));
-        const bool outside = viol > R(0);
+        const bool outside = (u0 < c.lo0) | (u1 < c.lo1) | (u0 > c.hi0) | (u1 > c.hi1);
         // same selection as ustar_sc<2>, additionally tracking which coordinate moves along the winning edge
         const R xb = M::min(M::max(M::fma(c.kN, Hu0, c.kQ[0]), c.lo0), c.hi0);
         const R yl = M::min(M::max(M::fma(c.kN, Hu1, c.kQ[1]), c.lo1), c.hi1);

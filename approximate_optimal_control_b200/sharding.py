@@ -63,7 +63,8 @@ class PipelinedGather:
       * within a step the shard can be cut into `chunks` pieces; the gather of piece k runs while piece
         k+1 is integrated (costs one extra kernel tail, ~50 us, per piece);
       * across steps (`run(..., wait=False)`): the gather of step s runs while step s+1 is integrated;
-        two sets of gather buffers alternate, so the result of step s stays valid until step s+2 is issued.
+        two sets of gather buffers alternate, so the result of step s stays valid until run() of step s+2 is called
+        (readers enqueued on the current stream before that call are safe, see run()).
 
     transport="p2p" (default when torch symmetric memory is available): every rank pushes its piece
         straight into the peers' gather buffers with peer-to-peer cudaMemcpyAsync over NVLink
@@ -87,7 +88,9 @@ class PipelinedGather:
         chunks = max(1, min(chunks, n_local))
         edges = [n_local * c // chunks for c in range(chunks + 1)]
         self.slices = [(edges[c], edges[c + 1]) for c in range(chunks) if edges[c + 1] > edges[c]]
-        self.inputs = [torch.empty((self.ns, b - a), dtype=dtype, device=device) for a, b in self.slices]
+        # staging of the pieces' inputs (one piece: the caller's shard is integrated in place, nothing is staged)
+        self.inputs = [torch.empty((self.ns, b - a) if len(self.slices) > 1 else (0,), dtype=dtype, device=device)
+                       for a, b in self.slices]
         self.nsets = 2 if self.world > 1 else 1
         self.outs = [[{} for _ in self.slices] for _ in range(self.nsets)]
         self.side = torch.cuda.Stream(device=device) if self.world > 1 else None
@@ -137,16 +140,32 @@ class PipelinedGather:
     def run(self, y_local: torch.Tensor, wait: bool = True):
         """y_local [NS, n_local] -> list of per-piece gathered endpoint arrays [world, NS, n_piece].
         wait=True: the current stream waits for the transfers of this step.  wait=False: the transfers
-        keep running on the side stream (call wait() before reading the result / at the end)."""
+        keep running on the side stream (call wait() before reading the result / at the end).
+
+        Buffer protocol (two sets, step s uses set s % 2): the arrays returned by step s stay valid until run() of
+        step s+2 is CALLED; whatever reads them must have been enqueued on the current stream by then.  run() records
+        that point of the current stream, and the side stream passes a symmetric-memory barrier behind it BEFORE any
+        peer may push step s+2 into the set ("every rank has consumed set s % 2"); that barrier runs while the
+        shard is being integrated, so it costs nothing.  A second barrier after the pushes says "every rank's
+        step-s records have landed"."""
         main = torch.cuda.current_stream()
         s = self.step % self.nsets
         self.step += 1
         outs = self.outs[s]
         rows = slice(self.rank * self.ns, (self.rank + 1) * self.ns)
+        if self.world > 1 and self.transport == "p2p":
+            consumed = torch.cuda.Event()
+            consumed.record(main)
+            with torch.cuda.stream(self.side):
+                self.side.wait_event(consumed)
+                self.hdl.barrier(channel=1)  # all ranks are past their readers of this set: peers may overwrite it
         if self._copied[s] is not None:  # the pushes of step-2 must have finished reading this set's local slot
             main.wait_event(self._copied[s])
         for c, ((a, b), y_in, out) in enumerate(zip(self.slices, self.inputs, outs)):
-            y_in.copy_(y_local[:, a:b])
+            if len(self.slices) == 1 and y_local.is_contiguous():
+                y_in = y_local  # one piece: integrate straight from the caller's shard (no staging copy)
+            else:
+                y_in.copy_(y_local[:, a:b])
             self._pu.solve_batch_soa(self.problem, self.opts, y_in, out)
             if self.world == 1:
                 continue

@@ -1,28 +1,40 @@
 #!/usr/bin/env python
 """bench.py -- PMP backward-shooting rollouts: trajectories/s on N B200s, fraction of the FP32 FMA peak.
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload endpoints|dense]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload endpoints|dense] [--scaling weak|strong]
                     [--dtype f32|f64] [--method tsit5|dopri5|rk4] [--log2n 20] [--impl reference]
 
 A "step" is ONE pass of the hot path over one batch of synthetic terminal samples: per GPU,
 2^20 flat-quadrotor trajectories (flatquad_landing_experiment.py:340-437 constants, terminal states
 on the LQR level set V_f = 1e-3 as in levelsets.py:551-599), Tsit5 + I-controller at
 rtol = atol = 1e-5, T = 3, <= 128 step attempts, fp32 -- BASELINE.json's headline configuration
-("2^20 flat-quadrotor PMP rollouts", config C4).  With N > 1 every rank solves its own 2^20 shard
-(weak scaling, no collective during the solve) and the step ends with the ONE all-gather of the
-endpoint records (x, lambda, v, t) the north star names.
+("2^20 flat-quadrotor PMP rollouts", config C4).  With N > 1 every rank solves its own shard
+(no collective during the solve) and the step ends with the ONE all-gather of the endpoint records
+(x, lambda, v, t) the north star names.  --scaling weak (default, what the driver runs): 2^20 per GPU.
+--scaling strong: BASELINE.json configs[3] as worded, 2^20 in all, 2^20 / N per GPU.  The weak line also carries
+the strong measurement of the same run under "strong".
+
+Timing (the same at every N): W >= 3 warm-up steps, barrier + synchronize, K steps issued back to back on the device
+between two CUDA events ("first step starts" .. "last gather has landed"), barrier + synchronize; max over ranks.
+No L2 flush: one step touches 172 MB per GPU (terminal states, k1, endpoints), more than the 126 MB L2 (the strong
+mode's smaller shards say so in config.l2).  The dominant kernel is timed on its own stream by an event pair around
+every launch of the same K steps.
 
 JSON keys beyond the base contract:
-  roofline      bound "fp32_fma" (the path is not a dense contraction and, endpoints-only, moves
-                ~170 B per trajectory): achieved = ALGORITHMIC flops (approximate_optimal_control_b200/
-                flops.py, counted on the oracle's op-counting scalar) / CUDA-event time of the solve;
-                peak = a register-resident FFMA chain measured in this same process
-                (MEASURED_PEAKS.json holds only HBM and bf16 numbers).  --workload dense reports the
-                HBM write roofline instead (peak = MEASURED_PEAKS.json hbm_gbs).
-  cpu_baseline  the CPU oracle (kind "port": a C++ restatement of the reference; jax/diffrax cannot
-                be installed here) on all host threads, on a bounded sample of the same workload.
-  e2e           the same metric through the public API (define_backward_solver -> solve_backward)
-                from pinned HOST buffers, host->device and device->host copies inside the timed region.
+  roofline      bound "fp32_fma" (the path is not a dense contraction and, endpoints-only, moves ~170 B per trajectory):
+                achieved = ALGORITHMIC flops (approximate_optimal_control_b200/flops.py, counted on the oracle's
+                op-counting scalar) / CUDA-event time of the solve; peak = register-resident FMA chains measured in this
+                same process (MEASURED_PEAKS.json holds only HBM and bf16 numbers); frac_of_theoretical uses
+                148 SM x 128 lanes x 2 x sm_max_mhz.  --workload dense (and the "dense" block of the default line)
+                report the HBM write roofline instead (peak = MEASURED_PEAKS.json hbm_gbs).
+  parity        accuracy of THIS run's endpoints: a 2^12 subsample against the converged fp64 solution (oracle at
+                tol 1e-12), next to the fp32 oracle's accuracy against the same truth, in units of the solver tolerance.
+  cpu_baseline  the CPU oracle (kind "port": a C++ restatement of the reference; jax/diffrax cannot be installed here) on
+                all host threads, on a bounded sample of the same workload; plus one-core and fp64 figures.
+  e2e           the same metric through the public API (define_backward_solver -> solve_backward) from pinned HOST
+                buffers, host->device and device->host copies inside the timed region.
+  gather_check  N > 1: rank 0 re-solves every rank's shard in one launch and compares it BIT FOR BIT with the slice
+                that rank pushed into rank 0's gathered dataset.
 """
 from __future__ import annotations
 
@@ -49,9 +61,11 @@ def parse_args():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="endpoints", choices=["endpoints", "dense"])
+    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
+                    help="weak: 2^log2n trajectories per GPU; strong: 2^log2n in all (BASELINE.json configs[3])")
     ap.add_argument("--dtype", default="f32", choices=["f32", "f64"])
     ap.add_argument("--method", default="tsit5", choices=["tsit5", "dopri5", "rk4"])
-    ap.add_argument("--log2n", type=int, default=20, help="log2 of trajectories per GPU")
+    ap.add_argument("--log2n", type=int, default=20, help="log2 of trajectories per GPU (weak) / in all (strong)")
     ap.add_argument("--cpu-log2n", type=int, default=20, help="log2 of the cpu_baseline sample")
     ap.add_argument("--cpu-seconds", type=float, default=10.0, help="wall time spent on the cpu_baseline sample")
     ap.add_argument("--gather-chunks", type=int, default=0,
@@ -62,6 +76,9 @@ def parse_args():
                     help="N>1 endpoint gather transport: peer-to-peer copies over NVLink (symmetric memory) or NCCL")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-parity", action="store_true")
+    ap.add_argument("--no-dense", action="store_true", help="skip the dense (C5) block of the default N=1 line")
+    ap.add_argument("--no-strong", action="store_true", help="N>1, weak: skip the strong-scaling block")
     return ap.parse_args()
 
 
@@ -130,25 +147,34 @@ def host_cores() -> int:
         return os.cpu_count() or 1
 
 
+def oracle_opts(O, args, dtype=None, dense=False):
+    method = {"tsit5": O.TSIT5, "dopri5": O.DOPRI5, "rk4": O.RK4}[args.method]
+    odt = {"f32": O.F32, "f64": O.F64}[dtype or args.dtype]
+    return O.make_opts(method=method, dtype=odt, adaptive=int(args.method != "rk4"),
+                       dt0=-0.1 if args.method != "rk4" else -1 / 32, save_dense=int(dense))
+
+
+def n_per_gpu(args, world):
+    n = 1 << args.log2n
+    return n if args.scaling == "weak" else max(1, n // world)
+
+
 # --------------------------------------------------------------------------------------------------
 def run_reference(args):
     """--impl reference: the reference's algorithm on the host cores.  The reference itself (jax 0.4.23 +
-    diffrax 0.4.1) is not installable offline, so this is the CPU oracle ("port"), all host threads,
-    each step a bounded sample (2^17 trajectories) of the same workload."""
+    diffrax 0.4.1) is not installable offline, so this is the CPU oracle ("port"), all host threads, on the SAME
+    configuration as the b200 arm: every step is one pass over the same 2^log2n-trajectory batch (0.4-2 s of CPU)."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
     from oracle import oracle as O
-    n = 1 << 17
-    odt = O.F32 if args.dtype == "f32" else O.F64
+    n = n_per_gpu(args, max(1, args.gpus)) if args.scaling == "weak" else (1 << args.log2n)
     y, _ = terminal_batch(n, 1, np.float32 if args.dtype == "f32" else np.float64)
-    method = {"tsit5": O.TSIT5, "dopri5": O.DOPRI5, "rk4": O.RK4}[args.method]
-    opts = O.make_opts(method=method, dtype=odt, adaptive=int(args.method != "rk4"),
-                       dt0=-0.1 if args.method != "rk4" else -1 / 32, save_dense=int(args.workload == "dense"))
+    opts = oracle_opts(O, args, dense=args.workload == "dense")
     prob = O.flatquad_problem()
     cores = host_cores()  # torchrun exports OMP_NUM_THREADS=1: ask for every core this process may run on explicitly
-    for _ in range(args.warmup):
-        O.solve_batch(prob, opts, y, n_threads=cores)
+    for _ in range(min(args.warmup, 2)):
+        O.solve_batch(prob, opts, y[:, : n // 4], n_threads=cores)
     t0 = time.perf_counter()
     attempts = 0
     for _ in range(args.steps):
@@ -159,28 +185,30 @@ def run_reference(args):
     line = {
         "impl": "reference", "metric": "PMP trajectories/sec", "value": value, "unit": "trajectories/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps,
-        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": args.dtype, "data": "synthetic",
+        "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None, "dtype": args.dtype, "data": "synthetic",
         "rk_step_attempts_per_s": attempts / dt,
-        "config": workload_config(args, n),
+        "config": workload_config(args, n, 1),
         "cpu_baseline": {"value": value, "unit": "trajectories/s", "cores": cores, "kind": "port",
-                         "sample": f"{args.steps} x 2^17 flatquad terminal samples, same solver settings "
-                                   "(CPU restatement of the reference; jax/diffrax unavailable offline)"},
+                         "sample": f"{args.steps} passes over 2^{int(np.log2(n))} flatquad terminal samples (one GPU's batch of the "
+                                   "b200 arm), same solver settings (CPU restatement of the reference; jax/diffrax unavailable offline)"},
         "e2e": {"value": value, "unit": "trajectories/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     print(json.dumps(line), flush=True)
 
 
-def workload_config(args, n_per_gpu):
+def workload_config(args, n_local, world):
+    per_step_mb = 3 * 14 * n_local * (4 if args.dtype == "f32" else 8) / 1e6
     return {
-        "workload": f"flatquad PMP backward shooting, 2^{int(np.log2(n_per_gpu))} terminal samples per GPU, "
+        "workload": f"flatquad PMP backward shooting, 2^{np.log2(n_local):g} terminal samples per GPU, "
                     f"{args.method} {'adaptive rtol=atol=1e-5' if args.method != 'rk4' else 'fixed dt=1/32'}, "
                     f"T=3, max 128 attempts, {'dense SaveAt(steps) output' if args.workload == 'dense' else 'endpoints only'}"
-                    + (", all-gather of endpoints" if args.gpus > 1 else ""),
-        "system": "flatquad (nx=6, nu=2, box-clipped u*)", "trajectories_per_gpu": n_per_gpu,
+                    + (", all-gather of endpoints" if world > 1 else ""),
+        "system": "flatquad (nx=6, nu=2, box-clipped u*)", "trajectories_per_gpu": n_local,
+        "trajectories_total": n_local * world,
         "solver": args.method, "rtol": 1e-5, "atol": 1e-5, "T": 3.0, "max_steps": 128,
-        "parallelism": f"shard{args.gpus}" if args.gpus > 1 else "single",
-        "l2": ("flushed between timed steps (256 MiB write); per-step working set 172 MB > 126 MB L2" if args.gpus == 1
-               else "no flush: back-to-back pipelined steps, per-step working set 172 MB per GPU > 126 MB L2"),
+        "parallelism": f"shard{world}" if world > 1 else "single",
+        "l2": (f"no flush: steps run back to back at every N; per-step working set {per_step_mb:.0f} MB per GPU "
+               + ("> 126 MB L2" if per_step_mb > 126 else "< 126 MB L2 (inputs and k1 of the previous step may still be cached)")),
     }
 
 
@@ -204,50 +232,99 @@ def main():
     dev = torch.device("cuda", local_rank)
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
-    n_gpus = world
 
-    n = 1 << args.log2n
     tdt = torch.float32 if args.dtype == "f32" else torch.float64
     ndt = np.float32 if args.dtype == "f32" else np.float64
-    y_np, st_np = terminal_batch(n, 1 + rank, ndt)
+    es = 4 if args.dtype == "f32" else 8
     pp, ap = systems.flatquad_problem_params(), systems.flatquad_algo_params()
     problem = systems.to_c_problem(pp)
     method = _capi.METHODS[args.method]
     dense = args.workload == "dense"
-    opts = _capi.make_opts(method=method, dtype=_capi.F32 if args.dtype == "f32" else _capi.F64,
-                           adaptive=int(args.method != "rk4"), dt0=-0.1 if args.method != "rk4" else -1 / 32,
-                           save_dense=int(dense))
+    mk_opts = lambda dn: _capi.make_opts(method=method, dtype=_capi.F32 if args.dtype == "f32" else _capi.F64,
+                                         adaptive=int(args.method != "rk4"), dt0=-0.1 if args.method != "rk4" else -1 / 32,
+                                         save_dense=int(dn))
+    opts = mk_opts(dense)
     L = _capi.lib()
-
-    y_dev = torch.as_tensor(y_np, device=dev).contiguous()
-    out = {}
-    # N > 1: the shard is integrated in pieces and the endpoint all-gather of piece k overlaps piece k+1
-    # (0 = auto: every extra piece costs one more kernel tail, ~50 us; worth it only when the gather is long)
+    launches_per_solve = L.pmp_solve_launch_count(C.byref(problem), C.byref(opts), 1 << 10)
     chunks = args.gather_chunks if args.gather_chunks > 0 else 1
-    pg = sharding.PipelinedGather(problem, opts, n, tdt, dev, chunks=chunks, transport=args.gather) if world > 1 else None
-    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+    gpu_launches = 0
 
-    def step():
-        if world > 1:
-            # software pipeline across steps: the gather of step s runs while step s+1 is integrated;
-            # every gather completes inside the timed region (pg.wait() before the closing barrier)
-            pg.run(y_dev, wait=args.no_step_overlap)
-        else:
-            pu.solve_batch_soa(problem, opts, y_dev, out)
+    def shard_inputs(scaling):
+        """(y_dev [14, n_local], st_np leaves of this rank's shard, n_local, seed rule)"""
+        if scaling == "weak":
+            n_loc = 1 << args.log2n
+            y_np, st_np = terminal_batch(n_loc, 1 + rank, ndt)
+        else:  # one global batch (seed 1), contiguous shards (iid samples: SURVEY.md 8(e))
+            n_all = 1 << args.log2n
+            n_loc = n_all // world
+            y_all, st_all = terminal_batch(n_all, 1, ndt)
+            sl = slice(rank * n_loc, (rank + 1) * n_loc)
+            y_np, st_np = np.ascontiguousarray(y_all[:, sl]), {k: np.ascontiguousarray(v[sl]) for k, v in st_all.items()}
+        return torch.as_tensor(y_np, device=dev).contiguous(), st_np, y_np, n_loc
 
-    def barrier():
-        if world > 1:
+    def barrier(pg=None):
+        if pg is not None:
             pg.wait()
-            torch.cuda.synchronize()
-            dist.barrier()
         torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    def reduce_max(x):
+        t = torch.tensor([x], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return t.item()
+
+    def reduce_sum(x):
+        t = torch.tensor([x], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        return t.item()
+
+    def timed_steps(y_dev, n_loc, o, with_gather, steps, warm):
+        """K steps back to back between two events (first step starts .. everything, gathers included, has landed);
+        per-launch event pairs around every solve give the kernel time.  Returns a dict (ms are max over ranks)."""
+        nonlocal gpu_launches
+        pg = (sharding.PipelinedGather(problem, o, n_loc, tdt, dev, chunks=chunks, transport=args.gather)
+              if (world > 1 and with_gather) else None)
+        out = {}
+
+        def step():
+            if pg is not None:
+                pg.run(y_dev, wait=args.no_step_overlap)
+            else:
+                pu.solve_batch_soa(problem, o, y_dev, out)
+
+        for _ in range(warm):
+            step()
+        barrier(pg)
+        pairs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
+        t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        barrier(pg)
+        t0.record()
+        for a, b in pairs:
+            a.record()
+            step()
+            b.record()   # end of this step's solve launches on the current stream (the gather runs on the side stream)
+        if pg is not None:
+            pg.wait()    # the current stream waits for the last gather: the pipeline is drained
+        t1.record()
+        barrier(pg)
+        gpu_launches += steps * launches_per_solve * (len(pg.slices) if pg is not None else 1)
+        total_ms = reduce_max(t0.elapsed_time(t1))
+        solve_ms = float(np.mean([a.elapsed_time(b) for a, b in pairs]))
+        att = (pg.attempts() if pg is not None else out["n_steps"].sum()).item()
+        return {"total_ms": total_ms, "ms_per_step": total_ms / steps, "solve_ms": solve_ms, "attempts": att, "pg": pg,
+                "out": out}
 
     # ---- FMA peak (roofline denominator), measured in this process ---------------------------------
     scratch = torch.zeros(16, dtype=torch.float64, device=dev)
     pdt = _capi.F32 if args.dtype == "f32" else _capi.F64
-    peak_tflops = 0.0
-    for variant in (0, 1):
+    peaks_by_variant = {}
+    for variant in ((0, 1, 2) if args.dtype == "f32" else (0, 1)):
         fl = C.c_double()
+        best = 0.0
         for it in range(5):
             a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             a.record()
@@ -256,103 +333,139 @@ def main():
             b.record()
             torch.cuda.synchronize()
             if it >= 1:
-                peak_tflops = max(peak_tflops, fl.value / (a.elapsed_time(b) * 1e-3) / 1e12)
+                best = max(best, fl.value / (a.elapsed_time(b) * 1e-3) / 1e12)
+        peaks_by_variant[{0: "ffma_reg", 1: "ffma_imm", 2: "ffma2_packed"}[variant]] = best
+    peak_tflops = max(peaks_by_variant.values())
 
-    # ---- warm-up, then K timed steps ----------------------------------------------------------------
+    # ---- the headline measurement ---------------------------------------------------------------------
     sampler = ClockSampler(local_rank) if rank == 0 else None
-    for _ in range(max(args.warmup, 3)):
-        step()
-    barrier()
-    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
-          for _ in range(args.steps)]
-    attempts = 0
     t_begin = time.time()
-    barrier()
-    drained = torch.cuda.Event(enable_timing=True)
-    for k in range(args.steps):
-        if world == 1:
-            flush.fill_(k & 0xFF)  # L2 flush, outside the per-step event pair
-        a, m, b = ev[k]
-        a.record()
-        step()
-        m.record()
-        b.record()
-    if world > 1:
-        pg.wait()  # the current stream waits for the last gather: the pipeline is drained
-    drained.record()
-    barrier()
-    t_end = time.time()
-    step_ms = [a.elapsed_time(b) for (a, m, b) in ev]
-    solve_ms = [a.elapsed_time(m) for (a, m, b) in ev]
-    if world > 1:
-        # steps are software-pipelined (gather of step s under the integration of step s+1) and run back
-        # to back without L2 flushes (the 172 MB per-step working set exceeds the 126 MB L2): the time of
-        # the K steps is first start .. pipeline drained
-        step_ms = [ev[0][0].elapsed_time(drained) / args.steps] * args.steps
-    total_ms = torch.tensor([sum(step_ms)], dtype=torch.float64, device=dev)
-    total_solve_ms = torch.tensor([sum(solve_ms)], dtype=torch.float64, device=dev)
-    my_attempts_t = (pg.attempts() if world > 1 else out["n_steps"].sum()).to(torch.float64).reshape(1)
-    attempts_t = my_attempts_t.clone()
-    if world > 1:
-        dist.all_reduce(total_ms, op=dist.ReduceOp.MAX)
-        dist.all_reduce(total_solve_ms, op=dist.ReduceOp.MAX)
-        dist.all_reduce(attempts_t, op=dist.ReduceOp.SUM)
-    total_s = total_ms.item() * 1e-3
-    attempts_per_step = attempts_t.item()  # all ranks, one step
+    y_dev, st_np, y_np, n = shard_inputs(args.scaling)
+    warm = max(args.warmup, 3)
+    main_run = timed_steps(y_dev, n, opts, True, args.steps, warm)
+    total_s = main_run["total_ms"] * 1e-3
     value = n * world * args.steps / total_s
-
-    # ---- roofline of the dominant kernel (rank 0's own launches) -------------------------------------
-    my_attempts = int(my_attempts_t.item())
+    attempts_all = reduce_sum(main_run["attempts"])  # all ranks, one step
+    pg = main_run["pg"]
+    gather = None
     if world > 1:
-        # kernel-only time of this rank's solve launches: re-time the same pieces without the collective
-        t_solo = []
-        for _ in range(3):
-            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            a.record()
-            for y_in, o_ in zip(pg.inputs, pg.outs[0]):
-                pu.solve_batch_soa(problem, opts, y_in, o_)
-            b.record()
-            torch.cuda.synchronize()
-            t_solo.append(a.elapsed_time(b))
-        solve_s = min(t_solo) * 1e-3
-    else:
-        solve_s = float(np.mean(solve_ms)) * 1e-3
+        solo = timed_steps(y_dev, n, opts, False, args.steps, 2)  # the same K steps without the collective
+        gather = {"chunks": len(pg.slices), "transport": pg.transport,
+                  "bytes_per_rank_per_step": int(y_dev.numel() * y_dev.element_size()),
+                  "ms_with_gather": main_run["ms_per_step"], "ms_without_gather": solo["ms_per_step"],
+                  "overlap": ("none across steps" if args.no_step_overlap else
+                              "gather of step s (copy engines, peer-to-peer over NVLink; NCCL all_gather_into_tensor with "
+                              "--gather nccl) overlaps the integration of step s+1 (double-buffered); all gathers complete "
+                              "inside the timed region")}
+    solve_s = main_run["solve_ms"] * 1e-3 if world == 1 else reduce_max(main_run["solve_ms"]) * 1e-3
+    my_attempts = int(main_run["attempts"])
+
+    # ---- gather_check: the gathered dataset is what a single launch computes, bit for bit ------------------------
+    gather_check = None
+    if world > 1:
+        pieces = pg.run(y_dev, wait=True)
+        torch.cuda.synchronize()
+        full = torch.cat(pieces, dim=2)  # [world, NS, n]
+        ok = True
+        detail = []
+        if rank == 0:
+            for r in range(world):
+                if args.scaling == "weak":
+                    y_r = torch.as_tensor(terminal_batch(n, 1 + r, ndt)[0], device=dev).contiguous()
+                else:
+                    y_r = torch.as_tensor(np.ascontiguousarray(terminal_batch(n * world, 1, ndt)[0][:, r * n:(r + 1) * n]), device=dev)
+                ref = pu.solve_batch_soa(problem, opts, y_r)["y_end"]
+                torch.cuda.synchronize()
+                same = bool(torch.equal(ref, full[r]))
+                detail.append(same)
+                ok = ok and same
+        flag = torch.tensor([1.0 if ok else 0.0], dtype=torch.float64, device=dev)
+        dist.broadcast(flag, 0)
+        gather_check = "ok" if flag.item() == 1.0 else f"MISMATCH {detail}"
+        if rank == 0 and gather_check != "ok":
+            print(f"gather_check failed: per-rank bit equality {detail}", file=sys.stderr)
+
+    # ---- roofline of the dominant kernel (this rank's own launches) -----------------------------------
+    mpeaks = {}
+    try:
+        mpeaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+
+    def dense_roof(sec, n_loc):
+        peak_gbs = mpeaks.get("hbm_gbs", 6650.0)
+        bytes_alg = flops.dense_bytes(n_loc, 6, opts.max_steps, es) + 2 * 14 * n_loc * es
+        return {"bound": "hbm", "achieved": bytes_alg / sec / 1e9, "peak": peak_gbs, "unit": "GB/s",
+                "frac": bytes_alg / sec / 1e9 / peak_gbs, "traffic": None,
+                "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured)" if mpeaks else "6650 GB/s (of fallback)",
+                "algorithmic_bytes_per_launch": bytes_alg, "kernel_ms": sec * 1e3}
+
+    def load_traffic(roof, workload):
+        tf = os.path.join(ROOT, "profiles", "traffic.json")
+        if os.path.exists(tf) and n == (1 << 20):
+            try:
+                roof["traffic"] = json.load(open(tf)).get(f"{workload}_{args.dtype}_{args.method}")
+            except Exception:
+                pass
+
     if dense:
-        peaks = {}
-        try:
-            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
-        except Exception:
-            pass
-        peak_gbs = peaks.get("hbm_gbs", 6650.0)
-        bytes_alg = flops.dense_bytes(n, 6, opts.max_steps, 4 if args.dtype == "f32" else 8) + 2 * y_dev.numel() * y_dev.element_size()
-        roof = {"bound": "hbm", "achieved": bytes_alg / solve_s / 1e9, "peak": peak_gbs, "unit": "GB/s",
-                "frac": bytes_alg / solve_s / 1e9 / peak_gbs, "traffic": None,
-                "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured)" if peaks else "6650 GB/s (of fallback)",
-                "algorithmic_bytes_per_launch": bytes_alg}
+        roof = dense_roof(solve_s, n)
     else:
         fl_alg = flops.solve_flops(problem.system_id, method, my_attempts, n)
+        sm_max = mpeaks.get("sm_max_mhz", 1965.0)
+        theo = 148 * 128 * 2 * sm_max * 1e6 / 1e12 / (1 if args.dtype == "f32" else 2)
         roof = {"bound": "fp32_fma" if args.dtype == "f32" else "fp64_fma", "achieved": fl_alg / solve_s / 1e12,
                 "peak": peak_tflops, "unit": "TFLOP/s", "frac": fl_alg / solve_s / 1e12 / peak_tflops, "traffic": None,
-                "peak_source": "FMA-chain microbenchmark (pmp_fma_peak_cuda) in this process, burst; "
-                               "MEASURED_PEAKS.json has no CUDA-core figure",
+                "peak_source": "FMA-chain microbenchmark (pmp_fma_peak_cuda) in this process, burst, best of "
+                               f"{peaks_by_variant}; MEASURED_PEAKS.json has no CUDA-core figure",
+                "peak_theoretical": theo, "frac_of_theoretical": fl_alg / solve_s / 1e12 / theo,
                 "algorithmic_flops_per_launch": fl_alg,
                 "flops_per_attempt": flops.ATTEMPT_FLOPS[(problem.system_id, method)],
                 "flops_per_rhs": flops.RHS_FLOPS[problem.system_id],
                 "kernel_ms": solve_s * 1e3}
-    # measured DRAM traffic of one launch (ncu --set full capture of this same configuration, committed under
-    # profiles/); null when no capture exists for the configuration
-    traffic_file = os.path.join(ROOT, "profiles", "traffic.json")
-    if os.path.exists(traffic_file) and args.log2n == 20:
+    load_traffic(roof, args.workload)
+
+    # ---- strong scaling (BASELINE.json configs[3]: 2^20 in all over N GPUs), same run ------------------------------
+    strong = None
+    if world > 1 and args.scaling == "weak" and not args.no_strong and not dense:
+        del pg
+        main_run["pg"] = None
+        saved = args.scaling
+        args.scaling = "strong"
+        ys_dev, _, _, ns_loc = shard_inputs("strong")
+        args.scaling = saved
+        sr = timed_steps(ys_dev, ns_loc, opts, True, args.steps, warm)
+        sr_solo = timed_steps(ys_dev, ns_loc, opts, False, args.steps, 2)
+        strong = {"trajectories_total": ns_loc * world, "trajectories_per_gpu": ns_loc,
+                  "value": ns_loc * world * args.steps / (sr["total_ms"] * 1e-3), "unit": "trajectories/s",
+                  "ms_per_step": sr["ms_per_step"], "ms_without_gather": sr_solo["ms_per_step"],
+                  "kernel_ms": reduce_max(sr["solve_ms"]),
+                  "limiter": "per-launch tail: a shard of 2^20/N trajectories is only a few trajectories per resident lane "
+                             "(148 SMs x 384 lanes), so the wait for the slowest lanes of the last wave no longer amortises"}
+        sr["pg"] = None
+
+    # ---- dense workload (BASELINE.json configs[4], C5) attached to the default line ------------------------------
+    dense_block = None
+    if world == 1 and not dense and not args.no_dense and args.log2n <= 20:
+        od = mk_opts(True)
+        dr = timed_steps(y_dev, n, od, False, max(3, min(args.steps, 10)), 2)
+        dense_block = {"workload": "same batch with SaveAt(steps) output: every slot of ts, t, v, x, vx written once",
+                       "ms_per_step": dr["ms_per_step"], "value": n / (dr["ms_per_step"] * 1e-3), "unit": "trajectories/s",
+                       "roofline": dense_roof(dr["solve_ms"] * 1e-3, n)}
         try:
-            roof["traffic"] = json.load(open(traffic_file)).get(f"{args.workload}_{args.dtype}_{args.method}")
+            dense_block["roofline"]["traffic"] = json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get(
+                f"dense_{args.dtype}_{args.method}")
         except Exception:
             pass
+        dr["out"].clear()
+        torch.cuda.empty_cache()
 
     # ---- e2e: public API, host buffers ---------------------------------------------------------------
     e2e = None
     if not args.no_e2e:
         solve_backward, _ = pu.define_backward_solver(pp, dict(ap, pontryagin_solver_method=args.method,
                                                                pontryagin_solver_save_steps=dense,
+                                                               dtype="float32" if args.dtype == "f32" else "float64",
                                                                **({"pontryagin_solver_dt0": 1 / 32} if args.method == "rk4" else {})))
         host_in = {k: torch.as_tensor(v).pin_memory() for k, v in st_np.items()}
         host_out = {k: torch.empty(v.shape, dtype=tdt).pin_memory() for k, v in st_np.items()}
@@ -382,11 +495,14 @@ def main():
         for _ in range(args.steps):
             e2e_step()
         barrier()
-        e_s = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
-        if world > 1:
-            dist.all_reduce(e_s, op=dist.ReduceOp.MAX)
-        e2e = {"value": n * world * args.steps / e_s.item(), "unit": "trajectories/s",
+        e_s = reduce_max(time.perf_counter() - t0)
+        if not dense:
+            k, c = C.c_int(), C.c_int()
+            pcs = L.pmp_solve_host_plan(C.byref(problem), C.byref(opts), n, 0, C.byref(k), C.byref(c)) if hasattr(L, "pmp_solve_host_plan") else 0
+            gpu_launches += (args.steps + 3) * (k.value if pcs > 0 else 0)
+        e2e = {"value": n * world * args.steps / e_s, "unit": "trajectories/s",
                "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+               "gather": "none: every rank returns its own shard's endpoints to its host; the NVLink gather is part of `value` only" if world > 1 else None,
                "api": "pontryagin_utils.define_backward_solver(...)[0](state dict of pinned host tensors) -> endpoints in pinned "
                       "host tensors through the C entry pmp_solve_host (host pointers), which pipelines host->device copy, integration "
                       "and device->host copy over pieces on its own streams"
@@ -399,47 +515,74 @@ def main():
     if clocks is not None:
         clocks["window"] = "warm-up + timed steps + e2e loop"
 
-    # ---- cpu baseline (rank 0, N=1 only) --------------------------------------------------------------
+    # ---- parity of this run's numbers + cpu baseline (rank 0, N=1 only) ----------------------------------
     cpu = None
-    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+    parity = None
+    if rank == 0 and world == 1 and not (args.no_cpu_baseline and args.no_parity):
         from oracle import oracle as O
+    if rank == 0 and world == 1 and not args.no_parity and not dense:
+        m = min(n, 1 << 12)
+        tol = 1e-5
+        rows = list(range(6)) + list(range(7, 14))
+        got = main_run["out"]["y_end"][:, :m].double().cpu().numpy()
+        orc = O.solve_batch(O.flatquad_problem(), oracle_opts(O, args), y_np[:, :m])
+        y64 = terminal_batch(1 << args.log2n, 1 + rank, np.float64)[0][:, :m] if args.scaling == "weak" else \
+            terminal_batch(1 << args.log2n, 1, np.float64)[0][:, :m]
+        truth = O.solve_batch(O.flatquad_problem(), O.make_opts(dtype=O.F64, rtol=1e-12, atol=1e-12, max_steps=100000, dtmin=0.0),
+                              y64)["y_end"]
+        se = lambda a, b: (np.abs(a[rows] - b[rows]) / (tol + tol * np.abs(b[rows]))).max(0)
+        eg, eo, d = se(got, truth), se(orc["y_end"].astype(np.float64), truth), se(got, orc["y_end"].astype(np.float64))
+        gpu_steps = main_run["out"]["n_steps"][:m].cpu().numpy()
+        parity = {"sample": f"first 2^{int(np.log2(m))} trajectories of the timed batch", "unit": "solver tolerance units: |a-b| / (tol + tol |b|), tol = 1e-5, max over x, lambda, v",
+                  "gpu_vs_fp64_truth_p50": float(np.percentile(eg, 50)), "gpu_vs_fp64_truth_p99": float(np.percentile(eg, 99)),
+                  "oracle_vs_fp64_truth_p50": float(np.percentile(eo, 50)), "oracle_vs_fp64_truth_p99": float(np.percentile(eo, 99)),
+                  "gpu_vs_oracle_p50": float(np.percentile(d, 50)), "gpu_vs_oracle_p99": float(np.percentile(d, 99)),
+                  "identical_step_counts": float((gpu_steps == orc["n_steps"]).mean()),
+                  "results_identical": bool((main_run["out"]["result"][:m].cpu().numpy() == orc["result"]).all()),
+                  "truth": "CPU oracle, fp64, Tsit5 at rtol = atol = 1e-12 (converged solution of the reference's ODE)",
+                  "step_control": "unpinned (diffrax 0.4.1 absent: oracle and kernel implement the restatement of DESIGN.md 5)",
+                  "note": "fp32 at T=3 amplifies rounding to tens of tolerance units (tests/test_oracle.py::test_fp32_reproducibility_floor); "
+                          "the gate is gpu_vs_fp64_truth <= 1.25 x oracle_vs_fp64_truth per percentile (tests/test_gpu_parity.py)"}
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
         nc = 1 << args.cpu_log2n
-        oo = O.make_opts(method={"tsit5": O.TSIT5, "dopri5": O.DOPRI5, "rk4": O.RK4}[args.method],
-                         dtype=O.F32 if args.dtype == "f32" else O.F64, adaptive=int(args.method != "rk4"),
-                         dt0=-0.1 if args.method != "rk4" else -1 / 32)
         ys = y_np[:, :nc] if nc <= n else y_np
         ncores = host_cores()
+        oo = oracle_opts(O, args)
         O.solve_batch(O.flatquad_problem(), oo, ys[:, :4096], n_threads=ncores)
-        t0 = time.perf_counter()
-        passes = 0
-        while True:  # bounded sample: whole passes over the batch until ~10 s of wall time on all host threads
-            O.solve_batch(O.flatquad_problem(), oo, ys, n_threads=ncores)
-            passes += 1
-            dtc = time.perf_counter() - t0
-            if dtc >= args.cpu_seconds or passes >= 64:
-                break
-        cpu = {"value": passes * ys.shape[1] / dtc, "unit": "trajectories/s", "cores": ncores, "kind": "port",
+
+        def cpu_rate(o_, y_, threads, seconds, max_passes=64):
+            t0 = time.perf_counter()
+            passes = 0
+            while True:  # bounded sample: whole passes over the batch until `seconds` of wall time
+                O.solve_batch(O.flatquad_problem(), o_, y_, n_threads=threads)
+                passes += 1
+                dtc = time.perf_counter() - t0
+                if dtc >= seconds or passes >= max_passes:
+                    return passes * y_.shape[1] / dtc, passes, dtc
+
+        v, passes, dtc = cpu_rate(oo, ys, ncores, args.cpu_seconds)
+        v1, p1, d1 = cpu_rate(oo, ys[:, : 1 << 14], 1, min(4.0, args.cpu_seconds))
+        o64 = oracle_opts(O, args, dtype="f64")
+        v64, p64, d64 = cpu_rate(o64, ys[:, : 1 << 17].astype(np.float64), ncores, min(4.0, args.cpu_seconds))
+        cpu = {"value": v, "unit": "trajectories/s", "cores": ncores, "kind": "port",
                "sample": f"{passes} passes over the first 2^{int(np.log2(ys.shape[1]))} trajectories of the same batch, same "
                          f"solver settings, {dtc:.1f} s wall on {ncores} threads; C++ restatement of the reference "
-                         "(jax/diffrax not installable offline)"}
+                         "(jax/diffrax not installable offline)",
+               "one_core": {"value": v1, "cores": 1, "sample": f"{p1} passes over 2^14 trajectories, {d1:.1f} s"},
+               "fp64": {"value": v64, "cores": ncores, "sample": f"{p64} passes over 2^17 trajectories in fp64, {d64:.1f} s"}}
 
     if rank == 0:
         line = {
-            "metric": "PMP trajectories/sec", "value": value, "unit": "trajectories/s", "n_gpus": n_gpus,
-            "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": total_ms.item() / args.steps,
-            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": args.dtype, "data": "synthetic",
-            "config": workload_config(args, n),
-            "rk_step_attempts_per_s": attempts_per_step * args.steps / total_s,
-            "mean_attempts_per_trajectory": attempts_per_step / (n * world),
-            "solve_ms_per_step": (total_solve_ms.item() / args.steps) if world == 1 else solve_s * 1e3,
-            "roofline": roof, "cpu_baseline": cpu, "e2e": e2e, "clocks": clocks,
-            "gpu_launches": args.steps * L.pmp_solve_launch_count(C.byref(problem), C.byref(opts), n) *
-                            (len(pg.slices) if world > 1 else 1),
-            "gather": ({"chunks": len(pg.slices), "transport": pg.transport, "bytes_per_rank_per_step": int(y_dev.numel() * y_dev.element_size()),
-                        "overlap": ("none across steps" if args.no_step_overlap else
-                                    "gather of step s overlaps the integration of step s+1 (double-buffered); "
-                                    "all gathers complete inside the timed region")}
-                       if world > 1 else None),
+            "metric": "PMP trajectories/sec", "value": value, "unit": "trajectories/s", "n_gpus": world,
+            "steps": args.steps, "warmup": warm, "ms_per_step": main_run["ms_per_step"],
+            "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None, "dtype": args.dtype, "data": "synthetic",
+            "config": workload_config(args, n, world),
+            "rk_step_attempts_per_s": attempts_all * args.steps / total_s,
+            "mean_attempts_per_trajectory": attempts_all / (n * world),
+            "solve_ms_per_step": solve_s * 1e3,
+            "roofline": roof, "parity": parity, "cpu_baseline": cpu, "e2e": e2e, "clocks": clocks,
+            "gpu_launches": int(gpu_launches),
+            "gather": gather, "gather_check": gather_check, "strong": strong, "dense": dense_block,
         }
         print(json.dumps(line), flush=True)
     if world > 1:

@@ -34,6 +34,26 @@ def _worker(rank, world, port, n_local, q):
         full = torch.cat([p for p in pieces], dim=2)              # [world, NS, n_local]
         full = full.permute(1, 0, 2).reshape(14, n)               # contiguous sharding: column r*n_local + j
         res[(transport, chunks)] = bool(torch.equal(full, ref))
+    # wait=False across steps with skewed ranks (write-after-read on the p2p gather buffers): the result of step s
+    # is read AFTER step s+1 has been issued, by a reader that is slow on rank 0, while rank 1 races ahead into step s+2,
+    # whose pushes land in the buffers of step s.  The 'consumed' barrier of PipelinedGather.run must hold them back.
+    ys = [torch.as_tensor(flatquad_terminal(n, seed=11 + k), device=dev) for k in range(3)]
+    refs = [pu.solve_batch_soa(prob, opts, y.contiguous())["y_end"].clone() for y in ys]
+    locs = [sharding.take_shard(y, n, rank, world) for y in ys]
+    for transport in ("p2p", "nccl"):
+        pg = sharding.PipelinedGather(prob, opts, n_local, torch.float64, dev, chunks=1, transport=transport)
+        pa = pg.run(locs[0], wait=False)
+        pb = pg.run(locs[1], wait=False)
+        pg.wait()
+        if rank == 0:
+            torch.cuda._sleep(int(1.5e9))  # ~0.8 s: rank 0's reader of step 0 is late
+        got_a = torch.cat(pa, dim=2).clone()   # enqueued before run() of step 2 is called: must see step 0's records
+        pc = pg.run(locs[2], wait=False)       # step 2 reuses the buffer set of step 0
+        pg.wait()
+        got_b, got_c = torch.cat(pb, dim=2).clone(), torch.cat(pc, dim=2).clone()
+        torch.cuda.synchronize()
+        for tag, g, r in (("a", got_a, refs[0]), ("b", got_b, refs[1]), ("c", got_c, refs[2])):
+            res[(transport, "nowait", tag)] = bool(torch.equal(g.permute(1, 0, 2).reshape(14, n), r))
     q.put((rank, res))
     dist.destroy_process_group()
 
