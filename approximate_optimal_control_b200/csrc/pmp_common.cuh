@@ -17,6 +17,8 @@ template <class R> struct Math;
 // by the 1.5*2^23 magic-number trick (valid for |x| < ~1e5 rad; the pitch angle Phi stays within a
 // few turns), then the Cephes minimax polynomials on [-pi/4, pi/4] (~1 ulp, exact-in-the-limit
 // relative accuracy near 0, which the MUFU.SIN/COS intrinsics do not give).
+// (A reduction by pi -- one sign flip, no swap, one more term per polynomial: 5 fewer ALU-pipe instructions -- was
+//  measured in round 2 and made no difference: 1.190 vs 1.187 ms per 2^20 rollouts.)
 __device__ __forceinline__ void pmp_sincosf(float x, float* sn_out, float* cs_out) {
     const float magic = 12582912.0f;  // 1.5 * 2^23
     const float kf_biased = fmaf(x, 0.636619772367581f, magic);
@@ -46,6 +48,10 @@ template <> struct Math<float> {
     static __device__ __forceinline__ float abs(float x) { return fabsf(x); }
     static __device__ __forceinline__ float max(float a, float b) { return fmaxf(a, b); }
     static __device__ __forceinline__ float min(float a, float b) { return fminf(a, b); }
+    static __device__ __forceinline__ float sat(float x) { return __saturatef(x); }  // clip to [0, 1]; NaN -> 0
+    // register copy through the FMA pipe: x * one with `one` = 1.0 read from the parameter bank (exact for every x).  A MOV
+    // runs on the half-rate ALU pipe and costs two issue cycles, an FMUL one; the accept path copies 2 (2nx+1) registers.
+    static __device__ __forceinline__ float copy(float x, float one) { return x * one; }
     static __device__ __forceinline__ float sqrt(float x) { return sqrtf(x); }
     static __device__ __forceinline__ float rcp(float x) { return __frcp_rn(x); }
     static __device__ __forceinline__ float div(float a, float b) { return __fdiv_rn(a, b); }
@@ -116,6 +122,8 @@ template <> struct Math<double> {
     static __device__ __forceinline__ double abs(double x) { return fabs(x); }
     static __device__ __forceinline__ double max(double a, double b) { return fmax(a, b); }
     static __device__ __forceinline__ double min(double a, double b) { return fmin(a, b); }
+    static __device__ __forceinline__ double sat(double x) { return fmin(fmax(x, 0.0), 1.0); }
+    static __device__ __forceinline__ double copy(double x, double) { return x; }
     static __device__ __forceinline__ double sqrt(double x) { return ::sqrt(x); }
     static __device__ __forceinline__ double rcp(double x) { return 1.0 / x; }
     static __device__ __forceinline__ double div(double a, double b) { return a / b; }
@@ -158,6 +166,7 @@ template <class R> struct SolveOpts {
     R dir;          // +1 / -1
     R rtol, atol, dtmin, dtmax, safety, factormin, factormax, inv_order;
     R event_level;
+    R one;          // 1.0 (see Math<R>::copy)
     int max_steps, adaptive, force_dtmin, event, use_dtmin, use_dtmax;
     int refill_min;  // lanes of a warp that must be waiting before the retire + refill detour is taken
 };

@@ -878,9 +878,9 @@ solve_kernel(const typename Sys::Consts sc, const SolveOpts<R> o, const SolveIO<
                 bool bad = step_nonfinite;
 #pragma unroll
                 for (int q = 0; q < ND; q++) {
-                    y[q] = y1[q];
+                    y[q] = M::copy(y1[q], o.one);
                     if (!(TB::EMBEDDED)) bad = bad || (y1[q] != y1[q]);
-                    if (TB::FSAL) k[0][q] = k[S - 1][q];
+                    if (TB::FSAL) k[0][q] = M::copy(k[S - 1][q], o.one);
                 }
                 if constexpr (VXX) {
                     R np[4] = {R(0), R(0), R(0), R(0)};
@@ -935,6 +935,7 @@ template <class R, class TB> inline SolveOpts<R> make_solve_opts(const pmp_opts_
     s.safety = R(o.safety); s.factormin = R(o.factormin); s.factormax = R(o.factormax);
     s.inv_order = R(1.0 / order);
     s.event_level = R(o.event_level);
+    s.one = R(1);
     s.max_steps = o.max_steps; s.adaptive = o.adaptive; s.force_dtmin = o.force_dtmin; s.event = o.event;
     s.refill_min = (o.flags & PMP_FLAG_VXX) ? kRefillMinVxx : (sizeof(R) == 4 ? kRefillMin32 : kRefillMin64);
     if (nx <= 2) s.refill_min = 1;  // two-state systems: the detour is as cheap as an attempt (orbits: 0.33 ms at 1, 0.36 at 3)

@@ -65,6 +65,8 @@ template <class R> struct Flatquad {
         // = +-(h01*coordinate + H_u[other axis] + kM[k])
         R kN, kQ[4], kM[4];
         R kNo;  // -h01/h00: slope of an edge minimiser in the fixed coordinate
+        R w0, w1, kNow0, kNow1;                   // box widths hi-lo; kNo / width
+        alignas(2 * sizeof(R)) R pNw[2], pLw[2];  // (kN/w0, kN/w1), (-lo0/w0, -lo1/w1)
         // vxx branch (rhs_jac): d(u0+u1)/dH_u and d(u1-u0)/d(lam5) of the unconstrained minimiser, kN r/I
         R jMS, jD3, kN_rI;
         // the same constants as PAIRS for the packed (FFMA2) form of the KKT selection: the two edges that move along
@@ -109,6 +111,12 @@ template <class R> struct Flatquad {
         }
         c.kN = R(-1.0 / d);
         c.kNo = R(-o / d);
+        {
+            const double w0 = p.u_hi[0] - p.u_lo[0], w1 = p.u_hi[1] - p.u_lo[1];
+            c.w0 = R(w0); c.w1 = R(w1); c.kNow0 = R(-o / d / w0); c.kNow1 = R(-o / d / w1);
+            c.pNw[0] = R(-1.0 / d / w0); c.pNw[1] = R(-1.0 / d / w1);
+            c.pLw[0] = R(-p.u_lo[0] / w0); c.pLw[1] = R(-p.u_lo[1] / w1);
+        }
         c.jMS = R(-2.0 * (d - o) / det);
         c.jD3 = R(-2.0 * (r / I) * (d + o) / det);
         c.kN_rI = R(-(r / I) / d);
@@ -158,9 +166,12 @@ template <class R> struct Flatquad {
             // outwards, i.e. have the sign of (uu1 - b1) negated.  Inside the box b == uu and neither test fires.
             const R b0 = M::min(M::max(uu.x, c.lo0), c.hi0), b1 = M::min(M::max(uu.y, c.lo1), c.hi1);
             const bool viol0 = b0 != uu.x, viol1 = b1 != uu.y;
-            const V2 t = M::mul2(c.kN, M::mk2(Hu0, Hu1));                 // -Hu / h00
-            const R u0A = M::min(M::max(M::fma(c.kNo, b1, t.x), c.lo0), c.hi0);
-            const R u1B = M::min(M::max(M::fma(c.kNo, b0, t.y), c.lo1), c.hi1);
+            // clip(w, lo, hi) = lo + (hi-lo) sat((w-lo)/(hi-lo)): the saturation is a free modifier of the FMA that forms its
+            // argument (fp32), against two ALU-pipe min/max for the direct form; the reference writes its edge minimisers
+            // the same way (s = clip(., 0, 1), u = s a + (1-s) b, pontryagin_utils.py:73-75)
+            const V2 t = M::fma2v(M::mk2(c.pNw[0], c.pNw[1]), M::mk2(Hu0, Hu1), M::mk2(c.pLw[0], c.pLw[1]));  // (-Hu/h00 - lo)/w
+            const R u0A = M::fma(M::sat(M::fma(c.kNow0, b1, t.x)), c.w0, c.lo0);
+            const R u1B = M::fma(M::sat(M::fma(c.kNow1, b0, t.y)), c.w1, c.lo1);
             const R gA = M::fma(c.h00, b1, M::fma(c.h01, u0A, Hu1));      // dH/du1 at candidate A
             const bool okA = gA * (b1 - uu.y) >= R(0);
             const bool useA = viol1 && (okA || !viol0);
