@@ -6,6 +6,7 @@
 #include <vector>
 
 #include "../../include/b200pmp.h"
+#include "pmp_hostq.h"
 
 namespace pmp {
 #ifndef PMP_PLUGIN
@@ -33,9 +34,10 @@ int nn_value_batch(const pmp_problem_t& p, const pmp_nn_costate_t* nn, int dtype
                    void* vm, void* vs, cudaStream_t st);
 int solve_host(const pmp_problem_t& p, const pmp_opts_t& o, long long n, const void* x_f, const void* t_f, const void* v_f,
                const void* vx_f, void* x_end, void* t_end, void* v_end, void* vx_end, int32_t* n_accepted, int32_t* n_steps,
-               int32_t* result, int n_pieces);
+               int32_t* result, int n_pieces, const double* term_P, const double* term_xeq);
 int host_plan(long long n, int n_pieces, std::vector<long long>* bounds, long long* cs_max);
 int host_release();
+int host_probe_copy(void* dst, const void* src, long long bytes, int blocks, cudaStream_t st);
 int fma_peak(int dtype, int variant, int iters, void* scratch, double* flops_out, cudaStream_t st);
 int interp_batch(const pmp_problem_t& p, const pmp_opts_t& o, long long nq, const void* y0, const void* t1,
                  const void* target, void* y_out, int mode, cudaStream_t st);
@@ -122,6 +124,29 @@ int check_pair(const pmp_problem_t* p, const pmp_opts_t* o) {
 }
 int64_t vxx_rows(const pmp_problem_t* p, int32_t flags) { return (flags & PMP_FLAG_VXX) ? (int64_t)p->nx * p->nx : 0; }
 }  // namespace
+
+namespace pmp {
+#ifdef PMP_PLUGIN
+int solve_generated_hostq(const pmp_problem_t&, const pmp_opts_t&, long long, const HostQueueRaw&, cudaStream_t);
+#else
+int solve_flatquad_hostq(const pmp_problem_t&, const pmp_opts_t&, long long, const HostQueueRaw&, cudaStream_t);
+int solve_orbits_hostq(const pmp_problem_t&, const pmp_opts_t&, long long, const HostQueueRaw&, cudaStream_t);
+int solve_lqr_hostq(const pmp_problem_t&, const pmp_opts_t&, long long, const HostQueueRaw&, cudaStream_t);
+#endif
+int solve_hostq_dispatch(const pmp_problem_t& p, const pmp_opts_t& o, long long n, const HostQueueRaw& q, cudaStream_t st) {
+    if (o.indep != PMP_INDEP_TIME || o.save_dense || o.flags != 0) return -1000;
+#ifdef PMP_PLUGIN
+    return solve_generated_hostq(p, o, n, q, st);
+#else
+    switch (p.system_id) {
+        case PMP_SYS_FLATQUAD: return solve_flatquad_hostq(p, o, n, q, st);
+        case PMP_SYS_ORBITS: return solve_orbits_hostq(p, o, n, q, st);
+        case PMP_SYS_LQR_STATEPENALTY: return solve_lqr_hostq(p, o, n, q, st);
+    }
+    return -1000;
+#endif
+}
+}  // namespace pmp
 
 extern "C" {
 
@@ -227,20 +252,43 @@ int pmp_solve_host(const pmp_problem_t* p, const pmp_opts_t* o, int64_t n, const
     if (n == 0) return PMP_OK;
     if (!x_f || !v_f || !vx_f) return fail(PMP_ERR_BAD_ARG, "x_f / v_f / vx_f is NULL");
     if (pmp_device_count() <= 0) return fail(PMP_ERR_NO_DEVICE, "no CUDA device: libb200pmp has no CPU fallback");
-    int rc = pmp::solve_host(*p, *o, n, x_f, t_f, v_f, vx_f, x_end, t_end, v_end, vx_end, n_accepted, n_steps, result, n_pieces);
+    int rc = pmp::solve_host(*p, *o, n, x_f, t_f, v_f, vx_f, x_end, t_end, v_end, vx_end, n_accepted, n_steps, result, n_pieces,
+                             nullptr, nullptr);
     if (rc > 0) return cuda_fail(rc);
     return rc;  // < 0: recorded by pmp_solve_batch_cuda
+}
+
+int pmp_solve_host_lqr(const pmp_problem_t* p, const pmp_opts_t* o, int64_t n, const void* x_f, const void* t_f,
+                       const double* P_lqr, const double* x_eq, void* x_end, void* t_end, void* v_end, void* vx_end,
+                       int32_t* n_accepted, int32_t* n_steps, int32_t* result, int32_t n_pieces) {
+    if (int e = check_host(p, o, n, n_pieces)) return e;
+    if (n == 0) return PMP_OK;
+    if (!x_f || !P_lqr) return fail(PMP_ERR_BAD_ARG, "x_f / P_lqr is NULL");
+    if (p->nx > 16) return fail(PMP_ERR_UNSUPPORTED, "pmp_solve_host_lqr: nx <= 16");
+    if (pmp_device_count() <= 0) return fail(PMP_ERR_NO_DEVICE, "no CUDA device: libb200pmp has no CPU fallback");
+    int rc = pmp::solve_host(*p, *o, n, x_f, t_f, nullptr, nullptr, x_end, t_end, v_end, vx_end, n_accepted, n_steps, result, n_pieces,
+                             P_lqr, x_eq);
+    if (rc > 0) return cuda_fail(rc);
+    return rc;
 }
 
 int pmp_solve_host_plan(const pmp_problem_t* p, const pmp_opts_t* o, int64_t n, int32_t n_pieces, int32_t* kernels,
                         int32_t* copies) {
     if (int e = check_host(p, o, n, n_pieces)) return e;
     const int pieces = n > 0 ? pmp::host_plan(n, n_pieces, nullptr, nullptr) : 0;
-    if (kernels) *kernels = pieces * (2 + pmp_solve_launch_count(p, o, 1));  // pack + solve + unpack
+    // n >= 2^16 with default flags: ONE persistent integrator launch (no pack / prep / unpack kernels); else per piece
+    const bool persistent = n >= (1 << 16) && o->indep == PMP_INDEP_TIME && o->flags == 0 && pieces <= 32;
+    if (kernels) *kernels = persistent ? 1 : pieces * (2 + pmp_solve_launch_count(p, o, 1));  // pack + solve + unpack
     // leaves in; leaves + counters out (all outputs requested, t_f given; the counters travel as one packed word when
     // max_steps < 2^14)
     if (copies) *copies = pieces * (4 + (o->max_steps < (1 << 14) ? 5 : 7));
     return pieces;
+}
+
+int pmp_host_probe_copy(void* dst, const void* src, int64_t bytes, int32_t blocks, void* cuda_stream) {
+    if (!dst || !src || bytes < 0 || (bytes & 15) || blocks < 1) return fail(PMP_ERR_BAD_ARG, "probe copy: 16-byte multiples, blocks >= 1");
+    int rc = pmp::host_probe_copy(dst, src, bytes, blocks, (cudaStream_t)cuda_stream);
+    return rc ? cuda_fail(rc) : PMP_OK;
 }
 
 int pmp_host_release(void) {

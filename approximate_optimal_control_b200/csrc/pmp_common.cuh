@@ -212,4 +212,28 @@ template <class R> struct SolveIO {
     long long n;
 };
 
+// ---- pmp_solve_host's persistent launch (csrc/pmp_host.cu) -------------------------------------------------------
+// ONE launch of the integrator serves the whole host batch while the copy engines are still delivering it: the
+// kernel reads the reference's state-dict leaves (array of structs, as they lie in host memory) straight from the
+// whole-batch device arrays the host->device stream fills, may only start trajectories below *ready (an 8-byte
+// copy the same stream issues behind every piece), evaluates k1 = F(y_f) itself, writes the endpoints in the
+// state-dict layout and counts retired trajectories per piece, so that the device->host stream can wait for "piece
+// complete" with a stream memory operation.  No other kernel runs meanwhile: nothing the
+// integrator waits for needs an SM.
+template <class R> struct HostQueue {
+    const R *in_x, *in_vx, *in_t, *in_v;   // [n][nx], [n][nx], [n] or NULL (then t_fill), [n]
+    const R* term;                         // non-NULL: [nx*nx + nx] = P row-major, x_eq; then in_vx / in_v are unused and the
+                                           // terminal costate and value are formed here, vx_f = P (x_f - x_eq),
+                                           // v_f = 1/2 (x_f - x_eq)' vx_f, as levelsets.py:585-586 does inside its vmap
+    R *out_x, *out_vx, *out_t, *out_v;     // endpoints, same layouts; any may be NULL
+    uint32_t* out_pk;                      // accepted | attempts << 14 | result << 28, or NULL
+    int32_t *out_na, *out_ns, *out_res;    // (used when the counters do not fit the packed word)
+    const unsigned long long* ready;       // trajectories [0, *ready) have landed
+    unsigned int* done;                    // done[piece]: retired trajectories of piece [bounds[piece], bounds[piece+1])
+    unsigned int* abort;                   // != 0: the watchdog gave up waiting for *ready (host reports an error)
+    int n_pieces;
+    long long bounds[33];
+    R t_fill;
+};
+
 }  // namespace pmp

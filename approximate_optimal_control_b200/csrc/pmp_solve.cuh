@@ -30,6 +30,7 @@
 #include <type_traits>
 
 #include "pmp_common.cuh"
+#include "pmp_hostq.h"
 #include "pmp_systems.cuh"
 #include "pmp_tableau.cuh"
 
@@ -39,7 +40,13 @@ namespace pmp {
 #define PMP_KBLOCK 128
 #endif
 constexpr int kBlock = PMP_KBLOCK;  // threads per CTA
-constexpr int kChunk = 64;   // trajectory indices claimed per atomicAdd
+#ifndef PMP_KCHUNK
+#define PMP_KCHUNK 32
+#endif
+constexpr int kChunk = PMP_KCHUNK;   // trajectory indices claimed per atomicAdd (one per lane: with 64 a warp at the queue tail,
+                                     // or at the frontier of the host queue, sat on a second round of work while others idled:
+                                     // 2^20 rollouts 1.190 -> 1.166 ms, 2^17 0.244 -> 0.229 ms)
+constexpr long long kWatchdogCycles = 4000000000LL;  // HOSTIO: ~2 s without new input => give up (never hang the GPU)
 // lanes that must wait before a warp takes the retire + refill detour (measured on 2^20 flatquad trajectories:
 // fp32 1.41 ms at 1, 1.33 at 4, 1.38 at 8; fp64 4.09 / 4.03 at 3 / 4.27 at 8; vxx 5.49 / 4.90 at 6 / 5.11 at 12)
 constexpr int kRefillMin32 = 4, kRefillMin64 = 3;
@@ -441,14 +448,17 @@ __device__ __forceinline__ R error_sumsq(const R* he, const R* y, const R* y1, c
 }
 
 // ---- the integrator -----------------------------------------------------------------------------
-template <class Sys, class R, int METHOD, bool DENSE, bool VALUE, bool ULIT, int MINB, int VXX = 0>
+// HOSTIO: the persistent launch behind pmp_solve_host (HostQueue, pmp_common.cuh): inputs and endpoints in the state
+// dict's own layout, work released piece by piece by the host->device stream, k1 evaluated in the refill.
+template <class Sys, class R, int METHOD, bool DENSE, bool VALUE, bool ULIT, int MINB, int VXX = 0, bool HOSTIO = false>
 #ifdef PMP_MAXNREG  /* tuning builds: an explicit register cap instead of the residency hint */
 __global__ void __maxnreg__(PMP_MAXNREG)
 #else
 __global__ void __launch_bounds__((BlockOf<R, VXX>::value), MINB)
 #endif
 solve_kernel(const typename Sys::Consts sc, const SolveOpts<R> o, const SolveIO<R> io, const TabParams<R> tp,
-             const VTab<R, VXX> vt) {
+             const VTab<R, VXX> vt, const HostQueue<R> hq) {
+    static_assert(!HOSTIO || (!DENSE && !VXX && !VALUE), "the host queue serves time-parameterised endpoint solves");
     using M = Math<R>;
     using TB = Tab<METHOD>;
     constexpr int NX = Sys::NX, ND = 2 * NX + 1, NS = 2 * NX + 2, S = TB::S;
@@ -480,6 +490,8 @@ solve_kernel(const typename Sys::Consts sc, const SolveOpts<R> o, const SolveIO<
     // warp-local slice of the work queue (uniform across the warp)
     long long w_next = 0, w_end = 0;
     bool exhausted = false;
+    bool starved = false;       // HOSTIO: the next chunk of the queue has not been delivered yet
+    long long starve_t0 = 0;    // HOSTIO: start of the current wait (watchdog)
 
     // dense write-out staging (shared memory, one private region per warp)
     extern __shared__ __align__(16) unsigned char pmp_smem[];
@@ -540,7 +552,29 @@ solve_kernel(const typename Sys::Consts sc, const SolveOpts<R> o, const SolveIO<
             if (fin) {
                 // endpoint = last accepted state (== ys[num_accepted_steps], levelsets.py:1215)
                 const R clock = tprev * o.dir;  // t (time mode) or v (value mode)
+                if constexpr (HOSTIO) {
+                    // state-dict layout: a lane's x / vx row is NX contiguous reals
+                    if (hq.out_x) {
+#pragma unroll
+                        for (int q = 0; q < NX; q++) hq.out_x[idx * NX + q] = y[q];
+                    }
+                    if (hq.out_vx) {
+#pragma unroll
+                        for (int q = 0; q < NX; q++) hq.out_vx[idx * NX + q] = y[NX + q];
+                    }
+                    if (hq.out_t) hq.out_t[idx] = aux_fixed + (clock - clock0);
+                    if (hq.out_v) hq.out_v[idx] = y[AUX];
+                    if (hq.out_pk) hq.out_pk[idx] = (uint32_t)nacc | ((uint32_t)nsteps << 14) | ((uint32_t)result << 28);
+                    if (hq.out_na) hq.out_na[idx] = nacc;
+                    if (hq.out_ns) hq.out_ns[idx] = nsteps;
+                    if (hq.out_res) hq.out_res[idx] = result;
+                    __threadfence();  // the record is visible device-wide before the block counter says so
+                    int piece = 0;  // the piece whose range holds idx (bounds ascending, <= 32 pieces)
+                    for (int c = 1; c < hq.n_pieces; c++) piece += idx >= hq.bounds[c] ? 1 : 0;
+                    atomicAdd(hq.done + piece, 1u);
+                }
                 R* ye = io.y_end;
+                if constexpr (!HOSTIO) {
 #pragma unroll
                 for (int q = 0; q < NX; q++) ye[q * n + idx] = y[q];
 #pragma unroll
@@ -554,6 +588,7 @@ solve_kernel(const typename Sys::Consts sc, const SolveOpts<R> o, const SolveIO<
                 if (io.n_accepted) io.n_accepted[idx] = nacc;
                 if (io.n_steps) io.n_steps[idx] = nsteps;
                 if (io.result) io.result[idx] = result;
+                }
                 has_work = false;
                 ready_v = false; ready_s = false;  // DENSE: the retirement code writes the last group
             }
@@ -583,10 +618,38 @@ solve_kernel(const typename Sys::Consts sc, const SolveOpts<R> o, const SolveIO<
             // start trajectory i on this lane
             auto start_traj = [&](long long i) {
                 idx = i;
+                if constexpr (HOSTIO) {
+                    // L2 loads (ld.global.cg): a neighbour's earlier read may have pulled this 128-byte line into L1 when
+                    // the copy engine had not yet delivered this trajectory's part of it
+#pragma unroll
+                    for (int q = 0; q < NX; q++) y[q] = __ldcg(hq.in_x + idx * NX + q);
+                    if (hq.term) {  // LQR terminal set: lambda = P (x - x_eq), v = 1/2 (x - x_eq)' lambda
+                        R dx[NX], v2 = R(0);
+#pragma unroll
+                        for (int q = 0; q < NX; q++) dx[q] = y[q] - __ldg(hq.term + NX * NX + q);
+#pragma unroll
+                        for (int q = 0; q < NX; q++) {
+                            R acc = R(0);
+#pragma unroll
+                            for (int j = 0; j < NX; j++) acc = M::fma(__ldg(hq.term + q * NX + j), dx[j], acc);
+                            y[NX + q] = acc;
+                            v2 = M::fma(dx[q], acc, v2);
+                        }
+                        y[AUX] = R(0.5) * v2;
+                    } else {
+#pragma unroll
+                        for (int q = 0; q < NX; q++) y[NX + q] = __ldcg(hq.in_vx + idx * NX + q);
+                        y[AUX] = __ldcg(hq.in_v + idx);
+                    }
+                    clock0 = R(0);
+                    aux_fixed = hq.in_t ? __ldcg(hq.in_t + idx) : hq.t_fill;
+                    if (TB::FSAL) field<Sys, R, VALUE, ULIT ? 0 : 2>(sc, y, k[0]);  // what the prep kernel does for device batches
+                } else {
                 load_state<R, NX, VALUE>(io.y_f, n, idx, y, clock0, aux_fixed);
                 if (TB::FSAL) {
 #pragma unroll
                     for (int q = 0; q < ND; q++) k[0][q] = __ldg(io.k1 + q * n + idx);
+                }
                 }
                 // diffrax: t0, t1, dt0 are multiplied by the direction; tnext = min(t0+dt0, t1)
                 const R T0 = VALUE ? clock0 * o.dir : o.T0;
@@ -627,8 +690,36 @@ solve_kernel(const typename Sys::Consts sc, const SolveOpts<R> o, const SolveIO<
             while (want && !exhausted) {
                 if (w_next >= w_end) {
                     unsigned long long base = 0;
+                    if constexpr (HOSTIO) {
+                        // claim a chunk only if its inputs have landed; otherwise go on integrating (or, with nothing to
+                        // integrate, sleep below) and ask again after the next attempt
+                        unsigned long long rdy = 0, cnt = 0;
+                        if (lane == 0) {
+                            rdy = *(volatile const unsigned long long*)hq.ready;
+                            cnt = *(volatile unsigned long long*)io.counter;
+                        }
+                        rdy = __shfl_sync(FULL, rdy, 0);
+                        cnt = __shfl_sync(FULL, cnt, 0);
+                        const unsigned long long need = cnt + kChunk < (unsigned long long)n ? cnt + kChunk : (unsigned long long)n;
+                        if (cnt < (unsigned long long)n && rdy < need) { starved = true; break; }
+                    }
                     if (lane == 0) base = atomicAdd(io.counter, (unsigned long long)kChunk);
                     base = __shfl_sync(FULL, base, 0);
+                    if constexpr (HOSTIO) {
+                        // several warps may pass the check above at once and one of them lands beyond the frontier: it
+                        // waits for its chunk (rare, bounded by the watchdog)
+                        const unsigned long long need = base + kChunk < (unsigned long long)n ? base + kChunk : (unsigned long long)n;
+                        if (base < (unsigned long long)n) {
+                            const long long t0 = clock64();
+                            while (*(volatile const unsigned long long*)hq.ready < need) {
+                                __nanosleep(200);
+                                if (clock64() - t0 > kWatchdogCycles || *(volatile unsigned int*)hq.abort) {
+                                    *hq.abort = 1u;
+                                    return;
+                                }
+                            }
+                        }
+                    }
                     w_next = (long long)base;
                     w_end = w_next + kChunk < n ? w_next + kChunk : n;
                     if (w_next >= n) { exhausted = true; break; }
@@ -678,7 +769,20 @@ solve_kernel(const typename Sys::Consts sc, const SolveOpts<R> o, const SolveIO<
                 if (pad_mask) bulk_commit();
             }
         }
-        if (!__any_sync(FULL, has_work)) break;
+        if (!__any_sync(FULL, has_work)) {
+            if (!HOSTIO || !starved) break;
+            // nothing to integrate and the next chunk has not landed yet: wait for the host->device stream
+            __nanosleep(500);
+            if (starve_t0 == 0) starve_t0 = clock64();
+            if (clock64() - starve_t0 > kWatchdogCycles || *(volatile unsigned int*)hq.abort) {
+                *hq.abort = 1u;
+                return;
+            }
+            starved = false;
+            continue;
+        }
+        starved = false;
+        starve_t0 = 0;
         const bool live = has_work && !finished;
         if (DENSE) {
             // write the groups completed by the previous attempt or by the refill above.  This is the
@@ -1002,8 +1106,54 @@ int launch_one(const pmp_problem_t& p, const pmp_opts_t& o, long long n, const v
         reset_counter_kernel<<<1, 1, 0, st>>>(io.counter);
     }
     const SolveOpts<R> so = make_solve_opts<R, TB>(o, TB::ORDER, Sys::NX);
-    kern<<<grid, BLK, smem, st>>>(sc, so, io, TabParams<R>::template make<TB>(), VTab<R, VXX>::template make<TB>());
+    kern<<<grid, BLK, smem, st>>>(sc, so, io, TabParams<R>::template make<TB>(), VTab<R, VXX>::template make<TB>(), HostQueue<R>());
     return (int)cudaGetLastError();
+}
+
+// ---- the persistent launch of pmp_solve_host (HOSTIO) ----------------------------------------------------------------
+template <class Sys, class R, int METHOD, int MINB>
+int launch_hostq_one(const pmp_problem_t& p, const pmp_opts_t& o, long long n, const HostQueueRaw& q, cudaStream_t st) {
+    using TB = Tab<METHOD>;
+    auto kern = solve_kernel<Sys, R, METHOD, false, false, false, MINB, 0, true>;
+    int dev = 0, sms = 0, occ = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) return (int)e;
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, kBlock, 0);
+    if (e != cudaSuccess) return (int)e;
+    if (occ < 1) occ = 1;
+    const long long need = (n + kBlock - 1) / kBlock, cap = (long long)sms * occ;
+    const int grid = (int)(need < cap ? need : cap);
+    SolveIO<R> io = {};
+    io.counter = q.counter;
+    io.n = n;
+    HostQueue<R> hq;
+    hq.in_x = (const R*)q.in_x; hq.in_vx = (const R*)q.in_vx; hq.in_t = (const R*)q.in_t; hq.in_v = (const R*)q.in_v;
+    hq.term = (const R*)q.term;
+    hq.out_x = (R*)q.out_x; hq.out_vx = (R*)q.out_vx; hq.out_t = (R*)q.out_t; hq.out_v = (R*)q.out_v;
+    hq.out_pk = q.out_pk; hq.out_na = q.out_na; hq.out_ns = q.out_ns; hq.out_res = q.out_res;
+    hq.ready = q.ready; hq.done = q.done; hq.abort = q.abort;
+    hq.n_pieces = q.n_pieces;
+    for (int c = 0; c <= q.n_pieces; c++) hq.bounds[c] = q.bounds[c];
+    hq.t_fill = R(o.t0);
+    const SolveOpts<R> so = make_solve_opts<R, TB>(o, TB::ORDER, Sys::NX);
+    kern<<<grid, kBlock, 0, st>>>(Sys::make(p), so, io, TabParams<R>::template make<TB>(), VTab<R, 0>::template make<TB>(), hq);
+    return (int)cudaGetLastError();
+}
+
+// -1000: this (method, dtype) has no host-queue instantiation (the caller falls back to per-piece launches)
+template <template <class> class SysT, int MINB32, int MINB64>
+int launch_hostq(const pmp_problem_t& p, const pmp_opts_t& o, long long n, const HostQueueRaw& q, cudaStream_t st) {
+#define PMP_HQ(R, MINB)                                                                                                      \
+    do {                                                                                                                     \
+        if (o.method == PMP_METHOD_RK4) return launch_hostq_one<SysT<R>, R, PMP_METHOD_RK4, MINB>(p, o, n, q, st);           \
+        if (o.method == PMP_METHOD_TSIT5) return launch_hostq_one<SysT<R>, R, PMP_METHOD_TSIT5, MINB>(p, o, n, q, st);       \
+        if (o.method == PMP_METHOD_DOPRI5) return launch_hostq_one<SysT<R>, R, PMP_METHOD_DOPRI5, MINB>(p, o, n, q, st);     \
+    } while (0)
+    if (o.dtype == PMP_F32) PMP_HQ(float, MINB32);
+    if (o.dtype == PMP_F64) PMP_HQ(double, MINB64);
+#undef PMP_HQ
+    return -1000;
 }
 
 // PMP_FLAG_VXX instantiations (time-parameterised, KKT-form u*): a compile unit of their own

@@ -8,4 +8,7 @@ int solve_flatquad(const pmp_problem_t& p, const pmp_opts_t& o, long long n, con
 #endif
     return launch_solve<Flatquad, PMP_MINB32, 1>(p, o, n, y_f, y_end, dense, a, s, r, ws, st);
 }
+int solve_flatquad_hostq(const pmp_problem_t& p, const pmp_opts_t& o, long long n, const HostQueueRaw& q, cudaStream_t st) {
+    return launch_hostq<Flatquad, PMP_MINB32, 1>(p, o, n, q, st);
+}
 }  // namespace pmp

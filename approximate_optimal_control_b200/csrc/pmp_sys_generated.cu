@@ -14,4 +14,7 @@ int solve_generated(const pmp_problem_t& p, const pmp_opts_t& o, long long n, co
                     const pmp_dense_t* dense, int32_t* a, int32_t* s, int32_t* r, void* ws, cudaStream_t st) {
     return launch_solve<Generated, PMP_GEN_MINB32, PMP_GEN_MINB64>(p, o, n, y_f, y_end, dense, a, s, r, ws, st);
 }
+int solve_generated_hostq(const pmp_problem_t& p, const pmp_opts_t& o, long long n, const HostQueueRaw& q, cudaStream_t st) {
+    return launch_hostq<Generated, PMP_GEN_MINB32, PMP_GEN_MINB64>(p, o, n, q, st);
+}
 }  // namespace pmp

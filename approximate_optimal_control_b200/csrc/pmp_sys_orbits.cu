@@ -5,4 +5,7 @@ int solve_orbits(const pmp_problem_t& p, const pmp_opts_t& o, long long n, const
                  const pmp_dense_t* dense, int32_t* a, int32_t* s, int32_t* r, void* ws, cudaStream_t st) {
     return launch_solve<Orbits, 4, 3>(p, o, n, y_f, y_end, dense, a, s, r, ws, st);
 }
+int solve_orbits_hostq(const pmp_problem_t& p, const pmp_opts_t& o, long long n, const HostQueueRaw& q, cudaStream_t st) {
+    return launch_hostq<Orbits, 4, 3>(p, o, n, q, st);
+}
 }  // namespace pmp

@@ -2,6 +2,7 @@
 levelsets.testbed (/root/reference/levelsets.py): they consume the dense `Solution` the backward
 solve returns and would otherwise round-trip ~8 GB of saved nodes through the host.
 
+    define_solve_backward_lqr(problem_params, algo_params, P)   levelsets.py:576-601  (the vmapped caller of the path)
     select_train_pts(value_interval, sols[, vxx_max_norm])      levelsets.py:667-709
     find_min_l(ys, v_lower, v_upper, problem_params)            levelsets.py:604-628
     forward_sim_lqr(problem_params, algo_params, P_lqr)(x0)     levelsets.py:818-836
@@ -15,6 +16,7 @@ from __future__ import annotations
 
 import ctypes as C
 
+import numpy as np
 import torch
 
 from . import _capi, systems
@@ -69,6 +71,47 @@ def find_min_l(ys: dict, v_lower, v_upper, problem_params: dict):
     if not bool(inside.any()):
         return torch.tensor(float("nan"), dtype=all_ls.dtype, device=all_ls.device)
     return all_ls[inside].min()
+
+
+def define_solve_backward_lqr(problem_params: dict, algo_params: dict, P_lqr):
+    """levelsets.py:576-601: `solve_backward_lqr(x_f, algo_params)` -- the function the reference vmaps over its terminal
+    samples, `sols_orig = jax.vmap(solve_backward_lqr, in_axes=(0, None))(xfs, algo_params)`.  It builds the terminal state
+    from x_f alone, v_f = 1/2 x_f' P_lqr x_f, vx_f = P_lqr x_f, t = 0 (:585-592, deviations from x_eq), and solves backward.
+
+    Returns solve_backward_lqr(xfs): xfs (N, nx) [or (nx,)] -> Solution.  Host xfs (numpy / CPU tensor) of >= 2^16 samples
+    with algo_params['pontryagin_solver_save_steps'] False: only xfs crosses the host link (pmp_solve_host_lqr forms v_f and
+    vx_f on the device) and the endpoints come back in pinned host tensors.  Otherwise the terminal state is formed with
+    torch on the device and handed to define_backward_solver's solve_backward (dense Solution)."""
+    problem = systems.to_c_problem(problem_params)
+    nx = problem.nx
+    solve_backward, _ = pu.define_backward_solver(problem_params, algo_params)
+    x_eq = problem_params.get("x_eq")
+
+    def solve_backward_lqr(x_f, algo_params_=None):
+        ap = algo_params if algo_params_ is None else algo_params_
+        save_steps = bool(ap.get("pontryagin_solver_save_steps", True))
+        with_vxx = bool(ap.get("pontryagin_solver_vxx", False))
+        dev = pu._device(x_f)
+        dtype = pu._infer_dtype(ap, x_f)
+        if pu._host_leaf(x_f) and np.ndim(x_f) == 2 and not save_steps and not with_vxx and np.shape(x_f)[0] >= (1 << 16):
+            T = float(ap["pontryagin_solver_T"])
+            method = ap.get("pontryagin_solver_method", pu._DEFAULTS["method"])
+            adaptive = bool(ap.get("pontryagin_solver_adaptive", True)) and str(method).lower() != "rk4"
+            opts = pu._solver_opts(ap, dtype, t0=0.0, t1=-T, dt0=-abs(float(ap.get("pontryagin_solver_dt0", pu._DEFAULTS["dt0"]))),
+                                   adaptive=int(adaptive), save_dense=0)
+            sol = pu._solve_host_lqr(problem, opts, nx, x_f, P_lqr, x_eq, dtype, dev, int(ap.get("pontryagin_solver_host_chunks", 0)))
+            pu.raise_if_failed(sol.result, ap)
+            return sol
+        x = pu._as_tensor(x_f, dtype, dev)
+        Pt = pu._as_tensor(P_lqr, dtype, dev)
+        dx = x if x_eq is None else x - pu._as_tensor(x_eq, dtype, dev)
+        vx = dx @ Pt.T
+        state_f = {"x": x, "t": torch.zeros(x.shape[:-1], dtype=dtype, device=dev), "v": 0.5 * (dx * vx).sum(-1), "vx": vx}
+        if with_vxx:
+            state_f["vxx"] = Pt
+        return solve_backward(state_f)
+
+    return solve_backward_lqr
 
 
 def _forward_sim(problem_params, algo_params, *, P=None, nn=None, event=None, level=0.0):

@@ -294,6 +294,30 @@ def _host_leaf(a) -> bool:
     return isinstance(a, np.ndarray) or (isinstance(a, torch.Tensor) and not a.is_cuda)
 
 
+def _solve_host_lqr(problem, opts, nx, x_f, P_lqr, x_eq, dtype, dev, n_pieces=0):
+    """Host terminal samples x_f (n, nx) -> endpoints in pinned host tensors through pmp_solve_host_lqr: only x_f crosses the
+    link, vx_f = P (x_f - x_eq) and v_f = 1/2 (x_f - x_eq)' vx_f are formed on the device (levelsets.py:585-586)."""
+    x = (x_f if isinstance(x_f, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(x_f))).to(dtype).contiguous()
+    n = x.shape[0]
+    if x.shape != (n, nx):
+        raise ValueError(f"x_f must be [n, {nx}]")
+    Ph = np.ascontiguousarray(np.asarray(P_lqr.detach().cpu() if isinstance(P_lqr, torch.Tensor) else P_lqr, dtype=np.float64).reshape(nx, nx))
+    xe = None if x_eq is None else np.ascontiguousarray(np.asarray(x_eq, dtype=np.float64).reshape(nx))
+    pin = lambda *shape, dt=dtype: torch.empty(shape, dtype=dt, pin_memory=True)
+    ho = dict(x=pin(n, nx), t=pin(n), v=pin(n), vx=pin(n, nx), n_accepted=pin(n, dt=torch.int32), n_steps=pin(n, dt=torch.int32),
+              result=pin(n, dt=torch.int32))
+    L = _capi.lib_of(problem)
+    with torch.cuda.device(dev):
+        _capi.check(L.pmp_solve_host_lqr(C.byref(problem), C.byref(opts), n, x.data_ptr(), None, Ph.ctypes.data,
+                                         None if xe is None else xe.ctypes.data, ho["x"].data_ptr(), ho["t"].data_ptr(),
+                                         ho["v"].data_ptr(), ho["vx"].data_ptr(), ho["n_accepted"].data_ptr(),
+                                         ho["n_steps"].data_ptr(), ho["result"].data_ptr(), int(n_pieces)), L)
+    stats = {"num_steps": ho["n_steps"], "num_accepted_steps": ho["n_accepted"],
+             "num_rejected_steps": ho["n_steps"] - ho["n_accepted"]}
+    return Solution(t0=opts.t0, t1=opts.t1, ts=None, ys=None, y_end={k: ho[k] for k in ("x", "t", "v", "vx")}, stats=stats,
+                    result=ho["result"], batched=True)
+
+
 def _solve_host_pipelined(problem, opts, nx, y_f, dtype, dev, n_pieces=0):
     """solve_backward for HOST inputs (the reference's habitat: everything lives in host memory): one call of
     pmp_solve_host (csrc/pmp_host.cu), which cuts the batch into pieces and overlaps the host->device copy, the

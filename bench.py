@@ -31,8 +31,9 @@ JSON keys beyond the base contract:
                 tol 1e-12), next to the fp32 oracle's accuracy against the same truth, in units of the solver tolerance.
   cpu_baseline  the CPU oracle (kind "port": a C++ restatement of the reference; jax/diffrax cannot be installed here) on
                 all host threads, on a bounded sample of the same workload; plus one-core and fp64 figures.
-  e2e           the same metric through the public API (define_backward_solver -> solve_backward) from pinned HOST
-                buffers, host->device and device->host copies inside the timed region.
+  e2e           the same metric through the reference's own call of the path, sols = vmap(solve_backward_lqr)(xfs)
+                (levelsets.py:576-601; here levelsets.define_solve_backward_lqr): pinned HOST terminal samples in, endpoints
+                in pinned host memory out, host->device and device->host copies inside the timed region.
   gather_check  N > 1: rank 0 re-solves every rank's shard in one launch and compares it BIT FOR BIT with the slice
                 that rank pushed into rank 0's gathered dataset.
 """
@@ -463,30 +464,34 @@ def main():
     # ---- e2e: public API, host buffers ---------------------------------------------------------------
     e2e = None
     if not args.no_e2e:
-        solve_backward, _ = pu.define_backward_solver(pp, dict(ap, pontryagin_solver_method=args.method,
-                                                               pontryagin_solver_save_steps=dense,
-                                                               dtype="float32" if args.dtype == "f32" else "float64",
-                                                               **({"pontryagin_solver_dt0": 1 / 32} if args.method == "rk4" else {})))
-        host_in = {k: torch.as_tensor(v).pin_memory() for k, v in st_np.items()}
+        from approximate_optimal_control_b200 import levelsets
+        ap_e = dict(ap, pontryagin_solver_method=args.method, pontryagin_solver_save_steps=dense,
+                    dtype="float32" if args.dtype == "f32" else "float64",
+                    **({"pontryagin_solver_dt0": 1 / 32} if args.method == "rk4" else {}))
+        _, P_lqr = pu.get_terminal_lqr(pp)
+        # the reference's own call of the path: sols = jax.vmap(solve_backward_lqr, in_axes=(0, None))(xfs, algo_params)
+        # (levelsets.py:576-601): host terminal samples xfs in; solve_backward_lqr builds v_f = 1/2 x'Px, vx_f = Px, t = 0
+        solve_backward_lqr = levelsets.define_solve_backward_lqr(pp, ap_e, P_lqr)
+        solve_backward, _ = pu.define_backward_solver(pp, ap_e)
+        host_x = torch.as_tensor(st_np["x"]).pin_memory()
         host_out = {k: torch.empty(v.shape, dtype=tdt).pin_memory() for k, v in st_np.items()}
-        h2d = sum(v.numel() * v.element_size() for v in host_in.values())
+        h2d = host_x.numel() * host_x.element_size()
         d2h = sum(v.numel() * v.element_size() for v in host_out.values())
         if not dense:
             d2h += n * 4  # num_accepted_steps, num_steps, result come back with the endpoints, one packed word each
 
         def e2e_step():
             if dense:  # dense solutions stay on the device (8 GB per step); only the endpoints travel back
-                dev_in = {k: v.to(dev, non_blocking=True) for k, v in host_in.items()}
-                ye = solve_backward(dev_in).y_end
+                ye = solve_backward_lqr(host_x.to(dev, non_blocking=True)).y_end
                 for k in host_out:
                     host_out[k].copy_(ye[k], non_blocking=True)
                 torch.cuda.synchronize()
                 return
-            # host in -> host out: the public call with pinned host tensors goes to pmp_solve_host (csrc/pmp_host.cu),
-            # which cuts the batch into pieces and overlaps the copies of neighbouring pieces with the integration; the
-            # endpoints and per-trajectory counters come back in pinned host memory
-            sol = solve_backward(host_in)
-            assert not sol.y_end["x"].is_cuda and sol.y_end["x"].shape == host_in["x"].shape
+            # host in -> host out: pinned xfs goes to pmp_solve_host_lqr (csrc/pmp_host.cu): ONE persistent launch of the
+            # integrator consumes the pieces as the copy engine delivers them and the endpoints + counters of every finished
+            # piece are copied back to pinned host memory while later pieces are still being integrated
+            sol = solve_backward_lqr(host_x)
+            assert not sol.y_end["x"].is_cuda and sol.y_end["x"].shape == host_x.shape
 
         for _ in range(3):
             e2e_step()
@@ -498,15 +503,17 @@ def main():
         e_s = reduce_max(time.perf_counter() - t0)
         if not dense:
             k, c = C.c_int(), C.c_int()
-            pcs = L.pmp_solve_host_plan(C.byref(problem), C.byref(opts), n, 0, C.byref(k), C.byref(c)) if hasattr(L, "pmp_solve_host_plan") else 0
+            pcs = L.pmp_solve_host_plan(C.byref(problem), C.byref(opts), n, 0, C.byref(k), C.byref(c))
             gpu_launches += (args.steps + 3) * (k.value if pcs > 0 else 0)
         e2e = {"value": n * world * args.steps / e_s, "unit": "trajectories/s",
                "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                "gather": "none: every rank returns its own shard's endpoints to its host; the NVLink gather is part of `value` only" if world > 1 else None,
-               "api": "pontryagin_utils.define_backward_solver(...)[0](state dict of pinned host tensors) -> endpoints in pinned "
-                      "host tensors through the C entry pmp_solve_host (host pointers), which pipelines host->device copy, integration "
-                      "and device->host copy over pieces on its own streams"
-                      if not dense else "define_backward_solver(...)[0](device state dict) after an explicit host->device copy; "
+               "api": "levelsets.define_solve_backward_lqr(...)(xfs): the reference's vmapped caller of the path (levelsets.py:576-601), "
+                      "pinned host terminal samples xfs -> endpoints (x, t, v, vx) + counters in pinned host tensors through the C "
+                      "entry pmp_solve_host_lqr (host pointers): one persistent integrator launch fed piece by piece by the "
+                      "host->device stream, device->host copies of finished pieces under the integration of later ones; the "
+                      "terminal v_f = 1/2 x'Px, vx_f = Px are formed on the device as the reference's vmap does"
+                      if not dense else "define_solve_backward_lqr(...)(xfs on the device after an explicit host->device copy); "
                       "endpoints copied back to pinned host memory, dense nodes stay on the device"}
 
     # clocks: the K-step region lasts tens of ms, shorter than nvidia-smi's sampling period, so the

@@ -207,15 +207,29 @@ int pmp_solve_batch_cuda(const pmp_problem_t *problem, const pmp_opts_t *opts, i
  * staging (~(8nx+7) reals per trajectory of three pieces) is kept between calls; pmp_host_release() frees it.
  * The three counters cross the link as one packed word per trajectory (max_steps < 2^14) and are unfolded by the
  * calling thread while later pieces are in flight.  Concurrent calls on one device are serialised.  Endpoints only: save_dense and PMP_FLAG_VXX are refused.
+ * Batches of >= 2^16 trajectories (time-parameterised, default flags) run as ONE persistent launch of the integrator that
+ * consumes the pieces as the copy engine delivers them (csrc/pmp_host.cu); smaller ones as one launch per piece.
  * Results are bit-identical to pmp_solve_batch_cuda on the same states. */
 int pmp_solve_host(const pmp_problem_t *problem, const pmp_opts_t *opts, int64_t n,
                    const void *x_f, const void *t_f, const void *v_f, const void *vx_f,
                    void *x_end, void *t_end, void *v_end, void *vx_end,
                    int32_t *n_accepted, int32_t *n_steps, int32_t *result, int32_t n_pieces);
+/* The same with the terminal set of levelsets.py:580-601 (`solve_backward_lqr`, the function the reference vmaps over its
+ * terminal samples `xfs`): only x_f [n][nx] crosses the link, the terminal costate and value are formed on the device,
+ * vx_f = P_lqr (x_f - x_eq), v_f = 1/2 (x_f - x_eq)' vx_f, in the solve's precision (as jax does inside the vmap).
+ * P_lqr [nx][nx] row-major and x_eq [nx] (NULL = 0) are HOST doubles; t_f as in pmp_solve_host (NULL: opts->t0). */
+int pmp_solve_host_lqr(const pmp_problem_t *problem, const pmp_opts_t *opts, int64_t n,
+                       const void *x_f, const void *t_f, const double *P_lqr, const double *x_eq,
+                       void *x_end, void *t_end, void *v_end, void *vx_end,
+                       int32_t *n_accepted, int32_t *n_steps, int32_t *result, int32_t n_pieces);
 /* kernels + copies one pmp_solve_host call enqueues: *kernels, *copies (bench bookkeeping); returns the piece count */
 int pmp_solve_host_plan(const pmp_problem_t *problem, const pmp_opts_t *opts, int64_t n, int32_t n_pieces,
                         int32_t *kernels, int32_t *copies);
 int pmp_host_release(void);
+/* Diagnostics: a plain copy kernel (16 bytes per thread and iteration, `blocks` CTAs of 256) between two unified-address
+ * pointers; with a pinned host pointer on one side it measures what SM loads / stores move over the host link, next to
+ * the copy engines (scripts/pcie_probe.py).  bytes must be a multiple of 16.  Asynchronous on cuda_stream. */
+int pmp_host_probe_copy(void *dst, const void *src, int64_t bytes, int32_t blocks, void *cuda_stream);
 
 /* number of kernels one pmp_solve_batch_cuda call launches with these options (bench bookkeeping) */
 int pmp_solve_launch_count(const pmp_problem_t *problem, const pmp_opts_t *opts, int64_t n);

@@ -639,6 +639,49 @@ def test_solve_host_c_abi_bit_identical_to_device_solve(name, dtype, n, pieces, 
     assert L.pmp_host_release() == 0
 
 
+def test_solve_backward_lqr_only_x_crosses_the_link():
+    """levelsets.define_solve_backward_lqr (levelsets.py:576-601, the function the reference vmaps over xfs): host xfs in,
+    endpoints in pinned host memory through pmp_solve_host_lqr, which forms v_f = 1/2 x'Px, vx_f = Px on the device.
+    (a) persistent launch == per-piece launches, bit for bit; (b) == the state-dict path on a terminal state built with the
+    same arithmetic, within the fp32 bar of a short horizon; (c) small batches / dense output take the device path."""
+    import os
+    import torch
+    from approximate_optimal_control_b200 import levelsets, pontryagin_utils as pu, systems, terminal
+    pp = systems.flatquad_problem_params()
+    ap = dict(systems.flatquad_algo_params(), pontryagin_solver_save_steps=False, pontryagin_solver_T=0.5, dtype="float32")
+    P = flatquad_P_()
+    n = (1 << 16) + 777
+    xf = terminal.sample_terminal_states(P, pp["V_f"], n, seed=9, dtype=np.float32)["x"]
+    f = levelsets.define_solve_backward_lqr(pp, ap, P)
+    a = f(torch.as_tensor(xf).pin_memory())
+    assert not a.y_end["x"].is_cuda and a.y_end["x"].shape == (n, 6)
+    os.environ["B200PMP_HOST_PER_PIECE"] = "1"
+    try:
+        b = f(xf)
+    finally:
+        del os.environ["B200PMP_HOST_PER_PIECE"]
+    for k in ("x", "t", "v", "vx"):
+        assert torch.equal(a.y_end[k], b.y_end[k]), k
+    assert torch.equal(a.stats["num_steps"], b.stats["num_steps"]) and torch.equal(a.result, b.result)
+    # (b) the state-dict path from a float64-built terminal state: same trajectories up to fp32 rounding of v_f, vx_f
+    x64 = xf.astype(np.float64)
+    st = {"x": xf, "t": np.zeros(n, np.float32), "v": (0.5 * np.einsum("ni,ij,nj->n", x64, P, x64)).astype(np.float32),
+          "vx": (x64 @ P.T).astype(np.float32)}
+    ref = pu.define_backward_solver(pp, ap)[0]({k: torch.as_tensor(v, device="cuda") for k, v in st.items()})
+    tol = 1e-5
+    for k in ("x", "v", "vx"):
+        r = ref.y_end[k].cpu().double().numpy()
+        e = np.abs(a.y_end[k].double().numpy() - r) / (tol + tol * np.abs(r))
+        assert e.max() <= 10.0, (k, e.max())
+    assert torch.allclose(a.y_end["t"], torch.full((n,), -0.5))
+    # (c) a small batch with dense output: terminal state formed with torch on the device, a dense Solution comes back
+    small = levelsets.define_solve_backward_lqr(pp, dict(ap, pontryagin_solver_save_steps=True), P)(xf[:300])
+    assert small.ys["x"].is_cuda and small.ys["x"].shape == (300, 129, 6)
+    assert np.allclose(small.ys["v"][:, 0].cpu().numpy(), st["v"][:300], rtol=1e-5)
+    e = np.abs(small.y_end["x"].cpu().double().numpy() - a.y_end["x"][:300].double().numpy())
+    assert e.max() <= 10 * (tol + tol * np.abs(a.y_end["x"][:300].double().numpy())).max()
+
+
 def flatquad_P_():
     from common import flatquad_P
     return flatquad_P()
