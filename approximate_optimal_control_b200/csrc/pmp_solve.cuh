@@ -491,6 +491,7 @@ solve_kernel(const typename Sys::Consts sc, const SolveOpts<R> o, const SolveIO<
     long long w_next = 0, w_end = 0;
     bool exhausted = false;
     bool starved = false;       // HOSTIO: the next chunk of the queue has not been delivered yet
+    bool chunk_ok = !HOSTIO;    // HOSTIO: the inputs of the chunk [w_next, w_end) this warp owns have landed
     long long starve_t0 = 0;    // HOSTIO: start of the current wait (watchdog)
 
     // dense write-out staging (shared memory, one private region per warp)
@@ -705,24 +706,10 @@ solve_kernel(const typename Sys::Consts sc, const SolveOpts<R> o, const SolveIO<
                     }
                     if (lane == 0) base = atomicAdd(io.counter, (unsigned long long)kChunk);
                     base = __shfl_sync(FULL, base, 0);
-                    if constexpr (HOSTIO) {
-                        // several warps may pass the check above at once and one of them lands beyond the frontier: it
-                        // waits for its chunk (rare, bounded by the watchdog)
-                        const unsigned long long need = base + kChunk < (unsigned long long)n ? base + kChunk : (unsigned long long)n;
-                        if (base < (unsigned long long)n) {
-                            const long long t0 = clock64();
-                            while (*(volatile const unsigned long long*)hq.ready < need) {
-                                __nanosleep(200);
-                                if (clock64() - t0 > kWatchdogCycles || *(volatile unsigned int*)hq.abort) {
-                                    *hq.abort = 1u;
-                                    return;
-                                }
-                            }
-                        }
-                    }
                     w_next = (long long)base;
                     w_end = w_next + kChunk < n ? w_next + kChunk : n;
                     if (w_next >= n) { exhausted = true; break; }
+                    chunk_ok = !HOSTIO;
                     if (DENSE) {
                         // the chunk's terminal states and k1 rows are needed over the next ~50 attempts: pull them
                         // into L2 now (the refill's loads otherwise miss to DRAM behind the padding's write traffic)
@@ -733,6 +720,19 @@ solve_kernel(const typename Sys::Consts sc, const SolveOpts<R> o, const SolveIO<
                             if (w_next + part * (long long)(128 / sizeof(R)) < n)
                                 asm volatile("prefetch.global.L2::evict_last [%0];" ::"l"(a + w_next + part * (128 / sizeof(R))));
                         }
+                    }
+                }
+                if constexpr (HOSTIO) {
+                    // Several warps can pass the frontier check at once and one of them then owns a chunk that has not
+                    // landed yet.  It keeps the claim but starts nothing from it until it has (it must NOT spin here: its
+                    // live lanes may belong to the piece the host is waiting for before it sends the next one -- pageable
+                    // output buffers make the host's device->host copies blocking).
+                    if (!chunk_ok) {
+                        unsigned long long rdy = 0;
+                        if (lane == 0) rdy = *(volatile const unsigned long long*)hq.ready;
+                        rdy = __shfl_sync(FULL, rdy, 0);
+                        if (rdy < (unsigned long long)w_end) { starved = true; break; }
+                        chunk_ok = true;
                     }
                 }
                 const int avail = (int)(w_end - w_next);
@@ -775,7 +775,10 @@ solve_kernel(const typename Sys::Consts sc, const SolveOpts<R> o, const SolveIO<
             __nanosleep(500);
             if (starve_t0 == 0) starve_t0 = clock64();
             if (clock64() - starve_t0 > kWatchdogCycles || *(volatile unsigned int*)hq.abort) {
+                // give up: flag the call as failed and release the device->host stream's waits on the piece counters
                 *hq.abort = 1u;
+                if (lane == 0)
+                    for (int c = 0; c < hq.n_pieces; c++) atomicExch(hq.done + c, 0x7fffffffu);
                 return;
             }
             starved = false;
