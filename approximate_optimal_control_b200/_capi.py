@@ -55,7 +55,7 @@ class NnCostate(C.Structure):
 
 
 EXPORTS = ("pmp_abi_version", "pmp_last_error", "pmp_state_rows", "pmp_state_rows_flags", "pmp_device_count",
-           "pmp_solve_workspace_bytes", "pmp_solve_batch_cuda", "pmp_solve_launch_count", "pmp_solve_host", "pmp_solve_host_lqr", "pmp_solve_host_plan", "pmp_host_release", "pmp_host_probe_copy",
+           "pmp_solve_workspace_bytes", "pmp_solve_batch_cuda", "pmp_solve_launch_count", "pmp_solve_host", "pmp_solve_host_lqr", "pmp_solve_host_plan", "pmp_host_release", "pmp_host_probe_copy", "pmp_select_count_cuda", "pmp_select_write_cuda",
            "pmp_rhs_batch_cuda", "pmp_rhs_batch_cuda_flags", "pmp_ustar_batch_cuda", "pmp_ustar_batch_cuda_flags", "pmp_interp_batch_cuda", "pmp_forward_batch_cuda", "pmp_forward_nn_batch_cuda", "pmp_nn_value_batch_cuda",
            "pmp_fma_peak_cuda")
 
@@ -108,6 +108,11 @@ def load(path: str) -> C.CDLL:
     L.pmp_solve_host_plan.argtypes = [C.POINTER(Problem), C.POINTER(Opts), C.c_int64, C.c_int32, C.POINTER(C.c_int32),
                                       C.POINTER(C.c_int32)]
     L.pmp_host_release.argtypes = []
+    if hasattr(L, "pmp_select_count_cuda"):  # (the main library; plug-ins do not carry the selection kernels)
+        L.pmp_select_count_cuda.argtypes = [C.c_int32, C.c_int64, C.c_int32, C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p,
+                                            C.c_double, C.c_double, C.c_double, C.c_void_p, C.c_void_p]
+        L.pmp_select_write_cuda.argtypes = [C.c_int32, C.c_int64, C.c_int32, C.c_int32] + [C.c_void_p] * 5 + [C.c_int32, C.c_void_p,
+                                            C.c_void_p, C.c_double, C.c_double, C.c_double] + [C.c_void_p] * 8
     if hasattr(L, "pmp_host_probe_copy"):
         L.pmp_host_probe_copy.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_void_p]
     L.pmp_rhs_batch_cuda.argtypes = [C.POINTER(Problem), C.c_int32, C.c_int64, C.c_void_p,

@@ -37,6 +37,11 @@ int solve_host(const pmp_problem_t& p, const pmp_opts_t& o, long long n, const v
                int32_t* result, int n_pieces, const double* term_P, const double* term_xeq);
 int host_plan(long long n, int n_pieces, std::vector<long long>* bounds, long long* cs_max);
 int host_release();
+int select_count(int dtype, long long n, int s1, const void* v, const void* vxx, int nvxx, const int32_t* n_accepted, double lo,
+                 double hi, double vxx_max, int32_t* counts, cudaStream_t st);
+int select_write(int dtype, long long n, int s1, int nx, const void* x, const void* t, const void* v, const void* vx, const void* vxx,
+                 int nvxx, const int32_t* n_accepted, const long long* offsets, double lo, double hi, double vxx_max, void* ox, void* ot,
+                 void* ov, void* ovx, void* ovxx, double* stats, int32_t* flags, cudaStream_t st);
 int host_probe_copy(void* dst, const void* src, long long bytes, int blocks, cudaStream_t st);
 int fma_peak(int dtype, int variant, int iters, void* scratch, double* flops_out, cudaStream_t st);
 int interp_batch(const pmp_problem_t& p, const pmp_opts_t& o, long long nq, const void* y0, const void* t1,
@@ -281,9 +286,34 @@ int pmp_solve_host_plan(const pmp_problem_t* p, const pmp_opts_t* o, int64_t n, 
     if (kernels) *kernels = persistent ? 1 : pieces * (2 + pmp_solve_launch_count(p, o, 1));  // pack + solve + unpack
     // leaves in; leaves + counters out (all outputs requested, t_f given; the counters travel as one packed word when
     // max_steps < 2^14)
-    if (copies) *copies = pieces * (4 + (o->max_steps < (1 << 14) ? 5 : 7));
+    // (+ the 8-byte frontier copy behind every piece of a persistent launch)
+    if (copies) *copies = pieces * (4 + (o->max_steps < (1 << 14) ? 5 : 7) + (persistent ? 1 : 0));
     return pieces;
 }
+
+#ifndef PMP_PLUGIN
+int pmp_select_count_cuda(int32_t dtype, int64_t n, int32_t s1, const void* v, const void* vxx, int32_t nvxx, const int32_t* n_accepted,
+                          double v_lower, double v_upper, double vxx_max_norm, int32_t* counts, void* cuda_stream) {
+    if (dtype != PMP_F32 && dtype != PMP_F64) return fail(PMP_ERR_BAD_ARG, "dtype");
+    if (n < 0 || s1 < 1 || (n > 0 && (!v || !counts)) || (vxx && nvxx < 1)) return fail(PMP_ERR_BAD_ARG, "select_count: n, s1, v, counts");
+    int rc = pmp::select_count(dtype, n, s1, v, vxx, nvxx, n_accepted, v_lower, v_upper, vxx_max_norm, counts, (cudaStream_t)cuda_stream);
+    return rc ? cuda_fail(rc) : PMP_OK;
+}
+
+int pmp_select_write_cuda(int32_t dtype, int64_t n, int32_t s1, int32_t nx, const void* x, const void* t, const void* v, const void* vx,
+                          const void* vxx, int32_t nvxx, const int32_t* n_accepted, const int64_t* offsets, double v_lower, double v_upper,
+                          double vxx_max_norm, void* x_out, void* t_out, void* v_out, void* vx_out, void* vxx_out, double* stats,
+                          int32_t* flags, void* cuda_stream) {
+    if (dtype != PMP_F32 && dtype != PMP_F64) return fail(PMP_ERR_BAD_ARG, "dtype");
+    if (n < 0 || s1 < 1 || nx < 1 || nx > 16) return fail(PMP_ERR_BAD_ARG, "select_write: n, s1, nx (<= 16)");
+    if (n > 0 && (!x || !t || !v || !vx || !offsets || !x_out || !t_out || !v_out || !vx_out || !stats || !flags))
+        return fail(PMP_ERR_BAD_ARG, "select_write: NULL argument");
+    if ((vxx != nullptr) != (vxx_out != nullptr)) return fail(PMP_ERR_BAD_ARG, "select_write: vxx and vxx_out go together");
+    int rc = pmp::select_write(dtype, n, s1, nx, x, t, v, vx, vxx, nvxx, n_accepted, (const long long*)offsets, v_lower, v_upper,
+                               vxx_max_norm, x_out, t_out, v_out, vx_out, vxx_out, stats, flags, (cudaStream_t)cuda_stream);
+    return rc ? cuda_fail(rc) : PMP_OK;
+}
+#endif
 
 int pmp_host_probe_copy(void* dst, const void* src, int64_t bytes, int32_t blocks, void* cuda_stream) {
     if (!dst || !src || bytes < 0 || (bytes & 15) || blocks < 1) return fail(PMP_ERR_BAD_ARG, "probe copy: 16-byte multiples, blocks >= 1");

@@ -23,26 +23,97 @@ from . import _capi, systems
 from . import pontryagin_utils as pu
 
 
-def select_train_pts(value_interval, sols, vxx_max_norm=None):
-    """levelsets.py:667-709: all saved nodes whose value lies in [v_lower, v_upper] (inf/NaN padding
-    drops out of the comparison), as a dict of flat arrays {'x','t','v','vx'[,'vxx']}.  With a 'vxx' leaf
-    (pontryagin_solver_vxx) nodes with ||vxx||_F >= vxx_max_norm are dropped as well (:684-689; the reference
-    reads algo_params['vxx_max_norm'] from its closure, here it is an argument)."""
+class data_normaliser(object):
+    """nn_utils.py:112-178: per-component affine scaling of x and v to zero mean / unit variance and the induced scalings
+    of vx and vxx.  The reference computes the statistics with four passes over the training set; here they come out of the
+    selection kernel (sums accumulated while the nodes are being compacted): select_train_pts(..., return_normaliser=True)."""
+
+    def __init__(self, train_ode_states=None, *, x_means=None, x_stds=None, v_mean=None, v_std=None):
+        if train_ode_states is not None:  # the reference's constructor: statistics of a given data set (torch, on its device)
+            x, v = train_ode_states["x"], train_ode_states["v"]
+            x_means, x_stds = x.mean(0), x.std(0, unbiased=False)
+            v_mean, v_std = v.mean(), v.std(unbiased=False)
+        self.x_means, self.x_stds, self.v_mean, self.v_std = x_means, x_stds, v_mean, v_std
+
+    def normalise_x(self, x): return (x - self.x_means) / self.x_stds
+    def unnormalise_x(self, xn): return xn * self.x_stds + self.x_means
+    def normalise_v(self, v): return (v - self.v_mean) / self.v_std
+    def unnormalise_v(self, vn): return vn * self.v_std + self.v_mean
+    def normalise_vx(self, vx): return vx * self.x_stds / self.v_std
+    def unnormalise_vx(self, vx_n): return (vx_n / self.x_stds) * self.v_std
+    def normalise_vxx(self, vxx): return self.x_stds[..., :, None] * vxx * self.x_stds[..., None, :] / self.v_std
+    def unnormalise_vxx(self, vxx_n): return (vxx_n * self.v_std) / self.x_stds[..., :, None] / self.x_stds[..., None, :]
+
+    def normalise_all_dict(self, train_ode_states):
+        oup = {"x": self.normalise_x(train_ode_states["x"]), "v": self.normalise_v(train_ode_states["v"]),
+               "vx": self.normalise_vx(train_ode_states["vx"])}
+        if "vxx" in train_ode_states:
+            oup["vxx"] = self.normalise_vxx(train_ode_states["vxx"])
+        return oup
+
+
+def select_train_pts(value_interval, sols, vxx_max_norm=None, return_normaliser=False, verbose=True):
+    """levelsets.py:667-709: all saved nodes whose value lies in [v_lower, v_upper] (inf/NaN padding drops out of the
+    comparison), as a dict of flat arrays {'x','t','v','vx'[,'vxx']} in the order of the reference's boolean-mask gather.
+    With a 'vxx' leaf (pontryagin_solver_vxx) nodes with ||vxx||_F >= vxx_max_norm are dropped as well (:684-689; the
+    reference reads algo_params['vxx_max_norm'] from its closure, here it is an argument).
+
+    Two kernels over the device-resident Solution (csrc/pmp_select.cu): a per-trajectory count, then a stable compaction
+    fused with the data_normaliser's sums (nn_utils.py:119-134) and the NaN check; only the n_accepted + 1 saved nodes of a
+    trajectory are read.  return_normaliser=True also returns the data_normaliser of the selected set."""
     v_lower, v_upper = value_interval
-    v = sols.ys["v"]
-    v_finite = torch.isfinite(v)
-    bool_train_idx = (v >= v_lower) & (v <= v_upper)
-    if "vxx" in sols.ys:
-        if vxx_max_norm is None:
-            raise ValueError("sols carries a 'vxx' leaf: pass vxx_max_norm (algo_params['vxx_max_norm'])")
-        bool_train_idx = bool_train_idx & (torch.linalg.matrix_norm(sols.ys["vxx"]) < vxx_max_norm)
-    all_ys = {k: node[bool_train_idx] for k, node in sols.ys.items()}
-    n_sel, n_fin = int(bool_train_idx.sum()), int(v_finite.sum())
-    perc = 100.0 * n_sel / max(n_fin, 1)
-    print(f"full (train+test) dataset size: {n_sel} points (= {perc:.2f}% of valid points)")
-    if any(bool(torch.isnan(a).any()) for a in all_ys.values()):
+    ys = sols.ys
+    v = ys["v"]
+    if v.dim() == 1:  # a single trajectory
+        ys = {k: a[None] for k, a in ys.items()}
+        v = ys["v"]
+    n, s1 = v.shape
+    nx = ys["x"].shape[-1]
+    dev, dtype = v.device, v.dtype
+    has_vxx = "vxx" in ys
+    if has_vxx and vxx_max_norm is None:
+        raise ValueError("sols carries a 'vxx' leaf: pass vxx_max_norm (algo_params['vxx_max_norm'])")
+    L = _capi.lib()
+    code = pu._code(dtype)
+    leaves = {k: ys[k].contiguous() for k in (("x", "t", "v", "vx", "vxx") if has_vxx else ("x", "t", "v", "vx"))}
+    nacc = sols.stats["num_accepted_steps"].reshape(-1).to(torch.int32).contiguous() if sols.stats is not None else None
+    vxx_p = leaves["vxx"].data_ptr() if has_vxx else None
+    nvxx = nx * nx if has_vxx else 0
+    vmax = float(vxx_max_norm) if has_vxx else 0.0
+    counts = torch.empty(n, dtype=torch.int32, device=dev)
+    stream = pu._stream_ptr(dev)
+    with torch.cuda.device(dev):
+        _capi.check(L.pmp_select_count_cuda(code, n, s1, leaves["v"].data_ptr(), vxx_p, nvxx, nacc.data_ptr() if nacc is not None else None,
+                                            float(v_lower), float(v_upper), vmax, counts.data_ptr(), stream), L)
+        ends = torch.cumsum(counts, 0, dtype=torch.int64)  # (the one library call of this path: a prefix sum over n counts)
+        offsets = (ends - counts).contiguous()
+        m = int(ends[-1]) if n else 0
+        mm = max(m, 1)  # (an empty selection still hands valid pointers to the C entry)
+        out = {"x": torch.empty((mm, nx), dtype=dtype, device=dev), "t": torch.empty(mm, dtype=dtype, device=dev),
+               "v": torch.empty(mm, dtype=dtype, device=dev), "vx": torch.empty((mm, nx), dtype=dtype, device=dev)}
+        if has_vxx:
+            out["vxx"] = torch.empty((mm, nx, nx), dtype=dtype, device=dev)
+        stats = torch.zeros(2 * nx + 2, dtype=torch.float64, device=dev)
+        flags = torch.zeros(1, dtype=torch.int32, device=dev)
+        _capi.check(L.pmp_select_write_cuda(code, n, s1, nx, leaves["x"].data_ptr(), leaves["t"].data_ptr(), leaves["v"].data_ptr(),
+                                            leaves["vx"].data_ptr(), vxx_p, nvxx, nacc.data_ptr() if nacc is not None else None,
+                                            offsets.data_ptr(), float(v_lower), float(v_upper), vmax, out["x"].data_ptr(),
+                                            out["t"].data_ptr(), out["v"].data_ptr(), out["vx"].data_ptr(),
+                                            out["vxx"].data_ptr() if has_vxx else None, stats.data_ptr(), flags.data_ptr(), stream), L)
+    out = {k: a[:m] for k, a in out.items()}
+    if verbose:
+        n_fin = int((nacc.long() + 1).clamp(max=s1).sum()) if nacc is not None else int(torch.isfinite(v).sum())
+        print(f"full (train+test) dataset size: {m} points (= {100.0 * m / max(n_fin, 1):.2f}% of valid points)")
+    if int(flags) & 1:
         raise RuntimeError("There are still NaNs in training data.")
-    return all_ys
+    if not return_normaliser:
+        return out
+    st = stats / max(m, 1)
+    mean_x, mean_v = st[:nx], st[2 * nx]
+    var_x = (st[nx:2 * nx] - mean_x * mean_x).clamp(min=0)
+    var_v = (st[2 * nx + 1] - mean_v * mean_v).clamp(min=0)
+    norm = data_normaliser(x_means=mean_x.to(dtype), x_stds=var_x.sqrt().to(dtype), v_mean=mean_v.to(dtype), v_std=var_v.sqrt().to(dtype))
+    return out, norm
 
 
 def running_cost(ys: dict, problem_params: dict) -> torch.Tensor:

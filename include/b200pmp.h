@@ -231,6 +231,25 @@ int pmp_host_release(void);
  * the copy engines (scripts/pcie_probe.py).  bytes must be a multiple of 16.  Asynchronous on cuda_stream. */
 int pmp_host_probe_copy(void *dst, const void *src, int64_t bytes, int32_t blocks, void *cuda_stream);
 
+/* ---- data selection after the solve: select_train_pts (levelsets.py:667-709) + data_normaliser statistics
+ * (nn_utils.py:112-134) on the device-resident SaveAt(steps) buffers of pmp_solve_batch_cuda (save_dense).  Not exported by
+ * codegen plug-ins (nothing here depends on the dynamics).
+ * Pass 1: counts[i] = number of saved nodes of trajectory i with v_lower <= v <= v_upper (and ||vxx||_F < vxx_max_norm when
+ * vxx != NULL; nvxx = nx*nx).  n_accepted (optional) bounds the slots read to 0..n_accepted[i]; padding never passes the
+ * test anyway.  v [n][s1], vxx [n][s1][nvxx]. */
+int pmp_select_count_cuda(int32_t dtype, int64_t n, int32_t s1, const void *v, const void *vxx, int32_t nvxx,
+                          const int32_t *n_accepted, double v_lower, double v_upper, double vxx_max_norm,
+                          int32_t *counts, void *cuda_stream);
+/* Pass 2: offsets [n] = exclusive prefix sum of counts (int64, device).  Writes the selected nodes of every leaf to flat
+ * arrays in the order of the reference's boolean-mask gather (trajectory by trajectory, slot by slot): x_out [M][nx],
+ * t_out, v_out [M], vx_out [M][nx] (, vxx_out [M][nvxx]); ADDS to stats [2 nx + 2] (device doubles, zeroed by the caller)
+ * sum x[nx], sum x^2[nx], sum v, sum v^2 over the selected nodes, and ORs 1 into flags[0] if a selected node holds a NaN. */
+int pmp_select_write_cuda(int32_t dtype, int64_t n, int32_t s1, int32_t nx, const void *x, const void *t, const void *v,
+                          const void *vx, const void *vxx, int32_t nvxx, const int32_t *n_accepted,
+                          const int64_t *offsets, double v_lower, double v_upper, double vxx_max_norm,
+                          void *x_out, void *t_out, void *v_out, void *vx_out, void *vxx_out,
+                          double *stats, int32_t *flags, void *cuda_stream);
+
 /* number of kernels one pmp_solve_batch_cuda call launches with these options (bench bookkeeping) */
 int pmp_solve_launch_count(const pmp_problem_t *problem, const pmp_opts_t *opts, int64_t n);
 

@@ -504,28 +504,81 @@ def test_solution_evaluate_and_state_at_value_public_api():
 
 
 # ---- the data-selection step right after the path -----------------------------------------
-def test_select_train_pts_and_find_min_l_on_device():
+@pytest.mark.parametrize("dtype", ["float64", "float32"])
+def test_select_train_pts_and_find_min_l_on_device(dtype):
+    """levelsets.select_train_pts (csrc/pmp_select.cu: count + stable compaction fused with the normaliser's sums) against the
+    reference's own formulation -- a boolean mask over the (N, S+1) inf-padded buffers, node[bool_train_idx] on every leaf
+    (levelsets.py:679-693), mean / std of nn_utils.py:119-134 -- evaluated with numpy on a host copy."""
     import torch
     from approximate_optimal_control_b200 import levelsets, pontryagin_utils as pu, systems, terminal
-    pp, ap = systems.flatquad_problem_params(), dict(systems.flatquad_algo_params(), dtype="float64")
+    pp, ap = systems.flatquad_problem_params(), dict(systems.flatquad_algo_params(), dtype=dtype)
     _, P = pu.get_terminal_lqr(pp)
-    st = terminal.sample_terminal_states(P, pp["V_f"], 300, seed=2)
+    st = terminal.sample_terminal_states(P, pp["V_f"], 3001, seed=2)
+    st["x"][17] = np.nan  # a NaN terminal state (levelsets.py:1233): retires at once, its slot 0 is NaN and must not be selected
     sol = pu.define_backward_solver(pp, ap)[0](st)
     band = (5 / 1000, 5.0)  # levelsets.py:716-719: v_k = 5, [v_k/1000, v_k]
-    sel = levelsets.select_train_pts(band, sol)
-    v = sol.ys["v"].cpu().numpy()
-    mask = (v >= band[0]) & (v <= band[1])
-    assert sel["x"].shape == (mask.sum(), 6) and sel["v"].shape == (mask.sum(),)
-    assert np.array_equal(sel["vx"].cpu().numpy(), sol.ys["vx"].cpu().numpy()[mask])
+    sel, norm = levelsets.select_train_pts(band, sol, return_normaliser=True)
+    ys = {k: a.cpu().numpy() for k, a in sol.ys.items()}
+    mask = (ys["v"] >= band[0]) & (ys["v"] <= band[1])
+    assert 0 < mask.sum() < np.isfinite(ys["v"]).sum()
+    for k in ("x", "t", "v", "vx"):
+        assert np.array_equal(sel[k].cpu().numpy(), ys[k][mask]), k   # same nodes, same order, bit for bit
+    x64, v64 = ys["x"][mask].astype(np.float64), ys["v"][mask].astype(np.float64)
+    rt = 1e-12 if dtype == "float64" else 2e-6
+    assert np.allclose(norm.x_means.cpu().numpy(), x64.mean(0), rtol=rt, atol=rt)
+    assert np.allclose(norm.x_stds.cpu().numpy(), x64.std(0), rtol=rt * 10, atol=rt)
+    assert np.allclose(float(norm.v_mean), v64.mean(), rtol=rt) and np.allclose(float(norm.v_std), v64.std(), rtol=rt * 10)
+    nd = norm.normalise_all_dict(sel)
+    assert abs(float(nd["x"].mean())) < 1e-4 and abs(float(nd["v"].std(unbiased=False)) - 1) < 1e-4
+    ref_norm = levelsets.data_normaliser(sel)  # the reference's constructor on the selected set
+    assert torch.allclose(ref_norm.x_stds, norm.x_stds, rtol=1e-4)
+    # single trajectory, empty selection, NULL n_accepted (a Solution sliced to one trajectory keeps its stats)
+    one = levelsets.select_train_pts(band, sol[5], verbose=False)
+    m5 = mask[5]
+    assert np.array_equal(one["v"].cpu().numpy(), ys["v"][5][m5])
+    none = levelsets.select_train_pts((1e9, 2e9), sol, verbose=False)
+    assert none["x"].shape == (0, 6) and none["v"].shape == (0,)
     # running cost at every node against the oracle's f_extended (l = -v')
-    x = sol.ys["x"].cpu().numpy()[mask].T.astype(np.float64)
-    lam = sol.ys["vx"].cpu().numpy()[mask].T.astype(np.float64)
+    x = ys["x"][mask].T.astype(np.float64)
+    lam = ys["vx"][mask].T.astype(np.float64)
     dy = O.rhs_batch(oracle_problem("flatquad"), O.F64, np.concatenate([x, np.zeros((2, x.shape[1])), lam], 0))
     want = (-dy[7]).min()
     got = float(levelsets.find_min_l(sol.ys, band[0], band[1], pp))
-    assert abs(got - want) <= 1e-4 * max(1.0, abs(want)), (got, want)
+    assert abs(got - want) <= (1e-4 if dtype == "float64" else 5e-3) * max(1.0, abs(want)), (got, want)
     l_all = levelsets.running_cost(sol.ys, pp)
     assert l_all.shape == sol.ys["v"].shape and torch.isnan(l_all[torch.isinf(sol.ys["v"])]).all()
+
+
+def test_select_train_pts_with_vxx_leaf_and_nan_guard():
+    """The vxx filter of levelsets.py:684-689 (||vxx||_F < vxx_max_norm) inside the selection kernels, and the NaN check of
+    :700-706 (a selected node with a NaN leaf raises)."""
+    import torch
+    from approximate_optimal_control_b200 import levelsets
+    from approximate_optimal_control_b200.solution import Solution
+    rng = np.random.Generator(np.random.PCG64(3))
+    n, s1, nx = 257, 33, 6
+    nacc = rng.integers(0, s1, n).astype(np.int32)
+    slot = np.arange(s1)[None, :]
+    valid = slot <= nacc[:, None]
+    ys = {"v": np.where(valid, rng.uniform(0, 10, (n, s1)), np.inf), "t": np.where(valid, -rng.uniform(0, 3, (n, s1)), -np.inf),
+          "x": np.where(valid[..., None], rng.standard_normal((n, s1, nx)), np.inf),
+          "vx": np.where(valid[..., None], rng.standard_normal((n, s1, nx)), np.inf),
+          "vxx": np.where(valid[..., None, None], rng.standard_normal((n, s1, nx, nx)) * rng.uniform(0.1, 3, (n, s1, 1, 1)), np.inf)}
+    dev = {k: torch.as_tensor(a, device="cuda") for k, a in ys.items()}
+    sol = Solution(t0=0.0, t1=-3.0, ts=dev["t"], ys=dev, y_end={}, stats={"num_accepted_steps": torch.as_tensor(nacc, device="cuda")},
+                   result=torch.zeros(n, dtype=torch.int32, device="cuda"))
+    sel = levelsets.select_train_pts((2.0, 7.0), sol, vxx_max_norm=6.0, verbose=False)
+    with np.errstate(invalid="ignore"):
+        mask = (ys["v"] >= 2.0) & (ys["v"] <= 7.0) & (np.linalg.norm(ys["vxx"], axis=(2, 3)) < 6.0)
+    assert 0 < mask.sum() < ((ys["v"] >= 2.0) & (ys["v"] <= 7.0)).sum()
+    for k in ys:
+        assert np.array_equal(sel[k].cpu().numpy(), ys[k][mask]), k
+    with pytest.raises(ValueError):
+        levelsets.select_train_pts((2.0, 7.0), sol)
+    i, j = np.argwhere(mask)[3]
+    dev["vx"][i, j, 2] = float("nan")
+    with pytest.raises(RuntimeError, match="NaN"):
+        levelsets.select_train_pts((2.0, 7.0), sol, vxx_max_norm=6.0, verbose=False)
 
 
 def test_dense_and_endpoint_writes_stay_inside_their_buffers():
