@@ -37,6 +37,8 @@ int solve_host(const pmp_problem_t& p, const pmp_opts_t& o, long long n, const v
                int32_t* result, int n_pieces, const double* term_P, const double* term_xeq);
 int host_plan(long long n, int n_pieces, std::vector<long long>* bounds, long long* cs_max);
 int host_release();
+int solve_jvp(const pmp_problem_t& p, const pmp_opts_t& o, long long n, const void* y_f, const void* dy_f, void* y_end, void* dy_end,
+              int32_t* a, int32_t* s, int32_t* r, cudaStream_t st);
 int select_count(int dtype, long long n, int s1, const void* v, const void* vxx, int nvxx, const int32_t* n_accepted, double lo,
                  double hi, double vxx_max, int32_t* counts, cudaStream_t st);
 int select_write(int dtype, long long n, int s1, int nx, const void* x, const void* t, const void* v, const void* vx, const void* vxx,
@@ -248,6 +250,21 @@ static int check_host(const pmp_problem_t* p, const pmp_opts_t* o, int64_t n, in
     if (n < 0) return fail(PMP_ERR_BAD_ARG, "n < 0");
     if (n_pieces < 0 || n_pieces > 1024) return fail(PMP_ERR_BAD_ARG, "n_pieces must be in 0..1024");
     return 0;
+}
+
+int pmp_solve_jvp_cuda(const pmp_problem_t* p, const pmp_opts_t* o, int64_t n, const void* y_f, const void* dy_f, void* y_end,
+                       void* dy_end, int32_t* n_accepted, int32_t* n_steps, int32_t* result, void* cuda_stream) {
+    if (int e = check_problem(p)) return e;
+    if (int e = check_opts(o)) return e;
+    if (int e = check_pair(p, o)) return e;
+    if (o->save_dense || o->flags != 0) return fail(PMP_ERR_UNSUPPORTED, "pmp_solve_jvp_cuda: endpoints only, default flags");
+    if (n < 0) return fail(PMP_ERR_BAD_ARG, "n < 0");
+    if (n == 0) return PMP_OK;
+    if (!y_f || !dy_f || !y_end || !dy_end) return fail(PMP_ERR_BAD_ARG, "y_f / dy_f / y_end / dy_end is NULL");
+    if (pmp_device_count() <= 0) return fail(PMP_ERR_NO_DEVICE, "no CUDA device: libb200pmp has no CPU fallback");
+    int rc = pmp::solve_jvp(*p, *o, n, y_f, dy_f, y_end, dy_end, n_accepted, n_steps, result, (cudaStream_t)cuda_stream);
+    if (rc == -1000) return fail(PMP_ERR_UNSUPPORTED, "pmp_solve_jvp_cuda: no instantiation for this system / method / dtype");
+    return rc ? cuda_fail(rc) : PMP_OK;
 }
 
 int pmp_solve_host(const pmp_problem_t* p, const pmp_opts_t* o, int64_t n, const void* x_f, const void* t_f, const void* v_f,

@@ -194,6 +194,23 @@ def solve_batch_soa(problem: _capi.Problem, opts: _capi.Opts, y_f: torch.Tensor,
     return out
 
 
+def solve_jvp_soa(problem: _capi.Problem, opts: _capi.Opts, y_f: torch.Tensor, dy_f: torch.Tensor):
+    """Thin wrapper of pmp_solve_jvp_cuda: y_f, dy_f [NS, n] CUDA tensors -> dict(y_end, dy_end [NS, n], n_accepted, n_steps,
+    result): the endpoints and their directional derivative along dy_f (forward mode through the whole solve)."""
+    L = _capi.lib_of(problem)
+    assert y_f.is_cuda and y_f.is_contiguous() and dy_f.is_cuda and dy_f.is_contiguous() and y_f.shape == dy_f.shape
+    n = y_f.shape[1]
+    dev = y_f.device
+    out = {"y_end": torch.empty_like(y_f), "dy_end": torch.empty_like(y_f)}
+    for k in ("n_accepted", "n_steps", "result"):
+        out[k] = torch.empty(n, dtype=torch.int32, device=dev)
+    with torch.cuda.device(dev):
+        _capi.check(L.pmp_solve_jvp_cuda(C.byref(problem), C.byref(opts), n, y_f.data_ptr(), dy_f.data_ptr(), out["y_end"].data_ptr(),
+                                         out["dy_end"].data_ptr(), out["n_accepted"].data_ptr(), out["n_steps"].data_ptr(),
+                                         out["result"].data_ptr(), _stream_ptr(dev)), L)
+    return out
+
+
 def forward_batch_soa(problem: _capi.Problem, opts: _capi.Opts, x0: torch.Tensor, P=None, x_eq=None, out=None, nn=None):
     """Thin wrapper of pmp_forward_batch_cuda / pmp_forward_nn_batch_cuda: closed-loop forward simulation under
     lambda(x) = P (x - x_eq), or under the costate law of a value-network ensemble (nn: nn_costate.NnEnsemble), with the
@@ -539,10 +556,65 @@ def make_pontryagin_solver_reparam(problem_params: dict, algo_params: dict):
           integrates dy/dv = (f, -H_x, 1) / (dv/dt), dv/dt = -l(x,u*) experiment_orbits.py:109-111
           sol.ts = value levels, sol.ys = (S+1, 2nx+1) [batched: (N, S+1, 2nx+1)]  rrt_sampler.py:76-82
     algo_params: pontryagin_solver_{dt, adaptive, rtol, atol, maxsteps} (experiment_orbits.py:97-104).
+    solver.jvp(y0, v0, v1, dy0) / solver.jacobian(y0, v0, v1): forward-mode sensitivities with respect to y0 (the
+    reference differentiates the solver with jax.jacobian, experiment_orbits.py:186-197).
     No reference output exists for this function: parity is pinned only against the oracle.
     """
     problem = systems.to_c_problem(problem_params)
     nx = problem.nx
+
+    def _soa(y0t, v0, dtype, dev):  # flat [x, lambda, t] rows -> [NS, n] (x, t, v, vx)
+        n = y0t.shape[0]
+        y = torch.empty((2 * nx + 2, n), dtype=dtype, device=dev)
+        y[:nx] = y0t[:, :nx].t()
+        y[nx] = y0t[:, 2 * nx]
+        y[nx + 1] = _as_tensor(v0, dtype, dev).reshape(-1).expand(n)
+        y[nx + 2:] = y0t[:, nx:2 * nx].t()
+        return y
+
+    def _flat(y):  # [NS, n] -> (n, 2nx+1) flat [x, lambda, t]
+        return torch.cat([y[:nx].t(), y[nx + 2:].t(), y[nx][:, None]], dim=1)
+
+    def _opts(dtype, v1, save_steps):
+        adaptive = bool(algo_params.get("pontryagin_solver_adaptive", True))
+        return _solver_opts(algo_params, dtype, indep=_capi.INDEP_VALUE, t0=0.0, t1=float(v1),
+                            dt0=float(algo_params.get("pontryagin_solver_dt", 1 / 16)),
+                            adaptive=int(adaptive), save_dense=int(save_steps),
+                            dtmin=float(algo_params.get("pontryagin_solver_dtmin", 0.0)),
+                            dtmax=float(algo_params.get("pontryagin_solver_dtmax", 0.0)))
+
+    def jvp(y0, v0, v1, dy0):
+        """(y(v1), dy(v1)): the state at value level v1 and its derivative along dy0, d y(v1) / d y0 . dy0 -- what
+        jax.jvp / jax.jacobian through `pontryagin_solver(y0, v0, v1)` gives (experiment_orbits.py:186-197: dsol_final =
+        jax.jacobian(get_final_x)(theta) is jvp with dy0 = d y0 / d theta).  y0, dy0: (2nx+1,) or (N, 2nx+1); v0, v1 fixed."""
+        dev = _device(y0)
+        dtype = _infer_dtype(algo_params, y0)
+        y0t = _as_tensor(y0, dtype, dev)
+        batched = y0t.dim() == 2
+        y0t = y0t.reshape(-1, 2 * nx + 1)
+        d0t = _as_tensor(dy0, dtype, dev).reshape(-1, 2 * nx + 1).expand_as(y0t)
+        y = _soa(y0t, v0, dtype, dev)
+        dy = _soa(d0t, 0.0, dtype, dev)
+        out = solve_jvp_soa(problem, _opts(dtype, v1, False), y.contiguous(), dy.contiguous())
+        raise_if_failed(out["result"], algo_params, "pontryagin_solver_reparam.jvp")
+        y1, dy1 = _flat(out["y_end"]), _flat(out["dy_end"])
+        return (y1, dy1) if batched else (y1[0], dy1[0])
+
+    def jacobian(y0, v0, v1):
+        """d y(v1) / d y0, shape (2nx+1, 2nx+1) [batched: (N, 2nx+1, 2nx+1)]: 2nx+1 forward-mode columns in one launch."""
+        dev = _device(y0)
+        dtype = _infer_dtype(algo_params, y0)
+        y0t = _as_tensor(y0, dtype, dev)
+        batched = y0t.dim() == 2
+        y0t = y0t.reshape(-1, 2 * nx + 1)
+        n, m = y0t.shape
+        eye = torch.eye(m, dtype=dtype, device=dev)
+        yy = y0t[:, None, :].expand(n, m, m).reshape(n * m, m)
+        dd = eye[None].expand(n, m, m).reshape(n * m, m)
+        v0t = _as_tensor(v0, dtype, dev).reshape(-1).expand(n)[:, None].expand(n, m).reshape(-1)
+        _, dy1 = jvp(yy, v0t, v1, dd)
+        J = dy1.reshape(n, m, m).transpose(1, 2)  # [i, out, in]
+        return J if batched else J[0]
 
     def solver(y0, v0, v1, save_steps=True):
         dev = _device(y0)
@@ -550,18 +622,8 @@ def make_pontryagin_solver_reparam(problem_params: dict, algo_params: dict):
         y0t = _as_tensor(y0, dtype, dev)
         batched = y0t.dim() == 2
         y0t = y0t.reshape(-1, 2 * nx + 1)
-        n = y0t.shape[0]
-        y = torch.empty((2 * nx + 2, n), dtype=dtype, device=dev)
-        y[:nx] = y0t[:, :nx].t()
-        y[nx] = y0t[:, 2 * nx]
-        y[nx + 1] = _as_tensor(v0, dtype, dev).reshape(-1).expand(n)
-        y[nx + 2:] = y0t[:, nx:2 * nx].t()
-        adaptive = bool(algo_params.get("pontryagin_solver_adaptive", True))
-        opts = _solver_opts(algo_params, dtype, indep=_capi.INDEP_VALUE, t0=0.0, t1=float(v1),
-                            dt0=float(algo_params.get("pontryagin_solver_dt", 1 / 16)),
-                            adaptive=int(adaptive), save_dense=int(save_steps),
-                            dtmin=float(algo_params.get("pontryagin_solver_dtmin", 0.0)),
-                            dtmax=float(algo_params.get("pontryagin_solver_dtmax", 0.0)))
+        y = _soa(y0t, v0, dtype, dev)
+        opts = _opts(dtype, v1, save_steps)
         out = solve_batch_soa(problem, opts, y)
         raise_if_failed(out["result"], algo_params, "pontryagin_solver_reparam")
         sol = _wrap_solution(out, nx, True, None, float(v1), opts, problem)
@@ -570,4 +632,6 @@ def make_pontryagin_solver_reparam(problem_params: dict, algo_params: dict):
             sol.ys = torch.cat([sol.ys["x"], sol.ys["vx"], sol.ys["t"][..., None]], dim=-1)
         return sol if batched else sol[0]
 
+    solver.jvp = jvp
+    solver.jacobian = jacobian
     return solver

@@ -231,6 +231,16 @@ int pmp_host_release(void);
  * the copy engines (scripts/pcie_probe.py).  bytes must be a multiple of 16.  Asynchronous on cuda_stream. */
 int pmp_host_probe_copy(void *dst, const void *src, int64_t bytes, int32_t blocks, void *cuda_stream);
 
+/* Forward-mode sensitivity of a solve: endpoint AND its directional derivative along dy_f, d y_end / d y_f . dy_f, for n
+ * trajectories (y_f, dy_f, y_end, dy_end [NS][n]).  Replaces jax.jacobian / jvp through diffrax.diffeqsolve
+ * (experiment_orbits.py:186-197 differentiates the value-parameterised solve, indep = PMP_INDEP_VALUE, with respect to the
+ * terminal state; the time-parameterised solve works the same way).  Dual numbers through the dynamics functor and the
+ * Runge-Kutta steps; step control, clipping and argmin decisions on primal values, as in jax's jvp of the traced program;
+ * t0 / t1 / v0 / v1 carry no tangent.  Works for every compiled and generated system.  Endpoints only, flags 0. */
+int pmp_solve_jvp_cuda(const pmp_problem_t *problem, const pmp_opts_t *opts, int64_t n, const void *y_f, const void *dy_f,
+                       void *y_end, void *dy_end, int32_t *n_accepted, int32_t *n_steps, int32_t *result,
+                       void *cuda_stream);
+
 /* ---- data selection after the solve: select_train_pts (levelsets.py:667-709) + data_normaliser statistics
  * (nn_utils.py:112-134) on the device-resident SaveAt(steps) buffers of pmp_solve_batch_cuda (save_dense).  Not exported by
  * codegen plug-ins (nothing here depends on the dynamics).

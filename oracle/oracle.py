@@ -163,6 +163,22 @@ def solve_batch(problem: Problem, opts: Opts, y_f: np.ndarray, n_threads: int = 
     return out
 
 
+def solve_jvp(problem: Problem, opts: Opts, y_f: np.ndarray, dy_f: np.ndarray) -> dict:
+    """fp64: endpoint and its directional derivative along dy_f (forward-mode dual numbers through the whole solve, the
+    step control decided on primal values as jax's jvp of diffeqsolve does).  y_f, dy_f [NS, n]."""
+    y_f = np.ascontiguousarray(y_f, dtype=np.float64)
+    dy_f = np.ascontiguousarray(dy_f, dtype=np.float64)
+    ns, n = y_f.shape
+    out = {"y_end": np.empty((ns, n)), "dy_end": np.empty((ns, n)), "n_accepted": np.empty(n, np.int32),
+           "n_steps": np.empty(n, np.int32), "result": np.empty(n, np.int32)}
+    L = lib()
+    L.pmp_oracle_solve_jvp.argtypes = [C.POINTER(Problem), C.POINTER(Opts), C.c_int64] + [C.c_void_p] * 7
+    _check(L.pmp_oracle_solve_jvp(C.byref(problem), C.byref(opts), n, y_f.ctypes.data, dy_f.ctypes.data, out["y_end"].ctypes.data,
+                                  out["dy_end"].ctypes.data, out["n_accepted"].ctypes.data, out["n_steps"].ctypes.data,
+                                  out["result"].ctypes.data))
+    return out
+
+
 def rhs_batch(problem: Problem, dtype: int, y: np.ndarray, model_pass1: bool = False) -> np.ndarray:
     dt = _np_dtype(dtype)
     y = np.ascontiguousarray(y, dtype=dt)

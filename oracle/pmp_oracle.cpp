@@ -7,6 +7,7 @@
 #include <string>
 #include <vector>
 
+#include "dual.hpp"
 #include "opcount.hpp"
 #ifdef _OPENMP
 #include <omp.h>
@@ -282,6 +283,36 @@ int pmp_oracle_interp_batch(const pmp_problem_t* p, const pmp_opts_t* o, int64_t
 // out[2..3] = flops, specials of ONE step attempt of opts->method excluding nothing (stages, RHS
 // evaluations, error estimate, norm, controller); measured by running one attempt on the counting
 // scalar from the state y0 [NS] (doubles).
+// Directional derivative of the endpoint with respect to the terminal state (fp64): y_f, dy_f [NS][n] -> y_end, dy_end [NS][n].
+// The test-side reference of pmp_solve_jvp_cuda (experiment_orbits.py:186-197: jax.jacobian through the value-parameterised solve).
+int pmp_oracle_solve_jvp(const pmp_problem_t* p, const pmp_opts_t* o, int64_t n, const double* y_f, const double* dy_f,
+                         double* y_end, double* dy_end, int32_t* n_accepted, int32_t* n_steps, int32_t* result) {
+    if (int e = check(p, o)) return e;
+    if (o->flags & PMP_FLAG_VXX) return fail(PMP_ERR_UNSUPPORTED, "jvp: no vxx leaf");
+    auto run = [&](auto sys) {
+        using Sys = decltype(sys);
+        constexpr int NS = 2 * Sys::NX + 2;
+        pmp_opts_t oo = *o;
+        oo.save_dense = 0;
+#pragma omp parallel for schedule(dynamic, 16)
+        for (int64_t i = 0; i < n; i++) {
+            Dual y[NS], ye[NS];
+            for (int q = 0; q < NS; q++) y[q] = Dual(y_f[q * n + i], dy_f[q * n + i]);
+            TrajStats st = solve_one<Dual, Sys>(sys, oo, y, ye, DenseSink<Dual>{});
+            for (int q = 0; q < NS; q++) { y_end[q * n + i] = ye[q].v; dy_end[q * n + i] = ye[q].d; }
+            if (n_accepted) n_accepted[i] = st.n_accepted;
+            if (n_steps) n_steps[i] = st.n_steps;
+            if (result) result[i] = st.result;
+        }
+    };
+    switch (p->system_id) {
+        case PMP_SYS_FLATQUAD: run(Flatquad<Dual>(*p)); return 0;
+        case PMP_SYS_ORBITS: run(Orbits<Dual>(*p)); return 0;
+        case PMP_SYS_LQR_STATEPENALTY: run(LqrStatePenalty<Dual>(*p)); return 0;
+    }
+    return fail(PMP_ERR_UNSUPPORTED, "unknown system_id");
+}
+
 int pmp_oracle_opcount(const pmp_problem_t* p, const pmp_opts_t* o, const double* y0, int64_t* out) {
     if (int e = check(p, o)) return e;
     auto run = [&](auto sys) {

@@ -334,6 +334,91 @@ def test_c3_orbits_value_reparam_fp64(log2n):
     assert (got["y_end"][2][ok] < 0).all()  # time ran backward
 
 
+@pytest.mark.parametrize("name,value_mode", [("orbits", True), ("orbits", False), ("flatquad", False), ("lqr", True)])
+def test_solve_jvp_vs_oracle_duals_and_finite_differences(name, value_mode):
+    """pmp_solve_jvp_cuda (dual numbers through the functor and the RK steps) against (a) the oracle instantiated on its own
+    dual-number scalar: same step sequences, tangents equal to rounding; (b) central finite differences of tight solves.
+    experiment_orbits.py:186-197 takes jax.jacobian through the value-parameterised solve."""
+    import torch
+    from approximate_optimal_control_b200 import pontryagin_utils as pu
+    n = 256
+    y = {"orbits": orbits_terminal, "flatquad": flatquad_terminal, "lqr": lqr_terminal}[name](n)
+    rng = np.random.Generator(np.random.PCG64(11))
+    dy = rng.standard_normal(y.shape)
+    nx = (y.shape[0] - 2) // 2
+    dy[nx] = 0.0      # t
+    if value_mode:
+        dy[nx + 1] = 0.0  # v0 is the (fixed) start of the independent variable
+    kw = dict(method="tsit5", dtype=_capi.F64, rtol=1e-9, atol=1e-9, max_steps=4096, dtmin=0.0, dtmax=0.0)
+    if value_mode:
+        kw.update(indep=_capi.INDEP_VALUE, t0=0.0, t1=1.5 if name == "orbits" else 0.05, dt0=1 / 64 if name == "orbits" else 1e-3)
+    else:
+        kw.update(t0=0.0, t1=-1.0 if name == "flatquad" else -3.0, dt0=-0.05)
+    opts = _capi.make_opts(**kw)
+    prob, _ = c_problem(name)
+    yd, dyd = (torch.as_tensor(a, device="cuda").contiguous() for a in (y, dy))
+    got = {k: v.cpu().numpy() for k, v in pu.solve_jvp_soa(prob, opts, yd, dyd).items()}
+    ref = O.solve_jvp(oracle_problem(name), as_oracle_opts(opts), y, dy)
+    plain = cuda_solve(prob, opts, y)
+    assert np.array_equal(got["y_end"], plain["y_end"]) and np.array_equal(got["n_steps"], plain["n_steps"])  # the primal IS the solve
+    assert (got["result"] == 0).all() and (got["result"] == ref["result"]).all()
+    same = got["n_steps"] == ref["n_steps"]
+    assert same.mean() >= 0.95  # (hundreds of steps at this tolerance: an ulp decides an accept here and there)
+    scale = np.abs(ref["dy_end"]).max(0) + 1e-300
+    # (tangents of these unstable flows amplify the last-bit differences between the two implementations)
+    assert (np.abs(got["dy_end"] - ref["dy_end"]).max(0) / scale)[same].max() <= 1e-4
+    eps = 1e-6
+    a = O.solve_batch(oracle_problem(name), as_oracle_opts(opts), y + eps * dy)["y_end"]
+    b = O.solve_batch(oracle_problem(name), as_oracle_opts(opts), y - eps * dy)["y_end"]
+    fd = (a - b) / (2 * eps)
+    rel = np.abs(got["dy_end"] - fd).max(0) / (np.abs(fd).max(0) + 1e-300)
+    assert np.median(rel) <= 1e-4 and np.percentile(rel, 95) <= 5e-3, np.percentile(rel, [50, 95, 100])
+
+
+def test_reparam_solver_jacobian_public_api():
+    """make_pontryagin_solver_reparam(...).jvp / .jacobian: d x(v1) / d theta for the terminal circle of experiment_orbits.py:166-197
+    against a finite difference in theta of the solver itself at a tight tolerance."""
+    import scipy.linalg
+    import torch
+    from approximate_optimal_control_b200 import pontryagin_utils as pu, systems
+    from common import orbits_P0
+    pp = systems.orbits_problem_params()
+    ap = {"pontryagin_solver_dt": 1 / 64, "pontryagin_solver_adaptive": True, "pontryagin_solver_rtol": 1e-10,
+          "pontryagin_solver_atol": 1e-10, "pontryagin_solver_maxsteps": 4096, "dtype": "float64"}
+    solver = pu.make_pontryagin_solver_reparam(pp, ap)
+    P0, xf = orbits_P0(), np.array([0.0, 1.0])
+    Sinv = np.linalg.inv(scipy.linalg.sqrtm(P0))
+
+    def y0_of(theta):
+        x0 = 0.01 * Sinv @ np.array([np.sin(theta), np.cos(theta)]) + xf
+        return np.concatenate([x0, 2 * P0 @ (x0 - xf), np.zeros(1)])
+
+    def dy0_of(theta):
+        dx0 = 0.01 * Sinv @ np.array([np.cos(theta), -np.sin(theta)])
+        return np.concatenate([dx0, 2 * P0 @ dx0, np.zeros(1)])
+
+    thetas = np.linspace(0.1, 6.0, 17)
+    v0 = float((y0_of(0.3)[:2] - xf) @ P0 @ (y0_of(0.3)[:2] - xf))
+    v1 = 1.0
+    Y0 = np.stack([y0_of(t) for t in thetas])
+    D0 = np.stack([dy0_of(t) for t in thetas])
+    y1, dy1 = solver.jvp(Y0, v0, v1, D0)
+    eps = 1e-6
+    yp = solver(np.stack([y0_of(t + eps) for t in thetas]), v0, v1, save_steps=False).y_end
+    ym = solver(np.stack([y0_of(t - eps) for t in thetas]), v0, v1, save_steps=False).y_end
+    fd = ((yp["x"] - ym["x"]) / (2 * eps)).cpu().numpy()
+    got = dy1[:, :2].cpu().numpy()
+    # Where the input saturates along the characteristic (|u*| = 0.2) the Jacobian of the field jumps, and the tangent of
+    # the step that straddles the switch carries an O(h) error -- in jax's differentiated diffrax steps just the same; the
+    # finite difference of two converged solves does not.  Hence: tight agreement in the median, percent-level at worst.
+    rel = np.abs(got - fd).max(1) / np.maximum(np.abs(fd).max(1), 1e-12)
+    assert np.median(rel) <= 2e-3 and rel.max() <= 5e-2, (np.median(rel), rel.max())
+    J = solver.jacobian(Y0[3], v0, v1)
+    assert J.shape == (5, 5) and torch.allclose(J @ torch.as_tensor(D0[3], device=J.device), dy1[3], rtol=1e-8, atol=1e-10)
+    single = solver.jvp(Y0[3], v0, v1, D0[3])
+    assert single[1].shape == (5,) and torch.allclose(single[1], dy1[3])
+
+
 # ---- edge cases ---------------------------------------------------------------------------------------
 def test_nan_terminal_states_retire_immediately():
     """levelsets.py:1233 feeds NaN terminal states on purpose; they must not hang or poison neighbours."""
