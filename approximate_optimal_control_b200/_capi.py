@@ -109,7 +109,7 @@ def load(path: str) -> C.CDLL:
     L.pmp_solve_host_plan.argtypes = [C.POINTER(Problem), C.POINTER(Opts), C.c_int64, C.c_int32, C.POINTER(C.c_int32),
                                       C.POINTER(C.c_int32)]
     L.pmp_host_release.argtypes = []
-    if hasattr(L, "pmp_select_count_cuda"):  # (the main library; plug-ins do not carry the selection kernels)
+    if True:
         L.pmp_select_count_cuda.argtypes = [C.c_int32, C.c_int64, C.c_int32, C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p,
                                             C.c_double, C.c_double, C.c_double, C.c_void_p, C.c_void_p]
         L.pmp_select_write_cuda.argtypes = [C.c_int32, C.c_int64, C.c_int32, C.c_int32] + [C.c_void_p] * 5 + [C.c_int32, C.c_void_p,

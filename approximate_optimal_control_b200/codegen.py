@@ -36,7 +36,7 @@ __all__ = ["derive", "emit_header", "build_plugin", "plugin_problem", "Derived",
 
 _PKG = os.path.dirname(os.path.abspath(__file__))
 PLUGIN_DIR = os.path.join(_PKG, "plugins")
-PLUGIN_SOURCES = ["pmp_capi.cu", "pmp_host.cu", "pmp_eval.cu", "pmp_interp.cu", "pmp_forward.cu", "pmp_forward_nn.cu", "pmp_forward_cluster.cu", "pmp_sens.cu", "pmp_sys_generated.cu"]
+PLUGIN_SOURCES = ["pmp_capi.cu", "pmp_host.cu", "pmp_eval.cu", "pmp_select.cu", "pmp_interp.cu", "pmp_forward.cu", "pmp_forward_nn.cu", "pmp_forward_cluster.cu", "pmp_sens.cu", "pmp_sys_generated.cu"]
 MAX_NX = 16
 
 
@@ -247,11 +247,11 @@ template <class R> struct Generated {{
     static __device__ __forceinline__ R gsin(R a) {{ R s, c; M::sincos(a, &s, &c); return s; }}
     static __device__ __forceinline__ R gcos(R a) {{ R s, c; M::sincos(a, &s, &c); return c; }}
     static __device__ __forceinline__ R gtan(R a) {{ R s, c; M::sincos(a, &s, &c); return M::div(s, c); }}
-    static __device__ __forceinline__ R gexp(R a) {{ return ::exp(a); }}
-    static __device__ __forceinline__ R glog(R a) {{ return ::log(a); }}
-    static __device__ __forceinline__ R gtanh(R a) {{ return ::tanh(a); }}
-    static __device__ __forceinline__ R gatan2(R a, R b) {{ return ::atan2(a, b); }}
-    static __device__ __forceinline__ R gpow(R a, R b) {{ return ::pow(a, b); }}
+    static __device__ __forceinline__ R gexp(R a) {{ return fx::exp(a); }}
+    static __device__ __forceinline__ R glog(R a) {{ return fx::log(a); }}
+    static __device__ __forceinline__ R gtanh(R a) {{ return fx::tanh(a); }}
+    static __device__ __forceinline__ R gatan2(R a, R b) {{ return fx::atan2(a, b); }}
+    static __device__ __forceinline__ R gpow(R a, R b) {{ return fx::pow(a, b); }}
 
     // u* = argmin_u H over the box.  MODE & 2: KKT selection (integrator default), else the literal two-pass form
     template <int MODE>

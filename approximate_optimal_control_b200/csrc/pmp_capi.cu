@@ -308,7 +308,6 @@ int pmp_solve_host_plan(const pmp_problem_t* p, const pmp_opts_t* o, int64_t n, 
     return pieces;
 }
 
-#ifndef PMP_PLUGIN
 int pmp_select_count_cuda(int32_t dtype, int64_t n, int32_t s1, const void* v, const void* vxx, int32_t nvxx, const int32_t* n_accepted,
                           double v_lower, double v_upper, double vxx_max_norm, int32_t* counts, void* cuda_stream) {
     if (dtype != PMP_F32 && dtype != PMP_F64) return fail(PMP_ERR_BAD_ARG, "dtype");
@@ -330,7 +329,6 @@ int pmp_select_write_cuda(int32_t dtype, int64_t n, int32_t s1, int32_t nx, cons
                                vxx_max_norm, x_out, t_out, v_out, vx_out, vxx_out, stats, flags, (cudaStream_t)cuda_stream);
     return rc ? cuda_fail(rc) : PMP_OK;
 }
-#endif
 
 int pmp_host_probe_copy(void* dst, const void* src, int64_t bytes, int32_t blocks, void* cuda_stream) {
     if (!dst || !src || bytes < 0 || (bytes & 15) || blocks < 1) return fail(PMP_ERR_BAD_ARG, "probe copy: 16-byte multiples, blocks >= 1");

@@ -212,6 +212,25 @@ template <class R> struct SolveIO {
     long long n;
 };
 
+// ---- elementary functions the generated functors (codegen.py) may call, one overload set per scalar type (pmp_sens.cuh adds
+// the dual-number overloads, so that a generated system differentiates like a hand-written one)
+namespace fx {
+__device__ __forceinline__ float exp(float x) { return ::expf(x); }
+__device__ __forceinline__ double exp(double x) { return ::exp(x); }
+__device__ __forceinline__ float log(float x) { return ::logf(x); }
+__device__ __forceinline__ double log(double x) { return ::log(x); }
+__device__ __forceinline__ float tanh(float x) { return ::tanhf(x); }
+__device__ __forceinline__ double tanh(double x) { return ::tanh(x); }
+__device__ __forceinline__ float atan2(float a, float b) { return ::atan2f(a, b); }
+__device__ __forceinline__ double atan2(double a, double b) { return ::atan2(a, b); }
+__device__ __forceinline__ float pow(float a, float b) { return ::powf(a, b); }
+__device__ __forceinline__ double pow(double a, double b) { return ::pow(a, b); }
+}  // namespace fx
+
+}  // namespace pmp
+#include "pmp_dual.cuh"
+namespace pmp {
+
 // ---- pmp_solve_host's persistent launch (csrc/pmp_host.cu) -------------------------------------------------------
 // ONE launch of the integrator serves the whole host batch while the copy engines are still delivering it: the
 // kernel reads the reference's state-dict leaves (array of structs, as they lie in host memory) straight from the

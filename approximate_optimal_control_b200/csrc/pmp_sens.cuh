@@ -10,42 +10,9 @@
 // controller sees values only, so the primal part of the result is the solve the integrator itself produces.
 // One thread per trajectory (this is not the throughput path: the caller differentiates a few thousand characteristics).
 #pragma once
-#include "pmp_solve.cuh"
+#include "pmp_solve.cuh"  // (Dual<R> itself lives in pmp_dual.cuh, included by pmp_common.cuh)
 
 namespace pmp {
-
-template <class R> struct Dual {
-    R v, d;
-    __host__ __device__ Dual() {}
-    template <class T> __host__ __device__ Dual(T x) : v(R(x)), d(R(0)) {}
-    __host__ __device__ Dual(R x, R dx) : v(x), d(dx) {}
-};
-template <class R> __host__ __device__ __forceinline__ Dual<R> operator+(Dual<R> a, Dual<R> b) { return Dual<R>(a.v + b.v, a.d + b.d); }
-template <class R> __host__ __device__ __forceinline__ Dual<R> operator-(Dual<R> a, Dual<R> b) { return Dual<R>(a.v - b.v, a.d - b.d); }
-template <class R> __host__ __device__ __forceinline__ Dual<R> operator*(Dual<R> a, Dual<R> b) { return Dual<R>(a.v * b.v, a.d * b.v + a.v * b.d); }
-template <class R> __host__ __device__ __forceinline__ Dual<R> operator-(Dual<R> a) { return Dual<R>(-a.v, -a.d); }
-template <class R> __host__ __device__ __forceinline__ Dual<R>& operator+=(Dual<R>& a, Dual<R> b) { a = a + b; return a; }
-template <class R> __host__ __device__ __forceinline__ Dual<R>& operator-=(Dual<R>& a, Dual<R> b) { a = a - b; return a; }
-template <class R> __host__ __device__ __forceinline__ Dual<R>& operator*=(Dual<R>& a, Dual<R> b) { a = a * b; return a; }
-#define PMP_DUAL_MIXED(op)                                                                                                   \
-    template <class R, class T> __host__ __device__ __forceinline__ auto operator op(Dual<R> a, T b)->decltype(R(b), Dual<R>()) { return a op Dual<R>(b); } \
-    template <class R, class T> __host__ __device__ __forceinline__ auto operator op(T a, Dual<R> b)->decltype(R(a), Dual<R>()) { return Dual<R>(a) op b; }
-PMP_DUAL_MIXED(+)
-PMP_DUAL_MIXED(-)
-PMP_DUAL_MIXED(*)
-#undef PMP_DUAL_MIXED
-// decisions look at values
-#define PMP_DUAL_CMP(op)                                                                                                      \
-    template <class R> __host__ __device__ __forceinline__ bool operator op(Dual<R> a, Dual<R> b) { return a.v op b.v; }       \
-    template <class R, class T> __host__ __device__ __forceinline__ auto operator op(Dual<R> a, T b)->decltype(R(b), bool()) { return a.v op R(b); } \
-    template <class R, class T> __host__ __device__ __forceinline__ auto operator op(T a, Dual<R> b)->decltype(R(a), bool()) { return R(a) op b.v; }
-PMP_DUAL_CMP(<)
-PMP_DUAL_CMP(>)
-PMP_DUAL_CMP(<=)
-PMP_DUAL_CMP(>=)
-PMP_DUAL_CMP(==)
-PMP_DUAL_CMP(!=)
-#undef PMP_DUAL_CMP
 
 template <class R> struct Math<Dual<R>> {
     using D = Dual<R>;
@@ -79,18 +46,6 @@ template <class R> struct Math<Dual<R>> {
     static __device__ __forceinline__ V2 mul2v(V2 c, V2 a) { return mk2(c.x * a.x, c.y * a.y); }
     static __device__ __forceinline__ V2 add2(D c, V2 a) { return mk2(c + a.x, c + a.y); }
 };
-// the generated functors call exp / log / tanh / atan2 / pow by their global names
-template <class R> __device__ __forceinline__ Dual<R> exp(Dual<R> x) { const R e = ::exp(x.v); return Dual<R>(e, e * x.d); }
-template <class R> __device__ __forceinline__ Dual<R> log(Dual<R> x) { return Dual<R>(::log(x.v), x.d / x.v); }
-template <class R> __device__ __forceinline__ Dual<R> tanh(Dual<R> x) { const R t = ::tanh(x.v); return Dual<R>(t, (R(1) - t * t) * x.d); }
-template <class R> __device__ __forceinline__ Dual<R> atan2(Dual<R> a, Dual<R> b) {
-    return Dual<R>(::atan2(a.v, b.v), (b.v * a.d - a.v * b.d) / (a.v * a.v + b.v * b.v));
-}
-template <class R> __device__ __forceinline__ Dual<R> pow(Dual<R> a, Dual<R> b) {
-    const R p = ::pow(a.v, b.v);
-    return Dual<R>(p, p * (b.v * a.d / a.v + (b.d != R(0) ? ::log(a.v) * b.d : R(0))));
-}
-
 // PairMap of the underlying system (the pairing is a property of the dynamics, not of the scalar)
 template <class R> struct PairMap<Flatquad<Dual<R>>> : PairMap<Flatquad<R>> {};
 

@@ -242,8 +242,7 @@ int pmp_solve_jvp_cuda(const pmp_problem_t *problem, const pmp_opts_t *opts, int
                        void *cuda_stream);
 
 /* ---- data selection after the solve: select_train_pts (levelsets.py:667-709) + data_normaliser statistics
- * (nn_utils.py:112-134) on the device-resident SaveAt(steps) buffers of pmp_solve_batch_cuda (save_dense).  Not exported by
- * codegen plug-ins (nothing here depends on the dynamics).
+ * (nn_utils.py:112-134) on the device-resident SaveAt(steps) buffers of pmp_solve_batch_cuda (save_dense).
  * Pass 1: counts[i] = number of saved nodes of trajectory i with v_lower <= v <= v_upper (and ||vxx||_F < vxx_max_norm when
  * vxx != NULL; nvxx = nx*nx).  n_accepted (optional) bounds the slots read to 0..n_accepted[i]; padding never passes the
  * test anyway.  v [n][s1], vxx [n][s1][nvxx]. */

@@ -166,3 +166,40 @@ def test_new_system_trajectories_vs_scipy(mk, T):
     # dense output of the generated system through the same interpolation kernel
     mid = sol.evaluate(torch.full((8,), -0.5 * T, dtype=torch.float64, device="cuda"))
     assert mid["x"].shape == (8, nx) and bool(torch.isfinite(mid["x"]).all())
+
+
+@pytest.mark.parametrize("mk,term,kw", [
+    (systems.orbits_problem_params, orbits_terminal, dict(indep=_capi.INDEP_VALUE, t0=0.0, t1=1.0, dt0=1 / 64)),
+    (CS.pendulum_problem_params, None, dict(t0=0.0, t1=-1.0, dt0=-0.05))])
+def test_generated_systems_differentiate_like_handwritten_ones(mk, term, kw):
+    """pmp_solve_jvp_cuda on GENERATED functors (dual numbers through the sympy-derived code, exp / tanh included): equal to
+    the hand-written functor's tangents where one exists, and to central finite differences of the solve otherwise."""
+    import torch
+    prob, pp = generated(mk)
+    n = 128
+    rng = np.random.Generator(np.random.PCG64(5))
+    if term is not None:
+        y = term(n)
+    else:
+        y = np.concatenate([rng.uniform(-0.5, 0.5, (2, n)), np.zeros((1, n)), np.full((1, n), 0.1), rng.uniform(-0.5, 0.5, (2, n))], 0)
+    dy = rng.standard_normal(y.shape)
+    dy[prob.nx] = 0.0
+    if kw.get("indep") == _capi.INDEP_VALUE:
+        dy[prob.nx + 1] = 0.0
+    opts = _capi.make_opts(method="tsit5", dtype=_capi.F64, rtol=1e-9, atol=1e-9, max_steps=4096, dtmin=0.0, dtmax=0.0, **kw)
+    yd, dyd = (torch.as_tensor(a, device="cuda").contiguous() for a in (y, dy))
+    got = {k: v.cpu().numpy() for k, v in pu.solve_jvp_soa(prob, opts, yd, dyd).items()}
+    assert (got["result"] == 0).all()
+    if term is not None:  # same dynamics, hand-written
+        from common import c_problem
+        hand = {k: v.cpu().numpy() for k, v in pu.solve_jvp_soa(c_problem("orbits")[0], opts, yd, dyd).items()}
+        same = hand["n_steps"] == got["n_steps"]
+        assert same.mean() >= 0.95
+        scale = np.abs(hand["dy_end"]).max(0) + 1e-300
+        assert (np.abs(got["dy_end"] - hand["dy_end"]).max(0) / scale)[same].max() <= 1e-4
+    eps = 1e-6
+    a = cuda_solve(prob, opts, y + eps * dy)["y_end"]
+    b = cuda_solve(prob, opts, y - eps * dy)["y_end"]
+    fd = (a - b) / (2 * eps)
+    rel = np.abs(got["dy_end"] - fd).max(0) / (np.abs(fd).max(0) + 1e-300)
+    assert np.median(rel) <= 1e-4 and np.percentile(rel, 90) <= 2e-2, np.percentile(rel, [50, 90, 100])
