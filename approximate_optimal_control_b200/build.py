@@ -19,7 +19,7 @@ _ROOT = os.path.dirname(_PKG)
 LIB_PATH = os.path.join(_PKG, "libb200pmp.so")
 _OBJ_DIR = os.path.join(_PKG, "build")
 
-SOURCES = ["pmp_capi.cu", "pmp_host.cu", "pmp_eval.cu", "pmp_select.cu", "pmp_sens.cu", "pmp_interp.cu", "pmp_forward.cu", "pmp_forward_nn.cu", "pmp_forward_cluster.cu", "pmp_sys_flatquad.cu", "pmp_sys_flatquad_vxx.cu", "pmp_sys_orbits.cu", "pmp_sys_lqr.cu"]
+SOURCES = ["pmp_capi.cu", "pmp_host.cu", "pmp_eval.cu", "pmp_select.cu", "pmp_gather.cu", "pmp_sens.cu", "pmp_interp.cu", "pmp_forward.cu", "pmp_forward_nn.cu", "pmp_forward_cluster.cu", "pmp_sys_flatquad.cu", "pmp_sys_flatquad_vxx.cu", "pmp_sys_orbits.cu", "pmp_sys_lqr.cu"]
 HEADERS = ["pmp_hostq.h", "pmp_common.cuh", "pmp_systems.cuh", "pmp_tableau.cuh", "pmp_solve.cuh", "pmp_interp.cuh", "pmp_forward.cuh", "pmp_forward_cluster.cuh", "pmp_ustar2d.cuh", "pmp_sens.cuh", "pmp_dual.cuh"]
 
 NVCC_FLAGS = [
@@ -50,8 +50,12 @@ def _stale() -> bool:
     return os.path.getmtime(LIB_PATH) < max(os.path.getmtime(d) for d in deps)
 
 
+LAST_BUILD = {"mode": None, "units": []}  # what the last build() call did (printed by __graft_entry__.build)
+
+
 def build(force: bool = False, verbose: bool = False) -> str:
     if not force and not _stale():
+        LAST_BUILD.update(mode="up to date (prebuilt library newer than every source)", units=[])
         return LIB_PATH
     os.makedirs(_OBJ_DIR, exist_ok=True)
     nvcc = _nvcc()
@@ -73,10 +77,11 @@ def build(force: bool = False, verbose: bool = False) -> str:
 
     with cf.ThreadPoolExecutor(max_workers=len(SOURCES)) as ex:
         objs = list(ex.map(compile_one, SOURCES))
-    link = [nvcc, "-shared", "-ccbin", host, "-gencode", "arch=compute_100a,code=sm_100a", "-o", LIB_PATH, *objs]
+    link = [nvcc, "-shared", "-ccbin", host, "-gencode", "arch=compute_100a,code=sm_100a", "-o", LIB_PATH, *objs, "-ldl"]
     r = subprocess.run(link, capture_output=True, text=True, env=env)
     if r.returncode != 0:
         raise RuntimeError(f"link failed:\n{r.stdout}\n{r.stderr}")
+    LAST_BUILD.update(mode="compiled with " + " ".join([os.path.basename(nvcc), *NVCC_FLAGS]), units=list(SOURCES))
     return LIB_PATH
 
 

@@ -36,7 +36,7 @@ __all__ = ["derive", "emit_header", "build_plugin", "plugin_problem", "Derived",
 
 _PKG = os.path.dirname(os.path.abspath(__file__))
 PLUGIN_DIR = os.path.join(_PKG, "plugins")
-PLUGIN_SOURCES = ["pmp_capi.cu", "pmp_host.cu", "pmp_eval.cu", "pmp_select.cu", "pmp_interp.cu", "pmp_forward.cu", "pmp_forward_nn.cu", "pmp_forward_cluster.cu", "pmp_sens.cu", "pmp_sys_generated.cu"]
+PLUGIN_SOURCES = ["pmp_capi.cu", "pmp_host.cu", "pmp_eval.cu", "pmp_select.cu", "pmp_gather.cu", "pmp_interp.cu", "pmp_forward.cu", "pmp_forward_nn.cu", "pmp_forward_cluster.cu", "pmp_sens.cu", "pmp_sys_generated.cu"]
 MAX_NX = 16
 
 
@@ -318,7 +318,7 @@ def build_plugin(problem_params: dict, force: bool = False, verbose: bool = Fals
     with cf.ThreadPoolExecutor(max_workers=len(PLUGIN_SOURCES)) as ex:
         objs = list(ex.map(compile_one, PLUGIN_SOURCES))
     tmp = lib_path + f".tmp{os.getpid()}"
-    r = subprocess.run([nvcc, "-shared", "-ccbin", host, "-gencode", "arch=compute_100a,code=sm_100a", "-o", tmp, *objs],
+    r = subprocess.run([nvcc, "-shared", "-ccbin", host, "-gencode", "arch=compute_100a,code=sm_100a", "-o", tmp, *objs, "-ldl"],
                        capture_output=True, text=True)
     if r.returncode != 0:
         raise RuntimeError(f"codegen: link failed:\n{r.stdout}\n{r.stderr}")

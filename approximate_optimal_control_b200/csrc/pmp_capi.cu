@@ -37,6 +37,10 @@ int solve_host(const pmp_problem_t& p, const pmp_opts_t& o, long long n, const v
                int32_t* result, int n_pieces, const double* term_P, const double* term_xeq);
 int host_plan(long long n, int n_pieces, std::vector<long long>* bounds, long long* cs_max);
 int host_release();
+int comm_unique_id(void* id128, std::string* msg);
+int comm_init(void** comm, int world, int rank, const void* id128, std::string* msg);
+int comm_destroy(void* comm, std::string* msg);
+int allgather(void* comm, const void* local, void* global, size_t count, int dtype, cudaStream_t st, std::string* msg);
 int solve_jvp(const pmp_problem_t& p, const pmp_opts_t& o, long long n, const void* y_f, const void* dy_f, void* y_end, void* dy_end,
               int32_t* a, int32_t* s, int32_t* r, cudaStream_t st);
 int select_count(int dtype, long long n, int s1, const void* v, const void* vxx, int nvxx, const int32_t* n_accepted, double lo,
@@ -328,6 +332,37 @@ int pmp_select_write_cuda(int32_t dtype, int64_t n, int32_t s1, int32_t nx, cons
     int rc = pmp::select_write(dtype, n, s1, nx, x, t, v, vx, vxx, nvxx, n_accepted, (const long long*)offsets, v_lower, v_upper,
                                vxx_max_norm, x_out, t_out, v_out, vx_out, vxx_out, stats, flags, (cudaStream_t)cuda_stream);
     return rc ? cuda_fail(rc) : PMP_OK;
+}
+
+int pmp_comm_unique_id(void* id128) {
+    if (!id128) return fail(PMP_ERR_BAD_ARG, "id128 is NULL");
+    std::string msg;
+    if (pmp::comm_unique_id(id128, &msg)) return fail(PMP_ERR_UNSUPPORTED, msg.c_str());
+    return PMP_OK;
+}
+
+int pmp_comm_init(void** comm, int32_t world, int32_t rank, const void* id128) {
+    if (!comm || !id128 || world < 1 || rank < 0 || rank >= world) return fail(PMP_ERR_BAD_ARG, "comm / id128 / world / rank");
+    std::string msg;
+    if (pmp::comm_init(comm, world, rank, id128, &msg)) return fail(PMP_ERR_UNSUPPORTED, msg.c_str());
+    return PMP_OK;
+}
+
+int pmp_comm_destroy(void* comm) {
+    if (!comm) return PMP_OK;
+    std::string msg;
+    if (pmp::comm_destroy(comm, &msg)) return fail(PMP_ERR_UNSUPPORTED, msg.c_str());
+    return PMP_OK;
+}
+
+int pmp_allgather_endpoints(void* comm, const void* local, void* global, int64_t n_local, int32_t rows, int32_t dtype, void* cuda_stream) {
+    if (!comm || n_local < 0 || rows < 1 || (dtype != PMP_F32 && dtype != PMP_F64)) return fail(PMP_ERR_BAD_ARG, "comm / n_local / rows / dtype");
+    if (n_local == 0) return PMP_OK;
+    if (!local || !global) return fail(PMP_ERR_BAD_ARG, "local / global is NULL");
+    std::string msg;
+    if (pmp::allgather(comm, local, global, (size_t)n_local * (size_t)rows, dtype, (cudaStream_t)cuda_stream, &msg))
+        return fail(PMP_ERR_UNSUPPORTED, msg.c_str());
+    return PMP_OK;
 }
 
 int pmp_host_probe_copy(void* dst, const void* src, int64_t bytes, int32_t blocks, void* cuda_stream) {

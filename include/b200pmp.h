@@ -231,6 +231,20 @@ int pmp_host_release(void);
  * the copy engines (scripts/pcie_probe.py).  bytes must be a multiple of 16.  Asynchronous on cuda_stream. */
 int pmp_host_probe_copy(void *dst, const void *src, int64_t bytes, int32_t blocks, void *cuda_stream);
 
+/* ---- multi-GPU: one process per GPU, terminal samples sharded by index, no exchange during the solve, then ONE all-gather of
+ * the endpoint records so that every rank holds the whole (x, t, v, lambda) dataset for the value fit.
+ * NCCL behind plain C entries (resolved with dlopen at the first call: no link-time dependency), for hosts that are not
+ * PyTorch.  Bootstrap as with NCCL itself: rank 0 calls pmp_comm_unique_id, ships the 128 bytes to the other ranks by any
+ * means (MPI, a file, jax.distributed), every rank -- its CUDA device current -- calls pmp_comm_init.
+ * pmp_allgather_endpoints: local [rows][n_local] (this rank's y_end) -> global [world][rows][n_local] on every rank,
+ * rank-major; asynchronous on cuda_stream.  (PyTorch hosts have sharding.PipelinedGather, which hides the transfer behind
+ * the next solve with peer-to-peer copies.) */
+int pmp_comm_unique_id(void *id128 /* 128 bytes, host */);
+int pmp_comm_init(void **comm, int32_t world, int32_t rank, const void *id128);
+int pmp_comm_destroy(void *comm);
+int pmp_allgather_endpoints(void *comm, const void *local, void *global, int64_t n_local, int32_t rows, int32_t dtype,
+                            void *cuda_stream);
+
 /* Forward-mode sensitivity of a solve: endpoint AND its directional derivative along dy_f, d y_end / d y_f . dy_f, for n
  * trajectories (y_f, dy_f, y_end, dy_end [NS][n]).  Replaces jax.jacobian / jvp through diffrax.diffeqsolve
  * (experiment_orbits.py:186-197 differentiates the value-parameterised solve, indep = PMP_INDEP_VALUE, with respect to the

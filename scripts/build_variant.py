@@ -23,7 +23,7 @@ if r.returncode:
 print("\n".join(l for l in r.stderr.splitlines() if "spill" in l and " 0 bytes spill stores" not in l)[:2000])
 objs = [obj if s == unit else os.path.join(B._OBJ_DIR, s.replace(".cu", ".o")) for s in B.SOURCES]
 lib = os.path.join(out_dir, f"lib_{tag}.so")
-r = subprocess.run([B._nvcc(), "-shared", "-ccbin", host, "-gencode", "arch=compute_100a,code=sm_100a", "-o", lib, *objs],
+r = subprocess.run([B._nvcc(), "-shared", "-ccbin", host, "-gencode", "arch=compute_100a,code=sm_100a", "-o", lib, *objs, "-ldl"],
                    capture_output=True, text=True)
 if r.returncode:
     sys.exit(r.stderr)

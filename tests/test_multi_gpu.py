@@ -54,6 +54,25 @@ def _worker(rank, world, port, n_local, q):
         torch.cuda.synchronize()
         for tag, g, r in (("a", got_a, refs[0]), ("b", got_b, refs[1]), ("c", got_c, refs[2])):
             res[(transport, "nowait", tag)] = bool(torch.equal(g.permute(1, 0, 2).reshape(14, n), r))
+    # the C-ABI gather (pmp_comm_* / pmp_allgather_endpoints: NCCL without torch in the data path); the 128-byte id travels
+    # through torch.distributed here only because the test already has it
+    import ctypes as C
+    L = _capi.lib()
+    idbuf = (C.c_char * 128)()
+    if rank == 0:
+        _capi.check(L.pmp_comm_unique_id(idbuf))
+    idt = torch.frombuffer(bytearray(idbuf.raw), dtype=torch.uint8).to(dev)
+    dist.broadcast(idt, 0)
+    idbuf = (C.c_char * 128).from_buffer_copy(bytes(idt.cpu().numpy().tobytes()))
+    comm = C.c_void_p()
+    _capi.check(L.pmp_comm_init(C.byref(comm), world, rank, idbuf))
+    local = pu.solve_batch_soa(prob, opts, locs[0])["y_end"].contiguous()
+    glob = torch.empty((world, 14, n_local), dtype=torch.float64, device=dev)
+    _capi.check(L.pmp_allgather_endpoints(comm, local.data_ptr(), glob.data_ptr(), n_local, 14, _capi.F64,
+                                          C.c_void_p(torch.cuda.current_stream().cuda_stream)))
+    torch.cuda.synchronize()
+    res[("c_abi_nccl",)] = bool(torch.equal(glob.permute(1, 0, 2).reshape(14, n), refs[0]))
+    _capi.check(L.pmp_comm_destroy(comm))
     q.put((rank, res))
     dist.destroy_process_group()
 
