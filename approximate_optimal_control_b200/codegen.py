@@ -36,7 +36,7 @@ __all__ = ["derive", "emit_header", "build_plugin", "plugin_problem", "Derived",
 
 _PKG = os.path.dirname(os.path.abspath(__file__))
 PLUGIN_DIR = os.path.join(_PKG, "plugins")
-PLUGIN_SOURCES = ["pmp_capi.cu", "pmp_host.cu", "pmp_eval.cu", "pmp_select.cu", "pmp_gather.cu", "pmp_interp.cu", "pmp_forward.cu", "pmp_forward_nn.cu", "pmp_forward_cluster.cu", "pmp_sens.cu", "pmp_sys_generated.cu"]
+PLUGIN_SOURCES = ["pmp_capi.cu", "pmp_host.cu", "pmp_eval.cu", "pmp_select.cu", "pmp_gather.cu", "pmp_interp.cu", "pmp_forward.cu", "pmp_forward_nn.cu", "pmp_forward_cluster.cu", "pmp_forward_tc.cu", "pmp_sens.cu", "pmp_sys_generated.cu"]
 MAX_NX = 16
 
 
@@ -230,6 +230,7 @@ def emit_header(d: Derived, name: str = "user") -> str:
 // system '{name}': nx = {nx}, nu = {nu}; {n_u} + {n_r} common subexpressions.
 // sympy derivatives of the user's f(x,u), l(x,u) in place of jax autodiff (pontryagin_utils.py:35-38,438-439,541-550).
 #pragma once
+#define PMP_GEN_NX {nx}
 #define PMP_GEN_MINB32 {minb32}
 #define PMP_GEN_MINB64 {minb64}
 namespace pmp {{

@@ -552,6 +552,11 @@ template <class Sys, class R, int W>
 int launch_forward_cluster(const pmp_problem_t& p, const pmp_opts_t& o, long long n, const ForwardIO<R>& io,
                            const NnCostate<R, Sys::NX, W>& pol, cudaStream_t st);
 
+// fp32 ensembles of width 64: the layer products on the tensor cores (pmp_forward_tc.cuh; own compile unit pmp_forward_tc.cu)
+template <class Sys>
+int launch_forward_tc_entry(const pmp_problem_t& p, const pmp_opts_t& o, long long n, const ForwardIO<float>& io,
+                            const NnCostate<float, Sys::NX, 64>& pol, cudaStream_t st);
+
 template <template <class> class SysT, class R>
 int launch_forward_nn_r(const pmp_problem_t& p, const pmp_opts_t& o, long long n, const void* x0, const pmp_nn_costate_t* nn,
                         void* z_end, void* ts, void* xs, void* cost, int32_t* a, int32_t* s, int32_t* r, cudaStream_t st) {
@@ -573,6 +578,14 @@ int launch_forward_nn_r(const pmp_problem_t& p, const pmp_opts_t& o, long long n
     const bool use_cluster = nn->n_nets >= 2 && !(env && env[0] == '0');
     if (nn->width == 64) {
         NnCostate<R, NX, 64> pol; fill(pol);
+        if constexpr (std::is_same<R, float>::value && NX <= 8) {
+            // default for fp32: tensor-core kernel (3xTF32 split precision); B200PMP_NN_TC=0 selects the CUDA-core kernels
+            const char* tc = getenv("B200PMP_NN_TC");
+            if (!(tc && tc[0] == '0') && nn->n_hidden_layers >= 1 && nn->n_hidden_layers <= 3) {
+                const int rc = launch_forward_tc_entry<Sys>(p, o, n, io, pol, st);
+                if (rc != -1000) return rc;
+            }
+        }
         return use_cluster ? launch_forward_cluster<Sys, R, 64>(p, o, n, io, pol, st) : launch_forward_pol<Sys, R>(p, o, n, io, pol, st);
     }
     if (nn->width == 32) {
