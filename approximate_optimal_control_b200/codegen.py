@@ -36,7 +36,7 @@ __all__ = ["derive", "emit_header", "build_plugin", "plugin_problem", "Derived",
 
 _PKG = os.path.dirname(os.path.abspath(__file__))
 PLUGIN_DIR = os.path.join(_PKG, "plugins")
-PLUGIN_SOURCES = ["pmp_capi.cu", "pmp_host.cu", "pmp_eval.cu", "pmp_select.cu", "pmp_gather.cu", "pmp_interp.cu", "pmp_forward.cu", "pmp_forward_nn.cu", "pmp_forward_cluster.cu", "pmp_forward_tc.cu", "pmp_sens.cu", "pmp_sys_generated.cu"]
+PLUGIN_SOURCES = ["pmp_capi.cu", "pmp_host.cu", "pmp_eval.cu", "pmp_select.cu", "pmp_gather.cu", "pmp_interp.cu", "pmp_forward.cu", "pmp_forward_nn.cu", "pmp_forward_cluster.cu", "pmp_forward_tc.cu", "pmp_forward_umma.cu", "pmp_sens.cu", "pmp_sys_generated.cu"]
 MAX_NX = 16
 
 

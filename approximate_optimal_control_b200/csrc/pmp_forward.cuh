@@ -557,6 +557,11 @@ template <class Sys>
 int launch_forward_tc_entry(const pmp_problem_t& p, const pmp_opts_t& o, long long n, const ForwardIO<float>& io,
                             const NnCostate<float, Sys::NX, 64>& pol, cudaStream_t st);
 
+// the same on the 5th-generation tensor cores: tcgen05.mma, clusters of one CTA per member (pmp_forward_umma.cuh; pmp_forward_umma.cu)
+template <class Sys>
+int launch_forward_umma_entry(const pmp_problem_t& p, const pmp_opts_t& o, long long n, const ForwardIO<float>& io,
+                              const NnCostate<float, Sys::NX, 64>& pol, cudaStream_t st);
+
 template <template <class> class SysT, class R>
 int launch_forward_nn_r(const pmp_problem_t& p, const pmp_opts_t& o, long long n, const void* x0, const pmp_nn_costate_t* nn,
                         void* z_end, void* ts, void* xs, void* cost, int32_t* a, int32_t* s, int32_t* r, cudaStream_t st) {
@@ -579,8 +584,14 @@ int launch_forward_nn_r(const pmp_problem_t& p, const pmp_opts_t& o, long long n
     if (nn->width == 64) {
         NnCostate<R, NX, 64> pol; fill(pol);
         if constexpr (std::is_same<R, float>::value && NX <= 8) {
-            // default for fp32: tensor-core kernel (3xTF32 split precision); B200PMP_NN_TC=0 selects the CUDA-core kernels
+            // default for fp32: tensor-core kernels (3xTF32 split precision) -- tcgen05 clusters for up to 8 members
+            // (B200PMP_NN_UMMA=0 skips them), else warp-level MMAs; B200PMP_NN_TC=0 selects the CUDA-core kernels
             const char* tc = getenv("B200PMP_NN_TC");
+            const char* um = getenv("B200PMP_NN_UMMA");
+            if (!(tc && tc[0] == '0') && !(um && um[0] == '0') && nn->n_hidden_layers >= 1 && nn->n_hidden_layers <= 3) {
+                const int rc = launch_forward_umma_entry<Sys>(p, o, n, io, pol, st);
+                if (rc != -1000) return rc;
+            }
             if (!(tc && tc[0] == '0') && nn->n_hidden_layers >= 1 && nn->n_hidden_layers <= 3) {
                 const int rc = launch_forward_tc_entry<Sys>(p, o, n, io, pol, st);
                 if (rc != -1000) return rc;
