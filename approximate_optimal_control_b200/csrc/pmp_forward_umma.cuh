@@ -13,8 +13,11 @@
 //     a_hi.w_hi, fp32 accumulation: fp32 quality, scripts/tc_probe.cu: 2.4e-7 relative) and commits them to an mbarrier the
 //     CTA waits on.  With 256 threads the two halves of the CTA share a row: columns 0-31 / 32-63;
 //   * per right hand side: 1 + (L-1) forward products, L-1 backward products, the input gradient (N = 16), then the members'
-//     (gradient, value) meet through DISTRIBUTED SHARED MEMORY exactly as in the cluster kernel (two cluster barriers, sums in
-//     rank order: every CTA holds bit-identical costates and takes identical steps);
+//     (gradient, value) meet through DISTRIBUTED SHARED MEMORY: every CTA PUSHES its row results into a slot of every peer's
+//     exchange buffer (remote stores do not stall; remote loads cost ~1 us each and were 45 % of the kernel), ONE cluster
+//     barrier, then everybody adds up its local copy in rank order -- every CTA holds bit-identical costates and takes identical
+//     steps.  The buffer is double-buffered by evaluation parity, which makes the second barrier unnecessary: nobody can be
+//     two evaluations ahead of a peer;
 //   * slots are refilled from the cluster's queue as trajectories end (same rounds as the cluster kernel).
 // Tensor-memory map (columns, 128 lanes x 32 bit each): D 0-63 | A_hi 64-127 | A_lo 128-191 | softplus' of layer l at 192 + 64 l.
 #pragma once
@@ -41,8 +44,8 @@ struct UmLayout {
     __host__ __device__ int wout() const { return bias(L); }
     __host__ __device__ int bout() const { return wout() + kUmW; }
     __host__ __device__ int vpart() const { return bout() + 4; }          // [2][128] partial values of the two column halves
-    __host__ __device__ int xch() const { return vpart() + 256; }         // [NX + 1][128] exchange buffer (gradient, value)
-    __host__ __device__ int total(int NX) const { return xch() + (NX + 1) * 128; }
+    __host__ __device__ int xch() const { return vpart() + 256; }         // [2 parities][8 ranks][NX + 1][128] exchange buffer
+    __host__ __device__ int total(int NX) const { return xch() + 2 * 8 * (NX + 1) * 128; }
 };
 
 // what the law needs besides the state: lives in registers / constant bank of the caller
@@ -51,6 +54,8 @@ template <int NX> struct UmCtx {
     unsigned long long* bar;    // completion barrier of the tensor core
     uint32_t tbase;             // tensor memory base
     uint32_t phase;             // parity of the next completion
+    uint32_t xpar;              // parity of the next exchange
+    int rank;                   // this CTA's rank = its member
     int L, C, E;
     float x_mean[NX], x_scale[NX], g_scale[NX], v_mean, v_std;
 };
@@ -161,30 +166,47 @@ __device__ __noinline__ void um_law(UmCtx<NX>& c, const float* x, float* lam, fl
     uint32_t gx[8];
     tmem_ld8(lane_base + kUmColD, gx);
     tmem_wait_ld();
-    // ---- the members meet: (scaled gradient, value) per row through distributed shared memory, sums in rank order
-    float* xch = c.sm + lay.xch();
-    if (wg == 0) {
+    // ---- the members meet: push (scaled gradient, value) of this row into slot `rank` of every CTA's buffer, one barrier,
+    // then add up the local copy in rank order
+    constexpr int XS = (NX + 1) * 128;
+    float* xbuf = c.sm + lay.xch() + c.xpar * 8 * XS;
+    c.xpar ^= 1u;
+    {
+        float val[NX + 1];
 #pragma unroll
-        for (int q = 0; q < NX; q++) xch[q * 128 + r] = __uint_as_float(gx[q]) * c.g_scale[q];
-        xch[NX * 128 + r] = fmaf(c.v_std, v, c.v_mean);
+        for (int q = 0; q < NX; q++) val[q] = __uint_as_float(gx[q]) * c.g_scale[q];
+        val[NX] = fmaf(c.v_std, v, c.v_mean);
+        constexpr int PER = 8 / NWG;  // destination ranks served by one warpgroup
+#pragma unroll
+        for (int dd = 0; dd < PER; dd++) {
+            const int d = wg * PER + dd;
+            if (d < c.C) {
+                float* dst = cluster.map_shared_rank(xbuf + c.rank * XS, d);
+#pragma unroll
+                for (int q = 0; q <= NX; q++) dst[q * 128 + r] = val[q];
+            }
+        }
     }
     cluster.sync();
     float ve[8], sum = 0.0f;
 #pragma unroll
     for (int q = 0; q < NX; q++) lam[q] = 0.0f;
-    for (int rr = 0; rr < c.C; rr++) {
-        const float* rx = cluster.map_shared_rank(xch, rr);
 #pragma unroll
-        for (int q = 0; q < NX; q++) lam[q] += rx[q * 128 + r];
-        const float vv = rx[NX * 128 + r];
-        ve[rr] = vv;
-        sum += vv;
+    for (int rr = 0; rr < 8; rr++) {
+        ve[rr] = 0.0f;
+        if (rr < c.C) {
+#pragma unroll
+            for (int q = 0; q < NX; q++) lam[q] += xbuf[rr * XS + q * 128 + r];
+            ve[rr] = xbuf[rr * XS + NX * 128 + r];
+            sum += ve[rr];
+        }
     }
-    cluster.sync();  // every CTA has read every exchange buffer: they may be overwritten
     const float inv_e = __fdiv_rn(1.0f, (float)c.E);
     vmean = sum * inv_e;
     float var = 0.0f;
-    for (int rr = 0; rr < c.C; rr++) var = fmaf(ve[rr] - vmean, ve[rr] - vmean, var);
+#pragma unroll
+    for (int rr = 0; rr < 8; rr++)
+        if (rr < c.C) var = fmaf(ve[rr] - vmean, ve[rr] - vmean, var);
     vstd = sqrtf(var * inv_e);
 #pragma unroll
     for (int q = 0; q < NX; q++) lam[q] *= inv_e;
@@ -262,7 +284,7 @@ forward_umma_kernel(const typename Sys::Consts sc, const SolveOpts<float> o, con
     __syncthreads();
     tc_fence_after();
     UmCtx<NX> ctx;
-    ctx.sm = sm; ctx.bar = &s_bar; ctx.tbase = s_tmem; ctx.phase = 0u; ctx.L = L; ctx.C = C; ctx.E = pol.n_nets;
+    ctx.sm = sm; ctx.bar = &s_bar; ctx.tbase = s_tmem; ctx.phase = 0u; ctx.xpar = 0u; ctx.rank = rank; ctx.L = L; ctx.C = C; ctx.E = pol.n_nets;
 #pragma unroll
     for (int q = 0; q < NX; q++) {
         ctx.x_mean[q] = pol.x_mean[q]; ctx.x_scale[q] = pol.inv_x_std[q]; ctx.g_scale[q] = pol.v_std * pol.inv_x_std[q];
