@@ -188,18 +188,22 @@ __device__ __noinline__ void um_law(UmCtx<NX>& c, const float* x, float* lam, fl
         }
     }
     cluster.sync();
+    // (all loads first, unconditionally: slots of absent ranks hold stale bits that the selects below drop)
+    float got[8][NX + 1];
+#pragma unroll
+    for (int rr = 0; rr < 8; rr++)
+#pragma unroll
+        for (int q = 0; q <= NX; q++) got[rr][q] = xbuf[rr * XS + q * 128 + r];
     float ve[8], sum = 0.0f;
 #pragma unroll
     for (int q = 0; q < NX; q++) lam[q] = 0.0f;
 #pragma unroll
     for (int rr = 0; rr < 8; rr++) {
-        ve[rr] = 0.0f;
-        if (rr < c.C) {
+        const bool on = rr < c.C;
 #pragma unroll
-            for (int q = 0; q < NX; q++) lam[q] += xbuf[rr * XS + q * 128 + r];
-            ve[rr] = xbuf[rr * XS + NX * 128 + r];
-            sum += ve[rr];
-        }
+        for (int q = 0; q < NX; q++) lam[q] += on ? got[rr][q] : 0.0f;
+        ve[rr] = on ? got[rr][NX] : 0.0f;
+        sum += ve[rr];
     }
     const float inv_e = __fdiv_rn(1.0f, (float)c.E);
     vmean = sum * inv_e;

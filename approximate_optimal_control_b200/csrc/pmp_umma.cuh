@@ -83,6 +83,7 @@ __device__ __forceinline__ void mbar_init(unsigned long long* bar, uint32_t coun
 // spins until the phase with the given parity has completed; false after ~2^26 polls (a lost commit must not hang the GPU)
 __device__ __forceinline__ bool mbar_wait(unsigned long long* bar, uint32_t parity) {
     const uint32_t a = smem_u32(bar);
+#pragma unroll 1
     for (int spin = 0; spin < (1 << 26); spin++) {
         uint32_t ok;
         asm volatile(
@@ -97,6 +98,7 @@ __device__ __forceinline__ bool mbar_wait(unsigned long long* bar, uint32_t pari
 // the same with the non-suspending test_wait (lowest wake-up latency; the waiting warps have nothing else to do)
 __device__ __forceinline__ bool mbar_spin(unsigned long long* bar, uint32_t parity) {
     const uint32_t a = smem_u32(bar);
+#pragma unroll 1
     for (int spin = 0; spin < (1 << 26); spin++) {
         uint32_t ok;
         asm volatile(

@@ -24,13 +24,13 @@ __global__ void __launch_bounds__(128, 1) probe_kernel(const float* __restrict__
     __shared__ __align__(8) unsigned long long bar;
     __shared__ uint32_t tmem_slot;
     const int tid = threadIdx.x, warp = tid >> 5;
-    if (warp == 0) tmem_alloc(&tmem_slot, 256);
+    if (warp == 0) tmem_alloc(&tmem_slot, 512);
     if (tid == 0) mbar_init(&bar, 1);
     for (int q = tid; q < N * K; q += 128) {
         const int n = q / K, k = q - n * K;
         uint32_t hi, lo;
         split_tf32(Wt[q], hi, lo);
-        const int off = MN_MAJOR ? b_off_mn<N, K>(n, k) : b_off_k<N, K>(n, k);
+        const int off = b_off_k<N, K>(n, k);
         sB[off] = __uint_as_float(hi);
         sB[N * K + off] = __uint_as_float(lo);
     }
@@ -40,7 +40,7 @@ __global__ void __launch_bounds__(128, 1) probe_kernel(const float* __restrict__
     tc_fence_after();
     const uint32_t tbase = tmem_slot;
     const uint32_t lane_base = tbase + ((uint32_t)(32 * warp) << 16);
-    const uint32_t tD = 0, tAh = 64, tAl = 128;
+    const uint32_t tD = 0, tAh = 256, tAl = 320;
     uint32_t phase = 0;
     long long t_acc = 0;
     float arow[K];
@@ -67,9 +67,9 @@ __global__ void __launch_bounds__(128, 1) probe_kernel(const float* __restrict__
         long long m3 = m2;
         if (tid == 0) {
             tc_fence_after();
-            const uint32_t idesc = make_idesc_tf32(128, N, false, MN_MAJOR);
+            const uint32_t idesc = make_idesc_tf32(128, N);
             const uint32_t sb = smem_u32(sB);
-            issue_3xtf32<N, K, MN_MAJOR, SWAP>(tbase + tD, tbase + tAh, tbase + tAl, sb, sb + N * K * 4, idesc);
+            issue_3xtf32<N, K>(tbase + tD, tbase + tAh, tbase + tAl, sb, sb + N * K * 4, idesc);
             umma_commit(&bar);
             m3 = clock64();
         }
@@ -99,7 +99,7 @@ __global__ void __launch_bounds__(128, 1) probe_kernel(const float* __restrict__
     if (tid == 0) *cycles = t_acc / 4;
     if (keep == 12345.678f) D[0] = keep;
     __syncthreads();
-    if (warp == 0) tmem_dealloc(tbase, 256);
+    if (warp == 0) tmem_dealloc(tbase, 512);
 }
 
 template <int N, int K, bool MN, bool SWAP = false, bool SPIN = false>
@@ -149,7 +149,8 @@ int main() {
     bad += run<64, 64, false, false, true>("layer product, B K-major");
     bad += run<16, 64, false, false, true>("input gradient (N = 16), B K-major");
     bad += run<64, 8, false, false, true>("first layer (K = 8), B K-major");
-    run<64, 64, true>("layer product, B MN-major (does not work: kept as a record)");
+    bad += run<128, 64, false, false, true>("N = 128 (cost of a wider instruction)");
+    bad += run<256, 64, false, false, true>("N = 256 (cost of a wider instruction)");
     printf("%s\n", bad ? "PROBE FAILED" : "PROBE OK");
     return bad;
 }
