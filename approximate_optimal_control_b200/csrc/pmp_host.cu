@@ -18,6 +18,7 @@
 
 #include <cstdio>
 #include <cstdlib>
+#include <chrono>
 #include <vector>
 
 #include "../../include/b200pmp.h"
@@ -234,6 +235,9 @@ int solve_host_persistent(HostPipe& P, const pmp_problem_t& p, const pmp_opts_t&
                           void* v_end, void* vx_end, int32_t* n_accepted, int32_t* n_steps, int32_t* result, bool pack, bool trace,
                           const void* d_term) {
     const int n_pieces = (int)bounds.size() - 1;
+    const auto h0 = std::chrono::steady_clock::now();  // host clock of the trace
+    auto host_ms = [&]() { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - h0).count(); };
+    double h_launched = 0, h_enqueued = 0, h_synced = 0;
     WaitValue32Fn wait32 = wait_value32();
     if (!wait32 || n_pieces > kHostMaxPieces || o.indep != PMP_INDEP_TIME || o.flags != 0 || o.save_dense) return -1000;
     const int nx = p.nx;
@@ -313,6 +317,7 @@ int solve_host_persistent(HostPipe& P, const pmp_problem_t& p, const pmp_opts_t&
         if (rc) return drain(rc);
     }
     stamp(sc);  // (recorded when the kernel has finished)
+    h_launched = host_ms();
     const char *hx = (const char*)x_f, *hvx = (const char*)vx_f, *ht = (const char*)t_f, *hv = (const char*)v_f;
     PMP_TRY(cudaStreamWaitEvent(P.s_out, P.ev_ctrl, 0));
     long long group_min = 1;  // every piece its own group
@@ -357,6 +362,7 @@ int solve_host_persistent(HostPipe& P, const pmp_problem_t& p, const pmp_opts_t&
         }
         stamp(P.s_out);
     }
+    h_enqueued = host_ms();
     {
         int first = 0;
         for (int c : group_end) {
@@ -374,7 +380,10 @@ int solve_host_persistent(HostPipe& P, const pmp_problem_t& p, const pmp_opts_t&
     PMP_TRY(cudaStreamSynchronize(P.s_in));
     unsigned int aborted = 0;
     PMP_TRY(cudaMemcpy(&aborted, &ctrl->abort, 4, cudaMemcpyDeviceToHost));
+    h_synced = host_ms();
     if (trace) {
+        fprintf(stderr, "[pmp_solve_host] calling thread: kernel launched at %.3f ms, every copy enqueued at %.3f, all results on the host at %.3f\n",
+                h_launched, h_enqueued, h_synced);
         float t;
         cudaEventElapsedTime(&t, tev[0], tev[1]);
         fprintf(stderr, "[pmp_solve_host] persistent launch: integrator finished at %.3f ms\n", t);

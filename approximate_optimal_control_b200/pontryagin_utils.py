@@ -31,7 +31,7 @@ import scipy.linalg
 import torch
 
 from . import _capi, systems
-from .solution import Solution
+from .solution import Solution, StepStats
 
 __all__ = ["define_backward_solver", "u_star_2d", "u_star_new", "lqr", "get_terminal_lqr",
            "make_pontryagin_solver_reparam", "solve_batch_soa", "forward_batch_soa", "pack_state", "unpack_state"]
@@ -329,8 +329,7 @@ def _solve_host_lqr(problem, opts, nx, x_f, P_lqr, x_eq, dtype, dev, n_pieces=0)
                                          None if xe is None else xe.ctypes.data, ho["x"].data_ptr(), ho["t"].data_ptr(),
                                          ho["v"].data_ptr(), ho["vx"].data_ptr(), ho["n_accepted"].data_ptr(),
                                          ho["n_steps"].data_ptr(), ho["result"].data_ptr(), int(n_pieces)), L)
-    stats = {"num_steps": ho["n_steps"], "num_accepted_steps": ho["n_accepted"],
-             "num_rejected_steps": ho["n_steps"] - ho["n_accepted"]}
+    stats = StepStats(ho["n_steps"], ho["n_accepted"])
     return Solution(t0=opts.t0, t1=opts.t1, ts=None, ys=None, y_end={k: ho[k] for k in ("x", "t", "v", "vx")}, stats=stats,
                     result=ho["result"], batched=True)
 
@@ -373,8 +372,7 @@ def _solve_host_pipelined(problem, opts, nx, y_f, dtype, dev, n_pieces=0):
                                      v.data_ptr(), vx.data_ptr(), ho["x"].data_ptr(), ho["t"].data_ptr(), ho["v"].data_ptr(),
                                      ho["vx"].data_ptr(), ho["n_accepted"].data_ptr(), ho["n_steps"].data_ptr(),
                                      ho["result"].data_ptr(), int(n_pieces)), L)
-    stats = {"num_steps": ho["n_steps"], "num_accepted_steps": ho["n_accepted"],
-             "num_rejected_steps": ho["n_steps"] - ho["n_accepted"]}
+    stats = StepStats(ho["n_steps"], ho["n_accepted"])
     return Solution(t0=opts.t0, t1=opts.t1, ts=None, ys=None, y_end={k: ho[k] for k in ("x", "t", "v", "vx")}, stats=stats,
                     result=ho["result"], batched=True)
 

@@ -11,3 +11,17 @@ for _ in range(3):
     solve(host_in)
 os.environ["B200PMP_HOST_TRACE"] = "1"
 solve(host_in)
+import time
+os.environ.pop("B200PMP_HOST_TRACE")
+for _ in range(3):
+    solve(host_in)
+t = time.perf_counter()
+for _ in range(20):
+    solve(host_in)
+print(f"python call: {(time.perf_counter() - t) / 20 * 1e3:.3f} ms per 2^20", file=sys.stderr)
+import cProfile, pstats
+pr = cProfile.Profile(); pr.enable()
+for _ in range(20):
+    solve(host_in)
+pr.disable()
+pstats.Stats(pr, stream=sys.stderr).sort_stats("tottime").print_stats(12)
