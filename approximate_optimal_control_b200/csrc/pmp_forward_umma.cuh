@@ -60,11 +60,27 @@ template <int NX> struct UmCtx {
     float x_mean[NX], x_scale[NX], g_scale[NX], v_mean, v_std;
 };
 
-__device__ __forceinline__ void um_act(float a, float& sp, float& sg) {  // softplus and its derivative (MUFU ex2 / lg2 / rcp)
-    const float e = __expf(-fabsf(a));
-    const float d = __fdividef(1.0f, 1.0f + e);
-    sp = fmaxf(a, 0.0f) + __logf(1.0f + e);
-    sg = a >= 0.0f ? d : e * d;
+// softplus and its derivative from three MUFU operations (ex2, rcp, lg2 in their .ftz.approx forms: the arguments are
+// e = exp(-|a|) in (0, 1] -- a denormal e may flush to zero, softplus then returns max(a, 0) exactly as it should to fp32
+// accuracy -- and 1 + e in [1, 2]); absolute error ~1e-7 on values of order one
+__device__ __forceinline__ void um_act(float a, float& sp, float& sg) {
+    float e, d, lg;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(-1.4426950408889634f * fabsf(a)));
+    const float y = 1.0f + e;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(d) : "f"(y));
+    asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(lg) : "f"(y));
+    sp = fmaf(0.6931471805599453f, lg, fmaxf(a, 0.0f));
+    sg = a >= 0.0f ? d : 1.0f - d;  // (1 - d = e d)
+}
+
+// a = hi + lo with hi = a rounded to TF32's 11 significant bits (Veltkamp splitting: three FMA-pipe operations, where
+// cvt.rna.tf32 is emulated with five integer ones) and lo = a - hi exactly; the tensor core reads lo's leading 11 bits:
+// |a - hi - lo_read| <= 2^-21 |a|
+__device__ __forceinline__ void um_split(float a, uint32_t& hi, uint32_t& lo) {
+    const float g = __fmul_rn(a, 8193.0f);       // 2^13 + 1 (no contraction into the sums below)
+    const float h = __fadd_rn(g, __fsub_rn(a, g));
+    hi = __float_as_uint(h);
+    lo = __float_as_uint(__fsub_rn(a, h));
 }
 
 // everybody has staged its operands -> one thread issues the product -> everybody waits for the tensor core
@@ -94,7 +110,9 @@ __device__ __noinline__ void um_law(UmCtx<NX>& c, const float* x, float* lam, fl
     const int r = threadIdx.x & 127, wg = threadIdx.x >> 7, c0 = wg * CH;
     const uint32_t lane_base = c.tbase + ((uint32_t)(threadIdx.x & 96) << 16);
     const UmLayout lay{c.L};
-    const float* sm = c.sm;
+    extern __shared__ __align__(128) unsigned char um_smem[];  // (named here so that the loads below are LDS, not generic)
+    float* const smw = reinterpret_cast<float*>(um_smem);
+    const float* sm = smw;
     const int L = c.L;
 
     // ---- first layer: A = normalised state (8 columns, zero padded)
@@ -103,7 +121,7 @@ __device__ __noinline__ void um_law(UmCtx<NX>& c, const float* x, float* lam, fl
 #pragma unroll
         for (int q = 0; q < 8; q++) {
             const float xn = q < NX ? (x[q < NX ? q : 0] - c.x_mean[q < NX ? q : 0]) * c.x_scale[q < NX ? q : 0] : 0.0f;
-            split_tf32(xn, hi[q], lo[q]);
+            um_split(xn, hi[q], lo[q]);
         }
         tmem_st8(lane_base + kUmColAh, hi);
         tmem_st8(lane_base + kUmColAl, lo);
@@ -121,17 +139,22 @@ __device__ __noinline__ void um_law(UmCtx<NX>& c, const float* x, float* lam, fl
             const int col = c0 + cc;
             uint32_t d[16], hi[16], lo[16], sg[16];
             tmem_ld16(lane_base + kUmColD + col, d);
+            float bv[16], wv[16];
+#pragma unroll
+            for (int j = 0; j < 16; j += 4) {
+                *reinterpret_cast<float4*>(bv + j) = *reinterpret_cast<const float4*>(bias + col + j);
+                if (last) *reinterpret_cast<float4*>(wv + j) = *reinterpret_cast<const float4*>(wo + col + j);
+            }
             tmem_wait_ld();
 #pragma unroll
             for (int j = 0; j < 16; j++) {
                 float h, s;
-                um_act(__uint_as_float(d[j]) + bias[col + j], h, s);
+                um_act(__uint_as_float(d[j]) + bv[j], h, s);
                 if (last) {  // value, and the backward sweep's first operand G = w_out (.) softplus'
-                    const float w = wo[col + j];
-                    vpart = fmaf(h, w, vpart);
-                    h = w * s;
+                    vpart = fmaf(h, wv[j], vpart);
+                    h = wv[j] * s;
                 }
-                split_tf32(h, hi[j], lo[j]);
+                um_split(h, hi[j], lo[j]);
                 sg[j] = __float_as_uint(s);
             }
             tmem_st16(lane_base + kUmColAh + col, hi);
@@ -141,7 +164,7 @@ __device__ __noinline__ void um_law(UmCtx<NX>& c, const float* x, float* lam, fl
         tmem_wait_st();
         if (!last) um_product<64, 64>(c.tbase, c.bar, c.phase, sm + lay.wf(l + 1, 0), sm + lay.wf(l + 1, 1));
     }
-    if (NWG > 1) c.sm[lay.vpart() + wg * 128 + r] = vpart;  // (read after the next product's barrier)
+    if (NWG > 1) smw[lay.vpart() + wg * 128 + r] = vpart;  // (read after the next product's barrier)
     // ---- backward sweep: G_{l-1} = (G_l . W_l^T) (.) softplus'_{l-1}
     for (int l = L - 1; l >= 1; l--) {
         um_product<64, 64>(c.tbase, c.bar, c.phase, sm + lay.wb(l, 0), sm + lay.wb(l, 1));
@@ -153,7 +176,7 @@ __device__ __noinline__ void um_law(UmCtx<NX>& c, const float* x, float* lam, fl
             tmem_ld16(lane_base + kUmColSg + 64 * (l - 1) + col, sg);
             tmem_wait_ld();
 #pragma unroll
-            for (int j = 0; j < 16; j++) split_tf32(__uint_as_float(d[j]) * __uint_as_float(sg[j]), hi[j], lo[j]);
+            for (int j = 0; j < 16; j++) um_split(__uint_as_float(d[j]) * __uint_as_float(sg[j]), hi[j], lo[j]);
             tmem_st16(lane_base + kUmColAh + col, hi);
             tmem_st16(lane_base + kUmColAl + col, lo);
         }
@@ -161,7 +184,7 @@ __device__ __noinline__ void um_law(UmCtx<NX>& c, const float* x, float* lam, fl
     }
     um_product<16, 64>(c.tbase, c.bar, c.phase, sm + lay.w0b(0), sm + lay.w0b(1));
     float v = vpart;
-    if (NWG > 1) v = c.sm[lay.vpart() + r] + c.sm[lay.vpart() + 128 + r];
+    if (NWG > 1) v = smw[lay.vpart() + r] + smw[lay.vpart() + 128 + r];
     v += sm[lay.bout()];
     uint32_t gx[8];
     tmem_ld8(lane_base + kUmColD, gx);
@@ -169,7 +192,7 @@ __device__ __noinline__ void um_law(UmCtx<NX>& c, const float* x, float* lam, fl
     // ---- the members meet: push (scaled gradient, value) of this row into slot `rank` of every CTA's buffer, one barrier,
     // then add up the local copy in rank order
     constexpr int XS = (NX + 1) * 128;
-    float* xbuf = c.sm + lay.xch() + c.xpar * 8 * XS;
+    float* xbuf = smw + lay.xch() + c.xpar * 8 * XS;
     c.xpar ^= 1u;
     {
         float val[NX + 1];
