@@ -14,10 +14,11 @@
 //     CTA waits on.  With 256 threads the two halves of the CTA share a row: columns 0-31 / 32-63;
 //   * per right hand side: 1 + (L-1) forward products, L-1 backward products, the input gradient (N = 16), then the members'
 //     (gradient, value) meet through DISTRIBUTED SHARED MEMORY: every CTA PUSHES its row results into a slot of every peer's
-//     exchange buffer (remote stores do not stall; remote loads cost ~1 us each and were 45 % of the kernel), ONE cluster
-//     barrier, then everybody adds up its local copy in rank order -- every CTA holds bit-identical costates and takes identical
-//     steps.  The buffer is double-buffered by evaluation parity, which makes the second barrier unnecessary: nobody can be
-//     two evaluations ahead of a peer;
+//     exchange buffer with st.async (remote stores that count bytes on the DESTINATION's mbarrier: no cluster barrier, no
+//     fence; remote loads cost ~1 us each and were 45 % of the first version), waits for its own barrier to have received
+//     the C x 3.5 KB of the evaluation, then adds up its local copy in rank order -- every CTA holds bit-identical costates
+//     and takes identical steps.  The buffer is double-buffered by evaluation parity: nobody can be two evaluations ahead
+//     of a peer, because evaluation n+1's data of a peer only leaves after that peer has consumed evaluation n;
 //   * slots are refilled from the cluster's queue as trajectories end (same rounds as the cluster kernel).
 // Tensor-memory map (columns, 128 lanes x 32 bit each): D 0-63 | A_hi 64-127 | A_lo 128-191 | softplus' of layer l at 192 + 64 l.
 #pragma once
@@ -54,7 +55,8 @@ template <int NX> struct UmCtx {
     unsigned long long* bar;    // completion barrier of the tensor core
     uint32_t tbase;             // tensor memory base
     uint32_t phase;             // parity of the next completion
-    uint32_t xpar;              // parity of the next exchange
+    uint32_t xcnt;              // exchanges so far (buffer = count & 1, barrier phase = (count >> 1) & 1)
+    unsigned long long* xbar;   // [2] arrival barriers of the two exchange buffers
     int rank;                   // this CTA's rank = its member
     int L, C, E;
     float x_mean[NX], x_scale[NX], g_scale[NX], v_mean, v_std;
@@ -192,25 +194,29 @@ __device__ __noinline__ void um_law(UmCtx<NX>& c, const float* x, float* lam, fl
     // ---- the members meet: push (scaled gradient, value) of this row into slot `rank` of every CTA's buffer, one barrier,
     // then add up the local copy in rank order
     constexpr int XS = (NX + 1) * 128;
-    float* xbuf = smw + lay.xch() + c.xpar * 8 * XS;
-    c.xpar ^= 1u;
+    const uint32_t xb = c.xcnt & 1u, xph = (c.xcnt >> 1) & 1u;
+    c.xcnt++;
+    float* xbuf = smw + lay.xch() + xb * 8 * XS;
+    unsigned long long* xbar = c.xbar + xb;
+    if (threadIdx.x == 0) mbar_arrive_expect_tx(xbar, (uint32_t)(c.C * XS * 4));
     {
-        float val[NX + 1];
+        uint32_t val[NX + 1];
 #pragma unroll
-        for (int q = 0; q < NX; q++) val[q] = __uint_as_float(gx[q]) * c.g_scale[q];
-        val[NX] = fmaf(c.v_std, v, c.v_mean);
+        for (int q = 0; q < NX; q++) val[q] = __float_as_uint(__uint_as_float(gx[q]) * c.g_scale[q]);
+        val[NX] = __float_as_uint(fmaf(c.v_std, v, c.v_mean));
         constexpr int PER = 8 / NWG;  // destination ranks served by one warpgroup
+        const uint32_t slot = smem_u32(xbuf + c.rank * XS + r), lbar = smem_u32(xbar);
 #pragma unroll
         for (int dd = 0; dd < PER; dd++) {
             const int d = wg * PER + dd;
             if (d < c.C) {
-                float* dst = cluster.map_shared_rank(xbuf + c.rank * XS, d);
+                const uint32_t dst = mapa_u32(slot, (uint32_t)d), dbar = mapa_u32(lbar, (uint32_t)d);
 #pragma unroll
-                for (int q = 0; q <= NX; q++) dst[q * 128 + r] = val[q];
+                for (int q = 0; q <= NX; q++) st_async_b32(dst + q * 512, val[q], dbar);
             }
         }
     }
-    cluster.sync();
+    if (!mbar_wait(xbar, xph)) __trap();
     // (all loads first, unconditionally: slots of absent ranks hold stale bits that the selects below drop)
     float got[8][NX + 1];
 #pragma unroll
@@ -262,13 +268,13 @@ forward_umma_kernel(const typename Sys::Consts sc, const SolveOpts<float> o, con
 
     extern __shared__ __align__(128) unsigned char um_smem[];
     float* sm = reinterpret_cast<float*>(um_smem);
-    __shared__ __align__(8) unsigned long long s_bar;
+    __shared__ __align__(8) unsigned long long s_bar, s_xbar[2];
     __shared__ uint32_t s_tmem;
     __shared__ int s_cnt[4];
 
     // ---- one-time setup: tensor memory, barrier, this CTA's member as UMMA images
     if (threadIdx.x < 32) tmem_alloc(&s_tmem, kUmCols);
-    if (threadIdx.x == 32) mbar_init(&s_bar, 1);
+    if (threadIdx.x == 32) { mbar_init(&s_bar, 1); mbar_init(&s_xbar[0], 1); mbar_init(&s_xbar[1], 1); }
     {
         const R* src = pol.w + (size_t)rank * Pol::net_stride(L);
         constexpr int NT = 128 * NWG;
@@ -311,7 +317,7 @@ forward_umma_kernel(const typename Sys::Consts sc, const SolveOpts<float> o, con
     __syncthreads();
     tc_fence_after();
     UmCtx<NX> ctx;
-    ctx.sm = sm; ctx.bar = &s_bar; ctx.tbase = s_tmem; ctx.phase = 0u; ctx.xpar = 0u; ctx.rank = rank; ctx.L = L; ctx.C = C; ctx.E = pol.n_nets;
+    ctx.sm = sm; ctx.bar = &s_bar; ctx.tbase = s_tmem; ctx.phase = 0u; ctx.xcnt = 0u; ctx.xbar = s_xbar; ctx.rank = rank; ctx.L = L; ctx.C = C; ctx.E = pol.n_nets;
 #pragma unroll
     for (int q = 0; q < NX; q++) {
         ctx.x_mean[q] = pol.x_mean[q]; ctx.x_scale[q] = pol.inv_x_std[q]; ctx.g_scale[q] = pol.v_std * pol.inv_x_std[q];
