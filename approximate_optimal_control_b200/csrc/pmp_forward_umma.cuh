@@ -37,16 +37,15 @@ constexpr uint32_t kUmColD = 0, kUmColAh = 64, kUmColAl = 128, kUmColSg = 192, k
 // shared-memory image of one member (float offsets; every matrix image is 16-byte aligned)
 struct UmLayout {
     int L;  // hidden layers, 1..3
-    __host__ __device__ int w0f(int part) const { return part * 512; }                             // B(n = unit, k = input): N 64, K 8
-    __host__ __device__ int w0b(int part) const { return 1024 + part * 1024; }                     // B(n = input, k = unit): N 16, K 64
-    __host__ __device__ int wf(int l, int part) const { return 3072 + (l - 1) * 16384 + part * 4096; }         // B(n = out, k = in)
-    __host__ __device__ int wb(int l, int part) const { return 3072 + (l - 1) * 16384 + 8192 + part * 4096; }  // B(n = in, k = out)
-    __host__ __device__ int bias(int l) const { return 3072 + (L - 1) * 16384 + l * kUmW; }
+    __host__ __device__ int w0() const { return 0; }                                                          // first layer, fp32 [8][64] (rows >= NX zero)
+    __host__ __device__ int wf(int l, int part) const { return 512 + (l - 1) * 16384 + part * 4096; }         // B(n = out, k = in)
+    __host__ __device__ int wb(int l, int part) const { return 512 + (l - 1) * 16384 + 8192 + part * 4096; }  // B(n = in, k = out)
+    __host__ __device__ int bias(int l) const { return 512 + (L - 1) * 16384 + l * kUmW; }
     __host__ __device__ int wout() const { return bias(L); }
     __host__ __device__ int bout() const { return wout() + kUmW; }
-    __host__ __device__ int vpart() const { return bout() + 4; }          // [2][128] partial values of the two column halves
-    __host__ __device__ int xch() const { return vpart() + 256; }         // [2 parities][8 ranks][NX + 1][128] exchange buffer
-    __host__ __device__ int total(int NX) const { return xch() + 2 * 8 * (NX + 1) * 128; }
+    __host__ __device__ int part() const { return bout() + 4; }           // [2 parities][NX + 1][2][128] partial gradients / values of the two column halves
+    __host__ __device__ int xch(int NX) const { return part() + 2 * (NX + 1) * 256; }  // [2 parities][8 ranks][NX + 1][128] exchange buffer
+    __host__ __device__ int total(int NX) const { return xch(NX) + 2 * 8 * (NX + 1) * 128; }
 };
 
 // what the law needs besides the state: lives in registers / constant bank of the caller
@@ -59,7 +58,7 @@ template <int NX> struct UmCtx {
     unsigned long long* xbar;   // [2] arrival barriers of the two exchange buffers
     int rank;                   // this CTA's rank = its member
     int L, C, E;
-    float x_mean[NX], x_scale[NX], g_scale[NX], v_mean, v_std;
+    float x_mean[NX], x_scale[NX], g_scale[NX], v_mean, v_std, inv_e;
 };
 
 // softplus and its derivative from three MUFU operations (ex2, rcp, lg2 in their .ftz.approx forms: the arguments are
@@ -117,20 +116,25 @@ __device__ __noinline__ void um_law(UmCtx<NX>& c, const float* x, float* lam, fl
     const float* sm = smw;
     const int L = c.L;
 
-    // ---- first layer: A = normalised state (8 columns, zero padded)
-    if (wg == 0) {
-        uint32_t hi[8], lo[8];
+    const int C = c.C;
+    // ---- the first layer and the input gradient run on the CUDA cores (K = NX: 6 FMAs per unit from broadcast LDS.128 of the
+    // fp32 weights; as tensor-core products each cost a full stage -> issue -> wait round trip of ~2000 cycles)
+    float xn[NX], gxp[NX];
 #pragma unroll
-        for (int q = 0; q < 8; q++) {
-            const float xn = q < NX ? (x[q < NX ? q : 0] - c.x_mean[q < NX ? q : 0]) * c.x_scale[q < NX ? q : 0] : 0.0f;
-            um_split(xn, hi[q], lo[q]);
+    for (int q = 0; q < NX; q++) { xn[q] = (x[q] - c.x_mean[q]) * c.x_scale[q]; gxp[q] = 0.0f; }
+    const float* w0 = sm + lay.w0();
+    // G = dV/d(pre-activation of layer 0) for 16 of this thread's columns: its share of the input gradient
+    auto input_grad = [&](int col, const float (&g)[16]) {
+#pragma unroll
+        for (int q = 0; q < NX; q++) {
+            float wr[16];
+#pragma unroll
+            for (int jj = 0; jj < 16; jj += 4) *reinterpret_cast<float4*>(wr + jj) = *reinterpret_cast<const float4*>(w0 + q * kUmW + col + jj);
+#pragma unroll
+            for (int jj = 0; jj < 16; jj++) gxp[q] = fmaf(g[jj], wr[jj], gxp[q]);
         }
-        tmem_st8(lane_base + kUmColAh, hi);
-        tmem_st8(lane_base + kUmColAl, lo);
-        tmem_wait_st();
-    }
-    um_product<64, 8>(c.tbase, c.bar, c.phase, sm + lay.w0f(0), sm + lay.w0f(1));
-    // ---- forward sweep: D = pre-activations of layer l (without bias)
+    };
+    // ---- forward sweep: D = pre-activations of layer l >= 1 (without bias)
     float vpart = 0.0f;
     for (int l = 0; l < L; l++) {
         const bool last = l == L - 1;
@@ -140,76 +144,109 @@ __device__ __noinline__ void um_law(UmCtx<NX>& c, const float* x, float* lam, fl
         for (int cc = 0; cc < CH; cc += 16) {
             const int col = c0 + cc;
             uint32_t d[16], hi[16], lo[16], sg[16];
-            tmem_ld16(lane_base + kUmColD + col, d);
-            float bv[16], wv[16];
+            float bv[16], wv[16], g[16];
+            if (l > 0) tmem_ld16(lane_base + kUmColD + col, d);
 #pragma unroll
-            for (int j = 0; j < 16; j += 4) {
-                *reinterpret_cast<float4*>(bv + j) = *reinterpret_cast<const float4*>(bias + col + j);
-                if (last) *reinterpret_cast<float4*>(wv + j) = *reinterpret_cast<const float4*>(wo + col + j);
+            for (int jj = 0; jj < 16; jj += 4) {
+                *reinterpret_cast<float4*>(bv + jj) = *reinterpret_cast<const float4*>(bias + col + jj);
+                if (last) *reinterpret_cast<float4*>(wv + jj) = *reinterpret_cast<const float4*>(wo + col + jj);
             }
-            tmem_wait_ld();
+            if (l == 0) {
 #pragma unroll
-            for (int j = 0; j < 16; j++) {
-                float h, s;
-                um_act(__uint_as_float(d[j]) + bv[j], h, s);
-                if (last) {  // value, and the backward sweep's first operand G = w_out (.) softplus'
-                    vpart = fmaf(h, wv[j], vpart);
-                    h = wv[j] * s;
+                for (int q = 0; q < NX; q++) {
+                    float wr[16];
+#pragma unroll
+                    for (int jj = 0; jj < 16; jj += 4) *reinterpret_cast<float4*>(wr + jj) = *reinterpret_cast<const float4*>(w0 + q * kUmW + col + jj);
+#pragma unroll
+                    for (int jj = 0; jj < 16; jj++) bv[jj] = fmaf(xn[q], wr[jj], bv[jj]);
                 }
-                um_split(h, hi[j], lo[j]);
-                sg[j] = __float_as_uint(s);
+#pragma unroll
+                for (int jj = 0; jj < 16; jj++) d[jj] = 0u;  // (+0.0f)
+            } else {
+                tmem_wait_ld();
             }
-            tmem_st16(lane_base + kUmColAh + col, hi);
-            tmem_st16(lane_base + kUmColAl + col, lo);
-            if (!last) tmem_st16(lane_base + kUmColSg + 64 * l + col, sg);
+#pragma unroll
+            for (int jj = 0; jj < 16; jj++) {
+                float h, sd;
+                um_act(__uint_as_float(d[jj]) + bv[jj], h, sd);
+                if (last) {  // value, and the backward sweep's first operand G = w_out (.) softplus'
+                    vpart = fmaf(h, wv[jj], vpart);
+                    h = wv[jj] * sd;
+                }
+                g[jj] = h;
+                um_split(h, hi[jj], lo[jj]);
+                sg[jj] = __float_as_uint(sd);
+            }
+            if (last && l == 0) {  // one hidden layer: G is already the gradient at the first layer
+                input_grad(col, g);
+            } else {
+                tmem_st16(lane_base + kUmColAh + col, hi);
+                tmem_st16(lane_base + kUmColAl + col, lo);
+                if (!last) tmem_st16(lane_base + kUmColSg + 64 * l + col, sg);
+            }
         }
-        tmem_wait_st();
+        if (!(last && l == 0)) tmem_wait_st();
         if (!last) um_product<64, 64>(c.tbase, c.bar, c.phase, sm + lay.wf(l + 1, 0), sm + lay.wf(l + 1, 1));
     }
-    if (NWG > 1) smw[lay.vpart() + wg * 128 + r] = vpart;  // (read after the next product's barrier)
-    // ---- backward sweep: G_{l-1} = (G_l . W_l^T) (.) softplus'_{l-1}
+    // ---- backward sweep: G_{l-1} = (G_l . W_l^T) (.) softplus'_{l-1}; G_0 goes straight into the input gradient
     for (int l = L - 1; l >= 1; l--) {
         um_product<64, 64>(c.tbase, c.bar, c.phase, sm + lay.wb(l, 0), sm + lay.wb(l, 1));
 #pragma unroll
         for (int cc = 0; cc < CH; cc += 16) {
             const int col = c0 + cc;
             uint32_t d[16], sg[16], hi[16], lo[16];
+            float g[16];
             tmem_ld16(lane_base + kUmColD + col, d);
             tmem_ld16(lane_base + kUmColSg + 64 * (l - 1) + col, sg);
             tmem_wait_ld();
 #pragma unroll
-            for (int j = 0; j < 16; j++) um_split(__uint_as_float(d[j]) * __uint_as_float(sg[j]), hi[j], lo[j]);
-            tmem_st16(lane_base + kUmColAh + col, hi);
-            tmem_st16(lane_base + kUmColAl + col, lo);
+            for (int jj = 0; jj < 16; jj++) g[jj] = __uint_as_float(d[jj]) * __uint_as_float(sg[jj]);
+            if (l == 1) {
+                input_grad(col, g);
+            } else {
+#pragma unroll
+                for (int jj = 0; jj < 16; jj++) um_split(g[jj], hi[jj], lo[jj]);
+                tmem_st16(lane_base + kUmColAh + col, hi);
+                tmem_st16(lane_base + kUmColAl + col, lo);
+            }
         }
-        tmem_wait_st();
+        if (l > 1) tmem_wait_st();
     }
-    um_product<16, 64>(c.tbase, c.bar, c.phase, sm + lay.w0b(0), sm + lay.w0b(1));
+    // the two column halves of a row meet in shared memory (fixed order: both warpgroups hold identical results)
     float v = vpart;
-    if (NWG > 1) v = smw[lay.vpart() + r] + smw[lay.vpart() + 128 + r];
+    float gx[NX];
+#pragma unroll
+    for (int q = 0; q < NX; q++) gx[q] = gxp[q];
+    if (NWG > 1) {
+        float* pt = smw + lay.part() + (c.xcnt & 1u) * (NX + 1) * 256;  // (by evaluation parity: with one hidden layer this is the only barrier)
+#pragma unroll
+        for (int q = 0; q < NX; q++) pt[q * 256 + wg * 128 + r] = gxp[q];
+        pt[NX * 256 + wg * 128 + r] = vpart;
+        __syncthreads();
+#pragma unroll
+        for (int q = 0; q < NX; q++) gx[q] = pt[q * 256 + r] + pt[q * 256 + 128 + r];
+        v = pt[NX * 256 + r] + pt[NX * 256 + 128 + r];
+    }
     v += sm[lay.bout()];
-    uint32_t gx[8];
-    tmem_ld8(lane_base + kUmColD, gx);
-    tmem_wait_ld();
     // ---- the members meet: push (scaled gradient, value) of this row into slot `rank` of every CTA's buffer, one barrier,
     // then add up the local copy in rank order
     constexpr int XS = (NX + 1) * 128;
     const uint32_t xb = c.xcnt & 1u, xph = (c.xcnt >> 1) & 1u;
     c.xcnt++;
-    float* xbuf = smw + lay.xch() + xb * 8 * XS;
+    float* xbuf = smw + lay.xch(NX) + xb * 8 * XS;
     unsigned long long* xbar = c.xbar + xb;
-    if (threadIdx.x == 0) mbar_arrive_expect_tx(xbar, (uint32_t)(c.C * XS * 4));
+    if (threadIdx.x == 0) mbar_arrive_expect_tx(xbar, (uint32_t)(C * XS * 4));
     {
         uint32_t val[NX + 1];
 #pragma unroll
-        for (int q = 0; q < NX; q++) val[q] = __float_as_uint(__uint_as_float(gx[q]) * c.g_scale[q]);
+        for (int q = 0; q < NX; q++) val[q] = __float_as_uint(gx[q] * c.g_scale[q]);
         val[NX] = __float_as_uint(fmaf(c.v_std, v, c.v_mean));
         constexpr int PER = 8 / NWG;  // destination ranks served by one warpgroup
         const uint32_t slot = smem_u32(xbuf + c.rank * XS + r), lbar = smem_u32(xbar);
 #pragma unroll
         for (int dd = 0; dd < PER; dd++) {
             const int d = wg * PER + dd;
-            if (d < c.C) {
+            if (d < C) {
                 const uint32_t dst = mapa_u32(slot, (uint32_t)d), dbar = mapa_u32(lbar, (uint32_t)d);
 #pragma unroll
                 for (int q = 0; q <= NX; q++) st_async_b32(dst + q * 512, val[q], dbar);
@@ -217,29 +254,35 @@ __device__ __noinline__ void um_law(UmCtx<NX>& c, const float* x, float* lam, fl
         }
     }
     if (!mbar_wait(xbar, xph)) __trap();
-    // (all loads first, unconditionally: slots of absent ranks hold stale bits that the selects below drop)
-    float got[8][NX + 1];
-#pragma unroll
-    for (int rr = 0; rr < 8; rr++)
-#pragma unroll
-        for (int q = 0; q <= NX; q++) got[rr][q] = xbuf[rr * XS + q * 128 + r];
     float ve[8], sum = 0.0f;
 #pragma unroll
     for (int q = 0; q < NX; q++) lam[q] = 0.0f;
+    if (C == 8) {  // the usual ensemble: straight sums
 #pragma unroll
-    for (int rr = 0; rr < 8; rr++) {
-        const bool on = rr < c.C;
+        for (int rr = 0; rr < 8; rr++) {
 #pragma unroll
-        for (int q = 0; q < NX; q++) lam[q] += on ? got[rr][q] : 0.0f;
-        ve[rr] = on ? got[rr][NX] : 0.0f;
-        sum += ve[rr];
+            for (int q = 0; q < NX; q++) lam[q] += xbuf[rr * XS + q * 128 + r];
+            ve[rr] = xbuf[rr * XS + NX * 128 + r];
+            sum += ve[rr];
+        }
+    } else {
+#pragma unroll
+        for (int rr = 0; rr < 8; rr++) {
+            ve[rr] = 0.0f;
+            if (rr < C) {
+#pragma unroll
+                for (int q = 0; q < NX; q++) lam[q] += xbuf[rr * XS + q * 128 + r];
+                ve[rr] = xbuf[rr * XS + NX * 128 + r];
+                sum += ve[rr];
+            }
+        }
     }
-    const float inv_e = __fdiv_rn(1.0f, (float)c.E);
+    const float inv_e = c.inv_e;
     vmean = sum * inv_e;
     float var = 0.0f;
 #pragma unroll
     for (int rr = 0; rr < 8; rr++)
-        if (rr < c.C) var = fmaf(ve[rr] - vmean, ve[rr] - vmean, var);
+        if (rr < C) var = fmaf(ve[rr] - vmean, ve[rr] - vmean, var);
     vstd = sqrtf(var * inv_e);
 #pragma unroll
     for (int q = 0; q < NX; q++) lam[q] *= inv_e;
@@ -278,22 +321,8 @@ forward_umma_kernel(const typename Sys::Consts sc, const SolveOpts<float> o, con
     {
         const R* src = pol.w + (size_t)rank * Pol::net_stride(L);
         constexpr int NT = 128 * NWG;
-        for (int q = threadIdx.x; q < 8 * W; q += NT) {  // first layer, forward: B(n, k) = W0[k][n], k >= NX zero
-            const int k = q / W, nn = q - k * W;
-            uint32_t hi, lo;
-            split_tf32(k < NX ? __ldg(src + k * W + nn) : 0.0f, hi, lo);
-            const int off = b_off_k<64, 8>(nn, k);
-            sm[lay.w0f(0) + off] = __uint_as_float(hi);
-            sm[lay.w0f(1) + off] = __uint_as_float(lo);
-        }
-        for (int q = threadIdx.x; q < 16 * W; q += NT) {  // first layer, backward: B(n, k) = W0[n][k], n >= NX zero
-            const int nn = q / W, k = q - nn * W;
-            uint32_t hi, lo;
-            split_tf32(nn < NX ? __ldg(src + nn * W + k) : 0.0f, hi, lo);
-            const int off = b_off_k<16, 64>(nn, k);
-            sm[lay.w0b(0) + off] = __uint_as_float(hi);
-            sm[lay.w0b(1) + off] = __uint_as_float(lo);
-        }
+        for (int q = threadIdx.x; q < 8 * W; q += NT)  // first layer: plain fp32 rows (used by the CUDA cores), rows >= NX zero
+            sm[lay.w0() + q] = q < NX * W ? __ldg(src + q) : 0.0f;
         if (threadIdx.x < W) sm[lay.bias(0) + threadIdx.x] = __ldg(src + NX * W + threadIdx.x);
         const R* pl = src + NX * W + W;
         for (int l = 1; l < L; l++, pl += W * W + W) {
@@ -322,7 +351,7 @@ forward_umma_kernel(const typename Sys::Consts sc, const SolveOpts<float> o, con
     for (int q = 0; q < NX; q++) {
         ctx.x_mean[q] = pol.x_mean[q]; ctx.x_scale[q] = pol.inv_x_std[q]; ctx.g_scale[q] = pol.v_std * pol.inv_x_std[q];
     }
-    ctx.v_mean = pol.v_mean; ctx.v_std = pol.v_std;
+    ctx.v_mean = pol.v_mean; ctx.v_std = pol.v_std; ctx.inv_e = __fdiv_rn(1.0f, (float)pol.n_nets);
     cluster.sync();  // every CTA of the cluster is resident before anybody reads remote shared memory
 
     auto field = [&](const R* z, R* k, R& vm, R& vs) {
