@@ -73,7 +73,8 @@ def lib() -> C.CDLL:
     if _lib is not None:
         return _lib
     path = os.environ.get("B200PMP_LIB") or _build.LIB_PATH  # B200PMP_LIB: a tuning variant built by scripts/build_variant.py
-    if not os.path.exists(path) or os.environ.get("B200PMP_REBUILD"):
+    if os.environ.get("B200PMP_LIB") is None and (os.environ.get("B200PMP_REBUILD") or _build._stale()):
+        # missing, or built from other sources than the ones in the tree (content hash): rebuild rather than run old kernels
         path = _build.build(force=bool(os.environ.get("B200PMP_REBUILD")))
     _lib = load(path)
     return _lib

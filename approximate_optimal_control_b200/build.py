@@ -42,12 +42,34 @@ def _nvcc() -> str:
     return exe
 
 
+def _deps():
+    deps = [os.path.join(_CSRC, f) for f in SOURCES + HEADERS]
+    return deps + [os.path.join(_ROOT, "include", "b200pmp.h"), os.path.abspath(__file__)]
+
+
+def _source_hash() -> str:
+    """Content hash of everything the library is built from (sources, headers, C header, this file with its flags)."""
+    import hashlib
+    h = hashlib.sha256()
+    for d in _deps():
+        h.update(os.path.basename(d).encode())
+        h.update(open(d, "rb").read())
+    h.update(" ".join(NVCC_FLAGS).encode())
+    return h.hexdigest()
+
+
+_HASH_PATH = LIB_PATH + ".srchash"
+
+
 def _stale() -> bool:
+    """True when the library is missing or was built from other sources.  Compared by CONTENT (the hash build() leaves next
+    to the library), not by mtime: the library travels to GPU boxes in snapshots that do not keep file times."""
     if not os.path.exists(LIB_PATH):
         return True
-    deps = [os.path.join(_CSRC, f) for f in SOURCES + HEADERS]
-    deps += [os.path.join(_ROOT, "include", "b200pmp.h"), os.path.abspath(__file__)]
-    return os.path.getmtime(LIB_PATH) < max(os.path.getmtime(d) for d in deps)
+    try:
+        return open(_HASH_PATH).read().strip() != _source_hash()
+    except OSError:
+        return os.path.getmtime(LIB_PATH) < max(os.path.getmtime(d) for d in _deps())
 
 
 LAST_BUILD = {"mode": None, "units": []}  # what the last build() call did (printed by __graft_entry__.build)
@@ -81,6 +103,8 @@ def build(force: bool = False, verbose: bool = False) -> str:
     r = subprocess.run(link, capture_output=True, text=True, env=env)
     if r.returncode != 0:
         raise RuntimeError(f"link failed:\n{r.stdout}\n{r.stderr}")
+    with open(_HASH_PATH, "w") as fh:
+        fh.write(_source_hash())
     LAST_BUILD.update(mode="compiled with " + " ".join([os.path.basename(nvcc), *NVCC_FLAGS]), units=list(SOURCES))
     return LIB_PATH
 

@@ -296,6 +296,22 @@ def build_plugin(problem_params: dict, force: bool = False, verbose: bool = Fals
     lib_path = os.path.join(PLUGIN_DIR, f"libb200pmp_gen_{tag}.so")
     if os.path.exists(lib_path) and not force:
         return lib_path
+    os.makedirs(PLUGIN_DIR, exist_ok=True)
+    # one builder per tag at a time: with one process per GPU, N ranks meet here for the same new system; the others wait
+    # for the lock and find the finished library
+    import fcntl
+    lock = open(os.path.join(PLUGIN_DIR, f"{tag}.lock"), "w")
+    fcntl.flock(lock, fcntl.LOCK_EX)
+    try:
+        if os.path.exists(lib_path) and not force:
+            return lib_path
+        return _build_plugin_locked(header, tag, lib_path, verbose)
+    finally:
+        fcntl.flock(lock, fcntl.LOCK_UN)
+        lock.close()
+
+
+def _build_plugin_locked(header: str, tag: str, lib_path: str, verbose: bool) -> str:
     work = os.path.join(PLUGIN_DIR, tag)
     os.makedirs(work, exist_ok=True)
     hpath = os.path.join(work, "pmp_generated.cuh")
@@ -327,9 +343,22 @@ def build_plugin(problem_params: dict, force: bool = False, verbose: bool = Fals
     return lib_path
 
 
+_plugin_paths: dict = {}  # (f, l, nx, nu, U_interval, name) -> library path: repeated calls skip the sympy derivation
+
+
 def plugin_problem(problem_params: dict) -> _capi.Problem:
-    """pmp_problem_t for a generated system (system_id PMP_SYS_GENERATED) bound to its plug-in library."""
-    path = build_plugin(problem_params)
+    """pmp_problem_t for a generated system (system_id PMP_SYS_GENERATED) bound to its plug-in library.  Only the first call
+    for a system pays the derivation (sympy trace, simplification, cse) and the compilation."""
+    key = (problem_params.get("f"), problem_params.get("l"), int(problem_params["nx"]), int(problem_params["nu"]),
+           repr(problem_params["U_interval"]), str(problem_params.get("system_name", "user")))
+    try:
+        path = _plugin_paths.get(key)
+    except TypeError:  # unhashable callables
+        key, path = None, None
+    if path is None or not os.path.exists(path):
+        path = build_plugin(problem_params)
+        if key is not None:
+            _plugin_paths[key] = path
     nx, nu = int(problem_params["nx"]), int(problem_params["nu"])
     p = _capi.Problem(system_id=_capi.SYS_GENERATED, nx=nx, nu=nu)
     lo, hi = problem_params["U_interval"]

@@ -79,6 +79,10 @@ def parse_args():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-parity", action="store_true")
     ap.add_argument("--no-dense", action="store_true", help="skip the dense (C5) block of the default N=1 line")
+    ap.add_argument("--no-forward-nn", action="store_true", help="skip the value-network forward-simulation block of the default N=1 line")
+    ap.add_argument("--e2e-per-piece", action="store_true",
+                    help="e2e through per-piece launches (state-dict solve_backward) instead of the persistent host-fed launch: the "
+                         "form a serialising profiler (ncu) can run -- the persistent kernel waits for copies ncu holds back")
     ap.add_argument("--no-strong", action="store_true", help="N>1, weak: skip the strong-scaling block")
     return ap.parse_args()
 
@@ -461,6 +465,33 @@ def main():
         dr["out"].clear()
         torch.cuda.empty_cache()
 
+    # ---- forward closed loop under the value-network ensemble costate law attached to the default line -----
+    forward_block = None
+    if world == 1 and not dense and not args.no_forward_nn and args.dtype == "f32" and args.log2n <= 20:
+        from approximate_optimal_control_b200 import nn_costate as NC
+        nf = 1 << 14
+        xf = torch.as_tensor(40.0 * y_np[:6, :nf], dtype=torch.float32, device=dev).contiguous()
+        ens = NC.NnEnsemble.from_flax(NC.init_flax_params(0, 6, (64, 64, 64), 8), NC.DataNormaliser.identity(6), dev, torch.float32)
+        fo = _capi.make_opts(dtype=_capi.F32, t0=0.0, t1=10.0, dt0=0.1, dtmin=0.05, dtmax=0.0, max_steps=256)
+        fout, fts = {}, []
+        for _ in range(5):
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            torch.cuda.synchronize(); a.record(); pu.forward_batch_soa(problem, fo, xf, out=fout, nn=ens); b.record(); torch.cuda.synchronize()
+            fts.append(a.elapsed_time(b))
+        gpu_launches += 5
+        fms = float(np.median(fts[1:]))
+        fatt = int(fout["n_steps"].sum())
+        fl = fatt * 6 * 8 * 2 * 2 * (6 * 64 + 64 * 64 * 2 + 64)  # attempts x stages x members x (forward + backward) x 2 flop x weights
+        forward_block = {"workload": "forward closed-loop simulation of 2^14 flatquad states, t: 0 -> 10, Tsit5 + PID(dtmin = .05), costate law = "
+                                     "gradient of the mean of an 8-member 6-64-64-64-1 softplus value-network ensemble (random flax-layout "
+                                     "weights), levelsets.py:838-933",
+                         "ms": fms, "value": nf / (fms * 1e-3), "unit": "trajectories/s", "rk_step_attempts_per_s": fatt / (fms * 1e-3),
+                         "mlp_tflops_fp32_equivalent": fl / (fms * 1e-3) / 1e12,
+                         "kernel": "forward_umma_kernel: tcgen05.mma kind::tf32 in 3xTF32 split precision, clusters of one CTA per member "
+                                   "(pmp_forward_umma.cuh)"}
+        del fout, xf, ens
+        torch.cuda.empty_cache()
+
     # ---- e2e: public API, host buffers ---------------------------------------------------------------
     e2e = None
     if not args.no_e2e:
@@ -474,6 +505,9 @@ def main():
         solve_backward_lqr = levelsets.define_solve_backward_lqr(pp, ap_e, P_lqr)
         solve_backward, _ = pu.define_backward_solver(pp, ap_e)
         host_x = torch.as_tensor(st_np["x"]).pin_memory()
+        host_state = {k: torch.as_tensor(v).pin_memory() for k, v in st_np.items()} if args.e2e_per_piece else None
+        if args.e2e_per_piece:
+            os.environ["B200PMP_HOST_PER_PIECE"] = "1"
         host_out = {k: torch.empty(v.shape, dtype=tdt).pin_memory() for k, v in st_np.items()}
         h2d = host_x.numel() * host_x.element_size()
         d2h = sum(v.numel() * v.element_size() for v in host_out.values())
@@ -490,7 +524,10 @@ def main():
             # host in -> host out: pinned xfs goes to pmp_solve_host_lqr (csrc/pmp_host.cu): ONE persistent launch of the
             # integrator consumes the pieces as the copy engine delivers them and the endpoints + counters of every finished
             # piece are copied back to pinned host memory while later pieces are still being integrated
-            sol = solve_backward_lqr(host_x)
+            if args.e2e_per_piece:
+                sol = solve_backward(host_state)
+            else:
+                sol = solve_backward_lqr(host_x)
             assert not sol.y_end["x"].is_cuda and sol.y_end["x"].shape == host_x.shape
 
         for _ in range(3):
@@ -589,7 +626,7 @@ def main():
             "solve_ms_per_step": solve_s * 1e3,
             "roofline": roof, "parity": parity, "cpu_baseline": cpu, "e2e": e2e, "clocks": clocks,
             "gpu_launches": int(gpu_launches),
-            "gather": gather, "gather_check": gather_check, "strong": strong, "dense": dense_block,
+            "gather": gather, "gather_check": gather_check, "strong": strong, "dense": dense_block, "forward_nn": forward_block,
         }
         print(json.dumps(line), flush=True)
     if world > 1:
