@@ -77,7 +77,7 @@ LAST_BUILD = {"mode": None, "units": []}  # what the last build() call did (prin
 
 def build(force: bool = False, verbose: bool = False) -> str:
     if not force and not _stale():
-        LAST_BUILD.update(mode="up to date (prebuilt library newer than every source)", units=[])
+        LAST_BUILD.update(mode="up to date (the content hash of the sources matches the prebuilt library)", units=[])
         return LIB_PATH
     os.makedirs(_OBJ_DIR, exist_ok=True)
     nvcc = _nvcc()
