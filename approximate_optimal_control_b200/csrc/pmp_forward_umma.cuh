@@ -20,7 +20,8 @@
 //     and takes identical steps.  The buffer is double-buffered by evaluation parity: nobody can be two evaluations ahead
 //     of a peer, because evaluation n+1's data of a peer only leaves after that peer has consumed evaluation n;
 //   * slots are refilled from the cluster's queue as trajectories end (same rounds as the cluster kernel).
-// Tensor-memory map (columns, 128 lanes x 32 bit each): D 0-63 | A_hi 64-127 | A_lo 128-191 | softplus' of layer l at 192 + 64 l.
+// Tensor-memory map (columns, 128 lanes x 32 bit each): D 0-63 (a_hi.w_hi + a_lo.w_hi) | D2 64-127 (a_hi.w_lo) | A_hi 128-191 |
+// A_lo 192-255 | softplus' of layer l at 256 + 64 l.
 #pragma once
 #include <cooperative_groups.h>
 
@@ -32,7 +33,7 @@ namespace cg = cooperative_groups;
 
 constexpr int kUmW = 64;          // hidden width served by this kernel
 constexpr int kUmRefillMin = 16;  // idle slots that trigger a refill round (each costs one extra law evaluation)
-constexpr uint32_t kUmColD = 0, kUmColAh = 64, kUmColAl = 128, kUmColSg = 192, kUmCols = 512;
+constexpr uint32_t kUmColD = 0, kUmColD2 = 64, kUmColAh = 128, kUmColAl = 192, kUmColSg = 256, kUmCols = 512;
 
 // shared-memory image of one member (float offsets; every matrix image is 16-byte aligned)
 struct UmLayout {
@@ -92,8 +93,9 @@ __device__ __forceinline__ void um_product(uint32_t tbase, unsigned long long* b
     __syncthreads();
     if (threadIdx.x == 0) {
         tc_fence_after();
-        issue_3xtf32<N, K>(tbase + kUmColD, tbase + kUmColAh, tbase + kUmColAl, smem_u32(b_hi), smem_u32(b_lo),
-                           make_idesc_tf32(128, N));
+        // (b_lo == b_hi + N K floats: the two images form one [B_hi | B_lo] operand of 2N rows)
+        issue_3xtf32_wide<N, K>(tbase + kUmColD, tbase + kUmColAh, tbase + kUmColAl, smem_u32(b_hi), make_idesc_tf32(128, 2 * N),
+                                make_idesc_tf32(128, N));
         umma_commit(bar);
     }
     if (!mbar_wait(bar, phase)) __trap();  // a lost completion must not hang the GPU
@@ -145,7 +147,11 @@ __device__ __noinline__ void um_law(UmCtx<NX>& c, const float* x, float* lam, fl
             const int col = c0 + cc;
             uint32_t d[16], hi[16], lo[16], sg[16];
             float bv[16], wv[16], g[16];
-            if (l > 0) tmem_ld16(lane_base + kUmColD + col, d);
+            uint32_t d2[16];
+            if (l > 0) {
+                tmem_ld16(lane_base + kUmColD + col, d);
+                tmem_ld16(lane_base + kUmColD2 + col, d2);
+            }
 #pragma unroll
             for (int jj = 0; jj < 16; jj += 4) {
                 *reinterpret_cast<float4*>(bv + jj) = *reinterpret_cast<const float4*>(bias + col + jj);
@@ -164,6 +170,8 @@ __device__ __noinline__ void um_law(UmCtx<NX>& c, const float* x, float* lam, fl
                 for (int jj = 0; jj < 16; jj++) d[jj] = 0u;  // (+0.0f)
             } else {
                 tmem_wait_ld();
+#pragma unroll
+                for (int jj = 0; jj < 16; jj++) d[jj] = __float_as_uint(__uint_as_float(d[jj]) + __uint_as_float(d2[jj]));
             }
 #pragma unroll
             for (int jj = 0; jj < 16; jj++) {
@@ -196,11 +204,13 @@ __device__ __noinline__ void um_law(UmCtx<NX>& c, const float* x, float* lam, fl
             const int col = c0 + cc;
             uint32_t d[16], sg[16], hi[16], lo[16];
             float g[16];
+            uint32_t d2[16];
             tmem_ld16(lane_base + kUmColD + col, d);
+            tmem_ld16(lane_base + kUmColD2 + col, d2);
             tmem_ld16(lane_base + kUmColSg + 64 * (l - 1) + col, sg);
             tmem_wait_ld();
 #pragma unroll
-            for (int jj = 0; jj < 16; jj++) g[jj] = __uint_as_float(d[jj]) * __uint_as_float(sg[jj]);
+            for (int jj = 0; jj < 16; jj++) g[jj] = (__uint_as_float(d[jj]) + __uint_as_float(d2[jj])) * __uint_as_float(sg[jj]);
             if (l == 1) {
                 input_grad(col, g);
             } else {

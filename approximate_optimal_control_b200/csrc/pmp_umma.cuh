@@ -168,5 +168,20 @@ __device__ __forceinline__ void issue_3xtf32(uint32_t d_tmem, uint32_t a_hi, uin
     }
 }
 
+// The same product with the two terms that share A_hi issued as ONE instruction of twice the width: the hi and lo images of B
+// are contiguous in shared memory (the lo image starts where row group N/8 of the hi image would), so a descriptor of 2N rows
+// at b_hi reads [B_hi | B_lo]:   D[:, 0:N) = A_hi.B_hi + A_lo.B_hi,   D[:, N:2N) = A_hi.B_lo   (the caller adds the two blocks).
+// 2 K/8 instead of 3 K/8 instructions; an instruction costs ~48 cycles at N = 64 and ~70 at N = 128 (scripts/tc_probe.cu).
+template <int N, int K>
+__device__ __forceinline__ void issue_3xtf32_wide(uint32_t d_tmem, uint32_t a_hi, uint32_t a_lo, uint32_t b_hi, uint32_t idesc_2n, uint32_t idesc_n) {
+    constexpr uint32_t LBO = 128, SBO = (K / 4) * 128;
+#pragma unroll
+    for (int ks = 0; ks < K / 8; ks++)
+        umma_tf32_ts(d_tmem, a_hi + 8 * ks, make_sdesc(b_hi + ks * 2 * LBO, LBO, SBO), idesc_2n, ks > 0 ? 1u : 0u);
+#pragma unroll
+    for (int ks = 0; ks < K / 8; ks++)
+        umma_tf32_ts(d_tmem, a_lo + 8 * ks, make_sdesc(b_hi + ks * 2 * LBO, LBO, SBO), idesc_n, 1u);
+}
+
 }  // namespace umma
 }  // namespace pmp
