@@ -366,7 +366,7 @@ int pmp_allgather_endpoints(void* comm, const void* local, void* global, int64_t
 }
 
 int pmp_host_probe_copy(void* dst, const void* src, int64_t bytes, int32_t blocks, void* cuda_stream) {
-    if (!dst || !src || bytes < 0 || (bytes & 15) || blocks < 1) return fail(PMP_ERR_BAD_ARG, "probe copy: 16-byte multiples, blocks >= 1");
+    if (!dst || !src || bytes < 0 || (bytes & 15) || blocks == 0) return fail(PMP_ERR_BAD_ARG, "probe copy: 16-byte multiples, blocks != 0");
     int rc = pmp::host_probe_copy(dst, src, bytes, blocks, (cudaStream_t)cuda_stream);
     return rc ? cuda_fail(rc) : PMP_OK;
 }

@@ -664,8 +664,15 @@ __global__ void probe_copy_kernel(uint4* __restrict__ dst, const uint4* __restri
     for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n16; i += (long long)gridDim.x * blockDim.x)
         dst[i] = src[i];
 }
+// blocks < 0: FILL with the 16-byte pattern at src (streaming stores, -blocks CTAs): scripts/exp_dense_prefill.py
+__global__ void __launch_bounds__(256) probe_fill_kernel(uint4* __restrict__ dst, const uint4* __restrict__ pat, long long n16) {
+    const uint4 v = *pat;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n16; i += (long long)gridDim.x * blockDim.x)
+        __stcs(dst + i, v);
+}
 int host_probe_copy(void* dst, const void* src, long long bytes, int blocks, cudaStream_t st) {
-    probe_copy_kernel<<<blocks, 256, 0, st>>>((uint4*)dst, (const uint4*)src, bytes / 16);
+    if (blocks < 0) probe_fill_kernel<<<-blocks, 256, 0, st>>>((uint4*)dst, (const uint4*)src, bytes / 16);
+    else probe_copy_kernel<<<blocks, 256, 0, st>>>((uint4*)dst, (const uint4*)src, bytes / 16);
     return (int)cudaGetLastError();
 }
 

@@ -50,6 +50,11 @@ constexpr long long kWatchdogCycles = 4000000000LL;  // HOSTIO: ~2 s without new
 // lanes that must wait before a warp takes the retire + refill detour (measured on 2^20 flatquad trajectories:
 // fp32 1.41 ms at 1, 1.33 at 4, 1.38 at 8; fp64 4.09 / 4.03 at 3 / 4.27 at 8; vxx 5.49 / 4.90 at 6 / 5.11 at 12)
 constexpr int kRefillMin32 = 4, kRefillMin64 = 3;
+#ifdef PMP_EXP_NOPAD  /* experiment builds (scripts/exp_dense_prefill.py): the dense kernel writes real nodes only */
+constexpr bool kExpNoPad = true;
+#else
+constexpr bool kExpNoPad = false;
+#endif
 constexpr int kRefillMinVxx = 6;  // with the vxx leaf the detour is heavier: 72 more loads, 36 more stores
 
 // ---- value-Hessian branch (PMP_FLAG_VXX, pontryagin_utils.py:460-467) ---------------------------------
@@ -744,7 +749,7 @@ solve_kernel(const typename Sys::Consts sc, const SolveOpts<R> o, const SolveIO<
                 want &= ~took;
                 w_next += __popc(took);
             }
-            if (DENSE) {
+            if (DENSE && !kExpNoPad) {
                 // +inf tails of the retired trajectories (ts: dir*inf), from the end of their last group to the end of
                 // the row: lane f issues the bulk copy of leaf f (bulk_fill); every slot of the output is written once.
                 __syncwarp();
