@@ -94,6 +94,9 @@ class PipelinedGather:
         self.nsets = 2 if self.world > 1 else 1
         self.outs = [[{} for _ in self.slices] for _ in range(self.nsets)]
         self.side = torch.cuda.Stream(device=device) if self.world > 1 else None
+        # a second copy stream: one stream = one copy engine pushed 7 x 59 MB in ~1.2 ms at N = 8, a little longer than the
+        # integration of the next step, and step s+2 waited 0.06 ms per step for step s's pushes to release the local slot
+        self.side2 = torch.cuda.Stream(device=device) if self.world > 2 else None
         self.transport = "none" if self.world == 1 else transport
         self.peer = None
         self.step = 0
@@ -174,9 +177,21 @@ class PipelinedGather:
             with torch.cuda.stream(self.side):
                 self.side.wait_event(ev)
                 if self.transport == "p2p":
-                    for d in range(1, self.world):  # staggered so that not everybody hits the same peer
+                    if self.side2 is not None:  # the pushes to every other peer leave on the second stream
+                        fork = torch.cuda.Event()
+                        fork.record(self.side)  # (behind the "consumed" barrier and the integration of this piece)
+                        with torch.cuda.stream(self.side2):
+                            self.side2.wait_event(fork)
+                            for d in range(2, self.world, 2):
+                                r = (self.rank + d) % self.world
+                                self.peer[s][c][r][rows].copy_(out["y_end"], non_blocking=True)
+                            join = torch.cuda.Event()
+                            join.record(self.side2)
+                    for d in range(1, self.world, 2 if self.side2 is not None else 1):  # staggered: not everybody hits the same peer
                         r = (self.rank + d) % self.world
                         self.peer[s][c][r][rows].copy_(out["y_end"], non_blocking=True)
+                    if self.side2 is not None:
+                        self.side.wait_event(join)
                 else:
                     self._works.append(dist.all_gather_into_tensor(self.gathered[s][c], out["y_end"], group=self.group,
                                                                    async_op=True))

@@ -77,15 +77,17 @@ def _worker(rank, world, port, n_local, q):
     dist.destroy_process_group()
 
 
-def test_sharded_solve_and_gather_two_gpus():
+@pytest.mark.parametrize("world", [2, 4])
+def test_sharded_solve_and_gather_two_gpus(world):
+    """world 4 also covers the second copy stream of the peer pushes (sharding.PipelinedGather.side2, world > 2)"""
     import torch
-    if torch.cuda.device_count() < 2:
-        pytest.skip("needs 2 GPUs")
+    if torch.cuda.device_count() < world:
+        pytest.skip(f"needs {world} GPUs")
     import torch.multiprocessing as mp
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
     port = 29600 + os.getpid() % 300
-    procs = [ctx.Process(target=_worker, args=(r, 2, port, 3001, q)) for r in range(2)]
+    procs = [ctx.Process(target=_worker, args=(r, world, port, 3001, q)) for r in range(world)]
     for p in procs:
         p.start()
     out = [q.get(timeout=300) for _ in procs]
