@@ -20,7 +20,7 @@ LIB_PATH = os.path.join(_PKG, "libb200pmp.so")
 _OBJ_DIR = os.path.join(_PKG, "build")
 
 SOURCES = ["pmp_capi.cu", "pmp_host.cu", "pmp_eval.cu", "pmp_select.cu", "pmp_gather.cu", "pmp_sens.cu", "pmp_interp.cu", "pmp_forward.cu", "pmp_forward_nn.cu", "pmp_forward_cluster.cu", "pmp_forward_tc.cu", "pmp_forward_umma.cu", "pmp_sys_flatquad.cu", "pmp_sys_flatquad_vxx.cu", "pmp_sys_orbits.cu", "pmp_sys_lqr.cu"]
-HEADERS = ["pmp_hostq.h", "pmp_common.cuh", "pmp_systems.cuh", "pmp_tableau.cuh", "pmp_solve.cuh", "pmp_interp.cuh", "pmp_forward.cuh", "pmp_forward_cluster.cuh", "pmp_forward_tc.cuh", "pmp_forward_umma.cuh", "pmp_umma.cuh", "pmp_ustar2d.cuh", "pmp_sens.cuh", "pmp_dual.cuh"]
+HEADERS = ["pmp_hostq.h", "pmp_common.cuh", "pmp_systems.cuh", "pmp_tableau.cuh", "pmp_solve.cuh", "pmp_interp.cuh", "pmp_forward.cuh", "pmp_forward_cluster.cuh", "pmp_forward_tc.cuh", "pmp_forward_umma.cuh", "pmp_umma.cuh", "pmp_ustar2d.cuh", "pmp_sens.cuh", "pmp_dual.cuh", "pmp_dual_math.cuh", "pmp_vxx_dual.cuh"]
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",

@@ -36,7 +36,7 @@ __all__ = ["derive", "emit_header", "build_plugin", "plugin_problem", "Derived",
 
 _PKG = os.path.dirname(os.path.abspath(__file__))
 PLUGIN_DIR = os.path.join(_PKG, "plugins")
-PLUGIN_SOURCES = ["pmp_capi.cu", "pmp_host.cu", "pmp_eval.cu", "pmp_select.cu", "pmp_gather.cu", "pmp_interp.cu", "pmp_forward.cu", "pmp_forward_nn.cu", "pmp_forward_cluster.cu", "pmp_forward_tc.cu", "pmp_forward_umma.cu", "pmp_sens.cu", "pmp_sys_generated.cu"]
+PLUGIN_SOURCES = ["pmp_capi.cu", "pmp_host.cu", "pmp_eval.cu", "pmp_select.cu", "pmp_gather.cu", "pmp_interp.cu", "pmp_forward.cu", "pmp_forward_nn.cu", "pmp_forward_cluster.cu", "pmp_forward_tc.cu", "pmp_forward_umma.cu", "pmp_sens.cu", "pmp_sys_generated.cu", "pmp_sys_generated_vxx.cu"]
 MAX_NX = 16
 
 
@@ -55,6 +55,7 @@ class Derived:
     Huu: list = field(default_factory=list)   # nu == 2: [h00, h01, h11] at u = 0
     num: object = None  # nu == 1: -lambda' df/du at u = 0
     den: object = None  # nu == 1: d2l/du2 at u = 0  (= R + R', R = 1/2 d2l/du2, pontryagin_utils.py:541-556)
+    policy: object = None  # problem_params['ustar_fct']: a feedback law u(x) that takes the place of u* (eval_utils.py:48-99)
 
 
 def _call(fn, x, u):
@@ -95,6 +96,19 @@ def derive(problem_params: dict) -> Derived:
     f = [scalar(e) for e in fr]
     l = scalar(lr[0])
     H = l + sum(li * fi for li, fi in zip(lam, f))
+    if problem_params.get("ustar_fct") is not None:
+        # closed_loop_eval_general(problem_params, algo_params, ustar_fct, x0s): "ustar_fct should be a jax function, X -> U. no
+        # time dependence" (eval_utils.py:50-51).  Traced like f and l; the functor's u* becomes this law (the costate is ignored)
+        try:
+            ur = np.asarray(problem_params["ustar_fct"](xa), dtype=object).reshape(-1)
+        except Exception as e:
+            raise NotImplementedError("codegen: ustar_fct could not be traced with sympy symbols (write it against "
+                                      f"approximate_optimal_control_b200.symnp): {type(e).__name__}: {e}") from e
+        if ur.size != nu:
+            raise ValueError(f"codegen: ustar_fct returned {ur.size} components (nu = {nu})")
+        d = Derived(nx, nu, x, u, lam, f, l, [sp.diff(H, xi) for xi in x])
+        d.policy = [scalar(e) for e in ur]
+        return d
     # the reference's u* formulas assume H quadratic in u (pontryagin_utils.py:30-34)
     for i in range(nu):
         for j in range(i, nu):
@@ -215,7 +229,10 @@ def emit_header(d: Derived, name: str = "user") -> str:
     est32 = 9 * nd + 50  # stage derivatives (7) + state + stage state, + addressing / controller
     minb32 = int(min(4, max(1, 65536 // (128 * min(est32, 255)))))
     minb64 = int(min(3, max(1, 65536 // (128 * min(2 * est32, 255)))))
-    if nu == 2:
+    if d.policy is not None:
+        body_u, n_u = _cse_block(d.policy, [f"u[{i}]" for i in range(nu)], "a")
+        ustar = body_u + "  // the caller's feedback law u(x) (closed_loop_eval_general, eval_utils.py:48-99): no costate, no clipping"
+    elif nu == 2:
         body_u, n_u = _cse_block(d.Hu + d.Huu, ["const R Hu0", "const R Hu1", "const R h00", "const R h01", "const R h11"], "a")
         ustar = f"""{body_u}
         ustar2d_box<R, MODE>(Hu0, Hu1, h00, h01, h11, c.lo[0], c.lo[1], c.hi[0], c.hi[1], u[0], u[1]);"""
@@ -350,7 +367,7 @@ def plugin_problem(problem_params: dict) -> _capi.Problem:
     """pmp_problem_t for a generated system (system_id PMP_SYS_GENERATED) bound to its plug-in library.  Only the first call
     for a system pays the derivation (sympy trace, simplification, cse) and the compilation."""
     key = (problem_params.get("f"), problem_params.get("l"), int(problem_params["nx"]), int(problem_params["nu"]),
-           repr(problem_params["U_interval"]), str(problem_params.get("system_name", "user")))
+           repr(problem_params["U_interval"]), str(problem_params.get("system_name", "user")), problem_params.get("ustar_fct"))
     try:
         path = _plugin_paths.get(key)
     except TypeError:  # unhashable callables

@@ -24,6 +24,8 @@ int generated_nx();
 int generated_nu();
 int solve_generated(const pmp_problem_t&, const pmp_opts_t&, long long, const void*, void*, const pmp_dense_t*,
                     int32_t*, int32_t*, int32_t*, void*, cudaStream_t);
+int solve_generated_vxx(const pmp_problem_t&, const pmp_opts_t&, long long, const void*, void*, const pmp_dense_t*,
+                        int32_t*, int32_t*, int32_t*, void*, cudaStream_t);
 #endif
 int eval_batch(int what, const pmp_problem_t& p, int dtype, long long n, const void* a, const void* b, void* out,
                cudaStream_t st);
@@ -124,13 +126,27 @@ int check_opts(const pmp_opts_t* o) {
     }
     return 0;
 }
+// PMP_FLAG_VXX: the hand-written flatquad functor carries closed-form Jacobians through u*; a generated functor is
+// differentiated in forward mode (pmp_vxx_dual.cuh); V_xx and its stage derivatives must fit one CTA's shared memory.
+// orbits / LQR run through u_star_new in the reference, which has no vxx branch.
+int check_vxx_system(const pmp_problem_t* p, int32_t flags) {
+    if (!(flags & PMP_FLAG_VXX)) return 0;
+    if (p->system_id == PMP_SYS_GENERATED) {
+        if (p->nx > 9) return fail(PMP_ERR_UNSUPPORTED, "PMP_FLAG_VXX on a generated system: nx <= 9 (V_xx and its stage derivatives live in shared memory)");
+        return 0;
+    }
+    if (p->system_id != PMP_SYS_FLATQUAD)
+        return fail(PMP_ERR_UNSUPPORTED, "PMP_FLAG_VXX: flatquad and generated systems only (the reference's vxx branch runs through u_star_2d)");
+    return 0;
+}
 // options that need a particular system
 int check_pair(const pmp_problem_t* p, const pmp_opts_t* o) {
     if (o->event == PMP_EVENT_LQR_VALUE_LE || o->event == PMP_EVENT_NN_VALUE_UCB_LE)
         return fail(PMP_ERR_BAD_ARG, "this event belongs to pmp_forward_batch_cuda / pmp_forward_nn_batch_cuda (the backward "
                                      "solve has no costate law)");
-    if ((o->flags & PMP_FLAG_VXX) && p->system_id != PMP_SYS_FLATQUAD)  // (a plug-in never is)
-        return fail(PMP_ERR_UNSUPPORTED, "PMP_FLAG_VXX: only the flatquad functor carries the Jacobians through u*");
+    if (int e = check_vxx_system(p, o->flags)) return e;
+    if ((o->flags & PMP_FLAG_VXX) && p->system_id == PMP_SYS_GENERATED && o->method == PMP_METHOD_DOPRI5)
+        return fail(PMP_ERR_UNSUPPORTED, "PMP_FLAG_VXX on a generated system: Tsit5 (the reference's solver for this branch) or RK4");
     return 0;
 }
 int64_t vxx_rows(const pmp_problem_t* p, int32_t flags) { return (flags & PMP_FLAG_VXX) ? (int64_t)p->nx * p->nx : 0; }
@@ -171,7 +187,7 @@ int pmp_state_rows(const pmp_problem_t* p) {
 
 int pmp_state_rows_flags(const pmp_problem_t* p, int32_t flags) {
     if (int e = check_problem(p)) return e;
-    if ((flags & PMP_FLAG_VXX) && p->system_id != PMP_SYS_FLATQUAD) return fail(PMP_ERR_UNSUPPORTED, "PMP_FLAG_VXX: flatquad only");
+    if (int e = check_vxx_system(p, flags)) return e;
     return 2 * p->nx + 2 + (int)vxx_rows(p, flags);
 }
 
@@ -228,7 +244,8 @@ int pmp_solve_batch_cuda(const pmp_problem_t* p, const pmp_opts_t* o, int64_t n,
     cudaStream_t st = (cudaStream_t)cuda_stream;
     int rc = -1000;
 #ifdef PMP_PLUGIN
-    rc = pmp::solve_generated(*p, *o, n, y_f, y_end, dense, n_accepted, n_steps, result, workspace, st);
+    if (o->flags & PMP_FLAG_VXX) rc = pmp::solve_generated_vxx(*p, *o, n, y_f, y_end, dense, n_accepted, n_steps, result, workspace, st);
+    else rc = pmp::solve_generated(*p, *o, n, y_f, y_end, dense, n_accepted, n_steps, result, workspace, st);
 #else
     switch (p->system_id) {
         case PMP_SYS_FLATQUAD:
@@ -394,7 +411,7 @@ int pmp_rhs_batch_cuda_flags(const pmp_problem_t* p, int32_t dtype, int32_t flag
     }
     if (int e = check_problem(p)) return e;
     if (flags != PMP_FLAG_VXX) return fail(PMP_ERR_BAD_ARG, "pmp_rhs_batch_cuda_flags: only PMP_FLAG_VXX is meaningful here");
-    if (p->system_id != PMP_SYS_FLATQUAD) return fail(PMP_ERR_UNSUPPORTED, "PMP_FLAG_VXX: flatquad only");
+    if (int e = check_vxx_system(p, flags)) return e;
     if (dtype != PMP_F32 && dtype != PMP_F64) return fail(PMP_ERR_BAD_ARG, "dtype must be 0 (f32) or 1 (f64)");
     if (n < 0 || (n > 0 && (!y || !dy))) return fail(PMP_ERR_BAD_ARG, "bad n or NULL buffers");
     if (n == 0) return PMP_OK;

@@ -4,6 +4,9 @@
 //                  (batched over all saved nodes at levelsets.py:604-628)
 #include "pmp_common.cuh"
 #include "pmp_systems.cuh"
+#ifdef PMP_PLUGIN
+#include "pmp_vxx_dual.cuh"
+#endif
 
 namespace pmp {
 
@@ -80,15 +83,20 @@ int eval_dispatch(int what, const pmp_problem_t& p, int dtype, long long n, cons
 
 int eval_batch(int what, const pmp_problem_t& p, int dtype, long long n, const void* a, const void* b, void* out,
                cudaStream_t st) {
-#ifndef PMP_PLUGIN
-    if (what == 3) {  // f_extended with the vxx leaf: flatquad only (checked by the caller)
+    if (what == 3) {  // f_extended with the vxx leaf: flatquad (closed-form Jacobians) or the generated functor (forward mode)
         if (n == 0) return 0;
         const unsigned grid = (unsigned)((n + 127) / 128);
-        if (dtype == PMP_F32) rhs_vxx_kernel<Flatquad<float>, float><<<grid, 128, 0, st>>>(Flatquad<float>::make(p), (const float*)a, (float*)out, n);
-        else rhs_vxx_kernel<Flatquad<double>, double><<<grid, 128, 0, st>>>(Flatquad<double>::make(p), (const double*)a, (double*)out, n);
+#ifdef PMP_PLUGIN
+        using SF = DualVxx<Generated, float>;
+        using SD = DualVxx<Generated, double>;
+#else
+        using SF = Flatquad<float>;
+        using SD = Flatquad<double>;
+#endif
+        if (dtype == PMP_F32) rhs_vxx_kernel<SF, float><<<grid, 128, 0, st>>>(SF::make(p), (const float*)a, (float*)out, n);
+        else rhs_vxx_kernel<SD, double><<<grid, 128, 0, st>>>(SD::make(p), (const double*)a, (double*)out, n);
         return (int)cudaGetLastError();
     }
-#endif
 #ifdef PMP_PLUGIN
     return eval_dispatch<Generated>(what, p, dtype, n, a, b, out, st);
 #else

@@ -10,42 +10,11 @@
 // controller sees values only, so the primal part of the result is the solve the integrator itself produces.
 // One thread per trajectory (this is not the throughput path: the caller differentiates a few thousand characteristics).
 #pragma once
-#include "pmp_solve.cuh"  // (Dual<R> itself lives in pmp_dual.cuh, included by pmp_common.cuh)
+#include "pmp_solve.cuh"      // (Dual<R> itself lives in pmp_dual.cuh, included by pmp_common.cuh)
+#include "pmp_dual_math.cuh"  // Math<Dual<R>>
 
 namespace pmp {
 
-template <class R> struct Math<Dual<R>> {
-    using D = Dual<R>;
-    using MR = Math<R>;
-    static __device__ __forceinline__ D fma(D a, D b, D c) { return D(MR::fma(a.v, b.v, c.v), MR::fma(a.d, b.v, MR::fma(a.v, b.d, c.d))); }
-    static __device__ __forceinline__ void sincos(D x, D* s, D* c) {
-        R sv, cv;
-        MR::sincos(x.v, &sv, &cv);
-        *s = D(sv, cv * x.d);
-        *c = D(cv, -sv * x.d);
-    }
-    static __device__ __forceinline__ D abs(D x) { return x.v < R(0) ? -x : x; }
-    // fmax / fmin semantics on the value (a NaN operand is dropped); the tangent follows the operand that was chosen
-    static __device__ __forceinline__ D max(D a, D b) { return (a.v != a.v) ? b : ((b.v != b.v) ? a : (a.v >= b.v ? a : b)); }
-    static __device__ __forceinline__ D min(D a, D b) { return (a.v != a.v) ? b : ((b.v != b.v) ? a : (a.v <= b.v ? a : b)); }
-    static __device__ __forceinline__ D sat(D x) { return (x.v > R(0) && x.v < R(1)) ? x : D(MR::sat(x.v)); }
-    static __device__ __forceinline__ D copy(D x, D) { return x; }
-    static __device__ __forceinline__ D sqrt(D x) { const R s = MR::sqrt(x.v); return D(s, x.d / (s + s)); }
-    static __device__ __forceinline__ D div(D a, D b) { const R q = MR::div(a.v, b.v); return D(q, MR::div(a.d - q * b.d, b.v)); }
-    static __device__ __forceinline__ D rcp(D x) { return div(D(R(1)), x); }
-    static __device__ __forceinline__ D ctl_div(D a, D b) { return D(MR::ctl_div(a.v, b.v)); }            // step control: value only
-    static __device__ __forceinline__ D pow_neg_inv(D x, D e) { return D(MR::pow_neg_inv(x.v, e.v)); }   // step control: value only
-    static __device__ __forceinline__ D inf() { return D(MR::inf()); }
-    static __device__ __forceinline__ D nan() { return D(MR::nan()); }
-    static __device__ __forceinline__ D clip_tol() { return D(MR::clip_tol()); }
-    struct V2 { D x, y; };
-    static __device__ __forceinline__ V2 mk2(D a, D b) { V2 r; r.x = a; r.y = b; return r; }
-    static __device__ __forceinline__ V2 fma2(D c, V2 a, V2 b) { return mk2(fma(c, a.x, b.x), fma(c, a.y, b.y)); }
-    static __device__ __forceinline__ V2 fma2v(V2 c, V2 a, V2 b) { return mk2(fma(c.x, a.x, b.x), fma(c.y, a.y, b.y)); }
-    static __device__ __forceinline__ V2 mul2(D c, V2 a) { return mk2(c * a.x, c * a.y); }
-    static __device__ __forceinline__ V2 mul2v(V2 c, V2 a) { return mk2(c.x * a.x, c.y * a.y); }
-    static __device__ __forceinline__ V2 add2(D c, V2 a) { return mk2(c + a.x, c + a.y); }
-};
 // PairMap of the underlying system (the pairing is a property of the dynamics, not of the scalar)
 template <class R> struct PairMap<Flatquad<Dual<R>>> : PairMap<Flatquad<R>> {};
 

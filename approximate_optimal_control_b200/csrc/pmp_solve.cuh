@@ -831,15 +831,19 @@ solve_kernel(const typename Sys::Consts sc, const SolveOpts<R> o, const SolveIO<
         R sumsq_base = R(0);                // VXX: base leaves' share of the squared error norm
         if constexpr (VXX != 0) {
             // ---- phase A: every base stage, in registers, exactly as without the vxx leaf; one JacPrim per stage
-            R ps[S], pc[S], pm[S], pu[S], px[S];
+            constexpr int NP = Sys::NPRIM;  // reals of a JacPrim (flatquad: 5; pmp_vxx_dual.cuh: the stage state, 2 nx)
+            R pr[NP][S];
             int acts = 0;
             auto base_stage = [&](int i, const R* yy) {
                 typename Sys::JacPrim p;
-                R vd;
+                R vd, pa[NP];
+                int act;
                 Sys::rhs_prim(sc, yy, yy + NX, k[i], vd, k[i] + NX, p);
                 k[i][AUX] = vd;
-                ps[i] = p.s; pc[i] = p.co; pm[i] = p.Sm; pu[i] = p.hxu2; px[i] = p.hxx22;
-                acts |= p.act << (2 * i);
+                Sys::prim_store(p, pa, act);
+#pragma unroll
+                for (int m = 0; m < NP; m++) pr[m][i] = pa[m];
+                acts |= act << (2 * i);
             };
             if (!TB::FSAL) base_stage(0, y);
 #pragma unroll
@@ -874,9 +878,10 @@ solve_kernel(const typename Sys::Consts sc, const SolveOpts<R> o, const SolveIO<
             // ---- phase B: the V_xx stages, a RUNTIME loop over one copy of the stage code (see vxx_stage)
             auto coef_of = [&](int i, typename Sys::JacCoef& jc) {
                 typename Sys::JacPrim p;
-                p.s = pick<R, S>(ps, i); p.co = pick<R, S>(pc, i); p.Sm = pick<R, S>(pm, i);
-                p.hxu2 = pick<R, S>(pu, i); p.hxx22 = pick<R, S>(px, i);
-                p.act = (acts >> (2 * i)) & 3;
+                R pa[NP];
+#pragma unroll
+                for (int m = 0; m < NP; m++) pa[m] = pick<R, S>(pr[m], i);
+                Sys::prim_load(p, pa, (acts >> (2 * i)) & 3);
                 Sys::jac_from_prim(sc, p, jc);
             };
 #pragma unroll 1
@@ -1165,7 +1170,8 @@ int launch_hostq(const pmp_problem_t& p, const pmp_opts_t& o, long long n, const
 }
 
 // PMP_FLAG_VXX instantiations (time-parameterised, KKT-form u*): a compile unit of their own
-template <template <class> class SysT>
+// METHODS: bit PMP_METHOD_x set = instantiate that method (plug-ins build Tsit5 -- the reference's only vxx solver -- and RK4)
+template <template <class> class SysT, int METHODS = 7>
 int launch_solve_vxx(const pmp_problem_t& p, const pmp_opts_t& o, long long n, const void* y_f, void* y_end,
                      const pmp_dense_t* dense, int32_t* a, int32_t* s, int32_t* r, void* ws, cudaStream_t st) {
     const bool dn = o.save_dense != 0, sym = (o.flags & PMP_FLAG_VXX_SYMMETRIC) != 0;
@@ -1179,9 +1185,9 @@ int launch_solve_vxx(const pmp_problem_t& p, const pmp_opts_t& o, long long n, c
     } while (0)
 #define PMP_BY_METHODV(R)                                              \
     do {                                                               \
-        if (o.method == PMP_METHOD_RK4) PMP_GOV(R, PMP_METHOD_RK4);       \
-        if (o.method == PMP_METHOD_TSIT5) PMP_GOV(R, PMP_METHOD_TSIT5);   \
-        if (o.method == PMP_METHOD_DOPRI5) PMP_GOV(R, PMP_METHOD_DOPRI5); \
+        if constexpr ((METHODS >> PMP_METHOD_RK4) & 1) if (o.method == PMP_METHOD_RK4) PMP_GOV(R, PMP_METHOD_RK4);          \
+        if constexpr ((METHODS >> PMP_METHOD_TSIT5) & 1) if (o.method == PMP_METHOD_TSIT5) PMP_GOV(R, PMP_METHOD_TSIT5);    \
+        if constexpr ((METHODS >> PMP_METHOD_DOPRI5) & 1) if (o.method == PMP_METHOD_DOPRI5) PMP_GOV(R, PMP_METHOD_DOPRI5); \
     } while (0)
     if (o.dtype == PMP_F32) PMP_BY_METHODV(float);
     if (o.dtype == PMP_F64) PMP_BY_METHODV(double);

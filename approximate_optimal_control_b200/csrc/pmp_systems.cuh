@@ -294,6 +294,17 @@ template <class R> struct Flatquad {
         int act;                   // 0 interior, 1 / 2 edge with u0 / u1 moving freely, 3 corner
     };
 
+    // the reals of a JacPrim as an array (the integrator keeps one register array per entry across the base stages)
+    static constexpr int NPRIM = 5;
+    static __device__ __forceinline__ void prim_store(const JacPrim& p, R* a, int& act) {
+        a[0] = p.s; a[1] = p.co; a[2] = p.Sm; a[3] = p.hxu2; a[4] = p.hxx22;
+        act = p.act;
+    }
+    static __device__ __forceinline__ void prim_load(JacPrim& p, const R* a, int act) {
+        p.s = a[0]; p.co = a[1]; p.Sm = a[2]; p.hxu2 = a[3]; p.hxx22 = a[4];
+        p.act = act;
+    }
+
     // rhs<2> (KKT-form u*) that also reports the Jacobian primitives
     static __device__ __forceinline__ void rhs_prim(const Consts& c, const R* x, const R* lam, R* xd, R& vd, R* ld,
                                                     JacPrim& p) {

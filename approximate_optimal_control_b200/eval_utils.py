@@ -4,8 +4,8 @@ costate laws the CUDA path can evaluate.
     closed_loop_eval_nn_ensemble(problem_params, algo_params, V_nn, nn_params, x0s)   eval_utils.py:10-45
     closed_loop_eval_lqr(problem_params, algo_params, P_lqr, x0s)     the same with lambda(x) = P (x - x_eq)
     compute_controlcost(problem_params, all_sols)                     eval_utils.py:101-107
-    closed_loop_eval_general(..., ustar_fct, ...)                     eval_utils.py:48-99: an arbitrary jax u*(x) callable
-                                                                      cannot enter a compiled kernel -> NotImplementedError
+    closed_loop_eval_general(problem_params, algo_params, ustar_fct, x0s)   eval_utils.py:48-99: the feedback law is traced
+                                                                      with sympy and compiled into a plug-in (codegen.py)
 
 z = (x, cost), z' = (f(x,u*), l(x,u*)), Tsit5 with the CONSTANT step algo_params['sim_dt'] from 0 to
 algo_params['sim_T'], max_steps = T/dt, SaveAt(steps=True): all_sols.ys has shape (N, T/dt, nx+1).
@@ -20,8 +20,16 @@ from .solution import Solution
 
 
 def closed_loop_eval_general(problem_params, algo_params, ustar_fct, x0s):
-    raise NotImplementedError("closed_loop_eval_general takes an arbitrary jax u*(x) callable; the CUDA path evaluates costate "
-                              "laws it has compiled: use closed_loop_eval_lqr (lambda = P (x - x_eq))")
+    """eval_utils.py:48-99: closed loop under an arbitrary feedback law `ustar_fct: X -> U` ("should be a jax function ... no
+    time dependence"), one extra state recording the control cost.  The law is traced with sympy like f and l (write it against
+    approximate_optimal_control_b200.symnp where the reference's script says jax.numpy) and compiled, together with f and l,
+    into a plug-in whose u*(x, lambda) IS that law; the forward kernel then runs with a zero costate."""
+    pp = dict(problem_params)
+    pp["ustar_fct"] = ustar_fct
+    pp["codegen"] = True
+    pp["system_name"] = str(problem_params.get("system_name", "user")) + "_with_feedback_law"
+    nx = int(pp["nx"])
+    return _closed_loop_eval(pp, algo_params, x0s, P=torch.zeros((nx, nx), dtype=torch.float64))
 
 
 def closed_loop_eval_nn_ensemble(problem_params, algo_params, V_nn, nn_params, x0s):

@@ -424,9 +424,12 @@ def define_backward_solver(problem_params: dict, algo_params: dict):
     nx = problem.nx
     # pontryagin_utils.py:425,460: also propagate the value Hessian ('vxx' leaf of the state)
     with_vxx = bool(algo_params.get("pontryagin_solver_vxx", False))
-    if with_vxx and problem.system_id != _capi.SYS_FLATQUAD:  # (generated functors included)
-        raise NotImplementedError("pontryagin_solver_vxx=True: only the flatquad functor carries the Jacobians "
-                                  "of the PMP right hand side through u*")
+    # flatquad: closed-form Jacobians of pmp_rhs through u*; generated functors: forward-mode differentiation of the
+    # generated code (csrc/pmp_vxx_dual.cuh), as the reference's jax.jacobian(pmp_rhs) handles any f, l.  orbits / LQR are
+    # u_star_new systems: the reference has no vxx branch for them (its define_backward_solver goes through u_star_2d)
+    if with_vxx and problem.system_id not in (_capi.SYS_FLATQUAD, _capi.SYS_GENERATED):
+        raise NotImplementedError("pontryagin_solver_vxx=True: flatquad and generated systems (problem_params['codegen'] = "
+                                  "True) only; the reference's vxx branch runs through u_star_2d")
 
     def f_extended(t, state, args=None):
         """RHS of the extended system in forward time (pontryagin_utils.py:418-482)."""

@@ -250,6 +250,20 @@ def vxx_rhs(problem: Problem, x, lam, vxx):
     return jac[0], jac[1], jac[2], jac[3], out
 
 
+def vxx_rhs_fwd(problem: Problem, x, lam, vxx):
+    """any system: (fx, flam, gx, glam, vxx_dot) by forward-mode differentiation of the oracle's pmp_rhs (dual numbers), the
+    construction of the CUDA adaptor for generated functors (csrc/pmp_vxx_dual.cuh); fp64, one state per call."""
+    x = np.ascontiguousarray(x, np.float64); lam = np.ascontiguousarray(lam, np.float64)
+    vxx = np.ascontiguousarray(vxx, np.float64)
+    nx = x.shape[0]
+    jac = np.zeros((4, nx, nx)); out = np.zeros((nx, nx))
+    L = lib()
+    L.pmp_oracle_vxx_rhs_fwd.argtypes = [C.POINTER(Problem), C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+    _check(L.pmp_oracle_vxx_rhs_fwd(C.byref(problem), x.ctypes.data, lam.ctypes.data, vxx.ctypes.data, jac.ctypes.data,
+                                    out.ctypes.data))
+    return jac[0], jac[1], jac[2], jac[3], out
+
+
 class NnCostate(C.Structure):
     _fields_ = [("n_nets", C.c_int32), ("n_hidden_layers", C.c_int32), ("width", C.c_int32), ("reserved", C.c_int32),
                 ("weights", C.c_void_p), ("x_mean", C.c_double * 16), ("x_std", C.c_double * 16),

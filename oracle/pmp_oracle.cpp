@@ -215,6 +215,49 @@ int pmp_oracle_vxx_rhs(const pmp_problem_t* p, const double* x, const double* la
     return 0;
 }
 
+// Any system: the same quantities by FORWARD-MODE differentiation of the oracle's own pmp_rhs (dual numbers through u*, decisions
+// on values -- what jax.jacobian(pmp_rhs, argnums=(0, 1)) does at pontryagin_utils.py:462), the way the CUDA adaptor for generated
+// functors forms them (csrc/pmp_vxx_dual.cuh).  jac_out = fx, flam, gx, glam (4 x nx*nx) from 2 nx passes; vxx_dot_out from nx
+// passes along (e_j, vxx e_j):  vxx'[:, j] = d lamdot - vxx d xdot.  fp64, one state per call.
+int pmp_oracle_vxx_rhs_fwd(const pmp_problem_t* p, const double* x, const double* lam, const double* vxx, double* jac_out,
+                           double* vxx_dot_out) {
+    if (int e = check(p, nullptr)) return e;
+    auto run = [&](auto sys) {
+        using Sys = decltype(sys);
+        constexpr int NX = Sys::NX, NS = 2 * NX + 2, NV = NX * NX;
+        auto pass = [&](const double* dx, const double* dlam, double* dxd, double* dld) {
+            Dual y[NS], dy[NS];
+            for (int q = 0; q < NX; q++) { y[q] = Dual(x[q], dx[q]); y[NX + 2 + q] = Dual(lam[q], dlam[q]); }
+            y[NX] = Dual(0.0); y[NX + 1] = Dual(0.0);
+            sys.rhs(y, dy);
+            for (int q = 0; q < NX; q++) { dxd[q] = dy[q].d; dld[q] = dy[NX + 2 + q].d; }
+        };
+        double zero[NX], unit[NX], a[NX], b[NX];
+        for (int q = 0; q < NX; q++) zero[q] = 0.0;
+        for (int j = 0; j < NX; j++) {
+            for (int q = 0; q < NX; q++) unit[q] = q == j ? 1.0 : 0.0;
+            pass(unit, zero, a, b);  // d/dx_j
+            for (int i = 0; i < NX; i++) { jac_out[i * NX + j] = a[i]; jac_out[2 * NV + i * NX + j] = b[i]; }
+            pass(zero, unit, a, b);  // d/dlam_j
+            for (int i = 0; i < NX; i++) { jac_out[NV + i * NX + j] = a[i]; jac_out[3 * NV + i * NX + j] = b[i]; }
+            double col[NX];
+            for (int q = 0; q < NX; q++) col[q] = vxx[q * NX + j];
+            pass(unit, col, a, b);
+            for (int i = 0; i < NX; i++) {
+                double acc = b[i];
+                for (int k = 0; k < NX; k++) acc -= vxx[i * NX + k] * a[k];
+                vxx_dot_out[i * NX + j] = acc;
+            }
+        }
+    };
+    switch (p->system_id) {
+        case PMP_SYS_FLATQUAD: run(Flatquad<Dual>(*p)); return 0;
+        case PMP_SYS_ORBITS: run(Orbits<Dual>(*p)); return 0;
+        case PMP_SYS_LQR_STATEPENALTY: run(LqrStatePenalty<Dual>(*p)); return 0;
+    }
+    return fail(PMP_ERR_UNSUPPORTED, "unknown system_id");
+}
+
 // costate law of the ensemble at n points: x [nx][n] -> lam [nx][n], vmean [n], vstd [n]   (fp64 weights)
 int pmp_oracle_nn_costate(const pmp_nn_costate_t* nn, int32_t nx, int64_t n, const double* x, double* lam, double* vmean,
                           double* vstd) {

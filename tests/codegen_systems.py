@@ -84,3 +84,34 @@ def numpy_field(pp):
         return onp.asarray(f, dtype=float), -float(l), -onp.asarray(hx, dtype=float), u
 
     return field
+
+
+# ---- caller-supplied feedback laws for eval_utils.closed_loop_eval_general (eval_utils.py:48-99) -------------------------
+def lqr_feedback_law(P, r_u=1.0, lo=-1.0, hi=1.0):
+    """the LQR law of the double integrator as a plain function of x: lambda = P x, u = clip(-lambda_1 / (2 r_u), U)
+    (what closed_loop_eval_lqr + the hand-written functor's u_star_new compute)."""
+    P = onp.asarray(P, dtype=float)
+
+    def law(x):
+        lam1 = P[1, 0] * x[0] + P[1, 1] * x[1]
+        return np.array([np.clip(-lam1 / (2.0 * r_u), lo, hi)])
+    return law
+
+
+def pendulum_feedback_law():
+    def law(x):
+        return np.array([np.clip(-(3.0 * x[0] + 1.5 * x[1]) + 0.2 * np.sin(x[0]), -2.0, 2.0)])
+    return law
+
+
+def numpy_closed_loop(pp, law):
+    """(f(x, u(x)), l(x, u(x)), u(x)) as numpy callables, by lambdifying the traced expressions."""
+    import sympy as sp
+    from approximate_optimal_control_b200 import codegen
+    d = codegen.derive(dict(pp, ustar_fct=law))
+    sub = dict(zip(d.u, d.policy))
+    mods = [{"Max": onp.maximum, "Min": onp.minimum}, "numpy"]
+    f = sp.lambdify([d.x], [e.subs(sub) for e in d.f], modules=mods)
+    l = sp.lambdify([d.x], d.l.subs(sub), modules=mods)
+    u = sp.lambdify([d.x], d.policy[0], modules=mods)
+    return (lambda x: onp.asarray(f(x), dtype=float)), (lambda x: float(l(x))), (lambda x: float(u(x)))

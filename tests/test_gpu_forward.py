@@ -103,13 +103,49 @@ def test_forward_public_api_and_generated_functor():
     assert abs(mean_cost - ref["z_end"][6].mean()) <= 1e-8 * abs(mean_cost)
     # infinite-horizon cost-to-go from the LQR level set V = 1.6 under the LQR law: a little above V (u saturates)
     assert 1.5 < mean_cost < 2.5
-    with pytest.raises(NotImplementedError):
-        eval_utils.closed_loop_eval_general(pp, ev, lambda x: x, x0)
     gen = dict(pp, codegen=True)
     sol_g = levelsets.forward_sim_lqr(gen, ap, P)(x0)
     assert float((sol_g.stats["num_steps"] == sol.stats["num_steps"]).float().mean()) >= 0.98
     same = sol_g.stats["num_steps"] == sol.stats["num_steps"]
     assert float((sol_g.y_end["cost"] - sol.y_end["cost"]).abs()[same].max()) <= 1e-6
+
+
+def test_closed_loop_eval_general_with_a_user_feedback_law():
+    """eval_utils.closed_loop_eval_general (eval_utils.py:48-99) with a caller-supplied u*(x): the law is traced and compiled
+    into a plug-in (codegen.py).  (1) The LQR law of the double integrator written out as such a function reproduces
+    closed_loop_eval_lqr on the hand-written functor; (2) a saturated linear feedback on the pendulum (a system that exists
+    nowhere else) against scipy on the same closed loop."""
+    import scipy.integrate
+    import torch
+    import codegen_systems as CS
+    from common import lqr_P
+    pp = systems.lqr_statepenalty_problem_params()
+    P = np.round(lqr_P(), 12)  # (rounded: the law's constants are part of the plug-in's content hash, prebuilt by build())
+    ev = {"sim_T": 4.0, "sim_dt": 1 / 32, "dtype": "float64"}
+    rng = np.random.Generator(np.random.PCG64(2))
+    x0 = rng.uniform(-1.5, 1.5, (64, 2))
+    a = eval_utils.closed_loop_eval_lqr(pp, ev, P, x0)
+    b = eval_utils.closed_loop_eval_general(pp, ev, CS.lqr_feedback_law(P), x0)
+    assert b.ys.shape == a.ys.shape == (64, 128, 3)
+    assert float((a.ys - b.ys).abs().max()) <= 1e-11 * float(a.ys.abs().max())
+    assert abs(float(eval_utils.compute_controlcost(pp, a)) - float(eval_utils.compute_controlcost(pp, b))) <= 1e-10
+    # pendulum under u = clip(-k.x): constant-step Tsit5 (dt = 1/64) against DOP853 at 1e-12
+    pq = CS.pendulum_problem_params()
+    law = CS.pendulum_feedback_law()
+    x0 = rng.uniform(-1.0, 1.0, (8, 2))
+    fnp, lnp, unp = CS.numpy_closed_loop(pq, law)
+    refs = [scipy.integrate.solve_ivp(lambda t, z: np.concatenate([fnp(z[:2]), [lnp(z[:2])]]), (0.0, 2.0), np.concatenate([x0[i], [0.0]]),
+                                      method="DOP853", rtol=1e-12, atol=1e-13).y[:, -1] for i in range(8)]
+    errs = []
+    for steps in (128, 512):  # the constant step crosses the saturation kink with an O(dt^2) error: it must shrink with dt
+        ev = {"sim_T": 2.0, "sim_dt": 2.0 / steps, "dtype": "float64"}
+        sol = eval_utils.closed_loop_eval_general(pq, ev, law, x0)
+        assert sol.ys.shape == (8, steps, 3) and bool((sol.result == 0).all())
+        got = sol.ys[:, -1].cpu().numpy()
+        errs.append(max(np.abs(got[i] - refs[i]).max() / (1 + np.abs(refs[i]).max()) for i in range(8)))
+    assert errs[0] <= 5e-4 and errs[1] <= 2e-5 and errs[1] <= errs[0] / 4, errs
+    sat = np.abs(np.array([unp(x) for x in x0])) >= 2.0 - 1e-12
+    assert sat.any() and not sat.all()  # the sample starts on both sides of the saturation
 
 
 # ---- value-network ensemble as the costate law (levelsets.py:838-933, eval_utils.py:10-45) -------------------------

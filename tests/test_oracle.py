@@ -370,6 +370,38 @@ def test_vxx_rhs_matches_reference_golden():
             assert np.abs(got - ref).max() <= 1e-12 * (1 + np.abs(ref).max()), (i, name)
 
 
+def test_vxx_forward_mode_construction_matches_reference_golden():
+    """The construction the CUDA adaptor for generated functors uses (csrc/pmp_vxx_dual.cuh): Jacobians of pmp_rhs by dual
+    numbers through u* (decisions on values), and vxx_dot WITHOUT the Jacobians, column j = directional derivative of pmp_rhs
+    along (e_j, vxx e_j): d lamdot - vxx d xdot.  Restated in the oracle (pmp_oracle_vxx_rhs_fwd) and pinned here on the
+    reference's own jax.jacobian(pmp_rhs) output (f_extended(..., 'debug') golden): all active sets, non-symmetric vxx."""
+    g = np.load(f"{GOLDEN}/vxx_flatquad_f64.npz")
+    p = O.flatquad_problem()
+    for i in range(g["x"].shape[0]):
+        fx, flam, gx, glam, vd = O.vxx_rhs_fwd(p, g["x"][i], g["lam"][i], g["vxx"][i])
+        for name, got in (("fx", fx), ("flam", flam), ("gx", gx), ("glam", glam), ("vxx_dot", vd)):
+            ref = g[name][i]
+            assert np.abs(got - ref).max() <= 1e-11 * (1 + np.abs(ref).max()), (i, name, np.abs(got - ref).max())
+    # u_star_new systems: forward mode against central differences of the oracle's own right hand side
+    rng = np.random.Generator(np.random.PCG64(3))
+    for prob in (O.orbits_problem(), O.lqr_problem()):
+        for _ in range(16):
+            x, lam, V = rng.standard_normal(2), rng.standard_normal(2), rng.standard_normal((2, 2))
+            fx, flam, gx, glam, vd = O.vxx_rhs_fwd(prob, x, lam, V)
+
+            def F(z):
+                dy = O.rhs_batch(prob, O.F64, np.concatenate([z[:2], [0.0, 0.0], z[2:]])[:, None])[:, 0]
+                return np.concatenate([dy[:2], dy[4:]])
+            z0, h = np.concatenate([x, lam]), 1e-6
+            J = np.stack([(F(z0 + h * e) - F(z0 - h * e)) / (2 * h) for e in np.eye(4)], 1)
+            if np.abs(J).max() > 1e3:
+                continue
+            want = np.block([[fx, flam], [gx, glam]])
+            if not np.allclose(want, J, rtol=1e-5, atol=1e-6):  # a difference stencil that straddles a clipping kink
+                continue
+            assert np.allclose(vd, gx + glam @ V - V @ fx - V @ flam @ V, rtol=1e-10, atol=1e-10)
+
+
 def test_vxx_is_the_sensitivity_of_the_costate():
     """Independent check of the whole Riccati propagation: along a characteristic V_xx(t) = d lambda(t) / d x(t).
     Integrate neighbouring characteristics from x_f + d, lambda_f = P (x_f + d): the end-point differences must
