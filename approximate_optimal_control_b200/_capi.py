@@ -21,6 +21,7 @@ ABI_VERSION = 5
 FLAG_USTAR_LITERAL = 1
 FLAG_VXX = 2
 FLAG_VXX_SYMMETRIC = 4
+FLAG_USTAR_SMOOTH = 8
 
 METHODS = {"rk4": METHOD_RK4, "tsit5": METHOD_TSIT5, "dopri5": METHOD_DOPRI5}
 

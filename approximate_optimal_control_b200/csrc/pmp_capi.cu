@@ -515,11 +515,13 @@ int pmp_ustar_batch_cuda_flags(const pmp_problem_t* p, int32_t dtype, int32_t fl
                                const void* lam, void* u, void* cuda_stream) {
     if (int e = check_problem(p)) return e;
     if (dtype != PMP_F32 && dtype != PMP_F64) return fail(PMP_ERR_BAD_ARG, "dtype must be 0 (f32) or 1 (f64)");
-    if ((flags & ~PMP_FLAG_USTAR_LITERAL) != 0) return fail(PMP_ERR_BAD_ARG, "unknown flags");
+    if (flags != PMP_FLAG_USTAR_SMOOTH && (flags & ~PMP_FLAG_USTAR_LITERAL) != 0) return fail(PMP_ERR_BAD_ARG, "unknown flags");
+    if (flags == PMP_FLAG_USTAR_SMOOTH && p->nu != 2) return fail(PMP_ERR_UNSUPPORTED, "PMP_FLAG_USTAR_SMOOTH: u_star_2d is for nu == 2");
     if (n < 0 || (n > 0 && (!x || !lam || !u))) return fail(PMP_ERR_BAD_ARG, "bad n or NULL buffers");
     if (n == 0) return PMP_OK;
     if (pmp_device_count() <= 0) return fail(PMP_ERR_NO_DEVICE, "no CUDA device: libb200pmp has no CPU fallback");
-    int rc = pmp::eval_batch((flags & PMP_FLAG_USTAR_LITERAL) ? 1 : 2, *p, dtype, n, x, lam, u, (cudaStream_t)cuda_stream);
+    const int what = flags == PMP_FLAG_USTAR_SMOOTH ? 4 : ((flags & PMP_FLAG_USTAR_LITERAL) ? 1 : 2);
+    int rc = pmp::eval_batch(what, *p, dtype, n, x, lam, u, (cudaStream_t)cuda_stream);
     return rc ? cuda_fail(rc) : PMP_OK;
 }
 

@@ -71,11 +71,13 @@ int eval_dispatch(int what, const pmp_problem_t& p, int dtype, long long n, cons
         using S = SysT<float>;
         if (what == 0) rhs_kernel<S, float><<<grid, 256, 0, st>>>(S::make(p), (const float*)a, (float*)out, n);
         else if (what == 1) ustar_kernel<S, float, 0><<<grid, 256, 0, st>>>(S::make(p), (const float*)a, (const float*)b, (float*)out, n);
+        else if (what == 4) ustar_kernel<S, float, 4><<<grid, 256, 0, st>>>(S::make(p), (const float*)a, (const float*)b, (float*)out, n);
         else ustar_kernel<S, float, 2><<<grid, 256, 0, st>>>(S::make(p), (const float*)a, (const float*)b, (float*)out, n);
     } else {
         using S = SysT<double>;
         if (what == 0) rhs_kernel<S, double><<<grid, 256, 0, st>>>(S::make(p), (const double*)a, (double*)out, n);
         else if (what == 1) ustar_kernel<S, double, 0><<<grid, 256, 0, st>>>(S::make(p), (const double*)a, (const double*)b, (double*)out, n);
+        else if (what == 4) ustar_kernel<S, double, 4><<<grid, 256, 0, st>>>(S::make(p), (const double*)a, (const double*)b, (double*)out, n);
         else ustar_kernel<S, double, 2><<<grid, 256, 0, st>>>(S::make(p), (const double*)a, (const double*)b, (double*)out, n);
     }
     return (int)cudaGetLastError();

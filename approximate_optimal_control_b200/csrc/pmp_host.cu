@@ -124,8 +124,8 @@ __global__ void unpack_kernel(int nx, long long m, const R* __restrict__ y, R* _
     if (packed) packed[i] = (uint32_t)na[i] | ((uint32_t)ns[i] << kPackBits) | ((uint32_t)res[i] << (2 * kPackBits));
 }
 
-void unpack_counters(const uint32_t* __restrict__ packed, long long m, int32_t* __restrict__ na, int32_t* __restrict__ ns,
-                     int32_t* __restrict__ res) {
+// (packed may BE na: the packed words of a piece can land in the n_accepted leaf itself, see pair_tvk below)
+void unpack_counters(const uint32_t* packed, long long m, int32_t* na, int32_t* __restrict__ ns, int32_t* __restrict__ res) {
     constexpr uint32_t mask = (1u << kPackBits) - 1u;
     if (na && ns && res) {  // one pass: a load and three stores per trajectory
         for (long long i = 0; i < m; i++) {
@@ -320,6 +320,26 @@ int solve_host_persistent(HostPipe& P, const pmp_problem_t& p, const pmp_opts_t&
     h_launched = host_ms();
     const char *hx = (const char*)x_f, *hvx = (const char*)vx_f, *ht = (const char*)t_f, *hv = (const char*)v_f;
     PMP_TRY(cudaStreamWaitEvent(P.s_out, P.ev_ctrl, 0));
+    int mode2d = 2;  // 0: one copy per leaf, 1: x+vx and t+v as two-row copies, 2: the packed counters as a third row (fp32)
+    if (const char* e = getenv("B200PMP_HOST_2D")) mode2d = atoi(e);
+    const bool use2d = mode2d != 0;
+    const long long kMaxPitch = 0x7fffffffLL;  // cudaDeviceProp::memPitch
+    const long long pitch_xvx = (x_end && vx_end) ? (long long)((char*)vx_end - (char*)x_end) : 0;
+    const long long pitch_tv = (t_end && v_end) ? (long long)((char*)v_end - (char*)t_end) : 0;
+    // (a pitched copy must stay inside ONE allocation on either side: leaves of separate allocations that merely lie close to
+    // each other are refused by the runtime at enqueue time -- the first refusal switches the pairing off for the call)
+    bool pair_xvx = use2d && pitch_xvx >= (long long)((size_t)n * nx * es) && pitch_xvx <= kMaxPitch && (long long)sv <= kMaxPitch;
+    bool pair_tv = use2d && pitch_tv >= (long long)((size_t)n * es) && pitch_tv <= kMaxPitch;
+    // fp32: the packed counters are a third row of the same pitched copy when the n_accepted leaf follows v at the same
+    // distance; they land in that leaf and are unfolded in place
+    bool pair_tvk = mode2d >= 2 && pair_tv && pack && es == 4 && n_accepted && n_steps && result &&
+                          (long long)((char*)n_accepted - (char*)v_end) == pitch_tv && (size_t)((char*)d_pk - d_ov) == ss;
+    const uint32_t* h_pk = pair_tvk ? (const uint32_t*)n_accepted : P.h_packed;
+    auto refused = [](cudaError_t e) {
+        if (e != cudaErrorInvalidValue && e != cudaErrorInvalidPitchValue) return false;
+        cudaGetLastError();
+        return true;
+    };
     long long group_min = 1;  // every piece its own group
     if (const char* e = getenv("B200PMP_HOST_GROUP")) group_min = 1LL << atoi(e);  // tuning knob
     int g0 = 0;  // first piece of the open group
@@ -338,8 +358,19 @@ int solve_host_persistent(HostPipe& P, const pmp_problem_t& p, const pmp_opts_t&
         if (int rc = wait32(P.s_out, (unsigned long long)(uintptr_t)&ctrl->done[c], (unsigned int)m, 0u /* CU_STREAM_WAIT_VALUE_GEQ */))
             return drain(-2000 - rc);
         stamp(P.s_out);
-        if (x_end) PMP_TRY(cudaMemcpyAsync((char*)x_end + a * nx * es, d_ox + a * nx * es, m * nx * es, cudaMemcpyDeviceToHost, P.s_out));
-        if (vx_end) PMP_TRY(cudaMemcpyAsync((char*)vx_end + a * nx * es, d_ovx + a * nx * es, m * nx * es, cudaMemcpyDeviceToHost, P.s_out));
+        // Two leaves that sit at a constant distance from each other on both sides leave as ONE two-row pitched copy (the
+        // device arrays are `sv` / `ss` apart by construction; the Python wrapper carves its pinned outputs out of one block):
+        // a piece costs three enqueued copies instead of five, and the copy engine switches direction less often while the
+        // input pieces are still arriving.  B200PMP_HOST_2D=0 restores one copy per leaf (A/B knob).
+        if (pair_xvx) {
+            const cudaError_t e2 = cudaMemcpy2DAsync((char*)x_end + a * nx * es, (size_t)pitch_xvx, d_ox + a * nx * es, sv, m * nx * es, 2, cudaMemcpyDeviceToHost, P.s_out);
+            if (refused(e2)) pair_xvx = false;
+            else PMP_TRY(e2);
+        }
+        if (!pair_xvx) {
+            if (x_end) PMP_TRY(cudaMemcpyAsync((char*)x_end + a * nx * es, d_ox + a * nx * es, m * nx * es, cudaMemcpyDeviceToHost, P.s_out));
+            if (vx_end) PMP_TRY(cudaMemcpyAsync((char*)vx_end + a * nx * es, d_ovx + a * nx * es, m * nx * es, cudaMemcpyDeviceToHost, P.s_out));
+        }
         // The per-trajectory scalars (t, v, counters: 12 of the 60 bytes) can leave once per GROUP of pieces (B200PMP_HOST_GROUP:
         // a 0.5 MB copy takes 13 us against 55 us for 3 MB).  Measured, 2^20 rollouts: 2.03 ms per piece (default), 2.12 at
         // 2^17, 2.22 at 2^18, 2.40 at 2^19 -- what the copies gain, the calling thread loses unfolding the counters of a
@@ -347,9 +378,21 @@ int solve_host_persistent(HostPipe& P, const pmp_problem_t& p, const pmp_opts_t&
         const bool close = c == n_pieces - 1 || c == n_pieces - 2 || bounds[c + 1] - bounds[g0] >= group_min;
         if (close) {
             const long long ga = bounds[g0], gm = bounds[c + 1] - ga;
-            if (t_end) PMP_TRY(cudaMemcpyAsync((char*)t_end + ga * es, d_ot + ga * es, gm * es, cudaMemcpyDeviceToHost, P.s_out));
-            if (v_end) PMP_TRY(cudaMemcpyAsync((char*)v_end + ga * es, d_ov + ga * es, gm * es, cudaMemcpyDeviceToHost, P.s_out));
-            if (pack) {
+            if (pair_tv) {
+                const cudaError_t e2 = cudaMemcpy2DAsync((char*)t_end + ga * es, (size_t)pitch_tv, d_ot + ga * es, ss, gm * es, pair_tvk ? 3 : 2, cudaMemcpyDeviceToHost, P.s_out);
+                if (refused(e2)) {  // (can only happen at the first group: the leaves' relation to each other is the same for all)
+                    pair_tv = pair_tvk = false;
+                    h_pk = P.h_packed;
+                } else {
+                    PMP_TRY(e2);
+                }
+            }
+            if (!pair_tv) {
+                if (t_end) PMP_TRY(cudaMemcpyAsync((char*)t_end + ga * es, d_ot + ga * es, gm * es, cudaMemcpyDeviceToHost, P.s_out));
+                if (v_end) PMP_TRY(cudaMemcpyAsync((char*)v_end + ga * es, d_ov + ga * es, gm * es, cudaMemcpyDeviceToHost, P.s_out));
+            }
+            if (pair_tvk) {
+            } else if (pack) {
                 PMP_TRY(cudaMemcpyAsync(P.h_packed + ga, d_pk + ga, gm * 4, cudaMemcpyDeviceToHost, P.s_out));
             } else {
                 if (n_accepted) PMP_TRY(cudaMemcpyAsync(n_accepted + ga, d_na + ga, gm * 4, cudaMemcpyDeviceToHost, P.s_out));
@@ -362,6 +405,13 @@ int solve_host_persistent(HostPipe& P, const pmp_problem_t& p, const pmp_opts_t&
         }
         stamp(P.s_out);
     }
+    // the watchdog flag travels behind the last piece into the spare slot of the pinned frontier array (the kernel sets it
+    // before it releases the piece counters): no blocking copy on the calling thread at the end.  NOT enqueued behind the
+    // kernel on its own stream: a device->host copy that sits in the engine's queue until the kernel ends holds up the
+    // pieces' copies enqueued after it.
+    unsigned int* h_abort = (unsigned int*)&P.h_frontier[kHostMaxPieces];
+    *h_abort = 0u;
+    PMP_TRY(cudaMemcpyAsync(h_abort, &ctrl->abort, 4, cudaMemcpyDeviceToHost, P.s_out));
     h_enqueued = host_ms();
     {
         int first = 0;
@@ -369,7 +419,7 @@ int solve_host_persistent(HostPipe& P, const pmp_problem_t& p, const pmp_opts_t&
             PMP_TRY(cudaEventSynchronize(P.ev_piece[c]));
             if (pack) {
                 const long long a = bounds[first], m = bounds[c + 1] - a;
-                unpack_counters(P.h_packed + a, m, n_accepted ? n_accepted + a : nullptr, n_steps ? n_steps + a : nullptr,
+                unpack_counters(h_pk + a, m, n_accepted ? n_accepted + a : nullptr, n_steps ? n_steps + a : nullptr,
                                 result ? result + a : nullptr);
             }
             first = c + 1;
@@ -378,8 +428,7 @@ int solve_host_persistent(HostPipe& P, const pmp_problem_t& p, const pmp_opts_t&
     PMP_TRY(cudaStreamSynchronize(P.s_out));
     PMP_TRY(cudaStreamSynchronize(sc));
     PMP_TRY(cudaStreamSynchronize(P.s_in));
-    unsigned int aborted = 0;
-    PMP_TRY(cudaMemcpy(&aborted, &ctrl->abort, 4, cudaMemcpyDeviceToHost));
+    const unsigned int aborted = *h_abort;
     h_synced = host_ms();
     if (trace) {
         fprintf(stderr, "[pmp_solve_host] calling thread: kernel launched at %.3f ms, every copy enqueued at %.3f, all results on the host at %.3f\n",

@@ -11,8 +11,8 @@
 // Vector layout used by the integrator: x[NX], lam[NX] and one scalar (v) are separate arguments.
 #pragma once
 #include "pmp_common.cuh"
-#ifdef PMP_PLUGIN
 #include "pmp_ustar2d.cuh"
+#ifdef PMP_PLUGIN
 #include PMP_GENERATED_HEADER  // template <class R> struct pmp::Generated, PMP_GEN_MINB32 / 64 (codegen.py)
 #endif
 
@@ -148,6 +148,10 @@ template <class R> struct Flatquad {
         const R base = M::fma(M::fma(lam[4], co, -(lam[3] * s)), c.inv_m, -(c.two_g_m * co));
         const R rot = lam[5] * c.r_I;
         const R Hu0 = base - rot, Hu1 = base + rot;
+        if (MODE & 4) {  // u_star_2d(smooth=True): pointwise evaluation only, through the run-time-H_uu routine
+            ustar2d_box<R, 4>(Hu0, Hu1, c.h00, c.h01, c.h00, c.lo0, c.lo1, c.hi0, c.hi1, u0, u1);
+            return;
+        }
         if (MODE & 2) {
             // ---- KKT form (integrator default).  Cost model measured on B200: compares, selects and
             // min/max run on the half-rate ALU pipe and cost two issue cycles each, FMA-pipe instructions one, so this

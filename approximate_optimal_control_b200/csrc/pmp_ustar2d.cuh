@@ -12,6 +12,44 @@ namespace pmp {
 // otherwise the literal two-pass form: score all candidates with the quadratic model, argmin, re-expand about the
 // winner, argmin again (:88-158).  Candidate order = the reference's: unconstrained, then the edges u1 = lo1 (bottom),
 // u0 = lo0 (left), u1 = hi1 (top), u0 = hi0 (right) (:78-86).  NaN compares false: a NaN minimiser counts as inside.
+// u_star_2d(smooth=True) (pontryagin_utils.py:217-254; a debugging aid of the reference, never inside a solve): instead of the
+// argmin, a softmax blend of the five candidates with smoothing length 0.01 -- the unconstrained minimiser carries the penalty
+// 1000 softplus(softmax-violation of the box), everything through log-sum-exp.  softmax is invariant to a common shift of the
+// scores, so the quadratic model H(u) - H(0) = H_u'u + 1/2 u'H_uu u stands in for the reference's full H(u) (they are equal:
+// H is quadratic in u).  cand: unconstrained, bottom, left, top, right -- the reference's order (:78-86).
+template <class R>
+__device__ __forceinline__ void ustar2d_blend(const R (&cx)[5], const R (&cy)[5], R Hu0, R Hu1, R h00, R h01, R h11, R lo0, R lo1,
+                                              R hi0, R hi1, R& u0, R& u1) {
+    using M = Math<R>;
+    const R ss = R(0.01), inv = R(100.0);
+    auto lse2 = [&](R a, R b) {  // log(exp(a) + exp(b)), stable
+        const R m = M::max(a, b);
+        return m + fx::log(fx::exp(a - m) + fx::exp(b - m));
+    };
+    // smooth max of the four constraint violations of the unconstrained minimiser, then "clipped" at 0 by another log-sum-exp
+    const R v0 = (lo0 - cx[0]) * inv, v1 = (lo1 - cy[0]) * inv, v2 = (cx[0] - hi0) * inv, v3 = (cy[0] - hi1) * inv;
+    const R viol = lse2(lse2(v0, v1), lse2(v2, v3)) * ss;
+    const R penalty = R(1000) * (lse2(R(0), viol * inv) * ss);
+    R sc[5], best = M::inf();
+#pragma unroll
+    for (int k = 0; k < 5; k++) {
+        const R t = M::fma(R(0.5) * h00, cx[k], M::fma(h01, cy[k], Hu0));
+        sc[k] = M::fma(cx[k], t, cy[k] * M::fma(R(0.5) * h11, cy[k], Hu1)) + (k == 0 ? penalty : R(0));
+        best = M::min(best, sc[k]);
+    }
+    R wsum = R(0), a0 = R(0), a1 = R(0);
+#pragma unroll
+    for (int k = 0; k < 5; k++) {
+        const R w = fx::exp((best - sc[k]) * inv);  // softmax(-score / ss), shifted by the smallest score
+        wsum += w;
+        a0 = M::fma(w, cx[k], a0);
+        a1 = M::fma(w, cy[k], a1);
+    }
+    u0 = M::div(a0, wsum);
+    u1 = M::div(a1, wsum);
+}
+
+// MODE & 4: the smooth blend above instead of a selection (pointwise evaluation only)
 template <class R, int MODE>
 __device__ __forceinline__ void ustar2d_box(R Hu0, R Hu1, R h00, R h01, R h11, R lo0, R lo1, R hi0, R hi1, R& u0, R& u1) {
     using M = Math<R>;
@@ -27,6 +65,11 @@ __device__ __forceinline__ void ustar2d_box(R Hu0, R Hu1, R h00, R h01, R h11, R
     const R yl = M::min(M::max(M::fma(h01, lo0, Hu1) * n1, lo1), hi1);  // left:   u0 = lo0, u1 moves
     const R xt = M::min(M::max(M::fma(h01, hi1, Hu0) * n0, lo0), hi0);  // top
     const R yr = M::min(M::max(M::fma(h01, hi0, Hu1) * n1, lo1), hi1);  // right
+    if (MODE & 4) {
+        const R bx[5] = {u0, xb, lo0, xt, hi0}, by[5] = {u1, lo1, yl, hi1, yr};
+        ustar2d_blend<R>(bx, by, Hu0, Hu1, h00, h01, h11, lo0, lo1, hi0, hi1, u0, u1);
+        return;
+    }
     if (MODE & 2) {
         // KKT multiplier of the active bound (outward component of -grad H); the box minimiser is the edge
         // minimiser whose multiplier is >= 0: take the largest, first maximum wins

@@ -311,6 +311,25 @@ def _host_leaf(a) -> bool:
     return isinstance(a, np.ndarray) or (isinstance(a, torch.Tensor) and not a.is_cuda)
 
 
+def _pinned_outputs(n: int, nx: int, dtype: torch.dtype) -> dict:
+    """The endpoint leaves and counters of one host solve as views of ONE pinned allocation, x | vx | t | v | n_accepted |
+    n_steps | result: leaves at a constant distance from each other leave the device as one pitched copy per piece
+    (csrc/pmp_host.cu), and a call makes one trip to the pinned allocator instead of seven."""
+    es = torch.empty((), dtype=dtype).element_size()
+    up = lambda b: (b + 255) // 256 * 256
+    sv, ss, si = up(n * nx * es), up(n * es), up(n * 4)
+    block = torch.empty(2 * sv + 2 * ss + 3 * si, dtype=torch.uint8, pin_memory=True)
+    off = [0]
+
+    def take(nbytes, shape, dt):
+        v = block[off[0]:off[0] + int(np.prod(shape)) * torch.empty((), dtype=dt).element_size()].view(dt).view(*shape)
+        off[0] += nbytes
+        return v
+    ho = dict(x=take(sv, (n, nx), dtype), vx=take(sv, (n, nx), dtype), t=take(ss, (n,), dtype), v=take(ss, (n,), dtype),
+              n_accepted=take(si, (n,), torch.int32), n_steps=take(si, (n,), torch.int32), result=take(si, (n,), torch.int32))
+    return ho
+
+
 def _solve_host_lqr(problem, opts, nx, x_f, P_lqr, x_eq, dtype, dev, n_pieces=0):
     """Host terminal samples x_f (n, nx) -> endpoints in pinned host tensors through pmp_solve_host_lqr: only x_f crosses the
     link, vx_f = P (x_f - x_eq) and v_f = 1/2 (x_f - x_eq)' vx_f are formed on the device (levelsets.py:585-586)."""
@@ -320,9 +339,7 @@ def _solve_host_lqr(problem, opts, nx, x_f, P_lqr, x_eq, dtype, dev, n_pieces=0)
         raise ValueError(f"x_f must be [n, {nx}]")
     Ph = np.ascontiguousarray(np.asarray(P_lqr.detach().cpu() if isinstance(P_lqr, torch.Tensor) else P_lqr, dtype=np.float64).reshape(nx, nx))
     xe = None if x_eq is None else np.ascontiguousarray(np.asarray(x_eq, dtype=np.float64).reshape(nx))
-    pin = lambda *shape, dt=dtype: torch.empty(shape, dtype=dt, pin_memory=True)
-    ho = dict(x=pin(n, nx), t=pin(n), v=pin(n), vx=pin(n, nx), n_accepted=pin(n, dt=torch.int32), n_steps=pin(n, dt=torch.int32),
-              result=pin(n, dt=torch.int32))
+    ho = _pinned_outputs(n, nx, dtype)
     L = _capi.lib_of(problem)
     with torch.cuda.device(dev):
         _capi.check(L.pmp_solve_host_lqr(C.byref(problem), C.byref(opts), n, x.data_ptr(), None, Ph.ctypes.data,
@@ -363,9 +380,7 @@ def _solve_host_pipelined(problem, opts, nx, y_f, dtype, dev, n_pieces=0):
                 t = per_traj(t_in, "t")
         else:
             t = per_traj(t_in, "t")
-    pin = lambda *shape, dt=dtype: torch.empty(shape, dtype=dt, pin_memory=True)
-    ho = dict(x=pin(n, nx), t=pin(n), v=pin(n), vx=pin(n, nx), n_accepted=pin(n, dt=torch.int32), n_steps=pin(n, dt=torch.int32),
-              result=pin(n, dt=torch.int32))
+    ho = _pinned_outputs(n, nx, dtype)
     L = _capi.lib_of(problem)
     with torch.cuda.device(dev):
         _capi.check(L.pmp_solve_host(C.byref(problem), C.byref(opts), n, x.data_ptr(), t.data_ptr() if t is not None else None,
@@ -484,7 +499,7 @@ def define_backward_solver(problem_params: dict, algo_params: dict):
     return solve_backward, f_extended
 
 
-def _ustar(x, costate, problem_params):
+def _ustar(x, costate, problem_params, flags=None):
     problem = systems.to_c_problem(problem_params)
     nx, nu = problem.nx, problem.nu
     dev = _device(x, costate)
@@ -495,22 +510,23 @@ def _ustar(x, costate, problem_params):
     ls = _as_tensor(costate, dtype, dev).reshape(-1, nx).t().contiguous()
     u = torch.empty((nu, xs.shape[1]), dtype=dtype, device=dev)
     with torch.cuda.device(dev):
-        _capi.check(_capi.lib_of(problem).pmp_ustar_batch_cuda(C.byref(problem), _code(dtype), xs.shape[1],
-                                                               xs.data_ptr(), ls.data_ptr(), u.data_ptr(),
-                                                               _stream_ptr(dev)))
+        L = _capi.lib_of(problem)
+        if flags is None:
+            _capi.check(L.pmp_ustar_batch_cuda(C.byref(problem), _code(dtype), xs.shape[1], xs.data_ptr(), ls.data_ptr(),
+                                               u.data_ptr(), _stream_ptr(dev)), L)
+        else:
+            _capi.check(L.pmp_ustar_batch_cuda_flags(C.byref(problem), _code(dtype), int(flags), xs.shape[1], xs.data_ptr(),
+                                                     ls.data_ptr(), u.data_ptr(), _stream_ptr(dev)), L)
     u = u.t()
     return u if batched else u[0]
 
 
 def u_star_2d(x, costate, problem_params, smooth=False, debug_oups=False):
     """pontryagin_utils.py:11-254: u* = argmin_u l(x,u) + costate.f(x,u) over the 2-D input box.
-    x, costate: (nx,) or (N, nx).  smooth=True (logsumexp blend, :217-254) is a debugging aid of
-    the reference and is not implemented."""
+    x, costate: (nx,) or (N, nx).  smooth=True: the reference's softmax blend of the candidates (:217-254, a debugging aid)."""
     if not problem_params["nu"] == 2:
         raise NotImplementedError("this ustar function is for 2d only!")
-    if smooth:
-        raise NotImplementedError("smooth=True variant of u_star_2d is not on the accelerated path")
-    return _ustar(x, costate, problem_params)
+    return _ustar(x, costate, problem_params, flags=_capi.FLAG_USTAR_SMOOTH if smooth else None)
 
 
 def u_star_new(x, costate, problem_params):

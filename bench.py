@@ -76,6 +76,8 @@ def parse_args():
     ap.add_argument("--gather", default="auto", choices=["auto", "p2p", "nccl"],
                     help="N>1 endpoint gather transport: peer-to-peer copies over NVLink (symmetric memory) or NCCL")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-bind-host", action="store_true",
+                    help="leave the process where the launcher put it (default: onto the CPUs / memory of the GPU's NUMA node)")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-parity", action="store_true")
     ap.add_argument("--no-dense", action="store_true", help="skip the dense (C5) block of the default N=1 line")
@@ -233,6 +235,9 @@ def main():
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device: the PMP path has no CPU fallback")
+    # before anything allocates pinned host memory: this rank's process onto the CPUs (and so the memory) next to its GPU
+    all_cpus = os.sched_getaffinity(0)
+    host_binding = {"bound": False, "why": "--no-bind-host"} if args.no_bind_host else sharding.bind_host_to_gpu(local_rank)
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     if world > 1:
@@ -565,6 +570,7 @@ def main():
     # ---- parity of this run's numbers + cpu baseline (rank 0, N=1 only) ----------------------------------
     cpu = None
     parity = None
+    os.sched_setaffinity(0, all_cpus)  # the CPU legs below (oracle, OpenMP) use every host core the process was given
     if rank == 0 and world == 1 and not (args.no_cpu_baseline and args.no_parity):
         from oracle import oracle as O
     if rank == 0 and world == 1 and not args.no_parity and not dense:
@@ -628,7 +634,7 @@ def main():
             "mean_attempts_per_trajectory": attempts_all / (n * world),
             "solve_ms_per_step": solve_s * 1e3,
             "roofline": roof, "parity": parity, "cpu_baseline": cpu, "e2e": e2e, "clocks": clocks,
-            "gpu_launches": int(gpu_launches),
+            "gpu_launches": int(gpu_launches), "host_binding": host_binding,
             "gather": gather, "gather_check": gather_check, "strong": strong, "dense": dense_block, "forward_nn": forward_block,
         }
         print(json.dumps(line), flush=True)

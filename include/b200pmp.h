@@ -111,14 +111,20 @@ enum {
     /* algo_params['pontryagin_solver_vxx']: also propagate the value Hessian V_xx along the characteristic,
      * vxx' = gx + glam vxx - vxx fx - vxx flam vxx with (fx, flam, gx, glam) the Jacobians of the PMP right
      * hand side THROUGH u* (pontryagin_utils.py:460-467).  The state gains nx*nx rows after vx (row-major
-     * vxx[i][j] at row 2nx+2 + i*nx + j), the error norm one more leaf.  flatquad only. */
+     * vxx[i][j] at row 2nx+2 + i*nx + j), the error norm one more leaf.  The flatquad functor carries the
+     * Jacobians in closed form; a generated system (PMP_SYS_GENERATED, nx <= 9, Tsit5 or RK4) is differentiated
+     * in forward mode, as the reference's jax.jacobian(pmp_rhs) handles any f, l (csrc/pmp_vxx_dual.cuh).  orbits /
+     * LQR: PMP_ERR_UNSUPPORTED (u_star_new systems; the reference's vxx branch runs through u_star_2d). */
     PMP_FLAG_VXX = 2,
     /* with PMP_FLAG_VXX: the caller guarantees that every terminal vxx is symmetric (vxx[i][j] == vxx[j][i]
      * bit for bit; the reference starts from the LQR solution P, levelsets.py:595).  vxx^T obeys the same
      * Riccati equation, so the solution stays symmetric: the kernel then reads, integrates and stores only
      * the upper triangle (21 of 36 entries; off-diagonal entries count twice in the error norm and in
      * ||vxx||_F) and mirrors it on output.  Differs from the general path by rounding only. */
-    PMP_FLAG_VXX_SYMMETRIC = 4
+    PMP_FLAG_VXX_SYMMETRIC = 4,
+    /* pmp_ustar_batch_cuda_flags only: u_star_2d(..., smooth=True) (pontryagin_utils.py:217-254), the softmax blend of the
+     * five candidates (smoothing length 0.01) the reference keeps as a debugging aid; nu == 2 systems.  Not a solver option. */
+    PMP_FLAG_USTAR_SMOOTH = 8
 };
 
 /* error codes */
@@ -345,7 +351,8 @@ int pmp_interp_batch_cuda(const pmp_problem_t *problem, const pmp_opts_t *opts, 
                           void *y_out, void *cuda_stream);
 
 /* Same with the selection rule the integrator uses for `flags` (PMP_FLAG_USTAR_LITERAL set: identical
- * to pmp_ustar_batch_cuda; clear: KKT-multiplier selection).  For verification of the two rules. */
+ * to pmp_ustar_batch_cuda; clear: KKT-multiplier selection).  For verification of the two rules.
+ * flags == PMP_FLAG_USTAR_SMOOTH: u_star_2d(x, costate, problem_params, smooth=True). */
 int pmp_ustar_batch_cuda_flags(const pmp_problem_t *problem, int32_t dtype, int32_t flags, int64_t n,
                                const void *x, const void *lam, void *u, void *cuda_stream);
 

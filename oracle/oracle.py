@@ -238,6 +238,16 @@ def solve_batch_to_times(problem: Problem, y_f: np.ndarray, tq: np.ndarray, rtol
     return out
 
 
+def ustar_smooth(problem: Problem, x: np.ndarray, lam: np.ndarray) -> np.ndarray:
+    """flatquad, fp64: u_star_2d(..., smooth=True) (pontryagin_utils.py:217-254); x, lam [6, n] -> u [2, n]."""
+    x = np.ascontiguousarray(x, np.float64); lam = np.ascontiguousarray(lam, np.float64)
+    u = np.empty((2, x.shape[1]))
+    L = lib()
+    L.pmp_oracle_ustar_smooth.argtypes = [C.POINTER(Problem), C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p]
+    _check(L.pmp_oracle_ustar_smooth(C.byref(problem), x.shape[1], x.ctypes.data, lam.ctypes.data, u.ctypes.data))
+    return u
+
+
 def vxx_rhs(problem: Problem, x, lam, vxx):
     """flatquad: (fx, flam, gx, glam, vxx_dot) of pontryagin_utils.py:460-467 for one state (fp64)."""
     x = np.ascontiguousarray(x, np.float64); lam = np.ascontiguousarray(lam, np.float64)

@@ -197,6 +197,20 @@ int pmp_oracle_ustar_batch(const pmp_problem_t* p, int32_t dtype, int64_t n, con
     return fail(PMP_ERR_UNSUPPORTED, "unknown system_id");
 }
 
+// flatquad only, fp64: u_star_2d(..., smooth=True) (pontryagin_utils.py:217-254) at n points, x, lam [6][n] -> u [2][n]
+int pmp_oracle_ustar_smooth(const pmp_problem_t* p, int64_t n, const double* x, const double* lam, double* u) {
+    if (int e = check(p, nullptr)) return e;
+    if (p->system_id != PMP_SYS_FLATQUAD) return fail(PMP_ERR_UNSUPPORTED, "ustar_smooth: flatquad only");
+    Flatquad<double> sys(*p);
+    for (int64_t i = 0; i < n; i++) {
+        double xi[6], li[6], ui[2];
+        for (int q = 0; q < 6; q++) { xi[q] = x[q * n + i]; li[q] = lam[q * n + i]; }
+        sys.ustar_smooth(xi, li, ui);
+        u[i] = ui[0]; u[n + i] = ui[1];
+    }
+    return 0;
+}
+
 // flatquad only: Jacobians of pmp_rhs through u* and vxx_dot (pontryagin_utils.py:460-467), fp64, one state per call.
 // jac_out = fx, flam, gx, glam (4 x 36, row-major), vxx_dot_out 36.
 int pmp_oracle_vxx_rhs(const pmp_problem_t* p, const double* x, const double* lam, const double* vxx, double* jac_out,

@@ -168,6 +168,56 @@ template <class R> struct Flatquad {
         bool moving_free;
         ustar_active(x, lam, s, c, u, best, moving_free);
     }
+    // u_star_2d(x, costate, problem_params, smooth=True)      pontryagin_utils.py:217-254 (fp64 restatement; a debugging aid of
+    // the reference): softmax blend of the five candidates, scored with the TRUE H(u) = l + lambda.f as the reference does
+    void ustar_smooth(const R* x, const R* lam, R* u) const {
+        const R s = r_sin(x[2]), c = r_cos(x[2]);
+        R Hu[2], cand[5][2], Hs[5];
+        hu0(lam, s, c, Hu);
+        cand[0][0] = -(Hinv[0][0] * Hu[0] + Hinv[0][1] * Hu[1]);
+        cand[0][1] = -(Hinv[1][0] * Hu[0] + Hinv[1][1] * Hu[1]);
+        for (int k = 0; k < 4; k++) {
+            const R* a = hull[k];
+            const R* b = hull[(k + 3) % 4];
+            const int ax = edge_axis[k];
+            R sc = r_clip(-((Hu[ax] + edge_g[k]) * edge_d[k]) * edge_inv_den[k], R(0), R(1));
+            cand[k + 1][ax] = sc * a[ax] + (R(1) - sc) * b[ax];
+            cand[k + 1][1 - ax] = a[1 - ax];
+        }
+        for (int k = 0; k < 5; k++) {  // :90 all_Hs = vmap(H_fct)(all_candidates)
+            R xd[6];
+            f_sc(x, cand[k], s, c, xd);
+            R h = l_acc(x, s, c, xd[3], xd[4], xd[5]);
+            for (int i = 0; i < 6; i++) h = h + lam[i] * xd[i];
+            Hs[k] = h;
+        }
+        const double ss = 0.01;  // :232 smoothing_size
+        auto lse = [](const double* a, int n) {
+            double m = a[0];
+            for (int i = 1; i < n; i++) m = a[i] > m ? a[i] : m;
+            double acc = 0;
+            for (int i = 0; i < n; i++) acc += std::exp(a[i] - m);
+            return m + std::log(acc);
+        };
+        // :231-238 violations of the unconstrained solution, smooth max, softplus-clipped at 0, times 1000
+        const double cv[4] = {(r_val(ulo[0]) - r_val(cand[0][0])) / ss, (r_val(ulo[1]) - r_val(cand[0][1])) / ss,
+                              (r_val(cand[0][0]) - r_val(uhi[0])) / ss, (r_val(cand[0][1]) - r_val(uhi[1])) / ss};
+        const double softmax_violation = lse(cv, 4) * ss;
+        const double z[2] = {0.0, softmax_violation / ss};
+        const double penalty = 1000.0 * lse(z, 2) * ss;
+        // :241-251 weights = softmax(-all_Hs_adjusted / smoothing_size); u = weights' candidates
+        double sc5[5], m = 0, wsum = 0, a0 = 0, a1 = 0;
+        for (int k = 0; k < 5; k++) {
+            sc5[k] = -(r_val(Hs[k]) + (k == 0 ? penalty : 0.0)) / ss;
+            m = (k == 0 || sc5[k] > m) ? sc5[k] : m;
+        }
+        for (int k = 0; k < 5; k++) {
+            const double w = std::exp(sc5[k] - m);
+            wsum += w; a0 += w * r_val(cand[k][0]); a1 += w * r_val(cand[k][1]);
+        }
+        u[0] = R(a0 / wsum);
+        u[1] = R(a1 / wsum);
+    }
     // same, also reporting which candidate won (0 = unconstrained, k = edge k) and, for an edge, whether its
     // line-search parameter is strictly inside (0,1) (else the point sits in a corner)
     void ustar_active(const R* x, const R* lam, R s, R c, R* u, int& best_out, bool& moving_free) const {

@@ -1,7 +1,8 @@
 #!/usr/bin/env python
 """Host-link probe (one GPU; run under torchrun for all ranks at once): what the copy engines and the SMs ("zero copy")
 move between pinned host memory and HBM, one direction and both, as a function of the copy size.
-usage: python scripts/pcie_probe.py [> profiles/rNN_pcie_probe.jsonl]"""
+usage: python scripts/pcie_probe.py [--bind] [--short] [> profiles/rNN_pcie_probe.jsonl]
+       torchrun --nproc-per-node 8 scripts/pcie_probe.py --short [--bind]   (every rank's line; the aggregate is their sum)"""
 import ctypes as C
 import json
 import os
@@ -12,8 +13,12 @@ sys.path.insert(0, ROOT)
 import torch
 from approximate_optimal_control_b200 import _capi
 
+from approximate_optimal_control_b200 import sharding
+
 rank = int(os.environ.get("LOCAL_RANK", "0"))
 world = int(os.environ.get("WORLD_SIZE", "1"))
+BIND, SHORT = "--bind" in sys.argv, "--short" in sys.argv  # --bind: process onto the GPU's NUMA node BEFORE the pinned allocations
+binding = sharding.bind_host_to_gpu(rank) if BIND else {"bound": False, "why": "not asked"}
 torch.cuda.set_device(rank)
 if world > 1:
     import torch.distributed as dist
@@ -63,6 +68,13 @@ def line(name, fn, nbytes, **kw):
     print(json.dumps(d), flush=True)
 
 
+print(json.dumps(dict(test="host_binding", rank=rank, world=world, **binding)), flush=True)
+if SHORT:  # all ranks at once: what the box's host links give every GPU at the same time
+    for piece in (1 << 20, 8 << 20):
+        line("ce_h2d", lambda: ce(d_a, h_in, s1, piece), TOTAL, piece_KiB=piece >> 10, bind=BIND)
+        line("ce_d2h", lambda: ce(h_out, d_b, s2, piece), TOTAL, piece_KiB=piece >> 10, bind=BIND)
+        line("ce_both", lambda: (ce(d_a, h_in, s1, piece), ce(h_out, d_b, s2, piece)), 2 * TOTAL, piece_KiB=piece >> 10, bind=BIND)
+    sys.exit(0)
 for piece in (512 << 10, 1 << 20, 3 << 20, 8 << 20, 64 << 20):
     line("ce_h2d", lambda: ce(d_a, h_in, s1, piece), TOTAL, piece_KiB=piece >> 10)
     line("ce_d2h", lambda: ce(h_out, d_b, s2, piece), TOTAL, piece_KiB=piece >> 10)

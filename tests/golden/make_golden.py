@@ -93,6 +93,15 @@ def install_shim():
     # reverse-over-reverse: forward-mode (torch.func.hessian = jacfwd(jacrev)) mixes dtypes in float32 mode
     jax.hessian = lambda f, argnums=0: torch.func.jacrev(torch.func.jacrev(f, argnums=argnums), argnums=argnums)
     jax.vmap = lambda f, in_axes=0: torch.func.vmap(f, in_dims=in_axes)
+    # u_star_2d(smooth=True): jax.scipy.special.logsumexp, jax.nn.softmax (pontryagin_utils.py:231-247)
+    special = types.ModuleType("jax.scipy.special")
+    special.logsumexp = lambda a: torch.logsumexp(_t(a), dim=0)
+    jscipy = types.ModuleType("jax.scipy")
+    jscipy.special = special
+    jax.scipy = jscipy
+    jax.nn = types.SimpleNamespace(softmax=lambda a: torch.softmax(_t(a), dim=0))
+    sys.modules["jax.scipy"] = jscipy
+    sys.modules["jax.scipy.special"] = special
     jax.config = types.SimpleNamespace(update=lambda *a, **k: None)
     jax.Array = type("Array", (), {})  # scipy's array-API probe looks for it when 'jax' is in sys.modules
     sys.modules["jax"] = jax
@@ -247,6 +256,44 @@ def gen_vxx_flatquad(jnp, n=192):
     print("vxx golden: both free", (~sat).all(1).mean(), "one clipped", (sat.sum(1) == 1).mean(), "corner", sat.all(1).mean())
 
 
+def gen_ustar_smooth_flatquad(jnp, n=256):
+    """u_star_2d(x, lambda, problem_params, smooth=True) (pontryagin_utils.py:217-254): the softmax blend of the five
+    candidates, from the reference itself (fp64)."""
+    import pontryagin_utils as ref
+    torch.set_default_dtype(torch.float64)
+    pp = flatquad_ref(jnp)
+    rng = onp.random.Generator(onp.random.PCG64(31))
+    xs, lams = flatquad_inputs(n, rng)
+    # half of the sample within a few smoothing lengths of an active-set change (the unconstrained minimiser close to an
+    # edge or a corner of the box), where the blend differs from the hard selection: pick that minimiser u_t, then the
+    # costate entries (lambda_4, lambda_5) that produce it: H_u(0) = -H_uu u_t, H_u(0) = base -+ rot,
+    # base = (lam4 cos - lam3 sin)/m - 2 g cos/m, rot = lam5 r/I  (flatquad_landing_experiment.py:269-329)
+    m, g, r = 20.0, 9.81, 0.5
+    I = m * (r / 2) ** 2
+    d, o = 2 * (1 / m ** 2 + r ** 2 / I ** 2), 2 * (1 / m ** 2 - r ** 2 / I ** 2)
+    umax = m * g * 1.2 / 2
+    for i in range(n // 2, n):
+        edge = rng.integers(0, 4)
+        along = rng.uniform(-0.05, 1.05) * umax if rng.uniform() < 0.7 else rng.choice([0.0, umax]) + rng.normal(0, 0.15)
+        off = rng.normal(0, 0.15)
+        ut = {0: (along, off), 1: (off, along), 2: (along, umax + off), 3: (umax + off, along)}[int(edge)]
+        hu0, hu1 = -(d * ut[0] + o * ut[1]), -(o * ut[0] + d * ut[1])
+        base, rot = 0.5 * (hu0 + hu1), 0.5 * (hu1 - hu0)
+        xs[i, 2] = rng.uniform(-1.0, 1.0)
+        sn, cs = onp.sin(xs[i, 2]), onp.cos(xs[i, 2])
+        lams[i, 3] = rng.normal(0, 5.0)
+        lams[i, 4] = ((base + 2 * g / m * cs) * m + lams[i, 3] * sn) / cs
+        lams[i, 5] = rot * I / r
+    us = onp.zeros((n, 2)); uh = onp.zeros((n, 2))
+    for i in range(n):
+        x = torch.as_tensor(xs[i]); lam = torch.as_tensor(lams[i])
+        us[i] = ref.u_star_2d(x, lam, pp, smooth=True).numpy()
+        uh[i] = ref.u_star_2d(x, lam, pp).numpy()
+    onp.savez(os.path.join(OUT, "ustar_smooth_flatquad_f64.npz"), x=xs, lam=lams, u_smooth=us, u=uh)
+    d = onp.abs(us - uh).max(1)
+    print("ustar_smooth: |smooth - hard| median %.3g, max %.3g, > 1e-3 at %d of %d points" % (onp.median(d), d.max(), (d > 1e-3).sum(), n))
+
+
 if __name__ == "__main__":
     jnp = install_shim()
     only = sys.argv[1:]
@@ -259,3 +306,5 @@ if __name__ == "__main__":
         gen_traj_flatquad(jnp)
     if not only or "vxx" in only:
         gen_vxx_flatquad(jnp)
+    if not only or "smooth" in only:
+        gen_ustar_smooth_flatquad(jnp)

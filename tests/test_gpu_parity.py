@@ -59,6 +59,36 @@ def test_rhs_and_ustar_flatquad_vs_reference_golden(tag, dtype, tol):
     assert rel.max() <= tol, rel.max(1)
 
 
+def test_ustar_smooth_vs_reference_golden():
+    """u_star_2d(x, costate, problem_params, smooth=True) (pontryagin_utils.py:217-254; PMP_FLAG_USTAR_SMOOTH) against the
+    reference's own output and the oracle: hand-written and generated flatquad functor, fp64 tight; fp32 only where the blend
+    is not balanced on a knife's edge (the weights are exp(-H / 0.01): an fp32 rounding of H ~ 1e3 is a factor e^(+-0.01))."""
+    import ctypes as C
+    import torch
+    from approximate_optimal_control_b200 import pontryagin_utils as pu, systems
+    g = np.load(f"{GOLDEN}/ustar_smooth_flatquad_f64.npz")
+    pp = systems.flatquad_problem_params()
+    x, lam = torch.as_tensor(g["x"], device="cuda"), torch.as_tensor(g["lam"], device="cuda")
+    ref = O.ustar_smooth(oracle_problem("flatquad"), g["x"].T, g["lam"].T).T
+    for params in (pp, dict(pp, codegen=True)):
+        u = pu.u_star_2d(x, lam, dict(params, dtype="float64"), smooth=True).cpu().numpy()
+        assert u.shape == (g["x"].shape[0], 2)
+        assert np.abs(u - g["u_smooth"]).max() <= 1e-7, np.abs(u - g["u_smooth"]).max()
+        assert np.abs(u - ref).max() <= 1e-7
+        one = pu.u_star_2d(x[200], lam[200], dict(params, dtype="float64"), smooth=True)
+        assert one.shape == (2,) and np.allclose(one.cpu().numpy(), u[200], rtol=0, atol=1e-12)
+    hard = pu.u_star_2d(x, lam, dict(pp, dtype="float64")).cpu().numpy()
+    assert np.abs(hard - g["u"]).max() <= 1e-9 and (np.abs(u - hard).max(1) > 1e-3).sum() >= 50
+    u32 = pu.u_star_2d(x.float(), lam.float(), dict(pp, dtype="float32"), smooth=True).cpu().numpy().astype(np.float64)
+    d = np.abs(u32 - g["u_smooth"]).max(1)
+    assert np.median(d) <= 2e-3 and d.max() <= 1.0, (np.median(d), d.max())
+    with pytest.raises(_capi.PmpError):  # u_star_2d is a nu == 2 function
+        prob, _ = c_problem("orbits")
+        xo = torch.zeros((2, 4), dtype=torch.float64, device="cuda")
+        _capi.check(_capi.lib().pmp_ustar_batch_cuda_flags(C.byref(prob), _capi.F64, _capi.FLAG_USTAR_SMOOTH, 4, xo.data_ptr(),
+                                                           xo.data_ptr(), xo.data_ptr(), None))
+
+
 @pytest.mark.parametrize("name", ["orbits", "lqr"])
 def test_rhs_and_ustar_2d_systems_vs_reference_golden(name):
     import ctypes as C

@@ -356,6 +356,17 @@ def test_value_mode_interpolation_oracle():
         assert np.allclose(got[:, k], ref, rtol=1e-5, atol=1e-6)
 
 
+def test_ustar_smooth_matches_reference_golden():
+    """u_star_2d(..., smooth=True) (pontryagin_utils.py:217-254), the reference's softmax blend of the candidates: golden from
+    the reference itself (tests/golden/make_golden.py::gen_ustar_smooth_flatquad; half of the sample within a few smoothing
+    lengths of an active-set change, where the blend differs from the hard selection by up to 0.24)."""
+    g = np.load(f"{GOLDEN}/ustar_smooth_flatquad_f64.npz")
+    u = O.ustar_smooth(O.flatquad_problem(), g["x"].T, g["lam"].T).T
+    # the weights are exp(-H / 0.01) with H ~ 1e2..1e4: rounding of H enters magnified by 100
+    assert np.abs(u - g["u_smooth"]).max() <= 1e-7, np.abs(u - g["u_smooth"]).max()
+    assert (np.abs(g["u_smooth"] - g["u"]).max(1) > 1e-3).sum() >= 50  # the sample does exercise the blend
+
+
 # ---- value-Hessian branch (pontryagin_solver_vxx, pontryagin_utils.py:460-467) ------------------------
 def test_vxx_rhs_matches_reference_golden():
     """vxx_dot and the Jacobians (fx, flam, gx, glam) of pmp_rhs THROUGH u_star_2d against the reference's
