@@ -145,8 +145,6 @@ int check_pair(const pmp_problem_t* p, const pmp_opts_t* o) {
         return fail(PMP_ERR_BAD_ARG, "this event belongs to pmp_forward_batch_cuda / pmp_forward_nn_batch_cuda (the backward "
                                      "solve has no costate law)");
     if (int e = check_vxx_system(p, o->flags)) return e;
-    if ((o->flags & PMP_FLAG_VXX) && p->system_id == PMP_SYS_GENERATED && o->method == PMP_METHOD_DOPRI5)
-        return fail(PMP_ERR_UNSUPPORTED, "PMP_FLAG_VXX on a generated system: Tsit5 (the reference's solver for this branch) or RK4");
     return 0;
 }
 int64_t vxx_rows(const pmp_problem_t* p, int32_t flags) { return (flags & PMP_FLAG_VXX) ? (int64_t)p->nx * p->nx : 0; }

@@ -1170,7 +1170,7 @@ int launch_hostq(const pmp_problem_t& p, const pmp_opts_t& o, long long n, const
 }
 
 // PMP_FLAG_VXX instantiations (time-parameterised, KKT-form u*): a compile unit of their own
-// METHODS: bit PMP_METHOD_x set = instantiate that method (plug-ins build Tsit5 -- the reference's only vxx solver -- and RK4)
+// METHODS: bit PMP_METHOD_x set = instantiate that method
 template <template <class> class SysT, int METHODS = 7>
 int launch_solve_vxx(const pmp_problem_t& p, const pmp_opts_t& o, long long n, const void* y_f, void* y_end,
                      const pmp_dense_t* dense, int32_t* a, int32_t* s, int32_t* r, void* ws, cudaStream_t st) {

@@ -112,7 +112,7 @@ enum {
      * vxx' = gx + glam vxx - vxx fx - vxx flam vxx with (fx, flam, gx, glam) the Jacobians of the PMP right
      * hand side THROUGH u* (pontryagin_utils.py:460-467).  The state gains nx*nx rows after vx (row-major
      * vxx[i][j] at row 2nx+2 + i*nx + j), the error norm one more leaf.  The flatquad functor carries the
-     * Jacobians in closed form; a generated system (PMP_SYS_GENERATED, nx <= 9, Tsit5 or RK4) is differentiated
+     * Jacobians in closed form; a generated system (PMP_SYS_GENERATED, nx <= 9) is differentiated
      * in forward mode, as the reference's jax.jacobian(pmp_rhs) handles any f, l (csrc/pmp_vxx_dual.cuh).  orbits /
      * LQR: PMP_ERR_UNSUPPORTED (u_star_new systems; the reference's vxx branch runs through u_star_2d). */
     PMP_FLAG_VXX = 2,

@@ -104,12 +104,10 @@ def test_generated_header_and_plugin_library():
     flat = systems.to_c_problem(systems.flatquad_problem_params())
     assert L.pmp_state_rows(C.byref(flat)) == -2 and b"plug-in" in L.pmp_last_error()
     assert _capi.lib().pmp_state_rows(C.byref(prob)) == -2  # and the main library does not know the generated id
-    # vxx leaf of a generated functor (forward mode, csrc/pmp_vxx_dual.cuh): 2 nx + 1 + nx^2 workspace rows; Tsit5 / RK4 only
+    # vxx leaf of a generated functor (forward mode, csrc/pmp_vxx_dual.cuh): 2 nx + 1 + nx^2 workspace rows
     o = _capi.make_opts(dtype=_capi.F64, flags=_capi.FLAG_VXX)
     assert L.pmp_solve_workspace_bytes(C.byref(prob), C.byref(o), 8) == 256 + (5 + 4) * 8 * 8
     assert L.pmp_state_rows_flags(C.byref(prob), _capi.FLAG_VXX) == 6 + 4
-    o = _capi.make_opts(method="dopri5", dtype=_capi.F64, flags=_capi.FLAG_VXX)
-    assert L.pmp_solve_workspace_bytes(C.byref(prob), C.byref(o), 8) == -2
     orb = systems.to_c_problem(systems.orbits_problem_params())
     assert _capi.lib().pmp_state_rows_flags(C.byref(orb), _capi.FLAG_VXX) == -2  # u_star_new systems: no vxx branch in the reference
     import torch
