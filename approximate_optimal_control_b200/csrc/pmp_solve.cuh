@@ -1171,16 +1171,18 @@ int launch_hostq(const pmp_problem_t& p, const pmp_opts_t& o, long long n, const
 
 // PMP_FLAG_VXX instantiations (time-parameterised, KKT-form u*): a compile unit of their own
 // METHODS: bit PMP_METHOD_x set = instantiate that method
-template <template <class> class SysT, int METHODS = 7>
+// SYM_MINB32: CTAs per SM the symmetric fp32 instantiation is compiled for (a register cap: 5 suits the hand-written flatquad
+// Jacobians; the forward-mode adaptor of pmp_vxx_dual.cuh needs the registers more than the residency)
+template <template <class> class SysT, int METHODS = 7, int SYM_MINB32 = 5>
 int launch_solve_vxx(const pmp_problem_t& p, const pmp_opts_t& o, long long n, const void* y_f, void* y_end,
                      const pmp_dense_t* dense, int32_t* a, int32_t* s, int32_t* r, void* ws, cudaStream_t st) {
     const bool dn = o.save_dense != 0, sym = (o.flags & PMP_FLAG_VXX_SYMMETRIC) != 0;
 #define PMP_GOV(R, METHOD)                                                                                          \
     do {                                                                                                            \
         /* symmetric fp32: 42 KB per CTA lets five CTAs share an SM if they stay within 204 registers */            \
-        if (dn && sym) return launch_one<SysT<R>, R, METHOD, true, false, false, (sizeof(R) == 4 ? 5 : 1), 2>(p, o, n, y_f, y_end, dense, a, s, r, ws, st);  \
+        if (dn && sym) return launch_one<SysT<R>, R, METHOD, true, false, false, (sizeof(R) == 4 ? SYM_MINB32 : 1), 2>(p, o, n, y_f, y_end, dense, a, s, r, ws, st);  \
         if (dn) return launch_one<SysT<R>, R, METHOD, true, false, false, 1, 1>(p, o, n, y_f, y_end, dense, a, s, r, ws, st);         \
-        if (sym) return launch_one<SysT<R>, R, METHOD, false, false, false, (sizeof(R) == 4 ? 5 : 1), 2>(p, o, n, y_f, y_end, dense, a, s, r, ws, st);       \
+        if (sym) return launch_one<SysT<R>, R, METHOD, false, false, false, (sizeof(R) == 4 ? SYM_MINB32 : 1), 2>(p, o, n, y_f, y_end, dense, a, s, r, ws, st);       \
         return launch_one<SysT<R>, R, METHOD, false, false, false, 1, 1>(p, o, n, y_f, y_end, dense, a, s, r, ws, st);                \
     } while (0)
 #define PMP_BY_METHODV(R)                                              \

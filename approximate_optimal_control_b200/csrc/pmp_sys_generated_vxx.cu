@@ -10,6 +10,6 @@ namespace pmp {
 template <class R> using GeneratedVxx = DualVxx<Generated, R>;
 int solve_generated_vxx(const pmp_problem_t& p, const pmp_opts_t& o, long long n, const void* y_f, void* y_end,
                         const pmp_dense_t* dense, int32_t* a, int32_t* s, int32_t* r, void* ws, cudaStream_t st) {
-    return launch_solve_vxx<GeneratedVxx>(p, o, n, y_f, y_end, dense, a, s, r, ws, st);
+    return launch_solve_vxx<GeneratedVxx, 7, 1>(p, o, n, y_f, y_end, dense, a, s, r, ws, st);
 }
 }  // namespace pmp

@@ -78,10 +78,11 @@ template <template <class> class SysT, class R> struct DualVxx : SysT<R> {
             SysD::template rhs<2>(c.dual, x, lam, xd, vd, ld);
 #pragma unroll
             for (int i = 0; i < NX; i++) {
+                if (VXX == 2 && i > col) continue;  // symmetric storage: the upper triangle only
                 R a = ld[i].d;
 #pragma unroll
                 for (int k = 0; k < NX; k++) a = M::fma(-V[MP::ent(i, k)], xd[k].d, a);
-                if (VXX != 2 || i <= col) put(MP::ent(i, col), a);
+                put(MP::ent(i, col), a);
             }
         }
     }

@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """Kernel time of the value-Hessian branch (PMP_FLAG_VXX, row N1 of SURVEY.md 8(f)) on one GPU: general
 36-entry storage and symmetric upper-triangle storage, fp32 / fp64, endpoints and dense.
-usage: python scripts/bench_vxx.py [log2_n] [> profiles/rNN_vxx.jsonl]"""
+usage: python scripts/bench_vxx.py [log2_n] [--generated] [> profiles/rNN_vxx.jsonl]"""
 import json
 import os
 import sys
@@ -28,9 +28,14 @@ def timed(problem, opts, y, reps=5):
 
 
 def main():
-    lg = int(sys.argv[1]) if len(sys.argv) > 1 else 18
+    args = [a for a in sys.argv[1:] if not a.startswith("--")]
+    lg = int(args[0]) if args else 18
     n = 1 << lg
     prob, _ = c_problem("flatquad")
+    generated = "--generated" in sys.argv  # the functor generated from f, l: vxx by forward mode (csrc/pmp_vxx_dual.cuh)
+    if generated:
+        from approximate_optimal_control_b200 import systems
+        prob = systems.to_c_problem(dict(systems.flatquad_problem_params(), codegen=True))
     y64 = flatquad_terminal_vxx(n)
     V, S = _capi.FLAG_VXX, _capi.FLAG_VXX | _capi.FLAG_VXX_SYMMETRIC
     cases = [("tsit5", 0, 0), ("tsit5", 0, V), ("tsit5", 0, S), ("dopri5", 0, S), ("rk4", 0, S), ("tsit5", 1, V), ("tsit5", 1, S)]
@@ -46,7 +51,7 @@ def main():
             opts = _capi.make_opts(**kw)
             med, best, out = timed(prob, opts, y)
             attempts = int(out["n_steps"].sum().item())
-            d = {"config": f"flatquad 2^{lg} {method} {'dense' if dense else 'endpoints'} "
+            d = {"config": f"{'GENERATED ' if generated else ''}flatquad 2^{lg} {method} {'dense' if dense else 'endpoints'} "
                            f"{'vxx-symmetric' if flags == S else ('vxx' if flags == V else 'no vxx')}",
                  "dtype": name, "ms": med, "ms_best": best, "trajectories_per_s": n / med * 1e3,
                  "attempts_per_s": attempts / med * 1e3, "mean_attempts": attempts / n,
