@@ -56,7 +56,7 @@ class NnCostate(C.Structure):
 
 
 EXPORTS = ("pmp_abi_version", "pmp_last_error", "pmp_state_rows", "pmp_state_rows_flags", "pmp_device_count",
-           "pmp_solve_workspace_bytes", "pmp_solve_batch_cuda", "pmp_solve_jvp_cuda", "pmp_solve_launch_count", "pmp_solve_host", "pmp_solve_host_lqr", "pmp_solve_host_plan", "pmp_host_release", "pmp_host_probe_copy", "pmp_select_count_cuda", "pmp_select_write_cuda", "pmp_comm_unique_id", "pmp_comm_init", "pmp_comm_destroy", "pmp_allgather_endpoints",
+           "pmp_solve_workspace_bytes", "pmp_solve_batch_cuda", "pmp_solve_batch_push_cuda", "pmp_solve_jvp_cuda", "pmp_solve_launch_count", "pmp_solve_host", "pmp_solve_host_lqr", "pmp_solve_host_plan", "pmp_host_release", "pmp_host_probe_copy", "pmp_select_count_cuda", "pmp_select_write_cuda", "pmp_comm_unique_id", "pmp_comm_init", "pmp_comm_destroy", "pmp_allgather_endpoints",
            "pmp_rhs_batch_cuda", "pmp_rhs_batch_cuda_flags", "pmp_ustar_batch_cuda", "pmp_ustar_batch_cuda_flags", "pmp_interp_batch_cuda", "pmp_forward_batch_cuda", "pmp_forward_nn_batch_cuda", "pmp_nn_value_batch_cuda",
            "pmp_fma_peak_cuda")
 
@@ -104,6 +104,9 @@ def load(path: str) -> C.CDLL:
     L.pmp_solve_batch_cuda.argtypes = [C.POINTER(Problem), C.POINTER(Opts), C.c_int64, C.c_void_p,
                                        C.c_void_p, C.POINTER(Dense), C.c_void_p, C.c_void_p,
                                        C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]
+    L.pmp_solve_batch_push_cuda.argtypes = [C.POINTER(Problem), C.POINTER(Opts), C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p,
+                                            C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.POINTER(C.c_void_p), C.c_int32,
+                                            C.c_void_p]
     L.pmp_comm_unique_id.argtypes = [C.c_void_p]
     L.pmp_comm_init.argtypes = [C.POINTER(C.c_void_p), C.c_int32, C.c_int32, C.c_void_p]
     L.pmp_comm_destroy.argtypes = [C.c_void_p]

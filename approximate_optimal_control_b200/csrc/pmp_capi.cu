@@ -9,6 +9,21 @@
 #include "pmp_hostq.h"
 
 namespace pmp {
+struct PushArgs {  // (pmp_solve.cuh)
+    void* peer[7];
+    int n_peers;
+};
+#ifndef PMP_PLUGIN
+int solve_flatquad_push(const pmp_problem_t&, const pmp_opts_t&, long long, const void*, void*, int32_t*, int32_t*, int32_t*, void*,
+                        const PushArgs&, cudaStream_t);
+int solve_orbits_push(const pmp_problem_t&, const pmp_opts_t&, long long, const void*, void*, int32_t*, int32_t*, int32_t*, void*,
+                      const PushArgs&, cudaStream_t);
+int solve_lqr_push(const pmp_problem_t&, const pmp_opts_t&, long long, const void*, void*, int32_t*, int32_t*, int32_t*, void*,
+                   const PushArgs&, cudaStream_t);
+#else
+int solve_generated_push(const pmp_problem_t&, const pmp_opts_t&, long long, const void*, void*, int32_t*, int32_t*, int32_t*, void*,
+                         const PushArgs&, cudaStream_t);
+#endif
 #ifndef PMP_PLUGIN
 int solve_flatquad(const pmp_problem_t&, const pmp_opts_t&, long long, const void*, void*, const pmp_dense_t*,
                    int32_t*, int32_t*, int32_t*, void*, cudaStream_t);
@@ -252,6 +267,44 @@ int pmp_solve_batch_cuda(const pmp_problem_t* p, const pmp_opts_t* o, int64_t n,
             break;
         case PMP_SYS_ORBITS: rc = pmp::solve_orbits(*p, *o, n, y_f, y_end, dense, n_accepted, n_steps, result, workspace, st); break;
         case PMP_SYS_LQR_STATEPENALTY: rc = pmp::solve_lqr(*p, *o, n, y_f, y_end, dense, n_accepted, n_steps, result, workspace, st); break;
+    }
+#endif
+    if (rc == -1000) return fail(PMP_ERR_UNSUPPORTED, "no kernel for this (system, dtype, method) combination");
+    if (rc != 0) return cuda_fail(rc);
+    return PMP_OK;
+}
+
+int pmp_solve_batch_push_cuda(const pmp_problem_t* p, const pmp_opts_t* o, int64_t n, const void* y_f, void* y_end,
+                              int32_t* n_accepted, int32_t* n_steps, int32_t* result, void* workspace, int64_t workspace_bytes,
+                              void* const* peer_slots, int32_t n_peers, void* cuda_stream) {
+    if (int e = check_problem(p)) return e;
+    if (int e = check_opts(o)) return e;
+    if (int e = check_pair(p, o)) return e;
+    if (o->save_dense || o->flags != 0 || o->indep != PMP_INDEP_TIME)
+        return fail(PMP_ERR_UNSUPPORTED, "pmp_solve_batch_push_cuda: time-parameterised endpoint solves with the default u* selection");
+    if (n < 0) return fail(PMP_ERR_BAD_ARG, "n < 0");
+    if (n_peers < 0 || n_peers > 7 || (n_peers > 0 && !peer_slots)) return fail(PMP_ERR_BAD_ARG, "n_peers must be 0..7 with peer_slots set");
+    if (n == 0) return PMP_OK;
+    if (!y_f || !y_end) return fail(PMP_ERR_BAD_ARG, "y_f / y_end is NULL");
+    if (!workspace || workspace_bytes < pmp_solve_workspace_bytes(p, o, n))
+        return fail(PMP_ERR_BAD_ARG, "workspace is NULL or smaller than pmp_solve_workspace_bytes()");
+    if (((uintptr_t)workspace & 255u) != 0) return fail(PMP_ERR_BAD_ARG, "workspace must be 256-byte aligned");
+    if (pmp_device_count() <= 0) return fail(PMP_ERR_NO_DEVICE, "no CUDA device: libb200pmp has no CPU fallback");
+    pmp::PushArgs push = {};
+    for (int q = 0; q < n_peers; q++) {
+        if (!peer_slots[q]) return fail(PMP_ERR_BAD_ARG, "peer_slots holds a NULL pointer");
+        push.peer[q] = peer_slots[q];
+    }
+    push.n_peers = n_peers;
+    cudaStream_t st = (cudaStream_t)cuda_stream;
+    int rc = -1000;
+#ifdef PMP_PLUGIN
+    rc = pmp::solve_generated_push(*p, *o, n, y_f, y_end, n_accepted, n_steps, result, workspace, push, st);
+#else
+    switch (p->system_id) {
+        case PMP_SYS_FLATQUAD: rc = pmp::solve_flatquad_push(*p, *o, n, y_f, y_end, n_accepted, n_steps, result, workspace, push, st); break;
+        case PMP_SYS_ORBITS: rc = pmp::solve_orbits_push(*p, *o, n, y_f, y_end, n_accepted, n_steps, result, workspace, push, st); break;
+        case PMP_SYS_LQR_STATEPENALTY: rc = pmp::solve_lqr_push(*p, *o, n, y_f, y_end, n_accepted, n_steps, result, workspace, push, st); break;
     }
 #endif
     if (rc == -1000) return fail(PMP_ERR_UNSUPPORTED, "no kernel for this (system, dtype, method) combination");

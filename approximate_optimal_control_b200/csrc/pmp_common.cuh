@@ -202,6 +202,7 @@ template <class R> struct DensePtrs {
 };
 enum { kDenseTs = 0, kDenseT = 1, kDenseV = 2, kDenseX = 3, kDenseVx = 4, kDenseVxx = 5 };
 
+constexpr int kMaxPeers = 7;  // one node: up to 8 GPUs
 template <class R> struct SolveIO {
     const R* y_f;   // [NS][n]
     const R* k1;    // [ND][n]  field at the terminal state (prep kernel)
@@ -210,6 +211,10 @@ template <class R> struct SolveIO {
     int32_t *n_accepted, *n_steps, *result;
     unsigned long long* counter;  // next unclaimed trajectory index
     long long n;
+    // PUSH instantiation (multi-GPU gather fused into the integrator, pmp_solve_batch_push_cuda): this rank's [NS][n] block in
+    // every peer's gather buffer (peer memory over NVLink)
+    R* peer[kMaxPeers];
+    int n_peers;
 };
 
 // ---- elementary functions the generated functors (codegen.py) may call, one overload set per scalar type (pmp_sens.cuh adds

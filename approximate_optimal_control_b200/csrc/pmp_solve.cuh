@@ -455,7 +455,7 @@ __device__ __forceinline__ R error_sumsq(const R* he, const R* y, const R* y1, c
 // ---- the integrator -----------------------------------------------------------------------------
 // HOSTIO: the persistent launch behind pmp_solve_host (HostQueue, pmp_common.cuh): inputs and endpoints in the state
 // dict's own layout, work released piece by piece by the host->device stream, k1 evaluated in the refill.
-template <class Sys, class R, int METHOD, bool DENSE, bool VALUE, bool ULIT, int MINB, int VXX = 0, bool HOSTIO = false>
+template <class Sys, class R, int METHOD, bool DENSE, bool VALUE, bool ULIT, int MINB, int VXX = 0, bool HOSTIO = false, bool PUSH = false>
 #ifdef PMP_MAXNREG  /* tuning builds: an explicit register cap instead of the residency hint */
 __global__ void __maxnreg__(PMP_MAXNREG)
 #else
@@ -464,6 +464,8 @@ __global__ void __launch_bounds__((BlockOf<R, VXX>::value), MINB)
 solve_kernel(const typename Sys::Consts sc, const SolveOpts<R> o, const SolveIO<R> io, const TabParams<R> tp,
              const VTab<R, VXX> vt, const HostQueue<R> hq) {
     static_assert(!HOSTIO || (!DENSE && !VXX && !VALUE), "the host queue serves time-parameterised endpoint solves");
+    static_assert(!PUSH || (!DENSE && !VXX && !HOSTIO), "the fused gather pushes endpoint records");
+    static_assert(!PUSH || kChunk == 32, "a completed work-queue chunk is pushed as one 32-lane row segment");
     using M = Math<R>;
     using TB = Tab<METHOD>;
     constexpr int NX = Sys::NX, ND = 2 * NX + 1, NS = 2 * NX + 2, S = TB::S;
@@ -597,6 +599,41 @@ solve_kernel(const typename Sys::Consts sc, const SolveOpts<R> o, const SolveIO<
                 }
                 has_work = false;
                 ready_v = false; ready_s = false;  // DENSE: the retirement code writes the last group
+            }
+            if constexpr (PUSH) {
+                // ---- the gather, fused: a work-queue chunk (32 consecutive trajectory indices) is integrated by the lanes of
+                // ONE warp; the lane that retires its last trajectory makes the warp copy the chunk's endpoint rows -- 128
+                // contiguous bytes per row (fp32) -- from this rank's slot into the same slot of every peer's gather buffer with
+                // plain stores to peer memory (NVLink).  The records travel while the rest of the shard is still being
+                // integrated: when the kernel ends, the gather has ended, and no copy engine is involved.
+                __syncwarp();  // the endpoint stores of the lanes that retired just now are ordered before the loads below
+                // Which chunk is complete needs no counter: a chunk is done when the warp has handed out all of its indices
+                // and no lane still carries one of its trajectories (parked lanes count as carrying).
+                const long long cb = idx & ~(long long)(kChunk - 1);  // (meaningful on retiring lanes only)
+                unsigned fm = __ballot_sync(FULL, fin);               // the lanes that retired just now (has_work is clear)
+                while (fm) {
+                    const int src = __ffs(fm) - 1;
+                    const long long b = __shfl_sync(FULL, cb, src);
+                    fm &= ~__ballot_sync(FULL, fin && cb == b);       // this chunk once, whatever the number of its retiring lanes
+                    const bool carried = __any_sync(FULL, has_work && (idx & ~(long long)(kChunk - 1)) == b);
+                    const bool unclaimed = w_next < w_end && (w_next & ~(long long)(kChunk - 1)) == b;
+                    if (carried || unclaimed) continue;
+                    const long long j = b + lane;
+                    if (j < n) {
+                        const R* ye = io.y_end;
+                        R rec[NS];
+#pragma unroll
+                        for (int q = 0; q < NS; q++) rec[q] = __ldcg(ye + q * n + j);  // (L2: written by other lanes of this warp)
+#pragma unroll
+                        for (int pr = 0; pr < kMaxPeers; pr++) {  // (unrolled: a run-time index would move the pointers to local memory)
+                            if (pr < io.n_peers) {
+                                R* dst = io.peer[pr];
+#pragma unroll
+                                for (int q = 0; q < NS; q++) dst[q * n + j] = rec[q];
+                            }
+                        }
+                    }
+                }
             }
             // DENSE: the +inf tails of the retiring trajectories are written after the refill below, so
             // that the refill's loads are in flight while the padding stores are issued
@@ -1071,13 +1108,19 @@ inline size_t workspace_bytes_for(int nd, long long n, size_t real_size) {
     return 256 + (size_t)nd * (size_t)n * real_size;
 }
 
-template <class Sys, class R, int METHOD, bool DENSE, bool VALUE, bool ULIT, int MINB, int VXX = 0>
+// the fused gather of pmp_solve_batch_push_cuda: where this rank's records go on the peers
+struct PushArgs {
+    void* peer[kMaxPeers];
+    int n_peers;
+};
+
+template <class Sys, class R, int METHOD, bool DENSE, bool VALUE, bool ULIT, int MINB, int VXX = 0, bool PUSH = false>
 int launch_one(const pmp_problem_t& p, const pmp_opts_t& o, long long n, const void* y_f, void* y_end,
                const pmp_dense_t* dense, int32_t* n_acc, int32_t* n_steps, int32_t* result,
-               void* workspace, cudaStream_t st) {
+               void* workspace, cudaStream_t st, const PushArgs* push = nullptr) {
     using TB = Tab<METHOD>;
     constexpr int ND = 2 * Sys::NX + 1, BLK = BlockOf<R, VXX>::value, NV = VxxMap<Sys::NX, VXX>::NV;
-    auto kern = solve_kernel<Sys, R, METHOD, DENSE, VALUE, ULIT, MINB, VXX>;
+    auto kern = solve_kernel<Sys, R, METHOD, DENSE, VALUE, ULIT, MINB, VXX, false, PUSH>;
     int dev = 0, sms = 0, occ = 0;
     cudaError_t e = cudaGetDevice(&dev);
     if (e != cudaSuccess) return (int)e;
@@ -1108,6 +1151,13 @@ int launch_one(const pmp_problem_t& p, const pmp_opts_t& o, long long n, const v
     io.y_end = (R*)y_end;
     io.n_accepted = n_acc; io.n_steps = n_steps; io.result = result;
     io.n = n;
+    io.n_peers = 0;
+    for (int q = 0; q < kMaxPeers; q++) io.peer[q] = nullptr;
+    if (PUSH) {
+        if (!push || push->n_peers < 0 || push->n_peers > kMaxPeers) return (int)cudaErrorInvalidValue;
+        io.n_peers = push->n_peers;
+        for (int q = 0; q < push->n_peers; q++) io.peer[q] = (R*)push->peer[q];
+    }
     io.dense = DensePtrs<R>{{nullptr, nullptr, nullptr, nullptr, nullptr, nullptr}};
     if (DENSE && dense)
         io.dense = DensePtrs<R>{{(R*)dense->ts, (R*)dense->t, (R*)dense->v, (R*)dense->x, (R*)dense->vx,
@@ -1166,6 +1216,22 @@ int launch_hostq(const pmp_problem_t& p, const pmp_opts_t& o, long long n, const
     if (o.dtype == PMP_F32) PMP_HQ(float, MINB32);
     if (o.dtype == PMP_F64) PMP_HQ(double, MINB64);
 #undef PMP_HQ
+    return -1000;
+}
+
+// The integrator with the gather fused in (time-parameterised endpoint solves, KKT-form u*): pmp_solve_batch_push_cuda
+template <template <class> class SysT, int MINB32, int MINB64>
+int launch_solve_push(const pmp_problem_t& p, const pmp_opts_t& o, long long n, const void* y_f, void* y_end, int32_t* a, int32_t* s,
+                      int32_t* r, void* ws, const PushArgs& push, cudaStream_t st) {
+#define PMP_PUSH(R, MINB)                                                                                                                        \
+    do {                                                                                                                                         \
+        if (o.method == PMP_METHOD_RK4) return launch_one<SysT<R>, R, PMP_METHOD_RK4, false, false, false, MINB, 0, true>(p, o, n, y_f, y_end, nullptr, a, s, r, ws, st, &push);       \
+        if (o.method == PMP_METHOD_TSIT5) return launch_one<SysT<R>, R, PMP_METHOD_TSIT5, false, false, false, MINB, 0, true>(p, o, n, y_f, y_end, nullptr, a, s, r, ws, st, &push);   \
+        if (o.method == PMP_METHOD_DOPRI5) return launch_one<SysT<R>, R, PMP_METHOD_DOPRI5, false, false, false, MINB, 0, true>(p, o, n, y_f, y_end, nullptr, a, s, r, ws, st, &push); \
+    } while (0)
+    if (o.dtype == PMP_F32) PMP_PUSH(float, MINB32);
+    if (o.dtype == PMP_F64) PMP_PUSH(double, MINB64);
+#undef PMP_PUSH
     return -1000;
 }
 

@@ -17,4 +17,8 @@ int solve_generated(const pmp_problem_t& p, const pmp_opts_t& o, long long n, co
 int solve_generated_hostq(const pmp_problem_t& p, const pmp_opts_t& o, long long n, const HostQueueRaw& q, cudaStream_t st) {
     return launch_hostq<Generated, PMP_GEN_MINB32, PMP_GEN_MINB64>(p, o, n, q, st);
 }
+int solve_generated_push(const pmp_problem_t& p, const pmp_opts_t& o, long long n, const void* y_f, void* y_end, int32_t* a, int32_t* s,
+                   int32_t* r, void* ws, const PushArgs& push, cudaStream_t st) {
+    return launch_solve_push<Generated, PMP_GEN_MINB32, PMP_GEN_MINB64>(p, o, n, y_f, y_end, a, s, r, ws, push, st);
+}
 }  // namespace pmp

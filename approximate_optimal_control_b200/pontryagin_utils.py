@@ -157,10 +157,11 @@ def unpack_state(y: torch.Tensor, nx: int, batched: bool = True) -> dict:
 
 
 # ---- the batched solve on the C ABI -----------------------------------------------------------------
-def solve_batch_soa(problem: _capi.Problem, opts: _capi.Opts, y_f: torch.Tensor, out=None):
+def solve_batch_soa(problem: _capi.Problem, opts: _capi.Opts, y_f: torch.Tensor, out=None, push=None):
     """Thin wrapper of pmp_solve_batch_cuda on struct-of-arrays CUDA tensors.  Asynchronous on the
     current stream.  `out` may carry preallocated outputs (keys y_end, n_accepted, n_steps, result,
-    and ts, x, t, v, vx (, vxx) when opts.save_dense)."""
+    and ts, x, t, v, vx (, vxx) when opts.save_dense).  push = peer_slots: pmp_solve_batch_push_cuda, the integrator with the
+    multi-GPU gather fused in -- tensors (or device pointers) of this rank's [NS, n] block in every peer's gather buffer."""
     L = _capi.lib_of(problem)
     assert y_f.is_cuda and y_f.is_contiguous()
     ns, n = y_f.shape
@@ -186,6 +187,14 @@ def solve_batch_soa(problem: _capi.Problem, opts: _capi.Opts, y_f: torch.Tensor,
     nbytes = _capi.check(L.pmp_solve_workspace_bytes(C.byref(problem), C.byref(opts), n))
     ws = _workspace(dev, nbytes)
     with torch.cuda.device(dev):
+        if push is not None:
+            slots = list(push)
+            ptrs = (C.c_void_p * max(1, len(slots)))(*[int(t.data_ptr() if isinstance(t, torch.Tensor) else t) for t in slots])
+            _capi.check(L.pmp_solve_batch_push_cuda(
+                C.byref(problem), C.byref(opts), n, y_f.data_ptr(), out["y_end"].data_ptr(), out["n_accepted"].data_ptr(),
+                out["n_steps"].data_ptr(), out["result"].data_ptr(), ws.data_ptr(), ws.numel(), ptrs, len(slots),
+                _stream_ptr(dev)), L)
+            return out
         _capi.check(L.pmp_solve_batch_cuda(
             C.byref(problem), C.byref(opts), n, y_f.data_ptr(), out["y_end"].data_ptr(),
             C.byref(dense) if dense is not None else None, out["n_accepted"].data_ptr(),

@@ -11,6 +11,8 @@ from __future__ import annotations
 import torch
 import torch.distributed as dist
 
+_INDEP_TIME = 0  # PMP_INDEP_TIME (include/b200pmp.h)
+
 
 def bind_host_to_gpu(device_index: int) -> dict:
     """Run the calling process on the CPUs next to its GPU (one process per GPU: call it FIRST, before anything allocates
@@ -111,12 +113,18 @@ class PipelinedGather:
         two sets of gather buffers alternate, so the result of step s stays valid until run() of step s+2 is called
         (readers enqueued on the current stream before that call are safe, see run()).
 
-    transport="p2p" (default when torch symmetric memory is available): every rank pushes its piece
+    transport="p2p": every rank pushes its piece
         straight into the peers' gather buffers with peer-to-peer cudaMemcpyAsync over NVLink
         (copy engines: no SM is taken from the integrator, a persistent kernel that owns all of them),
         followed by one symmetric-memory barrier per step.
     transport="nccl": all_gather_into_tensor on a side stream (NCCL's kernels need SMs, so they only
         partly overlap with the integrator).
+    transport="fused" (what "auto" picks when torch symmetric memory is available and the shard is one piece): the gather is
+        part of the integrator (pmp_solve_batch_push_cuda): the warp that finishes a work-queue
+        chunk of 32 trajectories stores its endpoint rows straight into every peer's gather buffer (peer memory over NVLink)
+        while the rest of the shard is integrated.  No copy engine, no transfer left when the kernel ends; THREE buffer sets,
+        so that the "every rank has consumed this set" barrier of a set completes a whole step before the kernel that
+        overwrites it is launched.
 
         pg = PipelinedGather(problem, opts, n_local, dtype, device)
         pieces = pg.run(y_local)        # list of [world, NS, n_piece] tensors, rank-major, on every rank
@@ -136,7 +144,15 @@ class PipelinedGather:
         # staging of the pieces' inputs (one piece: the caller's shard is integrated in place, nothing is staged)
         self.inputs = [torch.empty((self.ns, b - a) if len(self.slices) > 1 else (0,), dtype=dtype, device=device)
                        for a, b in self.slices]
-        self.nsets = 2 if self.world > 1 else 1
+        # "auto": the fused gather where it applies (one piece per step, time-parameterised endpoint solve with the default u*
+        # selection), else peer-to-peer copies; NCCL where symmetric memory is not available
+        fusable = (self.world > 1 and len(self.slices) == 1 and not opts.save_dense and opts.flags == 0
+                   and opts.indep == _INDEP_TIME)
+        if transport == "fused" and not fusable:
+            transport = "auto" if self.world == 1 else "p2p"
+        elif transport == "auto" and fusable:
+            transport = "fused?"  # fused if symmetric memory comes up, NCCL otherwise
+        self.nsets = (3 if transport.startswith("fused") else 2) if self.world > 1 else 1
         self.outs = [[{} for _ in self.slices] for _ in range(self.nsets)]
         self.side = torch.cuda.Stream(device=device) if self.world > 1 else None
         # a second copy stream: one stream = one copy engine pushed 7 x 59 MB in ~1.2 ms at N = 8, a little longer than the
@@ -147,15 +163,20 @@ class PipelinedGather:
         self.step = 0
         self._copied = [None] * self.nsets   # event: this set's local slot has been read by the pushes
         self._pending = False
-        if self.world > 1 and transport in ("auto", "p2p"):
+        if self.world > 1 and transport in ("auto", "p2p", "fused", "fused?"):
             try:
                 self._init_p2p(dtype, device)
-                self.transport = "p2p"
+                self.transport = "fused" if transport.startswith("fused") else "p2p"
             except Exception as e:  # symmetric memory unavailable: NCCL does the same job
-                if transport == "p2p":
+                if transport in ("p2p", "fused"):
                     raise
                 self.transport = "nccl"
+                self.nsets = 2
+                self.outs = [[{} for _ in self.slices] for _ in range(self.nsets)]
+                self._copied = [None] * self.nsets
                 self.p2p_error = repr(e)
+        if self.transport == "fused":
+            self._free = [None] * self.nsets  # event: every rank has consumed this set (it may be overwritten)
         if self.transport == "nccl":
             # per-piece gather buffers, rank-major: [world * NS, n_piece]
             self.gathered = [[torch.empty((self.world * self.ns, b - a), dtype=dtype, device=device) for a, b in self.slices]
@@ -196,6 +217,8 @@ class PipelinedGather:
         peer may push step s+2 into the set ("every rank has consumed set s % 2"); that barrier runs while the
         shard is being integrated, so it costs nothing.  A second barrier after the pushes says "every rank's
         step-s records have landed"."""
+        if self.transport == "fused":
+            return self._run_fused(y_local, wait)
         main = torch.cuda.current_stream()
         s = self.step % self.nsets
         self.step += 1
@@ -248,6 +271,42 @@ class PipelinedGather:
             self._copied[s] = done
             if self.transport == "p2p":
                 self.hdl.barrier(channel=0)  # every rank's pushes of this step have completed
+        self._pending = True
+        if wait:
+            self.wait()
+        return [g.view(self.world, self.ns, -1) for g in self.gathered[s]]
+
+    def _run_fused(self, y_local: torch.Tensor, wait: bool):
+        """Step t uses set t % 3.  The result of step t stays valid until run() of step t+2 is CALLED (as with the other
+        transports).  run(t) records that point of the current stream; behind it the side stream passes the "consumed" barrier
+        and records free[(t+1) % 3]: set (t-2) % 3 == (t+1) % 3 may be overwritten -- by this rank's kernel of step t+1 and, since
+        all ranks pass the same barrier, by the peers' kernels of step t+1.  The kernel of step t waits for free[t % 3], which
+        was recorded during step t-1: never on the critical path.  A second barrier behind the kernel says "every rank's
+        records of step t have landed everywhere"."""
+        main = torch.cuda.current_stream()
+        t = self.step
+        s = t % self.nsets
+        self.step += 1
+        out = self.outs[s][0]
+        rows = slice(self.rank * self.ns, (self.rank + 1) * self.ns)
+        consumed = torch.cuda.Event()
+        consumed.record(main)
+        with torch.cuda.stream(self.side):
+            self.side.wait_event(consumed)
+            self.hdl.barrier(channel=1)
+            free = torch.cuda.Event()
+            free.record(self.side)
+            self._free[(t + 1) % self.nsets] = free
+        if self._free[s] is not None and t > 0:
+            main.wait_event(self._free[s])
+        y_in = y_local if y_local.is_contiguous() else y_local.contiguous()
+        slots = [self.peer[s][0][(self.rank + d) % self.world][rows] for d in range(1, self.world)]
+        self._pu.solve_batch_soa(self.problem, self.opts, y_in, out, push=slots)
+        ev = torch.cuda.Event()
+        ev.record(main)
+        with torch.cuda.stream(self.side):
+            self.side.wait_event(ev)
+            self.hdl.barrier(channel=0)
         self._pending = True
         if wait:
             self.wait()

@@ -73,7 +73,7 @@ def parse_args():
                     help="N>1: pieces of the shard; the all-gather of piece k overlaps the solve of piece k+1")
     ap.add_argument("--no-step-overlap", action="store_true",
                     help="N>1: wait for the endpoint gather of step s before integrating step s+1")
-    ap.add_argument("--gather", default="auto", choices=["auto", "p2p", "nccl"],
+    ap.add_argument("--gather", default="auto", choices=["auto", "p2p", "nccl", "fused"],
                     help="N>1 endpoint gather transport: peer-to-peer copies over NVLink (symmetric memory) or NCCL")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-bind-host", action="store_true",
@@ -364,6 +364,10 @@ def main():
                   "bytes_per_rank_per_step": int(y_dev.numel() * y_dev.element_size()),
                   "ms_with_gather": main_run["ms_per_step"], "ms_without_gather": solo["ms_per_step"],
                   "overlap": ("none across steps" if args.no_step_overlap else
+                              "fused into the integrator (pmp_solve_batch_push_cuda): the warp that finishes a work-queue chunk of "
+                              "32 trajectories stores its endpoint rows into every peer's gather buffer over NVLink while the rest "
+                              "of the shard is integrated; three buffer sets; all records have landed inside the timed region"
+                              if pg.transport == "fused" else
                               "gather of step s (copy engines, peer-to-peer over NVLink; NCCL all_gather_into_tensor with "
                               "--gather nccl) overlaps the integration of step s+1 (double-buffered); all gathers complete "
                               "inside the timed region")}

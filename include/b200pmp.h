@@ -251,6 +251,19 @@ int pmp_comm_destroy(void *comm);
 int pmp_allgather_endpoints(void *comm, const void *local, void *global, int64_t n_local, int32_t rows, int32_t dtype,
                             void *cuda_stream);
 
+/* The same gather FUSED into the integrator (north star: "shard by terminal-sample index, with only an all-gather of endpoint
+ * (x, lambda, v) datasets"; no counterpart in the single-process reference).  pmp_solve_batch_cuda for time-parameterised endpoint
+ * solves (flags 0, save_dense 0) that, besides writing y_end [NS][n] locally, stores every finished work-queue chunk (32 consecutive
+ * trajectories = 128 contiguous bytes per fp32 row) into peer_slots[0 .. n_peers): device pointers, valid on THIS device (peer
+ * access / symmetric memory over NVLink), to this rank's [NS][n] block inside each peer's gather buffer.  The records travel while
+ * the rest of the shard is integrated: when the kernel has finished, so has this rank's part of the gather -- no copy engine, no
+ * NCCL kernel competing for SMs, no transfer left over after the last step.  The caller still tells the peers (a barrier / stream
+ * event exchange after the launch) and must not let a peer reuse the buffer before every rank has read it.
+ * Everything else as pmp_solve_batch_cuda. */
+int pmp_solve_batch_push_cuda(const pmp_problem_t *problem, const pmp_opts_t *opts, int64_t n, const void *y_f, void *y_end,
+                              int32_t *n_accepted, int32_t *n_steps, int32_t *result, void *workspace,
+                              int64_t workspace_bytes, void *const *peer_slots, int32_t n_peers, void *cuda_stream);
+
 /* Forward-mode sensitivity of a solve: endpoint AND its directional derivative along dy_f, d y_end / d y_f . dy_f, for n
  * trajectories (y_f, dy_f, y_end, dy_end [NS][n]).  Replaces jax.jacobian / jvp through diffrax.diffeqsolve
  * (experiment_orbits.py:186-197 differentiates the value-parameterised solve, indep = PMP_INDEP_VALUE, with respect to the

@@ -1,6 +1,6 @@
 """N>1 path on real GPUs (skipped with fewer than 2 devices): shard by terminal-sample index, integrate
-locally, gather the endpoints on every rank -- peer-to-peer (symmetric memory + copy engines) and
-NCCL transports must give the same, correct, global endpoint array."""
+locally, gather the endpoints on every rank -- peer-to-peer (symmetric memory + copy engines), NCCL and the gather fused
+into the integrator (pmp_solve_batch_push_cuda: stores to peer memory) must give the same, correct, global endpoint array."""
 import os
 
 import numpy as np
@@ -26,9 +26,10 @@ def _worker(rank, world, port, n_local, q):
     y_loc = sharding.take_shard(y_all, n, rank, world)
     ref = pu.solve_batch_soa(prob, opts, y_all.contiguous())["y_end"]  # every rank solves everything once
     res = {}
-    for transport, chunks in (("nccl", 1), ("p2p", 1), ("p2p", 3)):
+    for transport, chunks in (("nccl", 1), ("p2p", 1), ("p2p", 3), ("fused", 1)):
         pg = sharding.PipelinedGather(prob, opts, n_local, torch.float64, dev, chunks=chunks, transport=transport)
-        for _ in range(2):  # twice: buffers are reused across steps
+        assert pg.transport == transport
+        for _ in range(4):  # several times: buffers are reused across steps (two sets; three with the fused gather)
             pieces = pg.run(y_loc)
         torch.cuda.synchronize()
         full = torch.cat([p for p in pieces], dim=2)              # [world, NS, n_local]
@@ -40,7 +41,7 @@ def _worker(rank, world, port, n_local, q):
     ys = [torch.as_tensor(flatquad_terminal(n, seed=11 + k), device=dev) for k in range(3)]
     refs = [pu.solve_batch_soa(prob, opts, y.contiguous())["y_end"].clone() for y in ys]
     locs = [sharding.take_shard(y, n, rank, world) for y in ys]
-    for transport in ("p2p", "nccl"):
+    for transport in ("p2p", "nccl", "fused"):
         pg = sharding.PipelinedGather(prob, opts, n_local, torch.float64, dev, chunks=1, transport=transport)
         pa = pg.run(locs[0], wait=False)
         pb = pg.run(locs[1], wait=False)
@@ -51,8 +52,16 @@ def _worker(rank, world, port, n_local, q):
         pc = pg.run(locs[2], wait=False)       # step 2 reuses the buffer set of step 0
         pg.wait()
         got_b, got_c = torch.cat(pb, dim=2).clone(), torch.cat(pc, dim=2).clone()
+        if rank == world - 1:
+            torch.cuda._sleep(int(1.0e9))      # now the last rank lags: its peers' step 3 must not overwrite what it still reads
+        got_c2 = torch.cat(pc, dim=2).clone()
+        pd = pg.run(locs[0], wait=False)       # step 3: the fused gather's third set wraps around to the set of step 0
+        pe = pg.run(locs[1], wait=False)       # step 4
+        pg.wait()
+        got_d, got_e = torch.cat(pd, dim=2).clone(), torch.cat(pe, dim=2).clone()
         torch.cuda.synchronize()
-        for tag, g, r in (("a", got_a, refs[0]), ("b", got_b, refs[1]), ("c", got_c, refs[2])):
+        for tag, g, r in (("a", got_a, refs[0]), ("b", got_b, refs[1]), ("c", got_c, refs[2]), ("c2", got_c2, refs[2]),
+                          ("d", got_d, refs[0]), ("e", got_e, refs[1])):
             res[(transport, "nowait", tag)] = bool(torch.equal(g.permute(1, 0, 2).reshape(14, n), r))
     # the C-ABI gather (pmp_comm_* / pmp_allgather_endpoints: NCCL without torch in the data path); the 128-byte id travels
     # through torch.distributed here only because the test already has it
