@@ -106,7 +106,7 @@ def load(path: str) -> C.CDLL:
                                        C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]
     L.pmp_solve_batch_push_cuda.argtypes = [C.POINTER(Problem), C.POINTER(Opts), C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p,
                                             C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.POINTER(C.c_void_p), C.c_int32,
-                                            C.c_void_p]
+                                            C.c_void_p, C.c_void_p]
     L.pmp_comm_unique_id.argtypes = [C.c_void_p]
     L.pmp_comm_init.argtypes = [C.POINTER(C.c_void_p), C.c_int32, C.c_int32, C.c_void_p]
     L.pmp_comm_destroy.argtypes = [C.c_void_p]

@@ -12,6 +12,7 @@ namespace pmp {
 struct PushArgs {  // (pmp_solve.cuh)
     void* peer[7];
     int n_peers;
+    void* mc;
 };
 #ifndef PMP_PLUGIN
 int solve_flatquad_push(const pmp_problem_t&, const pmp_opts_t&, long long, const void*, void*, int32_t*, int32_t*, int32_t*, void*,
@@ -276,7 +277,7 @@ int pmp_solve_batch_cuda(const pmp_problem_t* p, const pmp_opts_t* o, int64_t n,
 
 int pmp_solve_batch_push_cuda(const pmp_problem_t* p, const pmp_opts_t* o, int64_t n, const void* y_f, void* y_end,
                               int32_t* n_accepted, int32_t* n_steps, int32_t* result, void* workspace, int64_t workspace_bytes,
-                              void* const* peer_slots, int32_t n_peers, void* cuda_stream) {
+                              void* const* peer_slots, int32_t n_peers, void* multicast_slot, void* cuda_stream) {
     if (int e = check_problem(p)) return e;
     if (int e = check_opts(o)) return e;
     if (int e = check_pair(p, o)) return e;
@@ -296,6 +297,7 @@ int pmp_solve_batch_push_cuda(const pmp_problem_t* p, const pmp_opts_t* o, int64
         push.peer[q] = peer_slots[q];
     }
     push.n_peers = n_peers;
+    push.mc = multicast_slot;
     cudaStream_t st = (cudaStream_t)cuda_stream;
     int rc = -1000;
 #ifdef PMP_PLUGIN

@@ -203,6 +203,9 @@ template <class R> struct DensePtrs {
 enum { kDenseTs = 0, kDenseT = 1, kDenseV = 2, kDenseX = 3, kDenseVx = 4, kDenseVxx = 5 };
 
 constexpr int kMaxPeers = 7;  // one node: up to 8 GPUs
+// store through a multicast (multimem) address: the NVSwitch replicates the write into every GPU of the multicast group
+__device__ __forceinline__ void mc_store(float* p, float v) { asm volatile("multimem.st.relaxed.sys.global.f32 [%0], %1;" ::"l"(p), "f"(v) : "memory"); }
+__device__ __forceinline__ void mc_store(double* p, double v) { asm volatile("multimem.st.relaxed.sys.global.f64 [%0], %1;" ::"l"(p), "d"(v) : "memory"); }
 template <class R> struct SolveIO {
     const R* y_f;   // [NS][n]
     const R* k1;    // [ND][n]  field at the terminal state (prep kernel)
@@ -215,6 +218,7 @@ template <class R> struct SolveIO {
     // every peer's gather buffer (peer memory over NVLink)
     R* peer[kMaxPeers];
     int n_peers;
+    R* mc;  // non-NULL: the same block through the NVSwitch MULTICAST mapping of the gather buffer (one multimem.st reaches every GPU)
 };
 
 // ---- elementary functions the generated functors (codegen.py) may call, one overload set per scalar type (pmp_sens.cuh adds

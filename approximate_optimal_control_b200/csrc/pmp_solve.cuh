@@ -624,6 +624,10 @@ solve_kernel(const typename Sys::Consts sc, const SolveOpts<R> o, const SolveIO<
                         R rec[NS];
 #pragma unroll
                         for (int q = 0; q < NS; q++) rec[q] = __ldcg(ye + q * n + j);  // (L2: written by other lanes of this warp)
+                        if (io.mc) {  // one store per row: the switch replicates it into every GPU's buffer (this one included)
+#pragma unroll
+                            for (int q = 0; q < NS; q++) mc_store(io.mc + q * n + j, rec[q]);
+                        } else
 #pragma unroll
                         for (int pr = 0; pr < kMaxPeers; pr++) {  // (unrolled: a run-time index would move the pointers to local memory)
                             if (pr < io.n_peers) {
@@ -1112,6 +1116,7 @@ inline size_t workspace_bytes_for(int nd, long long n, size_t real_size) {
 struct PushArgs {
     void* peer[kMaxPeers];
     int n_peers;
+    void* mc;  // multicast address of this rank's block, or NULL
 };
 
 template <class Sys, class R, int METHOD, bool DENSE, bool VALUE, bool ULIT, int MINB, int VXX = 0, bool PUSH = false>
@@ -1152,11 +1157,13 @@ int launch_one(const pmp_problem_t& p, const pmp_opts_t& o, long long n, const v
     io.n_accepted = n_acc; io.n_steps = n_steps; io.result = result;
     io.n = n;
     io.n_peers = 0;
+    io.mc = nullptr;
     for (int q = 0; q < kMaxPeers; q++) io.peer[q] = nullptr;
     if (PUSH) {
         if (!push || push->n_peers < 0 || push->n_peers > kMaxPeers) return (int)cudaErrorInvalidValue;
         io.n_peers = push->n_peers;
         for (int q = 0; q < push->n_peers; q++) io.peer[q] = (R*)push->peer[q];
+        io.mc = (R*)push->mc;
     }
     io.dense = DensePtrs<R>{{nullptr, nullptr, nullptr, nullptr, nullptr, nullptr}};
     if (DENSE && dense)

@@ -157,11 +157,12 @@ def unpack_state(y: torch.Tensor, nx: int, batched: bool = True) -> dict:
 
 
 # ---- the batched solve on the C ABI -----------------------------------------------------------------
-def solve_batch_soa(problem: _capi.Problem, opts: _capi.Opts, y_f: torch.Tensor, out=None, push=None):
+def solve_batch_soa(problem: _capi.Problem, opts: _capi.Opts, y_f: torch.Tensor, out=None, push=None, push_mc=None):
     """Thin wrapper of pmp_solve_batch_cuda on struct-of-arrays CUDA tensors.  Asynchronous on the
     current stream.  `out` may carry preallocated outputs (keys y_end, n_accepted, n_steps, result,
     and ts, x, t, v, vx (, vxx) when opts.save_dense).  push = peer_slots: pmp_solve_batch_push_cuda, the integrator with the
-    multi-GPU gather fused in -- tensors (or device pointers) of this rank's [NS, n] block in every peer's gather buffer."""
+    multi-GPU gather fused in -- tensors (or device pointers) of this rank's [NS, n] block in every peer's gather buffer;
+    push_mc: the address of that block through the buffer's NVSwitch multicast mapping (one store then reaches every GPU)."""
     L = _capi.lib_of(problem)
     assert y_f.is_cuda and y_f.is_contiguous()
     ns, n = y_f.shape
@@ -193,7 +194,7 @@ def solve_batch_soa(problem: _capi.Problem, opts: _capi.Opts, y_f: torch.Tensor,
             _capi.check(L.pmp_solve_batch_push_cuda(
                 C.byref(problem), C.byref(opts), n, y_f.data_ptr(), out["y_end"].data_ptr(), out["n_accepted"].data_ptr(),
                 out["n_steps"].data_ptr(), out["result"].data_ptr(), ws.data_ptr(), ws.numel(), ptrs, len(slots),
-                _stream_ptr(dev)), L)
+                C.c_void_p(int(push_mc)) if push_mc else None, _stream_ptr(dev)), L)
             return out
         _capi.check(L.pmp_solve_batch_cuda(
             C.byref(problem), C.byref(opts), n, y_f.data_ptr(), out["y_end"].data_ptr(),

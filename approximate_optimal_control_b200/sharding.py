@@ -192,6 +192,19 @@ class PipelinedGather:
         # carve the symmetric allocation into per-set, per-piece [world*NS, n_piece] buffers; the same
         # offsets are valid in every peer's copy
         self.gathered, self.peer = [], []
+        # NVSwitch multicast mapping of the same allocation (NVLS), if the platform has one: the fused gather then needs one
+        # store per row instead of one per row and peer.  B200PMP_GATHER_MULTICAST=0 keeps the per-peer stores.
+        import os
+        mc = 0
+        if os.environ.get("B200PMP_GATHER_MULTICAST", "1") != "0":
+            try:
+                mc = int(self.hdl.multicast_ptr) if getattr(self.hdl, "has_multicast_support", False) else 0
+                if mc:  # (the multicast mapping starts where the symmetric buffer does; `flat` may sit at an offset in it)
+                    mc += flat.data_ptr() - int(self.hdl.buffer_ptrs[self.rank])
+            except Exception:  # noqa: BLE001
+                mc = 0
+        self.multicast = bool(mc)
+        self.mc_slot = []
         off = 0
         for s in range(self.nsets):
             gs, ps = [], []
@@ -202,6 +215,9 @@ class PipelinedGather:
                 off += m
             self.gathered.append(gs)
             self.peer.append(ps)
+            # this rank's block inside piece 0 of the set, through the multicast mapping
+            self.mc_slot.append(mc + (off - sum(self.world * self.ns * (b - a) for a, b in self.slices)
+                                      + self.rank * self.ns * (self.slices[0][1] - self.slices[0][0])) * flat.element_size() if mc else 0)
             # the integrator writes this rank's endpoints directly into its own slot of the gather buffer
             for o, g in zip(self.outs[s], gs):
                 o["y_end"] = g[self.rank * self.ns:(self.rank + 1) * self.ns]
@@ -301,7 +317,7 @@ class PipelinedGather:
             main.wait_event(self._free[s])
         y_in = y_local if y_local.is_contiguous() else y_local.contiguous()
         slots = [self.peer[s][0][(self.rank + d) % self.world][rows] for d in range(1, self.world)]
-        self._pu.solve_batch_soa(self.problem, self.opts, y_in, out, push=slots)
+        self._pu.solve_batch_soa(self.problem, self.opts, y_in, out, push=slots, push_mc=self.mc_slot[s] or None)
         ev = torch.cuda.Event()
         ev.record(main)
         with torch.cuda.stream(self.side):

@@ -360,7 +360,7 @@ def main():
     gather = None
     if world > 1:
         solo = timed_steps(y_dev, n, opts, False, args.steps, 2)  # the same K steps without the collective
-        gather = {"chunks": len(pg.slices), "transport": pg.transport,
+        gather = {"chunks": len(pg.slices), "transport": pg.transport, "nvswitch_multicast": bool(getattr(pg, "multicast", False)),
                   "bytes_per_rank_per_step": int(y_dev.numel() * y_dev.element_size()),
                   "ms_with_gather": main_run["ms_per_step"], "ms_without_gather": solo["ms_per_step"],
                   "overlap": ("none across steps" if args.no_step_overlap else

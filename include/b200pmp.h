@@ -259,10 +259,13 @@ int pmp_allgather_endpoints(void *comm, const void *local, void *global, int64_t
  * the rest of the shard is integrated: when the kernel has finished, so has this rank's part of the gather -- no copy engine, no
  * NCCL kernel competing for SMs, no transfer left over after the last step.  The caller still tells the peers (a barrier / stream
  * event exchange after the launch) and must not let a peer reuse the buffer before every rank has read it.
+ *   multicast_slot  NULL, or the address of the same block through an NVSwitch multicast (multimem) mapping of the gather
+ *                   buffer: one multimem.st per row then reaches every GPU of the group and peer_slots is not used
  * Everything else as pmp_solve_batch_cuda. */
 int pmp_solve_batch_push_cuda(const pmp_problem_t *problem, const pmp_opts_t *opts, int64_t n, const void *y_f, void *y_end,
                               int32_t *n_accepted, int32_t *n_steps, int32_t *result, void *workspace,
-                              int64_t workspace_bytes, void *const *peer_slots, int32_t n_peers, void *cuda_stream);
+                              int64_t workspace_bytes, void *const *peer_slots, int32_t n_peers, void *multicast_slot,
+                              void *cuda_stream);
 
 /* Forward-mode sensitivity of a solve: endpoint AND its directional derivative along dy_f, d y_end / d y_f . dy_f, for n
  * trajectories (y_f, dy_f, y_end, dy_end [NS][n]).  Replaces jax.jacobian / jvp through diffrax.diffeqsolve
