@@ -36,6 +36,11 @@ JSON keys beyond the base contract:
                 in pinned host memory out, host->device and device->host copies inside the timed region.
   gather_check  N > 1: rank 0 re-solves every rank's shard in one launch and compares it BIT FOR BIT with the slice
                 that rank pushed into rank 0's gathered dataset.
+  gather        N > 1: transport ("fused": the gather is part of the integrator, pmp_solve_batch_push_cuda -- finished chunks are
+                stored into the peers' buffers over NVLink, through the NVSwitch multicast mapping when "nvswitch_multicast" is
+                true; --gather p2p / nccl select the copy-engine and NCCL transports), ms per step with and without it.
+  host_binding  what sharding.bind_host_to_gpu did for this rank (process onto the CPUs / memory next to its GPU; a no-op on
+                boxes that expose no NUMA topology).
 """
 from __future__ import annotations
 
@@ -74,7 +79,8 @@ def parse_args():
     ap.add_argument("--no-step-overlap", action="store_true",
                     help="N>1: wait for the endpoint gather of step s before integrating step s+1")
     ap.add_argument("--gather", default="auto", choices=["auto", "p2p", "nccl", "fused"],
-                    help="N>1 endpoint gather transport: peer-to-peer copies over NVLink (symmetric memory) or NCCL")
+                    help="N>1 endpoint gather transport: auto = fused into the integrator (stores to peer memory from the retiring "
+                         "warps) where symmetric memory is available; p2p = copy-engine pushes over NVLink; nccl")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-bind-host", action="store_true",
                     help="leave the process where the launcher put it (default: onto the CPUs / memory of the GPU's NUMA node)")
