@@ -114,3 +114,34 @@ def test_generated_header_and_plugin_library():
     if not torch.cuda.is_available():
         y = np.zeros((6, 8))
         assert L.pmp_rhs_batch_cuda(C.byref(prob), _capi.F64, 8, y.ctypes.data, y.ctypes.data, None) == -4
+
+
+def test_feedback_law_is_traced_into_the_functor():
+    """eval_utils.closed_loop_eval_general (eval_utils.py:48-99): a caller-supplied u*(x) becomes the generated functor's u*
+    (no costate, no clipping, no quadratic-H requirement); its constants are part of the plug-in's content hash."""
+    pp = dict(CS.pendulum_problem_params(), ustar_fct=CS.pendulum_feedback_law())
+    d = codegen.derive(pp)
+    assert d.policy is not None and len(d.policy) == 1 and d.num is None and not d.Hu
+    hdr = codegen.emit_header(d, "pendulum_with_law")
+    assert "the caller's feedback law" in hdr and "u_star_new" not in hdr and "ustar2d_box" not in hdr
+    assert "nan_min<R>(R(2.0)" in hdr and "gsin(x[0])" in hdr  # clip(-(3 x0 + 1.5 x1) + 0.2 sin x0, -2, 2)
+    f, l, u = CS.numpy_closed_loop(CS.pendulum_problem_params(), CS.pendulum_feedback_law())
+    assert u(np.array([2.0, 0.0])) == -2.0 and abs(u(np.array([0.1, 0.0])) - (-0.3 + 0.2 * np.sin(0.1))) < 1e-15
+    other = codegen.emit_header(codegen.derive(dict(CS.pendulum_problem_params(), ustar_fct=CS.lqr_feedback_law(np.eye(2)))), "pendulum_with_law")
+    assert other != hdr
+    with pytest.raises(ValueError, match="components"):
+        codegen.derive(dict(CS.pendulum_problem_params(), ustar_fct=lambda x: x))  # returns nx = 2 values for nu = 1
+
+
+def test_bind_host_to_gpu_never_fails():
+    """sharding.bind_host_to_gpu reports what it did and leaves the process alone when the platform has nothing to say
+    (here: no GPU at all)."""
+    import os
+    from approximate_optimal_control_b200 import sharding
+    before = os.sched_getaffinity(0)
+    info = sharding.bind_host_to_gpu(0)
+    assert isinstance(info, dict) and "bound" in info
+    import torch
+    if not torch.cuda.is_available():
+        assert info["bound"] is False and "why" in info and os.sched_getaffinity(0) == before
+    os.sched_setaffinity(0, before)
