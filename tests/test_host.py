@@ -211,3 +211,35 @@ def test_dtype_inference_follows_jax_x64_switch():
         assert pu._infer_dtype({}, x64) == torch.float64 and pu._infer_dtype({}, x32) == torch.float32
     finally:
         pu.enable_x64(False)
+
+
+def test_pinned_outputs_layout_serves_the_pitched_copies(monkeypatch):
+    """pontryagin_utils._pinned_outputs carves the endpoint leaves of a host solve out of ONE allocation so that csrc/pmp_host.cu
+    can ship a piece as two pitched copies: x -> vx one pitch apart, and (fp32) t -> v -> n_accepted equally spaced, every leaf
+    256-byte aligned, no leaf overlapping the next.  (Pinned memory needs a CUDA context: the allocator is stubbed here.)"""
+    import torch
+    from approximate_optimal_control_b200 import pontryagin_utils as pu
+    real_empty = torch.empty
+
+    def fake_empty(*a, **k):
+        k.pop("pin_memory", None)
+        return real_empty(*a, **k)
+    monkeypatch.setattr(torch, "empty", fake_empty)
+    for n, nx, dt in ((1000, 6, torch.float32), (100003, 6, torch.float32), (40001, 2, torch.float64), (1, 4, torch.float32)):
+        ho = pu._pinned_outputs(n, nx, dt)
+        es = 4 if dt == torch.float32 else 8
+        assert ho["x"].shape == (n, nx) and ho["vx"].shape == (n, nx) and ho["t"].shape == (n,) and ho["result"].dtype == torch.int32
+        base = ho["x"].data_ptr()
+        order = ["x", "vx", "t", "v", "n_accepted", "n_steps", "result"]
+        for a, b in zip(order, order[1:]):
+            assert (ho[b].data_ptr() - base) % 256 == 0
+            assert ho[b].data_ptr() >= ho[a].data_ptr() + ho[a].numel() * ho[a].element_size(), (a, b)
+        assert ho["vx"].data_ptr() - ho["x"].data_ptr() >= n * nx * es
+        pitch_tv = ho["v"].data_ptr() - ho["t"].data_ptr()
+        assert pitch_tv >= n * es
+        if es == 4:  # the packed counters travel as a third row into the n_accepted leaf
+            assert ho["n_accepted"].data_ptr() - ho["v"].data_ptr() == pitch_tv
+        for k in order:  # views of one block: writing one leaf leaves the others alone
+            ho[k].zero_()
+        ho["t"].fill_(1.0)
+        assert float(ho["v"].sum()) == 0.0 and float(ho["vx"].abs().sum()) == 0.0 and int(ho["n_accepted"].sum()) == 0
